@@ -1,0 +1,362 @@
+#!/usr/bin/env python
+"""bench.py - routed messages/s (send -> receive) at 1M agents, 64-way group fan-out.
+
+Contract (driver):  python bench.py --gpus N --steps K --warmup W   (N>1 under torchrun)
+prints ONE JSON line on rank 0.  `--impl reference` times the CPU restatement of the
+reference path (oracle/cpu_ref.c, all host threads) on the same workload.
+
+Workload = BASELINE config 2 (SURVEY.md section 8d "c2"): A = 1,000,000 agents, 15,625 disjoint groups
+of 64 (perm = default_rng(2).permutation(A)), one step = 65,536 group sends (group ~ U, sender
+~ U resampled until not a member, prio ~ U{0..3}, 256-byte [A-Za-z0-9] payloads from
+default_rng(3)) = 4,194,304 routed messages, followed by a full drain of every agent
+(receive_batch over all agents, max_messages = 100).
+
+  value   device-resident: the step's sends are already staged in HBM (sdb_stage_batch); the
+          timed region is submit (fan-out + commit kernels) + receive (7 kernels), timed with
+          CUDA events on the launching stream, barrier + synchronize on both sides.
+  e2e     the same step through the public API with HOST buffers: pinned payload/index
+          arrays in, H2D inside the call, receive results copied D2H into pinned buffers.
+  roofline  fan-out kernel: 280.25 algorithmic bytes per routed message x messages
+          per launch / mean launch duration from CUDA events inside the library
+          (sdb_profile), against MEASURED_PEAKS.json's copy bandwidth.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+from pathlib import Path
+
+import numpy as np
+
+ROOT = Path(__file__).resolve().parent
+if str(ROOT) not in sys.path:
+    sys.path.insert(0, str(ROOT))
+
+A_AGENTS = 1_000_000
+FANOUT = 64
+N_GROUPS = A_AGENTS // FANOUT          # 15,625
+SENDS_PER_STEP = 65_536
+PAYLOAD = 256
+ALG_BYTES_FANOUT = 256 + 16 + 4 + (256 + 16) / 64.0       # 280.25 B per routed message
+ALG_BYTES_GATHER = 2 * (256 + 16)                          # gather + emit per delivered message
+ALNUM = np.frombuffer(b"ABCDEFGHIJKLMNOPQRSTUVWXYZabcdefghijklmnopqrstuvwxyz0123456789", np.uint8)
+
+
+# ------------------------------------------------------------------------------------ workload
+class Workload:
+    def __init__(self, n_agents=A_AGENTS, fanout=FANOUT, sends=SENDS_PER_STEP, payload=PAYLOAD):
+        self.A, self.F, self.S, self.L = n_agents, fanout, sends, payload
+        self.G = n_agents // fanout
+        self.perm = np.random.default_rng(2).permutation(n_agents).astype(np.uint32)
+        self.group_of = np.empty(n_agents, np.uint32)
+        self.group_of[self.perm[: self.G * fanout]] = np.repeat(np.arange(self.G, dtype=np.uint32), fanout)
+        if self.G * fanout < n_agents:
+            self.group_of[self.perm[self.G * fanout:]] = 0xFFFFFFFF
+        self.rng_send = np.random.default_rng(12345)
+        self.rng_pay = np.random.default_rng(3)
+
+    def members(self, g):
+        return self.perm[g * self.F:(g + 1) * self.F]
+
+    def batch(self):
+        S = self.S
+        grp = self.rng_send.integers(0, self.G, S).astype(np.uint32)
+        snd = self.rng_send.integers(0, self.A, S).astype(np.uint32)
+        while True:                                    # resample senders that are members of their group
+            bad = self.group_of[snd] == grp
+            nb = int(bad.sum())
+            if nb == 0:
+                break
+            snd[bad] = self.rng_send.integers(0, self.A, nb).astype(np.uint32)
+        prio = self.rng_send.integers(0, 4, S).astype(np.uint8)
+        typ = np.zeros(S, np.uint8)
+        lens = np.full(S, self.L, np.uint16)
+        off = np.arange(S, dtype=np.uint64) * self.L
+        payload = ALNUM[self.rng_pay.integers(0, 62, S * self.L)]
+        return snd, grp, prio, typ, lens, off, payload
+
+
+# ------------------------------------------------------------------------------------ clocks
+class ClockSampler:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, device_index=0):
+        self.rows = []
+        self.proc = None
+        self.dev = device_index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "100", "-i", str(self.dev)], stdout=subprocess.PIPE, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        for r in self.rows:
+            f = [x.strip() for x in r.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def hbm_peak():
+    p = ROOT / "MEASURED_PEAKS.json"
+    if p.exists():
+        try:
+            return float(json.loads(p.read_text())["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+def traffic_note():
+    p = ROOT / "profiles" / "roofline_traffic.json"
+    if p.exists():
+        try:
+            return json.loads(p.read_text()).get("k_group_fanout_bytes_per_launch")
+        except Exception:
+            return None
+    return None
+
+
+# ------------------------------------------------------------------------------------ CPU arm
+def cpu_roundtrip(wl: Workload, budget_s: float, max_batches: int):
+    """Oracle port (oracle/cpu_ref.c), all host threads: fan-out + drain of c2 batches."""
+    from oracle.cpu_ref import CpuOracle
+    cores = os.cpu_count() or 1
+    o = CpuOracle(wl.A, wl.G)
+    for g in range(wl.G):
+        o.create_group(g, wl.members(g))
+    batches = [wl.batch() for _ in range(2)]
+    o.mt_group_roundtrip(cores, *batches[0], max_messages=100)          # warm-up (page faults, allocator)
+    routed = 0
+    per_batch_ms = []
+    t0 = time.perf_counter()
+    k = 0
+    while k < max_batches and (time.perf_counter() - t0) < budget_s:
+        t1 = time.perf_counter()
+        r, drained, _ = o.mt_group_roundtrip(cores, *batches[k % 2], max_messages=100)
+        per_batch_ms.append((time.perf_counter() - t1) * 1e3)
+        assert r == drained == wl.S * wl.F, (r, drained)
+        routed += drained
+        k += 1
+    dt = time.perf_counter() - t0
+    o.close()
+    return routed / dt, cores, k, per_batch_ms
+
+
+def run_reference(args, rank, world):
+    if rank != 0:
+        return
+    wl = Workload()
+    batches = max(args.steps, 1)
+    value, cores, k, per = cpu_roundtrip(wl, budget_s=120.0, max_batches=batches)
+    sample = (f"{k} full c2 batch(es) of {wl.S} group sends x {wl.F} (= {wl.S * wl.F} routed msgs each), fan-out + "
+              f"drain, {cores} threads partitioned by receiver")
+    line = {
+        "impl": "reference", "metric": "messages/sec routed (send->receive) at 1M agents, 64-way fanout",
+        "value": value, "unit": "messages/s", "n_gpus": args.gpus, "steps": k, "warmup": 1,
+        "ms_per_step": float(np.mean(per)) if per else None, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "u8", "data": "synthetic",
+        "config": {"workload": "c2: 1M agents, 15625 groups x 64, 65536 group sends/step, 256-byte payloads, full drain",
+                   "impl_detail": "oracle port of the reference path (oracle/cpu_ref.c); the Python reference and "
+                                  "its Kafka broker cannot run on the GPU box"},
+        "cpu_baseline": {"value": value, "unit": "messages/s", "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": "messages/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------ GPU arm
+def run_gpu(args, rank, world, local_rank):
+    import torch
+    import torch.distributed as dist
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device - swarmdb_b200 has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    from swarmdb_b200._native import Shard
+
+    wl = Workload()
+    if world > 1:
+        from swarmdb_b200.sharded import run_sharded_bench
+        return run_sharded_bench(args, rank, world, local_rank, wl)
+
+    stream = torch.cuda.Stream()
+    K, W = args.steps, args.warmup
+    shard = Shard(max_agents=wl.A, ring_slots=64, arena_bytes=1 << 33, max_payload_bytes=wl.L, max_groups=1 << 14,
+                  member_pool_entries=wl.A + 1024, max_batch_sends=wl.S, max_batch_payload=wl.S * wl.L,
+                  max_recv_records=wl.S * wl.F + (1 << 16), max_recv_payload=(wl.S * wl.F + (1 << 16)) * wl.L,
+                  device=local_rank, fanout_variant=args.variant)
+    shard.set_stream(stream.cuda_stream)
+    shard.register(np.arange(wl.A, dtype=np.uint32))
+    for g in range(wl.G):
+        shard.create_group(g, wl.members(g))
+    shard.sync()
+
+    n_distinct = min(W + K, 8)
+    host_batches = [wl.batch() for _ in range(n_distinct)]
+    staged = [shard.stage(1, *b) for b in host_batches]
+    per_step_msgs = wl.S * wl.F
+
+    def device_step(i):
+        shard.submit(staged[i % n_distinct])
+        _, total, _ = shard.receive_batch(None, 100, 0, copy_out=False)
+        return total
+
+    with torch.cuda.stream(stream):
+        for i in range(W):
+            assert device_step(i) == per_step_msgs
+        launches0 = shard.stats()["kernel_launches"]
+        shard.profile(True)
+        clocks = ClockSampler(local_rank); clocks.start()
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize()
+        ev0.record(stream)
+        delivered = 0
+        for i in range(K):
+            delivered += device_step(W + i)
+        ev1.record(stream)
+        torch.cuda.synchronize()
+        clk = clocks.stop()
+        ms_total = ev0.elapsed_time(ev1)
+        prof = shard.profile_read()
+        shard.profile(False)
+        launches = shard.stats()["kernel_launches"] - launches0
+    assert delivered == K * per_step_msgs, (delivered, K * per_step_msgs)
+    value = delivered / (ms_total * 1e-3)
+
+    # ---- e2e: host buffers through the public bulk API, H2D and D2H inside the timed region
+    rec_cap = per_step_msgs + (1 << 16)
+    from swarmdb_b200._native import HDR_DTYPE
+    pin_hdr = torch.empty(rec_cap * 32, dtype=torch.uint8, pin_memory=True).numpy().view(HDR_DTYPE)
+    pin_pay = torch.empty(rec_cap * wl.L, dtype=torch.uint8, pin_memory=True).numpy()
+    pinned_in = []
+    for b in host_batches[: min(n_distinct, 4)]:
+        t = torch.empty(b[6].nbytes, dtype=torch.uint8, pin_memory=True)
+        t.numpy()[:] = b[6]
+        pinned_in.append(b[:6] + (t.numpy(),))
+    Ke = max(1, min(K, 8))
+
+    def e2e_step(i):
+        b = pinned_in[i % len(pinned_in)]
+        shard.send_group_batch(*b)
+        cnt, hdr, pay = shard.receive_batch(None, 100, 0, copy_out=True, out_hdr=pin_hdr, out_payload=pin_pay)
+        return len(hdr), int(hdr["seq"][-1]) if len(hdr) else 0
+
+    with torch.cuda.stream(stream):
+        for i in range(2):
+            assert e2e_step(i)[0] == per_step_msgs
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        t_wall = time.perf_counter()
+        e0.record(stream)
+        got = 0
+        for i in range(Ke):
+            got += e2e_step(i)[0]
+        e1.record(stream)
+        torch.cuda.synchronize()
+        wall_ms = (time.perf_counter() - t_wall) * 1e3
+        e2e_ms = max(e0.elapsed_time(e1), wall_ms)          # host-side work between calls counts too
+    e2e_value = got / (e2e_ms * 1e-3)
+    h2d = wl.S * wl.L + wl.S * 64                            # payload + 64-byte descriptors built by the library
+    d2h = per_step_msgs * (32 + wl.L) + wl.A * 4 + 16        # headers + payloads + per-agent counts + totals
+
+    # ---- roofline of the dominant kernel (group fan-out)
+    peak, peak_src = hbm_peak()
+    fan_ms, fan_n = prof["fanout"]
+    fan_avg_ms = fan_ms / max(fan_n, 1)
+    achieved = ALG_BYTES_FANOUT * per_step_msgs / (fan_avg_ms * 1e-3) / 1e9 if fan_n else 0.0
+    gat_ms, gat_n = prof["recv_gather"]
+    gat_avg = gat_ms / max(gat_n, 1)
+    kernels = {k: {"ms_per_launch": (v[0] / v[1] if v[1] else None), "launches": v[1]} for k, v in prof.items() if v[1]}
+    kernels["recv_gather"]["achieved_gbs"] = ALG_BYTES_GATHER * per_step_msgs / (gat_avg * 1e-3) / 1e9 if gat_n else None
+    kernels["recv_gather"]["frac"] = kernels["recv_gather"]["achieved_gbs"] / peak if gat_n else None
+
+    # ---- CPU baseline beside it (rank 0, N=1): bounded sample of the same workload
+    cpu_value, cores, kb, _ = cpu_roundtrip(wl, budget_s=args.cpu_budget, max_batches=8)
+
+    line = {
+        "metric": "messages/sec routed (send->receive) at 1M agents, 64-way fanout",
+        "value": value, "unit": "messages/s", "n_gpus": 1, "steps": K, "warmup": W,
+        "ms_per_step": ms_total / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "u8", "data": "synthetic",
+        "config": {"workload": "c2: 1M agents, 15625 groups x 64, 65536 group sends/step (4,194,304 routed msgs), "
+                               "256-byte payloads, full drain (receive_batch all agents, max_messages=100) each step",
+                   "l2": "inputs larger than L2: each step writes 1.2 GB of records into an 8 GiB arena and reads "
+                         "them back; no explicit flush needed",
+                   "fanout_variant": args.variant, "ring_slots": 64, "arena_bytes": 1 << 33},
+        "clocks": clk,
+        "e2e": {"value": e2e_value, "unit": "messages/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                "steps": Ke, "ms_per_step": e2e_ms / Ke},
+        "gpu_launches": int(launches),
+        "roofline": {"kernel": "k_group_fanout", "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                     "frac": achieved / peak, "traffic": traffic_note(), "peak_source": peak_src,
+                     "algorithmic_bytes_per_msg": ALG_BYTES_FANOUT, "msgs_per_launch": per_step_msgs,
+                     "ms_per_launch": fan_avg_ms},
+        "kernels": kernels,
+        "cpu_baseline": {"value": cpu_value, "unit": "messages/s", "cores": cores, "kind": "port",
+                         "sample": f"{kb} full c2 batch(es) (4,194,304 routed msgs each), fan-out + drain, "
+                                   f"oracle/cpu_ref.c on {cores} threads"},
+    }
+    print(json.dumps(line), flush=True)
+    for s in staged:
+        shard.free_staged(s)
+    shard.close()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=16)
+    ap.add_argument("--warmup", type=int, default=4)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--variant", type=int, default=int(os.environ.get("SDB_FANOUT_VARIANT", "0")))
+    ap.add_argument("--cpu-budget", type=float, default=15.0)
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.warmup < 3:
+        args.warmup = 3
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+    run_gpu(args, rank, world, local_rank)
+
+
+if __name__ == "__main__":
+    main()

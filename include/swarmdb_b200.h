@@ -1,0 +1,236 @@
+/*
+ * swarmdb_b200.h - C ABI of the B200-native agent message queue + backend balancer.
+ *
+ * This is the drop-in boundary for the hot path of The-Swarm-Corporation/SwarmDB
+ * (reference class `SwarmsDB` in /root/reference/swarmdb/" main.py", tag `M:`).  The
+ * reference has no FFI of its own: its `SwarmsDB` methods call the third-party
+ * `confluent_kafka` client (librdkafka) directly.  Each entry point below replaces one
+ * reference method body plus the Kafka client calls it makes; the file:line it replaces is
+ * cited on every declaration.  INTEGRATION.md shows the ctypes binding a maintainer adds.
+ *
+ * Conventions
+ *   - plain C: opaque handle, POD structs, pointers and sizes; no C++/torch types.
+ *   - every function returns 0 (SDB_OK) or a negative sdb_status; sdb_last_error(h)
+ *     returns a human-readable string for the last failure on that handle.
+ *   - a handle is NOT thread-safe (the reference class has no locks either);
+ *     one handle drives one GPU (one shard).  One process per GPU.
+ *   - pointer arguments are caller-owned HOST buffers unless the name ends in `_dev`.
+ *   - calls are stream-ordered on the handle's CUDA stream; functions that return
+ *     data to the host synchronise that stream before returning, others may return early.
+ *   - agents, groups and backends are dense uint32 indices; the string ids of the Python
+ *     surface are mapped by the caller (swarmdb_b200/core.py keeps the dict, as the
+ *     reference keeps `registered_agents`, M:233).
+ *   - there is NO CPU fallback: without a CUDA device sdb_create fails with SDB_ECUDA.
+ */
+#ifndef SWARMDB_B200_H
+#define SWARMDB_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SDB_ABI_VERSION 1u
+#define SDB_GRANULE 32u                 /* arena allocation unit, bytes (one DRAM sector) */
+#define SDB_NO_GROUP 0xFFFFFFFFu        /* header.group when the message was not a group send */
+#define SDB_NO_RECEIVER 0xFFFFFFFFu     /* header.receiver for broadcast records (receiver_id=None, M:61) */
+
+typedef struct sdb_ctx* sdb_handle;
+
+typedef enum sdb_status {
+  SDB_OK = 0,
+  SDB_EINVAL = -1,         /* bad argument (index out of range, misaligned offset, ...) */
+  SDB_ECUDA = -2,          /* CUDA runtime failure (incl. no device) */
+  SDB_ENOMEM = -3,         /* host or device allocation failed */
+  SDB_ERING_OVERFLOW = -4, /* some receiver's ring was full: those records were NOT enqueued (counted) */
+  SDB_EARENA_FULL = -5,    /* message arena cannot hold the batch even after reclaiming consumed space */
+  SDB_ECAPACITY = -6,      /* batch larger than the configured staging capacity */
+  SDB_ENOTFOUND = -7,      /* unknown group / backend */
+  SDB_EOUTPUT = -8         /* caller's output buffer too small */
+} sdb_status;
+
+/* Message vocabularies, M:23-51.  Device codes; names in swarmdb_b200/core.py. */
+enum { SDB_PRIO_LOW = 0, SDB_PRIO_NORMAL = 1, SDB_PRIO_HIGH = 2, SDB_PRIO_CRITICAL = 3 };
+enum { SDB_TYPE_CHAT = 0, SDB_TYPE_COMMAND, SDB_TYPE_FUNCTION_CALL, SDB_TYPE_FUNCTION_RESULT,
+       SDB_TYPE_SYSTEM, SDB_TYPE_ERROR, SDB_TYPE_STATUS };
+#define SDB_TYPE_MASK 0x07u
+#define SDB_TYPEF_JSON 0x08u            /* payload content is JSON (dict/list content, M:75) */
+#define SDB_TYPEF_EXTRAS 0x10u          /* payload = u32 content_len | content | JSON extras */
+
+/* Replaces KafkaConfig (M:114-127) + SwarmsDB.__init__ kwargs (M:156-165) for the device side. */
+typedef struct sdb_config {
+  uint32_t struct_bytes;        /* sizeof(sdb_config), ABI check */
+  int32_t  device;              /* CUDA ordinal */
+  uint32_t shard_id;            /* this process's shard (== rank) */
+  uint32_t num_shards;          /* replaces num_partitions (M:121): 1, 2, 4 or 8 */
+  uint32_t max_agents;          /* size of the global agent index space */
+  uint32_t ring_slots;          /* per-agent ring capacity in messages, power of two */
+  uint64_t arena_bytes;         /* message arena, power of two */
+  uint32_t max_payload_bytes;   /* largest payload accepted (<= 65504) */
+  uint32_t max_groups;
+  uint64_t member_pool_entries; /* total group-member slots (groups may be re-created) */
+  uint32_t max_backends;
+  uint32_t max_batch_sends;     /* staging capacity: sends per batch */
+  uint64_t max_batch_payload;   /* staging capacity: payload bytes per batch */
+  uint64_t max_recv_records;    /* receive output capacity, records per call */
+  uint64_t max_recv_payload;    /* receive output capacity, payload bytes per call (0: records x 256) */
+  uint64_t list_pool_entries;   /* per-batch broadcast recipient-list capacity (0: 2 x max_agents) */
+  uint32_t fanout_variant;      /* 0: TMA-in / vector-store-out kernel, 1: TMA-in / TMA-out kernel */
+  uint32_t flags;               /* reserved, 0 */
+} sdb_config;
+
+/* One message as stored in the arena and returned by receive: 32-byte header followed by
+ * the payload padded to SDB_GRANULE.  Field set = the device-relevant subset of `Message`
+ * (M:54-82): id <-> seq, sender_id, receiver_id, type, priority, timestamp, metadata["group"]. */
+typedef struct sdb_msg_header {
+  uint64_t seq;        /* message identity; ids are derived from it (replaces uuid4, M:72) */
+  double   timestamp;  /* M:78, carried, never compared */
+  uint32_t sender;     /* agent index */
+  uint32_t receiver;   /* agent index this copy was delivered to */
+  uint32_t group;      /* group index (M:1264 metadata["group"]) or SDB_NO_GROUP */
+  uint16_t len;        /* payload bytes */
+  uint8_t  prio;       /* 0..3, M:35-41 */
+  uint8_t  type;       /* SDB_TYPE_* | SDB_TYPEF_* */
+} sdb_msg_header;
+
+typedef struct sdb_stats {
+  uint64_t next_seq;            /* messages created so far (M:454 message_count analogue) */
+  uint64_t enqueued;            /* records appended to rings */
+  uint64_t delivered;           /* records returned by receive */
+  uint64_t ring_overflow;       /* records dropped because a ring was full (reported, never silent) */
+  uint64_t skipped_sender;      /* group members skipped because member == sender (M:1268) */
+  uint64_t arena_tail_bytes;    /* monotonic arena write position */
+  uint64_t arena_floor_bytes;   /* everything below is reclaimed */
+  uint64_t n_agents;            /* registered-index watermark */
+  uint64_t kernel_launches;     /* CUDA kernels launched by this handle so far */
+  uint64_t backend_picks;
+} sdb_stats;
+
+/* ---- lifecycle: SwarmsDB.__init__ (M:156-237), close (M:1367-1394) ---------------------- */
+int sdb_abi_version(void);
+int sdb_create(const sdb_config* cfg, sdb_handle* out);
+int sdb_destroy(sdb_handle h);
+/* Run on a caller-provided CUDA stream (e.g. torch's current stream) instead of the internal one. */
+int sdb_set_stream(sdb_handle h, void* cuda_stream);
+int sdb_sync(sdb_handle h);
+const char* sdb_last_error(sdb_handle h);
+int sdb_get_stats(sdb_handle h, sdb_stats* out);
+
+/* Per-kernel device timing (CUDA events on the handle's stream), used by bench.py for the
+ * roofline: enable, run, then read accumulated milliseconds and launch counts per kernel class. */
+enum { SDB_PK_P2P = 0, SDB_PK_FANOUT, SDB_PK_COMMIT, SDB_PK_RECV_COUNT, SDB_PK_RECV_SCAN, SDB_PK_RECV_SELECT,
+       SDB_PK_RECV_GATHER, SDB_PK_ARENA_FLOOR, SDB_PK_PICK, SDB_PK_XSHARD, SDB_PK_N = 16 };
+int sdb_profile(sdb_handle h, int enable);
+int sdb_profile_read(sdb_handle h, double* ms_out /* [SDB_PK_N] */, uint64_t* count_out /* [SDB_PK_N] */);
+
+/* ---- registry: register_agent (M:314-349) / deregister_agent (M:351-372) ------------------
+ * Rings exist for every index < max_agents; registration only moves the watermark that
+ * bounds the per-batch commit sweep.  Deregistration keeps the ring and its read position
+ * (the Kafka consumer-group offset survives Consumer.close(), SURVEY App. A rule 11). */
+int sdb_register_agents(sdb_handle h, uint32_t n, const uint32_t* agent_idx);
+int sdb_deregister_agents(sdb_handle h, uint32_t n, const uint32_t* agent_idx);
+
+/* ---- groups: add_agent_group (M:1208-1227), overwrite semantics, duplicates kept --------- */
+int sdb_create_group(sdb_handle h, uint32_t group_idx, uint32_t n_members, const uint32_t* member_idx);
+
+/* ---- enqueue --------------------------------------------------------------------------
+ * All three take a batch of `n` sends in call order (struct-of-arrays).  payload_off[i] is a
+ * byte offset into `payload`, 16-byte aligned, with len[i] bytes valid and readable up to
+ * the next multiple of 16.  Sequence numbers are assigned in array order starting at the
+ * handle's next_seq; *seq_base_out (nullable) receives the first one.
+ *
+ * sdb_send_batch        point-to-point: send_message (M:393-519) -> Producer.produce (M:476-482);
+ *                       send i gets seq_base + i.
+ * sdb_send_group_batch  send_to_group (M:1229-1279): one copy per member != sender, in member
+ *                       order; member j of send i gets seq_base + sum(size of earlier groups) + j
+ *                       (ids of skipped members are left unused).
+ * sdb_send_list_batch   broadcast (M:449-463, M:810-850): recipient list i is
+ *                       list_idx[list_off[i] .. list_off[i+1]); every copy shares ONE seq
+ *                       (one Message, one id), receiver field = SDB_NO_RECEIVER.
+ */
+int sdb_send_batch(sdb_handle h, uint32_t n,
+                   const uint32_t* sender, const uint32_t* receiver,
+                   const uint8_t* prio, const uint8_t* type, const uint16_t* len,
+                   const uint64_t* payload_off, const uint8_t* payload, uint64_t payload_bytes,
+                   const double* timestamp /* [n] or NULL = 0.0 */, uint64_t* seq_base_out);
+int sdb_send_group_batch(sdb_handle h, uint32_t n,
+                         const uint32_t* sender, const uint32_t* group_idx,
+                         const uint8_t* prio, const uint8_t* type, const uint16_t* len,
+                         const uint64_t* payload_off, const uint8_t* payload, uint64_t payload_bytes,
+                         const double* timestamp, uint64_t* seq_base_out);
+int sdb_send_list_batch(sdb_handle h, uint32_t n,
+                        const uint32_t* sender, const uint64_t* list_off /* [n+1] */, const uint32_t* list_idx,
+                        const uint8_t* prio, const uint8_t* type, const uint16_t* len,
+                        const uint64_t* payload_off, const uint8_t* payload, uint64_t payload_bytes,
+                        const double* timestamp, uint64_t* seq_base_out);
+
+/* Mixed batch in call order - what a host-side send buffer flushes (the reference's producer
+ * also batches, linger.ms = 10, M:197).  kind[i]: 0 = point-to-point (target = receiver index),
+ * 1 = group send (target = group index), 2 = broadcast list (target = list number t, recipients
+ * list_idx[list_off[t] .. list_off[t+1])).  Sequence numbers advance by 1, group size, 1. */
+int sdb_send_mixed_batch(sdb_handle h, uint32_t n,
+                         const uint32_t* sender, const uint8_t* kind, const uint32_t* target,
+                         uint32_t n_lists, const uint64_t* list_off, const uint32_t* list_idx,
+                         const uint8_t* prio, const uint8_t* type, const uint16_t* len,
+                         const uint64_t* payload_off, const uint8_t* payload, uint64_t payload_bytes,
+                         const double* timestamp, uint64_t* seq_base_out);
+
+/* Staged variant used to keep inputs resident in HBM (bench `value` leg): stage copies the
+ * batch to device memory once; submit enqueues it (may be repeated; each submit takes fresh
+ * sequence numbers).  kind: 0 = p2p (second index array = receiver), 1 = group. */
+typedef struct sdb_staged* sdb_staged_t;
+int sdb_stage_batch(sdb_handle h, uint32_t kind, uint32_t n,
+                    const uint32_t* sender, const uint32_t* receiver_or_group,
+                    const uint8_t* prio, const uint8_t* type, const uint16_t* len,
+                    const uint64_t* payload_off, const uint8_t* payload, uint64_t payload_bytes,
+                    const double* timestamp, sdb_staged_t* out);
+int sdb_submit_staged(sdb_handle h, sdb_staged_t s, uint64_t* seq_base_out);
+int sdb_free_staged(sdb_handle h, sdb_staged_t s);
+
+/* ---- dequeue: receive_messages (M:521-601) -> Consumer.poll (M:557-559) ------------------
+ * For each listed agent (agent_idx == NULL: every index below the registration watermark)
+ * remove up to max_messages pending records and return them, agents in list order, records
+ * in delivery order:
+ *   flags == 0                 stream (arrival) order - the reference's behaviour;
+ *   flags & SDB_RECV_PRIORITY  (priority desc, arrival asc) - the extension of SURVEY
+ *                              App. A rule 9; equals stream order when priorities are equal.
+ * Outputs (host pointers, each nullable to skip the copy): count_out[n_agents];
+ * hdr_out[total]; payload_out = payloads back to back, each padded to SDB_GRANULE, in the
+ * same order (offset of record r = sum of pad32(hdr_out[0..r).len)).  *total_out /
+ * *payload_bytes_out receive the totals.  Capacity: hdr_cap records / payload_cap bytes;
+ * agents that would exceed max_recv_records are truncated (their remaining records stay
+ * queued), never dropped.
+ */
+#define SDB_RECV_PRIORITY 1u
+int sdb_receive_batch(sdb_handle h, uint32_t n_agents, const uint32_t* agent_idx,
+                      uint32_t max_messages, uint32_t flags,
+                      uint32_t* count_out, sdb_msg_header* hdr_out, uint64_t hdr_cap,
+                      uint8_t* payload_out, uint64_t payload_cap,
+                      uint64_t* total_out, uint64_t* payload_bytes_out);
+/* Device-resident results of the LAST receive call (valid until the next one). */
+int sdb_last_receive_dev(sdb_handle h, const uint32_t** count_dev, const sdb_msg_header** hdr_dev,
+                         const uint8_t** payload_dev);
+
+/* ---- LLM backend balancer: set_llm_load_balancing / assign_llm_backend / get_llm_backend
+ * (M:1281-1325).  The reference stores a flag and a dict and has NO pick algorithm
+ * (SURVEY 0.5); the per-agent sticky map stays in the Python layer, and these entry points
+ * add the batched pick over live load counters:
+ *   mode 0  weighted least-load: requests are served in index order, each goes to
+ *           argmin_b load[b]/weight[b] (exact rational compare, ties -> lowest index) and adds
+ *           cost[i] (NULL = 1) to that backend's load;
+ *   mode 1  weighted random (one-item weighted reservoir, Efraimidis-Spirakis exponential
+ *           race in integer fixed point): P(b) proportional to weight[b], keyed by
+ *           (seed, request index); loads are then incremented atomically.
+ */
+int sdb_set_backends(sdb_handle h, uint32_t n, const uint32_t* weight, const uint64_t* load0);
+int sdb_get_backend_loads(sdb_handle h, uint32_t n, uint64_t* load_out);
+int sdb_release_backends(sdb_handle h, uint32_t n, const uint32_t* backend, const uint32_t* cost /* NULL = 1 */);
+int sdb_select_backend_batch(sdb_handle h, uint32_t n_req, const uint32_t* cost, uint32_t mode,
+                             uint64_t seed, uint32_t* backend_out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SWARMDB_B200_H */

@@ -1,0 +1,381 @@
+/*
+ * cpu_ref.c - CPU restatement of the hot path at the C-ABI level (ORACLE, TEST INFRASTRUCTURE ONLY).
+ *
+ * Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may
+ * link or call this file.  The shipped product (swarmdb_b200/) never does.
+ *
+ * It restates what the reference's path does to a message, with agents/groups as dense
+ * indices exactly as include/swarmdb_b200.h numbers them (tag M: = /root/reference/swarmdb/" main.py"):
+ *
+ *   send_message     M:393-519   one record appended to the topic log; the receiver is the
+ *                                only consumer whose filter (M:579-585) accepts it
+ *   send_to_group    M:1229-1279 for each member != sender, in list order: send_message
+ *                                (M:1267-1277); duplicates deliver twice
+ *   broadcast        M:449-463   one record, visible to an explicit agent list
+ *   receive_messages M:521-601   walk the log from this consumer's offset, keep matching
+ *                                records, stop after max_messages (M:553-556)
+ *
+ * Because the filter only ever accepts records addressed to (or listing) the agent, walking
+ * the single-partition log from the agent's offset is equivalent to popping from a
+ * per-agent FIFO of the accepted records in log order; that is the data structure here.
+ * Priority receive (SURVEY App. A rule 9, an extension the reference does not define):
+ * the first k pending records in (priority desc, arrival asc) order.
+ *
+ * PINNING: tests/test_oracle_c.py replays the golden scenarios (produced by the unmodified
+ * reference class) through this file and requires identical per-agent streams.
+ *
+ * Sequence numbers, header layout and padding follow the ABI contract in
+ * include/swarmdb_b200.h (they are part of the boundary, not of the reference).
+ */
+#include <pthread.h>
+#include <stdint.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include "../include/swarmdb_b200.h"
+
+typedef struct {
+  sdb_msg_header hdr;
+  uint64_t pay_off;     /* offset into the payload store */
+} orc_rec;
+
+typedef struct {
+  uint64_t* idx;        /* indices into recs[], arrival order */
+  uint8_t* done;        /* consumed flag per entry (priority receive leaves holes) */
+  uint64_t n, cap, head;
+} orc_inbox;
+
+typedef struct orc {
+  uint32_t max_agents, max_groups;
+  orc_rec* recs; uint64_t n_recs, cap_recs;
+  uint8_t* store; uint64_t n_store, cap_store;
+  orc_inbox* inbox;
+  uint32_t** gmem; uint32_t* gcnt; uint8_t* gdef;
+  uint64_t next_seq;
+  uint32_t watermark;
+  /* balancer */
+  uint32_t n_backends; uint32_t* weight; uint64_t* load;
+  uint32_t logtab[257];
+} orc;
+
+static void* xrealloc(void* p, size_t n) { void* q = realloc(p, n ? n : 1); if (!q) abort(); return q; }
+static uint32_t pad32(uint32_t x) { return (x + 31u) & ~31u; }
+
+static void build_log2_table(uint32_t* tab) {
+  /* log2(1 + i/256) in Q24, integer only: 26 fractional bits by repeated squaring, rounded */
+  for (uint32_t i = 0; i < 256; ++i) {
+    unsigned __int128 x = (unsigned __int128)(256 + i) << 54;           /* Q62 */
+    const unsigned __int128 two = (unsigned __int128)2 << 62;
+    uint32_t r = 0;
+    for (int k = 0; k < 26; ++k) { x = (x * x) >> 62; r <<= 1; if (x >= two) { r |= 1u; x >>= 1; } }
+    tab[i] = (r + 2u) >> 2;
+  }
+  tab[256] = 1u << 24;
+}
+
+orc* orc_create(uint32_t max_agents, uint32_t max_groups) {
+  orc* o = (orc*)calloc(1, sizeof(orc));
+  o->max_agents = max_agents; o->max_groups = max_groups ? max_groups : 1;
+  o->inbox = (orc_inbox*)calloc(max_agents, sizeof(orc_inbox));
+  o->gmem = (uint32_t**)calloc(o->max_groups, sizeof(uint32_t*));
+  o->gcnt = (uint32_t*)calloc(o->max_groups, sizeof(uint32_t));
+  o->gdef = (uint8_t*)calloc(o->max_groups, 1);
+  o->next_seq = 1;
+  build_log2_table(o->logtab);
+  return o;
+}
+
+void orc_destroy(orc* o) {
+  if (!o) return;
+  for (uint32_t a = 0; a < o->max_agents; ++a) { free(o->inbox[a].idx); free(o->inbox[a].done); }
+  for (uint32_t g = 0; g < o->max_groups; ++g) free(o->gmem[g]);
+  free(o->inbox); free(o->gmem); free(o->gcnt); free(o->gdef); free(o->recs); free(o->store);
+  free(o->weight); free(o->load); free(o);
+}
+
+void orc_register(orc* o, uint32_t a) { if (a < o->max_agents && a + 1 > o->watermark) o->watermark = a + 1; }
+
+/* add_agent_group, M:1208-1227: overwrite, no validation, duplicates kept */
+int orc_create_group(orc* o, uint32_t g, uint32_t n, const uint32_t* members) {
+  if (g >= o->max_groups) return -1;
+  o->gmem[g] = (uint32_t*)xrealloc(o->gmem[g], (size_t)n * 4);
+  memcpy(o->gmem[g], members, (size_t)n * 4);
+  o->gcnt[g] = n; o->gdef[g] = 1;
+  for (uint32_t i = 0; i < n; ++i) orc_register(o, members[i]);
+  return 0;
+}
+
+static uint64_t store_payload(orc* o, const uint8_t* p, uint32_t len) {
+  const uint32_t pl = pad32(len);
+  if (o->n_store + pl > o->cap_store) {
+    o->cap_store = (o->n_store + pl) * 2 + 4096;
+    o->store = (uint8_t*)xrealloc(o->store, o->cap_store);
+  }
+  const uint64_t off = o->n_store;
+  memcpy(o->store + off, p, len);
+  memset(o->store + off + len, 0, pl - len);
+  o->n_store += pl;
+  return off;
+}
+
+/* one delivery: the record lands in agent a's stream (the consumer whose filter accepts it) */
+static void deliver(orc* o, uint32_t a, uint64_t seq, double ts, uint32_t sender, uint32_t receiver_field,
+                    uint32_t group, uint16_t len, uint8_t prio, uint8_t type, uint64_t pay_off) {
+  if (o->n_recs == o->cap_recs) { o->cap_recs = o->cap_recs * 2 + 1024; o->recs = (orc_rec*)xrealloc(o->recs, o->cap_recs * sizeof(orc_rec)); }
+  orc_rec* r = &o->recs[o->n_recs];
+  r->hdr.seq = seq; r->hdr.timestamp = ts; r->hdr.sender = sender; r->hdr.receiver = receiver_field;
+  r->hdr.group = group; r->hdr.len = len; r->hdr.prio = prio; r->hdr.type = type; r->pay_off = pay_off;
+  orc_inbox* in = &o->inbox[a];
+  if (in->n == in->cap) {
+    in->cap = in->cap * 2 + 8;
+    in->idx = (uint64_t*)xrealloc(in->idx, in->cap * 8);
+    in->done = (uint8_t*)xrealloc(in->done, in->cap);
+  }
+  in->idx[in->n] = o->n_recs; in->done[in->n] = 0; in->n++;
+  o->n_recs++;
+}
+
+/* send_message x n, M:393-519; returns seq base */
+uint64_t orc_send_batch(orc* o, uint32_t n, const uint32_t* sender, const uint32_t* receiver, const uint8_t* prio,
+                        const uint8_t* type, const uint16_t* len, const uint64_t* payload_off, const uint8_t* payload,
+                        const double* ts) {
+  const uint64_t base = o->next_seq;
+  for (uint32_t i = 0; i < n; ++i) {
+    const uint64_t po = store_payload(o, payload + (payload_off ? payload_off[i] : 0), len[i]);
+    orc_register(o, sender[i]); orc_register(o, receiver[i]);                 /* auto-registration M:419-427 */
+    deliver(o, receiver[i], base + i, ts ? ts[i] : 0.0, sender[i], receiver[i], SDB_NO_GROUP, len[i],
+            prio ? prio[i] : 1, type ? type[i] : 0, po);
+  }
+  o->next_seq += n;
+  return base;
+}
+
+/* send_to_group x n, M:1229-1279 */
+uint64_t orc_send_group_batch(orc* o, uint32_t n, const uint32_t* sender, const uint32_t* group, const uint8_t* prio,
+                              const uint8_t* type, const uint16_t* len, const uint64_t* payload_off,
+                              const uint8_t* payload, const double* ts, uint64_t* n_routed) {
+  const uint64_t base = o->next_seq;
+  uint64_t rec = 0, routed = 0;
+  for (uint32_t i = 0; i < n; ++i) {
+    const uint32_t g = group[i];
+    if (g >= o->max_groups || !o->gdef[g]) continue;                           /* unknown group -> [] (M:1255-1257) */
+    const uint64_t po = store_payload(o, payload + (payload_off ? payload_off[i] : 0), len[i]);
+    for (uint32_t j = 0; j < o->gcnt[g]; ++j) {                                 /* member order, M:1267 */
+      const uint32_t a = o->gmem[g][j];
+      if (a != sender[i]) {                                                     /* M:1268 */
+        deliver(o, a, base + rec + j, ts ? ts[i] : 0.0, sender[i], a, g, len[i], prio ? prio[i] : 1,
+                type ? type[i] : 0, po);
+        ++routed;
+      }
+    }
+    rec += o->gcnt[g];
+  }
+  o->next_seq += rec;
+  if (n_routed) *n_routed = routed;
+  return base;
+}
+
+/* broadcast with explicit visibility list, M:449-463 / M:810-850: ONE message, many readers */
+uint64_t orc_send_list_batch(orc* o, uint32_t n, const uint32_t* sender, const uint64_t* list_off, const uint32_t* list_idx,
+                             const uint8_t* prio, const uint8_t* type, const uint16_t* len, const uint64_t* payload_off,
+                             const uint8_t* payload, const double* ts) {
+  const uint64_t base = o->next_seq;
+  for (uint32_t i = 0; i < n; ++i) {
+    const uint64_t po = store_payload(o, payload + (payload_off ? payload_off[i] : 0), len[i]);
+    for (uint64_t k = list_off[i]; k < list_off[i + 1]; ++k)
+      deliver(o, list_idx[k], base + i, ts ? ts[i] : 0.0, sender[i], SDB_NO_RECEIVER, SDB_NO_GROUP, len[i],
+              prio ? prio[i] : 1, type ? type[i] : 0, po);
+  }
+  o->next_seq += n;
+  return base;
+}
+
+/* receive_messages for a list of agents, M:521-601.  Output format of sdb_receive_batch. */
+uint64_t orc_receive_batch(orc* o, uint32_t n_agents, const uint32_t* agent_idx, uint32_t max_messages, uint32_t flags,
+                           uint32_t* count_out, sdb_msg_header* hdr_out, uint8_t* payload_out, uint64_t* payload_bytes) {
+  uint64_t total = 0, pbytes = 0;
+  if (!agent_idx) n_agents = o->watermark;
+  for (uint32_t q = 0; q < n_agents; ++q) {
+    const uint32_t a = agent_idx ? agent_idx[q] : q;
+    orc_inbox* in = &o->inbox[a];
+    uint32_t got = 0;
+    if (flags & SDB_RECV_PRIORITY) {
+      for (int L = 3; L >= 0 && got < max_messages; --L)
+        for (uint64_t p = in->head; p < in->n && got < max_messages; ++p) {
+          if (in->done[p]) continue;
+          const orc_rec* r = &o->recs[in->idx[p]];
+          if (r->hdr.prio != (uint8_t)L) continue;
+          in->done[p] = 1;
+          if (hdr_out) hdr_out[total] = r->hdr;
+          if (payload_out) memcpy(payload_out + pbytes, o->store + r->pay_off, pad32(r->hdr.len));
+          pbytes += pad32(r->hdr.len); ++total; ++got;
+        }
+    } else {
+      for (uint64_t p = in->head; p < in->n && got < max_messages; ++p) {      /* stream order */
+        if (in->done[p]) continue;
+        const orc_rec* r = &o->recs[in->idx[p]];
+        in->done[p] = 1;
+        if (hdr_out) hdr_out[total] = r->hdr;
+        if (payload_out) memcpy(payload_out + pbytes, o->store + r->pay_off, pad32(r->hdr.len));
+        pbytes += pad32(r->hdr.len); ++total; ++got;
+      }
+    }
+    while (in->head < in->n && in->done[in->head]) in->head++;
+    if (count_out) count_out[q] = got;
+  }
+  if (payload_bytes) *payload_bytes = pbytes;
+  return total;
+}
+
+uint64_t orc_pending(orc* o, uint32_t a) {
+  orc_inbox* in = &o->inbox[a];
+  uint64_t c = 0;
+  for (uint64_t p = in->head; p < in->n; ++p) c += !in->done[p];
+  return c;
+}
+
+/* ---- balancer (definition in include/swarmdb_b200.h; the reference has none, M:1281-1325) ---- */
+void orc_set_backends(orc* o, uint32_t n, const uint32_t* weight, const uint64_t* load0) {
+  o->n_backends = n;
+  o->weight = (uint32_t*)xrealloc(o->weight, (size_t)n * 4);
+  o->load = (uint64_t*)xrealloc(o->load, (size_t)n * 8);
+  for (uint32_t b = 0; b < n; ++b) { o->weight[b] = weight[b]; o->load[b] = load0 ? load0[b] : 0; }
+}
+void orc_get_backend_loads(orc* o, uint64_t* out) { memcpy(out, o->load, (size_t)o->n_backends * 8); }
+
+static uint64_t mix(uint64_t seed, uint32_t t, uint32_t b) {
+  uint64_t x = seed ^ ((uint64_t)t + 1ull) * 0x9E3779B97F4A7C15ull;
+  x ^= ((uint64_t)b + 1ull) * 0xD1B54A32D192ED03ull;
+  x ^= x >> 30; x *= 0xBF58476D1CE4E5B9ull;
+  x ^= x >> 27; x *= 0x94D049BB133111EBull;
+  x ^= x >> 31;
+  return x;
+}
+static uint32_t neglog2_q24(uint32_t u, const uint32_t* tab) {
+  const uint32_t lz = (uint32_t)__builtin_clz(u);
+  const uint32_t un = u << lz;
+  const uint32_t idx = (un >> 23) & 0xFFu, frac = un & 0x7FFFFFu;
+  const uint32_t lg = tab[idx] + (uint32_t)(((uint64_t)(tab[idx + 1] - tab[idx]) * frac) >> 23);
+  return ((1u + lz) << 24) - lg;
+}
+
+void orc_select_backend_batch(orc* o, uint32_t n_req, const uint32_t* cost, uint32_t mode, uint64_t seed, uint32_t* out) {
+  const uint32_t B = o->n_backends;
+  if (mode == 0) {
+    /* sequential greedy: argmin load/weight, exact rational compare, ties -> lowest index */
+    for (uint32_t t = 0; t < n_req; ++t) {
+      uint32_t best = 0;
+      for (uint32_t b = 1; b < B; ++b)
+        if ((unsigned __int128)o->load[b] * o->weight[best] < (unsigned __int128)o->load[best] * o->weight[b]) best = b;
+      out[t] = best;
+      o->load[best] += cost ? cost[t] : 1u;
+    }
+  } else {
+    for (uint32_t t = 0; t < n_req; ++t) {
+      uint32_t best = 0, bw = 1; uint64_t bk = 0; int have = 0;
+      for (uint32_t b = 0; b < B; ++b) {
+        const uint32_t u = (uint32_t)(mix(seed, t, b) >> 32) | 1u;
+        const uint64_t k = neglog2_q24(u, o->logtab);
+        if (!have || k * bw < bk * o->weight[b]) { bk = k; bw = o->weight[b]; best = b; have = 1; }
+      }
+      out[t] = best;
+    }
+    for (uint32_t t = 0; t < n_req; ++t) o->load[out[t]] += cost ? cost[t] : 1u;
+  }
+}
+
+/* ---- multi-threaded group fan-out + drain for the CPU baseline --------------------------------
+ * Threads own disjoint receiver sets (receiver % T == tid), so every inbox is appended by exactly
+ * one thread in send order: same streams as the single-threaded path, no locks.  Records are
+ * materialised per delivery (header + payload copy) - the work a CPU queue does per routed
+ * message - into per-thread arenas, then drained per agent into per-thread output buffers. */
+typedef struct {
+  orc* o; uint32_t tid, T, n; const uint32_t* sender; const uint32_t* group; const uint8_t* prio; const uint8_t* type;
+  const uint16_t* len; const uint64_t* payload_off; const uint8_t* payload; uint64_t seq_base; const uint64_t* rec0;
+  uint8_t* arena; uint64_t arena_cap, arena_used; uint64_t** lists; uint32_t* lcnt; uint32_t* lcap;
+  uint64_t routed, drained, checksum; uint32_t max_messages; uint8_t* out; uint64_t out_cap;
+} mt_task;
+
+static void* mt_fanout(void* p) {
+  mt_task* t = (mt_task*)p; orc* o = t->o;
+  for (uint32_t i = 0; i < t->n; ++i) {
+    const uint32_t g = t->group[i];
+    const uint32_t pl = pad32(t->len[i]);
+    for (uint32_t j = 0; j < o->gcnt[g]; ++j) {
+      const uint32_t a = o->gmem[g][j];
+      if (a % t->T != t->tid || a == t->sender[i]) continue;
+      if (t->arena_used + 32 + pl > t->arena_cap) continue;      /* sized by the caller; never hit */
+      uint8_t* rec = t->arena + t->arena_used;
+      sdb_msg_header h; h.seq = t->seq_base + t->rec0[i] + j; h.timestamp = 0.0; h.sender = t->sender[i]; h.receiver = a;
+      h.group = g; h.len = t->len[i]; h.prio = t->prio[i]; h.type = t->type[i];
+      memcpy(rec, &h, 32);
+      memcpy(rec + 32, t->payload + t->payload_off[i], t->len[i]);
+      memset(rec + 32 + t->len[i], 0, pl - t->len[i]);
+      const uint32_t slot = a / t->T;
+      if (t->lcnt[slot] == t->lcap[slot]) {
+        t->lcap[slot] = t->lcap[slot] * 2 + 8;
+        t->lists[slot] = (uint64_t*)xrealloc(t->lists[slot], (size_t)t->lcap[slot] * 8);
+      }
+      t->lists[slot][t->lcnt[slot]++] = t->arena_used;
+      t->arena_used += 32 + pl;
+      t->routed++;
+    }
+  }
+  return NULL;
+}
+
+static void* mt_drain(void* p) {
+  mt_task* t = (mt_task*)p;
+  const uint32_t slots = (t->o->max_agents + t->T - 1) / t->T;
+  uint64_t used = 0, sum = 0;
+  for (uint32_t s = 0; s < slots; ++s) {
+    const uint32_t k = t->lcnt[s] < t->max_messages ? t->lcnt[s] : t->max_messages;
+    for (uint32_t e = 0; e < k; ++e) {
+      const uint8_t* rec = t->arena + t->lists[s][e];
+      const sdb_msg_header* h = (const sdb_msg_header*)rec;
+      const uint32_t sz = 32 + pad32(h->len);
+      if (used + sz > t->out_cap) used = 0;                       /* ring the output buffer */
+      memcpy(t->out + used, rec, sz);
+      used += sz; sum += h->seq; t->drained++;
+    }
+    t->lcnt[s] = 0;
+  }
+  t->checksum = sum;
+  return NULL;
+}
+
+/* Returns routed records; *drained_out and *checksum_out (sum of seq of drained records) verify the work. */
+uint64_t orc_mt_group_roundtrip(orc* o, uint32_t T, uint32_t n, const uint32_t* sender, const uint32_t* group,
+                                const uint8_t* prio, const uint8_t* type, const uint16_t* len, const uint64_t* payload_off,
+                                const uint8_t* payload, uint32_t max_messages, uint64_t* drained_out, uint64_t* checksum_out) {
+  if (T == 0) T = 1;
+  uint64_t* rec0 = (uint64_t*)malloc((size_t)n * 8);
+  uint64_t rec = 0, bytes = 0;
+  for (uint32_t i = 0; i < n; ++i) { rec0[i] = rec; rec += o->gcnt[group[i]]; bytes += (uint64_t)o->gcnt[group[i]] * (32 + pad32(len[i])); }
+  mt_task* ts = (mt_task*)calloc(T, sizeof(mt_task));
+  pthread_t* th = (pthread_t*)calloc(T, sizeof(pthread_t));
+  const uint32_t slots = (o->max_agents + T - 1) / T;
+  for (uint32_t k = 0; k < T; ++k) {
+    mt_task* t = &ts[k];
+    t->o = o; t->tid = k; t->T = T; t->n = n; t->sender = sender; t->group = group; t->prio = prio; t->type = type; t->len = len;
+    t->payload_off = payload_off; t->payload = payload; t->seq_base = o->next_seq; t->rec0 = rec0;
+    t->arena_cap = bytes / T * 2 + (1u << 20); t->arena = (uint8_t*)malloc(t->arena_cap);
+    t->lists = (uint64_t**)calloc(slots, sizeof(uint64_t*)); t->lcnt = (uint32_t*)calloc(slots, 4); t->lcap = (uint32_t*)calloc(slots, 4);
+    t->max_messages = max_messages; t->out_cap = 64u << 20; t->out = (uint8_t*)malloc(t->out_cap);
+  }
+  for (uint32_t k = 0; k < T; ++k) pthread_create(&th[k], NULL, mt_fanout, &ts[k]);
+  for (uint32_t k = 0; k < T; ++k) pthread_join(th[k], NULL);
+  for (uint32_t k = 0; k < T; ++k) pthread_create(&th[k], NULL, mt_drain, &ts[k]);
+  for (uint32_t k = 0; k < T; ++k) pthread_join(th[k], NULL);
+  uint64_t routed = 0, drained = 0, sum = 0;
+  for (uint32_t k = 0; k < T; ++k) {
+    routed += ts[k].routed; drained += ts[k].drained; sum += ts[k].checksum;
+    for (uint32_t s = 0; s < slots; ++s) free(ts[k].lists[s]);
+    free(ts[k].lists); free(ts[k].lcnt); free(ts[k].lcap); free(ts[k].arena); free(ts[k].out);
+  }
+  o->next_seq += rec;
+  free(ts); free(th); free(rec0);
+  if (drained_out) *drained_out = drained;
+  if (checksum_out) *checksum_out = sum;
+  return routed;
+}

@@ -1,0 +1,362 @@
+"""ctypes binding of the C ABI in include/swarmdb_b200.h (the drop-in boundary).
+
+`Shard` is one GPU-resident queue shard (one handle, one GPU).  There is no CPU
+implementation behind it: if the CUDA library is missing or no device is present, loading /
+construction fails loudly - it never falls back.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from pathlib import Path
+from typing import Optional, Sequence, Tuple
+
+import numpy as np
+
+_CSRC = Path(__file__).resolve().parent / "csrc"
+LIB_PATH = _CSRC / "libswarmdb_b200.so"
+
+HDR_DTYPE = np.dtype([("seq", "<u8"), ("timestamp", "<f8"), ("sender", "<u4"), ("receiver", "<u4"),
+                      ("group", "<u4"), ("len", "<u2"), ("prio", "u1"), ("type", "u1")])
+assert HDR_DTYPE.itemsize == 32
+
+NO_GROUP = 0xFFFFFFFF
+NO_RECEIVER = 0xFFFFFFFF
+RECV_PRIORITY = 1
+TYPEF_JSON = 0x08
+TYPEF_EXTRAS = 0x10
+TYPE_MASK = 0x07
+
+STATUS_NAMES = {0: "SDB_OK", -1: "SDB_EINVAL", -2: "SDB_ECUDA", -3: "SDB_ENOMEM", -4: "SDB_ERING_OVERFLOW",
+                -5: "SDB_EARENA_FULL", -6: "SDB_ECAPACITY", -7: "SDB_ENOTFOUND", -8: "SDB_EOUTPUT"}
+
+
+class SdbError(RuntimeError):
+    def __init__(self, code: int, msg: str) -> None:
+        super().__init__(f"{STATUS_NAMES.get(code, code)}: {msg}")
+        self.code = code
+
+
+class SdbConfig(C.Structure):
+    _fields_ = [("struct_bytes", C.c_uint32), ("device", C.c_int32), ("shard_id", C.c_uint32),
+                ("num_shards", C.c_uint32), ("max_agents", C.c_uint32), ("ring_slots", C.c_uint32),
+                ("arena_bytes", C.c_uint64), ("max_payload_bytes", C.c_uint32), ("max_groups", C.c_uint32),
+                ("member_pool_entries", C.c_uint64), ("max_backends", C.c_uint32), ("max_batch_sends", C.c_uint32),
+                ("max_batch_payload", C.c_uint64), ("max_recv_records", C.c_uint64), ("max_recv_payload", C.c_uint64),
+                ("list_pool_entries", C.c_uint64), ("fanout_variant", C.c_uint32), ("flags", C.c_uint32)]
+
+
+class SdbStats(C.Structure):
+    _fields_ = [(n, C.c_uint64) for n in ("next_seq", "enqueued", "delivered", "ring_overflow", "skipped_sender",
+                                          "arena_tail_bytes", "arena_floor_bytes", "n_agents", "kernel_launches",
+                                          "backend_picks")]
+
+
+EXPORTS = ["sdb_abi_version", "sdb_create", "sdb_destroy", "sdb_set_stream", "sdb_sync", "sdb_last_error",
+           "sdb_get_stats", "sdb_profile", "sdb_profile_read", "sdb_register_agents", "sdb_deregister_agents", "sdb_create_group", "sdb_send_batch",
+           "sdb_send_group_batch", "sdb_send_list_batch", "sdb_send_mixed_batch", "sdb_stage_batch", "sdb_submit_staged", "sdb_free_staged",
+           "sdb_receive_batch", "sdb_last_receive_dev", "sdb_set_backends", "sdb_get_backend_loads",
+           "sdb_release_backends", "sdb_select_backend_batch"]
+
+_lib = None
+
+
+def load_library() -> C.CDLL:
+    """dlopen the in-tree CUDA library.  Raises if it has not been built (no fallback)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    path = Path(os.environ.get("SWARMDB_B200_LIB", str(LIB_PATH)))
+    if not path.exists():
+        raise ImportError(f"{path} not built - run `python -c 'import __graft_entry__ as g; g.build()'` "
+                          f"(or make -C swarmdb_b200/csrc). swarmdb_b200 has no CPU fallback.")
+    L = C.CDLL(str(path))
+    vp, u32, u64, i32 = C.c_void_p, C.c_uint32, C.c_uint64, C.c_int
+    L.sdb_abi_version.restype = i32
+    L.sdb_create.restype = i32; L.sdb_create.argtypes = [C.POINTER(SdbConfig), C.POINTER(vp)]
+    L.sdb_destroy.restype = i32; L.sdb_destroy.argtypes = [vp]
+    L.sdb_set_stream.restype = i32; L.sdb_set_stream.argtypes = [vp, vp]
+    L.sdb_sync.restype = i32; L.sdb_sync.argtypes = [vp]
+    L.sdb_last_error.restype = C.c_char_p; L.sdb_last_error.argtypes = [vp]
+    L.sdb_get_stats.restype = i32; L.sdb_get_stats.argtypes = [vp, C.POINTER(SdbStats)]
+    L.sdb_profile.restype = i32; L.sdb_profile.argtypes = [vp, i32]
+    L.sdb_profile_read.restype = i32; L.sdb_profile_read.argtypes = [vp, vp, vp]
+    L.sdb_register_agents.restype = i32; L.sdb_register_agents.argtypes = [vp, u32, vp]
+    L.sdb_deregister_agents.restype = i32; L.sdb_deregister_agents.argtypes = [vp, u32, vp]
+    L.sdb_create_group.restype = i32; L.sdb_create_group.argtypes = [vp, u32, u32, vp]
+    L.sdb_send_batch.restype = i32; L.sdb_send_batch.argtypes = [vp, u32] + [vp] * 7 + [u64, vp, vp]
+    L.sdb_send_group_batch.restype = i32; L.sdb_send_group_batch.argtypes = [vp, u32] + [vp] * 7 + [u64, vp, vp]
+    L.sdb_send_list_batch.restype = i32; L.sdb_send_list_batch.argtypes = [vp, u32] + [vp] * 8 + [u64, vp, vp]
+    L.sdb_send_mixed_batch.restype = i32
+    L.sdb_send_mixed_batch.argtypes = [vp, u32, vp, vp, vp, u32] + [vp] * 7 + [u64, vp, vp]
+    L.sdb_stage_batch.restype = i32; L.sdb_stage_batch.argtypes = [vp, u32, u32] + [vp] * 7 + [u64, vp, C.POINTER(vp)]
+    L.sdb_submit_staged.restype = i32; L.sdb_submit_staged.argtypes = [vp, vp, vp]
+    L.sdb_free_staged.restype = i32; L.sdb_free_staged.argtypes = [vp, vp]
+    L.sdb_receive_batch.restype = i32
+    L.sdb_receive_batch.argtypes = [vp, u32, vp, u32, u32, vp, vp, u64, vp, u64, vp, vp]
+    L.sdb_last_receive_dev.restype = i32; L.sdb_last_receive_dev.argtypes = [vp, vp, vp, vp]
+    L.sdb_set_backends.restype = i32; L.sdb_set_backends.argtypes = [vp, u32, vp, vp]
+    L.sdb_get_backend_loads.restype = i32; L.sdb_get_backend_loads.argtypes = [vp, u32, vp]
+    L.sdb_release_backends.restype = i32; L.sdb_release_backends.argtypes = [vp, u32, vp, vp]
+    L.sdb_select_backend_batch.restype = i32; L.sdb_select_backend_batch.argtypes = [vp, u32, vp, u32, u64, vp]
+    if L.sdb_abi_version() != 1:
+        raise ImportError("swarmdb_b200 ABI version mismatch")
+    _lib = L
+    return L
+
+
+def _p(a):
+    if a is None:
+        return None
+    if isinstance(a, np.ndarray):
+        return a.ctypes.data_as(C.c_void_p)
+    if isinstance(a, int):
+        return C.c_void_p(a)
+    raise TypeError(type(a))
+
+
+def _arr(x, dt) -> np.ndarray:
+    return np.ascontiguousarray(x, dtype=dt)
+
+
+def pad32(n):
+    return (n + 31) & ~31
+
+
+class Shard:
+    """One GPU-resident shard: per-agent rings + message arena + backend table on one device."""
+
+    def __init__(self, max_agents: int, ring_slots: int = 64, arena_bytes: int = 1 << 28,
+                 max_payload_bytes: int = 256, max_groups: int = 1, member_pool_entries: int = 0,
+                 max_backends: int = 256, max_batch_sends: int = 65536, max_batch_payload: int = 0,
+                 max_recv_records: int = 1 << 20, max_recv_payload: int = 0, list_pool_entries: int = 0,
+                 device: int = 0, shard_id: int = 0, num_shards: int = 1, fanout_variant: int = 0) -> None:
+        self._L = load_library()
+        cfg = SdbConfig()
+        cfg.struct_bytes = C.sizeof(SdbConfig)
+        cfg.device, cfg.shard_id, cfg.num_shards = device, shard_id, num_shards
+        cfg.max_agents, cfg.ring_slots, cfg.arena_bytes = max_agents, ring_slots, arena_bytes
+        cfg.max_payload_bytes, cfg.max_groups = max_payload_bytes, max_groups
+        cfg.member_pool_entries = member_pool_entries or max(1024, 2 * max_agents)
+        cfg.max_backends, cfg.max_batch_sends, cfg.max_batch_payload = max_backends, max_batch_sends, max_batch_payload
+        cfg.max_recv_records, cfg.max_recv_payload, cfg.list_pool_entries = max_recv_records, max_recv_payload, list_pool_entries
+        cfg.fanout_variant = fanout_variant
+        self.cfg = cfg
+        self.max_agents = max_agents
+        self._h = C.c_void_p()
+        rc = self._L.sdb_create(C.byref(cfg), C.byref(self._h))
+        if rc != 0:
+            msg = self._L.sdb_last_error(self._h).decode() if self._h else "sdb_create failed"
+            if self._h:
+                self._L.sdb_destroy(self._h)
+                self._h = C.c_void_p()
+            raise SdbError(rc, msg)
+        self.max_recv_records = int(cfg.max_recv_records) or (1 << 20)
+        self._keep = None          # keeps the last payload buffer alive while its H2D copy is in flight
+        # pinned-or-pageable host output buffers, grown on demand
+        self._out_hdr = np.zeros(0, HDR_DTYPE)
+        self._out_pay = np.zeros(0, np.uint8)
+        self._nb = 0
+
+    # ------------------------------------------------------------------ plumbing
+    def _check(self, rc: int) -> None:
+        if rc != 0:
+            raise SdbError(rc, self._L.sdb_last_error(self._h).decode())
+
+    def close(self) -> None:
+        if getattr(self, "_h", None):
+            self._L.sdb_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def set_stream(self, cuda_stream: int) -> None:
+        self._check(self._L.sdb_set_stream(self._h, C.c_void_p(cuda_stream)))
+
+    def sync(self) -> None:
+        self._check(self._L.sdb_sync(self._h))
+
+    def stats(self) -> dict:
+        s = SdbStats()
+        self._check(self._L.sdb_get_stats(self._h, C.byref(s)))
+        return {n: int(getattr(s, n)) for n, _ in SdbStats._fields_}
+
+    PROFILE_KINDS = ["p2p", "fanout", "commit", "recv_count", "recv_scan", "recv_select", "recv_gather",
+                     "arena_floor", "pick", "xshard"]
+
+    def profile(self, enable: bool) -> None:
+        self._check(self._L.sdb_profile(self._h, 1 if enable else 0))
+
+    def profile_read(self) -> dict:
+        """{kernel class: (total ms, launches)} measured with CUDA events on the launching stream."""
+        ms = np.zeros(16, np.float64)
+        cnt = np.zeros(16, np.uint64)
+        self._check(self._L.sdb_profile_read(self._h, _p(ms), _p(cnt)))
+        return {k: (float(ms[i]), int(cnt[i])) for i, k in enumerate(self.PROFILE_KINDS)}
+
+    # ------------------------------------------------------------------ registry / groups
+    def register(self, idx) -> None:
+        a = _arr(np.atleast_1d(idx), np.uint32)
+        self._check(self._L.sdb_register_agents(self._h, len(a), _p(a)))
+
+    def deregister(self, idx) -> None:
+        a = _arr(np.atleast_1d(idx), np.uint32)
+        self._check(self._L.sdb_deregister_agents(self._h, len(a), _p(a)))
+
+    def create_group(self, g: int, members) -> None:
+        m = _arr(members, np.uint32)
+        self._check(self._L.sdb_create_group(self._h, g, len(m), _p(m)))
+
+    # ------------------------------------------------------------------ enqueue
+    @staticmethod
+    def _common(n, prio, typ, lens, payload_off, payload, ts):
+        prio = None if prio is None else _arr(prio, np.uint8)
+        typ = None if typ is None else _arr(typ, np.uint8)
+        lens = _arr(lens, np.uint16)
+        payload_off = _arr(payload_off, np.uint64)
+        payload = _arr(payload, np.uint8)
+        ts = None if ts is None else _arr(ts, np.float64)
+        assert len(lens) == n and len(payload_off) == n
+        return prio, typ, lens, payload_off, payload, ts
+
+    def send_batch(self, sender, receiver, prio, typ, lens, payload_off, payload, ts=None) -> int:
+        s, r = _arr(sender, np.uint32), _arr(receiver, np.uint32)
+        prio, typ, lens, po, pl, ts = self._common(len(s), prio, typ, lens, payload_off, payload, ts)
+        base = C.c_uint64(0)
+        self._keep = pl
+        self._check(self._L.sdb_send_batch(self._h, len(s), _p(s), _p(r), _p(prio), _p(typ), _p(lens), _p(po), _p(pl),
+                                           pl.nbytes, _p(ts), C.cast(C.byref(base), C.c_void_p)))
+        return base.value
+
+    def send_group_batch(self, sender, group, prio, typ, lens, payload_off, payload, ts=None) -> int:
+        s, g = _arr(sender, np.uint32), _arr(group, np.uint32)
+        prio, typ, lens, po, pl, ts = self._common(len(s), prio, typ, lens, payload_off, payload, ts)
+        base = C.c_uint64(0)
+        self._keep = pl
+        self._check(self._L.sdb_send_group_batch(self._h, len(s), _p(s), _p(g), _p(prio), _p(typ), _p(lens), _p(po),
+                                                 _p(pl), pl.nbytes, _p(ts), C.cast(C.byref(base), C.c_void_p)))
+        return base.value
+
+    def send_list_batch(self, sender, list_off, list_idx, prio, typ, lens, payload_off, payload, ts=None) -> int:
+        s = _arr(sender, np.uint32)
+        lo, li = _arr(list_off, np.uint64), _arr(list_idx, np.uint32)
+        prio, typ, lens, po, pl, ts = self._common(len(s), prio, typ, lens, payload_off, payload, ts)
+        base = C.c_uint64(0)
+        self._keep = pl
+        self._check(self._L.sdb_send_list_batch(self._h, len(s), _p(s), _p(lo), _p(li), _p(prio), _p(typ), _p(lens),
+                                                _p(po), _p(pl), pl.nbytes, _p(ts), C.cast(C.byref(base), C.c_void_p)))
+        return base.value
+
+    def send_mixed_batch(self, sender, kind, target, list_off, list_idx, prio, typ, lens, payload_off, payload,
+                         ts=None) -> int:
+        """kind[i]: 0 p2p (target = receiver), 1 group (target = group), 2 list (target = list number)."""
+        s, k, t = _arr(sender, np.uint32), _arr(kind, np.uint8), _arr(target, np.uint32)
+        lo = _arr(list_off if list_off is not None else [0], np.uint64)
+        li = _arr(list_idx if list_idx is not None else [], np.uint32)
+        prio, typ, lens, po, pl, ts = self._common(len(s), prio, typ, lens, payload_off, payload, ts)
+        base = C.c_uint64(0)
+        self._keep = pl
+        self._check(self._L.sdb_send_mixed_batch(self._h, len(s), _p(s), _p(k), _p(t), len(lo) - 1, _p(lo), _p(li),
+                                                 _p(prio), _p(typ), _p(lens), _p(po), _p(pl), pl.nbytes, _p(ts),
+                                                 C.cast(C.byref(base), C.c_void_p)))
+        return base.value
+
+    def stage(self, kind: int, sender, second, prio, typ, lens, payload_off, payload, ts=None) -> int:
+        """Copy a p2p (kind 0) or group (kind 1) batch to device memory; returns a staged handle."""
+        s, g = _arr(sender, np.uint32), _arr(second, np.uint32)
+        prio, typ, lens, po, pl, ts = self._common(len(s), prio, typ, lens, payload_off, payload, ts)
+        out = C.c_void_p()
+        self._check(self._L.sdb_stage_batch(self._h, kind, len(s), _p(s), _p(g), _p(prio), _p(typ), _p(lens), _p(po),
+                                            _p(pl), pl.nbytes, _p(ts), C.byref(out)))
+        return out.value
+
+    def submit(self, staged: int) -> int:
+        base = C.c_uint64(0)
+        self._check(self._L.sdb_submit_staged(self._h, C.c_void_p(staged), C.cast(C.byref(base), C.c_void_p)))
+        return base.value
+
+    def free_staged(self, staged: int) -> None:
+        self._check(self._L.sdb_free_staged(self._h, C.c_void_p(staged)))
+
+    # ------------------------------------------------------------------ dequeue
+    def receive_batch(self, agents, max_messages: int, flags: int = 0, copy_out: bool = True,
+                      out_hdr: Optional[np.ndarray] = None, out_payload: Optional[np.ndarray] = None):
+        """Returns (counts[n_agents], headers[total], payload bytes) - views into reusable buffers
+        unless explicit output arrays are given.  copy_out=False leaves results on the device."""
+        if agents is None:
+            a, n = None, 0
+            counts = np.zeros(self.max_agents, np.uint32) if copy_out else None
+        else:
+            a = _arr(agents, np.uint32)
+            n = len(a)
+            counts = np.zeros(n, np.uint32) if copy_out else None
+        total, pbytes = C.c_uint64(0), C.c_uint64(0)
+        hdr = pay = None
+        hdr_cap = pay_cap = 0
+        if copy_out:
+            hdr = out_hdr if out_hdr is not None else self._grow_hdr()
+            pay = out_payload if out_payload is not None else self._grow_pay()
+            hdr_cap, pay_cap = len(hdr), pay.nbytes
+        self._check(self._L.sdb_receive_batch(self._h, n, _p(a), max_messages, flags, _p(counts), _p(hdr), hdr_cap,
+                                              _p(pay), pay_cap, C.cast(C.byref(total), C.c_void_p),
+                                              C.cast(C.byref(pbytes), C.c_void_p)))
+        if not copy_out:
+            return None, total.value, pbytes.value
+        if agents is None:
+            counts = counts[: self.stats_n_agents()]
+        return counts, hdr[: total.value], pay[: pbytes.value]
+
+    def stats_n_agents(self) -> int:
+        return self.stats()["n_agents"]
+
+    def _grow_hdr(self) -> np.ndarray:
+        if len(self._out_hdr) < self.max_recv_records:
+            self._out_hdr = np.zeros(self.max_recv_records, HDR_DTYPE)
+        return self._out_hdr
+
+    def _grow_pay(self) -> np.ndarray:
+        need = int(self.cfg.max_recv_payload) or self.max_recv_records * 256
+        if self._out_pay.nbytes < need:
+            self._out_pay = np.zeros(need, np.uint8)
+        return self._out_pay
+
+    def last_receive_dev(self) -> Tuple[int, int, int]:
+        c, h, p = C.c_void_p(), C.c_void_p(), C.c_void_p()
+        self._check(self._L.sdb_last_receive_dev(self._h, C.byref(c), C.byref(h), C.byref(p)))
+        return c.value, h.value, p.value
+
+    # ------------------------------------------------------------------ backends
+    def set_backends(self, weight, load0=None) -> None:
+        w = _arr(weight, np.uint32)
+        l0 = None if load0 is None else _arr(load0, np.uint64)
+        self._check(self._L.sdb_set_backends(self._h, len(w), _p(w), _p(l0)))
+        self._nb = len(w)
+
+    def backend_loads(self) -> np.ndarray:
+        out = np.zeros(self._nb, np.uint64)
+        self._check(self._L.sdb_get_backend_loads(self._h, self._nb, _p(out)))
+        return out
+
+    def release_backends(self, backend, cost=None) -> None:
+        b = _arr(backend, np.uint32)
+        c = None if cost is None else _arr(cost, np.uint32)
+        self._check(self._L.sdb_release_backends(self._h, len(b), _p(b), _p(c)))
+
+    def select_backends(self, n_req: int, cost=None, mode: int = 0, seed: int = 0) -> np.ndarray:
+        c = None if cost is None else _arr(cost, np.uint32)
+        out = np.zeros(n_req, np.uint32)
+        self._check(self._L.sdb_select_backend_batch(self._h, n_req, _p(c), mode, seed, _p(out)))
+        return out
+
+
+def payload_offsets(hdr: np.ndarray) -> np.ndarray:
+    """Byte offset of each record's payload inside the packed payload stream of a receive."""
+    pl = pad32(hdr["len"].astype(np.int64))
+    off = np.zeros(len(hdr), np.int64)
+    if len(hdr) > 1:
+        np.cumsum(pl[:-1], out=off[1:])
+    return off

@@ -1,0 +1,705 @@
+// sdb_api.cu - host side of the C ABI declared in include/swarmdb_b200.h.
+//
+// Owns: device memory of one shard, the host mirror of the group table (CSR), the global
+// sequence counter, arena space accounting (tail / floor / reclaim), pinned staging for
+// per-send descriptors, and the launch sequence of every entry point.  No CPU data path:
+// every routed byte goes through the kernels in sdb_send.cu / sdb_recv.cu / sdb_balance.cu.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cstdio>
+#include <cstring>
+#include <new>
+#include <string>
+#include <vector>
+
+#include "sdb_common.cuh"
+
+extern "C" {
+cudaError_t sdb_launch_p2p(const sdb_dev_view*, const sdb_send_desc*, uint32_t, const uint8_t*, uint64_t, uint64_t, int, cudaStream_t, sdb_profiler*);
+cudaError_t sdb_launch_fanout(const sdb_dev_view*, const sdb_send_desc*, uint32_t, const uint8_t*, const uint32_t*,
+                              uint64_t, uint64_t, uint32_t, int, int, cudaStream_t, sdb_profiler*);
+cudaError_t sdb_launch_commit(const sdb_dev_view*, uint32_t, uint32_t, cudaStream_t, sdb_profiler*);
+cudaError_t sdb_launch_receive(const sdb_dev_view*, const sdb_recv_args*, cudaStream_t, int*, sdb_profiler*);
+cudaError_t sdb_launch_arena_floor(const sdb_dev_view*, uint32_t, uint32_t, unsigned long long*, cudaStream_t);
+cudaError_t sdb_launch_pick(int mode, uint32_t n_backends, const uint32_t* weight_dev, unsigned long long* load_dev,
+                            uint32_t n_req, const uint32_t* cost_dev, uint64_t seed, uint32_t* out_dev,
+                            unsigned long long* scratch_dev, const uint32_t* log_tab_dev,
+                            cudaStream_t stream, int* n_launches);
+void sdb_build_log2_table(uint32_t* tab257);
+}
+
+#define SDB_SCAN_TILE 4096u
+
+struct sdb_staged {
+  uint32_t kind = 0;          // 0 p2p, 1 group, 2 list
+  uint32_t n = 0;
+  uint64_t total_recs = 0;    // sequence numbers consumed
+  uint64_t total_grans = 0;   // arena granules consumed
+  uint32_t max_padlen = 0;
+  sdb_send_desc* descs_dev = nullptr;
+  uint8_t* payload_dev = nullptr;
+  uint32_t* list_dev = nullptr;
+  bool owns = false;          // device buffers owned by this object (else the handle's staging)
+};
+
+struct sdb_ctx {
+  sdb_config cfg{};
+  int sm_count = 148;
+  cudaStream_t stream = nullptr;
+  bool own_stream = false;
+  sdb_dev_view view{};
+  // device buffers
+  uint8_t* arena = nullptr;
+  uint64_t* ring_state = nullptr;
+  uint32_t* ring_handle = nullptr;
+  uint16_t* ring_meta = nullptr;
+  uint32_t* ctail = nullptr;
+  uint32_t* ntomb = nullptr;
+  uint32_t* members = nullptr;
+  sdb_dev_counters* ctr = nullptr;
+  // staging for non-staged sends
+  sdb_send_desc* descs_host = nullptr;   // pinned
+  sdb_staged scratch;                    // device descs/payload/list owned by the handle
+  uint32_t* list_host = nullptr;         // pinned
+  cudaEvent_t staging_free = nullptr;    // previous H2D of pinned staging has completed
+  // receive scratch + outputs
+  uint32_t* rx_agent = nullptr; uint32_t* rx_cnt = nullptr; uint32_t* rx_rec_local = nullptr; uint32_t* rx_rec_tops = nullptr;
+  uint32_t* rx_pay = nullptr; uint32_t* rx_pay_local = nullptr; uint32_t* rx_pay_tops = nullptr;
+  uint32_t* rx_old_head = nullptr; uint32_t* rx_new_head = nullptr; uint32_t* rx_new_ntomb = nullptr;
+  uint32_t* rx_sel_pos = nullptr; unsigned long long* rx_totals = nullptr;
+  uint32_t* rx_count = nullptr; sdb_msg_header* rx_hdr = nullptr; uint8_t* rx_payload = nullptr;
+  unsigned long long* totals_host = nullptr;   // pinned [4]
+  uint64_t pay_cap_gran = 0;
+  // backends
+  uint32_t* be_weight = nullptr; unsigned long long* be_load = nullptr; uint32_t n_backends = 0;
+  uint32_t* be_req_cost = nullptr; uint32_t* be_out = nullptr; unsigned long long* be_scratch = nullptr;
+  uint32_t* be_logtab = nullptr; uint32_t be_req_cap = 0;
+  // host state
+  uint64_t next_seq = 1;       // ids start at 1 like the deterministic-uuid reference counter
+  uint64_t arena_tail = 0;     // granules, monotonic
+  uint64_t arena_floor = 0;    // granules
+  uint64_t arena_grans = 0;
+  uint32_t n_agents = 0;       // watermark
+  std::vector<uint64_t> gstart; std::vector<uint32_t> gcount; std::vector<uint8_t> gdefined;
+  uint64_t member_used = 0;
+  std::vector<std::vector<uint32_t>> ghost;   // authoritative member lists (for pool compaction)
+  uint64_t launches = 0;
+  uint64_t picks = 0;
+  uint64_t seen_overflow = 0;
+  sdb_profiler prof{};
+  std::string err;
+};
+
+namespace {
+
+int fail(sdb_ctx* h, int code, const std::string& msg) {
+  if (h) h->err = msg;
+  return code;
+}
+#define CUDA_TRY(h, expr)                                                                       \
+  do {                                                                                          \
+    cudaError_t _e = (expr);                                                                    \
+    if (_e != cudaSuccess)                                                                      \
+      return fail(h, SDB_ECUDA, std::string(#expr) + ": " + cudaGetErrorString(_e));            \
+  } while (0)
+
+bool is_pow2(uint64_t x) { return x && !(x & (x - 1)); }
+uint32_t ilog2(uint64_t x) { uint32_t r = 0; while ((1ull << r) < x) ++r; return r; }
+inline uint32_t pad32(uint32_t len) { return (len + 31u) & ~31u; }
+
+template <typename T>
+cudaError_t dmalloc(T** p, size_t n) { return cudaMalloc(reinterpret_cast<void**>(p), n * sizeof(T)); }
+
+// Make room for `need` granules in the arena; may run the floor-reclaim kernel (synchronises).
+int arena_reserve(sdb_ctx* h, uint64_t need, uint64_t* base_out) {
+  const uint64_t G = h->arena_grans;
+  if (need > G) return fail(h, SDB_EARENA_FULL, "batch larger than the whole arena");
+  uint64_t tail = h->arena_tail;
+  if ((tail & (G - 1)) + need > G) tail = (tail + G - 1) & ~(G - 1);     // a batch never straddles the wrap
+  if (tail + need - h->arena_floor > G) {
+    // reclaim: recompute the floor from the oldest pending record of every ring
+    cudaError_t e = sdb_launch_arena_floor(&h->view, h->n_agents, static_cast<uint32_t>(h->arena_tail),
+                                           h->rx_totals + 2, h->stream);
+    h->launches += 1;
+    if (e == cudaSuccess) e = cudaMemcpyAsync(h->totals_host + 2, h->rx_totals + 2, sizeof(unsigned long long),
+                                             cudaMemcpyDeviceToHost, h->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
+    if (e != cudaSuccess) return fail(h, SDB_ECUDA, std::string("arena floor: ") + cudaGetErrorString(e));
+    h->arena_floor = h->arena_tail - h->totals_host[2];
+    if (tail + need - h->arena_floor > G)
+      return fail(h, SDB_EARENA_FULL, "message arena full: unconsumed messages pin the log (receive or enlarge arena_bytes)");
+  }
+  *base_out = tail;
+  return SDB_OK;
+}
+
+struct SendArrays {
+  const uint32_t* sender; const uint32_t* second; const uint8_t* prio; const uint8_t* type; const uint16_t* len;
+  const uint64_t* payload_off; const double* timestamp;
+  const uint8_t* kind = nullptr;      // mixed batches only
+  uint32_t n_lists = 0;               // mixed batches only
+  uint32_t* p2p_list = nullptr;       // mixed batches: where single receivers are appended (pinned list staging)
+  uint64_t p2p_list_base = 0, p2p_list_cap = 0, p2p_list_used = 0;
+};
+
+// Build descriptors into `out` (host).  kind 0: second = receiver; 1: second = group idx;
+// 2: list (list_off/list base offsets supplied).  Returns totals through the staged object.
+int build_descs(sdb_ctx* h, uint32_t batch_kind, uint32_t n, SendArrays& a, const uint64_t* list_off,
+                uint64_t payload_bytes, sdb_send_desc* out, sdb_staged* s) {
+  uint64_t rec = 0, gran = 0;
+  uint32_t max_padlen = 0;
+  const uint32_t A = h->cfg.max_agents;
+  for (uint32_t i = 0; i < n; ++i) {
+    sdb_send_desc d;
+    std::memset(&d, 0, sizeof(d));
+    const uint32_t len = a.len[i];
+    if (len > h->cfg.max_payload_bytes) return fail(h, SDB_EINVAL, "payload longer than max_payload_bytes");
+    const uint64_t off = a.payload_off ? a.payload_off[i] : 0;
+    if (off & 15u) return fail(h, SDB_EINVAL, "payload_off must be 16-byte aligned");
+    if (off + len > payload_bytes) return fail(h, SDB_EINVAL, "payload_off + len beyond payload_bytes");
+    if (a.sender[i] >= A) return fail(h, SDB_EINVAL, "sender index out of range");
+    if ((a.prio ? a.prio[i] : 1) > 3) return fail(h, SDB_EINVAL, "priority out of range");
+    const uint32_t pl = pad32(len);
+    max_padlen = std::max(max_padlen, pl);
+    d.payload_off = off;
+    d.timestamp = a.timestamp ? a.timestamp[i] : 0.0;
+    d.sender = a.sender[i];
+    d.len = static_cast<uint16_t>(len);
+    d.prio = a.prio ? a.prio[i] : 1;
+    d.type = a.type ? a.type[i] : 0;
+    d.rgran = 1u + pl / SDB_GRANULE;
+    d.group = SDB_NO_GROUP;
+    if (rec > 0xFFFFFFFFull || gran > 0xFFFFFFFFull) return fail(h, SDB_ECAPACITY, "batch exceeds 2^32 records/granules");
+    d.rec0 = static_cast<uint32_t>(rec);
+    d.gran0 = static_cast<uint32_t>(gran);
+    uint32_t kind = batch_kind;
+    if (batch_kind == 3) {
+      kind = a.kind[i];
+      if (kind > 2) return fail(h, SDB_EINVAL, "kind must be 0, 1 or 2");
+      if (kind == 0) {      // p2p inside a mixed batch: a one-entry temporary list through the fan-out kernel
+        if (a.second[i] >= A) return fail(h, SDB_EINVAL, "receiver index out of range");
+        if (a.p2p_list_used >= a.p2p_list_cap) return fail(h, SDB_ECAPACITY, "recipient lists exceed list_pool_entries");
+        a.p2p_list[a.p2p_list_used] = a.second[i];
+        h->n_agents = std::max(h->n_agents, a.second[i] + 1);
+        d.mstart = static_cast<uint32_t>(a.p2p_list_base + a.p2p_list_used); d.mcount = 1; d.flags = SDB_DESC_LIST_TEMP;
+        a.p2p_list_used++;
+        rec += 1; gran += d.rgran;
+        out[i] = d;
+        continue;
+      }
+      if (kind == 2 && a.second[i] >= a.n_lists) return fail(h, SDB_EINVAL, "list number out of range");
+    }
+    if (kind == 0) {
+      if (a.second[i] >= A) return fail(h, SDB_EINVAL, "receiver index out of range");
+      h->n_agents = std::max(h->n_agents, a.second[i] + 1);     // auto-registration of the receiver (M:423-427)
+      d.mstart = a.second[i]; d.mcount = 1; d.flags = 0;
+      rec += 1; gran += d.rgran;
+    } else if (kind == 1) {
+      const uint32_t g = a.second[i];
+      if (g >= h->cfg.max_groups || !h->gdefined[g]) return fail(h, SDB_ENOTFOUND, "unknown group index");
+      d.mstart = static_cast<uint32_t>(h->gstart[g]); d.mcount = h->gcount[g]; d.group = g;
+      d.flags = SDB_DESC_SKIP_SENDER;
+      rec += d.mcount; gran += static_cast<uint64_t>(d.mcount) * d.rgran;
+    } else {
+      const uint32_t li = batch_kind == 3 ? a.second[i] : i;
+      const uint64_t b = list_off[li], e = list_off[li + 1];
+      if (e < b || e - b > 0xFFFFFFFFull) return fail(h, SDB_EINVAL, "bad list_off");
+      d.mstart = static_cast<uint32_t>(b); d.mcount = static_cast<uint32_t>(e - b);
+      d.flags = SDB_DESC_SHARED_SEQ | SDB_DESC_LIST_TEMP;
+      rec += 1; gran += static_cast<uint64_t>(d.mcount) * d.rgran;
+    }
+    out[i] = d;
+  }
+  s->kind = batch_kind; s->n = n; s->total_recs = rec; s->total_grans = gran; s->max_padlen = max_padlen;
+  return SDB_OK;
+}
+
+int submit(sdb_ctx* h, const sdb_staged* s, uint64_t* seq_base_out) {
+  if (seq_base_out) *seq_base_out = h->next_seq;
+  if (s->n == 0) return SDB_OK;
+  uint64_t base = 0;
+  int rc = arena_reserve(h, s->total_grans, &base);
+  if (rc != SDB_OK) return rc;
+  cudaError_t e;
+  if (s->kind == 0) {
+    e = sdb_launch_p2p(&h->view, s->descs_dev, s->n, s->payload_dev, h->next_seq, base, h->sm_count, h->stream, &h->prof);
+  } else {
+    e = sdb_launch_fanout(&h->view, s->descs_dev, s->n, s->payload_dev, s->list_dev, h->next_seq, base,
+                          s->max_padlen, static_cast<int>(h->cfg.fanout_variant), h->sm_count, h->stream, &h->prof);
+  }
+  if (e == cudaSuccess) e = sdb_launch_commit(&h->view, h->n_agents, static_cast<uint32_t>(base), h->stream, &h->prof);
+  h->launches += 2;
+  if (e != cudaSuccess) return fail(h, SDB_ECUDA, std::string("enqueue launch: ") + cudaGetErrorString(e));
+  h->next_seq += s->total_recs;
+  h->arena_tail = base + s->total_grans;
+  return SDB_OK;
+}
+
+int send_common(sdb_ctx* h, uint32_t kind, uint32_t n, SendArrays& a, const uint64_t* list_off,
+                const uint32_t* list_idx, const uint8_t* payload, uint64_t payload_bytes, uint64_t* seq_base_out) {
+  if (!h) return SDB_EINVAL;
+  if (n == 0) { if (seq_base_out) *seq_base_out = h->next_seq; return SDB_OK; }
+  if (!a.sender || !a.len || (kind != 2 && !a.second) || (kind == 3 && !a.kind)) return fail(h, SDB_EINVAL, "null array");
+  if (n > h->cfg.max_batch_sends) return fail(h, SDB_ECAPACITY, "n exceeds max_batch_sends");
+  if (payload_bytes > h->cfg.max_batch_payload) return fail(h, SDB_ECAPACITY, "payload_bytes exceeds max_batch_payload");
+  if (payload_bytes && !payload) return fail(h, SDB_EINVAL, "null payload");
+  CUDA_TRY(h, cudaEventSynchronize(h->staging_free));     // pinned descriptor staging is reusable
+  sdb_staged* s = &h->scratch;
+  uint64_t list_total = 0;
+  if (kind == 2 || kind == 3) {
+    const uint32_t nl = kind == 2 ? n : a.n_lists;
+    list_total = (nl && list_off) ? list_off[nl] : 0;
+    const uint64_t cap = h->cfg.list_pool_entries;
+    if (list_total > cap) return fail(h, SDB_ECAPACITY, "recipient lists exceed list_pool_entries");
+    for (uint64_t k = 0; k < list_total; ++k) {
+      if (list_idx[k] >= h->cfg.max_agents) return fail(h, SDB_EINVAL, "recipient index out of range");
+      h->n_agents = std::max(h->n_agents, list_idx[k] + 1);
+    }
+    if (list_total) std::memcpy(h->list_host, list_idx, list_total * sizeof(uint32_t));
+    a.p2p_list = h->list_host + list_total; a.p2p_list_base = list_total; a.p2p_list_cap = cap - list_total;
+  }
+  int rc = build_descs(h, kind, n, a, list_off, payload_bytes, h->descs_host, s);
+  if (rc != SDB_OK) return rc;
+  list_total += a.p2p_list_used;
+  if (list_total)
+    CUDA_TRY(h, cudaMemcpyAsync(s->list_dev, h->list_host, list_total * sizeof(uint32_t), cudaMemcpyHostToDevice, h->stream));
+  CUDA_TRY(h, cudaMemcpyAsync(s->descs_dev, h->descs_host, static_cast<size_t>(n) * sizeof(sdb_send_desc),
+                              cudaMemcpyHostToDevice, h->stream));
+  if (payload_bytes)   // straight from the caller's buffer (pinned memory makes this a true async DMA)
+    CUDA_TRY(h, cudaMemcpyAsync(s->payload_dev, payload, payload_bytes, cudaMemcpyHostToDevice, h->stream));
+  CUDA_TRY(h, cudaEventRecord(h->staging_free, h->stream));
+  return submit(h, s, seq_base_out);
+}
+
+}  // namespace
+
+// =============================================================================================
+extern "C" {
+
+int sdb_abi_version(void) { return static_cast<int>(SDB_ABI_VERSION); }
+
+const char* sdb_last_error(sdb_handle h) { return h ? h->err.c_str() : "null handle"; }
+
+int sdb_create(const sdb_config* cfg, sdb_handle* out) {
+  if (!cfg || !out) return SDB_EINVAL;
+  *out = nullptr;
+  if (cfg->struct_bytes != sizeof(sdb_config)) return SDB_EINVAL;
+  sdb_ctx* h = new (std::nothrow) sdb_ctx();
+  if (!h) return SDB_ENOMEM;
+  *out = h;                       // returned even on failure so sdb_last_error works; caller destroys
+  h->cfg = *cfg;
+  sdb_config& c = h->cfg;
+  if (c.num_shards == 0) c.num_shards = 1;
+  if (!is_pow2(c.ring_slots) || c.ring_slots < 2 || c.ring_slots > (1u << 24)) return fail(h, SDB_EINVAL, "ring_slots must be a power of two in [2, 2^24]");
+  if (!is_pow2(c.arena_bytes) || c.arena_bytes < (1u << 16) || c.arena_bytes > (1ull << 37)) return fail(h, SDB_EINVAL, "arena_bytes must be a power of two in [64 KiB, 128 GiB]");
+  if (c.max_agents == 0 || c.max_agents > (1u << 30)) return fail(h, SDB_EINVAL, "max_agents out of range");
+  if (c.max_payload_bytes == 0 || c.max_payload_bytes > 65504) return fail(h, SDB_EINVAL, "max_payload_bytes must be in [1, 65504]");
+  if (c.max_groups == 0) c.max_groups = 1;
+  if (c.member_pool_entries == 0) c.member_pool_entries = 1;
+  if (c.max_backends == 0) c.max_backends = 256;
+  if (c.max_batch_sends == 0) c.max_batch_sends = 65536;
+  if (c.max_batch_payload == 0) c.max_batch_payload = static_cast<uint64_t>(c.max_batch_sends) * pad32(std::min(c.max_payload_bytes, 256u));
+  if (c.max_recv_records == 0) c.max_recv_records = 1u << 20;
+  if (c.max_recv_records > 0xFFFFFFF0ull) return fail(h, SDB_EINVAL, "max_recv_records too large");
+  if (c.max_recv_payload == 0) c.max_recv_payload = c.max_recv_records * 256ull;
+  if (c.list_pool_entries == 0) c.list_pool_entries = 2ull * c.max_agents + 1024;
+  if (c.fanout_variant > 1) return fail(h, SDB_EINVAL, "fanout_variant must be 0 or 1");
+
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
+    return fail(h, SDB_ECUDA, "no CUDA device: swarmdb_b200 has no CPU fallback");
+  if (c.device < 0 || c.device >= ndev) return fail(h, SDB_EINVAL, "device ordinal out of range");
+  CUDA_TRY(h, cudaSetDevice(c.device));
+  cudaDeviceProp prop;
+  CUDA_TRY(h, cudaGetDeviceProperties(&prop, c.device));
+  h->sm_count = prop.multiProcessorCount;
+  CUDA_TRY(h, cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+  h->own_stream = true;
+  CUDA_TRY(h, cudaEventCreateWithFlags(&h->staging_free, cudaEventDisableTiming));
+
+  const size_t A = c.max_agents, R = c.ring_slots;
+  h->arena_grans = c.arena_bytes / SDB_GRANULE;
+  CUDA_TRY(h, dmalloc(&h->arena, c.arena_bytes));
+  CUDA_TRY(h, dmalloc(&h->ring_state, A));
+  CUDA_TRY(h, dmalloc(&h->ring_handle, A * R));
+  CUDA_TRY(h, dmalloc(&h->ring_meta, A * R));
+  CUDA_TRY(h, dmalloc(&h->ctail, A));
+  CUDA_TRY(h, dmalloc(&h->ntomb, A));
+  CUDA_TRY(h, dmalloc(&h->members, c.member_pool_entries));
+  CUDA_TRY(h, dmalloc(&h->ctr, 1));
+  CUDA_TRY(h, cudaMemsetAsync(h->ring_state, 0, A * sizeof(uint64_t), h->stream));
+  CUDA_TRY(h, cudaMemsetAsync(h->ring_meta, 0xFF, A * R * sizeof(uint16_t), h->stream));
+  CUDA_TRY(h, cudaMemsetAsync(h->ctail, 0, A * sizeof(uint32_t), h->stream));
+  CUDA_TRY(h, cudaMemsetAsync(h->ntomb, 0, A * sizeof(uint32_t), h->stream));
+  CUDA_TRY(h, cudaMemsetAsync(h->ctr, 0, sizeof(sdb_dev_counters), h->stream));
+
+  // send staging
+  CUDA_TRY(h, cudaHostAlloc(reinterpret_cast<void**>(&h->descs_host), static_cast<size_t>(c.max_batch_sends) * sizeof(sdb_send_desc), cudaHostAllocDefault));
+  CUDA_TRY(h, cudaHostAlloc(reinterpret_cast<void**>(&h->list_host), c.list_pool_entries * sizeof(uint32_t), cudaHostAllocDefault));
+  CUDA_TRY(h, dmalloc(&h->scratch.descs_dev, c.max_batch_sends));
+  CUDA_TRY(h, dmalloc(&h->scratch.payload_dev, c.max_batch_payload + 64));
+  CUDA_TRY(h, dmalloc(&h->scratch.list_dev, c.list_pool_entries));
+  CUDA_TRY(h, cudaMemsetAsync(h->scratch.payload_dev, 0, c.max_batch_payload + 64, h->stream));
+
+  // receive scratch
+  const size_t tiles = (A + SDB_SCAN_TILE - 1) / SDB_SCAN_TILE + 1;
+  CUDA_TRY(h, dmalloc(&h->rx_agent, A)); CUDA_TRY(h, dmalloc(&h->rx_cnt, A));
+  CUDA_TRY(h, dmalloc(&h->rx_rec_local, A)); CUDA_TRY(h, dmalloc(&h->rx_rec_tops, tiles));
+  CUDA_TRY(h, dmalloc(&h->rx_pay, A)); CUDA_TRY(h, dmalloc(&h->rx_pay_local, A)); CUDA_TRY(h, dmalloc(&h->rx_pay_tops, tiles));
+  CUDA_TRY(h, dmalloc(&h->rx_old_head, A)); CUDA_TRY(h, dmalloc(&h->rx_new_head, A)); CUDA_TRY(h, dmalloc(&h->rx_new_ntomb, A));
+  CUDA_TRY(h, dmalloc(&h->rx_sel_pos, c.max_recv_records));
+  CUDA_TRY(h, dmalloc(&h->rx_totals, 4));
+  CUDA_TRY(h, dmalloc(&h->rx_count, A));
+  CUDA_TRY(h, dmalloc(&h->rx_hdr, c.max_recv_records));
+  h->pay_cap_gran = (c.max_recv_payload + SDB_GRANULE - 1) / SDB_GRANULE;
+  CUDA_TRY(h, dmalloc(&h->rx_payload, h->pay_cap_gran * SDB_GRANULE));
+  CUDA_TRY(h, cudaHostAlloc(reinterpret_cast<void**>(&h->totals_host), 4 * sizeof(unsigned long long), cudaHostAllocDefault));
+
+  // backends
+  CUDA_TRY(h, dmalloc(&h->be_weight, c.max_backends));
+  CUDA_TRY(h, dmalloc(&h->be_load, c.max_backends));
+  CUDA_TRY(h, dmalloc(&h->be_scratch, static_cast<size_t>(c.max_backends) * 4 + 16));
+  CUDA_TRY(h, dmalloc(&h->be_logtab, 257));
+  {
+    uint32_t tab[257];
+    sdb_build_log2_table(tab);
+    CUDA_TRY(h, cudaMemcpyAsync(h->be_logtab, tab, sizeof(tab), cudaMemcpyHostToDevice, h->stream));
+    CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+  }
+
+  h->gstart.assign(c.max_groups, 0); h->gcount.assign(c.max_groups, 0); h->gdefined.assign(c.max_groups, 0);
+  h->ghost.resize(c.max_groups);
+
+  sdb_dev_view& v = h->view;
+  v.arena = h->arena; v.ring_state = h->ring_state; v.ring_handle = h->ring_handle; v.ring_meta = h->ring_meta;
+  v.ctail = h->ctail; v.ntomb = h->ntomb; v.members = h->members; v.ctr = h->ctr;
+  v.gmask = h->arena_grans - 1; v.ring_slots = c.ring_slots; v.ring_shift = ilog2(c.ring_slots); v.max_agents = c.max_agents;
+  CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+  return SDB_OK;
+}
+
+int sdb_destroy(sdb_handle h) {
+  if (!h) return SDB_EINVAL;
+  cudaSetDevice(h->cfg.device);
+  if (h->stream) cudaStreamSynchronize(h->stream);
+  void* dev[] = {h->arena, h->ring_state, h->ring_handle, h->ring_meta, h->ctail, h->ntomb, h->members, h->ctr,
+                 h->scratch.descs_dev, h->scratch.payload_dev, h->scratch.list_dev, h->rx_agent, h->rx_cnt,
+                 h->rx_rec_local, h->rx_rec_tops, h->rx_pay, h->rx_pay_local, h->rx_pay_tops, h->rx_old_head,
+                 h->rx_new_head, h->rx_new_ntomb, h->rx_sel_pos, h->rx_totals, h->rx_count, h->rx_hdr, h->rx_payload,
+                 h->be_weight, h->be_load, h->be_scratch, h->be_logtab, h->be_req_cost, h->be_out};
+  for (void* p : dev) if (p) cudaFree(p);
+  if (h->descs_host) cudaFreeHost(h->descs_host);
+  if (h->list_host) cudaFreeHost(h->list_host);
+  if (h->totals_host) cudaFreeHost(h->totals_host);
+  if (h->staging_free) cudaEventDestroy(h->staging_free);
+  if (h->prof.cap) {
+    for (int i = 0; i < h->prof.cap; ++i) { cudaEventDestroy(h->prof.ev_a[i]); cudaEventDestroy(h->prof.ev_b[i]); }
+    delete[] h->prof.kind; delete[] h->prof.ev_a; delete[] h->prof.ev_b;
+  }
+  if (h->own_stream && h->stream) cudaStreamDestroy(h->stream);
+  delete h;
+  return SDB_OK;
+}
+
+int sdb_set_stream(sdb_handle h, void* cuda_stream) {
+  if (!h) return SDB_EINVAL;
+  CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+  if (h->own_stream) { cudaStreamDestroy(h->stream); h->own_stream = false; }
+  h->stream = static_cast<cudaStream_t>(cuda_stream);
+  return SDB_OK;
+}
+
+int sdb_sync(sdb_handle h) {
+  if (!h) return SDB_EINVAL;
+  CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+  return SDB_OK;
+}
+
+int sdb_profile(sdb_handle h, int enable) {
+  if (!h) return SDB_EINVAL;
+  sdb_profiler& p = h->prof;
+  if (enable && !p.cap) {
+    p.cap = 8192;
+    p.kind = new int[p.cap]; p.ev_a = new cudaEvent_t[p.cap]; p.ev_b = new cudaEvent_t[p.cap];
+    for (int i = 0; i < p.cap; ++i) { CUDA_TRY(h, cudaEventCreate(&p.ev_a[i])); CUDA_TRY(h, cudaEventCreate(&p.ev_b[i])); }
+  }
+  p.enabled = enable ? 1 : 0;
+  if (enable) p.n = 0;
+  return SDB_OK;
+}
+
+int sdb_profile_read(sdb_handle h, double* ms_out, uint64_t* count_out) {
+  if (!h || !ms_out || !count_out) return SDB_EINVAL;
+  for (int k = 0; k < SDB_PK_N; ++k) { ms_out[k] = 0.0; count_out[k] = 0; }
+  CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+  sdb_profiler& p = h->prof;
+  for (int i = 0; i < p.n; ++i) {
+    float ms = 0.f;
+    if (cudaEventElapsedTime(&ms, p.ev_a[i], p.ev_b[i]) == cudaSuccess && p.kind[i] < SDB_PK_N) {
+      ms_out[p.kind[i]] += ms; count_out[p.kind[i]] += 1;
+    }
+  }
+  p.n = 0;
+  return SDB_OK;
+}
+
+int sdb_get_stats(sdb_handle h, sdb_stats* out) {
+  if (!h || !out) return SDB_EINVAL;
+  sdb_dev_counters c;
+  CUDA_TRY(h, cudaMemcpyAsync(&c, h->ctr, sizeof(c), cudaMemcpyDeviceToHost, h->stream));
+  CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+  out->next_seq = h->next_seq; out->enqueued = c.enqueued; out->delivered = c.delivered;
+  out->ring_overflow = c.ring_overflow; out->skipped_sender = c.skipped_sender;
+  out->arena_tail_bytes = h->arena_tail * SDB_GRANULE; out->arena_floor_bytes = h->arena_floor * SDB_GRANULE;
+  out->n_agents = h->n_agents; out->kernel_launches = h->launches; out->backend_picks = h->picks;
+  return SDB_OK;
+}
+
+int sdb_register_agents(sdb_handle h, uint32_t n, const uint32_t* agent_idx) {
+  if (!h || (n && !agent_idx)) return SDB_EINVAL;
+  for (uint32_t i = 0; i < n; ++i) {
+    if (agent_idx[i] >= h->cfg.max_agents) return fail(h, SDB_EINVAL, "agent index >= max_agents");
+    h->n_agents = std::max(h->n_agents, agent_idx[i] + 1);
+  }
+  return SDB_OK;
+}
+
+int sdb_deregister_agents(sdb_handle h, uint32_t n, const uint32_t* agent_idx) {
+  if (!h || (n && !agent_idx)) return SDB_EINVAL;
+  for (uint32_t i = 0; i < n; ++i)
+    if (agent_idx[i] >= h->cfg.max_agents) return fail(h, SDB_EINVAL, "agent index >= max_agents");
+  return SDB_OK;   // ring and read position are kept (consumer-group offsets survive close, App. A rule 11)
+}
+
+int sdb_create_group(sdb_handle h, uint32_t g, uint32_t n_members, const uint32_t* member_idx) {
+  if (!h || (n_members && !member_idx)) return SDB_EINVAL;
+  if (g >= h->cfg.max_groups) return fail(h, SDB_EINVAL, "group index >= max_groups");
+  for (uint32_t i = 0; i < n_members; ++i) {
+    if (member_idx[i] >= h->cfg.max_agents) return fail(h, SDB_EINVAL, "member index >= max_agents");
+    h->n_agents = std::max(h->n_agents, member_idx[i] + 1);   // members will receive: keep them inside the commit sweep
+  }
+  if (h->member_used + n_members > h->cfg.member_pool_entries) {
+    // compact: rewrite every live group from the host mirror
+    h->ghost[g].assign(member_idx, member_idx + n_members);
+    h->gdefined[g] = 1;
+    uint64_t used = 0;
+    for (uint32_t k = 0; k < h->cfg.max_groups; ++k) if (h->gdefined[k]) used += h->ghost[k].size();
+    if (used > h->cfg.member_pool_entries) { h->gdefined[g] = 0; return fail(h, SDB_ECAPACITY, "member pool exhausted"); }
+    CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+    std::vector<uint32_t> flat; flat.reserve(used);
+    for (uint32_t k = 0; k < h->cfg.max_groups; ++k) if (h->gdefined[k]) {
+      h->gstart[k] = flat.size(); h->gcount[k] = static_cast<uint32_t>(h->ghost[k].size());
+      flat.insert(flat.end(), h->ghost[k].begin(), h->ghost[k].end());
+    }
+    if (!flat.empty()) CUDA_TRY(h, cudaMemcpy(h->members, flat.data(), flat.size() * sizeof(uint32_t), cudaMemcpyHostToDevice));
+    h->member_used = flat.size();
+    return SDB_OK;
+  }
+  h->ghost[g].assign(member_idx, member_idx + n_members);
+  h->gstart[g] = h->member_used; h->gcount[g] = n_members; h->gdefined[g] = 1;
+  if (n_members) {
+    // pageable source: cudaMemcpyAsync stages it before returning, ordering after earlier kernels on the stream
+    CUDA_TRY(h, cudaMemcpyAsync(h->members + h->member_used, h->ghost[g].data(), n_members * sizeof(uint32_t),
+                                cudaMemcpyHostToDevice, h->stream));
+  }
+  h->member_used += n_members;
+  if (h->member_used > 0xFFFFFFFFull) return fail(h, SDB_ECAPACITY, "member pool beyond 2^32 entries");
+  return SDB_OK;
+}
+
+int sdb_send_batch(sdb_handle h, uint32_t n, const uint32_t* sender, const uint32_t* receiver, const uint8_t* prio,
+                   const uint8_t* type, const uint16_t* len, const uint64_t* payload_off, const uint8_t* payload,
+                   uint64_t payload_bytes, const double* timestamp, uint64_t* seq_base_out) {
+  SendArrays a{sender, receiver, prio, type, len, payload_off, timestamp};
+  return send_common(h, 0, n, a, nullptr, nullptr, payload, payload_bytes, seq_base_out);
+}
+
+int sdb_send_group_batch(sdb_handle h, uint32_t n, const uint32_t* sender, const uint32_t* group_idx, const uint8_t* prio,
+                         const uint8_t* type, const uint16_t* len, const uint64_t* payload_off, const uint8_t* payload,
+                         uint64_t payload_bytes, const double* timestamp, uint64_t* seq_base_out) {
+  SendArrays a{sender, group_idx, prio, type, len, payload_off, timestamp};
+  return send_common(h, 1, n, a, nullptr, nullptr, payload, payload_bytes, seq_base_out);
+}
+
+int sdb_send_list_batch(sdb_handle h, uint32_t n, const uint32_t* sender, const uint64_t* list_off, const uint32_t* list_idx,
+                        const uint8_t* prio, const uint8_t* type, const uint16_t* len, const uint64_t* payload_off,
+                        const uint8_t* payload, uint64_t payload_bytes, const double* timestamp, uint64_t* seq_base_out) {
+  if (n && (!list_off || (list_off[n] && !list_idx))) return fail(h, SDB_EINVAL, "null list arrays");
+  SendArrays a{sender, nullptr, prio, type, len, payload_off, timestamp};
+  return send_common(h, 2, n, a, list_off, list_idx, payload, payload_bytes, seq_base_out);
+}
+
+int sdb_send_mixed_batch(sdb_handle h, uint32_t n, const uint32_t* sender, const uint8_t* kind, const uint32_t* target,
+                         uint32_t n_lists, const uint64_t* list_off, const uint32_t* list_idx, const uint8_t* prio,
+                         const uint8_t* type, const uint16_t* len, const uint64_t* payload_off, const uint8_t* payload,
+                         uint64_t payload_bytes, const double* timestamp, uint64_t* seq_base_out) {
+  if (!h) return SDB_EINVAL;
+  if (n_lists && (!list_off || (list_off[n_lists] && !list_idx))) return fail(h, SDB_EINVAL, "null list arrays");
+  SendArrays a{sender, target, prio, type, len, payload_off, timestamp};
+  a.kind = kind; a.n_lists = n_lists;
+  return send_common(h, 3, n, a, list_off, list_idx, payload, payload_bytes, seq_base_out);
+}
+
+int sdb_stage_batch(sdb_handle h, uint32_t kind, uint32_t n, const uint32_t* sender, const uint32_t* second,
+                    const uint8_t* prio, const uint8_t* type, const uint16_t* len, const uint64_t* payload_off,
+                    const uint8_t* payload, uint64_t payload_bytes, const double* timestamp, sdb_staged_t* out) {
+  if (!h || !out || kind > 1) return SDB_EINVAL;
+  *out = nullptr;
+  if (n == 0 || !sender || !second || !len) return fail(h, SDB_EINVAL, "empty or null batch");
+  sdb_staged* s = new (std::nothrow) sdb_staged();
+  if (!s) return SDB_ENOMEM;
+  s->owns = true;
+  std::vector<sdb_send_desc> descs(n);
+  SendArrays a{sender, second, prio, type, len, payload_off, timestamp};
+  int rc = build_descs(h, kind, n, a, nullptr, payload_bytes, descs.data(), s);
+  if (rc != SDB_OK) { delete s; return rc; }
+  cudaError_t e = dmalloc(&s->descs_dev, n);
+  if (e == cudaSuccess) e = dmalloc(&s->payload_dev, payload_bytes + 64);
+  if (e == cudaSuccess) e = cudaMemset(s->payload_dev, 0, payload_bytes + 64);
+  if (e == cudaSuccess) e = cudaMemcpy(s->descs_dev, descs.data(), static_cast<size_t>(n) * sizeof(sdb_send_desc), cudaMemcpyHostToDevice);
+  if (e == cudaSuccess && payload_bytes) e = cudaMemcpy(s->payload_dev, payload, payload_bytes, cudaMemcpyHostToDevice);
+  if (e != cudaSuccess) {
+    if (s->descs_dev) cudaFree(s->descs_dev);
+    if (s->payload_dev) cudaFree(s->payload_dev);
+    delete s;
+    return fail(h, SDB_ECUDA, std::string("stage: ") + cudaGetErrorString(e));
+  }
+  *out = s;
+  return SDB_OK;
+}
+
+int sdb_submit_staged(sdb_handle h, sdb_staged_t s, uint64_t* seq_base_out) {
+  if (!h || !s) return SDB_EINVAL;
+  return submit(h, s, seq_base_out);
+}
+
+int sdb_free_staged(sdb_handle h, sdb_staged_t s) {
+  if (!h || !s) return SDB_EINVAL;
+  cudaStreamSynchronize(h->stream);
+  if (s->owns) { cudaFree(s->descs_dev); cudaFree(s->payload_dev); }
+  delete s;
+  return SDB_OK;
+}
+
+int sdb_receive_batch(sdb_handle h, uint32_t n_agents, const uint32_t* agent_idx, uint32_t max_messages, uint32_t flags,
+                      uint32_t* count_out, sdb_msg_header* hdr_out, uint64_t hdr_cap, uint8_t* payload_out,
+                      uint64_t payload_cap, uint64_t* total_out, uint64_t* payload_bytes_out) {
+  if (!h) return SDB_EINVAL;
+  if (total_out) *total_out = 0;
+  if (payload_bytes_out) *payload_bytes_out = 0;
+  if (!agent_idx) n_agents = h->n_agents;
+  if (n_agents == 0 || max_messages == 0) return SDB_OK;
+  if (n_agents > h->cfg.max_agents) return fail(h, SDB_EINVAL, "n_agents > max_agents");
+  if (agent_idx) {
+    for (uint32_t i = 0; i < n_agents; ++i)
+      if (agent_idx[i] >= h->cfg.max_agents) return fail(h, SDB_EINVAL, "agent index out of range");
+    CUDA_TRY(h, cudaMemcpyAsync(h->rx_agent, agent_idx, static_cast<size_t>(n_agents) * sizeof(uint32_t), cudaMemcpyHostToDevice, h->stream));
+  }
+  sdb_recv_args r{};
+  r.agent_idx = agent_idx ? h->rx_agent : nullptr; r.n = n_agents; r.max_messages = max_messages; r.flags = flags;
+  r.cnt = h->rx_cnt; r.rec_local = h->rx_rec_local; r.rec_tops = h->rx_rec_tops; r.pay = h->rx_pay;
+  r.pay_local = h->rx_pay_local; r.pay_tops = h->rx_pay_tops; r.old_head = h->rx_old_head; r.new_head = h->rx_new_head;
+  r.new_ntomb = h->rx_new_ntomb; r.sel_pos = h->rx_sel_pos; r.totals = h->rx_totals;
+  r.count_out = h->rx_count; r.hdr_out = h->rx_hdr; r.payload_out = h->rx_payload;
+  r.rec_cap = hdr_out ? std::min<uint64_t>(h->cfg.max_recv_records, hdr_cap) : h->cfg.max_recv_records;
+  r.pay_cap_gran = payload_out ? std::min<uint64_t>(h->pay_cap_gran, payload_cap / SDB_GRANULE) : h->pay_cap_gran;
+  int nl = 0;
+  cudaError_t e = sdb_launch_receive(&h->view, &r, h->stream, &nl, &h->prof);
+  h->launches += nl;
+  if (e != cudaSuccess) return fail(h, SDB_ECUDA, std::string("receive launch: ") + cudaGetErrorString(e));
+  CUDA_TRY(h, cudaMemcpyAsync(h->totals_host, h->rx_totals, 2 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, h->stream));
+  if (count_out)
+    CUDA_TRY(h, cudaMemcpyAsync(count_out, h->rx_count, static_cast<size_t>(n_agents) * sizeof(uint32_t), cudaMemcpyDeviceToHost, h->stream));
+  CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+  const uint64_t total = h->totals_host[0], pbytes = h->totals_host[1] * SDB_GRANULE;
+  if (total_out) *total_out = total;
+  if (payload_bytes_out) *payload_bytes_out = pbytes;
+  if (total) {
+    if (hdr_out) CUDA_TRY(h, cudaMemcpyAsync(hdr_out, h->rx_hdr, total * sizeof(sdb_msg_header), cudaMemcpyDeviceToHost, h->stream));
+    if (payload_out && pbytes) CUDA_TRY(h, cudaMemcpyAsync(payload_out, h->rx_payload, pbytes, cudaMemcpyDeviceToHost, h->stream));
+    if (hdr_out || payload_out) CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+  }
+  return SDB_OK;
+}
+
+int sdb_last_receive_dev(sdb_handle h, const uint32_t** count_dev, const sdb_msg_header** hdr_dev, const uint8_t** payload_dev) {
+  if (!h) return SDB_EINVAL;
+  if (count_dev) *count_dev = h->rx_count;
+  if (hdr_dev) *hdr_dev = h->rx_hdr;
+  if (payload_dev) *payload_dev = h->rx_payload;
+  return SDB_OK;
+}
+
+// ---- backends -----------------------------------------------------------------------------
+int sdb_set_backends(sdb_handle h, uint32_t n, const uint32_t* weight, const uint64_t* load0) {
+  if (!h || !weight || n == 0) return SDB_EINVAL;
+  if (n > h->cfg.max_backends) return fail(h, SDB_ECAPACITY, "n > max_backends");
+  std::vector<unsigned long long> l(n, 0);
+  for (uint32_t i = 0; i < n; ++i) {
+    if (weight[i] == 0 || weight[i] > 65535) return fail(h, SDB_EINVAL, "backend weight must be in [1, 65535]");
+    if (load0) { if (load0[i] >= (1ull << 40)) return fail(h, SDB_EINVAL, "backend load must be < 2^40"); l[i] = load0[i]; }
+  }
+  CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+  CUDA_TRY(h, cudaMemcpy(h->be_weight, weight, n * sizeof(uint32_t), cudaMemcpyHostToDevice));
+  CUDA_TRY(h, cudaMemcpy(h->be_load, l.data(), n * sizeof(unsigned long long), cudaMemcpyHostToDevice));
+  h->n_backends = n;
+  return SDB_OK;
+}
+
+int sdb_get_backend_loads(sdb_handle h, uint32_t n, uint64_t* load_out) {
+  if (!h || !load_out || n > h->n_backends) return SDB_EINVAL;
+  CUDA_TRY(h, cudaMemcpyAsync(load_out, h->be_load, n * sizeof(uint64_t), cudaMemcpyDeviceToHost, h->stream));
+  CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+  return SDB_OK;
+}
+
+static int ensure_req_cap(sdb_ctx* h, uint32_t n) {
+  if (n <= h->be_req_cap) return SDB_OK;
+  CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+  if (h->be_req_cost) cudaFree(h->be_req_cost);
+  if (h->be_out) cudaFree(h->be_out);
+  h->be_req_cost = nullptr; h->be_out = nullptr; h->be_req_cap = 0;
+  CUDA_TRY(h, dmalloc(&h->be_req_cost, n));
+  CUDA_TRY(h, dmalloc(&h->be_out, n));
+  h->be_req_cap = n;
+  return SDB_OK;
+}
+
+int sdb_release_backends(sdb_handle h, uint32_t n, const uint32_t* backend, const uint32_t* cost) {
+  if (!h || (n && !backend)) return SDB_EINVAL;
+  if (n == 0) return SDB_OK;
+  // completion reports are rare and small: fold them on the host, apply as one device update
+  std::vector<unsigned long long> l(h->n_backends);
+  CUDA_TRY(h, cudaMemcpyAsync(l.data(), h->be_load, h->n_backends * sizeof(unsigned long long), cudaMemcpyDeviceToHost, h->stream));
+  CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+  for (uint32_t i = 0; i < n; ++i) {
+    if (backend[i] >= h->n_backends) return fail(h, SDB_ENOTFOUND, "backend index out of range");
+    const unsigned long long c = cost ? cost[i] : 1;
+    l[backend[i]] = l[backend[i]] >= c ? l[backend[i]] - c : 0;
+  }
+  CUDA_TRY(h, cudaMemcpy(h->be_load, l.data(), h->n_backends * sizeof(unsigned long long), cudaMemcpyHostToDevice));
+  return SDB_OK;
+}
+
+int sdb_select_backend_batch(sdb_handle h, uint32_t n_req, const uint32_t* cost, uint32_t mode, uint64_t seed, uint32_t* backend_out) {
+  if (!h || !backend_out) return SDB_EINVAL;
+  if (mode > 1) return fail(h, SDB_EINVAL, "mode must be 0 (least-load) or 1 (weighted random)");
+  if (h->n_backends == 0) return fail(h, SDB_ENOTFOUND, "no backends configured (sdb_set_backends)");
+  if (n_req == 0) return SDB_OK;
+  int rc = ensure_req_cap(h, n_req);
+  if (rc != SDB_OK) return rc;
+  if (cost) CUDA_TRY(h, cudaMemcpyAsync(h->be_req_cost, cost, static_cast<size_t>(n_req) * sizeof(uint32_t), cudaMemcpyHostToDevice, h->stream));
+  int nl = 0;
+  cudaError_t e = sdb_launch_pick(static_cast<int>(mode), h->n_backends, h->be_weight, h->be_load, n_req,
+                                  cost ? h->be_req_cost : nullptr, seed, h->be_out, h->be_scratch, h->be_logtab,
+                                  h->stream, &nl);
+  h->launches += nl;
+  h->picks += n_req;
+  if (e != cudaSuccess) return fail(h, SDB_ECUDA, std::string("backend pick: ") + cudaGetErrorString(e));
+  CUDA_TRY(h, cudaMemcpyAsync(backend_out, h->be_out, static_cast<size_t>(n_req) * sizeof(uint32_t), cudaMemcpyDeviceToHost, h->stream));
+  CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+  return SDB_OK;
+}
+
+}  // extern "C"

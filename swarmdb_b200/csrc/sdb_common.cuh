@@ -1,0 +1,221 @@
+// sdb_common.cuh - shared device/host definitions for the sm_100a kernels.
+//
+// HBM layout of one shard (all sizes powers of two where masks are used):
+//
+//   arena        uint8 [arena_bytes]      packed message records, 32-byte granules, written
+//                                         strictly sequentially in global send order (a log).
+//                                         record = sdb_msg_header (32 B) | payload pad32.
+//                                         position `apos` (granules, monotonic u64);
+//                                         byte address = arena + ((apos & gmask) << 5);
+//                                         a batch never straddles the wrap point.
+//   ring_state   uint64 [max_agents]      {tail:hi32, head:lo32} monotonic per-agent cursors.
+//                                         ONE 64-bit atomicAdd(1<<32) claims a slot and
+//                                         returns head in the same L2 transaction.
+//   ring_handle  uint32 [max_agents][R]   (uint32)apos of each pending record
+//   ring_meta    uint16 [max_agents][R]   prio<<14 | record_granules ; 0xFFFF = consumed
+//   ctail        uint32 [max_agents]      tail as of the last commit (published prefix)
+//   ntomb        uint32 [max_agents]      consumed entries still inside [head, tail)
+//   members      uint32 [member_pool]     group member lists (CSR kept on the host)
+//
+// Ordering contract: after `commit`, every ring is sorted by handle, i.e. by arena
+// position, i.e. by global send order (the reference's single-partition Kafka log order,
+// SURVEY App. A rule 7).  Enqueue kernels claim slots with atomics in arbitrary order;
+// the commit kernel sorts the few entries each agent received in the batch.
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/swarmdb_b200.h"
+
+#define SDB_META_TOMB 0xFFFFu
+#define SDB_META_GLEN_MASK 0x3FFFu
+
+// per-send descriptor staged to the device (64 B, one per send)
+struct __align__(16) sdb_send_desc {
+  uint64_t payload_off;  // byte offset into the batch payload buffer, 16-B aligned
+  double   timestamp;
+  uint32_t rec0;         // seq offset of member 0 relative to the batch seq base
+  uint32_t gran0;        // arena granule offset of member 0 relative to the batch arena base
+  uint32_t sender;
+  uint32_t mstart;       // first member in the member pool (group/list) or receiver idx (p2p)
+  uint32_t mcount;       // members (1 for p2p)
+  uint32_t group;        // group index or SDB_NO_GROUP
+  uint16_t len;
+  uint8_t  prio;
+  uint8_t  type;
+  uint32_t flags;        // SDB_DESC_*
+  uint32_t rgran;        // granules per record = 1 + pad32(len)/32
+  uint32_t pad[3];
+};
+static_assert(sizeof(sdb_send_desc) == 64, "desc must be 64 bytes");
+static_assert(sizeof(sdb_msg_header) == 32, "header must be 32 bytes");
+
+#define SDB_DESC_SKIP_SENDER 1u   // group send: member == sender is skipped (M:1268)
+#define SDB_DESC_SHARED_SEQ 2u    // broadcast: every copy carries the same seq (one Message)
+#define SDB_DESC_LIST_TEMP 4u     // mstart indexes the per-batch temporary list buffer
+
+struct sdb_dev_counters {   // device-resident, updated with atomics
+  unsigned long long enqueued;
+  unsigned long long delivered;
+  unsigned long long ring_overflow;
+  unsigned long long skipped_sender;
+  unsigned long long backend_picks;
+  unsigned long long pad[3];
+};
+
+// everything a kernel needs about the shard, passed by value
+struct sdb_dev_view {
+  uint8_t*  arena;
+  uint64_t* ring_state;
+  uint32_t* ring_handle;
+  uint16_t* ring_meta;
+  uint32_t* ctail;
+  uint32_t* ntomb;
+  const uint32_t* members;
+  sdb_dev_counters* ctr;
+  uint64_t gmask;        // arena granules - 1
+  uint32_t ring_slots;   // R
+  uint32_t ring_shift;   // log2 R
+  uint32_t max_agents;
+};
+
+// arguments of one receive call (scratch + outputs), shared by sdb_api.cu and sdb_recv.cu
+struct sdb_recv_args {
+  const uint32_t* agent_idx;   // [n] or nullptr (identity)
+  uint32_t n;
+  uint32_t max_messages;
+  uint32_t flags;
+  // scratch, all [n] unless noted
+  uint32_t* cnt;         // selected count | SDB_MODE_LIST
+  uint32_t* rec_local;   uint32_t* rec_tops;    // scan of cnt
+  uint32_t* pay;         // payload granules per agent
+  uint32_t* pay_local;   uint32_t* pay_tops;    // scan of pay
+  uint32_t* old_head;    uint32_t* new_head;    uint32_t* new_ntomb;
+  uint32_t* sel_pos;     // [rec_cap] ring positions of selected entries (list mode)
+  unsigned long long* totals;   // [2] {records, payload granules} actually delivered
+  // outputs
+  uint32_t* count_out;          // [n]
+  sdb_msg_header* hdr_out;      // [rec_cap]
+  uint8_t* payload_out;         // [pay_cap_gran * 32]
+  uint64_t rec_cap;
+  uint64_t pay_cap_gran;
+};
+
+// ---- optional per-kernel timing with CUDA events on the launching stream (bench / roofline) ----
+struct sdb_profiler {
+  int enabled;
+  int n, cap;
+  int* kind;
+  cudaEvent_t* ev_a;
+  cudaEvent_t* ev_b;
+};
+static inline int sdb_prof_begin(sdb_profiler* p, int kind, cudaStream_t s) {
+  if (!p || !p->enabled || p->n >= p->cap) return -1;
+  const int i = p->n++;
+  p->kind[i] = kind;
+  cudaEventRecord(p->ev_a[i], s);
+  return i;
+}
+static inline void sdb_prof_end(sdb_profiler* p, int i, cudaStream_t s) {
+  if (i >= 0) cudaEventRecord(p->ev_b[i], s);
+}
+
+#ifdef __CUDACC__
+
+__device__ __forceinline__ uint8_t* sdb_arena_ptr(const sdb_dev_view& v, uint64_t apos) {
+  return v.arena + ((apos & v.gmask) << 5);
+}
+
+// Claim the next slot of agent a's ring and publish (handle, meta) into it.
+// Returns false when the ring is full (nothing is written; the commit kernel clamps tail).
+__device__ __forceinline__ bool sdb_ring_append(const sdb_dev_view& v, uint32_t a, uint32_t handle, uint16_t meta) {
+  unsigned long long old = atomicAdd(reinterpret_cast<unsigned long long*>(v.ring_state + a), 1ull << 32);
+  uint32_t e = static_cast<uint32_t>(old >> 32);
+  uint32_t head = static_cast<uint32_t>(old);
+  if (e - head >= v.ring_slots) return false;
+  size_t slot = (static_cast<size_t>(a) << v.ring_shift) + (e & (v.ring_slots - 1));
+  v.ring_handle[slot] = handle;
+  v.ring_meta[slot] = meta;
+  return true;
+}
+
+__device__ __forceinline__ uint4 sdb_header_lo(uint64_t seq, double ts) {
+  uint4 r;
+  r.x = static_cast<uint32_t>(seq);
+  r.y = static_cast<uint32_t>(seq >> 32);
+  unsigned long long t = __double_as_longlong(ts);
+  r.z = static_cast<uint32_t>(t);
+  r.w = static_cast<uint32_t>(t >> 32);
+  return r;
+}
+__device__ __forceinline__ uint4 sdb_header_hi(uint32_t sender, uint32_t receiver, uint32_t group,
+                                               uint16_t len, uint8_t prio, uint8_t type) {
+  uint4 r;
+  r.x = sender;
+  r.y = receiver;
+  r.z = group;
+  r.w = static_cast<uint32_t>(len) | (static_cast<uint32_t>(prio) << 16) | (static_cast<uint32_t>(type) << 24);
+  return r;
+}
+
+// streaming 16-byte accesses: message bytes are touched once, keep them out of L1
+__device__ __forceinline__ uint4 sdb_ld_stream(const void* p) {
+  uint4 r;
+  asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];"
+               : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p));
+  return r;
+}
+__device__ __forceinline__ void sdb_st_stream(void* p, const uint4& v) {
+  asm volatile("st.global.L1::no_allocate.v4.u32 [%0], {%1,%2,%3,%4};"
+               :: "l"(p), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+
+// ---- mbarrier + TMA (bulk async copy) wrappers ----------------------------------------------
+__device__ __forceinline__ uint32_t sdb_smem_u32(const void* p) {
+  return static_cast<uint32_t>(__cvta_generic_to_shared(p));
+}
+__device__ __forceinline__ void sdb_mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(sdb_smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void sdb_fence_barrier_init() {
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void sdb_fence_proxy_async() {
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+__device__ __forceinline__ void sdb_mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(sdb_smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void sdb_mbar_wait(uint64_t* bar, uint32_t phase) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "WAIT_LOOP:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra DONE;\n"
+      "bra WAIT_LOOP;\n"
+      "DONE:\n"
+      "}\n" :: "r"(sdb_smem_u32(bar)), "r"(phase) : "memory");
+}
+// global -> shared bulk copy, completion counted on an mbarrier (SASS: UBLKCP)
+__device__ __forceinline__ void sdb_tma_load(void* smem_dst, const void* gsrc, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               :: "r"(sdb_smem_u32(smem_dst)), "l"(gsrc), "r"(bytes), "r"(sdb_smem_u32(bar)) : "memory");
+}
+// shared -> global bulk copy (bulk_group completion)
+__device__ __forceinline__ void sdb_tma_store(void* gdst, const void* smem_src, uint32_t bytes) {
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;"
+               :: "l"(gdst), "r"(sdb_smem_u32(smem_src)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void sdb_tma_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void sdb_tma_wait_read() {
+  asm volatile("cp.async.bulk.wait_group.read %0;" :: "n"(N) : "memory");
+}
+template <int N>
+__device__ __forceinline__ void sdb_tma_wait_all() {
+  asm volatile("cp.async.bulk.wait_group %0;" :: "n"(N) : "memory");
+}
+
+#endif  // __CUDACC__

@@ -1,0 +1,375 @@
+// sdb_send.cu - enqueue kernels (sm_100a).
+//
+//   k_enqueue_p2p     K1: send_message      (reference M:393-519, produce M:476-482)
+//   k_group_fanout    K2: send_to_group     (reference M:1229-1279, the per-member loop M:1267-1277)
+//                         and broadcast lists (M:449-463 / M:810-850)
+//   k_commit          publishes a batch: sorts each agent's newly claimed ring entries into
+//                     arena (= global send) order and clamps overflowed rings
+//                     (role of the delivery report, M:374-391: PENDING -> DELIVERED)
+//
+// Roofline: all three are pure data movement (HBM-bound).  Algorithmic bytes per routed
+// message for K2 at L=256, H=16 essential header bytes, F=64: (L+H) written + 4 member id
+// read + (L+H)/F source read = 280.25 B; the kernel physically writes a 32-byte
+// header (288 B/record) plus 6 B of ring entry.
+#include "sdb_common.cuh"
+
+namespace {
+
+__device__ __forceinline__ sdb_send_desc load_desc(const sdb_send_desc* p) {
+  // 64-byte descriptor, same address for the whole CTA -> L1 broadcast
+  const uint4* q = reinterpret_cast<const uint4*>(p);
+  union { uint4 v[4]; sdb_send_desc d; } u;
+  u.v[0] = __ldg(q); u.v[1] = __ldg(q + 1); u.v[2] = __ldg(q + 2); u.v[3] = __ldg(q + 3);
+  return u.d;
+}
+
+// zero the pad bytes [len, padlen) of a staged payload so arena contents are deterministic
+__device__ __forceinline__ void zero_pad(uint8_t* s_payload, uint32_t len, uint32_t padlen, uint32_t tid) {
+  uint32_t b = len + tid;
+  if (tid < 32 && b < padlen) s_payload[b] = 0;
+}
+
+}  // namespace
+
+// ------------------------------------------------------------------------------------------
+// K2 (variant A): one CTA per send, payload staged once in shared memory by a TMA bulk load,
+// then every member's copy is written with coalesced 16-byte streaming stores.
+// Thread j of a 256-member tile owns member j: builds its 32-byte header, stores it and
+// claims the ring slot; the 8 warps then stream the payload copies (warp w -> members w, w+8, ..).
+// ------------------------------------------------------------------------------------------
+template <int THREADS>
+__global__ void __launch_bounds__(THREADS)
+k_group_fanout_st(sdb_dev_view v, const sdb_send_desc* __restrict__ descs, uint32_t n,
+                  const uint8_t* __restrict__ payload, const uint32_t* __restrict__ tmp_list,
+                  uint64_t seq_base, uint64_t arena_base) {
+  extern __shared__ __align__(128) uint8_t s_payload[];
+  __shared__ __align__(8) uint64_t s_bar;
+  __shared__ uint32_t s_deliver[THREADS / 32];
+  constexpr int NW = THREADS / 32;
+  const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+
+  if (tid == 0) { sdb_mbar_init(&s_bar, 1); sdb_fence_barrier_init(); }
+  __syncthreads();
+  uint32_t phase = 0;
+  uint32_t n_enq = 0, n_ovf = 0, n_skip = 0;
+
+  for (uint32_t i = blockIdx.x; i < n; i += gridDim.x) {
+    const sdb_send_desc d = load_desc(descs + i);
+    if (d.mcount == 0) continue;                       // nobody to deliver to (uniform across the CTA)
+    const uint32_t padlen = (d.rgran - 1u) * SDB_GRANULE;
+    if (tid == 0 && padlen) {
+      sdb_mbar_expect_tx(&s_bar, padlen);
+      sdb_tma_load(s_payload, payload + d.payload_off, padlen, &s_bar);
+    }
+    const uint32_t* mem = (d.flags & SDB_DESC_LIST_TEMP) ? tmp_list + d.mstart : v.members + d.mstart;
+    const uint16_t meta = static_cast<uint16_t>((static_cast<uint32_t>(d.prio) << 14) | d.rgran);
+    const uint64_t apos0 = arena_base + d.gran0;
+
+    for (uint32_t tile = 0; tile < d.mcount; tile += THREADS) {
+      const uint32_t j = tile + tid;
+      const bool valid = j < d.mcount;
+      const uint32_t a = valid ? __ldg(mem + j) : 0xFFFFFFFFu;
+      const bool skip = valid && (d.flags & SDB_DESC_SKIP_SENDER) && a == d.sender;
+      const bool deliver = valid && !skip && a < v.max_agents;
+      const uint32_t bal = __ballot_sync(0xFFFFFFFFu, deliver);
+      if (lane == 0) s_deliver[warp] = bal;
+      if (deliver) {
+        const uint64_t apos = apos0 + static_cast<uint64_t>(j) * d.rgran;
+        const uint64_t seq = seq_base + d.rec0 + ((d.flags & SDB_DESC_SHARED_SEQ) ? 0u : j);
+        const uint32_t rcv = (d.flags & SDB_DESC_SHARED_SEQ) ? SDB_NO_RECEIVER : a;
+        uint4* dst = reinterpret_cast<uint4*>(sdb_arena_ptr(v, apos));
+        sdb_st_stream(dst, sdb_header_lo(seq, d.timestamp));
+        sdb_st_stream(dst + 1, sdb_header_hi(d.sender, rcv, d.group, d.len, d.prio, d.type));
+        if (sdb_ring_append(v, a, static_cast<uint32_t>(apos), meta)) ++n_enq; else ++n_ovf;
+      }
+      n_skip += skip;
+      if (tile == 0 && padlen) {
+        sdb_mbar_wait(&s_bar, phase);
+        zero_pad(s_payload, d.len, padlen, tid);
+      }
+      __syncthreads();
+      const uint32_t in_tile = min(static_cast<uint32_t>(THREADS), d.mcount - tile);
+      const uint32_t nchunk = padlen >> 4;
+      for (uint32_t jj = warp; jj < in_tile; jj += NW) {
+        if (!((s_deliver[jj >> 5] >> (jj & 31)) & 1u)) continue;
+        uint8_t* dst = sdb_arena_ptr(v, apos0 + static_cast<uint64_t>(tile + jj) * d.rgran) + 32;
+        for (uint32_t c = lane; c < nchunk; c += 32)
+          sdb_st_stream(dst + (c << 4), reinterpret_cast<const uint4*>(s_payload)[c]);
+      }
+      __syncthreads();
+    }
+    if (padlen) phase ^= 1;
+  }
+  // one atomic per warp for the counters
+  for (int o = 16; o; o >>= 1) {
+    n_enq += __shfl_xor_sync(0xFFFFFFFFu, n_enq, o);
+    n_ovf += __shfl_xor_sync(0xFFFFFFFFu, n_ovf, o);
+    n_skip += __shfl_xor_sync(0xFFFFFFFFu, n_skip, o);
+  }
+  if (lane == 0) {
+    if (n_enq) atomicAdd(&v.ctr->enqueued, n_enq);
+    if (n_ovf) atomicAdd(&v.ctr->ring_overflow, n_ovf);
+    if (n_skip) atomicAdd(&v.ctr->skipped_sender, n_skip);
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// K2 (variant B): TMA in, TMA out.  One small CTA (64 threads) per send; the payload is
+// bulk-loaded into one of two shared-memory stages, and thread j issues ONE bulk store
+// (cp.async.bulk.global.shared::cta) of the whole padded payload into member j's record,
+// after writing that record's 32-byte header with two vector stores and claiming the ring
+// slot.  No per-chunk store instructions: the LSU only sees headers, ring entries and atomics.
+// ------------------------------------------------------------------------------------------
+template <int THREADS>
+__global__ void __launch_bounds__(THREADS)
+k_group_fanout_tma(sdb_dev_view v, const sdb_send_desc* __restrict__ descs, uint32_t n,
+                   const uint8_t* __restrict__ payload, const uint32_t* __restrict__ tmp_list,
+                   uint64_t seq_base, uint64_t arena_base, uint32_t stage_bytes) {
+  extern __shared__ __align__(128) uint8_t s_stage[];   // 2 stages of stage_bytes
+  __shared__ __align__(8) uint64_t s_bar[2];
+  const uint32_t tid = threadIdx.x, lane = tid & 31;
+
+  if (tid == 0) { sdb_mbar_init(&s_bar[0], 1); sdb_mbar_init(&s_bar[1], 1); sdb_fence_barrier_init(); }
+  __syncthreads();
+  uint32_t phase[2] = {0, 0};
+  uint32_t n_enq = 0, n_ovf = 0, n_skip = 0;
+
+  // prologue: prefetch the first send's payload into stage 0
+  uint32_t i = blockIdx.x;
+  if (i < n && tid == 0) {
+    const sdb_send_desc d0 = load_desc(descs + i);
+    const uint32_t pl = (d0.rgran - 1u) * SDB_GRANULE;
+    if (pl) { sdb_mbar_expect_tx(&s_bar[0], pl); sdb_tma_load(s_stage, payload + d0.payload_off, pl, &s_bar[0]); }
+  }
+  uint32_t st = 0;
+  for (; i < n; i += gridDim.x, st ^= 1) {
+    const sdb_send_desc d = load_desc(descs + i);
+    const uint32_t padlen = (d.rgran - 1u) * SDB_GRANULE;
+    uint8_t* s_payload = s_stage + st * stage_bytes;
+    // prefetch the next send into the other stage; its previous bulk stores must have
+    // finished READING that stage (every issuing thread waits on its own bulk groups)
+    sdb_tma_wait_read<0>();
+    __syncthreads();
+    const uint32_t inext = i + gridDim.x;
+    if (inext < n && tid == 0) {
+      const sdb_send_desc dn = load_desc(descs + inext);
+      const uint32_t pl = (dn.rgran - 1u) * SDB_GRANULE;
+      if (pl) {
+        sdb_mbar_expect_tx(&s_bar[st ^ 1], pl);
+        sdb_tma_load(s_stage + (st ^ 1) * stage_bytes, payload + dn.payload_off, pl, &s_bar[st ^ 1]);
+      }
+    }
+    if (padlen) {
+      sdb_mbar_wait(&s_bar[st], phase[st]);
+      phase[st] ^= 1;
+      zero_pad(s_payload, d.len, padlen, tid);
+      sdb_fence_proxy_async();        // generic-proxy writes (pad zeroing) -> visible to the bulk store
+      __syncthreads();
+    }
+    const uint32_t* mem = (d.flags & SDB_DESC_LIST_TEMP) ? tmp_list + d.mstart : v.members + d.mstart;
+    const uint16_t meta = static_cast<uint16_t>((static_cast<uint32_t>(d.prio) << 14) | d.rgran);
+    const uint64_t apos0 = arena_base + d.gran0;
+    for (uint32_t j = tid; j < d.mcount; j += THREADS) {
+      const uint32_t a = __ldg(mem + j);
+      const bool skip = (d.flags & SDB_DESC_SKIP_SENDER) && a == d.sender;
+      n_skip += skip;
+      if (skip || a >= v.max_agents) continue;
+      const uint64_t apos = apos0 + static_cast<uint64_t>(j) * d.rgran;
+      const uint64_t seq = seq_base + d.rec0 + ((d.flags & SDB_DESC_SHARED_SEQ) ? 0u : j);
+      const uint32_t rcv = (d.flags & SDB_DESC_SHARED_SEQ) ? SDB_NO_RECEIVER : a;
+      uint8_t* rec = sdb_arena_ptr(v, apos);
+      if (padlen) sdb_tma_store(rec + 32, s_payload, padlen);
+      sdb_st_stream(rec, sdb_header_lo(seq, d.timestamp));
+      sdb_st_stream(rec + 16, sdb_header_hi(d.sender, rcv, d.group, d.len, d.prio, d.type));
+      if (sdb_ring_append(v, a, static_cast<uint32_t>(apos), meta)) ++n_enq; else ++n_ovf;
+    }
+    sdb_tma_commit();
+  }
+  sdb_tma_wait_all<0>();
+  for (int o = 16; o; o >>= 1) {
+    n_enq += __shfl_xor_sync(0xFFFFFFFFu, n_enq, o);
+    n_ovf += __shfl_xor_sync(0xFFFFFFFFu, n_ovf, o);
+    n_skip += __shfl_xor_sync(0xFFFFFFFFu, n_skip, o);
+  }
+  if (lane == 0) {
+    if (n_enq) atomicAdd(&v.ctr->enqueued, n_enq);
+    if (n_ovf) atomicAdd(&v.ctr->ring_overflow, n_ovf);
+    if (n_skip) atomicAdd(&v.ctr->skipped_sender, n_skip);
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// K1: point-to-point enqueue.  One warp per record: lanes 0-1 build the header, lanes 2.. copy
+// payload chunks global -> global with streaming 16-byte accesses; lane 0 claims the ring slot.
+// Algorithmic bytes: 2 (L+H) per record.
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+k_enqueue_p2p(sdb_dev_view v, const sdb_send_desc* __restrict__ descs, uint32_t n,
+              const uint8_t* __restrict__ payload, uint64_t seq_base, uint64_t arena_base) {
+  const uint32_t lane = threadIdx.x & 31;
+  const uint32_t wid = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const uint32_t nw = (gridDim.x * blockDim.x) >> 5;
+  uint32_t n_enq = 0, n_ovf = 0;
+  for (uint32_t i = wid; i < n; i += nw) {
+    const sdb_send_desc d = load_desc(descs + i);
+    const uint32_t a = d.mstart;
+    if (a >= v.max_agents) continue;
+    const uint32_t padlen = (d.rgran - 1u) * SDB_GRANULE;
+    const uint32_t nchunk = 2u + (padlen >> 4);
+    const uint64_t apos = arena_base + d.gran0;
+    uint8_t* rec = sdb_arena_ptr(v, apos);
+    const uint8_t* src = payload + d.payload_off;
+    for (uint32_t c = lane; c < nchunk; c += 32) {
+      uint4 x;
+      if (c == 0) x = sdb_header_lo(seq_base + d.rec0, d.timestamp);
+      else if (c == 1) x = sdb_header_hi(d.sender, a, d.group, d.len, d.prio, d.type);
+      else {
+        x = sdb_ld_stream(src + ((c - 2u) << 4));
+        const uint32_t b0 = (c - 2u) << 4;                 // zero pad bytes beyond len
+        if (b0 + 16u > d.len) {
+          uint8_t* xb = reinterpret_cast<uint8_t*>(&x);
+#pragma unroll
+          for (int k = 0; k < 16; ++k) if (b0 + k >= d.len) xb[k] = 0;
+        }
+      }
+      sdb_st_stream(rec + (c << 4), x);
+    }
+    if (lane == 0) {
+      const uint16_t meta = static_cast<uint16_t>((static_cast<uint32_t>(d.prio) << 14) | d.rgran);
+      if (sdb_ring_append(v, a, static_cast<uint32_t>(apos), meta)) ++n_enq; else ++n_ovf;
+    }
+  }
+  if (lane == 0) {
+    if (n_enq) atomicAdd(&v.ctr->enqueued, n_enq);
+    if (n_ovf) atomicAdd(&v.ctr->ring_overflow, n_ovf);
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// commit: one thread per agent below the registration watermark.  Entries claimed since the
+// last commit sit in [ctail, tail) in atomic-arrival order; sort them by arena position
+// relative to the batch base (all of them belong to this batch), clamp an overflowed tail,
+// publish ctail = tail.
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+k_commit(sdb_dev_view v, uint32_t n_agents, uint32_t batch_base32) {
+  const uint32_t a = blockIdx.x * blockDim.x + threadIdx.x;
+  if (a >= n_agents) return;
+  const uint64_t st = v.ring_state[a];
+  uint32_t tail = static_cast<uint32_t>(st >> 32);
+  const uint32_t head = static_cast<uint32_t>(st);
+  const uint32_t ct = v.ctail[a];
+  if (tail == ct) return;
+  const uint32_t R = v.ring_slots, mask = R - 1;
+  if (tail - head > R) {                       // overflowed claims were never written
+    tail = head + R;
+    v.ring_state[a] = (static_cast<uint64_t>(tail) << 32) | head;
+  }
+  const uint32_t cnt = tail - ct;
+  uint32_t* hs = v.ring_handle + (static_cast<size_t>(a) << v.ring_shift);
+  uint16_t* ms = v.ring_meta + (static_cast<size_t>(a) << v.ring_shift);
+  if (cnt > 1) {
+    constexpr uint32_t LOCAL = 16;
+    if (cnt <= LOCAL) {
+      uint32_t k[LOCAL]; uint16_t m[LOCAL];
+#pragma unroll
+      for (uint32_t i = 0; i < LOCAL; ++i)
+        if (i < cnt) { k[i] = hs[(ct + i) & mask] - batch_base32; m[i] = ms[(ct + i) & mask]; }
+      bool sorted = true;
+#pragma unroll
+      for (uint32_t i = 1; i < LOCAL; ++i) if (i < cnt && k[i] < k[i - 1]) sorted = false;
+      if (!sorted) {
+        // odd-even transposition network, fully unrolled so k[]/m[] stay in registers
+#pragma unroll
+        for (uint32_t r = 0; r < LOCAL; ++r) {
+#pragma unroll
+          for (uint32_t i = (r & 1); i + 1 < LOCAL; i += 2) {
+            if (i + 1 < cnt && k[i + 1] < k[i]) {
+              uint32_t tk = k[i]; k[i] = k[i + 1]; k[i + 1] = tk;
+              uint16_t tm = m[i]; m[i] = m[i + 1]; m[i + 1] = tm;
+            }
+          }
+        }
+#pragma unroll
+        for (uint32_t i = 0; i < LOCAL; ++i)
+          if (i < cnt) { hs[(ct + i) & mask] = k[i] + batch_base32; ms[(ct + i) & mask] = m[i]; }
+      }
+    } else {
+      // rare: many records for one agent in one batch -> in-place insertion sort (mostly sorted input)
+      for (uint32_t i = 1; i < cnt; ++i) {
+        const uint32_t hk = hs[(ct + i) & mask]; const uint16_t mk = ms[(ct + i) & mask];
+        const uint32_t key = hk - batch_base32;
+        uint32_t j = i;
+        while (j > 0 && hs[(ct + j - 1) & mask] - batch_base32 > key) {
+          hs[(ct + j) & mask] = hs[(ct + j - 1) & mask];
+          ms[(ct + j) & mask] = ms[(ct + j - 1) & mask];
+          --j;
+        }
+        if (j != i) { hs[(ct + j) & mask] = hk; ms[(ct + j) & mask] = mk; }
+      }
+    }
+  }
+  v.ctail[a] = tail;
+}
+
+// ------------------------------------------------------------------------------------------
+// host-side launchers (called from sdb_api.cu)
+// ------------------------------------------------------------------------------------------
+extern "C" cudaError_t sdb_launch_p2p(const sdb_dev_view* v, const sdb_send_desc* descs, uint32_t n,
+                                      const uint8_t* payload, uint64_t seq_base, uint64_t arena_base,
+                                      int sm_count, cudaStream_t stream, sdb_profiler* prof) {
+  if (n == 0) return cudaSuccess;
+  const uint32_t warps_per_cta = 8;
+  uint32_t grid = (n + warps_per_cta - 1) / warps_per_cta;
+  const uint32_t cap = static_cast<uint32_t>(sm_count) * 8u * 4u;   // ~4 waves of 8 CTAs/SM, grid-stride beyond
+  if (grid > cap) grid = cap;
+  const int pi = sdb_prof_begin(prof, SDB_PK_P2P, stream);
+  k_enqueue_p2p<<<grid, 256, 0, stream>>>(*v, descs, n, payload, seq_base, arena_base);
+  sdb_prof_end(prof, pi, stream);
+  return cudaGetLastError();
+}
+
+extern "C" cudaError_t sdb_launch_fanout(const sdb_dev_view* v, const sdb_send_desc* descs, uint32_t n,
+                                         const uint8_t* payload, const uint32_t* tmp_list,
+                                         uint64_t seq_base, uint64_t arena_base, uint32_t max_padlen,
+                                         int variant, int sm_count, cudaStream_t stream, sdb_profiler* prof) {
+  if (n == 0) return cudaSuccess;
+  const int pi = sdb_prof_begin(prof, SDB_PK_FANOUT, stream);
+  if (variant == 0) {
+    constexpr int T = 256;
+    const size_t smem = max_padlen ? max_padlen : 16;
+    static bool attr_set = false;
+    if (!attr_set) {
+      cudaFuncSetAttribute(k_group_fanout_st<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, 65536 + 1024);
+      attr_set = true;
+    }
+    uint32_t grid = static_cast<uint32_t>(sm_count) * 8u;           // persistent: 8 CTAs of 256 threads per SM
+    if (grid > n) grid = n;
+    k_group_fanout_st<T><<<grid, T, smem, stream>>>(*v, descs, n, payload, tmp_list, seq_base, arena_base);
+  } else {
+    constexpr int T = 64;
+    const uint32_t stage = ((max_padlen ? max_padlen : 16) + 127u) & ~127u;
+    static bool attr_set = false;
+    if (!attr_set) {
+      cudaFuncSetAttribute(k_group_fanout_tma<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * 65536 + 1024);
+      attr_set = true;
+    }
+    uint32_t per_sm = 16;
+    const size_t smem = 2ull * stage;
+    while (per_sm > 1 && per_sm * (smem + 1024) > 200 * 1024) per_sm >>= 1;
+    uint32_t grid = static_cast<uint32_t>(sm_count) * per_sm;
+    if (grid > n) grid = n;
+    k_group_fanout_tma<T><<<grid, T, smem, stream>>>(*v, descs, n, payload, tmp_list, seq_base, arena_base, stage);
+  }
+  sdb_prof_end(prof, pi, stream);
+  return cudaGetLastError();
+}
+
+extern "C" cudaError_t sdb_launch_commit(const sdb_dev_view* v, uint32_t n_agents, uint32_t batch_base32,
+                                         cudaStream_t stream, sdb_profiler* prof) {
+  if (n_agents == 0) return cudaSuccess;
+  const int pi = sdb_prof_begin(prof, SDB_PK_COMMIT, stream);
+  k_commit<<<(n_agents + 255) / 256, 256, 0, stream>>>(*v, n_agents, batch_base32);
+  sdb_prof_end(prof, pi, stream);
+  return cudaGetLastError();
+}

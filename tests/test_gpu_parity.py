@@ -1,0 +1,240 @@
+"""GPU parity: the CUDA path (through the C ABI) against the CPU oracle, bit-exact.
+
+Every test drives `swarmdb_b200._native.Shard` (ctypes -> libswarmdb_b200.so -> sm_100a kernels)
+and `oracle.cpu_ref.CpuOracle` (gcc-built restatement, pinned to the reference's goldens by
+tests/test_oracle_c.py) with the same seeded batches and compares headers and payload bytes
+of every delivered record, per agent, in delivery order.
+"""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+def _mk_payloads(rng, n, max_len, fixed=False):
+    lens = np.full(n, max_len, np.uint16) if fixed else rng.integers(0, max_len + 1, n).astype(np.uint16)
+    stride = (max_len + 31) & ~31
+    buf = np.zeros(n * stride + 64, np.uint8)
+    off = (np.arange(n, dtype=np.uint64) * stride)
+    alnum = np.frombuffer(b"ABCDEFGHIJKLMNOPQRSTUVWXYZabcdefghijklmnopqrstuvwxyz0123456789", np.uint8)
+    for i in range(n):
+        buf[int(off[i]): int(off[i]) + int(lens[i])] = alnum[rng.integers(0, 62, int(lens[i]))]
+    return lens, off, buf
+
+
+def _same(res_gpu, res_cpu):
+    cg, hg, pg = res_gpu
+    cc, hc, pc = res_cpu
+    assert np.array_equal(cg, cc), (cg[:16], cc[:16])
+    assert len(hg) == len(hc)
+    for f in hg.dtype.names:
+        assert np.array_equal(hg[f], hc[f]), f
+    assert pg.tobytes() == pc.tobytes()
+
+
+def _pair(max_agents, max_groups=8, **kw):
+    from oracle.cpu_ref import CpuOracle
+    from swarmdb_b200._native import Shard
+    g = Shard(max_agents=max_agents, max_groups=max_groups, **kw)
+    c = CpuOracle(max_agents, max_groups)
+    return g, c
+
+
+@pytest.mark.parametrize("variant", [0, 1])
+def test_p2p_then_drain(variant):
+    rng = np.random.default_rng(11)
+    A = 200
+    g, c = _pair(A, fanout_variant=variant)
+    idx = np.arange(A, dtype=np.uint32)
+    g.register(idx); c.register(idx)
+    for rnd in range(3):
+        n = 3000
+        s = rng.integers(0, A, n); r = rng.integers(0, A, n)
+        prio = rng.integers(0, 4, n); typ = rng.integers(0, 7, n)
+        lens, off, buf = _mk_payloads(rng, n, 256)
+        ts = rng.random(n)
+        assert g.send_batch(s, r, prio, typ, lens, off, buf, ts) == c.send_batch(s, r, prio, typ, lens, off, buf, ts)
+        _same(g.receive_batch(idx, 7), c.receive_batch(idx, 7))
+    _same(g.receive_batch(idx, 1000), c.receive_batch(idx, 1000))
+    _same(g.receive_batch(idx, 1000), c.receive_batch(idx, 1000))      # empty drain
+    st = g.stats()
+    assert st["enqueued"] == 9000 and st["delivered"] == 9000 and st["ring_overflow"] == 0
+
+
+@pytest.mark.parametrize("variant", [0, 1])
+@pytest.mark.parametrize("fixed", [True, False])
+def test_group_fanout_parity(variant, fixed):
+    rng = np.random.default_rng(5 + variant)
+    A, G, F = 4096, 64, 64
+    g, c = _pair(A, max_groups=G + 2, fanout_variant=variant, ring_slots=256)
+    perm = rng.permutation(A)
+    for k in range(G):
+        m = perm[k * F:(k + 1) * F]
+        g.create_group(k, m); c.create_group(k, m)
+    # a group with duplicate members and one of size 1, one empty
+    dup = np.array([3, 9, 3, 3, 17], np.uint32)
+    g.create_group(G, dup); c.create_group(G, dup)
+    g.create_group(G + 1, np.array([5], np.uint32)); c.create_group(G + 1, np.array([5], np.uint32))
+    allidx = np.arange(A, dtype=np.uint32)
+    for rnd in range(3):
+        n = 700
+        grp = rng.integers(0, G + 2, n)
+        s = rng.integers(0, A, n)                      # sometimes a member: skip-sender exercised
+        s[:20] = 3; grp[:20] = G                       # sender inside the duplicate group
+        s[20:30] = 5; grp[20:30] = G + 1               # group of one whose only member is the sender
+        prio = rng.integers(0, 4, n); typ = rng.integers(0, 7, n)
+        lens, off, buf = _mk_payloads(rng, n, 256, fixed=fixed)
+        bg = g.send_group_batch(s, grp, prio, typ, lens, off, buf)
+        bc, routed = c.send_group_batch(s, grp, prio, typ, lens, off, buf)
+        assert bg == bc
+        if rnd == 1:
+            _same(g.receive_batch(allidx, 3), c.receive_batch(allidx, 3))
+    _same(g.receive_batch(None, 1000), c.receive_batch(None, 1000))
+    st = g.stats()
+    assert st["enqueued"] == st["delivered"] and st["skipped_sender"] > 0 and st["ring_overflow"] == 0
+
+
+def test_group_overwrite_and_large_group():
+    rng = np.random.default_rng(3)
+    A = 3000
+    g, c = _pair(A, max_groups=4, ring_slots=64)
+    big = rng.permutation(A)[:1500]                    # > 256 members: several tiles per send
+    g.create_group(0, big); c.create_group(0, big)
+    lens, off, buf = _mk_payloads(rng, 4, 96)
+    g.send_group_batch([1, 2, 3, 4], [0, 0, 0, 0], [0, 1, 2, 3], [0, 0, 0, 0], lens, off, buf)
+    c.send_group_batch([1, 2, 3, 4], [0, 0, 0, 0], [0, 1, 2, 3], [0, 0, 0, 0], lens, off, buf)
+    small = np.array([7, 8], np.uint32)                # overwrite (M:1223)
+    g.create_group(0, small); c.create_group(0, small)
+    g.send_group_batch([1], [0], [1], [0], lens[:1], off[:1], buf)
+    c.send_group_batch([1], [0], [1], [0], lens[:1], off[:1], buf)
+    _same(g.receive_batch(None, 100), c.receive_batch(None, 100))
+    with pytest.raises(Exception):
+        g.send_group_batch([1], [3], [1], [0], lens[:1], off[:1], buf)   # undefined group
+
+
+def test_broadcast_lists_share_one_seq():
+    rng = np.random.default_rng(9)
+    A = 500
+    g, c = _pair(A)
+    idx = np.arange(A, dtype=np.uint32)
+    g.register(idx); c.register(idx)
+    n = 12
+    lists = [rng.choice(A, size=int(rng.integers(0, 300)), replace=False) for _ in range(n)]
+    lo = np.zeros(n + 1, np.uint64); lo[1:] = np.cumsum([len(x) for x in lists])
+    li = np.concatenate(lists).astype(np.uint32)
+    s = rng.integers(0, A, n); prio = rng.integers(0, 4, n); typ = rng.integers(0, 7, n)
+    lens, off, buf = _mk_payloads(rng, n, 200)
+    # interleave with p2p traffic so stream order across kinds is checked
+    l2, o2, b2 = _mk_payloads(rng, 50, 64)
+    s2 = rng.integers(0, A, 50); r2 = rng.integers(0, A, 50)
+    for sys in (g, c):
+        sys.send_batch(s2, r2, None, None, l2, o2, b2)
+        sys.send_list_batch(s, lo, li, prio, typ, lens, off, buf)
+        sys.send_batch(r2, s2, None, None, l2, o2, b2)
+    _same(g.receive_batch(idx, 1000), c.receive_batch(idx, 1000))
+
+
+def test_priority_receive_matches_oracle_and_equal_priority_is_fifo():
+    rng = np.random.default_rng(21)
+    from swarmdb_b200._native import RECV_PRIORITY
+    A = 64
+    g, c = _pair(A, ring_slots=4096)
+    idx = np.arange(A, dtype=np.uint32)
+    g.register(idx); c.register(idx)
+    for rnd in range(4):
+        n = 20000
+        s = rng.integers(0, A, n); r = rng.integers(0, A, n)
+        prio = rng.integers(0, 4, n)
+        lens, off, buf = _mk_payloads(rng, n, 64)
+        g.send_batch(s, r, prio, None, lens, off, buf); c.send_batch(s, r, prio, None, lens, off, buf)
+        for k in (1, 5, 33, 100):
+            _same(g.receive_batch(idx, k, RECV_PRIORITY), c.receive_batch(idx, k, RECV_PRIORITY))
+        # stream-order receive while holes exist
+        _same(g.receive_batch(idx, 17, 0), c.receive_batch(idx, 17, 0))
+    while True:
+        rg, rc = g.receive_batch(idx, 100, RECV_PRIORITY), c.receive_batch(idx, 100, RECV_PRIORITY)
+        _same(rg, rc)
+        if len(rg[1]) == 0:
+            break
+    # equal priorities: priority mode must equal stream order (the tie-break obligation)
+    n = 5000
+    s = rng.integers(0, A, n); r = rng.integers(0, A, n)
+    lens, off, buf = _mk_payloads(rng, n, 32)
+    g.send_batch(s, r, np.full(n, 2), None, lens, off, buf); c.send_batch(s, r, np.full(n, 2), None, lens, off, buf)
+    _same(g.receive_batch(idx, 40, RECV_PRIORITY), c.receive_batch(idx, 40, 0))
+    _same(g.receive_batch(idx, 1000, 0), c.receive_batch(idx, 1000, RECV_PRIORITY))
+
+
+def test_ring_overflow_is_reported_not_silent():
+    rng = np.random.default_rng(2)
+    g, c = _pair(8, ring_slots=4)
+    lens, off, buf = _mk_payloads(rng, 10, 16)
+    g.send_batch(np.zeros(10), np.ones(10), None, None, lens, off, buf)
+    st = g.stats()
+    assert st["enqueued"] == 4 and st["ring_overflow"] == 6
+    cnt, hdr, pay = g.receive_batch([1], 100)
+    assert cnt[0] == 4
+    # ring usable again afterwards
+    g.send_batch(np.zeros(3), np.ones(3), None, None, lens[:3], off[:3], buf)
+    assert g.receive_batch([1], 100)[0][0] == 3
+
+
+def test_arena_wraps_and_reclaims():
+    rng = np.random.default_rng(4)
+    A = 32
+    g, c = _pair(A, arena_bytes=1 << 16, ring_slots=64)      # 64 KiB arena: wraps every few batches
+    idx = np.arange(A, dtype=np.uint32)
+    for rnd in range(40):
+        n = 100
+        s = rng.integers(0, A, n); r = rng.integers(0, A, n)
+        lens, off, buf = _mk_payloads(rng, n, 200)
+        g.send_batch(s, r, None, None, lens, off, buf); c.send_batch(s, r, None, None, lens, off, buf)
+        _same(g.receive_batch(idx, 1000), c.receive_batch(idx, 1000))
+    st = g.stats()
+    assert st["arena_tail_bytes"] > 4 * (1 << 16)
+    # an undrained backlog larger than the arena must be refused, not overwritten
+    from swarmdb_b200._native import SdbError
+    with pytest.raises(SdbError):
+        for _ in range(40):
+            lens, off, buf = _mk_payloads(rng, 100, 200, fixed=True)
+            g.send_batch(rng.integers(0, A, 100), rng.integers(0, A, 100), None, None, lens, off, buf)
+
+
+def test_receive_capacity_truncates_by_whole_agents_without_loss():
+    rng = np.random.default_rng(8)
+    A = 50
+    g, c = _pair(A, max_recv_records=64, ring_slots=256)
+    idx = np.arange(A, dtype=np.uint32)
+    n = 2000
+    s = rng.integers(0, A, n); r = rng.integers(0, A, n)
+    lens, off, buf = _mk_payloads(rng, n, 64)
+    g.send_batch(s, r, None, None, lens, off, buf); c.send_batch(s, r, None, None, lens, off, buf)
+    got = {a: [] for a in range(A)}
+    for _ in range(1000):
+        cnt, hdr, pay = g.receive_batch(idx, 30)             # at most 2 agents x 30 fit in 64 records
+        if len(hdr) == 0:
+            break
+        assert len(hdr) <= 64
+        pos = 0
+        for a in range(A):
+            got[a].extend(hdr["seq"][pos:pos + cnt[a]].tolist()); pos += cnt[a]
+    cc, hc, pc = c.receive_batch(np.arange(A, dtype=np.uint32), 100000)
+    pos = 0
+    for a in range(A):
+        assert got[a] == hc["seq"][pos:pos + cc[a]].tolist(); pos += cc[a]
+
+
+@pytest.mark.parametrize("mode", [0, 1])
+def test_backend_select_matches_oracle(mode):
+    rng = np.random.default_rng(5)
+    g, c = _pair(4)
+    w = rng.integers(1, 9, 256); l0 = rng.integers(0, 50, 256)
+    g.set_backends(w, l0); c.set_backends(w, l0)
+    for n in (1, 1000, 100000):
+        pg, pc = g.select_backends(n, None, mode, seed=6), c.select_backends(n, None, mode, seed=6)
+        assert np.array_equal(pg, pc)
+        assert np.array_equal(g.backend_loads(), c.backend_loads())
+    cost = rng.integers(1, 20, 5000)
+    assert np.array_equal(g.select_backends(5000, cost, mode, seed=7), c.select_backends(5000, cost, mode, seed=7))
+    assert np.array_equal(g.backend_loads(), c.backend_loads())
+    g.release_backends([0, 1, 1], [1, 2, 3])
