@@ -217,7 +217,8 @@ def run_gpu(args, rank, world, local_rank):
 
     stream = torch.cuda.Stream()
     K, W = args.steps, args.warmup
-    shard = Shard(max_agents=wl.A, ring_slots=64, arena_bytes=1 << 33, max_payload_bytes=wl.L, max_groups=1 << 14,
+    ring_slots = int(os.environ.get("SDB_RING_SLOTS", "64"))
+    shard = Shard(max_agents=wl.A, ring_slots=ring_slots, arena_bytes=1 << 33, max_payload_bytes=wl.L, max_groups=1 << 14,
                   member_pool_entries=wl.A + 1024, max_batch_sends=wl.S, max_batch_payload=wl.S * wl.L,
                   max_recv_records=wl.S * wl.F + (1 << 16), max_recv_payload=(wl.S * wl.F + (1 << 16)) * wl.L,
                   device=local_rank, fanout_variant=args.variant)
@@ -307,7 +308,10 @@ def run_gpu(args, rank, world, local_rank):
     kernels["recv_gather"]["frac"] = kernels["recv_gather"]["achieved_gbs"] / peak if gat_n else None
 
     # ---- CPU baseline beside it (rank 0, N=1): bounded sample of the same workload
-    cpu_value, cores, kb, _ = cpu_roundtrip(wl, budget_s=args.cpu_budget, max_batches=8)
+    if args.cpu_budget > 0:
+        cpu_value, cores, kb, _ = cpu_roundtrip(wl, budget_s=args.cpu_budget, max_batches=8)
+    else:
+        cpu_value, cores, kb = None, os.cpu_count(), 0
 
     line = {
         "metric": "messages/sec routed (send->receive) at 1M agents, 64-way fanout",
@@ -318,7 +322,7 @@ def run_gpu(args, rank, world, local_rank):
                                "256-byte payloads, full drain (receive_batch all agents, max_messages=100) each step",
                    "l2": "inputs larger than L2: each step writes 1.2 GB of records into an 8 GiB arena and reads "
                          "them back; no explicit flush needed",
-                   "fanout_variant": args.variant, "ring_slots": 64, "arena_bytes": 1 << 33},
+                   "fanout_variant": args.variant, "ring_slots": ring_slots, "arena_bytes": 1 << 33},
         "clocks": clk,
         "e2e": {"value": e2e_value, "unit": "messages/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                 "steps": Ke, "ms_per_step": e2e_ms / Ke},
@@ -344,7 +348,7 @@ def main():
     ap.add_argument("--steps", type=int, default=16)
     ap.add_argument("--warmup", type=int, default=4)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--variant", type=int, default=int(os.environ.get("SDB_FANOUT_VARIANT", "0")))
+    ap.add_argument("--variant", type=int, default=int(os.environ.get("SDB_FANOUT_VARIANT", "2")))
     ap.add_argument("--cpu-budget", type=float, default=15.0)
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))

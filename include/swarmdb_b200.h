@@ -77,7 +77,7 @@ typedef struct sdb_config {
   uint64_t max_recv_records;    /* receive output capacity, records per call */
   uint64_t max_recv_payload;    /* receive output capacity, payload bytes per call (0: records x 256) */
   uint64_t list_pool_entries;   /* per-batch broadcast recipient-list capacity (0: 2 x max_agents) */
-  uint32_t fanout_variant;      /* 0: TMA-in / vector-store-out kernel, 1: TMA-in / TMA-out kernel */
+  uint32_t fanout_variant;      /* 2 (recommended): warp-per-send, TMA-in / coalesced stores; 0: CTA-per-send; 1: TMA-in / TMA-out */
   uint32_t flags;               /* reserved, 0 */
 } sdb_config;
 
@@ -121,7 +121,7 @@ int sdb_get_stats(sdb_handle h, sdb_stats* out);
 /* Per-kernel device timing (CUDA events on the handle's stream), used by bench.py for the
  * roofline: enable, run, then read accumulated milliseconds and launch counts per kernel class. */
 enum { SDB_PK_P2P = 0, SDB_PK_FANOUT, SDB_PK_COMMIT, SDB_PK_RECV_COUNT, SDB_PK_RECV_SCAN, SDB_PK_RECV_SELECT,
-       SDB_PK_RECV_GATHER, SDB_PK_ARENA_FLOOR, SDB_PK_PICK, SDB_PK_XSHARD, SDB_PK_N = 16 };
+       SDB_PK_RECV_GATHER, SDB_PK_ARENA_FLOOR, SDB_PK_PICK, SDB_PK_XSHARD, SDB_PK_INDEX, SDB_PK_N = 16 };
 int sdb_profile(sdb_handle h, int enable);
 int sdb_profile_read(sdb_handle h, double* ms_out /* [SDB_PK_N] */, uint64_t* count_out /* [SDB_PK_N] */);
 

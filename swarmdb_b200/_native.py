@@ -130,7 +130,7 @@ class Shard:
                  max_payload_bytes: int = 256, max_groups: int = 1, member_pool_entries: int = 0,
                  max_backends: int = 256, max_batch_sends: int = 65536, max_batch_payload: int = 0,
                  max_recv_records: int = 1 << 20, max_recv_payload: int = 0, list_pool_entries: int = 0,
-                 device: int = 0, shard_id: int = 0, num_shards: int = 1, fanout_variant: int = 0) -> None:
+                 device: int = 0, shard_id: int = 0, num_shards: int = 1, fanout_variant: int = 2) -> None:
         self._L = load_library()
         cfg = SdbConfig()
         cfg.struct_bytes = C.sizeof(SdbConfig)
@@ -186,7 +186,7 @@ class Shard:
         return {n: int(getattr(s, n)) for n, _ in SdbStats._fields_}
 
     PROFILE_KINDS = ["p2p", "fanout", "commit", "recv_count", "recv_scan", "recv_select", "recv_gather",
-                     "arena_floor", "pick", "xshard"]
+                     "arena_floor", "pick", "xshard", "index"]
 
     def profile(self, enable: bool) -> None:
         self._check(self._L.sdb_profile(self._h, 1 if enable else 0))

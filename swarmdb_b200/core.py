@@ -146,7 +146,7 @@ class GpuConfig:
     max_recv_payload: int = 1 << 26
     priority_dequeue: bool = False        # True: receive in (priority desc, arrival) order - extension
     deterministic_ids: bool = False       # True: ids are uuid.UUID(int=seq) (tests / reproducibility)
-    fanout_variant: int = 0
+    fanout_variant: int = 2
 
 
 def _encode_content(content: Any) -> (bytes, int):

@@ -20,7 +20,9 @@ cudaError_t sdb_launch_p2p(const sdb_dev_view*, const sdb_send_desc*, uint32_t, 
 cudaError_t sdb_launch_fanout(const sdb_dev_view*, const sdb_send_desc*, uint32_t, const uint8_t*, const uint32_t*,
                               uint64_t, uint64_t, uint32_t, int, int, cudaStream_t, sdb_profiler*);
 cudaError_t sdb_launch_commit(const sdb_dev_view*, uint32_t, uint32_t, cudaStream_t, sdb_profiler*);
-cudaError_t sdb_launch_receive(const sdb_dev_view*, const sdb_recv_args*, cudaStream_t, int*, sdb_profiler*);
+cudaError_t sdb_launch_pull(const sdb_dev_view*, const sdb_pull_view*, const sdb_send_desc*, uint32_t, uint64_t, int,
+                            cudaStream_t, sdb_profiler*);
+cudaError_t sdb_launch_receive(const sdb_dev_view*, const sdb_recv_args*, cudaStream_t, int*, sdb_profiler*, int);
 cudaError_t sdb_launch_arena_floor(const sdb_dev_view*, uint32_t, uint32_t, unsigned long long*, cudaStream_t);
 cudaError_t sdb_launch_pick(int mode, uint32_t n_backends, const uint32_t* weight_dev, unsigned long long* load_dev,
                             uint32_t n_req, const uint32_t* cost_dev, uint64_t seed, uint32_t* out_dev,
@@ -40,8 +42,15 @@ struct sdb_staged {
   sdb_send_desc* descs_dev = nullptr;
   uint8_t* payload_dev = nullptr;
   uint32_t* list_dev = nullptr;
+  uint32_t* gs_off_dev = nullptr;   // [max_groups + 1] group-send buckets (pull index build)
+  uint32_t* gs_idx_dev = nullptr;   // [n]
+  bool has_pull = false;      // group sends indexed by k_pull_index
+  bool has_atomic = false;    // some sends claim ring slots with atomics -> k_commit must sort
   bool owns = false;          // device buffers owned by this object (else the handle's staging)
 };
+
+// group batches at least this large build ring entries with the agent-parallel pull kernel
+static const uint64_t SDB_PULL_THRESHOLD = 16384;
 
 struct sdb_ctx {
   sdb_config cfg{};
@@ -62,12 +71,15 @@ struct sdb_ctx {
   sdb_send_desc* descs_host = nullptr;   // pinned
   sdb_staged scratch;                    // device descs/payload/list owned by the handle
   uint32_t* list_host = nullptr;         // pinned
+  uint32_t* gs_host = nullptr;           // pinned [max_groups + 1 + max_batch_sends]
+  // inverse group table (agent -> memberships), rebuilt lazily from `ghost`
+  uint32_t* memb_off_dev = nullptr; uint32_t* memb_grp_dev = nullptr; uint32_t* memb_pos_dev = nullptr;
+  bool memb_dirty = true;
   cudaEvent_t staging_free = nullptr;    // previous H2D of pinned staging has completed
   // receive scratch + outputs
   uint32_t* rx_agent = nullptr; uint32_t* rx_cnt = nullptr; uint32_t* rx_rec_local = nullptr; uint32_t* rx_rec_tops = nullptr;
-  uint32_t* rx_pay = nullptr; uint32_t* rx_pay_local = nullptr; uint32_t* rx_pay_tops = nullptr;
-  uint32_t* rx_old_head = nullptr; uint32_t* rx_new_head = nullptr; uint32_t* rx_new_ntomb = nullptr;
-  uint32_t* rx_sel_pos = nullptr; unsigned long long* rx_totals = nullptr;
+  uint32_t* rx_plan_handle = nullptr; uint32_t* rx_plan_glen = nullptr; uint32_t* rx_plan_local = nullptr;
+  uint32_t* rx_plan_tops = nullptr; unsigned long long* rx_totals = nullptr;
   uint32_t* rx_count = nullptr; sdb_msg_header* rx_hdr = nullptr; uint8_t* rx_payload = nullptr;
   unsigned long long* totals_host = nullptr;   // pinned [4]
   uint64_t pay_cap_gran = 0;
@@ -146,9 +158,11 @@ struct SendArrays {
 // Build descriptors into `out` (host).  kind 0: second = receiver; 1: second = group idx;
 // 2: list (list_off/list base offsets supplied).  Returns totals through the staged object.
 int build_descs(sdb_ctx* h, uint32_t batch_kind, uint32_t n, SendArrays& a, const uint64_t* list_off,
-                uint64_t payload_bytes, sdb_send_desc* out, sdb_staged* s) {
-  uint64_t rec = 0, gran = 0;
+                uint64_t payload_bytes, sdb_send_desc* out, sdb_staged* s, uint32_t* gs_out = nullptr,
+                uint32_t* n_gs_out = nullptr) {
+  uint64_t rec = 0, gran = 0, group_recs = 0;
   uint32_t max_padlen = 0;
+  uint32_t n_group_sends = 0, n_other = 0;
   const uint32_t A = h->cfg.max_agents;
   for (uint32_t i = 0; i < n; ++i) {
     sdb_send_desc d;
@@ -185,6 +199,7 @@ int build_descs(sdb_ctx* h, uint32_t batch_kind, uint32_t n, SendArrays& a, cons
         d.mstart = static_cast<uint32_t>(a.p2p_list_base + a.p2p_list_used); d.mcount = 1; d.flags = SDB_DESC_LIST_TEMP;
         a.p2p_list_used++;
         rec += 1; gran += d.rgran;
+        ++n_other;
         out[i] = d;
         continue;
       }
@@ -201,6 +216,7 @@ int build_descs(sdb_ctx* h, uint32_t batch_kind, uint32_t n, SendArrays& a, cons
       d.mstart = static_cast<uint32_t>(h->gstart[g]); d.mcount = h->gcount[g]; d.group = g;
       d.flags = SDB_DESC_SKIP_SENDER;
       rec += d.mcount; gran += static_cast<uint64_t>(d.mcount) * d.rgran;
+      group_recs += d.mcount; ++n_group_sends;
     } else {
       const uint32_t li = batch_kind == 3 ? a.second[i] : i;
       const uint64_t b = list_off[li], e = list_off[li + 1];
@@ -209,15 +225,54 @@ int build_descs(sdb_ctx* h, uint32_t batch_kind, uint32_t n, SendArrays& a, cons
       d.flags = SDB_DESC_SHARED_SEQ | SDB_DESC_LIST_TEMP;
       rec += 1; gran += static_cast<uint64_t>(d.mcount) * d.rgran;
     }
+    if (kind != 1) ++n_other;
     out[i] = d;
   }
   s->kind = batch_kind; s->n = n; s->total_recs = rec; s->total_grans = gran; s->max_padlen = max_padlen;
+  s->has_pull = false; s->has_atomic = true;
+  if (gs_out && group_recs >= SDB_PULL_THRESHOLD) {
+    // bucket the group sends by group (counting sort, ascending send index inside a bucket)
+    const uint32_t G = h->cfg.max_groups;
+    uint32_t* off = gs_out;            // [G + 1]
+    uint32_t* idx = gs_out + G + 1;    // [n_group_sends]
+    std::memset(off, 0, (static_cast<size_t>(G) + 1) * sizeof(uint32_t));
+    for (uint32_t i = 0; i < n; ++i) if (out[i].flags & SDB_DESC_SKIP_SENDER) off[out[i].group + 1]++;
+    for (uint32_t g = 0; g < G; ++g) off[g + 1] += off[g];
+    std::vector<uint32_t> cur(off, off + G);
+    for (uint32_t i = 0; i < n; ++i) if (out[i].flags & SDB_DESC_SKIP_SENDER) { idx[cur[out[i].group]++] = i; out[i].flags |= SDB_DESC_PULL; }
+    s->has_pull = true; s->has_atomic = n_other != 0;
+    *n_gs_out = n_group_sends;
+  }
+  return SDB_OK;
+}
+
+// agent -> (group, position) lists, CSR over agents, from the authoritative host group table
+int rebuild_inverse(sdb_ctx* h) {
+  const uint32_t A = h->cfg.max_agents, G = h->cfg.max_groups;
+  std::vector<uint32_t> off(static_cast<size_t>(A) + 1, 0);
+  uint64_t total = 0;
+  for (uint32_t g = 0; g < G; ++g) if (h->gdefined[g]) { for (uint32_t m : h->ghost[g]) off[m + 1]++; total += h->ghost[g].size(); }
+  if (total > h->cfg.member_pool_entries) return fail(h, SDB_ECAPACITY, "memberships exceed member_pool_entries");
+  for (uint32_t a = 0; a < A; ++a) off[a + 1] += off[a];
+  std::vector<uint32_t> grp(total ? total : 1), pos(total ? total : 1), cur(off.begin(), off.end() - 1);
+  for (uint32_t g = 0; g < G; ++g) if (h->gdefined[g]) {
+    const std::vector<uint32_t>& ms = h->ghost[g];
+    for (uint32_t j = 0; j < ms.size(); ++j) { const uint32_t c = cur[ms[j]]++; grp[c] = g; pos[c] = j; }
+  }
+  CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+  CUDA_TRY(h, cudaMemcpy(h->memb_off_dev, off.data(), off.size() * sizeof(uint32_t), cudaMemcpyHostToDevice));
+  if (total) {
+    CUDA_TRY(h, cudaMemcpy(h->memb_grp_dev, grp.data(), total * sizeof(uint32_t), cudaMemcpyHostToDevice));
+    CUDA_TRY(h, cudaMemcpy(h->memb_pos_dev, pos.data(), total * sizeof(uint32_t), cudaMemcpyHostToDevice));
+  }
+  h->memb_dirty = false;
   return SDB_OK;
 }
 
 int submit(sdb_ctx* h, const sdb_staged* s, uint64_t* seq_base_out) {
   if (seq_base_out) *seq_base_out = h->next_seq;
   if (s->n == 0) return SDB_OK;
+  if (s->has_pull && h->memb_dirty) { int rc0 = rebuild_inverse(h); if (rc0 != SDB_OK) return rc0; }
   uint64_t base = 0;
   int rc = arena_reserve(h, s->total_grans, &base);
   if (rc != SDB_OK) return rc;
@@ -228,8 +283,16 @@ int submit(sdb_ctx* h, const sdb_staged* s, uint64_t* seq_base_out) {
     e = sdb_launch_fanout(&h->view, s->descs_dev, s->n, s->payload_dev, s->list_dev, h->next_seq, base,
                           s->max_padlen, static_cast<int>(h->cfg.fanout_variant), h->sm_count, h->stream, &h->prof);
   }
-  if (e == cudaSuccess) e = sdb_launch_commit(&h->view, h->n_agents, static_cast<uint32_t>(base), h->stream, &h->prof);
-  h->launches += 2;
+  h->launches += 1;
+  if (e == cudaSuccess && s->has_pull) {
+    sdb_pull_view pv{h->memb_off_dev, h->memb_grp_dev, h->memb_pos_dev, s->gs_off_dev, s->gs_idx_dev};
+    e = sdb_launch_pull(&h->view, &pv, s->descs_dev, h->n_agents, base, s->has_atomic ? 0 : 1, h->stream, &h->prof);
+    h->launches += 1;
+  }
+  if (e == cudaSuccess && s->has_atomic) {
+    e = sdb_launch_commit(&h->view, h->n_agents, static_cast<uint32_t>(base), h->stream, &h->prof);
+    h->launches += 1;
+  }
   if (e != cudaSuccess) return fail(h, SDB_ECUDA, std::string("enqueue launch: ") + cudaGetErrorString(e));
   h->next_seq += s->total_recs;
   h->arena_tail = base + s->total_grans;
@@ -259,8 +322,14 @@ int send_common(sdb_ctx* h, uint32_t kind, uint32_t n, SendArrays& a, const uint
     if (list_total) std::memcpy(h->list_host, list_idx, list_total * sizeof(uint32_t));
     a.p2p_list = h->list_host + list_total; a.p2p_list_base = list_total; a.p2p_list_cap = cap - list_total;
   }
-  int rc = build_descs(h, kind, n, a, list_off, payload_bytes, h->descs_host, s);
+  uint32_t n_gs = 0;
+  int rc = build_descs(h, kind, n, a, list_off, payload_bytes, h->descs_host, s, h->gs_host, &n_gs);
   if (rc != SDB_OK) return rc;
+  if (s->has_pull) {
+    const size_t G1 = static_cast<size_t>(h->cfg.max_groups) + 1;
+    CUDA_TRY(h, cudaMemcpyAsync(s->gs_off_dev, h->gs_host, G1 * sizeof(uint32_t), cudaMemcpyHostToDevice, h->stream));
+    CUDA_TRY(h, cudaMemcpyAsync(s->gs_idx_dev, h->gs_host + G1, static_cast<size_t>(n_gs) * sizeof(uint32_t), cudaMemcpyHostToDevice, h->stream));
+  }
   list_total += a.p2p_list_used;
   if (list_total)
     CUDA_TRY(h, cudaMemcpyAsync(s->list_dev, h->list_host, list_total * sizeof(uint32_t), cudaMemcpyHostToDevice, h->stream));
@@ -304,7 +373,7 @@ int sdb_create(const sdb_config* cfg, sdb_handle* out) {
   if (c.max_recv_records > 0xFFFFFFF0ull) return fail(h, SDB_EINVAL, "max_recv_records too large");
   if (c.max_recv_payload == 0) c.max_recv_payload = c.max_recv_records * 256ull;
   if (c.list_pool_entries == 0) c.list_pool_entries = 2ull * c.max_agents + 1024;
-  if (c.fanout_variant > 1) return fail(h, SDB_EINVAL, "fanout_variant must be 0 or 1");
+  if (c.fanout_variant > 2) return fail(h, SDB_EINVAL, "fanout_variant must be 0, 1 or 2");
 
   int ndev = 0;
   if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
@@ -340,15 +409,21 @@ int sdb_create(const sdb_config* cfg, sdb_handle* out) {
   CUDA_TRY(h, dmalloc(&h->scratch.descs_dev, c.max_batch_sends));
   CUDA_TRY(h, dmalloc(&h->scratch.payload_dev, c.max_batch_payload + 64));
   CUDA_TRY(h, dmalloc(&h->scratch.list_dev, c.list_pool_entries));
+  CUDA_TRY(h, dmalloc(&h->scratch.gs_off_dev, static_cast<size_t>(c.max_groups) + 1));
+  CUDA_TRY(h, dmalloc(&h->scratch.gs_idx_dev, c.max_batch_sends));
+  CUDA_TRY(h, cudaHostAlloc(reinterpret_cast<void**>(&h->gs_host), (static_cast<size_t>(c.max_groups) + 1 + c.max_batch_sends) * sizeof(uint32_t), cudaHostAllocDefault));
+  CUDA_TRY(h, dmalloc(&h->memb_off_dev, static_cast<size_t>(c.max_agents) + 1));
+  CUDA_TRY(h, dmalloc(&h->memb_grp_dev, c.member_pool_entries));
+  CUDA_TRY(h, dmalloc(&h->memb_pos_dev, c.member_pool_entries));
   CUDA_TRY(h, cudaMemsetAsync(h->scratch.payload_dev, 0, c.max_batch_payload + 64, h->stream));
 
   // receive scratch
   const size_t tiles = (A + SDB_SCAN_TILE - 1) / SDB_SCAN_TILE + 1;
   CUDA_TRY(h, dmalloc(&h->rx_agent, A)); CUDA_TRY(h, dmalloc(&h->rx_cnt, A));
   CUDA_TRY(h, dmalloc(&h->rx_rec_local, A)); CUDA_TRY(h, dmalloc(&h->rx_rec_tops, tiles));
-  CUDA_TRY(h, dmalloc(&h->rx_pay, A)); CUDA_TRY(h, dmalloc(&h->rx_pay_local, A)); CUDA_TRY(h, dmalloc(&h->rx_pay_tops, tiles));
-  CUDA_TRY(h, dmalloc(&h->rx_old_head, A)); CUDA_TRY(h, dmalloc(&h->rx_new_head, A)); CUDA_TRY(h, dmalloc(&h->rx_new_ntomb, A));
-  CUDA_TRY(h, dmalloc(&h->rx_sel_pos, c.max_recv_records));
+  const size_t rtiles = (c.max_recv_records + SDB_SCAN_TILE - 1) / SDB_SCAN_TILE + 1;
+  CUDA_TRY(h, dmalloc(&h->rx_plan_handle, c.max_recv_records + 4)); CUDA_TRY(h, dmalloc(&h->rx_plan_glen, c.max_recv_records + 4));
+  CUDA_TRY(h, dmalloc(&h->rx_plan_local, c.max_recv_records + 4)); CUDA_TRY(h, dmalloc(&h->rx_plan_tops, rtiles));
   CUDA_TRY(h, dmalloc(&h->rx_totals, 4));
   CUDA_TRY(h, dmalloc(&h->rx_count, A));
   CUDA_TRY(h, dmalloc(&h->rx_hdr, c.max_recv_records));
@@ -384,13 +459,15 @@ int sdb_destroy(sdb_handle h) {
   cudaSetDevice(h->cfg.device);
   if (h->stream) cudaStreamSynchronize(h->stream);
   void* dev[] = {h->arena, h->ring_state, h->ring_handle, h->ring_meta, h->ctail, h->ntomb, h->members, h->ctr,
-                 h->scratch.descs_dev, h->scratch.payload_dev, h->scratch.list_dev, h->rx_agent, h->rx_cnt,
-                 h->rx_rec_local, h->rx_rec_tops, h->rx_pay, h->rx_pay_local, h->rx_pay_tops, h->rx_old_head,
-                 h->rx_new_head, h->rx_new_ntomb, h->rx_sel_pos, h->rx_totals, h->rx_count, h->rx_hdr, h->rx_payload,
+                 h->scratch.descs_dev, h->scratch.payload_dev, h->scratch.list_dev, h->scratch.gs_off_dev,
+                 h->scratch.gs_idx_dev, h->memb_off_dev, h->memb_grp_dev, h->memb_pos_dev, h->rx_agent, h->rx_cnt,
+                 h->rx_rec_local, h->rx_rec_tops, h->rx_plan_handle, h->rx_plan_glen, h->rx_plan_local, h->rx_plan_tops,
+                 h->rx_totals, h->rx_count, h->rx_hdr, h->rx_payload,
                  h->be_weight, h->be_load, h->be_scratch, h->be_logtab, h->be_req_cost, h->be_out};
   for (void* p : dev) if (p) cudaFree(p);
   if (h->descs_host) cudaFreeHost(h->descs_host);
   if (h->list_host) cudaFreeHost(h->list_host);
+  if (h->gs_host) cudaFreeHost(h->gs_host);
   if (h->totals_host) cudaFreeHost(h->totals_host);
   if (h->staging_free) cudaEventDestroy(h->staging_free);
   if (h->prof.cap) {
@@ -475,6 +552,7 @@ int sdb_deregister_agents(sdb_handle h, uint32_t n, const uint32_t* agent_idx) {
 int sdb_create_group(sdb_handle h, uint32_t g, uint32_t n_members, const uint32_t* member_idx) {
   if (!h || (n_members && !member_idx)) return SDB_EINVAL;
   if (g >= h->cfg.max_groups) return fail(h, SDB_EINVAL, "group index >= max_groups");
+  h->memb_dirty = true;
   for (uint32_t i = 0; i < n_members; ++i) {
     if (member_idx[i] >= h->cfg.max_agents) return fail(h, SDB_EINVAL, "member index >= max_agents");
     h->n_agents = std::max(h->n_agents, member_idx[i] + 1);   // members will receive: keep them inside the commit sweep
@@ -551,10 +629,19 @@ int sdb_stage_batch(sdb_handle h, uint32_t kind, uint32_t n, const uint32_t* sen
   if (!s) return SDB_ENOMEM;
   s->owns = true;
   std::vector<sdb_send_desc> descs(n);
+  std::vector<uint32_t> gs(static_cast<size_t>(h->cfg.max_groups) + 1 + n);
+  uint32_t n_gs = 0;
   SendArrays a{sender, second, prio, type, len, payload_off, timestamp};
-  int rc = build_descs(h, kind, n, a, nullptr, payload_bytes, descs.data(), s);
+  int rc = build_descs(h, kind, n, a, nullptr, payload_bytes, descs.data(), s, gs.data(), &n_gs);
   if (rc != SDB_OK) { delete s; return rc; }
   cudaError_t e = dmalloc(&s->descs_dev, n);
+  if (e == cudaSuccess && s->has_pull) {
+    const size_t G1 = static_cast<size_t>(h->cfg.max_groups) + 1;
+    e = dmalloc(&s->gs_off_dev, G1);
+    if (e == cudaSuccess) e = dmalloc(&s->gs_idx_dev, n_gs ? n_gs : 1);
+    if (e == cudaSuccess) e = cudaMemcpy(s->gs_off_dev, gs.data(), G1 * sizeof(uint32_t), cudaMemcpyHostToDevice);
+    if (e == cudaSuccess && n_gs) e = cudaMemcpy(s->gs_idx_dev, gs.data() + G1, static_cast<size_t>(n_gs) * sizeof(uint32_t), cudaMemcpyHostToDevice);
+  }
   if (e == cudaSuccess) e = dmalloc(&s->payload_dev, payload_bytes + 64);
   if (e == cudaSuccess) e = cudaMemset(s->payload_dev, 0, payload_bytes + 64);
   if (e == cudaSuccess) e = cudaMemcpy(s->descs_dev, descs.data(), static_cast<size_t>(n) * sizeof(sdb_send_desc), cudaMemcpyHostToDevice);
@@ -562,6 +649,8 @@ int sdb_stage_batch(sdb_handle h, uint32_t kind, uint32_t n, const uint32_t* sen
   if (e != cudaSuccess) {
     if (s->descs_dev) cudaFree(s->descs_dev);
     if (s->payload_dev) cudaFree(s->payload_dev);
+    if (s->gs_off_dev) cudaFree(s->gs_off_dev);
+    if (s->gs_idx_dev) cudaFree(s->gs_idx_dev);
     delete s;
     return fail(h, SDB_ECUDA, std::string("stage: ") + cudaGetErrorString(e));
   }
@@ -577,7 +666,11 @@ int sdb_submit_staged(sdb_handle h, sdb_staged_t s, uint64_t* seq_base_out) {
 int sdb_free_staged(sdb_handle h, sdb_staged_t s) {
   if (!h || !s) return SDB_EINVAL;
   cudaStreamSynchronize(h->stream);
-  if (s->owns) { cudaFree(s->descs_dev); cudaFree(s->payload_dev); }
+  if (s->owns) {
+    cudaFree(s->descs_dev); cudaFree(s->payload_dev);
+    if (s->gs_off_dev) cudaFree(s->gs_off_dev);
+    if (s->gs_idx_dev) cudaFree(s->gs_idx_dev);
+  }
   delete s;
   return SDB_OK;
 }
@@ -598,14 +691,19 @@ int sdb_receive_batch(sdb_handle h, uint32_t n_agents, const uint32_t* agent_idx
   }
   sdb_recv_args r{};
   r.agent_idx = agent_idx ? h->rx_agent : nullptr; r.n = n_agents; r.max_messages = max_messages; r.flags = flags;
-  r.cnt = h->rx_cnt; r.rec_local = h->rx_rec_local; r.rec_tops = h->rx_rec_tops; r.pay = h->rx_pay;
-  r.pay_local = h->rx_pay_local; r.pay_tops = h->rx_pay_tops; r.old_head = h->rx_old_head; r.new_head = h->rx_new_head;
-  r.new_ntomb = h->rx_new_ntomb; r.sel_pos = h->rx_sel_pos; r.totals = h->rx_totals;
+  r.cnt = h->rx_cnt; r.rec_local = h->rx_rec_local; r.rec_tops = h->rx_rec_tops;
+  r.plan_handle = h->rx_plan_handle; r.plan_glen = h->rx_plan_glen; r.plan_local = h->rx_plan_local;
+  r.plan_tops = h->rx_plan_tops; r.totals = h->rx_totals;
   r.count_out = h->rx_count; r.hdr_out = h->rx_hdr; r.payload_out = h->rx_payload;
-  r.rec_cap = hdr_out ? std::min<uint64_t>(h->cfg.max_recv_records, hdr_cap) : h->cfg.max_recv_records;
-  r.pay_cap_gran = payload_out ? std::min<uint64_t>(h->pay_cap_gran, payload_cap / SDB_GRANULE) : h->pay_cap_gran;
+  // record capacity: bounded so that even maximum-size payloads fit the payload buffers
+  const uint64_t max_rec_bytes = pad32(h->cfg.max_payload_bytes);
+  uint64_t rec_cap = std::min<uint64_t>(h->cfg.max_recv_records, h->pay_cap_gran * SDB_GRANULE / max_rec_bytes);
+  if (hdr_out) rec_cap = std::min<uint64_t>(rec_cap, hdr_cap);
+  if (payload_out) rec_cap = std::min<uint64_t>(rec_cap, payload_cap / max_rec_bytes);
+  if (rec_cap == 0) return fail(h, SDB_EOUTPUT, "output buffers cannot hold a single maximum-size record");
+  r.rec_cap = rec_cap;
   int nl = 0;
-  cudaError_t e = sdb_launch_receive(&h->view, &r, h->stream, &nl, &h->prof);
+  cudaError_t e = sdb_launch_receive(&h->view, &r, h->stream, &nl, &h->prof, h->sm_count);
   h->launches += nl;
   if (e != cudaSuccess) return fail(h, SDB_ECUDA, std::string("receive launch: ") + cudaGetErrorString(e));
   CUDA_TRY(h, cudaMemcpyAsync(h->totals_host, h->rx_totals, 2 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, h->stream));

@@ -31,21 +31,26 @@
 #define SDB_META_TOMB 0xFFFFu
 #define SDB_META_GLEN_MASK 0x3FFFu
 
-// per-send descriptor staged to the device (64 B, one per send)
+// per-send descriptor staged to the device (64 B, one per send); q1 is all the index-build
+// kernel needs, so it reads 16 bytes per (agent, send) pair
 struct __align__(16) sdb_send_desc {
+  // q0
   uint64_t payload_off;  // byte offset into the batch payload buffer, 16-B aligned
   double   timestamp;
-  uint32_t rec0;         // seq offset of member 0 relative to the batch seq base
+  // q1
   uint32_t gran0;        // arena granule offset of member 0 relative to the batch arena base
   uint32_t sender;
-  uint32_t mstart;       // first member in the member pool (group/list) or receiver idx (p2p)
-  uint32_t mcount;       // members (1 for p2p)
-  uint32_t group;        // group index or SDB_NO_GROUP
+  uint32_t rgran;        // granules per record = 1 + pad32(len)/32
   uint16_t len;
   uint8_t  prio;
   uint8_t  type;
+  // q2
+  uint32_t rec0;         // seq offset of member 0 relative to the batch seq base
+  uint32_t mstart;       // first member in the member pool (group/list) or receiver idx (p2p)
+  uint32_t mcount;       // members (1 for p2p)
+  uint32_t group;        // group index or SDB_NO_GROUP
+  // q3
   uint32_t flags;        // SDB_DESC_*
-  uint32_t rgran;        // granules per record = 1 + pad32(len)/32
   uint32_t pad[3];
 };
 static_assert(sizeof(sdb_send_desc) == 64, "desc must be 64 bytes");
@@ -54,6 +59,17 @@ static_assert(sizeof(sdb_msg_header) == 32, "header must be 32 bytes");
 #define SDB_DESC_SKIP_SENDER 1u   // group send: member == sender is skipped (M:1268)
 #define SDB_DESC_SHARED_SEQ 2u    // broadcast: every copy carries the same seq (one Message)
 #define SDB_DESC_LIST_TEMP 4u     // mstart indexes the per-batch temporary list buffer
+#define SDB_DESC_PULL 8u          // ring entries are built by k_pull_index, not by the fan-out kernel
+
+// per-batch view for the agent-parallel index build ("pull"): group sends of the batch bucketed
+// by group (gs_*), and the inverse of the group table (which groups/positions an agent is in)
+struct sdb_pull_view {
+  const uint32_t* memb_off;   // [max_agents + 1]
+  const uint32_t* memb_grp;   // [memberships]
+  const uint32_t* memb_pos;   // [memberships] position of the agent inside that group's member list
+  const uint32_t* gs_off;     // [max_groups + 1] bucket offsets into gs_idx
+  const uint32_t* gs_idx;     // [group sends of the batch] send indices, ascending inside a bucket
+};
 
 struct sdb_dev_counters {   // device-resident, updated with atomics
   unsigned long long enqueued;
@@ -86,20 +102,20 @@ struct sdb_recv_args {
   uint32_t n;
   uint32_t max_messages;
   uint32_t flags;
-  // scratch, all [n] unless noted
-  uint32_t* cnt;         // selected count | SDB_MODE_LIST
-  uint32_t* rec_local;   uint32_t* rec_tops;    // scan of cnt
-  uint32_t* pay;         // payload granules per agent
-  uint32_t* pay_local;   uint32_t* pay_tops;    // scan of pay
-  uint32_t* old_head;    uint32_t* new_head;    uint32_t* new_ntomb;
-  uint32_t* sel_pos;     // [rec_cap] ring positions of selected entries (list mode)
-  unsigned long long* totals;   // [2] {records, payload granules} actually delivered
+  uint32_t* cnt;               // [n] records selected per agent
+  uint32_t* rec_local;         // [n] scan of cnt (block-local part)
+  uint32_t* rec_tops;          // [tiles] scan of cnt (per-block part)
+  // per-record plan, indexed by output record number r = rec_off[agent] + rank
+  uint32_t* plan_handle;       // [rec_cap] arena handle of record r
+  uint32_t* plan_glen;         // [rec_cap] payload granules of record r
+  uint32_t* plan_local;        // [rec_cap] scan of plan_glen (block-local part)
+  uint32_t* plan_tops;         // [rec tiles]
+  unsigned long long* totals;  // [0] records delivered, [1] payload granules delivered
   // outputs
-  uint32_t* count_out;          // [n]
-  sdb_msg_header* hdr_out;      // [rec_cap]
-  uint8_t* payload_out;         // [pay_cap_gran * 32]
+  uint32_t* count_out;         // [n]
+  sdb_msg_header* hdr_out;     // [rec_cap]
+  uint8_t* payload_out;        // [rec_cap * pad32(max_payload)]
   uint64_t rec_cap;
-  uint64_t pay_cap_gran;
 };
 
 // ---- optional per-kernel timing with CUDA events on the launching stream (bench / roofline) ----

@@ -5,7 +5,8 @@
 // Pipeline of one sdb_receive_batch call (all stream-ordered, no host round trip inside):
 //   k_recv_count    cnt[q]   = min(max_messages, live(agent q))
 //   scan            rec_off  = exclusive scan of cnt             (k_scan_local + k_scan_tops)
-//   k_recv_select   per agent: choose WHICH pending entries are delivered
+//   k_recv_select   per agent: choose WHICH pending entries are delivered, write the per-record
+//                   plan (arena handle, payload size) at the record's output index, retire them
 //                     stream order      -> the first cnt live entries (contiguous when the
 //                                          window holds no consumed entries: nothing to do);
 //                     priority order    -> segmented radix-select on the 2-bit priority:
@@ -13,10 +14,8 @@
 //                                          warp ballots/popc, pick the cut level and residual,
 //                                          pass 2 stable compaction (ballot prefix ranks) of
 //                                          the selected ring positions in (prio desc, arrival);
-//                   also payload granules per agent and the would-be new head / tombstone count
-//   scan            pay_off  = exclusive scan of payload granules per agent
-//   k_recv_gather   per agent: copy header + payload of each selected record from the arena to
-//                   the packed output, then retire the entries (advance head / tombstone)
+//   scan            pay_off  = exclusive scan of payload granules over the planned RECORDS
+//   k_recv_gather   flat over records: copy header + payload from the arena to the packed output
 //
 // Roofline: HBM-bound.  Algorithmic bytes per agent-call: P*1 priority bytes scanned (we scan
 // 2-byte ring_meta entries) + 2*k*(L+H) gather+emit.
@@ -122,9 +121,12 @@ k_recv_count(sdb_dev_view v, sdb_recv_args r) {
 }
 
 // ------------------------------------------------------------------------------------------
-// select: one warp owns 32 consecutive agents of the request list.  Agents whose selection is
-// a short contiguous run are finished by their own lane; the rest are processed one at a
-// time by the whole warp (window scans with ballots).
+// select + retire: one warp owns 32 consecutive agents of the request list.  Agents whose
+// selection is a short contiguous run are finished by their own lane; the rest are processed
+// one at a time by the whole warp (window scans with ballots).  For every selected record the
+// plan (arena handle, payload granules) is written at its output index, the ring entry is
+// retired (head advanced / tombstoned), and count_out is final.  Agents that would overflow
+// the record capacity are left untouched (whole-agent truncation: nothing is ever lost).
 // ------------------------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t lane_prefix(uint32_t ballot, uint32_t lane) {
   return __popc(ballot & ((1u << lane) - 1u));
@@ -142,7 +144,11 @@ k_recv_select(sdb_dev_view v, sdb_recv_args r) {
     a = r.agent_idx ? r.agent_idx[q] : q;
     cnt = r.cnt[q];
     roff = r.rec_local[q] + r.rec_tops[q / SDB_SCAN_TILE];
-    if (static_cast<uint64_t>(roff) + cnt > r.rec_cap) cnt = 0;     // whole-agent truncation, lossless
+    if (cnt && static_cast<uint64_t>(roff) + cnt > r.rec_cap) {      // does not fit: stays queued
+      atomicMin(r.totals, static_cast<unsigned long long>(roff));
+      cnt = 0;
+    }
+    r.count_out[q] = cnt;
     if (cnt) {
       const uint64_t st = v.ring_state[a];
       head = static_cast<uint32_t>(st); tail = static_cast<uint32_t>(st >> 32);
@@ -150,18 +156,21 @@ k_recv_select(sdb_dev_view v, sdb_recv_args r) {
     }
   }
   const bool prio_mode = (r.flags & SDB_RECV_PRIORITY) != 0;
-  const bool contiguous = !prio_mode && nt == 0;
   constexpr uint32_t SMALL = 8;
   bool done = !valid || cnt == 0;
-  if (valid && cnt == 0) { r.cnt[q] = 0; r.pay[q] = 0; }
-  if (!done && contiguous && cnt <= SMALL) {
+  if (!done && !prio_mode && nt == 0 && cnt <= SMALL) {
     const uint16_t* ms = v.ring_meta + (static_cast<size_t>(a) << v.ring_shift);
-    uint32_t g = 0;
-    for (uint32_t j = 0; j < cnt; ++j) g += (ms[(head + j) & mask] & SDB_META_GLEN_MASK) - 1u;
-    r.pay[q] = g; r.cnt[q] = cnt; r.old_head[q] = head; r.new_head[q] = head + cnt; r.new_ntomb[q] = 0;
+    const uint32_t* hs = v.ring_handle + (static_cast<size_t>(a) << v.ring_shift);
+    for (uint32_t j = 0; j < cnt; ++j) {
+      r.plan_handle[roff + j] = hs[(head + j) & mask];
+      r.plan_glen[roff + j] = (ms[(head + j) & mask] & SDB_META_GLEN_MASK) - 1u;
+    }
+    reinterpret_cast<uint32_t*>(v.ring_state + a)[0] = head + cnt;    // low word = head (little endian)
     done = true;
   }
   uint32_t todo = __ballot_sync(0xFFFFFFFFu, !done);
+  uint32_t n_deliv = __popc(0);
+  n_deliv = valid ? cnt : 0;
   while (todo) {
     const int src = __ffs(todo) - 1;
     todo &= todo - 1;
@@ -171,15 +180,16 @@ k_recv_select(sdb_dev_view v, sdb_recv_args r) {
     const uint32_t NT = __shfl_sync(0xFFFFFFFFu, nt, src);
     const uint32_t C = __shfl_sync(0xFFFFFFFFu, cnt, src);
     const uint32_t RO = __shfl_sync(0xFFFFFFFFu, roff, src);
-    const uint32_t Q = (q - lane) + src;
-    const uint16_t* ms = v.ring_meta + (static_cast<size_t>(A) << v.ring_shift);
+    uint16_t* ms = v.ring_meta + (static_cast<size_t>(A) << v.ring_shift);
+    const uint32_t* hs = v.ring_handle + (static_cast<size_t>(A) << v.ring_shift);
 
     if (!prio_mode && NT == 0) {
-      // long contiguous run: just add up payload granules
-      uint32_t g = 0;
-      for (uint32_t j = lane; j < C; j += 32) g += (ms[(H + j) & mask] & SDB_META_GLEN_MASK) - 1u;
-      for (int o = 16; o; o >>= 1) g += __shfl_xor_sync(0xFFFFFFFFu, g, o);
-      if (lane == 0) { r.pay[Q] = g; r.cnt[Q] = C; r.old_head[Q] = H; r.new_head[Q] = H + C; r.new_ntomb[Q] = 0; }
+      // long contiguous run [H, H+C)
+      for (uint32_t j = lane; j < C; j += 32) {
+        r.plan_handle[RO + j] = hs[(H + j) & mask];
+        r.plan_glen[RO + j] = (ms[(H + j) & mask] & SDB_META_GLEN_MASK) - 1u;
+      }
+      if (lane == 0) reinterpret_cast<uint32_t*>(v.ring_state + A)[0] = H + C;
       continue;
     }
     // ---- pass 1: histogram of live entries per priority level over the window [H, T)
@@ -191,7 +201,6 @@ k_recv_select(sdb_dev_view v, sdb_recv_args r) {
         const uint32_t L = m >> 14;
         h0 += (L == 0); h1 += (L == 1); h2 += (L == 2); h3 += (L == 3);
       }
-      // 4 counters, each < 2^16 per lane only if window < 2M entries: reduce as two packed u64
       unsigned long long lo = (static_cast<unsigned long long>(h1) << 32) | h0;
       unsigned long long hi = (static_cast<unsigned long long>(h3) << 32) | h2;
       for (int o = 16; o; o >>= 1) {
@@ -203,7 +212,7 @@ k_recv_select(sdb_dev_view v, sdb_recv_args r) {
     } else {
       h0 = (T - H) - NT;     // single level: every live entry
     }
-    // ---- cut: take every entry of levels above `cut`, and the first `resid` of level `cut`
+    // ---- cut: take every entry of the levels above the cut, and the first `quota` of the cut level
     uint32_t hist[4] = {h0, h1, h2, h3};
     uint32_t quota[4] = {0, 0, 0, 0}, basek[4] = {0, 0, 0, 0};
     {
@@ -216,7 +225,7 @@ k_recv_select(sdb_dev_view v, sdb_recv_args r) {
     // ---- pass 2: stable compaction of the selected positions, window order within a level
     uint32_t taken[4] = {0, 0, 0, 0};
     uint32_t first_unsel = T;      // first live entry left behind
-    uint32_t g = 0, got = 0;
+    uint32_t got = 0;
     uint32_t p0 = H;
     for (; static_cast<int32_t>(T - p0) > 0 && got < C; p0 += 32) {
       const uint32_t p = p0 + lane;
@@ -235,8 +244,9 @@ k_recv_select(sdb_dev_view v, sdb_recv_args r) {
         taken[lev] += __popc(b);
       }
       if (sel) {
-        r.sel_pos[RO + rank] = p;
-        g += (m & SDB_META_GLEN_MASK) - 1u;
+        r.plan_handle[RO + rank] = hs[p & mask];
+        r.plan_glen[RO + rank] = (m & SDB_META_GLEN_MASK) - 1u;
+        ms[p & mask] = SDB_META_TOMB;                      // retire
       }
       const uint32_t bs = __ballot_sync(0xFFFFFFFFu, sel);
       got += __popc(bs);
@@ -246,108 +256,126 @@ k_recv_select(sdb_dev_view v, sdb_recv_args r) {
     const uint32_t scan_end = static_cast<int32_t>(T - p0) > 0 ? p0 : T;
     uint32_t nh = first_unsel;
     if (static_cast<int32_t>(nh - scan_end) > 0) nh = scan_end;
-    for (int o = 16; o; o >>= 1) g += __shfl_xor_sync(0xFFFFFFFFu, g, o);
     if (lane == 0) {
-      r.pay[Q] = g; r.cnt[Q] = got | SDB_MODE_LIST; r.old_head[Q] = H;
-      r.new_head[Q] = nh; r.new_ntomb[Q] = NT + got - (nh - H);
+      reinterpret_cast<uint32_t*>(v.ring_state + A)[0] = nh;
+      v.ntomb[A] = NT + got - (nh - H);
     }
+  }
+  for (int o = 16; o; o >>= 1) n_deliv += __shfl_xor_sync(0xFFFFFFFFu, n_deliv, o);
+  if (lane == 0 && n_deliv) atomicAdd(&v.ctr->delivered, static_cast<unsigned long long>(n_deliv));
+}
+
+// scan over the per-record payload sizes; the element count lives on the device (totals[0])
+__global__ void __launch_bounds__(1024)
+k_scan_plan(const uint32_t* __restrict__ in, uint32_t* __restrict__ local, uint32_t* __restrict__ tops,
+            const unsigned long long* __restrict__ n_dev) {
+  __shared__ uint32_t s_warp[32];
+  const uint32_t n = static_cast<uint32_t>(*n_dev);
+  const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const uint32_t base = blockIdx.x * SDB_SCAN_TILE + tid * 4u;
+  if (blockIdx.x * SDB_SCAN_TILE >= n) { if (tid == 0) tops[blockIdx.x] = 0; return; }
+  uint32_t x[4];
+  if (base + 3 < n) {
+    const uint4 q = *reinterpret_cast<const uint4*>(in + base);
+    x[0] = q.x; x[1] = q.y; x[2] = q.z; x[3] = q.w;
+  } else {
+#pragma unroll
+    for (int k = 0; k < 4; ++k) x[k] = (base + k < n) ? in[base + k] : 0u;
+  }
+  const uint32_t tsum = x[0] + x[1] + x[2] + x[3];
+  uint32_t incl = tsum;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const uint32_t y = __shfl_up_sync(0xFFFFFFFFu, incl, o);
+    if (lane >= o) incl += y;
+  }
+  if (lane == 31) s_warp[warp] = incl;
+  __syncthreads();
+  if (warp == 0) {
+    const uint32_t w = s_warp[lane];
+    uint32_t wi = w;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const uint32_t y = __shfl_up_sync(0xFFFFFFFFu, wi, o);
+      if (lane >= o) wi += y;
+    }
+    s_warp[lane] = wi - w;
+    if (lane == 31) tops[blockIdx.x] = wi;
+  }
+  __syncthreads();
+  uint32_t run = s_warp[warp] + incl - tsum;
+  uint4 o4; o4.x = run; o4.y = run + x[0]; o4.z = o4.y + x[1]; o4.w = o4.z + x[2];
+  if (base + 3 < n) *reinterpret_cast<uint4*>(local + base) = o4;
+  else {
+    if (base < n) local[base] = o4.x;
+    if (base + 1 < n) local[base + 1] = o4.y;
+    if (base + 2 < n) local[base + 2] = o4.z;
   }
 }
 
 // ------------------------------------------------------------------------------------------
-// gather: one warp per agent.  Copies each selected record (32-byte header -> hdr_out,
-// padded payload -> payload_out) with 16-byte streaming accesses, then retires the entries.
+// gather: flat over output records, 8 lanes per record (4 records per warp step), all loads of a
+// step issued before its stores.  Pure indexed copy: arena record -> hdr_out[r] + payload_out.
 // ------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256)
 k_recv_gather(sdb_dev_view v, sdb_recv_args r) {
-  const uint32_t lane = threadIdx.x & 31;
-  const uint32_t q = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  if (q >= r.n) return;
-  const uint32_t cm = r.cnt[q];
-  const uint32_t cnt = cm & ~SDB_MODE_LIST;
-  const bool list = (cm & SDB_MODE_LIST) != 0;
-  if (cnt == 0) { if (lane == 0) r.count_out[q] = 0; return; }
-  const uint32_t roff = r.rec_local[q] + r.rec_tops[q / SDB_SCAN_TILE];
-  const uint64_t poff = static_cast<uint64_t>(r.pay_local[q]) + r.pay_tops[q / SDB_SCAN_TILE];
-  const uint32_t pay = r.pay[q];
-  if (poff + pay > r.pay_cap_gran) { if (lane == 0) r.count_out[q] = 0; return; }   // does not fit: stays queued
-
-  const uint32_t a = r.agent_idx ? r.agent_idx[q] : q;
-  const uint32_t R = v.ring_slots, mask = R - 1;
-  const uint32_t H = r.old_head[q];
-  uint32_t* hs = v.ring_handle + (static_cast<size_t>(a) << v.ring_shift);
-  uint16_t* ms = v.ring_meta + (static_cast<size_t>(a) << v.ring_shift);
-  // arena position of a 32-bit handle: handles of live entries are within 2^32 granules of each
-  // other and the arena is at most 2^32 granules, so the low bits select the slot directly.
-  uint32_t run = 0;                       // payload granules emitted so far for this agent
-  for (uint32_t j0 = 0; j0 < cnt; j0 += 32) {
-    const uint32_t j = j0 + lane;
-    uint32_t pos = 0, handle = 0, pg = 0;
-    if (j < cnt) {
-      pos = list ? r.sel_pos[roff + j] : H + j;
-      handle = hs[pos & mask];
-      pg = (ms[pos & mask] & SDB_META_GLEN_MASK) - 1u;
-      if (list) ms[pos & mask] = SDB_META_TOMB;
+  const uint32_t total = static_cast<uint32_t>(r.totals[0]);
+  const uint32_t lane = threadIdx.x & 31, sub = lane >> 3, l8 = lane & 7;
+  const uint32_t gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const uint32_t nw = (gridDim.x * blockDim.x) >> 5;
+  for (uint32_t r0 = gw * 4u; r0 < total; r0 += nw * 4u) {
+    const uint32_t rec = r0 + sub;
+    if (rec >= total) continue;
+    const uint32_t handle = r.plan_handle[rec];
+    const uint32_t g = r.plan_glen[rec];
+    const uint64_t po = static_cast<uint64_t>(r.plan_local[rec]) + r.plan_tops[rec / SDB_SCAN_TILE];
+    const uint8_t* src = v.arena + ((static_cast<uint64_t>(handle) & v.gmask) << 5);
+    uint8_t* hdst = reinterpret_cast<uint8_t*>(r.hdr_out + rec);
+    uint8_t* pdst = r.payload_out + (po << 5) - 32;          // chunk c >= 2 lands at pdst + 16 c
+    const uint32_t nchunk = 2u + (g << 1);
+    for (uint32_t c = l8; c < nchunk; c += 24) {
+      const uint32_t c1 = c + 8, c2 = c + 16;
+      uint4 x0 = sdb_ld_stream(src + (c << 4)), x1, x2;
+      if (c1 < nchunk) x1 = sdb_ld_stream(src + (c1 << 4));
+      if (c2 < nchunk) x2 = sdb_ld_stream(src + (c2 << 4));
+      sdb_st_stream((c < 2 ? hdst : pdst) + (c << 4), x0);
+      if (c1 < nchunk) sdb_st_stream(pdst + (c1 << 4), x1);
+      if (c2 < nchunk) sdb_st_stream(pdst + (c2 << 4), x2);
     }
-    uint32_t incl = pg;
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-      uint32_t y = __shfl_up_sync(0xFFFFFFFFu, incl, o);
-      if (lane >= o) incl += y;
-    }
-    const uint32_t excl = run + incl - pg;
-    run += __shfl_sync(0xFFFFFFFFu, incl, 31);
-    const uint32_t m = min(32u, cnt - j0);
-    for (uint32_t t = 0; t < m; ++t) {
-      const uint32_t hd = __shfl_sync(0xFFFFFFFFu, handle, t);
-      const uint32_t g = __shfl_sync(0xFFFFFFFFu, pg, t);
-      const uint32_t ex = __shfl_sync(0xFFFFFFFFu, excl, t);
-      const uint8_t* src = v.arena + ((static_cast<uint64_t>(hd) & v.gmask) << 5);
-      uint8_t* hdst = reinterpret_cast<uint8_t*>(r.hdr_out + roff + j0 + t);
-      uint8_t* pdst = r.payload_out + ((poff + ex) << 5);
-      const uint32_t nchunk = 2u + (g << 1);
-      for (uint32_t c = lane; c < nchunk; c += 32) {
-        const uint4 x = sdb_ld_stream(src + (c << 4));
-        if (c < 2) sdb_st_stream(hdst + (c << 4), x);
-        else sdb_st_stream(pdst + ((c - 2u) << 4), x);
-      }
-    }
-  }
-  if (lane == 0) {
-    r.count_out[q] = cnt;
-    // retire: the low word of ring_state is head (little endian); no enqueue runs concurrently
-    reinterpret_cast<uint32_t*>(v.ring_state + a)[0] = r.new_head[q];
-    v.ntomb[a] = r.new_ntomb[q];
-    atomicAdd(&v.ctr->delivered, static_cast<unsigned long long>(cnt));
-    atomicMax(r.totals + 0, static_cast<unsigned long long>(roff) + cnt);
-    atomicMax(r.totals + 1, poff + pay);
   }
 }
 
 // ------------------------------------------------------------------------------------------
 extern "C" cudaError_t sdb_launch_receive(const sdb_dev_view* v, const sdb_recv_args* r, cudaStream_t stream,
-                                          int* n_launches, sdb_profiler* prof) {
+                                          int* n_launches, sdb_profiler* prof, int sm_count) {
   if (r->n == 0) return cudaSuccess;
   const uint32_t n = r->n;
   const uint32_t tiles = (n + SDB_SCAN_TILE - 1) / SDB_SCAN_TILE;
-  cudaMemsetAsync(r->totals, 0, 2 * sizeof(unsigned long long), stream);
   int pi = sdb_prof_begin(prof, SDB_PK_RECV_COUNT, stream);
   k_recv_count<<<(n + 255) / 256, 256, 0, stream>>>(*v, *r);
   sdb_prof_end(prof, pi, stream);
   pi = sdb_prof_begin(prof, SDB_PK_RECV_SCAN, stream);
   k_scan_local<<<tiles, 1024, 0, stream>>>(r->cnt, 0xFFFFFFFFu, r->rec_local, r->rec_tops, n);
-  k_scan_tops<<<1, 1024, 0, stream>>>(r->rec_tops, tiles, nullptr);
+  k_scan_tops<<<1, 1024, 0, stream>>>(r->rec_tops, tiles, r->totals);          // totals[0] = records requested
   sdb_prof_end(prof, pi, stream);
   pi = sdb_prof_begin(prof, SDB_PK_RECV_SELECT, stream);
-  k_recv_select<<<(n + 255) / 256, 256, 0, stream>>>(*v, *r);
+  k_recv_select<<<(n + 255) / 256, 256, 0, stream>>>(*v, *r);                   // may lower totals[0] (capacity)
   sdb_prof_end(prof, pi, stream);
+  // upper bound on records: min(rec_cap, n * max_messages); grids sized from it, kernels read the true count
+  uint64_t bound = static_cast<uint64_t>(n) * r->max_messages;
+  if (bound > r->rec_cap) bound = r->rec_cap;
+  const uint32_t rtiles = static_cast<uint32_t>((bound + SDB_SCAN_TILE - 1) / SDB_SCAN_TILE);
   pi = sdb_prof_begin(prof, SDB_PK_RECV_SCAN, stream);
-  k_scan_local<<<tiles, 1024, 0, stream>>>(r->pay, 0xFFFFFFFFu, r->pay_local, r->pay_tops, n);
-  k_scan_tops<<<1, 1024, 0, stream>>>(r->pay_tops, tiles, nullptr);
+  k_scan_plan<<<rtiles, 1024, 0, stream>>>(r->plan_glen, r->plan_local, r->plan_tops, r->totals);
+  k_scan_tops<<<1, 1024, 0, stream>>>(r->plan_tops, rtiles, r->totals + 1);    // totals[1] = payload granules
   sdb_prof_end(prof, pi, stream);
-  const uint64_t threads = static_cast<uint64_t>(n) * 32;
+  uint64_t gwarps = (bound + 3) / 4;
+  uint64_t gblocks = (gwarps + 7) / 8;
+  const uint64_t cap = static_cast<uint64_t>(sm_count) * 8 * 4;                // grid-stride beyond ~4 waves
+  if (gblocks > cap) gblocks = cap;
+  if (gblocks == 0) gblocks = 1;
   pi = sdb_prof_begin(prof, SDB_PK_RECV_GATHER, stream);
-  k_recv_gather<<<static_cast<uint32_t>((threads + 255) / 256), 256, 0, stream>>>(*v, *r);
+  k_recv_gather<<<static_cast<uint32_t>(gblocks), 256, 0, stream>>>(*v, *r);
   sdb_prof_end(prof, pi, stream);
   if (n_launches) *n_launches += 7;
   return cudaGetLastError();

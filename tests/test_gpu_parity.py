@@ -40,7 +40,7 @@ def _pair(max_agents, max_groups=8, **kw):
     return g, c
 
 
-@pytest.mark.parametrize("variant", [0, 1])
+@pytest.mark.parametrize("variant", [0, 1, 2])
 def test_p2p_then_drain(variant):
     rng = np.random.default_rng(11)
     A = 200
@@ -61,7 +61,7 @@ def test_p2p_then_drain(variant):
     assert st["enqueued"] == 9000 and st["delivered"] == 9000 and st["ring_overflow"] == 0
 
 
-@pytest.mark.parametrize("variant", [0, 1])
+@pytest.mark.parametrize("variant", [0, 1, 2])
 @pytest.mark.parametrize("fixed", [True, False])
 def test_group_fanout_parity(variant, fixed):
     rng = np.random.default_rng(5 + variant)
@@ -115,7 +115,7 @@ def test_group_overwrite_and_large_group():
 def test_broadcast_lists_share_one_seq():
     rng = np.random.default_rng(9)
     A = 500
-    g, c = _pair(A)
+    g, c = _pair(A, list_pool_entries=8192)
     idx = np.arange(A, dtype=np.uint32)
     g.register(idx); c.register(idx)
     n = 12
