@@ -187,6 +187,53 @@ __device__ __forceinline__ void sdb_st_stream(void* p, const uint4& v) {
                :: "l"(p), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
 }
 
+// L2 eviction-priority policies: message bytes stream through once (evict_first) so that the
+// small, hot ring metadata (evict_last) stays L2-resident between enqueue and dequeue
+__device__ __forceinline__ uint64_t sdb_policy_evict_first() {
+  uint64_t p;
+  asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
+  return p;
+}
+__device__ __forceinline__ uint64_t sdb_policy_evict_last() {
+  uint64_t p;
+  asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p));
+  return p;
+}
+__device__ __forceinline__ uint4 sdb_ld_stream_pol(const void* p, uint64_t pol) {
+  uint4 r;
+  asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.v4.u32 {%0,%1,%2,%3}, [%4], %5;"
+               : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p), "l"(pol));
+  return r;
+}
+__device__ __forceinline__ void sdb_st_stream_pol(void* p, const uint4& v, uint64_t pol) {
+  asm volatile("st.global.L1::no_allocate.L2::cache_hint.v4.u32 [%0], {%1,%2,%3,%4}, %5;"
+               :: "l"(p), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w), "l"(pol) : "memory");
+}
+__device__ __forceinline__ void sdb_st_u32_pol(uint32_t* p, uint32_t v, uint64_t pol) {
+  asm volatile("st.global.L2::cache_hint.u32 [%0], %1, %2;" :: "l"(p), "r"(v), "l"(pol) : "memory");
+}
+__device__ __forceinline__ void sdb_st_u16_pol(uint16_t* p, uint16_t v, uint64_t pol) {
+  asm volatile("st.global.L2::cache_hint.u16 [%0], %1, %2;" :: "l"(p), "h"(v), "l"(pol) : "memory");
+}
+__device__ __forceinline__ void sdb_st_u64_pol(uint64_t* p, uint64_t v, uint64_t pol) {
+  asm volatile("st.global.L2::cache_hint.u64 [%0], %1, %2;" :: "l"(p), "l"(v), "l"(pol) : "memory");
+}
+__device__ __forceinline__ uint32_t sdb_ld_u32_pol(const uint32_t* p, uint64_t pol) {
+  uint32_t r;
+  asm volatile("ld.global.L2::cache_hint.u32 %0, [%1], %2;" : "=r"(r) : "l"(p), "l"(pol));
+  return r;
+}
+__device__ __forceinline__ uint16_t sdb_ld_u16_pol(const uint16_t* p, uint64_t pol) {
+  uint16_t r;
+  asm volatile("ld.global.L2::cache_hint.u16 %0, [%1], %2;" : "=h"(r) : "l"(p), "l"(pol));
+  return r;
+}
+__device__ __forceinline__ uint64_t sdb_ld_u64_pol(const uint64_t* p, uint64_t pol) {
+  uint64_t r;
+  asm volatile("ld.global.L2::cache_hint.u64 %0, [%1], %2;" : "=l"(r) : "l"(p), "l"(pol));
+  return r;
+}
+
 // ---- mbarrier + TMA (bulk async copy) wrappers ----------------------------------------------
 __device__ __forceinline__ uint32_t sdb_smem_u32(const void* p) {
   return static_cast<uint32_t>(__cvta_generic_to_shared(p));

@@ -159,11 +159,12 @@ k_recv_select(sdb_dev_view v, sdb_recv_args r) {
   constexpr uint32_t SMALL = 8;
   bool done = !valid || cnt == 0;
   if (!done && !prio_mode && nt == 0 && cnt <= SMALL) {
+    const uint64_t pol = sdb_policy_evict_last();
     const uint16_t* ms = v.ring_meta + (static_cast<size_t>(a) << v.ring_shift);
     const uint32_t* hs = v.ring_handle + (static_cast<size_t>(a) << v.ring_shift);
     for (uint32_t j = 0; j < cnt; ++j) {
-      r.plan_handle[roff + j] = hs[(head + j) & mask];
-      r.plan_glen[roff + j] = (ms[(head + j) & mask] & SDB_META_GLEN_MASK) - 1u;
+      r.plan_handle[roff + j] = sdb_ld_u32_pol(hs + ((head + j) & mask), pol);
+      r.plan_glen[roff + j] = (sdb_ld_u16_pol(ms + ((head + j) & mask), pol) & SDB_META_GLEN_MASK) - 1u;
     }
     reinterpret_cast<uint32_t*>(v.ring_state + a)[0] = head + cnt;    // low word = head (little endian)
     done = true;
@@ -321,6 +322,7 @@ __global__ void __launch_bounds__(256)
 k_recv_gather(sdb_dev_view v, sdb_recv_args r) {
   const uint32_t total = static_cast<uint32_t>(r.totals[0]);
   const uint32_t lane = threadIdx.x & 31, sub = lane >> 3, l8 = lane & 7;
+  const uint64_t pol = sdb_policy_evict_first();
   const uint32_t gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const uint32_t nw = (gridDim.x * blockDim.x) >> 5;
   for (uint32_t r0 = gw * 4u; r0 < total; r0 += nw * 4u) {
@@ -335,12 +337,12 @@ k_recv_gather(sdb_dev_view v, sdb_recv_args r) {
     const uint32_t nchunk = 2u + (g << 1);
     for (uint32_t c = l8; c < nchunk; c += 24) {
       const uint32_t c1 = c + 8, c2 = c + 16;
-      uint4 x0 = sdb_ld_stream(src + (c << 4)), x1, x2;
-      if (c1 < nchunk) x1 = sdb_ld_stream(src + (c1 << 4));
-      if (c2 < nchunk) x2 = sdb_ld_stream(src + (c2 << 4));
-      sdb_st_stream((c < 2 ? hdst : pdst) + (c << 4), x0);
-      if (c1 < nchunk) sdb_st_stream(pdst + (c1 << 4), x1);
-      if (c2 < nchunk) sdb_st_stream(pdst + (c2 << 4), x2);
+      uint4 x0 = sdb_ld_stream_pol(src + (c << 4), pol), x1, x2;
+      if (c1 < nchunk) x1 = sdb_ld_stream_pol(src + (c1 << 4), pol);
+      if (c2 < nchunk) x2 = sdb_ld_stream_pol(src + (c2 << 4), pol);
+      sdb_st_stream_pol((c < 2 ? hdst : pdst) + (c << 4), x0, pol);
+      if (c1 < nchunk) sdb_st_stream_pol(pdst + (c1 << 4), x1, pol);
+      if (c2 < nchunk) sdb_st_stream_pol(pdst + (c2 << 4), x2, pol);
     }
   }
 }

@@ -234,6 +234,7 @@ k_group_fanout_warp(sdb_dev_view v, const sdb_send_desc* __restrict__ descs, uin
   uint32_t phase = 0;
   uint32_t n_enq = 0, n_ovf = 0, n_skip = 0;
   const uint32_t gw = blockIdx.x * WARPS + warp, nw = gridDim.x * WARPS;
+  const uint64_t pol_stream = sdb_policy_evict_first();
 
   for (uint32_t i = gw; i < n; i += nw) {
     const sdb_send_desc d = load_desc(descs + i);
@@ -292,7 +293,7 @@ k_group_fanout_warp(sdb_dev_view v, const sdb_send_desc* __restrict__ descs, uin
           if (ch == 0) x = sdb_header_lo(seq0 + (shared_seq ? 0u : rec), d.timestamp);
           else if (ch == 1) x = sdb_header_hi(d.sender, shared_seq ? SDB_NO_RECEIVER : (lo_half ? ra0 : ra1), d.group, d.len, d.prio, d.type);
           else x = my4[ch - 2u];
-          sdb_st_stream(tb + static_cast<size_t>(rec) * rbytes + (ch << 4), x);
+          sdb_st_stream_pol(tb + static_cast<size_t>(rec) * rbytes + (ch << 4), x, pol_stream);
         }
         ch += r32; rec += q32;
         if (ch >= PC) { ch -= PC; ++rec; }
@@ -369,14 +370,14 @@ k_enqueue_p2p(sdb_dev_view v, const sdb_send_desc* __restrict__ descs, uint32_t 
 // ------------------------------------------------------------------------------------------
 __device__ __forceinline__ void pull_emit(const sdb_dev_view& v, const sdb_send_desc* descs, uint32_t s, uint32_t j,
                                           uint32_t a, uint64_t arena_base, uint32_t head, uint32_t& tail,
-                                          uint32_t& n_enq, uint32_t& n_ovf) {
+                                          uint32_t& n_enq, uint32_t& n_ovf, uint64_t pol) {
   const uint4 q1 = __ldg(reinterpret_cast<const uint4*>(descs + s) + 1);   // gran0, sender, rgran, len|prio|type
   if (q1.y == a) return;                                                     // member == sender (M:1268)
   if (tail - head >= v.ring_slots) { ++n_ovf; return; }
   const uint32_t prio = (q1.w >> 16) & 0xFFu;
   const size_t slot = (static_cast<size_t>(a) << v.ring_shift) + (tail & (v.ring_slots - 1));
-  v.ring_handle[slot] = static_cast<uint32_t>(arena_base + q1.x + static_cast<uint64_t>(j) * q1.z);
-  v.ring_meta[slot] = static_cast<uint16_t>((prio << 14) | q1.z);
+  sdb_st_u32_pol(v.ring_handle + slot, static_cast<uint32_t>(arena_base + q1.x + static_cast<uint64_t>(j) * q1.z), pol);
+  sdb_st_u16_pol(v.ring_meta + slot, static_cast<uint16_t>((prio << 14) | q1.z), pol);
   ++tail; ++n_enq;
 }
 
@@ -386,17 +387,18 @@ k_pull_index(sdb_dev_view v, sdb_pull_view pv, const sdb_send_desc* __restrict__
   const uint32_t a = blockIdx.x * blockDim.x + threadIdx.x;
   const uint32_t lane = threadIdx.x & 31;
   uint32_t n_enq = 0, n_ovf = 0;
+  const uint64_t pol = sdb_policy_evict_last();
   if (a < n_agents) {
     const uint32_t k0 = pv.memb_off[a], k1 = pv.memb_off[a + 1];
     if (k1 > k0) {
-      const uint64_t st = v.ring_state[a];
+      const uint64_t st = sdb_ld_u64_pol(v.ring_state + a, pol);
       const uint32_t head = static_cast<uint32_t>(st);
       uint32_t tail = static_cast<uint32_t>(st >> 32);
       const uint32_t tail0 = tail;
       if (k1 - k0 == 1) {
         const uint32_t g = pv.memb_grp[k0], j = pv.memb_pos[k0];
         const uint32_t e = pv.gs_off[g + 1];
-        for (uint32_t p = pv.gs_off[g]; p < e; ++p) pull_emit(v, descs, pv.gs_idx[p], j, a, arena_base, head, tail, n_enq, n_ovf);
+        for (uint32_t p = pv.gs_off[g]; p < e; ++p) pull_emit(v, descs, pv.gs_idx[p], j, a, arena_base, head, tail, n_enq, n_ovf, pol);
       } else {
         // merge the buckets of every membership by (send index, member position); the pair strictly
         // greater than the last emitted one is found per list by binary search, so no cursor storage
@@ -418,13 +420,13 @@ k_pull_index(sdb_dev_view v, sdb_pull_view pv, const sdb_send_desc* __restrict__
             }
           }
           if (best_s == 0xFFFFFFFFu) break;
-          pull_emit(v, descs, best_s, best_j, a, arena_base, head, tail, n_enq, n_ovf);
+          pull_emit(v, descs, best_s, best_j, a, arena_base, head, tail, n_enq, n_ovf, pol);
           last_s = best_s; last_j = best_j;
         }
       }
       if (tail != tail0) {
-        v.ring_state[a] = (static_cast<uint64_t>(tail) << 32) | head;
-        if (set_ctail) v.ctail[a] = tail;
+        sdb_st_u64_pol(v.ring_state + a, (static_cast<uint64_t>(tail) << 32) | head, pol);
+        if (set_ctail) sdb_st_u32_pol(v.ctail + a, tail, pol);
       }
     }
   }
