@@ -213,6 +213,31 @@ int sdb_receive_batch(sdb_handle h, uint32_t n_agents, const uint32_t* agent_idx
 int sdb_last_receive_dev(sdb_handle h, const uint32_t** count_dev, const sdb_msg_header** hdr_dev,
                          const uint8_t** payload_dev);
 
+/* ---- cross-shard delivery (one handle per GPU, one process per GPU) ----------------------------
+ * Replaces the partitioned topic: _get_partition (M:309-312, salted hash() % num_partitions) and
+ * the explicit-partition produce (M:469-482).  Agents are hash-partitioned over num_shards GPUs;
+ * sdb_set_agent_shards declares the owner of every agent index (the Python layer uses
+ * fnv1a64(utf8(agent_id)) % num_shards).  Group tables are replicated: every shard calls
+ * sdb_create_group with the FULL member list and keeps the members it owns plus their positions.
+ *
+ * A rank exports the group sends it ingested as ONE wire batch in device memory - descriptor +
+ * payload per SEND, not per recipient.  The caller moves wire batches between ranks (NCCL
+ * all-gather over NVLink through torch.distributed) and every rank imports the wire batches of
+ * all ranks, in rank order: each send is expanded into the copies for the members this shard owns.
+ * Sequence numbers are global (rank r's sends follow rank r-1's), so per-agent streams are
+ * identical to a single-shard run over the concatenated batch.  With num_shards == 1 the same
+ * two calls work without any collective.
+ */
+uint64_t sdb_wire_bytes(uint32_t max_sends, uint64_t max_payload_bytes);
+int sdb_set_agent_shards(sdb_handle h, uint32_t n, const uint8_t* shard_of);
+int sdb_export_group_batch(sdb_handle h, uint32_t n,
+                           const uint32_t* sender, const uint32_t* group_idx,
+                           const uint8_t* prio, const uint8_t* type, const uint16_t* len,
+                           const uint64_t* payload_off, const uint8_t* payload, uint64_t payload_bytes,
+                           const double* timestamp, void* wire_dev, uint64_t wire_cap);
+int sdb_import_wire_batches(sdb_handle h, uint32_t n_src, const void* wire_dev_all, uint64_t wire_stride,
+                            uint64_t* seq_base_out);
+
 /* ---- LLM backend balancer: set_llm_load_balancing / assign_llm_backend / get_llm_backend
  * (M:1281-1325).  The reference stores a flag and a dict and has NO pick algorithm
  * (SURVEY 0.5); the per-agent sticky map stays in the Python layer, and these entry points

@@ -51,6 +51,7 @@ typedef struct orc {
   uint8_t* store; uint64_t n_store, cap_store;
   orc_inbox* inbox;
   uint32_t** gmem; uint32_t* gcnt; uint8_t* gdef;
+  uint32_t** gposv;       /* optional: position of each kept member in the full (unsharded) list */
   uint64_t next_seq;
   uint32_t watermark;
   /* balancer */
@@ -80,6 +81,7 @@ orc* orc_create(uint32_t max_agents, uint32_t max_groups) {
   o->gmem = (uint32_t**)calloc(o->max_groups, sizeof(uint32_t*));
   o->gcnt = (uint32_t*)calloc(o->max_groups, sizeof(uint32_t));
   o->gdef = (uint8_t*)calloc(o->max_groups, 1);
+  o->gposv = (uint32_t**)calloc(o->max_groups, sizeof(uint32_t*));
   o->next_seq = 1;
   build_log2_table(o->logtab);
   return o;
@@ -88,8 +90,8 @@ orc* orc_create(uint32_t max_agents, uint32_t max_groups) {
 void orc_destroy(orc* o) {
   if (!o) return;
   for (uint32_t a = 0; a < o->max_agents; ++a) { free(o->inbox[a].idx); free(o->inbox[a].done); }
-  for (uint32_t g = 0; g < o->max_groups; ++g) free(o->gmem[g]);
-  free(o->inbox); free(o->gmem); free(o->gcnt); free(o->gdef); free(o->recs); free(o->store);
+  for (uint32_t g = 0; g < o->max_groups; ++g) { free(o->gmem[g]); free(o->gposv[g]); }
+  free(o->gposv); free(o->inbox); free(o->gmem); free(o->gcnt); free(o->gdef); free(o->recs); free(o->store);
   free(o->weight); free(o->load); free(o);
 }
 
@@ -117,6 +119,16 @@ static uint64_t store_payload(orc* o, const uint8_t* p, uint32_t len) {
   o->n_store += pl;
   return off;
 }
+
+/* sharded restatement: a shard keeps only the members it owns, with their original positions */
+int orc_create_group_pos(orc* o, uint32_t g, uint32_t n, const uint32_t* members, const uint32_t* pos) {
+  if (orc_create_group(o, g, n, members) != 0) return -1;
+  o->gposv[g] = (uint32_t*)xrealloc(o->gposv[g], (size_t)n * 4);
+  memcpy(o->gposv[g], pos, (size_t)n * 4);
+  return 0;
+}
+void orc_set_next_seq(orc* o, uint64_t s) { o->next_seq = s; }
+uint64_t orc_get_next_seq(orc* o) { return o->next_seq; }
 
 /* one delivery: the record lands in agent a's stream (the consumer whose filter accepts it) */
 static void deliver(orc* o, uint32_t a, uint64_t seq, double ts, uint32_t sender, uint32_t receiver_field,
@@ -173,6 +185,24 @@ uint64_t orc_send_group_batch(orc* o, uint32_t n, const uint32_t* sender, const 
   o->next_seq += rec;
   if (n_routed) *n_routed = routed;
   return base;
+}
+
+/* group sends whose sequence numbers were assigned elsewhere (cross-shard import): member k of
+ * the locally kept list gets seq0[i] + original position; the rest is send_to_group (M:1267-1277) */
+void orc_send_group_seq(orc* o, uint32_t n, const uint32_t* sender, const uint32_t* group, const uint8_t* prio,
+                        const uint8_t* type, const uint16_t* len, const uint64_t* payload_off, const uint8_t* payload,
+                        const double* ts, const uint64_t* seq0) {
+  for (uint32_t i = 0; i < n; ++i) {
+    const uint32_t g = group[i];
+    if (g >= o->max_groups || !o->gdef[g]) continue;
+    const uint64_t po = store_payload(o, payload + (payload_off ? payload_off[i] : 0), len[i]);
+    for (uint32_t k = 0; k < o->gcnt[g]; ++k) {
+      const uint32_t a = o->gmem[g][k];
+      const uint32_t j = o->gposv[g] ? o->gposv[g][k] : k;
+      if (a != sender[i])
+        deliver(o, a, seq0[i] + j, ts ? ts[i] : 0.0, sender[i], a, g, len[i], prio ? prio[i] : 1, type ? type[i] : 0, po);
+    }
+  }
 }
 
 /* broadcast with explicit visibility list, M:449-463 / M:810-850: ONE message, many readers */

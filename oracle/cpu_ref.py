@@ -41,6 +41,10 @@ def lib():
         L.orc_destroy.argtypes = [vp]
         L.orc_register.argtypes = [vp, u32]
         L.orc_create_group.restype = C.c_int; L.orc_create_group.argtypes = [vp, u32, u32, vp]
+        L.orc_create_group_pos.restype = C.c_int; L.orc_create_group_pos.argtypes = [vp, u32, u32, vp, vp]
+        L.orc_set_next_seq.argtypes = [vp, u64]
+        L.orc_get_next_seq.restype = u64; L.orc_get_next_seq.argtypes = [vp]
+        L.orc_send_group_seq.argtypes = [vp, u32] + [vp] * 10
         L.orc_send_batch.restype = u64; L.orc_send_batch.argtypes = [vp, u32] + [vp] * 8
         L.orc_send_group_batch.restype = u64; L.orc_send_group_batch.argtypes = [vp, u32] + [vp] * 9
         L.orc_send_list_batch.restype = u64; L.orc_send_list_batch.argtypes = [vp, u32] + [vp] * 9
@@ -87,6 +91,24 @@ class CpuOracle:
     def create_group(self, g: int, members) -> None:
         m = _arr(members, np.uint32)
         assert lib().orc_create_group(self._h, g, len(m), _p(m)) == 0
+
+    def create_group_pos(self, g: int, members, pos) -> None:
+        m, p = _arr(members, np.uint32), _arr(pos, np.uint32)
+        assert lib().orc_create_group_pos(self._h, g, len(m), _p(m), _p(p)) == 0
+
+    @property
+    def next_seq(self) -> int:
+        return lib().orc_get_next_seq(self._h)
+
+    @next_seq.setter
+    def next_seq(self, v: int) -> None:
+        lib().orc_set_next_seq(self._h, v)
+
+    def send_group_seq(self, sender, group, prio, typ, lens, payload_off, payload, seq0, ts=None) -> None:
+        s, g = _arr(sender, np.uint32), _arr(group, np.uint32)
+        prio, typ, lens, po, pl, ts = self._common(len(s), prio, typ, lens, payload_off, payload, ts)
+        q = _arr(seq0, np.uint64)
+        lib().orc_send_group_seq(self._h, len(s), _p(s), _p(g), _p(prio), _p(typ), _p(lens), _p(po), _p(pl), _p(ts), _p(q))
 
     @staticmethod
     def _common(n, prio, typ, lens, payload_off, payload, ts):

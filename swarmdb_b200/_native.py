@@ -55,7 +55,8 @@ class SdbStats(C.Structure):
 EXPORTS = ["sdb_abi_version", "sdb_create", "sdb_destroy", "sdb_set_stream", "sdb_sync", "sdb_last_error",
            "sdb_get_stats", "sdb_profile", "sdb_profile_read", "sdb_register_agents", "sdb_deregister_agents", "sdb_create_group", "sdb_send_batch",
            "sdb_send_group_batch", "sdb_send_list_batch", "sdb_send_mixed_batch", "sdb_stage_batch", "sdb_submit_staged", "sdb_free_staged",
-           "sdb_receive_batch", "sdb_last_receive_dev", "sdb_set_backends", "sdb_get_backend_loads",
+           "sdb_receive_batch", "sdb_last_receive_dev", "sdb_wire_bytes", "sdb_set_agent_shards",
+           "sdb_export_group_batch", "sdb_import_wire_batches", "sdb_set_backends", "sdb_get_backend_loads",
            "sdb_release_backends", "sdb_select_backend_batch"]
 
 _lib = None
@@ -95,6 +96,10 @@ def load_library() -> C.CDLL:
     L.sdb_receive_batch.restype = i32
     L.sdb_receive_batch.argtypes = [vp, u32, vp, u32, u32, vp, vp, u64, vp, u64, vp, vp]
     L.sdb_last_receive_dev.restype = i32; L.sdb_last_receive_dev.argtypes = [vp, vp, vp, vp]
+    L.sdb_wire_bytes.restype = u64; L.sdb_wire_bytes.argtypes = [u32, u64]
+    L.sdb_set_agent_shards.restype = i32; L.sdb_set_agent_shards.argtypes = [vp, u32, vp]
+    L.sdb_export_group_batch.restype = i32; L.sdb_export_group_batch.argtypes = [vp, u32] + [vp] * 7 + [u64, vp, vp, u64]
+    L.sdb_import_wire_batches.restype = i32; L.sdb_import_wire_batches.argtypes = [vp, u32, vp, u64, vp]
     L.sdb_set_backends.restype = i32; L.sdb_set_backends.argtypes = [vp, u32, vp, vp]
     L.sdb_get_backend_loads.restype = i32; L.sdb_get_backend_loads.argtypes = [vp, u32, vp]
     L.sdb_release_backends.restype = i32; L.sdb_release_backends.argtypes = [vp, u32, vp, vp]
@@ -281,6 +286,30 @@ class Shard:
 
     def free_staged(self, staged: int) -> None:
         self._check(self._L.sdb_free_staged(self._h, C.c_void_p(staged)))
+
+    # ------------------------------------------------------------------ cross-shard
+    def wire_bytes(self, max_sends: int, max_payload: int) -> int:
+        return int(self._L.sdb_wire_bytes(max_sends, max_payload))
+
+    def set_agent_shards(self, shard_of) -> None:
+        s = _arr(shard_of, np.uint8)
+        self._check(self._L.sdb_set_agent_shards(self._h, len(s), _p(s)))
+
+    def export_group_batch(self, sender, group, prio, typ, lens, payload_off, payload, wire_dev: int, wire_cap: int,
+                           ts=None) -> None:
+        """Write this rank's batch of group sends as one wire batch into device memory at `wire_dev`."""
+        s, g = _arr(sender, np.uint32), _arr(group, np.uint32)
+        prio, typ, lens, po, pl, ts = self._common(len(s), prio, typ, lens, payload_off, payload, ts)
+        self._keep = pl
+        self._check(self._L.sdb_export_group_batch(self._h, len(s), _p(s), _p(g), _p(prio), _p(typ), _p(lens), _p(po),
+                                                   _p(pl), pl.nbytes, _p(ts), C.c_void_p(wire_dev), wire_cap))
+
+    def import_wire_batches(self, n_src: int, wire_dev_all: int, stride: int) -> int:
+        """Expand the wire batches of `n_src` ranks (rank order, `stride` bytes apart) for the agents this shard owns."""
+        base = C.c_uint64(0)
+        self._check(self._L.sdb_import_wire_batches(self._h, n_src, C.c_void_p(wire_dev_all), stride,
+                                                    C.cast(C.byref(base), C.c_void_p)))
+        return base.value
 
     # ------------------------------------------------------------------ dequeue
     def receive_batch(self, agents, max_messages: int, flags: int = 0, copy_out: bool = True,

@@ -29,6 +29,9 @@ cudaError_t sdb_launch_pick(int mode, uint32_t n_backends, const uint32_t* weigh
                             unsigned long long* scratch_dev, const uint32_t* log_tab_dev,
                             cudaStream_t stream, int* n_launches);
 void sdb_build_log2_table(uint32_t* tab257);
+cudaError_t sdb_launch_import_measure(const sdb_import_args*, uint32_t, uint32_t*, uint32_t*, uint32_t*, uint32_t*, uint32_t*,
+                                      unsigned long long*, cudaStream_t, sdb_profiler*, int*);
+cudaError_t sdb_launch_import_localize(const sdb_import_args*, uint32_t, uint32_t*, cudaStream_t, sdb_profiler*, int*);
 }
 
 #define SDB_SCAN_TILE 4096u
@@ -75,6 +78,20 @@ struct sdb_ctx {
   // inverse group table (agent -> memberships), rebuilt lazily from `ghost`
   uint32_t* memb_off_dev = nullptr; uint32_t* memb_grp_dev = nullptr; uint32_t* memb_pos_dev = nullptr;
   bool memb_dirty = true;
+  // sharding (one handle = one shard): owner of each agent, full group lists, local positions
+  std::vector<uint8_t> shard_of; bool sharded = false;
+  std::vector<std::vector<uint32_t>> gfull;    // full member lists as given by the caller
+  std::vector<std::vector<uint32_t>> gpos;     // position in the full list of each kept member
+  std::vector<uint32_t> gcount_full;
+  uint32_t* member_pos_dev = nullptr;          // [member_pool] parallel to `members`
+  uint32_t* lstart_dev = nullptr; uint32_t* lcount_dev = nullptr; bool ltab_dirty = true;
+  // import scratch (capacity xs_cap = num_shards * max_batch_sends sends)
+  uint32_t xs_cap = 0;
+  uint32_t* xs_w = nullptr; uint32_t* xs_w_local = nullptr; uint32_t* xs_w_tops = nullptr;
+  uint32_t* xs_gs_cnt = nullptr; uint32_t* xs_gs_local = nullptr; uint32_t* xs_gs_tops = nullptr; uint32_t* xs_gs_cur = nullptr;
+  uint32_t* xs_gs_off = nullptr; uint32_t* xs_gs_idx = nullptr; sdb_send_desc* xs_descs = nullptr;
+  uint8_t* wire_host = nullptr;                // pinned: header + descriptors of an export
+  sdb_wire_header* hdrs_host = nullptr;        // pinned [num_shards]
   cudaEvent_t staging_free = nullptr;    // previous H2D of pinned staging has completed
   // receive scratch + outputs
   uint32_t* rx_agent = nullptr; uint32_t* rx_cnt = nullptr; uint32_t* rx_rec_local = nullptr; uint32_t* rx_rec_tops = nullptr;
@@ -213,6 +230,7 @@ int build_descs(sdb_ctx* h, uint32_t batch_kind, uint32_t n, SendArrays& a, cons
     } else if (kind == 1) {
       const uint32_t g = a.second[i];
       if (g >= h->cfg.max_groups || !h->gdefined[g]) return fail(h, SDB_ENOTFOUND, "unknown group index");
+      if (h->sharded) return fail(h, SDB_EINVAL, "sharded handle: use sdb_export_group_batch + sdb_import_wire_batches");
       d.mstart = static_cast<uint32_t>(h->gstart[g]); d.mcount = h->gcount[g]; d.group = g;
       d.flags = SDB_DESC_SKIP_SENDER;
       rec += d.mcount; gran += static_cast<uint64_t>(d.mcount) * d.rgran;
@@ -444,11 +462,31 @@ int sdb_create(const sdb_config* cfg, sdb_handle* out) {
   }
 
   h->gstart.assign(c.max_groups, 0); h->gcount.assign(c.max_groups, 0); h->gdefined.assign(c.max_groups, 0);
-  h->ghost.resize(c.max_groups);
+  h->ghost.resize(c.max_groups); h->gfull.resize(c.max_groups); h->gpos.resize(c.max_groups);
+  h->gcount_full.assign(c.max_groups, 0);
+  h->shard_of.assign(c.max_agents, static_cast<uint8_t>(c.shard_id));
+  if (c.shard_id >= c.num_shards || c.num_shards > 255) return fail(h, SDB_EINVAL, "shard_id / num_shards out of range");
+  CUDA_TRY(h, dmalloc(&h->member_pos_dev, c.member_pool_entries));
+  CUDA_TRY(h, dmalloc(&h->lstart_dev, c.max_groups)); CUDA_TRY(h, dmalloc(&h->lcount_dev, c.max_groups));
+  CUDA_TRY(h, cudaMemset(h->lcount_dev, 0, static_cast<size_t>(c.max_groups) * sizeof(uint32_t)));
+  CUDA_TRY(h, cudaMemset(h->lstart_dev, 0, static_cast<size_t>(c.max_groups) * sizeof(uint32_t)));
+  {
+    const uint64_t cap64 = static_cast<uint64_t>(c.num_shards) * c.max_batch_sends;
+    if (cap64 > 0x7FFFFFFFull) return fail(h, SDB_EINVAL, "num_shards * max_batch_sends too large");
+    h->xs_cap = static_cast<uint32_t>(cap64);
+    const size_t n = h->xs_cap, G1 = static_cast<size_t>(c.max_groups) + 1;
+    const size_t wt = n / SDB_SCAN_TILE + 2, gt = G1 / SDB_SCAN_TILE + 2;
+    CUDA_TRY(h, dmalloc(&h->xs_w, n)); CUDA_TRY(h, dmalloc(&h->xs_w_local, n)); CUDA_TRY(h, dmalloc(&h->xs_w_tops, wt));
+    CUDA_TRY(h, dmalloc(&h->xs_gs_cnt, G1)); CUDA_TRY(h, dmalloc(&h->xs_gs_local, G1)); CUDA_TRY(h, dmalloc(&h->xs_gs_tops, gt));
+    CUDA_TRY(h, dmalloc(&h->xs_gs_cur, G1)); CUDA_TRY(h, dmalloc(&h->xs_gs_off, G1)); CUDA_TRY(h, dmalloc(&h->xs_gs_idx, n));
+    CUDA_TRY(h, dmalloc(&h->xs_descs, n));
+    CUDA_TRY(h, cudaHostAlloc(reinterpret_cast<void**>(&h->wire_host), 64 + static_cast<size_t>(c.max_batch_sends) * sizeof(sdb_send_desc), cudaHostAllocDefault));
+    CUDA_TRY(h, cudaHostAlloc(reinterpret_cast<void**>(&h->hdrs_host), static_cast<size_t>(c.num_shards) * sizeof(sdb_wire_header), cudaHostAllocDefault));
+  }
 
   sdb_dev_view& v = h->view;
   v.arena = h->arena; v.ring_state = h->ring_state; v.ring_handle = h->ring_handle; v.ring_meta = h->ring_meta;
-  v.ctail = h->ctail; v.ntomb = h->ntomb; v.members = h->members; v.ctr = h->ctr;
+  v.ctail = h->ctail; v.ntomb = h->ntomb; v.members = h->members; v.member_pos = h->member_pos_dev; v.ctr = h->ctr;
   v.gmask = h->arena_grans - 1; v.ring_slots = c.ring_slots; v.ring_shift = ilog2(c.ring_slots); v.max_agents = c.max_agents;
   CUDA_TRY(h, cudaStreamSynchronize(h->stream));
   return SDB_OK;
@@ -460,7 +498,9 @@ int sdb_destroy(sdb_handle h) {
   if (h->stream) cudaStreamSynchronize(h->stream);
   void* dev[] = {h->arena, h->ring_state, h->ring_handle, h->ring_meta, h->ctail, h->ntomb, h->members, h->ctr,
                  h->scratch.descs_dev, h->scratch.payload_dev, h->scratch.list_dev, h->scratch.gs_off_dev,
-                 h->scratch.gs_idx_dev, h->memb_off_dev, h->memb_grp_dev, h->memb_pos_dev, h->rx_agent, h->rx_cnt,
+                 h->scratch.gs_idx_dev, h->memb_off_dev, h->memb_grp_dev, h->memb_pos_dev, h->member_pos_dev,
+                 h->lstart_dev, h->lcount_dev, h->xs_w, h->xs_w_local, h->xs_w_tops, h->xs_gs_cnt, h->xs_gs_local,
+                 h->xs_gs_tops, h->xs_gs_cur, h->xs_gs_off, h->xs_gs_idx, h->xs_descs, h->rx_agent, h->rx_cnt,
                  h->rx_rec_local, h->rx_rec_tops, h->rx_plan_handle, h->rx_plan_glen, h->rx_plan_local, h->rx_plan_tops,
                  h->rx_totals, h->rx_count, h->rx_hdr, h->rx_payload,
                  h->be_weight, h->be_load, h->be_scratch, h->be_logtab, h->be_req_cost, h->be_out};
@@ -468,6 +508,8 @@ int sdb_destroy(sdb_handle h) {
   if (h->descs_host) cudaFreeHost(h->descs_host);
   if (h->list_host) cudaFreeHost(h->list_host);
   if (h->gs_host) cudaFreeHost(h->gs_host);
+  if (h->wire_host) cudaFreeHost(h->wire_host);
+  if (h->hdrs_host) cudaFreeHost(h->hdrs_host);
   if (h->totals_host) cudaFreeHost(h->totals_host);
   if (h->staging_free) cudaEventDestroy(h->staging_free);
   if (h->prof.cap) {
@@ -549,40 +591,171 @@ int sdb_deregister_agents(sdb_handle h, uint32_t n, const uint32_t* agent_idx) {
   return SDB_OK;   // ring and read position are kept (consumer-group offsets survive close, App. A rule 11)
 }
 
+// (re)compute the members this shard owns for group g and their positions in the full list
+static void localize_group(sdb_ctx* h, uint32_t g) {
+  const std::vector<uint32_t>& full = h->gfull[g];
+  std::vector<uint32_t>& loc = h->ghost[g];
+  std::vector<uint32_t>& pos = h->gpos[g];
+  loc.clear(); pos.clear();
+  for (uint32_t j = 0; j < full.size(); ++j)
+    if (!h->sharded || h->shard_of[full[j]] == h->cfg.shard_id) { loc.push_back(full[j]); pos.push_back(j); }
+  h->gcount_full[g] = static_cast<uint32_t>(full.size());
+}
+
+// write every defined group's local list into the device pools from scratch
+static int upload_all_groups(sdb_ctx* h) {
+  uint64_t used = 0;
+  for (uint32_t k = 0; k < h->cfg.max_groups; ++k) if (h->gdefined[k]) used += h->ghost[k].size();
+  if (used > h->cfg.member_pool_entries) return fail(h, SDB_ECAPACITY, "member pool exhausted");
+  CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+  std::vector<uint32_t> flat, fpos; flat.reserve(used); fpos.reserve(used);
+  for (uint32_t k = 0; k < h->cfg.max_groups; ++k) if (h->gdefined[k]) {
+    h->gstart[k] = flat.size(); h->gcount[k] = static_cast<uint32_t>(h->ghost[k].size());
+    flat.insert(flat.end(), h->ghost[k].begin(), h->ghost[k].end());
+    fpos.insert(fpos.end(), h->gpos[k].begin(), h->gpos[k].end());
+  }
+  if (!flat.empty()) {
+    CUDA_TRY(h, cudaMemcpy(h->members, flat.data(), flat.size() * sizeof(uint32_t), cudaMemcpyHostToDevice));
+    CUDA_TRY(h, cudaMemcpy(h->member_pos_dev, fpos.data(), fpos.size() * sizeof(uint32_t), cudaMemcpyHostToDevice));
+  }
+  h->member_used = flat.size();
+  h->memb_dirty = true; h->ltab_dirty = true;
+  return SDB_OK;
+}
+
 int sdb_create_group(sdb_handle h, uint32_t g, uint32_t n_members, const uint32_t* member_idx) {
   if (!h || (n_members && !member_idx)) return SDB_EINVAL;
   if (g >= h->cfg.max_groups) return fail(h, SDB_EINVAL, "group index >= max_groups");
-  h->memb_dirty = true;
-  for (uint32_t i = 0; i < n_members; ++i) {
+  for (uint32_t i = 0; i < n_members; ++i)
     if (member_idx[i] >= h->cfg.max_agents) return fail(h, SDB_EINVAL, "member index >= max_agents");
-    h->n_agents = std::max(h->n_agents, member_idx[i] + 1);   // members will receive: keep them inside the commit sweep
+  h->memb_dirty = true; h->ltab_dirty = true;
+  h->gfull[g].assign(member_idx, member_idx + n_members);
+  localize_group(h, g);
+  h->gdefined[g] = 1;
+  const std::vector<uint32_t>& loc = h->ghost[g];
+  for (uint32_t m : loc) h->n_agents = std::max(h->n_agents, m + 1);   // members will receive: keep them inside the sweeps
+  if (h->member_used + loc.size() > h->cfg.member_pool_entries) return upload_all_groups(h);   // compact the pool
+  h->gstart[g] = h->member_used; h->gcount[g] = static_cast<uint32_t>(loc.size());
+  if (!loc.empty()) {
+    // pageable source: cudaMemcpyAsync stages it before returning, ordered after earlier kernels on the stream
+    CUDA_TRY(h, cudaMemcpyAsync(h->members + h->member_used, loc.data(), loc.size() * sizeof(uint32_t), cudaMemcpyHostToDevice, h->stream));
+    CUDA_TRY(h, cudaMemcpyAsync(h->member_pos_dev + h->member_used, h->gpos[g].data(), loc.size() * sizeof(uint32_t), cudaMemcpyHostToDevice, h->stream));
   }
-  if (h->member_used + n_members > h->cfg.member_pool_entries) {
-    // compact: rewrite every live group from the host mirror
-    h->ghost[g].assign(member_idx, member_idx + n_members);
-    h->gdefined[g] = 1;
-    uint64_t used = 0;
-    for (uint32_t k = 0; k < h->cfg.max_groups; ++k) if (h->gdefined[k]) used += h->ghost[k].size();
-    if (used > h->cfg.member_pool_entries) { h->gdefined[g] = 0; return fail(h, SDB_ECAPACITY, "member pool exhausted"); }
-    CUDA_TRY(h, cudaStreamSynchronize(h->stream));
-    std::vector<uint32_t> flat; flat.reserve(used);
-    for (uint32_t k = 0; k < h->cfg.max_groups; ++k) if (h->gdefined[k]) {
-      h->gstart[k] = flat.size(); h->gcount[k] = static_cast<uint32_t>(h->ghost[k].size());
-      flat.insert(flat.end(), h->ghost[k].begin(), h->ghost[k].end());
-    }
-    if (!flat.empty()) CUDA_TRY(h, cudaMemcpy(h->members, flat.data(), flat.size() * sizeof(uint32_t), cudaMemcpyHostToDevice));
-    h->member_used = flat.size();
-    return SDB_OK;
-  }
-  h->ghost[g].assign(member_idx, member_idx + n_members);
-  h->gstart[g] = h->member_used; h->gcount[g] = n_members; h->gdefined[g] = 1;
-  if (n_members) {
-    // pageable source: cudaMemcpyAsync stages it before returning, ordering after earlier kernels on the stream
-    CUDA_TRY(h, cudaMemcpyAsync(h->members + h->member_used, h->ghost[g].data(), n_members * sizeof(uint32_t),
-                                cudaMemcpyHostToDevice, h->stream));
-  }
-  h->member_used += n_members;
+  h->member_used += loc.size();
   if (h->member_used > 0xFFFFFFFFull) return fail(h, SDB_ECAPACITY, "member pool beyond 2^32 entries");
+  return SDB_OK;
+}
+
+uint64_t sdb_wire_bytes(uint32_t max_sends, uint64_t max_payload_bytes) {
+  return 64ull + static_cast<uint64_t>(max_sends) * sizeof(sdb_send_desc) + ((max_payload_bytes + 64 + 63) & ~63ull);
+}
+
+int sdb_set_agent_shards(sdb_handle h, uint32_t n, const uint8_t* shard_of) {
+  if (!h || (n && !shard_of)) return SDB_EINVAL;
+  if (n > h->cfg.max_agents) return fail(h, SDB_EINVAL, "n > max_agents");
+  for (uint32_t i = 0; i < n; ++i) {
+    if (shard_of[i] >= h->cfg.num_shards) return fail(h, SDB_EINVAL, "shard id >= num_shards");
+    h->shard_of[i] = shard_of[i];
+  }
+  h->sharded = h->cfg.num_shards > 1;
+  // groups created earlier are re-filtered against the new ownership map
+  bool any = false;
+  for (uint32_t g = 0; g < h->cfg.max_groups; ++g) if (h->gdefined[g]) { localize_group(h, g); any = true; }
+  return any ? upload_all_groups(h) : SDB_OK;
+}
+
+int sdb_export_group_batch(sdb_handle h, uint32_t n, const uint32_t* sender, const uint32_t* group_idx, const uint8_t* prio,
+                           const uint8_t* type, const uint16_t* len, const uint64_t* payload_off, const uint8_t* payload,
+                           uint64_t payload_bytes, const double* timestamp, void* wire_dev, uint64_t wire_cap) {
+  if (!h || !wire_dev) return SDB_EINVAL;
+  if (n && (!sender || !group_idx || !len)) return fail(h, SDB_EINVAL, "null array");
+  if (n > h->cfg.max_batch_sends) return fail(h, SDB_ECAPACITY, "n exceeds max_batch_sends");
+  if (payload_bytes && !payload) return fail(h, SDB_EINVAL, "null payload");
+  const uint64_t desc_off = 64, pay_off = 64 + static_cast<uint64_t>(n) * sizeof(sdb_send_desc);
+  if (pay_off + payload_bytes + 64 > wire_cap) return fail(h, SDB_ECAPACITY, "wire buffer too small (sdb_wire_bytes)");
+  CUDA_TRY(h, cudaEventSynchronize(h->staging_free));
+  sdb_wire_header* wh = reinterpret_cast<sdb_wire_header*>(h->wire_host);
+  sdb_send_desc* wd = reinterpret_cast<sdb_send_desc*>(h->wire_host + 64);
+  std::memset(wh, 0, sizeof(*wh));
+  uint64_t rec = 0; uint32_t max_padlen = 0;
+  for (uint32_t i = 0; i < n; ++i) {
+    sdb_send_desc d; std::memset(&d, 0, sizeof(d));
+    const uint32_t g = group_idx[i];
+    if (g >= h->cfg.max_groups || !h->gdefined[g]) return fail(h, SDB_ENOTFOUND, "unknown group index");
+    if (sender[i] >= h->cfg.max_agents) return fail(h, SDB_EINVAL, "sender index out of range");
+    if (len[i] > h->cfg.max_payload_bytes) return fail(h, SDB_EINVAL, "payload longer than max_payload_bytes");
+    const uint64_t off = payload_off ? payload_off[i] : 0;
+    if ((off & 15u) || off + len[i] > payload_bytes) return fail(h, SDB_EINVAL, "bad payload_off");
+    if ((prio ? prio[i] : 1) > 3) return fail(h, SDB_EINVAL, "priority out of range");
+    if (rec > 0xFFFFFFFFull) return fail(h, SDB_ECAPACITY, "batch exceeds 2^32 records");
+    const uint32_t pl = pad32(len[i]);
+    max_padlen = std::max(max_padlen, pl);
+    d.payload_off = off; d.timestamp = timestamp ? timestamp[i] : 0.0;
+    d.sender = sender[i]; d.group = g; d.len = len[i]; d.prio = prio ? prio[i] : 1; d.type = type ? type[i] : 0;
+    d.rgran = 1u + pl / SDB_GRANULE; d.rec0 = static_cast<uint32_t>(rec);
+    rec += h->gcount_full[g];
+    wd[i] = d;
+  }
+  wh->magic = SDB_WIRE_MAGIC; wh->n_sends = n; wh->total_recs = rec; wh->payload_bytes = payload_bytes;
+  wh->desc_off = desc_off; wh->payload_off = pay_off; wh->max_padlen = max_padlen;
+  uint8_t* w = static_cast<uint8_t*>(wire_dev);
+  CUDA_TRY(h, cudaMemcpyAsync(w, h->wire_host, 64 + static_cast<size_t>(n) * sizeof(sdb_send_desc), cudaMemcpyHostToDevice, h->stream));
+  if (payload_bytes) CUDA_TRY(h, cudaMemcpyAsync(w + pay_off, payload, payload_bytes, cudaMemcpyHostToDevice, h->stream));
+  CUDA_TRY(h, cudaEventRecord(h->staging_free, h->stream));
+  return SDB_OK;
+}
+
+int sdb_import_wire_batches(sdb_handle h, uint32_t n_src, const void* wire_dev_all, uint64_t wire_stride, uint64_t* seq_base_out) {
+  if (!h || !wire_dev_all || n_src == 0) return SDB_EINVAL;
+  if (seq_base_out) *seq_base_out = h->next_seq;
+  if (n_src > h->cfg.num_shards) return fail(h, SDB_EINVAL, "n_src > num_shards");
+  const uint8_t* wire = static_cast<const uint8_t*>(wire_dev_all);
+  if (h->ltab_dirty) {      // device copy of the local group table (start, count per group)
+    CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+    std::vector<uint32_t> st(h->cfg.max_groups), ct(h->cfg.max_groups);
+    for (uint32_t g = 0; g < h->cfg.max_groups; ++g) { st[g] = static_cast<uint32_t>(h->gstart[g]); ct[g] = h->gdefined[g] ? h->gcount[g] : 0; }
+    CUDA_TRY(h, cudaMemcpy(h->lstart_dev, st.data(), st.size() * sizeof(uint32_t), cudaMemcpyHostToDevice));
+    CUDA_TRY(h, cudaMemcpy(h->lcount_dev, ct.data(), ct.size() * sizeof(uint32_t), cudaMemcpyHostToDevice));
+    h->ltab_dirty = false;
+  }
+  if (h->memb_dirty) { int rc0 = rebuild_inverse(h); if (rc0 != SDB_OK) return rc0; }
+  const uint32_t n_cap = n_src * h->cfg.max_batch_sends;
+  sdb_import_args a{};
+  a.wire = wire; a.stride = wire_stride; a.n_src = n_src; a.max_sends = h->cfg.max_batch_sends;
+  a.lstart = h->lstart_dev; a.lcount = h->lcount_dev; a.max_groups = h->cfg.max_groups;
+  a.w = h->xs_w; a.gs_cnt = h->xs_gs_cnt; a.descs = h->xs_descs; a.w_local = h->xs_w_local; a.w_tops = h->xs_w_tops;
+  a.gs_off = h->xs_gs_off; a.gs_idx = h->xs_gs_idx;
+  int nl = 0;
+  cudaError_t e = sdb_launch_import_measure(&a, n_cap, h->xs_w_local, h->xs_w_tops, h->xs_gs_local, h->xs_gs_tops,
+                                            h->xs_gs_off, h->rx_totals + 3, h->stream, &h->prof, &nl);
+  if (e != cudaSuccess) return fail(h, SDB_ECUDA, std::string("import measure: ") + cudaGetErrorString(e));
+  // the host needs the arena footprint and the sequence numbers consumed: one small sync
+  CUDA_TRY(h, cudaMemcpyAsync(h->totals_host + 3, h->rx_totals + 3, sizeof(unsigned long long), cudaMemcpyDeviceToHost, h->stream));
+  CUDA_TRY(h, cudaMemcpy2DAsync(h->hdrs_host, sizeof(sdb_wire_header), wire, wire_stride, sizeof(sdb_wire_header), n_src,
+                                cudaMemcpyDeviceToHost, h->stream));
+  CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+  uint64_t total_recs = 0; uint32_t max_padlen = 0;
+  for (uint32_t s = 0; s < n_src; ++s) {
+    const sdb_wire_header& wh = h->hdrs_host[s];
+    if (wh.magic != SDB_WIRE_MAGIC) return fail(h, SDB_EINVAL, "wire batch without magic (not exported by sdb_export_group_batch?)");
+    if (wh.n_sends > h->cfg.max_batch_sends) return fail(h, SDB_ECAPACITY, "wire batch larger than max_batch_sends");
+    total_recs += wh.total_recs; max_padlen = std::max(max_padlen, wh.max_padlen);
+  }
+  const uint64_t total_grans = h->totals_host[3];
+  uint64_t base = 0;
+  int rc = arena_reserve(h, total_grans, &base);
+  if (rc != SDB_OK) return rc;
+  e = sdb_launch_import_localize(&a, n_cap, h->xs_gs_cur, h->stream, &h->prof, &nl);
+  if (e == cudaSuccess)
+    e = sdb_launch_fanout(&h->view, h->xs_descs, n_cap, wire, nullptr, h->next_seq, base, max_padlen, 2, h->sm_count, h->stream, &h->prof);
+  if (e == cudaSuccess) {
+    sdb_pull_view pv{h->memb_off_dev, h->memb_grp_dev, h->memb_pos_dev, h->xs_gs_off, h->xs_gs_idx};
+    e = sdb_launch_pull(&h->view, &pv, h->xs_descs, h->n_agents, base, 1, h->stream, &h->prof);
+  }
+  h->launches += nl + 2;
+  if (e != cudaSuccess) return fail(h, SDB_ECUDA, std::string("import launch: ") + cudaGetErrorString(e));
+  h->next_seq += total_recs;
+  h->arena_tail = base + total_grans;
   return SDB_OK;
 }
 

@@ -60,6 +60,24 @@ static_assert(sizeof(sdb_msg_header) == 32, "header must be 32 bytes");
 #define SDB_DESC_SHARED_SEQ 2u    // broadcast: every copy carries the same seq (one Message)
 #define SDB_DESC_LIST_TEMP 4u     // mstart indexes the per-batch temporary list buffer
 #define SDB_DESC_PULL 8u          // ring entries are built by k_pull_index, not by the fan-out kernel
+#define SDB_DESC_POS 16u          // seq offset of member k is member_pos[mstart + k] (sharded: original group position)
+
+// cross-shard wire batch (device memory, moved between ranks by the caller):
+//   [sdb_wire_header 64 B][n_sends x sdb_send_desc 64 B][payload bytes]
+// descriptors use: payload_off (relative to the wire payload), timestamp, sender, group, rgran,
+// len, prio, type, rec0 (seq offset inside the source's batch, counted in FULL group sizes)
+struct __align__(16) sdb_wire_header {
+  uint32_t magic;          // 'SDBW'
+  uint32_t n_sends;
+  uint64_t total_recs;     // sequence numbers this batch consumes (sum of full group sizes)
+  uint64_t payload_bytes;
+  uint64_t desc_off;       // byte offsets from the start of the wire batch
+  uint64_t payload_off;
+  uint32_t max_padlen;
+  uint32_t pad[5];
+};
+static_assert(sizeof(sdb_wire_header) == 64, "wire header must be 64 bytes");
+#define SDB_WIRE_MAGIC 0x57424453u
 
 // per-batch view for the agent-parallel index build ("pull"): group sends of the batch bucketed
 // by group (gs_*), and the inverse of the group table (which groups/positions an agent is in)
@@ -89,6 +107,7 @@ struct sdb_dev_view {
   uint32_t* ctail;
   uint32_t* ntomb;
   const uint32_t* members;
+  const uint32_t* member_pos;   // sharded mode: original group position of members[k]; else nullptr
   sdb_dev_counters* ctr;
   uint64_t gmask;        // arena granules - 1
   uint32_t ring_slots;   // R
@@ -116,6 +135,25 @@ struct sdb_recv_args {
   sdb_msg_header* hdr_out;     // [rec_cap]
   uint8_t* payload_out;        // [rec_cap * pad32(max_payload)]
   uint64_t rec_cap;
+};
+
+// arguments of one cross-shard import (sdb_xshard.cu)
+struct sdb_import_args {
+  const uint8_t* wire;        // n_src wire batches, `stride` bytes apart
+  uint64_t stride;
+  uint32_t n_src;
+  uint32_t max_sends;         // capacity per wire batch
+  const uint32_t* lstart;     // [max_groups] local member list of each group
+  const uint32_t* lcount;
+  uint32_t max_groups;
+  // outputs / scratch
+  uint32_t* w;                // [n_src * max_sends] granules written locally per send (scan input)
+  uint32_t* gs_cnt;           // [max_groups + 1] bucket histogram (zeroed by the caller), then cursors
+  sdb_send_desc* descs;       // [n_src * max_sends] localized descriptors
+  const uint32_t* w_local;    // scan of w
+  const uint32_t* w_tops;
+  const uint32_t* gs_off;     // [max_groups + 1] scan of the histogram
+  uint32_t* gs_idx;           // [n_src * max_sends]
 };
 
 // ---- optional per-kernel timing with CUDA events on the launching stream (bench / roofline) ----

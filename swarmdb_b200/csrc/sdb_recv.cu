@@ -105,6 +105,25 @@ k_scan_tops(uint32_t* __restrict__ tops, uint32_t n_tiles, unsigned long long* _
   if (tid == 0 && total_out) *total_out = s_carry;
 }
 
+// out[i] = local[i] + tops[i / TILE]: materialise a scan as a plain array
+__global__ void __launch_bounds__(256)
+k_scan_apply(const uint32_t* __restrict__ local, const uint32_t* __restrict__ tops, uint32_t* __restrict__ out, uint32_t n) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = local[i] + tops[i / SDB_SCAN_TILE];
+}
+
+// exclusive scan of n uint32 (block-local part in `local`, per-block part in `tops`), optional
+// grand total and optional materialised output; usable from the other translation units
+extern "C" cudaError_t sdb_scan_u32(const uint32_t* in, uint32_t* local, uint32_t* tops, uint32_t n,
+                                    unsigned long long* total_out, uint32_t* out, cudaStream_t stream) {
+  if (n == 0) return cudaSuccess;
+  const uint32_t tiles = (n + SDB_SCAN_TILE - 1) / SDB_SCAN_TILE;
+  k_scan_local<<<tiles, 1024, 0, stream>>>(in, 0xFFFFFFFFu, local, tops, n);
+  k_scan_tops<<<1, 1024, 0, stream>>>(tops, tiles, total_out);
+  if (out) k_scan_apply<<<(n + 255) / 256, 256, 0, stream>>>(local, tops, out, n);
+  return cudaGetLastError();
+}
+
 // ------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256)
 k_recv_count(sdb_dev_view v, sdb_recv_args r) {

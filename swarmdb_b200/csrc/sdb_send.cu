@@ -77,7 +77,8 @@ k_group_fanout_st(sdb_dev_view v, const sdb_send_desc* __restrict__ descs, uint3
       if (lane == 0) s_deliver[warp] = bal;
       if (deliver) {
         const uint64_t apos = apos0 + static_cast<uint64_t>(j) * d.rgran;
-        const uint64_t seq = seq_base + d.rec0 + ((d.flags & SDB_DESC_SHARED_SEQ) ? 0u : j);
+        const uint32_t pj = (d.flags & SDB_DESC_POS) ? __ldg(v.member_pos + d.mstart + j) : j;
+        const uint64_t seq = seq_base + d.rec0 + ((d.flags & SDB_DESC_SHARED_SEQ) ? 0u : pj);
         const uint32_t rcv = (d.flags & SDB_DESC_SHARED_SEQ) ? SDB_NO_RECEIVER : a;
         uint4* dst = reinterpret_cast<uint4*>(sdb_arena_ptr(v, apos));
         sdb_st_stream(dst, sdb_header_lo(seq, d.timestamp));
@@ -177,7 +178,8 @@ k_group_fanout_tma(sdb_dev_view v, const sdb_send_desc* __restrict__ descs, uint
       n_skip += skip;
       if (skip || a >= v.max_agents) continue;
       const uint64_t apos = apos0 + static_cast<uint64_t>(j) * d.rgran;
-      const uint64_t seq = seq_base + d.rec0 + ((d.flags & SDB_DESC_SHARED_SEQ) ? 0u : j);
+      const uint32_t pj = (d.flags & SDB_DESC_POS) ? __ldg(v.member_pos + d.mstart + j) : j;
+      const uint64_t seq = seq_base + d.rec0 + ((d.flags & SDB_DESC_SHARED_SEQ) ? 0u : pj);
       const uint32_t rcv = (d.flags & SDB_DESC_SHARED_SEQ) ? SDB_NO_RECEIVER : a;
       uint8_t* rec = sdb_arena_ptr(v, apos);
       if (padlen) sdb_tma_store(rec + 32, s_payload, padlen);
@@ -253,11 +255,15 @@ k_group_fanout_warp(sdb_dev_view v, const sdb_send_desc* __restrict__ descs, uin
     const bool shared_seq = (d.flags & SDB_DESC_SHARED_SEQ) != 0;
     const bool skip_sender = (d.flags & SDB_DESC_SKIP_SENDER) != 0;
     const bool pull = (d.flags & SDB_DESC_PULL) != 0;
+    const uint32_t* mpos = (d.flags & SDB_DESC_POS) ? v.member_pos + d.mstart : nullptr;
 
     for (uint32_t tile = 0; tile < d.mcount; tile += 64) {
       const uint32_t j0 = tile + lane, j1 = j0 + 32;
       const uint32_t a0 = j0 < d.mcount ? __ldg(mem + j0) : 0xFFFFFFFFu;
       const uint32_t a1 = j1 < d.mcount ? __ldg(mem + j1) : 0xFFFFFFFFu;
+      // sequence offset of each member: its position in the (full) group
+      const uint32_t p0 = mpos ? (j0 < d.mcount ? __ldg(mpos + j0) : 0u) : j0;
+      const uint32_t p1 = mpos ? (j1 < d.mcount ? __ldg(mpos + j1) : 0u) : j1;
       const bool s0 = j0 < d.mcount && skip_sender && a0 == d.sender;
       const bool s1 = j1 < d.mcount && skip_sender && a1 == d.sender;
       const bool d0 = j0 < d.mcount && !s0 && a0 < v.max_agents;
@@ -282,15 +288,16 @@ k_group_fanout_warp(sdb_dev_view v, const sdb_send_desc* __restrict__ descs, uin
       const uint32_t q32 = 32u / PC, r32 = 32u % PC;
       uint32_t rec = lane / PC, ch = lane % PC;
       uint8_t* const tb = base + static_cast<size_t>(tile) * rbytes;
-      const uint64_t seq0 = seq_base + d.rec0 + (shared_seq ? 0u : tile);
+      const uint64_t seq0 = seq_base + d.rec0;
       for (uint32_t done = 0; done < total; done += 32) {
         const uint32_t src = rec & 31u;
         const uint32_t ra0 = __shfl_sync(0xFFFFFFFFu, a0, src), ra1 = __shfl_sync(0xFFFFFFFFu, a1, src);
+        const uint32_t rp0 = __shfl_sync(0xFFFFFFFFu, p0, src), rp1 = __shfl_sync(0xFFFFFFFFu, p1, src);
         const bool lo_half = rec < 32u;
         const uint32_t bit = ((lo_half ? m0 : m1) >> src) & 1u;
         if (rec < nrec && bit) {
           uint4 x;
-          if (ch == 0) x = sdb_header_lo(seq0 + (shared_seq ? 0u : rec), d.timestamp);
+          if (ch == 0) x = sdb_header_lo(seq0 + (shared_seq ? 0u : (lo_half ? rp0 : rp1)), d.timestamp);
           else if (ch == 1) x = sdb_header_hi(d.sender, shared_seq ? SDB_NO_RECEIVER : (lo_half ? ra0 : ra1), d.group, d.len, d.prio, d.type);
           else x = my4[ch - 2u];
           sdb_st_stream_pol(tb + static_cast<size_t>(rec) * rbytes + (ch << 4), x, pol_stream);

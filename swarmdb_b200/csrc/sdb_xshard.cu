@@ -1,0 +1,128 @@
+// sdb_xshard.cu - cross-shard delivery of group sends (sm_100a): the receiving half.
+//
+// Replaces the reference's partitioned Kafka topic (explicit-partition produce M:469-482, one
+// consumer per agent over all partitions M:334-345).  Agents are hash-partitioned over the GPUs
+// of the box; group tables are replicated, each shard keeping the members it owns and their
+// positions in the full list.  A rank exports its batch of group sends ONCE per send
+// (descriptor + payload), the caller all-gathers the wire batches over NVLink (NCCL), and
+// every shard expands, for every send of every source, the copies for the members it owns:
+//
+//   k_wire_measure    per wire send: local member count x record size (scan input), bucket
+//                     histogram by group
+//   scans             arena offsets of every send's local region; bucket offsets
+//   k_wire_localize   writes the local fan-out descriptor (payload address inside the gathered
+//                     buffer, global sequence offset, local member list) and fills the buckets
+//   k_bucket_sort     orders each group's bucket by global send index (deterministic)
+//   then the ordinary fan-out kernel + pull index build run over the localized descriptors.
+//
+// NVLink carries (64 + payload) bytes per (send, peer) instead of (32 + payload) per recipient:
+// 8 x less for 64-way groups on 8 shards.
+#include "sdb_common.cuh"
+
+#define SDB_SCAN_TILE 4096u
+
+
+__device__ __forceinline__ const sdb_wire_header* wire_hdr(const sdb_import_args& a, uint32_t src) {
+  return reinterpret_cast<const sdb_wire_header*>(a.wire + static_cast<uint64_t>(src) * a.stride);
+}
+
+// global send index -> (source, index inside the source), sources concatenated in rank order
+__device__ __forceinline__ bool locate(const sdb_import_args& a, uint32_t gi, uint32_t& src, uint32_t& i,
+                                       uint64_t& rec_base) {
+  uint32_t first = 0; rec_base = 0;
+  for (uint32_t s = 0; s < a.n_src; ++s) {
+    const sdb_wire_header* h = wire_hdr(a, s);
+    const uint32_t n = h->magic == SDB_WIRE_MAGIC ? min(h->n_sends, a.max_sends) : 0u;
+    if (gi < first + n) { src = s; i = gi - first; return true; }
+    first += n; rec_base += h->magic == SDB_WIRE_MAGIC ? h->total_recs : 0ull;
+  }
+  return false;
+}
+
+__global__ void __launch_bounds__(256)
+k_wire_measure(sdb_import_args a, uint32_t n_total) {
+  const uint32_t gi = blockIdx.x * blockDim.x + threadIdx.x;
+  if (gi >= n_total) return;
+  uint32_t src, i; uint64_t rb;
+  if (!locate(a, gi, src, i, rb)) { a.w[gi] = 0; return; }
+  const sdb_wire_header* h = wire_hdr(a, src);
+  const sdb_send_desc* d = reinterpret_cast<const sdb_send_desc*>(reinterpret_cast<const uint8_t*>(h) + h->desc_off) + i;
+  const uint32_t g = d->group;
+  const uint32_t lc = g < a.max_groups ? a.lcount[g] : 0u;
+  a.w[gi] = lc * d->rgran;
+  if (lc) atomicAdd(a.gs_cnt + g, 1u);
+}
+
+__global__ void __launch_bounds__(256)
+k_wire_localize(sdb_import_args a, uint32_t n_total, uint32_t* gs_cur) {
+  const uint32_t gi = blockIdx.x * blockDim.x + threadIdx.x;
+  if (gi >= n_total) return;
+  uint32_t src, i; uint64_t rb;
+  sdb_send_desc out;
+  if (!locate(a, gi, src, i, rb)) {                  // unused capacity: an empty send
+    uint4 z = make_uint4(0, 0, 0, 0);
+    uint4* o = reinterpret_cast<uint4*>(a.descs + gi);
+    o[0] = z; o[1] = z; o[2] = z; o[3] = z;
+    return;
+  }
+  const sdb_wire_header* h = wire_hdr(a, src);
+  const sdb_send_desc* d = reinterpret_cast<const sdb_send_desc*>(reinterpret_cast<const uint8_t*>(h) + h->desc_off) + i;
+  out = *d;
+  const uint32_t g = d->group;
+  const uint32_t lc = g < a.max_groups ? a.lcount[g] : 0u;
+  out.payload_off = static_cast<uint64_t>(src) * a.stride + h->payload_off + d->payload_off;
+  out.gran0 = a.w_local[gi] + a.w_tops[gi / SDB_SCAN_TILE];
+  out.rec0 = static_cast<uint32_t>(rb + d->rec0);
+  out.mstart = lc ? a.lstart[g] : 0u;
+  out.mcount = lc;
+  out.flags = SDB_DESC_SKIP_SENDER | SDB_DESC_PULL | SDB_DESC_POS;
+  a.descs[gi] = out;
+  if (lc) {
+    const uint32_t slot = atomicAdd(gs_cur + g, 1u);
+    a.gs_idx[a.gs_off[g] + slot] = gi;
+  }
+}
+
+// one thread per group: ascending global send index inside the bucket (atomic fill order is arbitrary)
+__global__ void __launch_bounds__(256)
+k_bucket_sort(const uint32_t* __restrict__ gs_off, uint32_t* __restrict__ gs_idx, uint32_t n_groups) {
+  const uint32_t g = blockIdx.x * blockDim.x + threadIdx.x;
+  if (g >= n_groups) return;
+  const uint32_t b = gs_off[g], e = gs_off[g + 1];
+  for (uint32_t i = b + 1; i < e; ++i) {
+    const uint32_t x = gs_idx[i];
+    uint32_t j = i;
+    while (j > b && gs_idx[j - 1] > x) { gs_idx[j] = gs_idx[j - 1]; --j; }
+    gs_idx[j] = x;
+  }
+}
+
+extern "C" cudaError_t sdb_scan_u32(const uint32_t* in, uint32_t* local, uint32_t* tops, uint32_t n,
+                                    unsigned long long* total_out, uint32_t* out, cudaStream_t stream);
+
+// phase 1: measure + scans.  totals_dev[0] receives the arena granules this import will write.
+extern "C" cudaError_t sdb_launch_import_measure(const sdb_import_args* a, uint32_t n_cap, uint32_t* w_local,
+                                                 uint32_t* w_tops, uint32_t* gs_local, uint32_t* gs_tops,
+                                                 uint32_t* gs_off_out, unsigned long long* totals_dev,
+                                                 cudaStream_t stream, sdb_profiler* prof, int* n_launches) {
+  const int pi = sdb_prof_begin(prof, SDB_PK_XSHARD, stream);
+  cudaMemsetAsync(a->gs_cnt, 0, (static_cast<size_t>(a->max_groups) + 1) * sizeof(uint32_t), stream);
+  k_wire_measure<<<(n_cap + 255) / 256, 256, 0, stream>>>(*a, n_cap);
+  cudaError_t e = sdb_scan_u32(a->w, w_local, w_tops, n_cap, totals_dev, nullptr, stream);
+  if (e == cudaSuccess) e = sdb_scan_u32(a->gs_cnt, gs_local, gs_tops, a->max_groups + 1, nullptr, gs_off_out, stream);
+  sdb_prof_end(prof, pi, stream);
+  if (n_launches) *n_launches += 6;
+  return e != cudaSuccess ? e : cudaGetLastError();
+}
+
+// phase 2: localized descriptors + ordered buckets
+extern "C" cudaError_t sdb_launch_import_localize(const sdb_import_args* a, uint32_t n_cap, uint32_t* gs_cur,
+                                                  cudaStream_t stream, sdb_profiler* prof, int* n_launches) {
+  const int pi = sdb_prof_begin(prof, SDB_PK_XSHARD, stream);
+  cudaMemsetAsync(gs_cur, 0, static_cast<size_t>(a->max_groups) * sizeof(uint32_t), stream);
+  k_wire_localize<<<(n_cap + 255) / 256, 256, 0, stream>>>(*a, n_cap, gs_cur);
+  k_bucket_sort<<<(a->max_groups + 255) / 256, 256, 0, stream>>>(a->gs_off, a->gs_idx, a->max_groups);
+  sdb_prof_end(prof, pi, stream);
+  if (n_launches) *n_launches += 2;
+  return cudaGetLastError();
+}

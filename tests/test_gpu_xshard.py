@@ -1,0 +1,107 @@
+"""Cross-shard delivery parity: N shards must yield, agent by agent, exactly
+the streams of a 1-shard run over the concatenated batch.  All shards live on ONE GPU here (one
+handle each, wire batches concatenated in device memory instead of NCCL-all-gathered) so the
+kernels and the import protocol are checked without a multi-GPU box; tests/test_sharded_cpu.py
+covers the process-group plumbing and the N-GPU bench exercises real NCCL."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+def _payloads(rng, n, max_len):
+    lens = rng.integers(0, max_len + 1, n).astype(np.uint16)
+    stride = (max_len + 31) & ~31
+    buf = rng.integers(48, 123, n * stride + 64).astype(np.uint8)
+    return lens, np.arange(n, dtype=np.uint64) * stride, buf
+
+
+def _per_agent(counts, hdr, pay, agents):
+    from swarmdb_b200._native import payload_offsets
+    off = payload_offsets(hdr)
+    out, pos = {}, 0
+    raw = pay.tobytes()
+    for a, c in zip(agents, counts):
+        recs = []
+        for r in range(pos, pos + int(c)):
+            h = hdr[r]
+            recs.append((h.tobytes(), raw[int(off[r]): int(off[r]) + ((int(h["len"]) + 31) // 32) * 32]))
+        out[int(a)] = recs
+        pos += int(c)
+    return out
+
+
+@pytest.mark.parametrize("world", [1, 2, 4])
+def test_sharded_streams_equal_single_shard(world):
+    import torch
+    from oracle.cpu_ref import CpuOracle
+    from swarmdb_b200._native import Shard
+    from swarmdb_b200.sharded import shard_map_numbered
+
+    rng = np.random.default_rng(100 + world)
+    A, G, F, S = 2048, 40, 48, 300                       # 300 sends per rank
+    smap = shard_map_numbered("agent_", 7, A, world)
+    groups = [rng.choice(A, size=F, replace=False) for _ in range(G - 1)] + [np.array([7, 7, 9, 11], np.uint32)]
+    shards = []
+    for r in range(world):
+        s = Shard(max_agents=A, max_groups=G, ring_slots=2048, arena_bytes=1 << 27, max_batch_sends=S,
+                  max_batch_payload=S * 256 + 64, shard_id=r, num_shards=world, max_recv_records=1 << 18)
+        s.set_agent_shards(smap)
+        for g, m in enumerate(groups):
+            s.create_group(g, m)
+        shards.append(s)
+    oracle = CpuOracle(A, G)
+    for g, m in enumerate(groups):
+        oracle.create_group(g, m)
+    wire_bytes = shards[0].wire_bytes(S, S * 256 + 64)
+    wire = torch.zeros(world * wire_bytes, dtype=torch.uint8, device="cuda")
+    all_agents = np.arange(A, dtype=np.uint32)
+    for step in range(3):
+        for r in range(world):                            # every rank ingests its own slice, in rank order
+            sender = rng.integers(0, A, S); grp = rng.integers(0, G, S)
+            sender[:5] = 7; grp[:5] = G - 1                # sender inside the duplicate group
+            prio = rng.integers(0, 4, S); typ = rng.integers(0, 7, S)
+            lens, off, buf = _payloads(rng, S, 256)
+            ts = rng.random(S)
+            shards[r].export_group_batch(sender, grp, prio, typ, lens, off, buf,
+                                         wire.data_ptr() + r * wire_bytes, wire_bytes, ts)
+            shards[r].sync()
+            oracle.send_group_batch(sender, grp, prio, typ, lens, off, buf, ts)
+        bases = [s.import_wire_batches(world, wire.data_ptr(), wire_bytes) for s in shards]
+        assert len(set(bases)) == 1                        # every shard agrees on the global sequence base
+        k = [3, 1000, 1000][step]
+        merged = {}
+        for r, s in enumerate(shards):
+            local = np.nonzero(smap == r)[0].astype(np.uint32)
+            merged.update(_per_agent(*s.receive_batch(local, k), local))
+        want = _per_agent(*oracle.receive_batch(all_agents, k, rec_cap=1 << 18), all_agents)
+        assert merged.keys() == want.keys()
+        for a in range(A):
+            assert merged[a] == want[a], (step, a)
+    assert shards[0].stats()["next_seq"] == oracle.next_seq
+    for s in shards:
+        st = s.stats()
+        assert st["ring_overflow"] == 0 and st["enqueued"] == st["delivered"]
+        s.close()
+
+
+def test_wire_path_equals_direct_path_on_one_shard():
+    import torch
+    from swarmdb_b200._native import Shard
+    rng = np.random.default_rng(5)
+    A, G, F, S = 4096, 64, 64, 400
+    a = Shard(max_agents=A, max_groups=G, ring_slots=256, arena_bytes=1 << 27, max_batch_sends=S, max_batch_payload=S * 256 + 64)
+    b = Shard(max_agents=A, max_groups=G, ring_slots=256, arena_bytes=1 << 27, max_batch_sends=S, max_batch_payload=S * 256 + 64)
+    perm = rng.permutation(A)
+    for g in range(G):
+        a.create_group(g, perm[g * F:(g + 1) * F]); b.create_group(g, perm[g * F:(g + 1) * F])
+    wire = torch.zeros(a.wire_bytes(S, S * 256 + 64), dtype=torch.uint8, device="cuda")
+    for _ in range(2):
+        sender = rng.integers(0, A, S); grp = rng.integers(0, G, S)
+        prio = rng.integers(0, 4, S); lens, off, buf = _payloads(rng, S, 256)
+        base_a = a.send_group_batch(sender, grp, prio, None, lens, off, buf)
+        b.export_group_batch(sender, grp, prio, None, lens, off, buf, wire.data_ptr(), wire.numel())
+        assert b.import_wire_batches(1, wire.data_ptr(), wire.numel()) == base_a
+    ra, rb = a.receive_batch(None, 1000), b.receive_batch(None, 1000)
+    assert np.array_equal(ra[0], rb[0]) and ra[1].tobytes() == rb[1].tobytes() and ra[2].tobytes() == rb[2].tobytes()
+    a.close(); b.close()
