@@ -44,7 +44,7 @@ def lib():
         L.orc_create_group_pos.restype = C.c_int; L.orc_create_group_pos.argtypes = [vp, u32, u32, vp, vp]
         L.orc_set_next_seq.argtypes = [vp, u64]
         L.orc_get_next_seq.restype = u64; L.orc_get_next_seq.argtypes = [vp]
-        L.orc_send_group_seq.argtypes = [vp, u32] + [vp] * 10
+        L.orc_send_group_seq.argtypes = [vp, u32] + [vp] * 9
         L.orc_send_batch.restype = u64; L.orc_send_batch.argtypes = [vp, u32] + [vp] * 8
         L.orc_send_group_batch.restype = u64; L.orc_send_group_batch.argtypes = [vp, u32] + [vp] * 9
         L.orc_send_list_batch.restype = u64; L.orc_send_list_batch.argtypes = [vp, u32] + [vp] * 9
