@@ -216,6 +216,7 @@ def run_gpu(args, rank, world, local_rank):
         raise SystemExit("bench.py: no CUDA device - swarmdb_b200 has no CPU fallback")
     torch.cuda.set_device(local_rank)
     if world > 1:
+        os.environ["NCCL_DEBUG"] = os.environ.get("SDB_NCCL_DEBUG", "WARN")   # keep stdout to the one JSON line
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     from swarmdb_b200._native import Shard
 
@@ -305,6 +306,24 @@ def run_gpu(args, rank, world, local_rank):
     h2d = wl.S * wl.L + wl.S * 64                            # payload + 64-byte descriptors built by the library
     d2h = per_step_msgs * (32 + wl.L) + wl.A * 4 + 16        # headers + payloads + per-agent counts + totals
 
+    # ---- p50 dequeue: one receive_batch([agent], max_messages=100) through ctypes -> kernels -> D2H,
+    # host buffers, >= 1 message pending; 2000 distinct agents after one more group batch
+    shard.send_group_batch(*pinned_in[0])
+    shard.sync()
+    probe = np.random.default_rng(99).permutation(wl.A)[:2200].astype(np.uint32)
+    lat = []
+    small_hdr = np.zeros(128, HDR_DTYPE); small_pay = np.zeros(128 * wl.L, np.uint8)
+    for k, a in enumerate(probe):
+        one = probe[k:k + 1]
+        t1 = time.perf_counter()
+        c, h, _ = shard.receive_batch(one, 100, 0, copy_out=True, out_hdr=small_hdr, out_payload=small_pay)
+        dt = time.perf_counter() - t1
+        if k >= 200 and len(h):
+            lat.append(dt * 1e6)
+    p50 = float(np.percentile(lat, 50)) if lat else None
+    p99 = float(np.percentile(lat, 99)) if lat else None
+    shard.receive_batch(None, 100, 0, copy_out=False)          # drain the rest
+
     # ---- roofline of the dominant kernel (group fan-out)
     peak, peak_src = hbm_peak()
     fan_ms, fan_n = prof["fanout"]
@@ -336,6 +355,7 @@ def run_gpu(args, rank, world, local_rank):
         "e2e": {"value": e2e_value, "unit": "messages/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                 "steps": Ke, "ms_per_step": e2e_ms / Ke},
         "gpu_launches": int(launches),
+        "p50_dequeue_us": p50, "p99_dequeue_us": p99,
         "roofline": {"kernel": "k_group_fanout", "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                      "frac": achieved / peak, "traffic": traffic_note(), "peak_source": peak_src,
                      "algorithmic_bytes_per_msg": ALG_BYTES_FANOUT, "msgs_per_launch": per_step_msgs,
