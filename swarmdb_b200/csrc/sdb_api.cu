@@ -23,6 +23,8 @@ cudaError_t sdb_launch_commit(const sdb_dev_view*, uint32_t, uint32_t, cudaStrea
 cudaError_t sdb_launch_pull(const sdb_dev_view*, const sdb_pull_view*, const sdb_send_desc*, uint32_t, uint64_t, int,
                             cudaStream_t, sdb_profiler*);
 cudaError_t sdb_launch_receive(const sdb_dev_view*, const sdb_recv_args*, cudaStream_t, int*, sdb_profiler*, int);
+cudaError_t sdb_launch_receive_small(const sdb_dev_view*, const uint32_t*, uint32_t, uint32_t, uint32_t, uint32_t, uint32_t*,
+                                     uint32_t*, uint8_t*, cudaStream_t, sdb_profiler*);
 cudaError_t sdb_launch_arena_floor(const sdb_dev_view*, uint32_t, uint32_t, unsigned long long*, cudaStream_t);
 cudaError_t sdb_launch_pick(int mode, uint32_t n_backends, const uint32_t* weight_dev, unsigned long long* load_dev,
                             uint32_t n_req, const uint32_t* cost_dev, uint64_t seed, uint32_t* out_dev,
@@ -97,8 +99,12 @@ struct sdb_ctx {
   uint32_t* rx_agent = nullptr; uint32_t* rx_cnt = nullptr; uint32_t* rx_rec_local = nullptr; uint32_t* rx_rec_tops = nullptr;
   uint32_t* rx_plan_handle = nullptr; uint32_t* rx_plan_glen = nullptr; uint32_t* rx_plan_local = nullptr;
   uint32_t* rx_plan_tops = nullptr; unsigned long long* rx_totals = nullptr;
+  uint32_t* rx_big_list = nullptr; uint32_t* rx_big_count = nullptr;
   uint32_t* rx_count = nullptr; sdb_msg_header* rx_hdr = nullptr; uint8_t* rx_payload = nullptr;
   unsigned long long* totals_host = nullptr;   // pinned [4]
+  uint8_t* rx_small = nullptr;                 // device output block of the latency path
+  uint8_t* small_host = nullptr;               // pinned mirror
+  uint64_t small_bytes = 0;
   uint64_t pay_cap_gran = 0;
   // backends
   uint32_t* be_weight = nullptr; unsigned long long* be_load = nullptr; uint32_t n_backends = 0;
@@ -443,11 +449,15 @@ int sdb_create(const sdb_config* cfg, sdb_handle* out) {
   CUDA_TRY(h, dmalloc(&h->rx_plan_handle, c.max_recv_records + 4)); CUDA_TRY(h, dmalloc(&h->rx_plan_glen, c.max_recv_records + 4));
   CUDA_TRY(h, dmalloc(&h->rx_plan_local, c.max_recv_records + 4)); CUDA_TRY(h, dmalloc(&h->rx_plan_tops, rtiles));
   CUDA_TRY(h, dmalloc(&h->rx_totals, 4));
+  CUDA_TRY(h, dmalloc(&h->rx_big_list, A)); CUDA_TRY(h, dmalloc(&h->rx_big_count, 4));
   CUDA_TRY(h, dmalloc(&h->rx_count, A));
   CUDA_TRY(h, dmalloc(&h->rx_hdr, c.max_recv_records));
   h->pay_cap_gran = (c.max_recv_payload + SDB_GRANULE - 1) / SDB_GRANULE;
   CUDA_TRY(h, dmalloc(&h->rx_payload, h->pay_cap_gran * SDB_GRANULE));
   CUDA_TRY(h, cudaHostAlloc(reinterpret_cast<void**>(&h->totals_host), 4 * sizeof(unsigned long long), cudaHostAllocDefault));
+  h->small_bytes = 64 + 1024ull * (32 + pad32(c.max_payload_bytes));
+  CUDA_TRY(h, dmalloc(&h->rx_small, h->small_bytes));
+  CUDA_TRY(h, cudaHostAlloc(reinterpret_cast<void**>(&h->small_host), h->small_bytes, cudaHostAllocDefault));
 
   // backends
   CUDA_TRY(h, dmalloc(&h->be_weight, c.max_backends));
@@ -502,7 +512,7 @@ int sdb_destroy(sdb_handle h) {
                  h->lstart_dev, h->lcount_dev, h->xs_w, h->xs_w_local, h->xs_w_tops, h->xs_gs_cnt, h->xs_gs_local,
                  h->xs_gs_tops, h->xs_gs_cur, h->xs_gs_off, h->xs_gs_idx, h->xs_descs, h->rx_agent, h->rx_cnt,
                  h->rx_rec_local, h->rx_rec_tops, h->rx_plan_handle, h->rx_plan_glen, h->rx_plan_local, h->rx_plan_tops,
-                 h->rx_totals, h->rx_count, h->rx_hdr, h->rx_payload,
+                 h->rx_totals, h->rx_big_list, h->rx_big_count, h->rx_count, h->rx_hdr, h->rx_payload,
                  h->be_weight, h->be_load, h->be_scratch, h->be_logtab, h->be_req_cost, h->be_out};
   for (void* p : dev) if (p) cudaFree(p);
   if (h->descs_host) cudaFreeHost(h->descs_host);
@@ -511,6 +521,8 @@ int sdb_destroy(sdb_handle h) {
   if (h->wire_host) cudaFreeHost(h->wire_host);
   if (h->hdrs_host) cudaFreeHost(h->hdrs_host);
   if (h->totals_host) cudaFreeHost(h->totals_host);
+  if (h->small_host) cudaFreeHost(h->small_host);
+  if (h->rx_small) cudaFree(h->rx_small);
   if (h->staging_free) cudaEventDestroy(h->staging_free);
   if (h->prof.cap) {
     for (int i = 0; i < h->prof.cap; ++i) { cudaEventDestroy(h->prof.ev_a[i]); cudaEventDestroy(h->prof.ev_b[i]); }
@@ -860,13 +872,48 @@ int sdb_receive_batch(sdb_handle h, uint32_t n_agents, const uint32_t* agent_idx
   if (agent_idx) {
     for (uint32_t i = 0; i < n_agents; ++i)
       if (agent_idx[i] >= h->cfg.max_agents) return fail(h, SDB_EINVAL, "agent index out of range");
+  }
+  // ---- latency path: few agents, host outputs -> one launch, one D2H, one sync
+  if (agent_idx && n_agents <= 8 && hdr_out && payload_out &&
+      static_cast<uint64_t>(n_agents) * max_messages <= 1024) {
+    const uint64_t max_rec_bytes = pad32(h->cfg.max_payload_bytes);
+    uint64_t rec_cap = std::min<uint64_t>(1024, std::min<uint64_t>(hdr_cap, payload_cap / max_rec_bytes));
+    if (rec_cap == 0) return fail(h, SDB_EOUTPUT, "output buffers cannot hold a single maximum-size record");
+    cudaError_t e = sdb_launch_receive_small(&h->view, agent_idx, n_agents, max_messages, flags, static_cast<uint32_t>(rec_cap),
+                                             h->rx_plan_handle, h->rx_plan_glen, h->rx_small, h->stream, &h->prof);
+    h->launches += 1;
+    if (e != cudaSuccess) return fail(h, SDB_ECUDA, std::string("receive launch: ") + cudaGetErrorString(e));
+    const uint64_t window = std::min<uint64_t>(h->small_bytes, 16384);
+    CUDA_TRY(h, cudaMemcpyAsync(h->small_host, h->rx_small, window, cudaMemcpyDeviceToHost, h->stream));
+    CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+    const unsigned long long* t = reinterpret_cast<const unsigned long long*>(h->small_host);
+    const uint64_t total = t[0], bytes = 64 + t[1] * SDB_GRANULE;
+    if (bytes > window) {
+      CUDA_TRY(h, cudaMemcpyAsync(h->small_host + window, h->rx_small + window, bytes - window, cudaMemcpyDeviceToHost, h->stream));
+      CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+    }
+    if (count_out) std::memcpy(count_out, h->small_host + 16, static_cast<size_t>(n_agents) * sizeof(uint32_t));
+    const uint8_t* p = h->small_host + 64;
+    uint64_t poff = 0;
+    for (uint64_t r = 0; r < total; ++r) {
+      const sdb_msg_header* hd = reinterpret_cast<const sdb_msg_header*>(p);
+      hdr_out[r] = *hd;
+      const uint32_t pl = pad32(hd->len);
+      std::memcpy(payload_out + poff, p + 32, pl);
+      poff += pl; p += 32 + pl;
+    }
+    if (total_out) *total_out = total;
+    if (payload_bytes_out) *payload_bytes_out = poff;
+    return SDB_OK;
+  }
+  if (agent_idx) {
     CUDA_TRY(h, cudaMemcpyAsync(h->rx_agent, agent_idx, static_cast<size_t>(n_agents) * sizeof(uint32_t), cudaMemcpyHostToDevice, h->stream));
   }
   sdb_recv_args r{};
   r.agent_idx = agent_idx ? h->rx_agent : nullptr; r.n = n_agents; r.max_messages = max_messages; r.flags = flags;
   r.cnt = h->rx_cnt; r.rec_local = h->rx_rec_local; r.rec_tops = h->rx_rec_tops;
   r.plan_handle = h->rx_plan_handle; r.plan_glen = h->rx_plan_glen; r.plan_local = h->rx_plan_local;
-  r.plan_tops = h->rx_plan_tops; r.totals = h->rx_totals;
+  r.plan_tops = h->rx_plan_tops; r.totals = h->rx_totals; r.big_list = h->rx_big_list; r.big_count = h->rx_big_count;
   r.count_out = h->rx_count; r.hdr_out = h->rx_hdr; r.payload_out = h->rx_payload;
   // record capacity: bounded so that even maximum-size payloads fit the payload buffers
   const uint64_t max_rec_bytes = pad32(h->cfg.max_payload_bytes);

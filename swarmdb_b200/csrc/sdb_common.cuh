@@ -130,6 +130,8 @@ struct sdb_recv_args {
   uint32_t* plan_local;        // [rec_cap] scan of plan_glen (block-local part)
   uint32_t* plan_tops;         // [rec tiles]
   unsigned long long* totals;  // [0] records delivered, [1] payload granules delivered
+  uint32_t* big_list;          // [n] request slots that need the warp-per-agent selector
+  uint32_t* big_count;         // [1]
   // outputs
   uint32_t* count_out;         // [n]
   sdb_msg_header* hdr_out;     // [rec_cap]

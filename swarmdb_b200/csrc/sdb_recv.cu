@@ -151,75 +151,59 @@ __device__ __forceinline__ uint32_t lane_prefix(uint32_t ballot, uint32_t lane) 
   return __popc(ballot & ((1u << lane) - 1u));
 }
 
-__global__ void __launch_bounds__(256)
-k_recv_select(sdb_dev_view v, sdb_recv_args r) {
-  const uint32_t lane = threadIdx.x & 31;
-  const uint32_t q = blockIdx.x * blockDim.x + threadIdx.x;
-  const bool valid = q < r.n;
-  const uint32_t R = v.ring_slots, mask = R - 1;
-
-  uint32_t a = 0, head = 0, tail = 0, nt = 0, cnt = 0, roff = 0;
-  if (valid) {
-    a = r.agent_idx ? r.agent_idx[q] : q;
-    cnt = r.cnt[q];
-    roff = r.rec_local[q] + r.rec_tops[q / SDB_SCAN_TILE];
-    if (cnt && static_cast<uint64_t>(roff) + cnt > r.rec_cap) {      // does not fit: stays queued
-      atomicMin(r.totals, static_cast<unsigned long long>(roff));
-      cnt = 0;
-    }
-    r.count_out[q] = cnt;
-    if (cnt) {
-      const uint64_t st = v.ring_state[a];
-      head = static_cast<uint32_t>(st); tail = static_cast<uint32_t>(st >> 32);
-      nt = v.ntomb[a];
-    }
-  }
-  const bool prio_mode = (r.flags & SDB_RECV_PRIORITY) != 0;
-  constexpr uint32_t SMALL = 8;
-  bool done = !valid || cnt == 0;
-  if (!done && !prio_mode && nt == 0 && cnt <= SMALL) {
-    const uint64_t pol = sdb_policy_evict_last();
-    const uint16_t* ms = v.ring_meta + (static_cast<size_t>(a) << v.ring_shift);
-    const uint32_t* hs = v.ring_handle + (static_cast<size_t>(a) << v.ring_shift);
-    for (uint32_t j = 0; j < cnt; ++j) {
-      r.plan_handle[roff + j] = sdb_ld_u32_pol(hs + ((head + j) & mask), pol);
-      r.plan_glen[roff + j] = (sdb_ld_u16_pol(ms + ((head + j) & mask), pol) & SDB_META_GLEN_MASK) - 1u;
-    }
-    reinterpret_cast<uint32_t*>(v.ring_state + a)[0] = head + cnt;    // low word = head (little endian)
-    done = true;
-  }
-  uint32_t todo = __ballot_sync(0xFFFFFFFFu, !done);
-  uint32_t n_deliv = __popc(0);
-  n_deliv = valid ? cnt : 0;
-  while (todo) {
-    const int src = __ffs(todo) - 1;
-    todo &= todo - 1;
-    const uint32_t A = __shfl_sync(0xFFFFFFFFu, a, src);
-    const uint32_t H = __shfl_sync(0xFFFFFFFFu, head, src);
-    const uint32_t T = __shfl_sync(0xFFFFFFFFu, tail, src);
-    const uint32_t NT = __shfl_sync(0xFFFFFFFFu, nt, src);
-    const uint32_t C = __shfl_sync(0xFFFFFFFFu, cnt, src);
-    const uint32_t RO = __shfl_sync(0xFFFFFFFFu, roff, src);
+// one agent, whole warp: choose the C entries to deliver from the window [H, T), write their plan at
+// output index RO.., retire them (advance head / tombstone).  Stream order when !prio_mode.
+__device__ __forceinline__ void select_agent_warp(const sdb_dev_view& v, uint32_t* plan_handle, uint32_t* plan_glen,
+                                                  bool prio_mode, uint32_t A, uint32_t H, uint32_t T, uint32_t NT,
+                                                  uint32_t C, uint32_t RO, uint32_t lane) {
+  const uint32_t mask = v.ring_slots - 1;
     uint16_t* ms = v.ring_meta + (static_cast<size_t>(A) << v.ring_shift);
     const uint32_t* hs = v.ring_handle + (static_cast<size_t>(A) << v.ring_shift);
 
     if (!prio_mode && NT == 0) {
       // long contiguous run [H, H+C)
       for (uint32_t j = lane; j < C; j += 32) {
-        r.plan_handle[RO + j] = hs[(H + j) & mask];
-        r.plan_glen[RO + j] = (ms[(H + j) & mask] & SDB_META_GLEN_MASK) - 1u;
+        plan_handle[RO + j] = hs[(H + j) & mask];
+        plan_glen[RO + j] = (ms[(H + j) & mask] & SDB_META_GLEN_MASK) - 1u;
       }
       if (lane == 0) reinterpret_cast<uint32_t*>(v.ring_state + A)[0] = H + C;
-      continue;
+      return;
     }
     // ---- pass 1: histogram of live entries per priority level over the window [H, T)
     uint32_t h0 = 0, h1 = 0, h2 = 0, h3 = 0;
     if (prio_mode) {
-      for (uint32_t p = H + lane; static_cast<int32_t>(T - p) > 0; p += 32) {
-        const uint16_t m = ms[p & mask];
-        if (m == SDB_META_TOMB) continue;
-        const uint32_t L = m >> 14;
-        h0 += (L == 0); h1 += (L == 1); h2 += (L == 2); h3 += (L == 3);
+      if (v.ring_slots >= 8) {
+        // 8 metas (16 bytes) per lane per load, 4 independent loads in flight per lane (1024 entries per
+        // warp step), aligned groups of the circular window
+        for (uint32_t b8 = (H & ~7u) + (lane << 3); static_cast<int32_t>(T - b8) > 0; b8 += 1024) {
+          uint4 q[4];
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            const uint32_t p8 = b8 + u * 256;
+            q[u] = static_cast<int32_t>(T - p8) > 0 ? *reinterpret_cast<const uint4*>(ms + (p8 & mask)) : make_uint4(~0u, ~0u, ~0u, ~0u);
+          }
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            const uint32_t p8 = b8 + u * 256;
+            const uint32_t w[4] = {q[u].x, q[u].y, q[u].z, q[u].w};
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+              const uint32_t p = p8 + k;
+              const uint32_t m = (w[k >> 1] >> ((k & 1) * 16)) & 0xFFFFu;
+              if (static_cast<int32_t>(p - H) >= 0 && static_cast<int32_t>(T - p) > 0 && m != SDB_META_TOMB) {
+                const uint32_t L = m >> 14;
+                h0 += (L == 0); h1 += (L == 1); h2 += (L == 2); h3 += (L == 3);
+              }
+            }
+          }
+        }
+      } else {
+        for (uint32_t p = H + lane; static_cast<int32_t>(T - p) > 0; p += 32) {
+          const uint16_t m = ms[p & mask];
+          if (m == SDB_META_TOMB) continue;
+          const uint32_t L = m >> 14;
+          h0 += (L == 0); h1 += (L == 1); h2 += (L == 2); h3 += (L == 3);
+        }
       }
       unsigned long long lo = (static_cast<unsigned long long>(h1) << 32) | h0;
       unsigned long long hi = (static_cast<unsigned long long>(h3) << 32) | h2;
@@ -264,8 +248,8 @@ k_recv_select(sdb_dev_view v, sdb_recv_args r) {
         taken[lev] += __popc(b);
       }
       if (sel) {
-        r.plan_handle[RO + rank] = hs[p & mask];
-        r.plan_glen[RO + rank] = (m & SDB_META_GLEN_MASK) - 1u;
+        plan_handle[RO + rank] = hs[p & mask];
+        plan_glen[RO + rank] = (m & SDB_META_GLEN_MASK) - 1u;
         ms[p & mask] = SDB_META_TOMB;                      // retire
       }
       const uint32_t bs = __ballot_sync(0xFFFFFFFFu, sel);
@@ -280,9 +264,79 @@ k_recv_select(sdb_dev_view v, sdb_recv_args r) {
       reinterpret_cast<uint32_t*>(v.ring_state + A)[0] = nh;
       v.ntomb[A] = NT + got - (nh - H);
     }
+}
+
+__global__ void __launch_bounds__(256)
+k_recv_select(sdb_dev_view v, sdb_recv_args r) {
+  // one lane per requested agent: short contiguous runs (the common drain case) are planned and
+  // retired here; everything else is queued for k_recv_select_big (one warp per agent)
+  const uint32_t lane = threadIdx.x & 31;
+  const uint32_t q = blockIdx.x * blockDim.x + threadIdx.x;
+  const bool valid = q < r.n;
+  const uint32_t R = v.ring_slots, mask = R - 1;
+
+  uint32_t a = 0, head = 0, nt = 0, cnt = 0, roff = 0;
+  if (valid) {
+    a = r.agent_idx ? r.agent_idx[q] : q;
+    cnt = r.cnt[q];
+    roff = r.rec_local[q] + r.rec_tops[q / SDB_SCAN_TILE];
+    if (cnt && static_cast<uint64_t>(roff) + cnt > r.rec_cap) {      // does not fit: stays queued
+      atomicMin(r.totals, static_cast<unsigned long long>(roff));
+      cnt = 0;
+    }
+    r.count_out[q] = cnt;
+    if (cnt) {
+      head = static_cast<uint32_t>(v.ring_state[a]);
+      nt = v.ntomb[a];
+    }
+  }
+  const bool prio_mode = (r.flags & SDB_RECV_PRIORITY) != 0;
+  constexpr uint32_t SMALL = 8;
+  const bool small = valid && cnt && !prio_mode && nt == 0 && cnt <= SMALL;
+  if (small) {
+    const uint64_t pol = sdb_policy_evict_last();
+    const uint16_t* ms = v.ring_meta + (static_cast<size_t>(a) << v.ring_shift);
+    const uint32_t* hs = v.ring_handle + (static_cast<size_t>(a) << v.ring_shift);
+    uint32_t hv[SMALL]; uint16_t mv[SMALL];
+#pragma unroll
+    for (uint32_t j = 0; j < SMALL; ++j)       // all loads first, then the stores
+      if (j < cnt) { hv[j] = sdb_ld_u32_pol(hs + ((head + j) & mask), pol); mv[j] = sdb_ld_u16_pol(ms + ((head + j) & mask), pol); }
+#pragma unroll
+    for (uint32_t j = 0; j < SMALL; ++j)
+      if (j < cnt) { r.plan_handle[roff + j] = hv[j]; r.plan_glen[roff + j] = (mv[j] & SDB_META_GLEN_MASK) - 1u; }
+    reinterpret_cast<uint32_t*>(v.ring_state + a)[0] = head + cnt;    // low word = head (little endian)
+  }
+  // everything else (long runs, holes, priority order) goes to the warp-per-agent kernel
+  const bool big = valid && cnt && !small;
+  const uint32_t todo = __ballot_sync(0xFFFFFFFFu, big);
+  uint32_t n_deliv = valid ? cnt : 0;
+  if (todo) {
+    uint32_t basew = 0;
+    if (lane == 0) basew = atomicAdd(r.big_count, static_cast<uint32_t>(__popc(todo)));
+    basew = __shfl_sync(0xFFFFFFFFu, basew, 0);
+    if (big) r.big_list[basew + lane_prefix(todo, lane)] = q;
   }
   for (int o = 16; o; o >>= 1) n_deliv += __shfl_xor_sync(0xFFFFFFFFu, n_deliv, o);
   if (lane == 0 && n_deliv) atomicAdd(&v.ctr->delivered, static_cast<unsigned long long>(n_deliv));
+}
+
+// warp per listed agent (persistent grid-stride over the worklist built by k_recv_select)
+__global__ void __launch_bounds__(256)
+k_recv_select_big(sdb_dev_view v, sdb_recv_args r) {
+  const uint32_t lane = threadIdx.x & 31;
+  const uint32_t gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const uint32_t nw = (gridDim.x * blockDim.x) >> 5;
+  const uint32_t n_big = *r.big_count;
+  const bool prio_mode = (r.flags & SDB_RECV_PRIORITY) != 0;
+  for (uint32_t w = gw; w < n_big; w += nw) {
+    const uint32_t q = r.big_list[w];
+    const uint32_t a = r.agent_idx ? r.agent_idx[q] : q;
+    const uint32_t cnt = r.count_out[q];
+    const uint32_t roff = r.rec_local[q] + r.rec_tops[q / SDB_SCAN_TILE];
+    const uint64_t st = v.ring_state[a];
+    select_agent_warp(v, r.plan_handle, r.plan_glen, prio_mode, a, static_cast<uint32_t>(st),
+                      static_cast<uint32_t>(st >> 32), v.ntomb[a], cnt, roff, lane);
+  }
 }
 
 // scan over the per-record payload sizes; the element count lives on the device (totals[0])
@@ -367,6 +421,96 @@ k_recv_gather(sdb_dev_view v, sdb_recv_args r) {
 }
 
 // ------------------------------------------------------------------------------------------
+// latency path: up to 8 agents, up to 1024 records, ONE launch (count, scan, select, retire, gather).
+// Output block: u64 total records | u64 total granules | u32 counts[8] | pad to 64 B | the records
+// back to back in arena format (32-B header + padded payload), so the host needs one D2H.
+// ------------------------------------------------------------------------------------------
+#define SDB_SMALL_AGENTS 8u
+#define SDB_SMALL_RECS 1024u
+struct sdb_small_agents { uint32_t idx[SDB_SMALL_AGENTS]; };
+
+__global__ void __launch_bounds__(256)
+k_recv_small(sdb_dev_view v, sdb_small_agents ag, uint32_t n, uint32_t max_messages, uint32_t flags, uint32_t rec_cap,
+             uint32_t* __restrict__ plan_handle, uint32_t* __restrict__ plan_glen, uint8_t* __restrict__ out) {
+  __shared__ uint32_t s_cnt[SDB_SMALL_AGENTS], s_roff[SDB_SMALL_AGENTS + 1], s_goff[SDB_SMALL_RECS + 1];
+  __shared__ uint32_t s_total;
+  const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const bool mine = warp < n;
+  const uint32_t a = mine ? ag.idx[warp] : 0u;
+  uint32_t head = 0, tail = 0, nt = 0;
+  if (lane == 0) {
+    uint32_t c = 0;
+    if (mine && a < v.max_agents) {
+      const uint64_t st = v.ring_state[a];
+      head = static_cast<uint32_t>(st); tail = static_cast<uint32_t>(st >> 32); nt = v.ntomb[a];
+      c = min(tail - head - nt, max_messages);
+    }
+    s_cnt[warp] = c;
+  }
+  __syncthreads();
+  if (tid == 0) {
+    uint32_t acc = 0, total = 0; bool open = true;
+    for (uint32_t w = 0; w < SDB_SMALL_AGENTS; ++w) {
+      s_roff[w] = acc;
+      const uint32_t c = s_cnt[w];
+      if (open && acc + c <= rec_cap) total = acc + c; else { open = false; s_cnt[w] = 0; }   // whole-agent truncation
+      acc += c;
+    }
+    s_total = total;
+  }
+  __syncthreads();
+  const uint32_t cnt = s_cnt[warp], roff = s_roff[warp];
+  if (lane == 0 && mine) reinterpret_cast<uint32_t*>(out + 16)[warp] = cnt;
+  if (cnt) {
+    const uint32_t H = __shfl_sync(0xFFFFFFFFu, head, 0), T = __shfl_sync(0xFFFFFFFFu, tail, 0);
+    const uint32_t NT = __shfl_sync(0xFFFFFFFFu, nt, 0);
+    select_agent_warp(v, plan_handle, plan_glen, (flags & SDB_RECV_PRIORITY) != 0, a, H, T, NT, cnt, roff, lane);
+  }
+  __syncthreads();
+  const uint32_t total = s_total;
+  if (warp == 0) {                       // record offsets (granules, header included)
+    uint32_t run = 0;
+    for (uint32_t r0 = 0; r0 < total; r0 += 32) {
+      const uint32_t r = r0 + lane;
+      const uint32_t g = r < total ? plan_glen[r] + 1u : 0u;
+      uint32_t incl = g;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) { const uint32_t y = __shfl_up_sync(0xFFFFFFFFu, incl, o); if (lane >= o) incl += y; }
+      if (r < total) s_goff[r] = run + incl - g;
+      run += __shfl_sync(0xFFFFFFFFu, incl, 31);
+    }
+    if (lane == 0) {
+      s_goff[total] = run;
+      reinterpret_cast<unsigned long long*>(out)[0] = total;
+      reinterpret_cast<unsigned long long*>(out)[1] = run;
+      if (total) atomicAdd(&v.ctr->delivered, static_cast<unsigned long long>(total));
+    }
+  }
+  __syncthreads();
+  const uint32_t l8 = tid & 7;
+  for (uint32_t r = tid >> 3; r < total; r += 32) {
+    const uint32_t g = plan_glen[r];
+    const uint8_t* src = v.arena + ((static_cast<uint64_t>(plan_handle[r]) & v.gmask) << 5);
+    uint8_t* dst = out + 64 + (static_cast<size_t>(s_goff[r]) << 5);
+    const uint32_t nchunk = 2u + (g << 1);
+    for (uint32_t c = l8; c < nchunk; c += 8) sdb_st_stream(dst + (c << 4), sdb_ld_stream(src + (c << 4)));
+  }
+}
+
+extern "C" cudaError_t sdb_launch_receive_small(const sdb_dev_view* v, const uint32_t* agents_host, uint32_t n,
+                                                uint32_t max_messages, uint32_t flags, uint32_t rec_cap,
+                                                uint32_t* plan_handle, uint32_t* plan_glen, uint8_t* out,
+                                                cudaStream_t stream, sdb_profiler* prof) {
+  sdb_small_agents ag{};
+  for (uint32_t i = 0; i < n && i < SDB_SMALL_AGENTS; ++i) ag.idx[i] = agents_host[i];
+  const int pi = sdb_prof_begin(prof, SDB_PK_RECV_GATHER, stream);
+  k_recv_small<<<1, 256, 0, stream>>>(*v, ag, n, max_messages, flags, rec_cap < SDB_SMALL_RECS ? rec_cap : SDB_SMALL_RECS,
+                                      plan_handle, plan_glen, out);
+  sdb_prof_end(prof, pi, stream);
+  return cudaGetLastError();
+}
+
+// ------------------------------------------------------------------------------------------
 extern "C" cudaError_t sdb_launch_receive(const sdb_dev_view* v, const sdb_recv_args* r, cudaStream_t stream,
                                           int* n_launches, sdb_profiler* prof, int sm_count) {
   if (r->n == 0) return cudaSuccess;
@@ -380,7 +524,14 @@ extern "C" cudaError_t sdb_launch_receive(const sdb_dev_view* v, const sdb_recv_
   k_scan_tops<<<1, 1024, 0, stream>>>(r->rec_tops, tiles, r->totals);          // totals[0] = records requested
   sdb_prof_end(prof, pi, stream);
   pi = sdb_prof_begin(prof, SDB_PK_RECV_SELECT, stream);
+  cudaMemsetAsync(r->big_count, 0, sizeof(uint32_t), stream);
   k_recv_select<<<(n + 255) / 256, 256, 0, stream>>>(*v, *r);                   // may lower totals[0] (capacity)
+  {
+    uint32_t bg = static_cast<uint32_t>(sm_count) * 8u;                         // 8 warps per CTA, 8 CTAs per SM
+    const uint32_t need = (n + 7) / 8;
+    if (bg > need) bg = need;
+    k_recv_select_big<<<bg, 256, 0, stream>>>(*v, *r);
+  }
   sdb_prof_end(prof, pi, stream);
   // upper bound on records: min(rec_cap, n * max_messages); grids sized from it, kernels read the true count
   uint64_t bound = static_cast<uint64_t>(n) * r->max_messages;
@@ -398,7 +549,7 @@ extern "C" cudaError_t sdb_launch_receive(const sdb_dev_view* v, const sdb_recv_
   pi = sdb_prof_begin(prof, SDB_PK_RECV_GATHER, stream);
   k_recv_gather<<<static_cast<uint32_t>(gblocks), 256, 0, stream>>>(*v, *r);
   sdb_prof_end(prof, pi, stream);
-  if (n_launches) *n_launches += 7;
+  if (n_launches) *n_launches += 8;
   return cudaGetLastError();
 }
 

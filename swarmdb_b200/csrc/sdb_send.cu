@@ -388,54 +388,76 @@ __device__ __forceinline__ void pull_emit(const sdb_dev_view& v, const sdb_send_
   ++tail; ++n_enq;
 }
 
+// Four lanes per agent ("quad"): the lanes of a quad take consecutive sends of the agent's bucket,
+// so the dependent loads (bucket entry -> descriptor) of one agent run in parallel and its new
+// ring entries leave in one coalesced store per array.  Agents with several memberships are
+// merged serially by the quad's first lane.
 __global__ void __launch_bounds__(256)
 k_pull_index(sdb_dev_view v, sdb_pull_view pv, const sdb_send_desc* __restrict__ descs, uint32_t n_agents,
              uint64_t arena_base, uint32_t set_ctail) {
-  const uint32_t a = blockIdx.x * blockDim.x + threadIdx.x;
-  const uint32_t lane = threadIdx.x & 31;
+  const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+  const uint32_t a = t >> 2, sub = t & 3u, lane = threadIdx.x & 31, qb = lane & ~3u;
   uint32_t n_enq = 0, n_ovf = 0;
   const uint64_t pol = sdb_policy_evict_last();
-  if (a < n_agents) {
-    const uint32_t k0 = pv.memb_off[a], k1 = pv.memb_off[a + 1];
-    if (k1 > k0) {
-      const uint64_t st = sdb_ld_u64_pol(v.ring_state + a, pol);
-      const uint32_t head = static_cast<uint32_t>(st);
-      uint32_t tail = static_cast<uint32_t>(st >> 32);
-      const uint32_t tail0 = tail;
-      if (k1 - k0 == 1) {
-        const uint32_t g = pv.memb_grp[k0], j = pv.memb_pos[k0];
-        const uint32_t e = pv.gs_off[g + 1];
-        for (uint32_t p = pv.gs_off[g]; p < e; ++p) pull_emit(v, descs, pv.gs_idx[p], j, a, arena_base, head, tail, n_enq, n_ovf, pol);
-      } else {
-        // merge the buckets of every membership by (send index, member position); the pair strictly
-        // greater than the last emitted one is found per list by binary search, so no cursor storage
-        long long last_s = -1; uint32_t last_j = 0;
-        for (;;) {
-          uint32_t best_s = 0xFFFFFFFFu, best_j = 0xFFFFFFFFu;
-          for (uint32_t k = k0; k < k1; ++k) {
-            const uint32_t g = pv.memb_grp[k], j = pv.memb_pos[k];
-            uint32_t lo = pv.gs_off[g], hi = pv.gs_off[g + 1];
-            // first send s in the bucket with (s, j) > (last_s, last_j)
-            const long long need = (last_s >= 0 && j <= last_j) ? last_s + 1 : last_s;   // s >= need
-            while (lo < hi) {
-              const uint32_t mid = (lo + hi) >> 1;
-              if (static_cast<long long>(pv.gs_idx[mid]) < need) lo = mid + 1; else hi = mid;
-            }
-            if (lo < pv.gs_off[g + 1]) {
-              const uint32_t s = pv.gs_idx[lo];
-              if (s < best_s || (s == best_s && j < best_j)) { best_s = s; best_j = j; }
-            }
-          }
-          if (best_s == 0xFFFFFFFFu) break;
-          pull_emit(v, descs, best_s, best_j, a, arena_base, head, tail, n_enq, n_ovf, pol);
-          last_s = best_s; last_j = best_j;
-        }
-      }
-      if (tail != tail0) {
-        sdb_st_u64_pol(v.ring_state + a, (static_cast<uint64_t>(tail) << 32) | head, pol);
-        if (set_ctail) sdb_st_u32_pol(v.ctail + a, tail, pol);
+  const bool valid = a < n_agents;
+  uint32_t k0 = 0, k1 = 0;
+  if (valid) { k0 = pv.memb_off[a]; k1 = pv.memb_off[a + 1]; }
+  const uint32_t nk = k1 - k0;
+  uint32_t head = 0, tail = 0, tail0 = 0;
+  if (nk) {
+    const uint64_t st = sdb_ld_u64_pol(v.ring_state + a, pol);
+    head = static_cast<uint32_t>(st); tail = tail0 = static_cast<uint32_t>(st >> 32);
+  }
+  // ---- single membership: the common case, quad-parallel
+  uint32_t b0 = 0, b1 = 0, j = 0;
+  if (nk == 1) { const uint32_t g = pv.memb_grp[k0]; j = pv.memb_pos[k0]; b0 = pv.gs_off[g]; b1 = pv.gs_off[g + 1]; }
+  const uint32_t R = v.ring_slots;
+  for (uint32_t p = b0 + sub; __any_sync(0xFFFFFFFFu, p - sub < b1); p += 4) {
+    const bool act = p < b1;
+    uint4 q1 = make_uint4(0, 0, 0, 0);
+    if (act) q1 = __ldg(reinterpret_cast<const uint4*>(descs + pv.gs_idx[p]) + 1);     // gran0, sender, rgran, len|prio|type
+    const bool keep = act && q1.y != a;                                                 // member == sender (M:1268)
+    const uint32_t bal = __ballot_sync(0xFFFFFFFFu, keep);
+    const uint32_t qbits = (bal >> qb) & 0xFu;
+    const uint32_t pos = tail + __popc(qbits & ((1u << sub) - 1u));
+    if (keep) {
+      if (pos - head >= R) ++n_ovf;
+      else {
+        const size_t slot = (static_cast<size_t>(a) << v.ring_shift) + (pos & (R - 1));
+        sdb_st_u32_pol(v.ring_handle + slot, static_cast<uint32_t>(arena_base + q1.x + static_cast<uint64_t>(j) * q1.z), pol);
+        sdb_st_u16_pol(v.ring_meta + slot, static_cast<uint16_t>((((q1.w >> 16) & 0xFFu) << 14) | q1.z), pol);
+        ++n_enq;
       }
     }
+    tail += __popc(qbits);
+  }
+  if (nk == 1 && tail - head > R) tail = head + R;           // dropped entries were counted, never written
+  // ---- several memberships: serial merge by (send index, member position) on the quad's first lane
+  if (nk > 1 && sub == 0) {
+    long long last_s = -1; uint32_t last_j = 0;
+    for (;;) {
+      uint32_t best_s = 0xFFFFFFFFu, best_j = 0xFFFFFFFFu;
+      for (uint32_t k = k0; k < k1; ++k) {
+        const uint32_t g = pv.memb_grp[k], jj = pv.memb_pos[k];
+        uint32_t lo = pv.gs_off[g], hi = pv.gs_off[g + 1];
+        const long long need = (last_s >= 0 && jj <= last_j) ? last_s + 1 : last_s;   // first s with (s, jj) > (last_s, last_j)
+        while (lo < hi) {
+          const uint32_t mid = (lo + hi) >> 1;
+          if (static_cast<long long>(pv.gs_idx[mid]) < need) lo = mid + 1; else hi = mid;
+        }
+        if (lo < pv.gs_off[g + 1]) {
+          const uint32_t s2 = pv.gs_idx[lo];
+          if (s2 < best_s || (s2 == best_s && jj < best_j)) { best_s = s2; best_j = jj; }
+        }
+      }
+      if (best_s == 0xFFFFFFFFu) break;
+      pull_emit(v, descs, best_s, best_j, a, arena_base, head, tail, n_enq, n_ovf, pol);
+      last_s = best_s; last_j = best_j;
+    }
+  }
+  if (sub == 0 && tail != tail0) {
+    sdb_st_u64_pol(v.ring_state + a, (static_cast<uint64_t>(tail) << 32) | head, pol);
+    if (set_ctail) sdb_st_u32_pol(v.ctail + a, tail, pol);
   }
   for (int o = 16; o; o >>= 1) {
     n_enq += __shfl_xor_sync(0xFFFFFFFFu, n_enq, o);
@@ -587,7 +609,8 @@ extern "C" cudaError_t sdb_launch_pull(const sdb_dev_view* v, const sdb_pull_vie
                                        sdb_profiler* prof) {
   if (n_agents == 0) return cudaSuccess;
   const int pi = sdb_prof_begin(prof, SDB_PK_INDEX, stream);
-  k_pull_index<<<(n_agents + 255) / 256, 256, 0, stream>>>(*v, *pv, descs, n_agents, arena_base, set_ctail ? 1u : 0u);
+  const uint64_t threads = static_cast<uint64_t>(n_agents) * 4;
+  k_pull_index<<<static_cast<uint32_t>((threads + 255) / 256), 256, 0, stream>>>(*v, *pv, descs, n_agents, arena_base, set_ctail ? 1u : 0u);
   sdb_prof_end(prof, pi, stream);
   return cudaGetLastError();
 }
