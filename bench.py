@@ -216,8 +216,19 @@ def run_gpu(args, rank, world, local_rank):
         raise SystemExit("bench.py: no CUDA device - swarmdb_b200 has no CPU fallback")
     torch.cuda.set_device(local_rank)
     if world > 1:
-        os.environ["NCCL_DEBUG"] = os.environ.get("SDB_NCCL_DEBUG", "WARN")   # keep stdout to the one JSON line
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+        # NCCL prints its version banner to stdout at communicator creation: keep stdout to the one JSON line
+        sys.stdout.flush()
+        saved = os.dup(1)
+        os.dup2(2, 1)
+        try:
+            dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+            warm = torch.zeros(1, device="cuda")
+            dist.all_reduce(warm)
+            torch.cuda.synchronize()
+        finally:
+            sys.stdout.flush()
+            os.dup2(saved, 1)
+            os.close(saved)
     from swarmdb_b200._native import Shard
 
     wl = Workload()

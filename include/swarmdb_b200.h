@@ -235,6 +235,15 @@ int sdb_export_group_batch(sdb_handle h, uint32_t n,
                            const uint8_t* prio, const uint8_t* type, const uint16_t* len,
                            const uint64_t* payload_off, const uint8_t* payload, uint64_t payload_bytes,
                            const double* timestamp, void* wire_dev, uint64_t wire_cap);
+/* Same, for a mixed batch in call order (kinds as in sdb_send_mixed_batch): point-to-point sends are
+ * delivered only by the shard that owns the receiver, broadcast lists by every shard for the
+ * recipients it owns.  Recipient lists travel inside the wire batch (count them in max_payload_bytes). */
+int sdb_export_mixed_batch(sdb_handle h, uint32_t n,
+                           const uint32_t* sender, const uint8_t* kind, const uint32_t* target,
+                           uint32_t n_lists, const uint64_t* list_off, const uint32_t* list_idx,
+                           const uint8_t* prio, const uint8_t* type, const uint16_t* len,
+                           const uint64_t* payload_off, const uint8_t* payload, uint64_t payload_bytes,
+                           const double* timestamp, void* wire_dev, uint64_t wire_cap);
 int sdb_import_wire_batches(sdb_handle h, uint32_t n_src, const void* wire_dev_all, uint64_t wire_stride,
                             uint64_t* seq_base_out);
 

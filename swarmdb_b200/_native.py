@@ -56,7 +56,7 @@ EXPORTS = ["sdb_abi_version", "sdb_create", "sdb_destroy", "sdb_set_stream", "sd
            "sdb_get_stats", "sdb_profile", "sdb_profile_read", "sdb_register_agents", "sdb_deregister_agents", "sdb_create_group", "sdb_send_batch",
            "sdb_send_group_batch", "sdb_send_list_batch", "sdb_send_mixed_batch", "sdb_stage_batch", "sdb_submit_staged", "sdb_free_staged",
            "sdb_receive_batch", "sdb_last_receive_dev", "sdb_wire_bytes", "sdb_set_agent_shards",
-           "sdb_export_group_batch", "sdb_import_wire_batches", "sdb_set_backends", "sdb_get_backend_loads",
+           "sdb_export_group_batch", "sdb_export_mixed_batch", "sdb_import_wire_batches", "sdb_set_backends", "sdb_get_backend_loads",
            "sdb_release_backends", "sdb_select_backend_batch"]
 
 _lib = None
@@ -99,6 +99,8 @@ def load_library() -> C.CDLL:
     L.sdb_wire_bytes.restype = u64; L.sdb_wire_bytes.argtypes = [u32, u64]
     L.sdb_set_agent_shards.restype = i32; L.sdb_set_agent_shards.argtypes = [vp, u32, vp]
     L.sdb_export_group_batch.restype = i32; L.sdb_export_group_batch.argtypes = [vp, u32] + [vp] * 7 + [u64, vp, vp, u64]
+    L.sdb_export_mixed_batch.restype = i32
+    L.sdb_export_mixed_batch.argtypes = [vp, u32, vp, vp, vp, u32] + [vp] * 7 + [u64, vp, vp, u64]
     L.sdb_import_wire_batches.restype = i32; L.sdb_import_wire_batches.argtypes = [vp, u32, vp, u64, vp]
     L.sdb_set_backends.restype = i32; L.sdb_set_backends.argtypes = [vp, u32, vp, vp]
     L.sdb_get_backend_loads.restype = i32; L.sdb_get_backend_loads.argtypes = [vp, u32, vp]
@@ -303,6 +305,17 @@ class Shard:
         self._keep = pl
         self._check(self._L.sdb_export_group_batch(self._h, len(s), _p(s), _p(g), _p(prio), _p(typ), _p(lens), _p(po),
                                                    _p(pl), pl.nbytes, _p(ts), C.c_void_p(wire_dev), wire_cap))
+
+    def export_mixed_batch(self, sender, kind, target, list_off, list_idx, prio, typ, lens, payload_off, payload,
+                           wire_dev: int, wire_cap: int, ts=None) -> None:
+        s, k, t = _arr(sender, np.uint32), _arr(kind, np.uint8), _arr(target, np.uint32)
+        lo = _arr(list_off if list_off is not None else [0], np.uint64)
+        li = _arr(list_idx if list_idx is not None else [], np.uint32)
+        prio, typ, lens, po, pl, ts = self._common(len(s), prio, typ, lens, payload_off, payload, ts)
+        self._keep = pl
+        self._check(self._L.sdb_export_mixed_batch(self._h, len(s), _p(s), _p(k), _p(t), len(lo) - 1, _p(lo), _p(li),
+                                                   _p(prio), _p(typ), _p(lens), _p(po), _p(pl), pl.nbytes, _p(ts),
+                                                   C.c_void_p(wire_dev), wire_cap))
 
     def import_wire_batches(self, n_src: int, wire_dev_all: int, stride: int) -> int:
         """Expand the wire batches of `n_src` ranks (rank order, `stride` bytes apart) for the agents this shard owns."""

@@ -32,7 +32,7 @@ cudaError_t sdb_launch_pick(int mode, uint32_t n_backends, const uint32_t* weigh
                             cudaStream_t stream, int* n_launches);
 void sdb_build_log2_table(uint32_t* tab257);
 cudaError_t sdb_launch_import_measure(const sdb_import_args*, uint32_t, uint32_t*, uint32_t*, uint32_t*, uint32_t*, uint32_t*,
-                                      unsigned long long*, cudaStream_t, sdb_profiler*, int*);
+                                      uint32_t*, uint32_t*, unsigned long long*, cudaStream_t, sdb_profiler*, int*);
 cudaError_t sdb_launch_import_localize(const sdb_import_args*, uint32_t, uint32_t*, cudaStream_t, sdb_profiler*, int*);
 }
 
@@ -92,6 +92,8 @@ struct sdb_ctx {
   uint32_t* xs_w = nullptr; uint32_t* xs_w_local = nullptr; uint32_t* xs_w_tops = nullptr;
   uint32_t* xs_gs_cnt = nullptr; uint32_t* xs_gs_local = nullptr; uint32_t* xs_gs_tops = nullptr; uint32_t* xs_gs_cur = nullptr;
   uint32_t* xs_gs_off = nullptr; uint32_t* xs_gs_idx = nullptr; sdb_send_desc* xs_descs = nullptr;
+  uint32_t* xs_lw = nullptr; uint32_t* xs_lw_local = nullptr; uint32_t* xs_lw_tops = nullptr;
+  uint8_t* shard_of_dev = nullptr;
   uint8_t* wire_host = nullptr;                // pinned: header + descriptors of an export
   sdb_wire_header* hdrs_host = nullptr;        // pinned [num_shards]
   cudaEvent_t staging_free = nullptr;    // previous H2D of pinned staging has completed
@@ -448,13 +450,13 @@ int sdb_create(const sdb_config* cfg, sdb_handle* out) {
   const size_t rtiles = (c.max_recv_records + SDB_SCAN_TILE - 1) / SDB_SCAN_TILE + 1;
   CUDA_TRY(h, dmalloc(&h->rx_plan_handle, c.max_recv_records + 4)); CUDA_TRY(h, dmalloc(&h->rx_plan_glen, c.max_recv_records + 4));
   CUDA_TRY(h, dmalloc(&h->rx_plan_local, c.max_recv_records + 4)); CUDA_TRY(h, dmalloc(&h->rx_plan_tops, rtiles));
-  CUDA_TRY(h, dmalloc(&h->rx_totals, 4));
+  CUDA_TRY(h, dmalloc(&h->rx_totals, 8));
   CUDA_TRY(h, dmalloc(&h->rx_big_list, A)); CUDA_TRY(h, dmalloc(&h->rx_big_count, 4));
   CUDA_TRY(h, dmalloc(&h->rx_count, A));
   CUDA_TRY(h, dmalloc(&h->rx_hdr, c.max_recv_records));
   h->pay_cap_gran = (c.max_recv_payload + SDB_GRANULE - 1) / SDB_GRANULE;
   CUDA_TRY(h, dmalloc(&h->rx_payload, h->pay_cap_gran * SDB_GRANULE));
-  CUDA_TRY(h, cudaHostAlloc(reinterpret_cast<void**>(&h->totals_host), 4 * sizeof(unsigned long long), cudaHostAllocDefault));
+  CUDA_TRY(h, cudaHostAlloc(reinterpret_cast<void**>(&h->totals_host), 8 * sizeof(unsigned long long), cudaHostAllocDefault));
   h->small_bytes = 64 + 1024ull * (32 + pad32(c.max_payload_bytes));
   CUDA_TRY(h, dmalloc(&h->rx_small, h->small_bytes));
   CUDA_TRY(h, cudaHostAlloc(reinterpret_cast<void**>(&h->small_host), h->small_bytes, cudaHostAllocDefault));
@@ -490,6 +492,9 @@ int sdb_create(const sdb_config* cfg, sdb_handle* out) {
     CUDA_TRY(h, dmalloc(&h->xs_gs_cnt, G1)); CUDA_TRY(h, dmalloc(&h->xs_gs_local, G1)); CUDA_TRY(h, dmalloc(&h->xs_gs_tops, gt));
     CUDA_TRY(h, dmalloc(&h->xs_gs_cur, G1)); CUDA_TRY(h, dmalloc(&h->xs_gs_off, G1)); CUDA_TRY(h, dmalloc(&h->xs_gs_idx, n));
     CUDA_TRY(h, dmalloc(&h->xs_descs, n));
+    CUDA_TRY(h, dmalloc(&h->xs_lw, n)); CUDA_TRY(h, dmalloc(&h->xs_lw_local, n)); CUDA_TRY(h, dmalloc(&h->xs_lw_tops, wt));
+    CUDA_TRY(h, dmalloc(&h->shard_of_dev, c.max_agents));
+    CUDA_TRY(h, cudaMemset(h->shard_of_dev, static_cast<int>(c.shard_id), c.max_agents));
     CUDA_TRY(h, cudaHostAlloc(reinterpret_cast<void**>(&h->wire_host), 64 + static_cast<size_t>(c.max_batch_sends) * sizeof(sdb_send_desc), cudaHostAllocDefault));
     CUDA_TRY(h, cudaHostAlloc(reinterpret_cast<void**>(&h->hdrs_host), static_cast<size_t>(c.num_shards) * sizeof(sdb_wire_header), cudaHostAllocDefault));
   }
@@ -510,7 +515,8 @@ int sdb_destroy(sdb_handle h) {
                  h->scratch.descs_dev, h->scratch.payload_dev, h->scratch.list_dev, h->scratch.gs_off_dev,
                  h->scratch.gs_idx_dev, h->memb_off_dev, h->memb_grp_dev, h->memb_pos_dev, h->member_pos_dev,
                  h->lstart_dev, h->lcount_dev, h->xs_w, h->xs_w_local, h->xs_w_tops, h->xs_gs_cnt, h->xs_gs_local,
-                 h->xs_gs_tops, h->xs_gs_cur, h->xs_gs_off, h->xs_gs_idx, h->xs_descs, h->rx_agent, h->rx_cnt,
+                 h->xs_gs_tops, h->xs_gs_cur, h->xs_gs_off, h->xs_gs_idx, h->xs_descs, h->xs_lw, h->xs_lw_local,
+                 h->xs_lw_tops, h->shard_of_dev, h->rx_agent, h->rx_cnt,
                  h->rx_rec_local, h->rx_rec_tops, h->rx_plan_handle, h->rx_plan_glen, h->rx_plan_local, h->rx_plan_tops,
                  h->rx_totals, h->rx_big_list, h->rx_big_count, h->rx_count, h->rx_hdr, h->rx_payload,
                  h->be_weight, h->be_load, h->be_scratch, h->be_logtab, h->be_req_cost, h->be_out};
@@ -659,7 +665,8 @@ int sdb_create_group(sdb_handle h, uint32_t g, uint32_t n_members, const uint32_
 }
 
 uint64_t sdb_wire_bytes(uint32_t max_sends, uint64_t max_payload_bytes) {
-  return 64ull + static_cast<uint64_t>(max_sends) * sizeof(sdb_send_desc) + ((max_payload_bytes + 64 + 63) & ~63ull);
+  // header + descriptors + payload (+ slack); broadcast recipient lists count towards max_payload_bytes
+  return 64ull + static_cast<uint64_t>(max_sends) * sizeof(sdb_send_desc) + ((max_payload_bytes + 128 + 63) & ~63ull);
 }
 
 int sdb_set_agent_shards(sdb_handle h, uint32_t n, const uint8_t* shard_of) {
@@ -670,30 +677,38 @@ int sdb_set_agent_shards(sdb_handle h, uint32_t n, const uint8_t* shard_of) {
     h->shard_of[i] = shard_of[i];
   }
   h->sharded = h->cfg.num_shards > 1;
+  if (h->sharded) h->n_agents = h->cfg.max_agents;   // receivers are named by other ranks: sweeps cover the whole index space
+  CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+  CUDA_TRY(h, cudaMemcpy(h->shard_of_dev, h->shard_of.data(), h->cfg.max_agents, cudaMemcpyHostToDevice));
   // groups created earlier are re-filtered against the new ownership map
   bool any = false;
   for (uint32_t g = 0; g < h->cfg.max_groups; ++g) if (h->gdefined[g]) { localize_group(h, g); any = true; }
   return any ? upload_all_groups(h) : SDB_OK;
 }
 
-int sdb_export_group_batch(sdb_handle h, uint32_t n, const uint32_t* sender, const uint32_t* group_idx, const uint8_t* prio,
-                           const uint8_t* type, const uint16_t* len, const uint64_t* payload_off, const uint8_t* payload,
-                           uint64_t payload_bytes, const double* timestamp, void* wire_dev, uint64_t wire_cap) {
+// kind == nullptr: every send is a group send (target = group index)
+static int export_common(sdb_ctx* h, uint32_t n, const uint32_t* sender, const uint8_t* kind, const uint32_t* target,
+                         uint32_t n_lists, const uint64_t* list_off, const uint32_t* list_idx, const uint8_t* prio,
+                         const uint8_t* type, const uint16_t* len, const uint64_t* payload_off, const uint8_t* payload,
+                         uint64_t payload_bytes, const double* timestamp, void* wire_dev, uint64_t wire_cap) {
   if (!h || !wire_dev) return SDB_EINVAL;
-  if (n && (!sender || !group_idx || !len)) return fail(h, SDB_EINVAL, "null array");
+  if (n && (!sender || !target || !len)) return fail(h, SDB_EINVAL, "null array");
   if (n > h->cfg.max_batch_sends) return fail(h, SDB_ECAPACITY, "n exceeds max_batch_sends");
   if (payload_bytes && !payload) return fail(h, SDB_EINVAL, "null payload");
-  const uint64_t desc_off = 64, pay_off = 64 + static_cast<uint64_t>(n) * sizeof(sdb_send_desc);
+  const uint64_t n_list = (n_lists && list_off) ? list_off[n_lists] : 0;
+  if (n_list > h->cfg.list_pool_entries) return fail(h, SDB_ECAPACITY, "recipient lists exceed list_pool_entries");
+  const uint64_t desc_off = 64, l_off = 64 + static_cast<uint64_t>(n) * sizeof(sdb_send_desc);
+  const uint64_t pay_off = (l_off + n_list * sizeof(uint32_t) + 63) & ~63ull;
   if (pay_off + payload_bytes + 64 > wire_cap) return fail(h, SDB_ECAPACITY, "wire buffer too small (sdb_wire_bytes)");
   CUDA_TRY(h, cudaEventSynchronize(h->staging_free));
   sdb_wire_header* wh = reinterpret_cast<sdb_wire_header*>(h->wire_host);
   sdb_send_desc* wd = reinterpret_cast<sdb_send_desc*>(h->wire_host + 64);
   std::memset(wh, 0, sizeof(*wh));
-  uint64_t rec = 0; uint32_t max_padlen = 0;
+  uint64_t rec = 0; uint32_t max_padlen = 0, n_other = 0;
+  for (uint64_t k = 0; k < n_list; ++k) if (list_idx[k] >= h->cfg.max_agents) return fail(h, SDB_EINVAL, "recipient index out of range");
   for (uint32_t i = 0; i < n; ++i) {
     sdb_send_desc d; std::memset(&d, 0, sizeof(d));
-    const uint32_t g = group_idx[i];
-    if (g >= h->cfg.max_groups || !h->gdefined[g]) return fail(h, SDB_ENOTFOUND, "unknown group index");
+    const uint32_t k = kind ? kind[i] : 1u;
     if (sender[i] >= h->cfg.max_agents) return fail(h, SDB_EINVAL, "sender index out of range");
     if (len[i] > h->cfg.max_payload_bytes) return fail(h, SDB_EINVAL, "payload longer than max_payload_bytes");
     const uint64_t off = payload_off ? payload_off[i] : 0;
@@ -703,18 +718,51 @@ int sdb_export_group_batch(sdb_handle h, uint32_t n, const uint32_t* sender, con
     const uint32_t pl = pad32(len[i]);
     max_padlen = std::max(max_padlen, pl);
     d.payload_off = off; d.timestamp = timestamp ? timestamp[i] : 0.0;
-    d.sender = sender[i]; d.group = g; d.len = len[i]; d.prio = prio ? prio[i] : 1; d.type = type ? type[i] : 0;
+    d.sender = sender[i]; d.group = SDB_NO_GROUP; d.len = len[i]; d.prio = prio ? prio[i] : 1; d.type = type ? type[i] : 0;
     d.rgran = 1u + pl / SDB_GRANULE; d.rec0 = static_cast<uint32_t>(rec);
-    rec += h->gcount_full[g];
+    if (k == 1) {
+      const uint32_t g = target[i];
+      if (g >= h->cfg.max_groups || !h->gdefined[g]) return fail(h, SDB_ENOTFOUND, "unknown group index");
+      d.group = g; rec += h->gcount_full[g];
+    } else if (k == 0) {
+      if (target[i] >= h->cfg.max_agents) return fail(h, SDB_EINVAL, "receiver index out of range");
+      d.mstart = target[i]; d.mcount = 1; d.flags = SDB_DESC_P2P; rec += 1; ++n_other;
+    } else if (k == 2) {
+      if (target[i] >= n_lists) return fail(h, SDB_EINVAL, "list number out of range");
+      const uint64_t b = list_off[target[i]], e = list_off[target[i] + 1];
+      if (e < b || e > n_list) return fail(h, SDB_EINVAL, "bad list_off");
+      d.mstart = static_cast<uint32_t>(b); d.mcount = static_cast<uint32_t>(e - b); d.flags = SDB_DESC_LIST_TEMP; rec += 1; ++n_other;
+    } else return fail(h, SDB_EINVAL, "kind must be 0, 1 or 2");
     wd[i] = d;
   }
   wh->magic = SDB_WIRE_MAGIC; wh->n_sends = n; wh->total_recs = rec; wh->payload_bytes = payload_bytes;
-  wh->desc_off = desc_off; wh->payload_off = pay_off; wh->max_padlen = max_padlen;
+  wh->desc_off = desc_off; wh->payload_off = pay_off; wh->max_padlen = max_padlen; wh->n_other = n_other;
+  wh->list_off = l_off; wh->n_list = static_cast<uint32_t>(n_list);
   uint8_t* w = static_cast<uint8_t*>(wire_dev);
   CUDA_TRY(h, cudaMemcpyAsync(w, h->wire_host, 64 + static_cast<size_t>(n) * sizeof(sdb_send_desc), cudaMemcpyHostToDevice, h->stream));
+  if (n_list) {
+    std::memcpy(h->list_host, list_idx, n_list * sizeof(uint32_t));
+    CUDA_TRY(h, cudaMemcpyAsync(w + l_off, h->list_host, n_list * sizeof(uint32_t), cudaMemcpyHostToDevice, h->stream));
+  }
   if (payload_bytes) CUDA_TRY(h, cudaMemcpyAsync(w + pay_off, payload, payload_bytes, cudaMemcpyHostToDevice, h->stream));
   CUDA_TRY(h, cudaEventRecord(h->staging_free, h->stream));
   return SDB_OK;
+}
+
+int sdb_export_group_batch(sdb_handle h, uint32_t n, const uint32_t* sender, const uint32_t* group_idx, const uint8_t* prio,
+                           const uint8_t* type, const uint16_t* len, const uint64_t* payload_off, const uint8_t* payload,
+                           uint64_t payload_bytes, const double* timestamp, void* wire_dev, uint64_t wire_cap) {
+  return export_common(h, n, sender, nullptr, group_idx, 0, nullptr, nullptr, prio, type, len, payload_off, payload, payload_bytes,
+                       timestamp, wire_dev, wire_cap);
+}
+
+int sdb_export_mixed_batch(sdb_handle h, uint32_t n, const uint32_t* sender, const uint8_t* kind, const uint32_t* target,
+                           uint32_t n_lists, const uint64_t* list_off, const uint32_t* list_idx, const uint8_t* prio,
+                           const uint8_t* type, const uint16_t* len, const uint64_t* payload_off, const uint8_t* payload,
+                           uint64_t payload_bytes, const double* timestamp, void* wire_dev, uint64_t wire_cap) {
+  if (h && n && !kind) return fail(h, SDB_EINVAL, "null kind array");
+  return export_common(h, n, sender, kind, target, n_lists, list_off, list_idx, prio, type, len, payload_off, payload, payload_bytes,
+                       timestamp, wire_dev, wire_cap);
 }
 
 int sdb_import_wire_batches(sdb_handle h, uint32_t n_src, const void* wire_dev_all, uint64_t wire_stride, uint64_t* seq_base_out) {
@@ -737,32 +785,41 @@ int sdb_import_wire_batches(sdb_handle h, uint32_t n_src, const void* wire_dev_a
   a.lstart = h->lstart_dev; a.lcount = h->lcount_dev; a.max_groups = h->cfg.max_groups;
   a.w = h->xs_w; a.gs_cnt = h->xs_gs_cnt; a.descs = h->xs_descs; a.w_local = h->xs_w_local; a.w_tops = h->xs_w_tops;
   a.gs_off = h->xs_gs_off; a.gs_idx = h->xs_gs_idx;
+  a.shard_of = h->shard_of_dev; a.shard_id = h->cfg.shard_id; a.max_agents = h->cfg.max_agents;
+  a.lw = h->xs_lw; a.lw_local = h->xs_lw_local; a.lw_tops = h->xs_lw_tops;
+  a.tmp_list = h->scratch.list_dev; a.list_cap = static_cast<uint32_t>(std::min<uint64_t>(h->cfg.list_pool_entries, 0xFFFFFFFFull));
   int nl = 0;
   cudaError_t e = sdb_launch_import_measure(&a, n_cap, h->xs_w_local, h->xs_w_tops, h->xs_gs_local, h->xs_gs_tops,
-                                            h->xs_gs_off, h->rx_totals + 3, h->stream, &h->prof, &nl);
+                                            h->xs_gs_off, h->xs_lw_local, h->xs_lw_tops, h->rx_totals + 4, h->stream, &h->prof, &nl);
   if (e != cudaSuccess) return fail(h, SDB_ECUDA, std::string("import measure: ") + cudaGetErrorString(e));
   // the host needs the arena footprint and the sequence numbers consumed: one small sync
-  CUDA_TRY(h, cudaMemcpyAsync(h->totals_host + 3, h->rx_totals + 3, sizeof(unsigned long long), cudaMemcpyDeviceToHost, h->stream));
+  CUDA_TRY(h, cudaMemcpyAsync(h->totals_host + 4, h->rx_totals + 4, 2 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, h->stream));
   CUDA_TRY(h, cudaMemcpy2DAsync(h->hdrs_host, sizeof(sdb_wire_header), wire, wire_stride, sizeof(sdb_wire_header), n_src,
                                 cudaMemcpyDeviceToHost, h->stream));
   CUDA_TRY(h, cudaStreamSynchronize(h->stream));
-  uint64_t total_recs = 0; uint32_t max_padlen = 0;
+  uint64_t total_recs = 0, n_other = 0; uint32_t max_padlen = 0;
+  if (h->totals_host[5] > a.list_cap) return fail(h, SDB_ECAPACITY, "owned recipients of this import exceed list_pool_entries");
   for (uint32_t s = 0; s < n_src; ++s) {
     const sdb_wire_header& wh = h->hdrs_host[s];
+    n_other += wh.n_other;
     if (wh.magic != SDB_WIRE_MAGIC) return fail(h, SDB_EINVAL, "wire batch without magic (not exported by sdb_export_group_batch?)");
     if (wh.n_sends > h->cfg.max_batch_sends) return fail(h, SDB_ECAPACITY, "wire batch larger than max_batch_sends");
     total_recs += wh.total_recs; max_padlen = std::max(max_padlen, wh.max_padlen);
   }
-  const uint64_t total_grans = h->totals_host[3];
+  const uint64_t total_grans = h->totals_host[4];
   uint64_t base = 0;
   int rc = arena_reserve(h, total_grans, &base);
   if (rc != SDB_OK) return rc;
   e = sdb_launch_import_localize(&a, n_cap, h->xs_gs_cur, h->stream, &h->prof, &nl);
   if (e == cudaSuccess)
-    e = sdb_launch_fanout(&h->view, h->xs_descs, n_cap, wire, nullptr, h->next_seq, base, max_padlen, 2, h->sm_count, h->stream, &h->prof);
+    e = sdb_launch_fanout(&h->view, h->xs_descs, n_cap, wire, h->scratch.list_dev, h->next_seq, base, max_padlen, 2, h->sm_count, h->stream, &h->prof);
   if (e == cudaSuccess) {
     sdb_pull_view pv{h->memb_off_dev, h->memb_grp_dev, h->memb_pos_dev, h->xs_gs_off, h->xs_gs_idx};
-    e = sdb_launch_pull(&h->view, &pv, h->xs_descs, h->n_agents, base, 1, h->stream, &h->prof);
+    e = sdb_launch_pull(&h->view, &pv, h->xs_descs, h->n_agents, base, n_other ? 0 : 1, h->stream, &h->prof);
+  }
+  if (e == cudaSuccess && n_other) {     // p2p / broadcast copies claimed their slots with atomics: sort them into place
+    e = sdb_launch_commit(&h->view, h->n_agents, static_cast<uint32_t>(base), h->stream, &h->prof);
+    h->launches += 1;
   }
   h->launches += nl + 2;
   if (e != cudaSuccess) return fail(h, SDB_ECUDA, std::string("import launch: ") + cudaGetErrorString(e));

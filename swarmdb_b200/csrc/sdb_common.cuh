@@ -61,6 +61,7 @@ static_assert(sizeof(sdb_msg_header) == 32, "header must be 32 bytes");
 #define SDB_DESC_LIST_TEMP 4u     // mstart indexes the per-batch temporary list buffer
 #define SDB_DESC_PULL 8u          // ring entries are built by k_pull_index, not by the fan-out kernel
 #define SDB_DESC_POS 16u          // seq offset of member k is member_pos[mstart + k] (sharded: original group position)
+#define SDB_DESC_P2P 32u          // wire batches only: point-to-point send, mstart = receiver index
 
 // cross-shard wire batch (device memory, moved between ranks by the caller):
 //   [sdb_wire_header 64 B][n_sends x sdb_send_desc 64 B][payload bytes]
@@ -74,7 +75,10 @@ struct __align__(16) sdb_wire_header {
   uint64_t desc_off;       // byte offsets from the start of the wire batch
   uint64_t payload_off;
   uint32_t max_padlen;
-  uint32_t pad[5];
+  uint32_t n_other;        // sends that are not group sends (p2p / broadcast lists)
+  uint64_t list_off;       // recipient lists of broadcast sends (uint32 agent indices)
+  uint32_t n_list;
+  uint32_t pad;
 };
 static_assert(sizeof(sdb_wire_header) == 64, "wire header must be 64 bytes");
 #define SDB_WIRE_MAGIC 0x57424453u
@@ -156,6 +160,15 @@ struct sdb_import_args {
   const uint32_t* w_tops;
   const uint32_t* gs_off;     // [max_groups + 1] scan of the histogram
   uint32_t* gs_idx;           // [n_src * max_sends]
+  // point-to-point and broadcast sends: recipients this shard owns, compacted into a temporary list
+  const uint8_t* shard_of;    // [max_agents]
+  uint32_t shard_id;
+  uint32_t max_agents;
+  uint32_t* lw;               // [n_src * max_sends] owned recipients of each non-group send (scan input)
+  const uint32_t* lw_local;   // scan of lw
+  const uint32_t* lw_tops;
+  uint32_t* tmp_list;         // [list_cap]
+  uint32_t list_cap;
 };
 
 // ---- optional per-kernel timing with CUDA events on the launching stream (bench / roofline) ----

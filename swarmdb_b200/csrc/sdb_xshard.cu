@@ -39,18 +39,33 @@ __device__ __forceinline__ bool locate(const sdb_import_args& a, uint32_t gi, ui
   return false;
 }
 
+__device__ __forceinline__ const uint32_t* wire_list(const sdb_wire_header* h) {
+  return reinterpret_cast<const uint32_t*>(reinterpret_cast<const uint8_t*>(h) + h->list_off);
+}
+
 __global__ void __launch_bounds__(256)
 k_wire_measure(sdb_import_args a, uint32_t n_total) {
   const uint32_t gi = blockIdx.x * blockDim.x + threadIdx.x;
   if (gi >= n_total) return;
   uint32_t src, i; uint64_t rb;
-  if (!locate(a, gi, src, i, rb)) { a.w[gi] = 0; return; }
+  if (!locate(a, gi, src, i, rb)) { a.w[gi] = 0; a.lw[gi] = 0; return; }
   const sdb_wire_header* h = wire_hdr(a, src);
   const sdb_send_desc* d = reinterpret_cast<const sdb_send_desc*>(reinterpret_cast<const uint8_t*>(h) + h->desc_off) + i;
-  const uint32_t g = d->group;
-  const uint32_t lc = g < a.max_groups ? a.lcount[g] : 0u;
+  uint32_t lc = 0, own = 0;
+  if (d->flags & SDB_DESC_P2P) {                                   // delivered by the receiver's owner only
+    own = (d->mstart < a.max_agents && a.shard_of[d->mstart] == a.shard_id) ? 1u : 0u;
+    lc = own;
+  } else if (d->flags & SDB_DESC_LIST_TEMP) {                      // broadcast: the recipients this shard owns
+    const uint32_t* l = wire_list(h) + d->mstart;
+    for (uint32_t k = 0; k < d->mcount; ++k) { const uint32_t x = l[k]; own += (x < a.max_agents && a.shard_of[x] == a.shard_id); }
+    lc = own;
+  } else {
+    const uint32_t g = d->group;
+    lc = g < a.max_groups ? a.lcount[g] : 0u;
+    if (lc) atomicAdd(a.gs_cnt + g, 1u);
+  }
   a.w[gi] = lc * d->rgran;
-  if (lc) atomicAdd(a.gs_cnt + g, 1u);
+  a.lw[gi] = own;
 }
 
 __global__ void __launch_bounds__(256)
@@ -68,11 +83,29 @@ k_wire_localize(sdb_import_args a, uint32_t n_total, uint32_t* gs_cur) {
   const sdb_wire_header* h = wire_hdr(a, src);
   const sdb_send_desc* d = reinterpret_cast<const sdb_send_desc*>(reinterpret_cast<const uint8_t*>(h) + h->desc_off) + i;
   out = *d;
-  const uint32_t g = d->group;
-  const uint32_t lc = g < a.max_groups ? a.lcount[g] : 0u;
   out.payload_off = static_cast<uint64_t>(src) * a.stride + h->payload_off + d->payload_off;
   out.gran0 = a.w_local[gi] + a.w_tops[gi / SDB_SCAN_TILE];
   out.rec0 = static_cast<uint32_t>(rb + d->rec0);
+  if (d->flags & (SDB_DESC_P2P | SDB_DESC_LIST_TEMP)) {
+    const uint32_t own = a.lw[gi];
+    uint32_t lo = a.lw_local[gi] + a.lw_tops[gi / SDB_SCAN_TILE];
+    const bool fits = static_cast<uint64_t>(lo) + own <= a.list_cap;      // checked on the host before launch
+    out.mstart = lo; out.mcount = fits ? own : 0u; out.group = SDB_NO_GROUP;
+    if (d->flags & SDB_DESC_P2P) {
+      out.flags = SDB_DESC_LIST_TEMP;
+      if (own && fits) a.tmp_list[lo] = d->mstart;
+    } else {
+      out.flags = SDB_DESC_LIST_TEMP | SDB_DESC_SHARED_SEQ;
+      if (fits) {
+        const uint32_t* l = wire_list(h) + d->mstart;
+        for (uint32_t k = 0; k < d->mcount; ++k) { const uint32_t x = l[k]; if (x < a.max_agents && a.shard_of[x] == a.shard_id) a.tmp_list[lo++] = x; }
+      }
+    }
+    a.descs[gi] = out;
+    return;
+  }
+  const uint32_t g = d->group;
+  const uint32_t lc = g < a.max_groups ? a.lcount[g] : 0u;
   out.mstart = lc ? a.lstart[g] : 0u;
   out.mcount = lc;
   out.flags = SDB_DESC_SKIP_SENDER | SDB_DESC_PULL | SDB_DESC_POS;
@@ -103,15 +136,17 @@ extern "C" cudaError_t sdb_scan_u32(const uint32_t* in, uint32_t* local, uint32_
 // phase 1: measure + scans.  totals_dev[0] receives the arena granules this import will write.
 extern "C" cudaError_t sdb_launch_import_measure(const sdb_import_args* a, uint32_t n_cap, uint32_t* w_local,
                                                  uint32_t* w_tops, uint32_t* gs_local, uint32_t* gs_tops,
-                                                 uint32_t* gs_off_out, unsigned long long* totals_dev,
+                                                 uint32_t* gs_off_out, uint32_t* lw_local, uint32_t* lw_tops,
+                                                 unsigned long long* totals_dev,
                                                  cudaStream_t stream, sdb_profiler* prof, int* n_launches) {
   const int pi = sdb_prof_begin(prof, SDB_PK_XSHARD, stream);
   cudaMemsetAsync(a->gs_cnt, 0, (static_cast<size_t>(a->max_groups) + 1) * sizeof(uint32_t), stream);
   k_wire_measure<<<(n_cap + 255) / 256, 256, 0, stream>>>(*a, n_cap);
   cudaError_t e = sdb_scan_u32(a->w, w_local, w_tops, n_cap, totals_dev, nullptr, stream);
   if (e == cudaSuccess) e = sdb_scan_u32(a->gs_cnt, gs_local, gs_tops, a->max_groups + 1, nullptr, gs_off_out, stream);
+  if (e == cudaSuccess) e = sdb_scan_u32(a->lw, lw_local, lw_tops, n_cap, totals_dev + 1, nullptr, stream);   // owned recipients
   sdb_prof_end(prof, pi, stream);
-  if (n_launches) *n_launches += 6;
+  if (n_launches) *n_launches += 8;
   return e != cudaSuccess ? e : cudaGetLastError();
 }
 

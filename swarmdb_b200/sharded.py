@@ -65,6 +65,11 @@ class ShardExchange:
         self.shard.export_group_batch(sender, group, prio, typ, lens, payload_off, payload,
                                       self.backend.ptr(self.send_buf), self.wire_bytes, ts)
 
+    def export_mixed(self, sender, kind, target, list_off, list_idx, prio, typ, lens, payload_off, payload, ts=None) -> None:
+        """Mixed batch in call order: kind 0 = p2p (target receiver), 1 = group, 2 = broadcast list."""
+        self.shard.export_mixed_batch(sender, kind, target, list_off, list_idx, prio, typ, lens, payload_off, payload,
+                                      self.backend.ptr(self.send_buf), self.wire_bytes, ts)
+
     def exchange(self) -> None:
         if self.world > 1:
             self.backend.all_gather(self.recv_buf, self.send_buf)
@@ -114,7 +119,13 @@ def run_sharded_bench(args, rank: int, world: int, local_rank: int, wl):
     K, W = args.steps, args.warmup
     per_rank_msgs = wl.S * wl.F                     # routed messages each rank's sends produce
     recv_cap = per_rank_msgs * 2 + (1 << 16)        # a shard receives ~1/world of world x that, hash imbalance aside
-    shard = Shard(max_agents=wl.A, ring_slots=int(os.environ.get("SDB_RING_SLOTS", "64")), arena_bytes=1 << 33,
+    # every agent receives from the sends of ALL ranks: mean pending per step = world x 4.19, sized with headroom
+    mean_pending = world * wl.S * wl.F / wl.A
+    ring_slots = 64
+    while ring_slots < 3 * mean_pending + 32:
+        ring_slots *= 2
+    ring_slots = int(os.environ.get("SDB_RING_SLOTS", ring_slots))
+    shard = Shard(max_agents=wl.A, ring_slots=ring_slots, arena_bytes=1 << 33,
                   max_payload_bytes=wl.L, max_groups=1 << 14, member_pool_entries=wl.A + 1024, max_batch_sends=wl.S,
                   max_batch_payload=wl.S * wl.L, max_recv_records=recv_cap, max_recv_payload=recv_cap * wl.L,
                   device=local_rank, shard_id=rank, num_shards=world, fanout_variant=2)
@@ -144,11 +155,26 @@ def run_sharded_bench(args, rank: int, world: int, local_rank: int, wl):
             torch.cuda.synchronize()
             wires.append(ex.send_buf.clone())
 
-        def device_step(i):
+        phase_ev = []
+
+        def device_step(i, timed=False):
+            evs = [torch.cuda.Event(enable_timing=True) for _ in range(5)] if timed else None
+            if timed:
+                evs[0].record(stream)
             ex.send_buf.copy_(wires[i % n_distinct], non_blocking=True)       # HBM -> HBM staging of this step's input
+            if timed:
+                evs[1].record(stream)
             ex.exchange()
+            if timed:
+                evs[2].record(stream)
             ex.import_all()
-            _, total, _ = shard.receive_batch(local_agents, 100, 0, copy_out=False)
+            if timed:
+                evs[3].record(stream)
+            # non-local agents have empty rings on this shard: draining "all" needs no index upload
+            _, total, _ = shard.receive_batch(None, 100, 0, copy_out=False)
+            if timed:
+                evs[4].record(stream)
+                phase_ev.append(evs)
             return total
 
         for i in range(W):
@@ -162,13 +188,17 @@ def run_sharded_bench(args, rank: int, world: int, local_rank: int, wl):
         ev0.record(stream)
         delivered = 0
         for i in range(K):
-            delivered += device_step(W + i)
+            delivered += device_step(W + i, timed=True)
         ev1.record(stream)
         torch.cuda.synchronize(); dist.barrier()
         clk = clocks.stop()
         ms = ev0.elapsed_time(ev1)
         prof = shard.profile_read(); shard.profile(False)
-        launches = shard.stats()["kernel_launches"] - launches0
+        names = ["stage_input", "nccl_all_gather", "import", "receive"]
+        phases = {n: float(np.mean([e[k].elapsed_time(e[k + 1]) for e in phase_ev])) for k, n in enumerate(names)}
+        st_end = shard.stats()
+        launches = st_end["kernel_launches"] - launches0
+        assert st_end["ring_overflow"] == 0, f"ring overflow on rank {rank}: {st_end['ring_overflow']} records (ring_slots={ring_slots})"
 
         # ---- e2e: host buffers in (export H2D), results out (D2H into pinned buffers)
         pin_hdr = torch.empty(recv_cap * 32, dtype=torch.uint8, pin_memory=True).numpy().view(HDR_DTYPE)
@@ -181,7 +211,7 @@ def run_sharded_bench(args, rank: int, world: int, local_rank: int, wl):
 
         def e2e_step(i):
             ex.step(*pinned[i % n_distinct])
-            _, hdr, _ = shard.receive_batch(local_agents, 100, 0, copy_out=True, out_hdr=pin_hdr, out_payload=pin_pay)
+            _, hdr, _ = shard.receive_batch(None, 100, 0, copy_out=True, out_hdr=pin_hdr, out_payload=pin_pay)
             return len(hdr)
 
         e2e_step(0); e2e_step(1)
@@ -214,7 +244,7 @@ def run_sharded_bench(args, rank: int, world: int, local_rank: int, wl):
                                    f"hash-sharded (fnv1a64 % {world}) over {world} GPUs; every rank ingests 65536 group "
                                    f"sends/step, wire batches all-gathered over NCCL/NVLink, each shard drains its agents",
                        "l2": "inputs larger than L2 (each shard writes and reads back ~1.2 GB of records per step)",
-                       "parallelism": f"shard{world}"},
+                       "parallelism": f"shard{world}", "ring_slots": ring_slots},
             "clocks": clk,
             "e2e": {"value": total_got / (e2e_max * 1e-3), "unit": "messages/s",
                     "h2d_bytes_per_step": (wl.S * wl.L + wl.S * 64) * world,
@@ -226,6 +256,7 @@ def run_sharded_bench(args, rank: int, world: int, local_rank: int, wl):
                          "algorithmic_bytes_per_msg": ALG_BYTES_FANOUT, "msgs_per_launch": local_msgs,
                          "ms_per_launch": fan_avg, "note": "rank 0's shard; per-send local fan-out is world-times narrower"},
             "kernels": {k: {"ms_per_launch": v[0] / v[1], "launches": v[1]} for k, v in prof.items() if v[1]},
+            "phases_ms_rank0": phases,
             "cpu_baseline": None,
         }
         print(json.dumps(line), flush=True)
