@@ -246,6 +246,16 @@ int sdb_export_mixed_batch(sdb_handle h, uint32_t n,
                            const double* timestamp, void* wire_dev, uint64_t wire_cap);
 int sdb_import_wire_batches(sdb_handle h, uint32_t n_src, const void* wire_dev_all, uint64_t wire_stride,
                             uint64_t* seq_base_out);
+/* Peer-memory transport (no collective): each rank exports into a buffer allocated with
+ * sdb_wire_alloc, hands the 64-byte CUDA-IPC handle to the other ranks (any side channel), which
+ * map it with sdb_wire_open; after a cross-rank barrier every rank imports from the table of
+ * pointers (its own buffer + the mapped peer buffers, rank order).  The import kernels and the
+ * fan-out kernel's TMA loads then read descriptors and payloads directly out of the exporting
+ * GPU's memory over NVLink, overlapped with the fan-out itself. */
+int sdb_wire_alloc(sdb_handle h, uint64_t bytes, void** dev_out, void* ipc_handle_out /* 64 bytes, nullable */);
+int sdb_wire_open(sdb_handle h, const void* ipc_handle, void** dev_out);
+int sdb_wire_close(sdb_handle h, void* dev, int opened /* 1: from sdb_wire_open, 0: from sdb_wire_alloc */);
+int sdb_import_wire_ptrs(sdb_handle h, uint32_t n_src, const void* const* wire_ptrs, uint64_t* seq_base_out);
 
 /* ---- LLM backend balancer: set_llm_load_balancing / assign_llm_backend / get_llm_backend
  * (M:1281-1325).  The reference stores a flag and a dict and has NO pick algorithm

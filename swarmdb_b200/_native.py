@@ -56,7 +56,8 @@ EXPORTS = ["sdb_abi_version", "sdb_create", "sdb_destroy", "sdb_set_stream", "sd
            "sdb_get_stats", "sdb_profile", "sdb_profile_read", "sdb_register_agents", "sdb_deregister_agents", "sdb_create_group", "sdb_send_batch",
            "sdb_send_group_batch", "sdb_send_list_batch", "sdb_send_mixed_batch", "sdb_stage_batch", "sdb_submit_staged", "sdb_free_staged",
            "sdb_receive_batch", "sdb_last_receive_dev", "sdb_wire_bytes", "sdb_set_agent_shards",
-           "sdb_export_group_batch", "sdb_export_mixed_batch", "sdb_import_wire_batches", "sdb_set_backends", "sdb_get_backend_loads",
+           "sdb_export_group_batch", "sdb_export_mixed_batch", "sdb_import_wire_batches", "sdb_wire_alloc", "sdb_wire_open",
+           "sdb_wire_close", "sdb_import_wire_ptrs", "sdb_set_backends", "sdb_get_backend_loads",
            "sdb_release_backends", "sdb_select_backend_batch"]
 
 _lib = None
@@ -101,6 +102,10 @@ def load_library() -> C.CDLL:
     L.sdb_export_group_batch.restype = i32; L.sdb_export_group_batch.argtypes = [vp, u32] + [vp] * 7 + [u64, vp, vp, u64]
     L.sdb_export_mixed_batch.restype = i32
     L.sdb_export_mixed_batch.argtypes = [vp, u32, vp, vp, vp, u32] + [vp] * 7 + [u64, vp, vp, u64]
+    L.sdb_wire_alloc.restype = i32; L.sdb_wire_alloc.argtypes = [vp, u64, C.POINTER(vp), vp]
+    L.sdb_wire_open.restype = i32; L.sdb_wire_open.argtypes = [vp, vp, C.POINTER(vp)]
+    L.sdb_wire_close.restype = i32; L.sdb_wire_close.argtypes = [vp, vp, i32]
+    L.sdb_import_wire_ptrs.restype = i32; L.sdb_import_wire_ptrs.argtypes = [vp, u32, vp, vp]
     L.sdb_import_wire_batches.restype = i32; L.sdb_import_wire_batches.argtypes = [vp, u32, vp, u64, vp]
     L.sdb_set_backends.restype = i32; L.sdb_set_backends.argtypes = [vp, u32, vp, vp]
     L.sdb_get_backend_loads.restype = i32; L.sdb_get_backend_loads.argtypes = [vp, u32, vp]
@@ -316,6 +321,29 @@ class Shard:
         self._check(self._L.sdb_export_mixed_batch(self._h, len(s), _p(s), _p(k), _p(t), len(lo) - 1, _p(lo), _p(li),
                                                    _p(prio), _p(typ), _p(lens), _p(po), _p(pl), pl.nbytes, _p(ts),
                                                    C.c_void_p(wire_dev), wire_cap))
+
+    def wire_alloc(self, nbytes: int):
+        """Device export buffer + its 64-byte CUDA-IPC handle (bytes) for the peer-memory transport."""
+        dev = C.c_void_p()
+        handle = C.create_string_buffer(64)
+        self._check(self._L.sdb_wire_alloc(self._h, nbytes, C.byref(dev), C.cast(handle, C.c_void_p)))
+        return dev.value, handle.raw
+
+    def wire_open(self, ipc_handle: bytes) -> int:
+        dev = C.c_void_p()
+        buf = C.create_string_buffer(ipc_handle, 64)
+        self._check(self._L.sdb_wire_open(self._h, C.cast(buf, C.c_void_p), C.byref(dev)))
+        return dev.value
+
+    def wire_close(self, dev: int, opened: bool) -> None:
+        self._check(self._L.sdb_wire_close(self._h, C.c_void_p(dev), 1 if opened else 0))
+
+    def import_wire_ptrs(self, ptrs) -> int:
+        """Import one wire batch per source rank from a table of device pointers (rank order)."""
+        arr = (C.c_void_p * len(ptrs))(*[C.c_void_p(int(x)) for x in ptrs])
+        base = C.c_uint64(0)
+        self._check(self._L.sdb_import_wire_ptrs(self._h, len(ptrs), C.cast(arr, C.c_void_p), C.cast(C.byref(base), C.c_void_p)))
+        return base.value
 
     def import_wire_batches(self, n_src: int, wire_dev_all: int, stride: int) -> int:
         """Expand the wire batches of `n_src` ranks (rank order, `stride` bytes apart) for the agents this shard owns."""

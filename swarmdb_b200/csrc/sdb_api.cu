@@ -765,11 +765,48 @@ int sdb_export_mixed_batch(sdb_handle h, uint32_t n, const uint32_t* sender, con
                        timestamp, wire_dev, wire_cap);
 }
 
+// ---- peer-memory transport: export buffers that other ranks map with CUDA IPC ---------------------
+int sdb_wire_alloc(sdb_handle h, uint64_t bytes, void** dev_out, void* ipc_handle_out) {
+  if (!h || !dev_out || bytes == 0) return SDB_EINVAL;
+  void* p = nullptr;
+  CUDA_TRY(h, cudaMalloc(&p, bytes));
+  CUDA_TRY(h, cudaMemset(p, 0, bytes));
+  if (ipc_handle_out) {
+    cudaIpcMemHandle_t hd;
+    CUDA_TRY(h, cudaIpcGetMemHandle(&hd, p));
+    static_assert(sizeof(hd) == 64, "cudaIpcMemHandle_t is 64 bytes");
+    std::memcpy(ipc_handle_out, &hd, sizeof(hd));
+  }
+  *dev_out = p;
+  return SDB_OK;
+}
+
+int sdb_wire_open(sdb_handle h, const void* ipc_handle, void** dev_out) {
+  if (!h || !ipc_handle || !dev_out) return SDB_EINVAL;
+  cudaIpcMemHandle_t hd;
+  std::memcpy(&hd, ipc_handle, sizeof(hd));
+  CUDA_TRY(h, cudaIpcOpenMemHandle(dev_out, hd, cudaIpcMemLazyEnablePeerAccess));
+  return SDB_OK;
+}
+
+int sdb_wire_close(sdb_handle h, void* dev, int opened) {
+  if (!h || !dev) return SDB_EINVAL;
+  CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+  if (opened) CUDA_TRY(h, cudaIpcCloseMemHandle(dev)); else CUDA_TRY(h, cudaFree(dev));
+  return SDB_OK;
+}
+
 int sdb_import_wire_batches(sdb_handle h, uint32_t n_src, const void* wire_dev_all, uint64_t wire_stride, uint64_t* seq_base_out) {
-  if (!h || !wire_dev_all || n_src == 0) return SDB_EINVAL;
+  if (!h || !wire_dev_all || n_src == 0 || n_src > SDB_MAX_SRC) return SDB_EINVAL;
+  const void* ptrs[SDB_MAX_SRC];
+  for (uint32_t s = 0; s < n_src; ++s) ptrs[s] = static_cast<const uint8_t*>(wire_dev_all) + static_cast<uint64_t>(s) * wire_stride;
+  return sdb_import_wire_ptrs(h, n_src, ptrs, seq_base_out);
+}
+
+int sdb_import_wire_ptrs(sdb_handle h, uint32_t n_src, const void* const* wire_ptrs, uint64_t* seq_base_out) {
+  if (!h || !wire_ptrs || n_src == 0) return SDB_EINVAL;
   if (seq_base_out) *seq_base_out = h->next_seq;
-  if (n_src > h->cfg.num_shards) return fail(h, SDB_EINVAL, "n_src > num_shards");
-  const uint8_t* wire = static_cast<const uint8_t*>(wire_dev_all);
+  if (n_src > h->cfg.num_shards || n_src > SDB_MAX_SRC) return fail(h, SDB_EINVAL, "n_src > num_shards (or > 16)");
   if (h->ltab_dirty) {      // device copy of the local group table (start, count per group)
     CUDA_TRY(h, cudaStreamSynchronize(h->stream));
     std::vector<uint32_t> st(h->cfg.max_groups), ct(h->cfg.max_groups);
@@ -781,7 +818,11 @@ int sdb_import_wire_batches(sdb_handle h, uint32_t n_src, const void* wire_dev_a
   if (h->memb_dirty) { int rc0 = rebuild_inverse(h); if (rc0 != SDB_OK) return rc0; }
   const uint32_t n_cap = n_src * h->cfg.max_batch_sends;
   sdb_import_args a{};
-  a.wire = wire; a.stride = wire_stride; a.n_src = n_src; a.max_sends = h->cfg.max_batch_sends;
+  for (uint32_t k = 0; k < n_src; ++k) {
+    if (!wire_ptrs[k]) return fail(h, SDB_EINVAL, "null wire pointer");
+    a.wire[k] = static_cast<const uint8_t*>(wire_ptrs[k]);
+  }
+  a.n_src = n_src; a.max_sends = h->cfg.max_batch_sends;
   a.lstart = h->lstart_dev; a.lcount = h->lcount_dev; a.max_groups = h->cfg.max_groups;
   a.w = h->xs_w; a.gs_cnt = h->xs_gs_cnt; a.descs = h->xs_descs; a.w_local = h->xs_w_local; a.w_tops = h->xs_w_tops;
   a.gs_off = h->xs_gs_off; a.gs_idx = h->xs_gs_idx;
@@ -794,8 +835,8 @@ int sdb_import_wire_batches(sdb_handle h, uint32_t n_src, const void* wire_dev_a
   if (e != cudaSuccess) return fail(h, SDB_ECUDA, std::string("import measure: ") + cudaGetErrorString(e));
   // the host needs the arena footprint and the sequence numbers consumed: one small sync
   CUDA_TRY(h, cudaMemcpyAsync(h->totals_host + 4, h->rx_totals + 4, 2 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, h->stream));
-  CUDA_TRY(h, cudaMemcpy2DAsync(h->hdrs_host, sizeof(sdb_wire_header), wire, wire_stride, sizeof(sdb_wire_header), n_src,
-                                cudaMemcpyDeviceToHost, h->stream));
+  for (uint32_t k = 0; k < n_src; ++k)
+    CUDA_TRY(h, cudaMemcpyAsync(h->hdrs_host + k, wire_ptrs[k], sizeof(sdb_wire_header), cudaMemcpyDeviceToHost, h->stream));
   CUDA_TRY(h, cudaStreamSynchronize(h->stream));
   uint64_t total_recs = 0, n_other = 0; uint32_t max_padlen = 0;
   if (h->totals_host[5] > a.list_cap) return fail(h, SDB_ECAPACITY, "owned recipients of this import exceed list_pool_entries");
@@ -812,7 +853,7 @@ int sdb_import_wire_batches(sdb_handle h, uint32_t n_src, const void* wire_dev_a
   if (rc != SDB_OK) return rc;
   e = sdb_launch_import_localize(&a, n_cap, h->xs_gs_cur, h->stream, &h->prof, &nl);
   if (e == cudaSuccess)
-    e = sdb_launch_fanout(&h->view, h->xs_descs, n_cap, wire, h->scratch.list_dev, h->next_seq, base, max_padlen, 2, h->sm_count, h->stream, &h->prof);
+    e = sdb_launch_fanout(&h->view, h->xs_descs, n_cap, nullptr, h->scratch.list_dev, h->next_seq, base, max_padlen, 2, h->sm_count, h->stream, &h->prof);
   if (e == cudaSuccess) {
     sdb_pull_view pv{h->memb_off_dev, h->memb_grp_dev, h->memb_pos_dev, h->xs_gs_off, h->xs_gs_idx};
     e = sdb_launch_pull(&h->view, &pv, h->xs_descs, h->n_agents, base, n_other ? 0 : 1, h->stream, &h->prof);

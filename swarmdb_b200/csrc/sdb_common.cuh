@@ -144,9 +144,9 @@ struct sdb_recv_args {
 };
 
 // arguments of one cross-shard import (sdb_xshard.cu)
+#define SDB_MAX_SRC 16
 struct sdb_import_args {
-  const uint8_t* wire;        // n_src wire batches, `stride` bytes apart
-  uint64_t stride;
+  const uint8_t* wire[SDB_MAX_SRC];   // one wire batch per source rank; may point into PEER GPU memory (NVLink)
   uint32_t n_src;
   uint32_t max_sends;         // capacity per wire batch
   const uint32_t* lstart;     // [max_groups] local member list of each group

@@ -226,27 +226,45 @@ __global__ void __launch_bounds__(WARPS * 32)
 k_group_fanout_warp(sdb_dev_view v, const sdb_send_desc* __restrict__ descs, uint32_t n,
                     const uint8_t* __restrict__ payload, const uint32_t* __restrict__ tmp_list,
                     uint64_t seq_base, uint64_t arena_base, uint32_t stage_bytes) {
-  extern __shared__ __align__(128) uint8_t s_stage[];      // WARPS stages of stage_bytes
-  __shared__ __align__(8) uint64_t s_bar[WARPS];
+  extern __shared__ __align__(128) uint8_t s_stage[];      // WARPS x 2 stages of stage_bytes
+  __shared__ __align__(8) uint64_t s_bar[WARPS][2];
   const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  uint8_t* my = s_stage + warp * stage_bytes;
-  const uint4* my4 = reinterpret_cast<const uint4*>(my);
-  if (lane == 0) { sdb_mbar_init(&s_bar[warp], 1); sdb_fence_barrier_init(); }
+  uint8_t* const my_base = s_stage + static_cast<size_t>(warp) * 2u * stage_bytes;
+  if (lane == 0) { sdb_mbar_init(&s_bar[warp][0], 1); sdb_mbar_init(&s_bar[warp][1], 1); sdb_fence_barrier_init(); }
   __syncwarp();
-  uint32_t phase = 0;
+  uint32_t phase0 = 0, phase1 = 0;
   uint32_t n_enq = 0, n_ovf = 0, n_skip = 0;
   const uint32_t gw = blockIdx.x * WARPS + warp, nw = gridDim.x * WARPS;
   const uint64_t pol_stream = sdb_policy_evict_first();
 
-  for (uint32_t i = gw; i < n; i += nw) {
-    const sdb_send_desc d = load_desc(descs + i);
-    if (d.mcount == 0) continue;
+  // two-stage software pipeline per warp: while send i is being written out, the descriptor of
+  // send i + nw is already loaded and its payload is in flight (TMA) into the other stage - the
+  // payload may live in a peer GPU's memory (cross-shard import reads it over NVLink)
+  uint32_t i = gw, st = 0;
+  bool have = i < n;
+  sdb_send_desc d;
+  if (have) {
+    d = load_desc(descs + i);
+    const uint32_t pl = (d.rgran - 1u) * SDB_GRANULE;
+    if (lane == 0 && d.mcount && pl) { sdb_mbar_expect_tx(&s_bar[warp][0], pl); sdb_tma_load(my_base, payload + d.payload_off, pl, &s_bar[warp][0]); }
+  }
+  while (have) {
+    const uint32_t inext = i + nw;
+    const bool have_next = inext < n;
+    sdb_send_desc dn;
+    if (have_next) {
+      dn = load_desc(descs + inext);
+      const uint32_t pl = (dn.rgran - 1u) * SDB_GRANULE;
+      if (lane == 0 && dn.mcount && pl) {
+        uint8_t* dst = my_base + (st ^ 1u) * stage_bytes;
+        sdb_mbar_expect_tx(&s_bar[warp][st ^ 1u], pl);
+        sdb_tma_load(dst, payload + dn.payload_off, pl, &s_bar[warp][st ^ 1u]);
+      }
+    }
+    uint8_t* const my = my_base + st * stage_bytes;
+    const uint4* const my4 = reinterpret_cast<const uint4*>(my);
     const uint32_t padlen = (d.rgran - 1u) * SDB_GRANULE;
     const uint32_t P = padlen >> 4;                        // 16-byte chunks per payload
-    if (lane == 0 && padlen) {
-      sdb_mbar_expect_tx(&s_bar[warp], padlen);
-      sdb_tma_load(my, payload + d.payload_off, padlen, &s_bar[warp]);
-    }
     const uint32_t* mem = (d.flags & SDB_DESC_LIST_TEMP) ? tmp_list + d.mstart : v.members + d.mstart;
     const uint16_t meta = static_cast<uint16_t>((static_cast<uint32_t>(d.prio) << 14) | d.rgran);
     const uint64_t apos0 = arena_base + d.gran0;
@@ -275,8 +293,8 @@ k_group_fanout_warp(sdb_dev_view v, const sdb_send_desc* __restrict__ descs, uin
       }
       const uint32_t m0 = __ballot_sync(0xFFFFFFFFu, d0), m1 = __ballot_sync(0xFFFFFFFFu, d1);
       if (tile == 0 && padlen) {
-        sdb_mbar_wait(&s_bar[warp], phase);
-        phase ^= 1;
+        sdb_mbar_wait(&s_bar[warp][st], st ? phase1 : phase0);
+        if (st) phase1 ^= 1; else phase0 ^= 1;
         if (d.len + lane < padlen) my[d.len + lane] = 0;   // deterministic pad bytes
         __syncwarp();
       }
@@ -307,6 +325,7 @@ k_group_fanout_warp(sdb_dev_view v, const sdb_send_desc* __restrict__ descs, uin
       }
       __syncwarp();
     }
+    d = dn; i = inext; have = have_next; st ^= 1u;
   }
   for (int o = 16; o; o >>= 1) {
     n_enq += __shfl_xor_sync(0xFFFFFFFFu, n_enq, o);
@@ -562,10 +581,10 @@ extern "C" cudaError_t sdb_launch_fanout(const sdb_dev_view* v, const sdb_send_d
   if (variant == 2 && max_padlen <= 4096) {
     constexpr int WARPS = 4;
     const uint32_t stage = ((max_padlen ? max_padlen : 16) + 127u) & ~127u;
-    const size_t smem = static_cast<size_t>(WARPS) * stage;
+    const size_t smem = static_cast<size_t>(WARPS) * 2 * stage;
     static bool attr_set = false;
     if (!attr_set) {
-      cudaFuncSetAttribute(k_group_fanout_warp<WARPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, 4 * 4096 + 512);
+      cudaFuncSetAttribute(k_group_fanout_warp<WARPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * 4 * 4096 + 512);
       attr_set = true;
     }
     uint32_t per_sm = 16;

@@ -16,14 +16,18 @@
 //   then the ordinary fan-out kernel + pull index build run over the localized descriptors.
 //
 // NVLink carries (64 + payload) bytes per (send, peer) instead of (32 + payload) per recipient:
-// 8 x less for 64-way groups on 8 shards.
+// 8 x less for 64-way groups on 8 shards.  With the peer-memory transport (sdb_import_wire_ptrs over
+// CUDA-IPC mapped export buffers) there is no separate collective at all: these kernels read the
+// descriptors, and the fan-out kernel's TMA bulk loads read the payloads, straight out of the
+// exporting GPU's memory, so the NVLink transfer overlaps the fan-out send by send and a shard only
+// pulls the sends it has recipients for.
 #include "sdb_common.cuh"
 
 #define SDB_SCAN_TILE 4096u
 
 
 __device__ __forceinline__ const sdb_wire_header* wire_hdr(const sdb_import_args& a, uint32_t src) {
-  return reinterpret_cast<const sdb_wire_header*>(a.wire + static_cast<uint64_t>(src) * a.stride);
+  return reinterpret_cast<const sdb_wire_header*>(a.wire[src]);
 }
 
 // global send index -> (source, index inside the source), sources concatenated in rank order
@@ -83,7 +87,9 @@ k_wire_localize(sdb_import_args a, uint32_t n_total, uint32_t* gs_cur) {
   const sdb_wire_header* h = wire_hdr(a, src);
   const sdb_send_desc* d = reinterpret_cast<const sdb_send_desc*>(reinterpret_cast<const uint8_t*>(h) + h->desc_off) + i;
   out = *d;
-  out.payload_off = static_cast<uint64_t>(src) * a.stride + h->payload_off + d->payload_off;
+  // absolute address (the fan-out kernel is launched with a null payload base): the payload stays where the
+  // source rank exported it - possibly in a peer GPU's memory - and is pulled by the fan-out's TMA loads
+  out.payload_off = reinterpret_cast<uint64_t>(a.wire[src]) + h->payload_off + d->payload_off;
   out.gran0 = a.w_local[gi] + a.w_tops[gi / SDB_SCAN_TILE];
   out.rec0 = static_cast<uint32_t>(rb + d->rec0);
   if (d->flags & (SDB_DESC_P2P | SDB_DESC_LIST_TEMP)) {

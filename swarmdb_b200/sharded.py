@@ -83,6 +83,72 @@ class ShardExchange:
         return self.import_all()
 
 
+class PeerExchange:
+    """Peer-memory transport: no collective moves message bytes.
+
+    Every rank exports into its own CUDA-IPC-shared buffer (two of them, alternating per step);
+    `exchange()` is a one-element all-reduce used purely as a stream-ordered cross-rank barrier;
+    `import_all()` hands the shard the table of peer pointers, and the import + fan-out kernels
+    pull descriptors and payloads straight out of the exporting GPUs' memory over NVLink.
+    """
+
+    def __init__(self, shard, rank: int, world: int, max_sends: int, max_payload: int, device):
+        import torch
+        import torch.distributed as dist
+        self.shard, self.rank, self.world = shard, rank, world
+        self.wire_bytes = shard.wire_bytes(max_sends, max_payload)
+        self.mine = [shard.wire_alloc(self.wire_bytes) for _ in range(2)]          # (ptr, ipc handle)
+        handles = [None] * world
+        if world > 1:
+            dist.all_gather_object(handles, [h for _, h in self.mine])
+        self.ptrs = [[0] * world for _ in range(2)]
+        self.opened = []
+        for b in range(2):
+            for r in range(world):
+                if r == rank:
+                    self.ptrs[b][r] = self.mine[b][0]
+                else:
+                    p = shard.wire_open(handles[r][b])
+                    self.ptrs[b][r] = p
+                    self.opened.append(p)
+        self.flag = torch.zeros(1, device=device)
+        self.step_no = 0
+
+    @property
+    def cur(self) -> int:
+        return self.step_no & 1
+
+    def export(self, sender, group, prio, typ, lens, payload_off, payload, ts=None) -> None:
+        self.shard.export_group_batch(sender, group, prio, typ, lens, payload_off, payload,
+                                      self.mine[self.cur][0], self.wire_bytes, ts)
+
+    def export_mixed(self, sender, kind, target, list_off, list_idx, prio, typ, lens, payload_off, payload, ts=None) -> None:
+        self.shard.export_mixed_batch(sender, kind, target, list_off, list_idx, prio, typ, lens, payload_off, payload,
+                                      self.mine[self.cur][0], self.wire_bytes, ts)
+
+    def exchange(self) -> None:
+        if self.world > 1:
+            import torch.distributed as dist
+            dist.all_reduce(self.flag)                     # stream-ordered barrier: every rank's export is complete
+
+    def import_all(self) -> int:
+        base = self.shard.import_wire_ptrs(self.ptrs[self.cur])
+        self.step_no += 1                                   # the other buffer is free: its readers passed the barrier above
+        return base
+
+    def step(self, *batch, ts=None) -> int:
+        self.export(*batch, ts=ts)
+        self.exchange()
+        return self.import_all()
+
+    def close(self) -> None:
+        for p in self.opened:
+            self.shard.wire_close(p, True)
+        for p, _ in self.mine:
+            self.shard.wire_close(p, False)
+        self.opened, self.mine = [], []
+
+
 class TorchCudaBackend:
     """Wire buffers in CUDA memory, exchanged with NCCL (torch.distributed), on torch's current stream."""
 
@@ -137,8 +203,12 @@ def run_sharded_bench(args, rank: int, world: int, local_rank: int, wl):
     for g in range(wl.G):
         shard.create_group(g, wl.members(g))
     shard.sync()
+    transport = os.environ.get("SDB_XSHARD", "peer")
     with torch.cuda.stream(stream):
-        ex = ShardExchange(shard, rank, world, wl.S, wl.S * wl.L, TorchCudaBackend(dev))
+        if transport == "peer":
+            ex = PeerExchange(shard, rank, world, wl.S, wl.S * wl.L, dev)
+        else:
+            ex = ShardExchange(shard, rank, world, wl.S, wl.S * wl.L, TorchCudaBackend(dev))
         # each rank draws its own slice of the global batch: advance the generators by rank
         for _ in range(rank):
             wl.batch()
@@ -150,10 +220,17 @@ def run_sharded_bench(args, rank: int, world: int, local_rank: int, wl):
                 wl.batch()
         # device-resident inputs: wire batches exported once, before the timed region
         wires = []
-        for b in batches:
-            ex.export(*b)
-            torch.cuda.synchronize()
-            wires.append(ex.send_buf.clone())
+        if transport == "peer":
+            for k, b in enumerate(batches):                 # batch k lives in this rank's export buffer k
+                ex.step_no = k
+                ex.export(*b)
+            ex.step_no = 0
+            torch.cuda.synchronize(); dist.barrier()
+        else:
+            for b in batches:
+                ex.export(*b)
+                torch.cuda.synchronize()
+                wires.append(ex.send_buf.clone())
 
         phase_ev = []
 
@@ -161,7 +238,8 @@ def run_sharded_bench(args, rank: int, world: int, local_rank: int, wl):
             evs = [torch.cuda.Event(enable_timing=True) for _ in range(5)] if timed else None
             if timed:
                 evs[0].record(stream)
-            ex.send_buf.copy_(wires[i % n_distinct], non_blocking=True)       # HBM -> HBM staging of this step's input
+            if transport != "peer":
+                ex.send_buf.copy_(wires[i % n_distinct], non_blocking=True)   # HBM -> HBM staging of this step's input
             if timed:
                 evs[1].record(stream)
             ex.exchange()
@@ -194,7 +272,7 @@ def run_sharded_bench(args, rank: int, world: int, local_rank: int, wl):
         clk = clocks.stop()
         ms = ev0.elapsed_time(ev1)
         prof = shard.profile_read(); shard.profile(False)
-        names = ["stage_input", "nccl_all_gather", "import", "receive"]
+        names = ["stage_input", "exchange", "import", "receive"]
         phases = {n: float(np.mean([e[k].elapsed_time(e[k + 1]) for e in phase_ev])) for k, n in enumerate(names)}
         st_end = shard.stats()
         launches = st_end["kernel_launches"] - launches0
@@ -242,7 +320,11 @@ def run_sharded_bench(args, rank: int, world: int, local_rank: int, wl):
             "dtype": "u8", "data": "synthetic",
             "config": {"workload": f"c3: c2's workload (1M agents, 15625 groups x 64, 256-byte payloads) with agents "
                                    f"hash-sharded (fnv1a64 % {world}) over {world} GPUs; every rank ingests 65536 group "
-                                   f"sends/step, wire batches all-gathered over NCCL/NVLink, each shard drains its agents",
+                                   f"sends/step; " + ("peer-memory transport: import/fan-out kernels pull descriptors and "
+                                   "payloads from the exporting GPUs over NVLink (one-element all-reduce as barrier)"
+                                   if transport == "peer" else "wire batches all-gathered over NCCL/NVLink") +
+                                   "; each shard drains its agents",
+                       "transport": transport,
                        "l2": "inputs larger than L2 (each shard writes and reads back ~1.2 GB of records per step)",
                        "parallelism": f"shard{world}", "ring_slots": ring_slots},
             "clocks": clk,
@@ -260,5 +342,8 @@ def run_sharded_bench(args, rank: int, world: int, local_rank: int, wl):
             "cpu_baseline": None,
         }
         print(json.dumps(line), flush=True)
+    if transport == "peer":
+        torch.cuda.synchronize(); dist.barrier()
+        ex.close()
     shard.close()
     dist.destroy_process_group()

@@ -67,7 +67,11 @@ def test_sharded_streams_equal_single_shard(world):
                                          wire.data_ptr() + r * wire_bytes, wire_bytes, ts)
             shards[r].sync()
             oracle.send_group_batch(sender, grp, prio, typ, lens, off, buf, ts)
-        bases = [s.import_wire_batches(world, wire.data_ptr(), wire_bytes) for s in shards]
+        if step == 1:                                      # pointer-table import (what the peer-memory transport uses)
+            ptrs = [wire.data_ptr() + r * wire_bytes for r in range(world)]
+            bases = [s.import_wire_ptrs(ptrs) for s in shards]
+        else:
+            bases = [s.import_wire_batches(world, wire.data_ptr(), wire_bytes) for s in shards]
         assert len(set(bases)) == 1                        # every shard agrees on the global sequence base
         k = [3, 1000, 1000][step]
         merged = {}
