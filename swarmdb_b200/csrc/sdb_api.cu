@@ -93,6 +93,7 @@ struct sdb_ctx {
   uint32_t* xs_gs_cnt = nullptr; uint32_t* xs_gs_local = nullptr; uint32_t* xs_gs_tops = nullptr; uint32_t* xs_gs_cur = nullptr;
   uint32_t* xs_gs_off = nullptr; uint32_t* xs_gs_idx = nullptr; sdb_send_desc* xs_descs = nullptr;
   uint32_t* xs_lw = nullptr; uint32_t* xs_lw_local = nullptr; uint32_t* xs_lw_tops = nullptr;
+  sdb_src_tab* xs_tab = nullptr;
   uint8_t* shard_of_dev = nullptr;
   uint8_t* wire_host = nullptr;                // pinned: header + descriptors of an export
   sdb_wire_header* hdrs_host = nullptr;        // pinned [num_shards]
@@ -493,6 +494,7 @@ int sdb_create(const sdb_config* cfg, sdb_handle* out) {
     CUDA_TRY(h, dmalloc(&h->xs_gs_cur, G1)); CUDA_TRY(h, dmalloc(&h->xs_gs_off, G1)); CUDA_TRY(h, dmalloc(&h->xs_gs_idx, n));
     CUDA_TRY(h, dmalloc(&h->xs_descs, n));
     CUDA_TRY(h, dmalloc(&h->xs_lw, n)); CUDA_TRY(h, dmalloc(&h->xs_lw_local, n)); CUDA_TRY(h, dmalloc(&h->xs_lw_tops, wt));
+    CUDA_TRY(h, dmalloc(&h->xs_tab, 1));
     CUDA_TRY(h, dmalloc(&h->shard_of_dev, c.max_agents));
     CUDA_TRY(h, cudaMemset(h->shard_of_dev, static_cast<int>(c.shard_id), c.max_agents));
     CUDA_TRY(h, cudaHostAlloc(reinterpret_cast<void**>(&h->wire_host), 64 + static_cast<size_t>(c.max_batch_sends) * sizeof(sdb_send_desc), cudaHostAllocDefault));
@@ -516,7 +518,7 @@ int sdb_destroy(sdb_handle h) {
                  h->scratch.gs_idx_dev, h->memb_off_dev, h->memb_grp_dev, h->memb_pos_dev, h->member_pos_dev,
                  h->lstart_dev, h->lcount_dev, h->xs_w, h->xs_w_local, h->xs_w_tops, h->xs_gs_cnt, h->xs_gs_local,
                  h->xs_gs_tops, h->xs_gs_cur, h->xs_gs_off, h->xs_gs_idx, h->xs_descs, h->xs_lw, h->xs_lw_local,
-                 h->xs_lw_tops, h->shard_of_dev, h->rx_agent, h->rx_cnt,
+                 h->xs_lw_tops, h->xs_tab, h->shard_of_dev, h->rx_agent, h->rx_cnt,
                  h->rx_rec_local, h->rx_rec_tops, h->rx_plan_handle, h->rx_plan_glen, h->rx_plan_local, h->rx_plan_tops,
                  h->rx_totals, h->rx_big_list, h->rx_big_count, h->rx_count, h->rx_hdr, h->rx_payload,
                  h->be_weight, h->be_load, h->be_scratch, h->be_logtab, h->be_req_cost, h->be_out};
@@ -822,7 +824,7 @@ int sdb_import_wire_ptrs(sdb_handle h, uint32_t n_src, const void* const* wire_p
     if (!wire_ptrs[k]) return fail(h, SDB_EINVAL, "null wire pointer");
     a.wire[k] = static_cast<const uint8_t*>(wire_ptrs[k]);
   }
-  a.n_src = n_src; a.max_sends = h->cfg.max_batch_sends;
+  a.n_src = n_src; a.max_sends = h->cfg.max_batch_sends; a.tab = h->xs_tab;
   a.lstart = h->lstart_dev; a.lcount = h->lcount_dev; a.max_groups = h->cfg.max_groups;
   a.w = h->xs_w; a.gs_cnt = h->xs_gs_cnt; a.descs = h->xs_descs; a.w_local = h->xs_w_local; a.w_tops = h->xs_w_tops;
   a.gs_off = h->xs_gs_off; a.gs_idx = h->xs_gs_idx;

@@ -145,7 +145,15 @@ struct sdb_recv_args {
 
 // arguments of one cross-shard import (sdb_xshard.cu)
 #define SDB_MAX_SRC 16
+// per-source prefix table built once per import by k_wire_table (so the per-send kernels never
+// touch the - possibly remote - wire headers)
+struct sdb_src_tab {
+  uint32_t first[SDB_MAX_SRC + 1];   // global index of each source's first send
+  uint64_t rec_base[SDB_MAX_SRC];    // sequence offset of each source inside the global batch
+  uint64_t desc_off[SDB_MAX_SRC], list_off[SDB_MAX_SRC], payload_off[SDB_MAX_SRC];
+};
 struct sdb_import_args {
+  const sdb_src_tab* tab;
   const uint8_t* wire[SDB_MAX_SRC];   // one wire batch per source rank; may point into PEER GPU memory (NVLink)
   uint32_t n_src;
   uint32_t max_sends;         // capacity per wire batch

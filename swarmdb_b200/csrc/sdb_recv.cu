@@ -291,19 +291,21 @@ k_recv_select(sdb_dev_view v, sdb_recv_args r) {
     }
   }
   const bool prio_mode = (r.flags & SDB_RECV_PRIORITY) != 0;
-  constexpr uint32_t SMALL = 8;
+  constexpr uint32_t SMALL = 64, CH = 8;
   const bool small = valid && cnt && !prio_mode && nt == 0 && cnt <= SMALL;
   if (small) {
     const uint64_t pol = sdb_policy_evict_last();
     const uint16_t* ms = v.ring_meta + (static_cast<size_t>(a) << v.ring_shift);
     const uint32_t* hs = v.ring_handle + (static_cast<size_t>(a) << v.ring_shift);
-    uint32_t hv[SMALL]; uint16_t mv[SMALL];
+    for (uint32_t b = 0; b < cnt; b += CH) {
+      uint32_t hv[CH]; uint16_t mv[CH];
 #pragma unroll
-    for (uint32_t j = 0; j < SMALL; ++j)       // all loads first, then the stores
-      if (j < cnt) { hv[j] = sdb_ld_u32_pol(hs + ((head + j) & mask), pol); mv[j] = sdb_ld_u16_pol(ms + ((head + j) & mask), pol); }
+      for (uint32_t j = 0; j < CH; ++j)       // all loads of the chunk first, then the stores
+        if (b + j < cnt) { hv[j] = sdb_ld_u32_pol(hs + ((head + b + j) & mask), pol); mv[j] = sdb_ld_u16_pol(ms + ((head + b + j) & mask), pol); }
 #pragma unroll
-    for (uint32_t j = 0; j < SMALL; ++j)
-      if (j < cnt) { r.plan_handle[roff + j] = hv[j]; r.plan_glen[roff + j] = (mv[j] & SDB_META_GLEN_MASK) - 1u; }
+      for (uint32_t j = 0; j < CH; ++j)
+        if (b + j < cnt) { r.plan_handle[roff + b + j] = hv[j]; r.plan_glen[roff + b + j] = (mv[j] & SDB_META_GLEN_MASK) - 1u; }
+    }
     reinterpret_cast<uint32_t*>(v.ring_state + a)[0] = head + cnt;    // low word = head (little endian)
   }
   // everything else (long runs, holes, priority order) goes to the warp-per-agent kernel

@@ -30,21 +30,38 @@ __device__ __forceinline__ const sdb_wire_header* wire_hdr(const sdb_import_args
   return reinterpret_cast<const sdb_wire_header*>(a.wire[src]);
 }
 
+// one thread: read the n_src wire headers (remote when the batch lives in a peer GPU) and publish the prefix table
+__global__ void k_wire_table(sdb_import_args a, sdb_src_tab* tab) {
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  uint32_t first = 0; uint64_t rb = 0;
+  for (uint32_t s = 0; s < a.n_src; ++s) {
+    const sdb_wire_header* h = wire_hdr(a, s);
+    const bool ok = h->magic == SDB_WIRE_MAGIC;
+    tab->first[s] = first; tab->rec_base[s] = rb;
+    tab->desc_off[s] = ok ? h->desc_off : 0; tab->list_off[s] = ok ? h->list_off : 0; tab->payload_off[s] = ok ? h->payload_off : 0;
+    first += ok ? min(h->n_sends, a.max_sends) : 0u;
+    rb += ok ? h->total_recs : 0ull;
+  }
+  for (uint32_t s = a.n_src; s <= SDB_MAX_SRC; ++s) tab->first[s] = first;
+}
+
 // global send index -> (source, index inside the source), sources concatenated in rank order
 __device__ __forceinline__ bool locate(const sdb_import_args& a, uint32_t gi, uint32_t& src, uint32_t& i,
                                        uint64_t& rec_base) {
-  uint32_t first = 0; rec_base = 0;
-  for (uint32_t s = 0; s < a.n_src; ++s) {
-    const sdb_wire_header* h = wire_hdr(a, s);
-    const uint32_t n = h->magic == SDB_WIRE_MAGIC ? min(h->n_sends, a.max_sends) : 0u;
-    if (gi < first + n) { src = s; i = gi - first; return true; }
-    first += n; rec_base += h->magic == SDB_WIRE_MAGIC ? h->total_recs : 0ull;
-  }
-  return false;
+  const sdb_src_tab* t = a.tab;
+  if (gi >= t->first[a.n_src]) return false;
+  uint32_t s = 0;
+  while (s + 1 < a.n_src && gi >= t->first[s + 1]) ++s;
+  src = s; i = gi - t->first[s]; rec_base = t->rec_base[s];
+  return true;
 }
 
-__device__ __forceinline__ const uint32_t* wire_list(const sdb_wire_header* h) {
-  return reinterpret_cast<const uint32_t*>(reinterpret_cast<const uint8_t*>(h) + h->list_off);
+__device__ __forceinline__ const sdb_send_desc* wire_desc(const sdb_import_args& a, uint32_t src, uint32_t i) {
+  return reinterpret_cast<const sdb_send_desc*>(a.wire[src] + a.tab->desc_off[src]) + i;
+}
+
+__device__ __forceinline__ const uint32_t* wire_list(const sdb_import_args& a, uint32_t src) {
+  return reinterpret_cast<const uint32_t*>(a.wire[src] + a.tab->list_off[src]);
 }
 
 __global__ void __launch_bounds__(256)
@@ -53,14 +70,17 @@ k_wire_measure(sdb_import_args a, uint32_t n_total) {
   if (gi >= n_total) return;
   uint32_t src, i; uint64_t rb;
   if (!locate(a, gi, src, i, rb)) { a.w[gi] = 0; a.lw[gi] = 0; return; }
-  const sdb_wire_header* h = wire_hdr(a, src);
-  const sdb_send_desc* d = reinterpret_cast<const sdb_send_desc*>(reinterpret_cast<const uint8_t*>(h) + h->desc_off) + i;
+  const uint4* dq = reinterpret_cast<const uint4*>(wire_desc(a, src, i));
+  sdb_send_desc dd;                                             // one 64-byte read of the (remote) descriptor
+  reinterpret_cast<uint4*>(&dd)[0] = __ldg(dq); reinterpret_cast<uint4*>(&dd)[1] = __ldg(dq + 1);
+  reinterpret_cast<uint4*>(&dd)[2] = __ldg(dq + 2); reinterpret_cast<uint4*>(&dd)[3] = __ldg(dq + 3);
+  const sdb_send_desc* d = &dd;
   uint32_t lc = 0, own = 0;
   if (d->flags & SDB_DESC_P2P) {                                   // delivered by the receiver's owner only
     own = (d->mstart < a.max_agents && a.shard_of[d->mstart] == a.shard_id) ? 1u : 0u;
     lc = own;
   } else if (d->flags & SDB_DESC_LIST_TEMP) {                      // broadcast: the recipients this shard owns
-    const uint32_t* l = wire_list(h) + d->mstart;
+    const uint32_t* l = wire_list(a, src) + d->mstart;
     for (uint32_t k = 0; k < d->mcount; ++k) { const uint32_t x = l[k]; own += (x < a.max_agents && a.shard_of[x] == a.shard_id); }
     lc = own;
   } else {
@@ -84,12 +104,16 @@ k_wire_localize(sdb_import_args a, uint32_t n_total, uint32_t* gs_cur) {
     o[0] = z; o[1] = z; o[2] = z; o[3] = z;
     return;
   }
-  const sdb_wire_header* h = wire_hdr(a, src);
-  const sdb_send_desc* d = reinterpret_cast<const sdb_send_desc*>(reinterpret_cast<const uint8_t*>(h) + h->desc_off) + i;
-  out = *d;
+  {
+    const uint4* dq = reinterpret_cast<const uint4*>(wire_desc(a, src, i));
+    reinterpret_cast<uint4*>(&out)[0] = __ldg(dq); reinterpret_cast<uint4*>(&out)[1] = __ldg(dq + 1);
+    reinterpret_cast<uint4*>(&out)[2] = __ldg(dq + 2); reinterpret_cast<uint4*>(&out)[3] = __ldg(dq + 3);
+  }
+  const sdb_send_desc wd = out;
+  const sdb_send_desc* d = &wd;
   // absolute address (the fan-out kernel is launched with a null payload base): the payload stays where the
   // source rank exported it - possibly in a peer GPU's memory - and is pulled by the fan-out's TMA loads
-  out.payload_off = reinterpret_cast<uint64_t>(a.wire[src]) + h->payload_off + d->payload_off;
+  out.payload_off = reinterpret_cast<uint64_t>(a.wire[src]) + a.tab->payload_off[src] + d->payload_off;
   out.gran0 = a.w_local[gi] + a.w_tops[gi / SDB_SCAN_TILE];
   out.rec0 = static_cast<uint32_t>(rb + d->rec0);
   if (d->flags & (SDB_DESC_P2P | SDB_DESC_LIST_TEMP)) {
@@ -103,7 +127,7 @@ k_wire_localize(sdb_import_args a, uint32_t n_total, uint32_t* gs_cur) {
     } else {
       out.flags = SDB_DESC_LIST_TEMP | SDB_DESC_SHARED_SEQ;
       if (fits) {
-        const uint32_t* l = wire_list(h) + d->mstart;
+        const uint32_t* l = wire_list(a, src) + d->mstart;
         for (uint32_t k = 0; k < d->mcount; ++k) { const uint32_t x = l[k]; if (x < a.max_agents && a.shard_of[x] == a.shard_id) a.tmp_list[lo++] = x; }
       }
     }
@@ -147,12 +171,13 @@ extern "C" cudaError_t sdb_launch_import_measure(const sdb_import_args* a, uint3
                                                  cudaStream_t stream, sdb_profiler* prof, int* n_launches) {
   const int pi = sdb_prof_begin(prof, SDB_PK_XSHARD, stream);
   cudaMemsetAsync(a->gs_cnt, 0, (static_cast<size_t>(a->max_groups) + 1) * sizeof(uint32_t), stream);
+  k_wire_table<<<1, 32, 0, stream>>>(*a, const_cast<sdb_src_tab*>(a->tab));
   k_wire_measure<<<(n_cap + 255) / 256, 256, 0, stream>>>(*a, n_cap);
   cudaError_t e = sdb_scan_u32(a->w, w_local, w_tops, n_cap, totals_dev, nullptr, stream);
   if (e == cudaSuccess) e = sdb_scan_u32(a->gs_cnt, gs_local, gs_tops, a->max_groups + 1, nullptr, gs_off_out, stream);
   if (e == cudaSuccess) e = sdb_scan_u32(a->lw, lw_local, lw_tops, n_cap, totals_dev + 1, nullptr, stream);   // owned recipients
   sdb_prof_end(prof, pi, stream);
-  if (n_launches) *n_launches += 8;
+  if (n_launches) *n_launches += 9;
   return e != cudaSuccess ? e : cudaGetLastError();
 }
 
