@@ -94,6 +94,7 @@ struct sdb_ctx {
   uint32_t* xs_gs_off = nullptr; uint32_t* xs_gs_idx = nullptr; sdb_send_desc* xs_descs = nullptr;
   uint32_t* xs_lw = nullptr; uint32_t* xs_lw_local = nullptr; uint32_t* xs_lw_tops = nullptr;
   sdb_src_tab* xs_tab = nullptr;
+  uint8_t* xs_meta = nullptr; uint64_t xs_meta_stride = 0;   // local copies of remote headers + descriptors
   uint8_t* shard_of_dev = nullptr;
   uint8_t* wire_host = nullptr;                // pinned: header + descriptors of an export
   sdb_wire_header* hdrs_host = nullptr;        // pinned [num_shards]
@@ -495,6 +496,8 @@ int sdb_create(const sdb_config* cfg, sdb_handle* out) {
     CUDA_TRY(h, dmalloc(&h->xs_descs, n));
     CUDA_TRY(h, dmalloc(&h->xs_lw, n)); CUDA_TRY(h, dmalloc(&h->xs_lw_local, n)); CUDA_TRY(h, dmalloc(&h->xs_lw_tops, wt));
     CUDA_TRY(h, dmalloc(&h->xs_tab, 1));
+    h->xs_meta_stride = 64 + static_cast<uint64_t>(c.max_batch_sends) * sizeof(sdb_send_desc);
+    CUDA_TRY(h, dmalloc(&h->xs_meta, h->xs_meta_stride * c.num_shards));
     CUDA_TRY(h, dmalloc(&h->shard_of_dev, c.max_agents));
     CUDA_TRY(h, cudaMemset(h->shard_of_dev, static_cast<int>(c.shard_id), c.max_agents));
     CUDA_TRY(h, cudaHostAlloc(reinterpret_cast<void**>(&h->wire_host), 64 + static_cast<size_t>(c.max_batch_sends) * sizeof(sdb_send_desc), cudaHostAllocDefault));
@@ -518,7 +521,7 @@ int sdb_destroy(sdb_handle h) {
                  h->scratch.gs_idx_dev, h->memb_off_dev, h->memb_grp_dev, h->memb_pos_dev, h->member_pos_dev,
                  h->lstart_dev, h->lcount_dev, h->xs_w, h->xs_w_local, h->xs_w_tops, h->xs_gs_cnt, h->xs_gs_local,
                  h->xs_gs_tops, h->xs_gs_cur, h->xs_gs_off, h->xs_gs_idx, h->xs_descs, h->xs_lw, h->xs_lw_local,
-                 h->xs_lw_tops, h->xs_tab, h->shard_of_dev, h->rx_agent, h->rx_cnt,
+                 h->xs_lw_tops, h->xs_tab, h->xs_meta, h->shard_of_dev, h->rx_agent, h->rx_cnt,
                  h->rx_rec_local, h->rx_rec_tops, h->rx_plan_handle, h->rx_plan_glen, h->rx_plan_local, h->rx_plan_tops,
                  h->rx_totals, h->rx_big_list, h->rx_big_count, h->rx_count, h->rx_hdr, h->rx_payload,
                  h->be_weight, h->be_load, h->be_scratch, h->be_logtab, h->be_req_cost, h->be_out};
@@ -823,6 +826,15 @@ int sdb_import_wire_ptrs(sdb_handle h, uint32_t n_src, const void* const* wire_p
   for (uint32_t k = 0; k < n_src; ++k) {
     if (!wire_ptrs[k]) return fail(h, SDB_EINVAL, "null wire pointer");
     a.wire[k] = static_cast<const uint8_t*>(wire_ptrs[k]);
+    a.meta[k] = a.wire[k];
+    cudaPointerAttributes pa;
+    if (cudaPointerGetAttributes(&pa, wire_ptrs[k]) == cudaSuccess && pa.type == cudaMemoryTypeDevice && pa.device != h->cfg.device) {
+      // header + descriptors of a peer's batch: one DMA copy over NVLink instead of per-thread remote reads;
+      // the payload (the bulk) stays remote and is pulled by the fan-out kernel's TMA loads
+      uint8_t* dst = h->xs_meta + static_cast<uint64_t>(k) * h->xs_meta_stride;
+      CUDA_TRY(h, cudaMemcpyAsync(dst, wire_ptrs[k], h->xs_meta_stride, cudaMemcpyDeviceToDevice, h->stream));
+      a.meta[k] = dst;
+    }
   }
   a.n_src = n_src; a.max_sends = h->cfg.max_batch_sends; a.tab = h->xs_tab;
   a.lstart = h->lstart_dev; a.lcount = h->lcount_dev; a.max_groups = h->cfg.max_groups;

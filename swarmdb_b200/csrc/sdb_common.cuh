@@ -154,6 +154,7 @@ struct sdb_src_tab {
 };
 struct sdb_import_args {
   const sdb_src_tab* tab;
+  const uint8_t* meta[SDB_MAX_SRC];   // header + descriptors of each source: a LOCAL copy when the wire batch is remote
   const uint8_t* wire[SDB_MAX_SRC];   // one wire batch per source rank; may point into PEER GPU memory (NVLink)
   uint32_t n_src;
   uint32_t max_sends;         // capacity per wire batch

@@ -243,15 +243,29 @@ k_group_fanout_warp(sdb_dev_view v, const sdb_send_desc* __restrict__ descs, uin
   uint32_t i = gw, st = 0;
   bool have = i < n;
   sdb_send_desc d;
+  uint32_t pa0 = 0xFFFFFFFFu, pa1 = 0xFFFFFFFFu, pp0 = 0, pp1 = 0;      // first-tile members of the current send
+  auto member_list = [&](const sdb_send_desc& x) { return (x.flags & SDB_DESC_LIST_TEMP) ? tmp_list + x.mstart : v.members + x.mstart; };
+  auto fetch_members = [&](const sdb_send_desc& x, uint32_t& a0, uint32_t& a1, uint32_t& q0, uint32_t& q1) {
+    const uint32_t* m = member_list(x);
+    const uint32_t j0 = lane, j1 = lane + 32;
+    a0 = j0 < x.mcount ? __ldg(m + j0) : 0xFFFFFFFFu;
+    a1 = j1 < x.mcount ? __ldg(m + j1) : 0xFFFFFFFFu;
+    if (x.flags & SDB_DESC_POS) {
+      const uint32_t* mp = v.member_pos + x.mstart;
+      q0 = j0 < x.mcount ? __ldg(mp + j0) : 0u; q1 = j1 < x.mcount ? __ldg(mp + j1) : 0u;
+    } else { q0 = j0; q1 = j1; }
+  };
   if (have) {
     d = load_desc(descs + i);
     const uint32_t pl = (d.rgran - 1u) * SDB_GRANULE;
     if (lane == 0 && d.mcount && pl) { sdb_mbar_expect_tx(&s_bar[warp][0], pl); sdb_tma_load(my_base, payload + d.payload_off, pl, &s_bar[warp][0]); }
+    fetch_members(d, pa0, pa1, pp0, pp1);
   }
   while (have) {
     const uint32_t inext = i + nw;
     const bool have_next = inext < n;
     sdb_send_desc dn;
+    uint32_t na0 = 0xFFFFFFFFu, na1 = 0xFFFFFFFFu, np0 = 0, np1 = 0;
     if (have_next) {
       dn = load_desc(descs + inext);
       const uint32_t pl = (dn.rgran - 1u) * SDB_GRANULE;
@@ -260,12 +274,13 @@ k_group_fanout_warp(sdb_dev_view v, const sdb_send_desc* __restrict__ descs, uin
         sdb_mbar_expect_tx(&s_bar[warp][st ^ 1u], pl);
         sdb_tma_load(dst, payload + dn.payload_off, pl, &s_bar[warp][st ^ 1u]);
       }
+      fetch_members(dn, na0, na1, np0, np1);                           // member ids of the next send, in flight with its payload
     }
     uint8_t* const my = my_base + st * stage_bytes;
     const uint4* const my4 = reinterpret_cast<const uint4*>(my);
     const uint32_t padlen = (d.rgran - 1u) * SDB_GRANULE;
     const uint32_t P = padlen >> 4;                        // 16-byte chunks per payload
-    const uint32_t* mem = (d.flags & SDB_DESC_LIST_TEMP) ? tmp_list + d.mstart : v.members + d.mstart;
+    const uint32_t* mem = member_list(d);
     const uint16_t meta = static_cast<uint16_t>((static_cast<uint32_t>(d.prio) << 14) | d.rgran);
     const uint64_t apos0 = arena_base + d.gran0;
     uint8_t* const base = sdb_arena_ptr(v, apos0);         // the batch region never wraps: plain pointer math below
@@ -277,11 +292,14 @@ k_group_fanout_warp(sdb_dev_view v, const sdb_send_desc* __restrict__ descs, uin
 
     for (uint32_t tile = 0; tile < d.mcount; tile += 64) {
       const uint32_t j0 = tile + lane, j1 = j0 + 32;
-      const uint32_t a0 = j0 < d.mcount ? __ldg(mem + j0) : 0xFFFFFFFFu;
-      const uint32_t a1 = j1 < d.mcount ? __ldg(mem + j1) : 0xFFFFFFFFu;
-      // sequence offset of each member: its position in the (full) group
-      const uint32_t p0 = mpos ? (j0 < d.mcount ? __ldg(mpos + j0) : 0u) : j0;
-      const uint32_t p1 = mpos ? (j1 < d.mcount ? __ldg(mpos + j1) : 0u) : j1;
+      uint32_t a0, a1, p0, p1;                               // member ids and their sequence offsets (group positions)
+      if (tile == 0) { a0 = pa0; a1 = pa1; p0 = pp0; p1 = pp1; }
+      else {
+        a0 = j0 < d.mcount ? __ldg(mem + j0) : 0xFFFFFFFFu;
+        a1 = j1 < d.mcount ? __ldg(mem + j1) : 0xFFFFFFFFu;
+        p0 = mpos ? (j0 < d.mcount ? __ldg(mpos + j0) : 0u) : j0;
+        p1 = mpos ? (j1 < d.mcount ? __ldg(mpos + j1) : 0u) : j1;
+      }
       const bool s0 = j0 < d.mcount && skip_sender && a0 == d.sender;
       const bool s1 = j1 < d.mcount && skip_sender && a1 == d.sender;
       const bool d0 = j0 < d.mcount && !s0 && a0 < v.max_agents;
@@ -326,6 +344,7 @@ k_group_fanout_warp(sdb_dev_view v, const sdb_send_desc* __restrict__ descs, uin
       __syncwarp();
     }
     d = dn; i = inext; have = have_next; st ^= 1u;
+    pa0 = na0; pa1 = na1; pp0 = np0; pp1 = np1;
   }
   for (int o = 16; o; o >>= 1) {
     n_enq += __shfl_xor_sync(0xFFFFFFFFu, n_enq, o);

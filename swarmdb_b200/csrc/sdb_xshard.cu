@@ -27,7 +27,7 @@
 
 
 __device__ __forceinline__ const sdb_wire_header* wire_hdr(const sdb_import_args& a, uint32_t src) {
-  return reinterpret_cast<const sdb_wire_header*>(a.wire[src]);
+  return reinterpret_cast<const sdb_wire_header*>(a.meta[src]);
 }
 
 // one thread: read the n_src wire headers (remote when the batch lives in a peer GPU) and publish the prefix table
@@ -57,7 +57,7 @@ __device__ __forceinline__ bool locate(const sdb_import_args& a, uint32_t gi, ui
 }
 
 __device__ __forceinline__ const sdb_send_desc* wire_desc(const sdb_import_args& a, uint32_t src, uint32_t i) {
-  return reinterpret_cast<const sdb_send_desc*>(a.wire[src] + a.tab->desc_off[src]) + i;
+  return reinterpret_cast<const sdb_send_desc*>(a.meta[src] + a.tab->desc_off[src]) + i;
 }
 
 __device__ __forceinline__ const uint32_t* wire_list(const sdb_import_args& a, uint32_t src) {
