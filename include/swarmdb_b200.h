@@ -228,7 +228,7 @@ int sdb_last_receive_dev(sdb_handle h, const uint32_t** count_dev, const sdb_msg
  * identical to a single-shard run over the concatenated batch.  With num_shards == 1 the same
  * two calls work without any collective.
  */
-uint64_t sdb_wire_bytes(uint32_t max_sends, uint64_t max_payload_bytes);
+uint64_t sdb_wire_bytes(sdb_handle h, uint32_t max_sends, uint64_t max_payload_bytes);
 int sdb_set_agent_shards(sdb_handle h, uint32_t n, const uint8_t* shard_of);
 int sdb_export_group_batch(sdb_handle h, uint32_t n,
                            const uint32_t* sender, const uint32_t* group_idx,

@@ -97,7 +97,7 @@ def load_library() -> C.CDLL:
     L.sdb_receive_batch.restype = i32
     L.sdb_receive_batch.argtypes = [vp, u32, vp, u32, u32, vp, vp, u64, vp, u64, vp, vp]
     L.sdb_last_receive_dev.restype = i32; L.sdb_last_receive_dev.argtypes = [vp, vp, vp, vp]
-    L.sdb_wire_bytes.restype = u64; L.sdb_wire_bytes.argtypes = [u32, u64]
+    L.sdb_wire_bytes.restype = u64; L.sdb_wire_bytes.argtypes = [vp, u32, u64]
     L.sdb_set_agent_shards.restype = i32; L.sdb_set_agent_shards.argtypes = [vp, u32, vp]
     L.sdb_export_group_batch.restype = i32; L.sdb_export_group_batch.argtypes = [vp, u32] + [vp] * 7 + [u64, vp, vp, u64]
     L.sdb_export_mixed_batch.restype = i32
@@ -296,7 +296,7 @@ class Shard:
 
     # ------------------------------------------------------------------ cross-shard
     def wire_bytes(self, max_sends: int, max_payload: int) -> int:
-        return int(self._L.sdb_wire_bytes(max_sends, max_payload))
+        return int(self._L.sdb_wire_bytes(self._h, max_sends, max_payload))
 
     def set_agent_shards(self, shard_of) -> None:
         s = _arr(shard_of, np.uint8)

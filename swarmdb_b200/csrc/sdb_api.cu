@@ -33,7 +33,7 @@ cudaError_t sdb_launch_pick(int mode, uint32_t n_backends, const uint32_t* weigh
 void sdb_build_log2_table(uint32_t* tab257);
 cudaError_t sdb_launch_import_measure(const sdb_import_args*, uint32_t, uint32_t*, uint32_t*, uint32_t*, uint32_t*, uint32_t*,
                                       uint32_t*, uint32_t*, unsigned long long*, cudaStream_t, sdb_profiler*, int*);
-cudaError_t sdb_launch_import_localize(const sdb_import_args*, uint32_t, uint32_t*, cudaStream_t, sdb_profiler*, int*);
+cudaError_t sdb_launch_import_localize(const sdb_import_args*, uint32_t, const uint32_t*, uint32_t*, cudaStream_t, sdb_profiler*, int*);
 }
 
 #define SDB_SCAN_TILE 4096u
@@ -144,6 +144,11 @@ int fail(sdb_ctx* h, int code, const std::string& msg) {
   } while (0)
 
 bool is_pow2(uint64_t x) { return x && !(x & (x - 1)); }
+// header + descriptors + group buckets of a wire batch (the part a remote importer copies locally)
+uint64_t wire_meta_bytes(uint32_t max_sends, uint32_t max_groups) {
+  const uint64_t b = sizeof(sdb_wire_header) + static_cast<uint64_t>(max_sends) * (sizeof(sdb_send_desc) + 4) + (static_cast<uint64_t>(max_groups) + 1) * 4 + 64;
+  return (b + 127) & ~127ull;                         // wire batches are laid out back to back: keep them 128-byte aligned
+}
 uint32_t ilog2(uint64_t x) { uint32_t r = 0; while ((1ull << r) < x) ++r; return r; }
 inline uint32_t pad32(uint32_t len) { return (len + 31u) & ~31u; }
 
@@ -489,18 +494,19 @@ int sdb_create(const sdb_config* cfg, sdb_handle* out) {
     if (cap64 > 0x7FFFFFFFull) return fail(h, SDB_EINVAL, "num_shards * max_batch_sends too large");
     h->xs_cap = static_cast<uint32_t>(cap64);
     const size_t n = h->xs_cap, G1 = static_cast<size_t>(c.max_groups) + 1;
-    const size_t wt = n / SDB_SCAN_TILE + 2, gt = G1 / SDB_SCAN_TILE + 2;
+    const size_t GB = G1 * c.num_shards + 2;                 // (group, source) pairs
+    const size_t wt = n / SDB_SCAN_TILE + 2, gt = GB / SDB_SCAN_TILE + 2;
     CUDA_TRY(h, dmalloc(&h->xs_w, n)); CUDA_TRY(h, dmalloc(&h->xs_w_local, n)); CUDA_TRY(h, dmalloc(&h->xs_w_tops, wt));
-    CUDA_TRY(h, dmalloc(&h->xs_gs_cnt, G1)); CUDA_TRY(h, dmalloc(&h->xs_gs_local, G1)); CUDA_TRY(h, dmalloc(&h->xs_gs_tops, gt));
-    CUDA_TRY(h, dmalloc(&h->xs_gs_cur, G1)); CUDA_TRY(h, dmalloc(&h->xs_gs_off, G1)); CUDA_TRY(h, dmalloc(&h->xs_gs_idx, n));
+    CUDA_TRY(h, dmalloc(&h->xs_gs_cnt, GB)); CUDA_TRY(h, dmalloc(&h->xs_gs_local, GB)); CUDA_TRY(h, dmalloc(&h->xs_gs_tops, gt));
+    CUDA_TRY(h, dmalloc(&h->xs_gs_cur, GB)); CUDA_TRY(h, dmalloc(&h->xs_gs_off, G1)); CUDA_TRY(h, dmalloc(&h->xs_gs_idx, n));
     CUDA_TRY(h, dmalloc(&h->xs_descs, n));
     CUDA_TRY(h, dmalloc(&h->xs_lw, n)); CUDA_TRY(h, dmalloc(&h->xs_lw_local, n)); CUDA_TRY(h, dmalloc(&h->xs_lw_tops, wt));
     CUDA_TRY(h, dmalloc(&h->xs_tab, 1));
-    h->xs_meta_stride = 64 + static_cast<uint64_t>(c.max_batch_sends) * sizeof(sdb_send_desc);
+    h->xs_meta_stride = wire_meta_bytes(c.max_batch_sends, c.max_groups);
     CUDA_TRY(h, dmalloc(&h->xs_meta, h->xs_meta_stride * c.num_shards));
     CUDA_TRY(h, dmalloc(&h->shard_of_dev, c.max_agents));
     CUDA_TRY(h, cudaMemset(h->shard_of_dev, static_cast<int>(c.shard_id), c.max_agents));
-    CUDA_TRY(h, cudaHostAlloc(reinterpret_cast<void**>(&h->wire_host), 64 + static_cast<size_t>(c.max_batch_sends) * sizeof(sdb_send_desc), cudaHostAllocDefault));
+    CUDA_TRY(h, cudaHostAlloc(reinterpret_cast<void**>(&h->wire_host), wire_meta_bytes(c.max_batch_sends, c.max_groups), cudaHostAllocDefault));
     CUDA_TRY(h, cudaHostAlloc(reinterpret_cast<void**>(&h->hdrs_host), static_cast<size_t>(c.num_shards) * sizeof(sdb_wire_header), cudaHostAllocDefault));
   }
 
@@ -669,9 +675,10 @@ int sdb_create_group(sdb_handle h, uint32_t g, uint32_t n_members, const uint32_
   return SDB_OK;
 }
 
-uint64_t sdb_wire_bytes(uint32_t max_sends, uint64_t max_payload_bytes) {
-  // header + descriptors + payload (+ slack); broadcast recipient lists count towards max_payload_bytes
-  return 64ull + static_cast<uint64_t>(max_sends) * sizeof(sdb_send_desc) + ((max_payload_bytes + 128 + 63) & ~63ull);
+uint64_t sdb_wire_bytes(sdb_handle h, uint32_t max_sends, uint64_t max_payload_bytes) {
+  // header + descriptors + group buckets + payload (+ slack); broadcast recipient lists count towards max_payload_bytes
+  const uint32_t G = h ? h->cfg.max_groups : 0;
+  return wire_meta_bytes(max_sends, G) + ((max_payload_bytes + 256 + 127) & ~127ull);
 }
 
 int sdb_set_agent_shards(sdb_handle h, uint32_t n, const uint8_t* shard_of) {
@@ -702,12 +709,20 @@ static int export_common(sdb_ctx* h, uint32_t n, const uint32_t* sender, const u
   if (payload_bytes && !payload) return fail(h, SDB_EINVAL, "null payload");
   const uint64_t n_list = (n_lists && list_off) ? list_off[n_lists] : 0;
   if (n_list > h->cfg.list_pool_entries) return fail(h, SDB_ECAPACITY, "recipient lists exceed list_pool_entries");
-  const uint64_t desc_off = 64, l_off = 64 + static_cast<uint64_t>(n) * sizeof(sdb_send_desc);
+  const uint32_t G = h->cfg.max_groups;
+  const uint64_t desc_off = sizeof(sdb_wire_header);
+  const uint64_t gso_off = desc_off + static_cast<uint64_t>(n) * sizeof(sdb_send_desc);
+  const uint64_t gsi_off = gso_off + (static_cast<uint64_t>(G) + 1) * 4;
+  const uint64_t l_off = gsi_off + static_cast<uint64_t>(n) * 4;            // room for every send being a group send
   const uint64_t pay_off = (l_off + n_list * sizeof(uint32_t) + 63) & ~63ull;
   if (pay_off + payload_bytes + 64 > wire_cap) return fail(h, SDB_ECAPACITY, "wire buffer too small (sdb_wire_bytes)");
   CUDA_TRY(h, cudaEventSynchronize(h->staging_free));
   sdb_wire_header* wh = reinterpret_cast<sdb_wire_header*>(h->wire_host);
-  sdb_send_desc* wd = reinterpret_cast<sdb_send_desc*>(h->wire_host + 64);
+  sdb_send_desc* wd = reinterpret_cast<sdb_send_desc*>(h->wire_host + desc_off);
+  uint32_t* gso = reinterpret_cast<uint32_t*>(h->wire_host + gso_off);
+  uint32_t* gsi = reinterpret_cast<uint32_t*>(h->wire_host + gsi_off);
+  std::memset(gso, 0, (static_cast<size_t>(G) + 1) * 4);
+  uint32_t n_group = 0;
   std::memset(wh, 0, sizeof(*wh));
   uint64_t rec = 0; uint32_t max_padlen = 0, n_other = 0;
   for (uint64_t k = 0; k < n_list; ++k) if (list_idx[k] >= h->cfg.max_agents) return fail(h, SDB_EINVAL, "recipient index out of range");
@@ -729,6 +744,7 @@ static int export_common(sdb_ctx* h, uint32_t n, const uint32_t* sender, const u
       const uint32_t g = target[i];
       if (g >= h->cfg.max_groups || !h->gdefined[g]) return fail(h, SDB_ENOTFOUND, "unknown group index");
       d.group = g; rec += h->gcount_full[g];
+      gso[g + 1]++; ++n_group;
     } else if (k == 0) {
       if (target[i] >= h->cfg.max_agents) return fail(h, SDB_EINVAL, "receiver index out of range");
       d.mstart = target[i]; d.mcount = 1; d.flags = SDB_DESC_P2P; rec += 1; ++n_other;
@@ -740,11 +756,18 @@ static int export_common(sdb_ctx* h, uint32_t n, const uint32_t* sender, const u
     } else return fail(h, SDB_EINVAL, "kind must be 0, 1 or 2");
     wd[i] = d;
   }
+  // bucket the group sends by group: counting sort, ascending send index inside a bucket
+  for (uint32_t g = 0; g < G; ++g) gso[g + 1] += gso[g];
+  {
+    std::vector<uint32_t> cur(gso, gso + G);
+    for (uint32_t i = 0; i < n; ++i) if (wd[i].group != SDB_NO_GROUP) gsi[cur[wd[i].group]++] = i;
+  }
   wh->magic = SDB_WIRE_MAGIC; wh->n_sends = n; wh->total_recs = rec; wh->payload_bytes = payload_bytes;
   wh->desc_off = desc_off; wh->payload_off = pay_off; wh->max_padlen = max_padlen; wh->n_other = n_other;
   wh->list_off = l_off; wh->n_list = static_cast<uint32_t>(n_list);
+  wh->n_group_sends = n_group; wh->gs_off_off = gso_off; wh->gs_idx_off = gsi_off; wh->max_groups = G;
   uint8_t* w = static_cast<uint8_t*>(wire_dev);
-  CUDA_TRY(h, cudaMemcpyAsync(w, h->wire_host, 64 + static_cast<size_t>(n) * sizeof(sdb_send_desc), cudaMemcpyHostToDevice, h->stream));
+  CUDA_TRY(h, cudaMemcpyAsync(w, h->wire_host, l_off, cudaMemcpyHostToDevice, h->stream));
   if (n_list) {
     std::memcpy(h->list_host, list_idx, n_list * sizeof(uint32_t));
     CUDA_TRY(h, cudaMemcpyAsync(w + l_off, h->list_host, n_list * sizeof(uint32_t), cudaMemcpyHostToDevice, h->stream));
@@ -845,7 +868,7 @@ int sdb_import_wire_ptrs(sdb_handle h, uint32_t n_src, const void* const* wire_p
   a.tmp_list = h->scratch.list_dev; a.list_cap = static_cast<uint32_t>(std::min<uint64_t>(h->cfg.list_pool_entries, 0xFFFFFFFFull));
   int nl = 0;
   cudaError_t e = sdb_launch_import_measure(&a, n_cap, h->xs_w_local, h->xs_w_tops, h->xs_gs_local, h->xs_gs_tops,
-                                            h->xs_gs_off, h->xs_lw_local, h->xs_lw_tops, h->rx_totals + 4, h->stream, &h->prof, &nl);
+                                            h->xs_gs_cur /* goff */, h->xs_lw_local, h->xs_lw_tops, h->rx_totals + 4, h->stream, &h->prof, &nl);
   if (e != cudaSuccess) return fail(h, SDB_ECUDA, std::string("import measure: ") + cudaGetErrorString(e));
   // the host needs the arena footprint and the sequence numbers consumed: one small sync
   CUDA_TRY(h, cudaMemcpyAsync(h->totals_host + 4, h->rx_totals + 4, 2 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, h->stream));
@@ -865,7 +888,7 @@ int sdb_import_wire_ptrs(sdb_handle h, uint32_t n_src, const void* const* wire_p
   uint64_t base = 0;
   int rc = arena_reserve(h, total_grans, &base);
   if (rc != SDB_OK) return rc;
-  e = sdb_launch_import_localize(&a, n_cap, h->xs_gs_cur, h->stream, &h->prof, &nl);
+  e = sdb_launch_import_localize(&a, n_cap, h->xs_gs_cur /* goff */, h->xs_gs_off, h->stream, &h->prof, &nl);
   if (e == cudaSuccess)
     e = sdb_launch_fanout(&h->view, h->xs_descs, n_cap, nullptr, h->scratch.list_dev, h->next_seq, base, max_padlen, 2, h->sm_count, h->stream, &h->prof);
   if (e == cudaSuccess) {

@@ -64,7 +64,7 @@ static_assert(sizeof(sdb_msg_header) == 32, "header must be 32 bytes");
 #define SDB_DESC_P2P 32u          // wire batches only: point-to-point send, mstart = receiver index
 
 // cross-shard wire batch (device memory, moved between ranks by the caller):
-//   [sdb_wire_header 64 B][n_sends x sdb_send_desc 64 B][payload bytes]
+//   [sdb_wire_header 128 B][n_sends x sdb_send_desc 64 B][group buckets][broadcast lists][payload bytes]
 // descriptors use: payload_off (relative to the wire payload), timestamp, sender, group, rgran,
 // len, prio, type, rec0 (seq offset inside the source's batch, counted in FULL group sizes)
 struct __align__(16) sdb_wire_header {
@@ -78,9 +78,13 @@ struct __align__(16) sdb_wire_header {
   uint32_t n_other;        // sends that are not group sends (p2p / broadcast lists)
   uint64_t list_off;       // recipient lists of broadcast sends (uint32 agent indices)
   uint32_t n_list;
-  uint32_t pad;
+  uint32_t n_group_sends;
+  uint64_t gs_off_off;     // group-send buckets of THIS batch: offsets [max_groups + 1] ...
+  uint64_t gs_idx_off;     // ... and send indices, ascending inside a bucket (built by the exporter)
+  uint32_t max_groups;
+  uint32_t pad[11];
 };
-static_assert(sizeof(sdb_wire_header) == 64, "wire header must be 64 bytes");
+static_assert(sizeof(sdb_wire_header) == 128, "wire header must be 128 bytes");
 #define SDB_WIRE_MAGIC 0x57424453u
 
 // per-batch view for the agent-parallel index build ("pull"): group sends of the batch bucketed
@@ -151,6 +155,7 @@ struct sdb_src_tab {
   uint32_t first[SDB_MAX_SRC + 1];   // global index of each source's first send
   uint64_t rec_base[SDB_MAX_SRC];    // sequence offset of each source inside the global batch
   uint64_t desc_off[SDB_MAX_SRC], list_off[SDB_MAX_SRC], payload_off[SDB_MAX_SRC];
+  uint64_t gs_off_off[SDB_MAX_SRC], gs_idx_off[SDB_MAX_SRC];
 };
 struct sdb_import_args {
   const sdb_src_tab* tab;
@@ -163,7 +168,7 @@ struct sdb_import_args {
   uint32_t max_groups;
   // outputs / scratch
   uint32_t* w;                // [n_src * max_sends] granules written locally per send (scan input)
-  uint32_t* gs_cnt;           // [max_groups + 1] bucket histogram (zeroed by the caller), then cursors
+  uint32_t* gs_cnt;           // [(max_groups + 1) * n_src + 1] bucket sizes per (group, source), then their scan
   sdb_send_desc* descs;       // [n_src * max_sends] localized descriptors
   const uint32_t* w_local;    // scan of w
   const uint32_t* w_tops;

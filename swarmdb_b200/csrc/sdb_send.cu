@@ -244,6 +244,7 @@ k_group_fanout_warp(sdb_dev_view v, const sdb_send_desc* __restrict__ descs, uin
   bool have = i < n;
   sdb_send_desc d;
   uint32_t pa0 = 0xFFFFFFFFu, pa1 = 0xFFFFFFFFu, pp0 = 0, pp1 = 0;      // first-tile members of the current send
+  uint32_t pc_c = 0, q32_c = 0, r32_c = 0, rec_c = 0, ch_c = 0;         // cached (record, chunk) walk parameters
   auto member_list = [&](const sdb_send_desc& x) { return (x.flags & SDB_DESC_LIST_TEMP) ? tmp_list + x.mstart : v.members + x.mstart; };
   auto fetch_members = [&](const sdb_send_desc& x, uint32_t& a0, uint32_t& a1, uint32_t& q0, uint32_t& q1) {
     const uint32_t* m = member_list(x);
@@ -321,25 +322,46 @@ k_group_fanout_warp(sdb_dev_view v, const sdb_send_desc* __restrict__ descs, uin
       const uint32_t nrec = min(64u, d.mcount - tile);
       const uint32_t PC = P + 2u;
       const uint32_t total = nrec * PC;
-      const uint32_t q32 = 32u / PC, r32 = 32u % PC;
-      uint32_t rec = lane / PC, ch = lane % PC;
+      if (PC != pc_c) {                                     // the divisions are redone only when the record size changes
+        pc_c = PC; q32_c = 32u / PC; r32_c = 32u % PC; rec_c = lane / PC; ch_c = lane % PC;
+      }
+      const uint32_t q32 = q32_c, r32 = r32_c;
+      uint32_t rec = rec_c, ch = ch_c;
       uint8_t* const tb = base + static_cast<size_t>(tile) * rbytes;
       const uint64_t seq0 = seq_base + d.rec0;
-      for (uint32_t done = 0; done < total; done += 32) {
-        const uint32_t src = rec & 31u;
-        const uint32_t ra0 = __shfl_sync(0xFFFFFFFFu, a0, src), ra1 = __shfl_sync(0xFFFFFFFFu, a1, src);
-        const uint32_t rp0 = __shfl_sync(0xFFFFFFFFu, p0, src), rp1 = __shfl_sync(0xFFFFFFFFu, p1, src);
-        const bool lo_half = rec < 32u;
-        const uint32_t bit = ((lo_half ? m0 : m1) >> src) & 1u;
-        if (rec < nrec && bit) {
-          uint4 x;
-          if (ch == 0) x = sdb_header_lo(seq0 + (shared_seq ? 0u : (lo_half ? rp0 : rp1)), d.timestamp);
-          else if (ch == 1) x = sdb_header_hi(d.sender, shared_seq ? SDB_NO_RECEIVER : (lo_half ? ra0 : ra1), d.group, d.len, d.prio, d.type);
-          else x = my4[ch - 2u];
-          sdb_st_stream_pol(tb + static_cast<size_t>(rec) * rbytes + (ch << 4), x, pol_stream);
+      const uint4 hdr_hi = sdb_header_hi(d.sender, SDB_NO_RECEIVER, d.group, d.len, d.prio, d.type);
+      if (nrec <= 32u) {
+        // narrow sends (few local members, e.g. one shard's share of a group): one shuffle pair per step
+        for (uint32_t done = 0; done < total; done += 32) {
+          const uint32_t src = rec & 31u;
+          const uint32_t ra = __shfl_sync(0xFFFFFFFFu, a0, src), rp = __shfl_sync(0xFFFFFFFFu, p0, src);
+          if (rec < nrec && ((m0 >> src) & 1u)) {
+            uint4 x;
+            if (ch == 0) x = sdb_header_lo(seq0 + (shared_seq ? 0u : rp), d.timestamp);
+            else if (ch == 1) { x = hdr_hi; if (!shared_seq) x.y = ra; }
+            else x = my4[ch - 2u];
+            sdb_st_stream_pol(tb + static_cast<size_t>(rec) * rbytes + (ch << 4), x, pol_stream);
+          }
+          ch += r32; rec += q32;
+          if (ch >= PC) { ch -= PC; ++rec; }
         }
-        ch += r32; rec += q32;
-        if (ch >= PC) { ch -= PC; ++rec; }
+      } else {
+        for (uint32_t done = 0; done < total; done += 32) {
+          const uint32_t src = rec & 31u;
+          const uint32_t ra0 = __shfl_sync(0xFFFFFFFFu, a0, src), ra1 = __shfl_sync(0xFFFFFFFFu, a1, src);
+          const uint32_t rp0 = __shfl_sync(0xFFFFFFFFu, p0, src), rp1 = __shfl_sync(0xFFFFFFFFu, p1, src);
+          const bool lo_half = rec < 32u;
+          const uint32_t bit = ((lo_half ? m0 : m1) >> src) & 1u;
+          if (rec < nrec && bit) {
+            uint4 x;
+            if (ch == 0) x = sdb_header_lo(seq0 + (shared_seq ? 0u : (lo_half ? rp0 : rp1)), d.timestamp);
+            else if (ch == 1) { x = hdr_hi; if (!shared_seq) x.y = lo_half ? ra0 : ra1; }
+            else x = my4[ch - 2u];
+            sdb_st_stream_pol(tb + static_cast<size_t>(rec) * rbytes + (ch << 4), x, pol_stream);
+          }
+          ch += r32; rec += q32;
+          if (ch >= PC) { ch -= PC; ++rec; }
+        }
       }
       __syncwarp();
     }

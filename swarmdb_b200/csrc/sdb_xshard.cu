@@ -7,12 +7,13 @@
 // (descriptor + payload), the caller all-gathers the wire batches over NVLink (NCCL), and
 // every shard expands, for every send of every source, the copies for the members it owns:
 //
-//   k_wire_measure    per wire send: local member count x record size (scan input), bucket
-//                     histogram by group
-//   scans             arena offsets of every send's local region; bucket offsets
-//   k_wire_localize   writes the local fan-out descriptor (payload address inside the gathered
-//                     buffer, global sequence offset, local member list) and fills the buckets
-//   k_bucket_sort     orders each group's bucket by global send index (deterministic)
+//   k_wire_table      prefix table over the sources (sends, sequence offsets, section offsets)
+//   k_wire_measure    per wire send: local member count x record size (scan input)
+//   k_bucket_sizes    per (group, source): size of the exporter-built bucket
+//   scans             arena offsets of every send's local region; global bucket offsets
+//   k_wire_localize   writes the local fan-out descriptor (payload address in the exporter's buffer,
+//                     global sequence offset, local member list)
+//   k_bucket_fill     concatenates the sources' buckets in rank order (= global send order)
 //   then the ordinary fan-out kernel + pull index build run over the localized descriptors.
 //
 // NVLink carries (64 + payload) bytes per (send, peer) instead of (32 + payload) per recipient:
@@ -39,6 +40,7 @@ __global__ void k_wire_table(sdb_import_args a, sdb_src_tab* tab) {
     const bool ok = h->magic == SDB_WIRE_MAGIC;
     tab->first[s] = first; tab->rec_base[s] = rb;
     tab->desc_off[s] = ok ? h->desc_off : 0; tab->list_off[s] = ok ? h->list_off : 0; tab->payload_off[s] = ok ? h->payload_off : 0;
+    tab->gs_off_off[s] = (ok && h->max_groups == a.max_groups) ? h->gs_off_off : 0; tab->gs_idx_off[s] = ok ? h->gs_idx_off : 0;
     first += ok ? min(h->n_sends, a.max_sends) : 0u;
     rb += ok ? h->total_recs : 0ull;
   }
@@ -86,14 +88,13 @@ k_wire_measure(sdb_import_args a, uint32_t n_total) {
   } else {
     const uint32_t g = d->group;
     lc = g < a.max_groups ? a.lcount[g] : 0u;
-    if (lc) atomicAdd(a.gs_cnt + g, 1u);
   }
   a.w[gi] = lc * d->rgran;
   a.lw[gi] = own;
 }
 
 __global__ void __launch_bounds__(256)
-k_wire_localize(sdb_import_args a, uint32_t n_total, uint32_t* gs_cur) {
+k_wire_localize(sdb_import_args a, uint32_t n_total) {
   const uint32_t gi = blockIdx.x * blockDim.x + threadIdx.x;
   if (gi >= n_total) return;
   uint32_t src, i; uint64_t rb;
@@ -140,24 +141,40 @@ k_wire_localize(sdb_import_args a, uint32_t n_total, uint32_t* gs_cur) {
   out.mcount = lc;
   out.flags = SDB_DESC_SKIP_SENDER | SDB_DESC_PULL | SDB_DESC_POS;
   a.descs[gi] = out;
-  if (lc) {
-    const uint32_t slot = atomicAdd(gs_cur + g, 1u);
-    a.gs_idx[a.gs_off[g] + slot] = gi;
-  }
 }
 
-// one thread per group: ascending global send index inside the bucket (atomic fill order is arbitrary)
+// The exporter already bucketed its group sends by group (ascending send index).  The global bucket of a
+// group is the concatenation of the sources' buckets in rank order - which is global send order - so no
+// atomics and no sort: sizes per (group, source), one scan, one copy.
+__device__ __forceinline__ const uint32_t* src_gs_off(const sdb_import_args& a, uint32_t s) {
+  return reinterpret_cast<const uint32_t*>(a.meta[s] + a.tab->gs_off_off[s]);
+}
 __global__ void __launch_bounds__(256)
-k_bucket_sort(const uint32_t* __restrict__ gs_off, uint32_t* __restrict__ gs_idx, uint32_t n_groups) {
-  const uint32_t g = blockIdx.x * blockDim.x + threadIdx.x;
-  if (g >= n_groups) return;
-  const uint32_t b = gs_off[g], e = gs_off[g + 1];
-  for (uint32_t i = b + 1; i < e; ++i) {
-    const uint32_t x = gs_idx[i];
-    uint32_t j = i;
-    while (j > b && gs_idx[j - 1] > x) { gs_idx[j] = gs_idx[j - 1]; --j; }
-    gs_idx[j] = x;
+k_bucket_sizes(sdb_import_args a) {
+  const uint32_t idx = blockIdx.x * blockDim.x + threadIdx.x;
+  const uint32_t n = a.max_groups * a.n_src;
+  if (idx > n) return;
+  uint32_t c = 0;
+  if (idx < n) {
+    const uint32_t g = idx / a.n_src, s = idx % a.n_src;
+    if (a.lcount[g] && a.tab->gs_off_off[s]) { const uint32_t* o = src_gs_off(a, s); c = o[g + 1] - o[g]; }
   }
+  a.gs_cnt[idx] = c;
+}
+__global__ void __launch_bounds__(256)
+k_bucket_fill(sdb_import_args a, const uint32_t* __restrict__ goff, uint32_t* __restrict__ gs_off_out) {
+  const uint32_t idx = blockIdx.x * blockDim.x + threadIdx.x;
+  const uint32_t n = a.max_groups * a.n_src;
+  if (idx > n) return;
+  if (idx == n) { gs_off_out[a.max_groups] = goff[n]; return; }
+  const uint32_t g = idx / a.n_src, s = idx % a.n_src;
+  const uint32_t dst = goff[idx];
+  if (s == 0) gs_off_out[g] = dst;
+  if (!a.lcount[g] || !a.tab->gs_off_off[s]) return;
+  const uint32_t* o = src_gs_off(a, s);
+  const uint32_t* ix = reinterpret_cast<const uint32_t*>(a.meta[s] + a.tab->gs_idx_off[s]);
+  const uint32_t b = o[g], e = o[g + 1], first = a.tab->first[s];
+  for (uint32_t k = b; k < e; ++k) a.gs_idx[dst + (k - b)] = first + ix[k];
 }
 
 extern "C" cudaError_t sdb_scan_u32(const uint32_t* in, uint32_t* local, uint32_t* tops, uint32_t n,
@@ -170,11 +187,13 @@ extern "C" cudaError_t sdb_launch_import_measure(const sdb_import_args* a, uint3
                                                  unsigned long long* totals_dev,
                                                  cudaStream_t stream, sdb_profiler* prof, int* n_launches) {
   const int pi = sdb_prof_begin(prof, SDB_PK_XSHARD, stream);
-  cudaMemsetAsync(a->gs_cnt, 0, (static_cast<size_t>(a->max_groups) + 1) * sizeof(uint32_t), stream);
   k_wire_table<<<1, 32, 0, stream>>>(*a, const_cast<sdb_src_tab*>(a->tab));
   k_wire_measure<<<(n_cap + 255) / 256, 256, 0, stream>>>(*a, n_cap);
   cudaError_t e = sdb_scan_u32(a->w, w_local, w_tops, n_cap, totals_dev, nullptr, stream);
-  if (e == cudaSuccess) e = sdb_scan_u32(a->gs_cnt, gs_local, gs_tops, a->max_groups + 1, nullptr, gs_off_out, stream);
+  const uint32_t nb = a->max_groups * a->n_src + 1;
+  k_bucket_sizes<<<(nb + 255) / 256, 256, 0, stream>>>(*a);
+  // gs_off_out here is the materialised scan over (group, source) pairs ("goff", nb entries)
+  if (e == cudaSuccess) e = sdb_scan_u32(a->gs_cnt, gs_local, gs_tops, nb, nullptr, gs_off_out, stream);
   if (e == cudaSuccess) e = sdb_scan_u32(a->lw, lw_local, lw_tops, n_cap, totals_dev + 1, nullptr, stream);   // owned recipients
   sdb_prof_end(prof, pi, stream);
   if (n_launches) *n_launches += 9;
@@ -182,12 +201,13 @@ extern "C" cudaError_t sdb_launch_import_measure(const sdb_import_args* a, uint3
 }
 
 // phase 2: localized descriptors + ordered buckets
-extern "C" cudaError_t sdb_launch_import_localize(const sdb_import_args* a, uint32_t n_cap, uint32_t* gs_cur,
-                                                  cudaStream_t stream, sdb_profiler* prof, int* n_launches) {
+extern "C" cudaError_t sdb_launch_import_localize(const sdb_import_args* a, uint32_t n_cap, const uint32_t* goff,
+                                                  uint32_t* gs_off_out, cudaStream_t stream, sdb_profiler* prof,
+                                                  int* n_launches) {
   const int pi = sdb_prof_begin(prof, SDB_PK_XSHARD, stream);
-  cudaMemsetAsync(gs_cur, 0, static_cast<size_t>(a->max_groups) * sizeof(uint32_t), stream);
-  k_wire_localize<<<(n_cap + 255) / 256, 256, 0, stream>>>(*a, n_cap, gs_cur);
-  k_bucket_sort<<<(a->max_groups + 255) / 256, 256, 0, stream>>>(a->gs_off, a->gs_idx, a->max_groups);
+  k_wire_localize<<<(n_cap + 255) / 256, 256, 0, stream>>>(*a, n_cap);
+  const uint32_t nb = a->max_groups * a->n_src + 1;
+  k_bucket_fill<<<(nb + 255) / 256, 256, 0, stream>>>(*a, goff, gs_off_out);
   sdb_prof_end(prof, pi, stream);
   if (n_launches) *n_launches += 2;
   return cudaGetLastError();
