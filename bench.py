@@ -323,11 +323,10 @@ def run_gpu(args, rank, world, local_rank):
     shard.sync()
     probe = np.random.default_rng(99).permutation(wl.A)[:2200].astype(np.uint32)
     lat = []
-    small_hdr = np.zeros(128, HDR_DTYPE); small_pay = np.zeros(128 * wl.L, np.uint8)
     for k, a in enumerate(probe):
-        one = probe[k:k + 1]
+        ai = int(a)
         t1 = time.perf_counter()
-        c, h, _ = shard.receive_batch(one, 100, 0, copy_out=True, out_hdr=small_hdr, out_payload=small_pay)
+        h, _, _ = shard.receive_one(ai, 100, 0)
         dt = time.perf_counter() - t1
         if k >= 200 and len(h):
             lat.append(dt * 1e6)

@@ -524,14 +524,10 @@ class SwarmsDB:
             return []
         flags = RECV_PRIORITY if self.gpu_config.priority_dequeue else 0
         out: List[Message] = []
-        idx = np.array([self._index(agent_id)], np.uint32)
-        g = self.gpu_config
-        # records per device call: bounded so that the worst-case payload always fits the output buffer
-        cap = max(1, min(g.max_recv_records, g.max_recv_payload // pad32(g.max_payload_bytes)))
+        a = self._index(agent_id)
         remaining = max_messages
         while remaining > 0:
-            k = min(remaining, cap)
-            _, hdr, pay = self.shard.receive_batch(idx, k, flags)
+            hdr, pay, k = self.shard.receive_one(a, remaining, flags)   # single-launch latency path of the C ABI
             if len(hdr) == 0:
                 break
             out.extend(self._decode(hdr, pay, agent_id))

@@ -196,6 +196,7 @@ int build_descs(sdb_ctx* h, uint32_t batch_kind, uint32_t n, SendArrays& a, cons
   uint32_t max_padlen = 0;
   uint32_t n_group_sends = 0, n_other = 0;
   const uint32_t A = h->cfg.max_agents;
+  if (h->sharded) return fail(h, SDB_EINVAL, "sharded handle: sends go through sdb_export_*_batch + sdb_import_wire_*");
   for (uint32_t i = 0; i < n; ++i) {
     sdb_send_desc d;
     std::memset(&d, 0, sizeof(d));

@@ -84,3 +84,19 @@ def test_balancer_surface(tmp_path):
         assert db.llm_backend_loads()["claude"] == 2
     finally:
         db.close()
+
+
+def test_random_interleavings_match_the_pinned_oracle(tmp_path):
+    """Property test on the GPU surface: seeded random op sequences vs the Python oracle (itself pinned
+    to the reference's goldens).  Seeds instead of hypothesis shrinking: device construction is the cost."""
+    from oracle import pyref
+    for seed in range(20, 28):
+        ops = scenarios.scenario_random(seed, n_agents=10 + seed % 7, n_ops=120)
+        want = json.loads(json.dumps(scenarios.run_ops(pyref.OracleSwarmsDB(id_factory=pyref.counter_ids()), ops, pyref)))
+        sdb, db = _db(tmp_path)
+        try:
+            got = json.loads(json.dumps(scenarios.run_ops(db, ops, sdb)))
+        finally:
+            db.close()
+        for i, (g, w) in enumerate(zip(got, want)):
+            assert g == w, (seed, i, ops[i])
