@@ -117,6 +117,9 @@ int sdb_set_stream(sdb_handle h, void* cuda_stream);
 int sdb_sync(sdb_handle h);
 const char* sdb_last_error(sdb_handle h);
 int sdb_get_stats(sdb_handle h, sdb_stats* out);
+/* Test hook: move the (empty) arena's write position, e.g. next to the 2^32-granule boundary where the
+ * 32-bit ring handles wrap.  Only valid while no message is pending. */
+int sdb_debug_set_arena_pos(sdb_handle h, uint64_t granules);
 
 /* Per-kernel device timing (CUDA events on the handle's stream), used by bench.py for the
  * roofline: enable, run, then read accumulated milliseconds and launch counts per kernel class. */

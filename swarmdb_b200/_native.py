@@ -53,7 +53,7 @@ class SdbStats(C.Structure):
 
 
 EXPORTS = ["sdb_abi_version", "sdb_create", "sdb_destroy", "sdb_set_stream", "sdb_sync", "sdb_last_error",
-           "sdb_get_stats", "sdb_profile", "sdb_profile_read", "sdb_register_agents", "sdb_deregister_agents", "sdb_create_group", "sdb_send_batch",
+           "sdb_get_stats", "sdb_debug_set_arena_pos", "sdb_profile", "sdb_profile_read", "sdb_register_agents", "sdb_deregister_agents", "sdb_create_group", "sdb_send_batch",
            "sdb_send_group_batch", "sdb_send_list_batch", "sdb_send_mixed_batch", "sdb_stage_batch", "sdb_submit_staged", "sdb_free_staged",
            "sdb_receive_batch", "sdb_last_receive_dev", "sdb_wire_bytes", "sdb_set_agent_shards",
            "sdb_export_group_batch", "sdb_export_mixed_batch", "sdb_import_wire_batches", "sdb_wire_alloc", "sdb_wire_open",
@@ -81,6 +81,7 @@ def load_library() -> C.CDLL:
     L.sdb_sync.restype = i32; L.sdb_sync.argtypes = [vp]
     L.sdb_last_error.restype = C.c_char_p; L.sdb_last_error.argtypes = [vp]
     L.sdb_get_stats.restype = i32; L.sdb_get_stats.argtypes = [vp, C.POINTER(SdbStats)]
+    L.sdb_debug_set_arena_pos.restype = i32; L.sdb_debug_set_arena_pos.argtypes = [vp, u64]
     L.sdb_profile.restype = i32; L.sdb_profile.argtypes = [vp, i32]
     L.sdb_profile_read.restype = i32; L.sdb_profile_read.argtypes = [vp, vp, vp]
     L.sdb_register_agents.restype = i32; L.sdb_register_agents.argtypes = [vp, u32, vp]
@@ -196,6 +197,9 @@ class Shard:
         s = SdbStats()
         self._check(self._L.sdb_get_stats(self._h, C.byref(s)))
         return {n: int(getattr(s, n)) for n, _ in SdbStats._fields_}
+
+    def debug_set_arena_pos(self, granules: int) -> None:
+        self._check(self._L.sdb_debug_set_arena_pos(self._h, granules))
 
     PROFILE_KINDS = ["p2p", "fanout", "commit", "recv_count", "recv_scan", "recv_select", "recv_gather",
                      "arena_floor", "pick", "xshard", "index"]

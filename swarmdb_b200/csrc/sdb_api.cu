@@ -605,6 +605,16 @@ int sdb_get_stats(sdb_handle h, sdb_stats* out) {
   return SDB_OK;
 }
 
+int sdb_debug_set_arena_pos(sdb_handle h, uint64_t granules) {
+  if (!h) return SDB_EINVAL;
+  sdb_stats st;
+  int rc = sdb_get_stats(h, &st);
+  if (rc != SDB_OK) return rc;
+  if (st.enqueued != st.delivered + 0 && st.enqueued - st.delivered != 0) return fail(h, SDB_EINVAL, "messages pending");
+  h->arena_tail = granules; h->arena_floor = granules;
+  return SDB_OK;
+}
+
 int sdb_register_agents(sdb_handle h, uint32_t n, const uint32_t* agent_idx) {
   if (!h || (n && !agent_idx)) return SDB_EINVAL;
   for (uint32_t i = 0; i < n; ++i) {

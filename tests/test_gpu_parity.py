@@ -238,3 +238,52 @@ def test_backend_select_matches_oracle(mode):
     assert np.array_equal(g.select_backends(5000, cost, mode, seed=7), c.select_backends(5000, cost, mode, seed=7))
     assert np.array_equal(g.backend_loads(), c.backend_loads())
     g.release_backends([0, 1, 1], [1, 2, 3])
+
+
+@pytest.mark.parametrize("max_len", [4096, 8192, 60000])
+def test_large_payloads_all_kernel_variants(max_len):
+    """Payloads above 4 KiB leave the warp-per-send kernel for the CTA-per-send variants."""
+    rng = np.random.default_rng(max_len)
+    A, G = 300, 6
+    for variant in (0, 1, 2):
+        g, c = _pair(A, max_groups=G, fanout_variant=variant, max_payload_bytes=max_len, arena_bytes=1 << 28,
+                     max_batch_sends=64, max_batch_payload=64 * ((max_len + 31) & ~31) + 64, ring_slots=256,
+                     max_recv_records=4096, max_recv_payload=1 << 28)
+        groups = [rng.choice(A, size=int(rng.integers(1, 70)), replace=False) for _ in range(G)]
+        for k, m in enumerate(groups):
+            g.create_group(k, m); c.create_group(k, m)
+        n = 40
+        lens, off, buf = _mk_payloads(rng, n, max_len)
+        lens[0] = max_len; lens[1] = 0
+        s = rng.integers(0, A, n); grp = rng.integers(0, G, n); prio = rng.integers(0, 4, n)
+        assert g.send_group_batch(s, grp, prio, None, lens, off, buf) == c.send_group_batch(s, grp, prio, None, lens, off, buf)[0]
+        r = rng.integers(0, A, n)
+        g.send_batch(s, r, prio, None, lens, off, buf); c.send_batch(s, r, prio, None, lens, off, buf)
+        idx = np.arange(A, dtype=np.uint32)
+        _same(g.receive_batch(idx, 3), c.receive_batch(idx, 3, pay_cap=1 << 29))
+        _same(g.receive_batch(idx, 1000), c.receive_batch(idx, 1000, pay_cap=1 << 29))
+        g.close(); c.close()
+
+
+def test_ring_handles_wrap_at_2_pow_32_granules():
+    """Ring handles are the low 32 bits of the arena position: run batches across the 2^32 boundary."""
+    rng = np.random.default_rng(77)
+    A, G = 500, 8
+    g, c = _pair(A, max_groups=G, arena_bytes=1 << 24, ring_slots=512)
+    groups = [rng.choice(A, size=40, replace=False) for _ in range(G)]
+    for k, m in enumerate(groups):
+        g.create_group(k, m); c.create_group(k, m)
+    g.debug_set_arena_pos((1 << 32) - 20000)             # ~20k granules before the handles wrap
+    idx = np.arange(A, dtype=np.uint32)
+    from swarmdb_b200._native import RECV_PRIORITY
+    for step in range(6):
+        n = 60
+        lens, off, buf = _mk_payloads(rng, n, 200)
+        s = rng.integers(0, A, n); grp = rng.integers(0, G, n); prio = rng.integers(0, 4, n)
+        g.send_group_batch(s, grp, prio, None, lens, off, buf); c.send_group_batch(s, grp, prio, None, lens, off, buf)
+        r = rng.integers(0, A, 200); l2, o2, b2 = _mk_payloads(rng, 200, 64); s2 = rng.integers(0, A, 200)
+        g.send_batch(s2, r, None, None, l2, o2, b2); c.send_batch(s2, r, None, None, l2, o2, b2)
+        flags = RECV_PRIORITY if step % 2 else 0
+        _same(g.receive_batch(idx, 4, flags), c.receive_batch(idx, 4, flags))       # leaves a backlog that straddles the wrap
+    _same(g.receive_batch(idx, 10000), c.receive_batch(idx, 10000))
+    assert g.stats()["arena_tail_bytes"] > (1 << 32) * 32
