@@ -212,17 +212,8 @@ k_group_fanout_tma(sdb_dev_view v, const sdb_send_desc* __restrict__ descs, uint
 //   payload size.  When the chunk count divides 32 the lane's chunk never changes and is held in
 //   a register.  ~3 warp-instructions per routed message instead of ~75 for variant A.
 // ------------------------------------------------------------------------------------------
-__device__ __forceinline__ void st_header(uint8_t* rec, uint64_t seq, double ts, uint32_t sender, uint32_t rcv,
-                                          uint32_t group, uint16_t len, uint8_t prio, uint8_t type) {
-  const uint4 lo = sdb_header_lo(seq, ts);
-  const uint4 hi = sdb_header_hi(sender, rcv, group, len, prio, type);
-  asm volatile("st.global.L1::no_allocate.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};"
-               :: "l"(rec), "r"(lo.x), "r"(lo.y), "r"(lo.z), "r"(lo.w), "r"(hi.x), "r"(hi.y), "r"(hi.z), "r"(hi.w)
-               : "memory");
-}
-
 template <int WARPS>
-__global__ void __launch_bounds__(WARPS * 32)
+__global__ void __launch_bounds__(WARPS * 32, 6)
 k_group_fanout_warp(sdb_dev_view v, const sdb_send_desc* __restrict__ descs, uint32_t n,
                     const uint8_t* __restrict__ payload, const uint32_t* __restrict__ tmp_list,
                     uint64_t seq_base, uint64_t arena_base, uint32_t stage_bytes) {
@@ -330,34 +321,37 @@ k_group_fanout_warp(sdb_dev_view v, const sdb_send_desc* __restrict__ descs, uin
       uint8_t* const tb = base + static_cast<size_t>(tile) * rbytes;
       const uint64_t seq0 = seq_base + d.rec0;
       const uint4 hdr_hi = sdb_header_hi(d.sender, SDB_NO_RECEIVER, d.group, d.len, d.prio, d.type);
+      // record j occupies chunks [j*PC, (j+1)*PC) of the send's region, so flat chunk f lands at tb + 16 f
+      uint8_t* dst = tb + (static_cast<size_t>(lane) << 4);
+      const bool all_in = (nrec <= 32u) ? (m0 == (nrec == 32u ? 0xFFFFFFFFu : ((1u << nrec) - 1u)))
+                                        : (m0 == 0xFFFFFFFFu && m1 == (nrec == 64u ? 0xFFFFFFFFu : ((1u << (nrec - 32u)) - 1u)));
       if (nrec <= 32u) {
         // narrow sends (few local members, e.g. one shard's share of a group): one shuffle pair per step
-        for (uint32_t done = 0; done < total; done += 32) {
+        for (uint32_t done = 0; done < total; done += 32, dst += 512) {
           const uint32_t src = rec & 31u;
           const uint32_t ra = __shfl_sync(0xFFFFFFFFu, a0, src), rp = __shfl_sync(0xFFFFFFFFu, p0, src);
-          if (rec < nrec && ((m0 >> src) & 1u)) {
+          if (rec < nrec && (all_in || ((m0 >> src) & 1u))) {
             uint4 x;
-            if (ch == 0) x = sdb_header_lo(seq0 + (shared_seq ? 0u : rp), d.timestamp);
-            else if (ch == 1) { x = hdr_hi; if (!shared_seq) x.y = ra; }
-            else x = my4[ch - 2u];
-            sdb_st_stream_pol(tb + static_cast<size_t>(rec) * rbytes + (ch << 4), x, pol_stream);
+            if (ch >= 2u) x = my4[ch - 2u];
+            else if (ch == 0) x = sdb_header_lo(seq0 + (shared_seq ? 0u : rp), d.timestamp);
+            else { x = hdr_hi; if (!shared_seq) x.y = ra; }
+            sdb_st_stream_pol(dst, x, pol_stream);
           }
           ch += r32; rec += q32;
           if (ch >= PC) { ch -= PC; ++rec; }
         }
       } else {
-        for (uint32_t done = 0; done < total; done += 32) {
+        for (uint32_t done = 0; done < total; done += 32, dst += 512) {
           const uint32_t src = rec & 31u;
           const uint32_t ra0 = __shfl_sync(0xFFFFFFFFu, a0, src), ra1 = __shfl_sync(0xFFFFFFFFu, a1, src);
           const uint32_t rp0 = __shfl_sync(0xFFFFFFFFu, p0, src), rp1 = __shfl_sync(0xFFFFFFFFu, p1, src);
           const bool lo_half = rec < 32u;
-          const uint32_t bit = ((lo_half ? m0 : m1) >> src) & 1u;
-          if (rec < nrec && bit) {
+          if (rec < nrec && (all_in || (((lo_half ? m0 : m1) >> src) & 1u))) {
             uint4 x;
-            if (ch == 0) x = sdb_header_lo(seq0 + (shared_seq ? 0u : (lo_half ? rp0 : rp1)), d.timestamp);
-            else if (ch == 1) { x = hdr_hi; if (!shared_seq) x.y = lo_half ? ra0 : ra1; }
-            else x = my4[ch - 2u];
-            sdb_st_stream_pol(tb + static_cast<size_t>(rec) * rbytes + (ch << 4), x, pol_stream);
+            if (ch >= 2u) x = my4[ch - 2u];
+            else if (ch == 0) x = sdb_header_lo(seq0 + (shared_seq ? 0u : (lo_half ? rp0 : rp1)), d.timestamp);
+            else { x = hdr_hi; if (!shared_seq) x.y = lo_half ? ra0 : ra1; }
+            sdb_st_stream_pol(dst, x, pol_stream);
           }
           ch += r32; rec += q32;
           if (ch >= PC) { ch -= PC; ++rec; }
