@@ -207,6 +207,7 @@ int sdb_free_staged(sdb_handle h, sdb_staged_t s);
  * queued), never dropped.
  */
 #define SDB_RECV_PRIORITY 1u
+#define SDB_RECV_PEEK 2u                /* return what a receive would deliver, retire nothing (history snapshots, M:852-892) */
 int sdb_receive_batch(sdb_handle h, uint32_t n_agents, const uint32_t* agent_idx,
                       uint32_t max_messages, uint32_t flags,
                       uint32_t* count_out, sdb_msg_header* hdr_out, uint64_t hdr_cap,

@@ -23,6 +23,7 @@ assert HDR_DTYPE.itemsize == 32
 NO_GROUP = 0xFFFFFFFF
 NO_RECEIVER = 0xFFFFFFFF
 RECV_PRIORITY = 1
+RECV_PEEK = 2
 TYPEF_JSON = 0x08
 TYPEF_EXTRAS = 0x10
 TYPE_MASK = 0x07

@@ -38,7 +38,7 @@ import numpy as np
 from pydantic import BaseModel, Field
 
 from . import _native
-from ._native import NO_GROUP, RECV_PRIORITY, TYPE_MASK, TYPEF_EXTRAS, TYPEF_JSON, SdbError, Shard, pad32
+from ._native import NO_GROUP, RECV_PEEK, RECV_PRIORITY, TYPE_MASK, TYPEF_EXTRAS, TYPEF_JSON, SdbError, Shard, pad32
 
 try:  # the reference logs through loguru; keep the same logger object when it is installed
     from loguru import logger
@@ -536,7 +536,41 @@ class SwarmsDB:
                 break
         return out
 
-    def _decode(self, hdr: np.ndarray, pay: np.ndarray, agent_id: str) -> List[Message]:
+    def peek_messages(self, agent_id: str, max_messages: int = 100) -> List[Message]:
+        """What `receive_messages` would return next, without consuming it (device PEEK receive)."""
+        self.flush()
+        flags = RECV_PEEK | (RECV_PRIORITY if self.gpu_config.priority_dequeue else 0)
+        hdr, pay, _ = self.shard.receive_one(self._index(agent_id), max_messages, flags)
+        return self._decode(hdr, pay, agent_id, record=False, status=MessageStatus.DELIVERED)
+
+    def pending_snapshot(self, per_agent: int = 1024) -> Dict[str, List[Message]]:
+        """Every message still queued on the device, per agent, in delivery order (non-destructive).
+        This is the D2H ring dump behind `save_message_history(include_device=True)`."""
+        self.flush()
+        n = len(self._agent_name)
+        out: Dict[str, List[Message]] = {}
+        if n == 0:
+            return out
+        idx = np.arange(n, dtype=np.uint32)
+        g = self.gpu_config
+        chunk = max(1, min(n, g.max_recv_records // max(per_agent, 1)))
+        flags = RECV_PEEK | (RECV_PRIORITY if g.priority_dequeue else 0)
+        for b in range(0, n, chunk):
+            part = idx[b:b + chunk]
+            counts, hdr, pay = self.shard.receive_batch(part, per_agent, flags)
+            offs = _native.payload_offsets(hdr)
+            pos = 0
+            for a, c in zip(part, counts):
+                c = int(c)
+                if c:
+                    name = self._agent_name[int(a)]
+                    sub_pay = pay[int(offs[pos]):] if pos < len(offs) else pay[:0]
+                    out[name] = self._decode(hdr[pos:pos + c], sub_pay, name, record=False, status=MessageStatus.DELIVERED)
+                pos += c
+        return out
+
+    def _decode(self, hdr: np.ndarray, pay: np.ndarray, agent_id: str, record: bool = True,
+                status: MessageStatus = MessageStatus.READ) -> List[Message]:
         msgs: List[Message] = []
         offs = _native.payload_offsets(hdr)
         raw = pay.tobytes()
@@ -559,9 +593,10 @@ class SwarmsDB:
             m = Message(id=self._make_id(int(h["seq"])), sender_id=self._agent_name[int(h["sender"])],
                         receiver_id=None if receiver == _native.NO_RECEIVER else self._agent_name[receiver],
                         content=content, type=_TYPE_BY_CODE[t & TYPE_MASK], priority=MessagePriority(int(h["prio"])),
-                        timestamp=float(h["timestamp"]), status=MessageStatus.READ, metadata=metadata,
+                        timestamp=float(h["timestamp"]), status=status, metadata=metadata,
                         token_count=extras.get("t"), visible_to=list(extras.get("v", [])))
-            self.messages[m.id] = m                        # M:587-588
+            if record:
+                self.messages[m.id] = m                    # M:587-588
             msgs.append(m)
         return msgs
 
@@ -748,18 +783,31 @@ class SwarmsDB:
         return len(old)
 
     # ------------------------------------------------------------------ history (schema of M:878-884)
-    def _history(self) -> Dict[str, Any]:
-        return {"messages": {mid: m.to_dict() for mid, m in self.messages.items()},
-                "agent_inbox": self.agent_inbox, "registered_agents": list(self.registered_agents),
-                "timestamp": time.time(), "message_count": self.message_count}
+    def _history(self, include_device: bool = False) -> Dict[str, Any]:
+        messages = {mid: m.to_dict() for mid, m in self.messages.items()}
+        inbox = self.agent_inbox
+        if include_device:
+            # messages that only exist on the device (bulk index-level sends have no host record): add the
+            # pending ones to the same schema (M:878-884) so a history file is complete
+            inbox = {a: list(v) for a, v in self.agent_inbox.items()}
+            for agent, pend in self.pending_snapshot().items():
+                box = inbox.setdefault(agent, [])
+                have = set(box)
+                for m in pend:
+                    if m.id not in messages:
+                        messages[m.id] = m.to_dict()
+                    if m.id not in have:
+                        box.append(m.id); have.add(m.id)
+        return {"messages": messages, "agent_inbox": inbox, "registered_agents": list(self.registered_agents),
+                "timestamp": time.time(), "message_count": max(self.message_count, len(messages))}
 
-    def save_message_history(self, filename: Optional[str] = None) -> None:
+    def save_message_history(self, filename: Optional[str] = None, include_device: bool = False) -> None:
         if not filename:
             stamp = datetime.datetime.now().strftime("%Y%m%d_%H%M%S")
             filename = f"message_history_{stamp}_{self.message_count}.json"
         try:
             with open(self.save_dir / filename, "w") as f:
-                json.dump(self._history(), f, indent=2)
+                json.dump(self._history(include_device), f, indent=2)
             self.last_save_time = time.time()
         except Exception as e:
             logger.error(f"Failed to save message history: {e}")

@@ -155,7 +155,7 @@ __device__ __forceinline__ uint32_t lane_prefix(uint32_t ballot, uint32_t lane) 
 // output index RO.., retire them (advance head / tombstone).  Stream order when !prio_mode.
 __device__ __forceinline__ void select_agent_warp(const sdb_dev_view& v, uint32_t* plan_handle, uint32_t* plan_glen,
                                                   bool prio_mode, uint32_t A, uint32_t H, uint32_t T, uint32_t NT,
-                                                  uint32_t C, uint32_t RO, uint32_t lane) {
+                                                  uint32_t C, uint32_t RO, uint32_t lane, bool retire) {
   const uint32_t mask = v.ring_slots - 1;
     uint16_t* ms = v.ring_meta + (static_cast<size_t>(A) << v.ring_shift);
     const uint32_t* hs = v.ring_handle + (static_cast<size_t>(A) << v.ring_shift);
@@ -166,7 +166,7 @@ __device__ __forceinline__ void select_agent_warp(const sdb_dev_view& v, uint32_
         plan_handle[RO + j] = hs[(H + j) & mask];
         plan_glen[RO + j] = (ms[(H + j) & mask] & SDB_META_GLEN_MASK) - 1u;
       }
-      if (lane == 0) reinterpret_cast<uint32_t*>(v.ring_state + A)[0] = H + C;
+      if (lane == 0 && retire) reinterpret_cast<uint32_t*>(v.ring_state + A)[0] = H + C;
       return;
     }
     // ---- pass 1: histogram of live entries per priority level over the window [H, T)
@@ -250,7 +250,7 @@ __device__ __forceinline__ void select_agent_warp(const sdb_dev_view& v, uint32_
       if (sel) {
         plan_handle[RO + rank] = hs[p & mask];
         plan_glen[RO + rank] = (m & SDB_META_GLEN_MASK) - 1u;
-        ms[p & mask] = SDB_META_TOMB;                      // retire
+        if (retire) ms[p & mask] = SDB_META_TOMB;
       }
       const uint32_t bs = __ballot_sync(0xFFFFFFFFu, sel);
       got += __popc(bs);
@@ -260,7 +260,7 @@ __device__ __forceinline__ void select_agent_warp(const sdb_dev_view& v, uint32_
     const uint32_t scan_end = static_cast<int32_t>(T - p0) > 0 ? p0 : T;
     uint32_t nh = first_unsel;
     if (static_cast<int32_t>(nh - scan_end) > 0) nh = scan_end;
-    if (lane == 0) {
+    if (lane == 0 && retire) {
       reinterpret_cast<uint32_t*>(v.ring_state + A)[0] = nh;
       v.ntomb[A] = NT + got - (nh - H);
     }
@@ -306,12 +306,12 @@ k_recv_select(sdb_dev_view v, sdb_recv_args r) {
       for (uint32_t j = 0; j < CH; ++j)
         if (b + j < cnt) { r.plan_handle[roff + b + j] = hv[j]; r.plan_glen[roff + b + j] = (mv[j] & SDB_META_GLEN_MASK) - 1u; }
     }
-    reinterpret_cast<uint32_t*>(v.ring_state + a)[0] = head + cnt;    // low word = head (little endian)
+    if (!(r.flags & SDB_RECV_PEEK)) reinterpret_cast<uint32_t*>(v.ring_state + a)[0] = head + cnt;    // low word = head (little endian)
   }
   // everything else (long runs, holes, priority order) goes to the warp-per-agent kernel
   const bool big = valid && cnt && !small;
   const uint32_t todo = __ballot_sync(0xFFFFFFFFu, big);
-  uint32_t n_deliv = valid ? cnt : 0;
+  uint32_t n_deliv = (valid && !(r.flags & SDB_RECV_PEEK)) ? cnt : 0;
   if (todo) {
     uint32_t basew = 0;
     if (lane == 0) basew = atomicAdd(r.big_count, static_cast<uint32_t>(__popc(todo)));
@@ -337,7 +337,7 @@ k_recv_select_big(sdb_dev_view v, sdb_recv_args r) {
     const uint32_t roff = r.rec_local[q] + r.rec_tops[q / SDB_SCAN_TILE];
     const uint64_t st = v.ring_state[a];
     select_agent_warp(v, r.plan_handle, r.plan_glen, prio_mode, a, static_cast<uint32_t>(st),
-                      static_cast<uint32_t>(st >> 32), v.ntomb[a], cnt, roff, lane);
+                      static_cast<uint32_t>(st >> 32), v.ntomb[a], cnt, roff, lane, !(r.flags & SDB_RECV_PEEK));
   }
 }
 
@@ -466,7 +466,8 @@ k_recv_small(sdb_dev_view v, sdb_small_agents ag, uint32_t n, uint32_t max_messa
   if (cnt) {
     const uint32_t H = __shfl_sync(0xFFFFFFFFu, head, 0), T = __shfl_sync(0xFFFFFFFFu, tail, 0);
     const uint32_t NT = __shfl_sync(0xFFFFFFFFu, nt, 0);
-    select_agent_warp(v, plan_handle, plan_glen, (flags & SDB_RECV_PRIORITY) != 0, a, H, T, NT, cnt, roff, lane);
+    select_agent_warp(v, plan_handle, plan_glen, (flags & SDB_RECV_PRIORITY) != 0, a, H, T, NT, cnt, roff, lane,
+                      !(flags & SDB_RECV_PEEK));
   }
   __syncthreads();
   const uint32_t total = s_total;
@@ -485,7 +486,7 @@ k_recv_small(sdb_dev_view v, sdb_small_agents ag, uint32_t n, uint32_t max_messa
       s_goff[total] = run;
       reinterpret_cast<unsigned long long*>(out)[0] = total;
       reinterpret_cast<unsigned long long*>(out)[1] = run;
-      if (total) atomicAdd(&v.ctr->delivered, static_cast<unsigned long long>(total));
+      if (total && !(flags & SDB_RECV_PEEK)) atomicAdd(&v.ctr->delivered, static_cast<unsigned long long>(total));
     }
   }
   __syncthreads();

@@ -100,3 +100,42 @@ def test_random_interleavings_match_the_pinned_oracle(tmp_path):
             db.close()
         for i, (g, w) in enumerate(zip(got, want)):
             assert g == w, (seed, i, ops[i])
+
+
+def test_peek_and_device_history_snapshot(tmp_path):
+    """N2: non-destructive device dump -> history file in the reference's schema (M:878-884)."""
+    sdb, db = _db(tmp_path)
+    try:
+        db.add_agent_group("g", ["a", "b", "c"])
+        db.send_to_group("s", "g", "hello", metadata={"k": 1})
+        db.send_message("s", {"x": [1, 2]}, "a", priority=sdb.MessagePriority.HIGH)
+        peek = db.peek_messages("a")
+        assert [m.content for m in peek] == ["hello", {"x": [1, 2]}] and peek[0].status == sdb.MessageStatus.DELIVERED
+        assert [m.content for m in db.peek_messages("a", 1)] == ["hello"]          # nothing was consumed
+        # bulk, index-level sends leave no host-side Message objects: only the device knows them
+        import numpy as np
+        ia, ib = db.agent_index("a"), db.agent_index("b")
+        buf = np.frombuffer(b"bulk-one" + bytes(24) + b"bulk-two" + bytes(24), np.uint8)
+        db.send_batch([ib, ib], [ia, ia], [1, 1], [0, 0], [8, 8], [0, 32], buf)
+        snap = db.pending_snapshot()
+        assert [m.content for m in snap["a"]] == ["hello", {"x": [1, 2]}, "bulk-one", "bulk-two"]
+        assert [m.content for m in snap["b"]] == ["hello"] and "s" not in snap
+        db.save_message_history("h.json", include_device=True)
+        doc = json.loads((tmp_path / "h.json").read_text())
+        assert set(doc) == {"messages", "agent_inbox", "registered_agents", "timestamp", "message_count"}
+        assert len(doc["agent_inbox"]["a"]) == 4 and len(doc["messages"]) == 6
+        one = next(iter(doc["messages"].values()))
+        assert list(one) == ["id", "sender_id", "receiver_id", "content", "type", "priority", "timestamp", "status",
+                             "metadata", "token_count", "visible_to"]          # field order of M:54-82
+        # the snapshot consumed nothing
+        assert [m.content for m in db.receive_messages("a")] == ["hello", {"x": [1, 2]}, "bulk-one", "bulk-two"]
+        # and a fresh instance can load the file (M:894-934)
+        sdb2, db2 = _db(tmp_path / "second")
+        try:
+            db2.load_message_history(tmp_path / "h.json")
+            assert db2.message_count == doc["message_count"] and "a" in db2.registered_agents
+            assert len(db2.messages) == 6
+        finally:
+            db2.close()
+    finally:
+        db.close()
