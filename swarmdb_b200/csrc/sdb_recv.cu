@@ -322,22 +322,102 @@ k_recv_select(sdb_dev_view v, sdb_recv_args r) {
   if (lane == 0 && n_deliv) atomicAdd(&v.ctr->delivered, static_cast<unsigned long long>(n_deliv));
 }
 
+// Single-pass bounded selection (priority order, or stream order with holes) for C <= SDB_CAND:
+// walk the window once in arrival order keeping, per level, the first C live positions (stable,
+// ballot-prefix ranks) in shared memory; stop as soon as the top level alone fills the quota -
+// with mixed priorities that happens after a few hundred entries instead of the whole window.
+#define SDB_CAND 128u
+__device__ __forceinline__ void select_agent_warp_bounded(const sdb_dev_view& v, uint32_t* plan_handle, uint32_t* plan_glen,
+                                                          bool prio_mode, uint32_t A, uint32_t H, uint32_t T, uint32_t NT,
+                                                          uint32_t C, uint32_t RO, uint32_t lane, bool retire,
+                                                          uint32_t (*cand)[SDB_CAND]) {
+  const uint32_t mask = v.ring_slots - 1;
+  uint16_t* ms = v.ring_meta + (static_cast<size_t>(A) << v.ring_shift);
+  const uint32_t* hs = v.ring_handle + (static_cast<size_t>(A) << v.ring_shift);
+  const uint32_t top = prio_mode ? 3u : 0u;
+  uint32_t cnt[4] = {0, 0, 0, 0};
+  uint32_t p0 = H;
+  while (static_cast<int32_t>(T - p0) > 0 && cnt[top] < C) {
+    // four chunks of 32 entries in flight per step (the loads do not depend on the running counts)
+    uint16_t mm[4];
+#pragma unroll
+    for (uint32_t u = 0; u < 4; ++u) {
+      const uint32_t p = p0 + u * 32u + lane;
+      mm[u] = static_cast<int32_t>(T - p) > 0 ? ms[p & mask] : SDB_META_TOMB;
+    }
+#pragma unroll
+    for (uint32_t u = 0; u < 4; ++u) {
+      if (static_cast<int32_t>(T - p0) <= 0 || cnt[top] >= C) break;       // warp-uniform
+      const uint32_t p = p0 + lane;
+      const uint16_t m = mm[u];
+      const bool live = m != SDB_META_TOMB;
+      const uint32_t L = (live && prio_mode) ? (m >> 14) : 0u;
+#pragma unroll
+      for (uint32_t lev = 0; lev < 4; ++lev) {
+        const uint32_t b = __ballot_sync(0xFFFFFFFFu, live && L == lev);
+        if (live && L == lev) {
+          const uint32_t k = cnt[lev] + lane_prefix(b, lane);
+          if (k < C) cand[lev][k] = p;
+        }
+        cnt[lev] += __popc(b);
+      }
+      p0 += 32;
+    }
+  }
+  const uint32_t scan_end = static_cast<int32_t>(T - p0) > 0 ? p0 : T;
+  __syncwarp();
+  // quotas: everything of the higher levels first, then the first entries of the cut level
+  uint32_t need = C, acc = 0, got = 0;
+  for (int lev = 3; lev >= 0; --lev) {
+    const uint32_t have = min(cnt[lev], C);
+    const uint32_t take = min(have, need);
+    for (uint32_t k = lane; k < take; k += 32) {
+      const uint32_t p = cand[lev][k];
+      plan_handle[RO + acc + k] = hs[p & mask];
+      plan_glen[RO + acc + k] = (ms[p & mask] & SDB_META_GLEN_MASK) - 1u;
+      if (retire) ms[p & mask] = SDB_META_TOMB;
+    }
+    acc += take; need -= take; got += take;
+  }
+  if (!retire) return;
+  __syncwarp();
+  // new head: first live entry left behind inside the scanned range (the tombstones just written count as consumed)
+  uint32_t nh = scan_end;
+  for (uint32_t q0 = H; static_cast<int32_t>(scan_end - q0) > 0; q0 += 32) {
+    const uint32_t p = q0 + lane;
+    const bool live = static_cast<int32_t>(scan_end - p) > 0 && ms[p & mask] != SDB_META_TOMB;
+    const uint32_t b = __ballot_sync(0xFFFFFFFFu, live);
+    if (b) { nh = q0 + (__ffs(b) - 1); break; }
+  }
+  if (lane == 0) {
+    reinterpret_cast<uint32_t*>(v.ring_state + A)[0] = nh;
+    v.ntomb[A] = NT + got - (nh - H);
+  }
+}
+
 // warp per listed agent (persistent grid-stride over the worklist built by k_recv_select)
 __global__ void __launch_bounds__(256)
 k_recv_select_big(sdb_dev_view v, sdb_recv_args r) {
   const uint32_t lane = threadIdx.x & 31;
   const uint32_t gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const uint32_t nw = (gridDim.x * blockDim.x) >> 5;
+  __shared__ uint32_t s_cand[8][4][SDB_CAND];            // per warp: first C positions of each level
   const uint32_t n_big = *r.big_count;
   const bool prio_mode = (r.flags & SDB_RECV_PRIORITY) != 0;
+  const bool retire = !(r.flags & SDB_RECV_PEEK);
   for (uint32_t w = gw; w < n_big; w += nw) {
     const uint32_t q = r.big_list[w];
     const uint32_t a = r.agent_idx ? r.agent_idx[q] : q;
     const uint32_t cnt = r.count_out[q];
     const uint32_t roff = r.rec_local[q] + r.rec_tops[q / SDB_SCAN_TILE];
     const uint64_t st = v.ring_state[a];
-    select_agent_warp(v, r.plan_handle, r.plan_glen, prio_mode, a, static_cast<uint32_t>(st),
-                      static_cast<uint32_t>(st >> 32), v.ntomb[a], cnt, roff, lane, !(r.flags & SDB_RECV_PEEK));
+    const uint32_t H = static_cast<uint32_t>(st), T = static_cast<uint32_t>(st >> 32), NT = v.ntomb[a];
+    if (cnt <= SDB_CAND && (prio_mode || NT != 0))
+      select_agent_warp_bounded(v, r.plan_handle, r.plan_glen, prio_mode, a, H, T, NT, cnt, roff, lane, retire,
+                                s_cand[threadIdx.x >> 5]);
+    else
+      select_agent_warp(v, r.plan_handle, r.plan_glen, prio_mode, a, H, T, NT, cnt, roff, lane, retire);
+    __syncwarp();
   }
 }
 
