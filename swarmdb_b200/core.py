@@ -244,7 +244,8 @@ class SwarmsDB:
         return self._index(agent_id)
 
     def _make_id(self, seq: int) -> str:
-        return str(uuid.UUID(int=self._id_hi | seq))
+        h = "%032x" % (self._id_hi | seq)                 # same text as str(uuid.UUID(int=...)), 4x cheaper
+        return f"{h[:8]}-{h[8:12]}-{h[12:16]}-{h[16:20]}-{h[20:]}"
 
     def _count_tokens(self, content: Any) -> int:          # M:295-307
         if self.token_counter is None:
@@ -339,9 +340,14 @@ class SwarmsDB:
         token_count = self._count_tokens(content) if self.token_counter else None
 
         seq = self._next_seq
-        message = Message(id=self._make_id(seq), sender_id=sender_id, receiver_id=receiver_id, content=content,
-                          type=message_type, priority=priority, metadata=metadata or {}, token_count=token_count,
-                          visible_to=visible_to or [])
+        if not isinstance(content, (str, dict, list)):
+            raise TypeError("content must be str, dict or list")
+        # fields are normalised here, so pydantic's per-field validation (14 % of the reference's send cost) is skipped
+        message = Message.model_construct(
+            id=self._make_id(seq), sender_id=str(sender_id), receiver_id=receiver_id, content=content,
+            type=MessageType(message_type), priority=MessagePriority(priority), timestamp=time.time(),
+            status=MessageStatus.PENDING, metadata=dict(metadata or {}), token_count=token_count,
+            visible_to=list(visible_to or []))
         if receiver_id is None and not message.visible_to:
             message.visible_to = list(self.registered_agents)           # M:449-450
 
@@ -487,6 +493,9 @@ class SwarmsDB:
             payload = body
         base = self._next_seq
         now = time.time()
+        mtype, mprio = MessageType(message_type), MessagePriority(priority)
+        if not isinstance(content, (str, dict, list)):
+            raise TypeError("content must be str, dict or list")
         ids: List[str] = []
         staged = False
         for j, agent_id in enumerate(members):
@@ -494,9 +503,10 @@ class SwarmsDB:
                 continue
             if agent_id not in self.registered_agents:
                 self.register_agent(agent_id)
-            m = Message(id=self._make_id(base + j), sender_id=sender_id, receiver_id=agent_id, content=content,
-                        type=message_type, priority=priority, metadata=dict(msg_metadata), token_count=token_count,
-                        timestamp=now, status=MessageStatus.DELIVERED)
+            m = Message.model_construct(
+                id=self._make_id(base + j), sender_id=str(sender_id), receiver_id=agent_id, content=content,
+                type=mtype, priority=mprio, metadata=dict(msg_metadata), token_count=token_count,
+                timestamp=now, status=MessageStatus.DELIVERED, visible_to=[])
             self.messages[m.id] = m
             self.message_count += 1
             self.agent_inbox[agent_id].append(m.id)
@@ -572,12 +582,19 @@ class SwarmsDB:
     def _decode(self, hdr: np.ndarray, pay: np.ndarray, agent_id: str, record: bool = True,
                 status: MessageStatus = MessageStatus.READ) -> List[Message]:
         msgs: List[Message] = []
-        offs = _native.payload_offsets(hdr)
+        n = len(hdr)
+        if n == 0:
+            return msgs
+        offs = _native.payload_offsets(hdr).tolist()
         raw = pay.tobytes()
-        for k in range(len(hdr)):
-            h = hdr[k]
-            blob = raw[int(offs[k]): int(offs[k]) + int(h["len"])]
-            t = int(h["type"])
+        # column-wise conversion once: per-record structured-array field access dominates otherwise
+        seqs, lens, types, prios = hdr["seq"].tolist(), hdr["len"].tolist(), hdr["type"].tolist(), hdr["prio"].tolist()
+        senders, receivers, groups, stamps = (hdr["sender"].tolist(), hdr["receiver"].tolist(), hdr["group"].tolist(),
+                                              hdr["timestamp"].tolist())
+        names = self._agent_name
+        for k in range(n):
+            blob = raw[offs[k]: offs[k] + lens[k]]
+            t = types[k]
             extras: Dict[str, Any] = {}
             if t & TYPEF_EXTRAS:
                 clen = int.from_bytes(blob[:4], "little")
@@ -585,16 +602,17 @@ class SwarmsDB:
             else:
                 body = blob
             content: Any = json.loads(body.decode("utf-8")) if t & TYPEF_JSON else body.decode("utf-8")
-            metadata = dict(extras.get("m", {}))
-            grp = int(h["group"])
+            metadata = dict(extras.get("m", {})) if extras else {}
+            grp = groups[k]
             if grp != NO_GROUP:
                 metadata["group"] = self._group_name[grp]
-            receiver = int(h["receiver"])
-            m = Message(id=self._make_id(int(h["seq"])), sender_id=self._agent_name[int(h["sender"])],
-                        receiver_id=None if receiver == _native.NO_RECEIVER else self._agent_name[receiver],
-                        content=content, type=_TYPE_BY_CODE[t & TYPE_MASK], priority=MessagePriority(int(h["prio"])),
-                        timestamp=float(h["timestamp"]), status=status, metadata=metadata,
-                        token_count=extras.get("t"), visible_to=list(extras.get("v", [])))
+            receiver = receivers[k]
+            m = Message.model_construct(
+                id=self._make_id(seqs[k]), sender_id=names[senders[k]],
+                receiver_id=None if receiver == _native.NO_RECEIVER else names[receiver],
+                content=content, type=_TYPE_BY_CODE[t & TYPE_MASK], priority=MessagePriority(prios[k]),
+                timestamp=stamps[k], status=status, metadata=metadata,
+                token_count=extras.get("t") if extras else None, visible_to=list(extras.get("v", [])) if extras else [])
             if record:
                 self.messages[m.id] = m                    # M:587-588
             msgs.append(m)

@@ -20,7 +20,7 @@ extern "C" {
 cudaError_t sdb_launch_p2p(const sdb_dev_view*, const sdb_send_desc*, uint32_t, const uint8_t*, uint64_t, uint64_t, int, cudaStream_t, sdb_profiler*);
 cudaError_t sdb_launch_fanout(const sdb_dev_view*, const sdb_send_desc*, uint32_t, const uint8_t*, const uint32_t*,
                               uint64_t, uint64_t, uint32_t, int, int, cudaStream_t, sdb_profiler*);
-cudaError_t sdb_launch_commit(const sdb_dev_view*, uint32_t, uint32_t, cudaStream_t, sdb_profiler*);
+cudaError_t sdb_launch_commit(const sdb_dev_view*, uint32_t, uint32_t, uint32_t*, uint32_t*, int, cudaStream_t, sdb_profiler*);
 cudaError_t sdb_launch_pull(const sdb_dev_view*, const sdb_pull_view*, const sdb_send_desc*, uint32_t, uint64_t, int,
                             cudaStream_t, sdb_profiler*);
 cudaError_t sdb_launch_receive(const sdb_dev_view*, const sdb_recv_args*, cudaStream_t, int*, sdb_profiler*, int);
@@ -344,8 +344,8 @@ int submit(sdb_ctx* h, const sdb_staged* s, uint64_t* seq_base_out) {
     h->launches += 1;
   }
   if (e == cudaSuccess && s->has_atomic) {
-    e = sdb_launch_commit(&h->view, h->n_agents, static_cast<uint32_t>(base), h->stream, &h->prof);
-    h->launches += 1;
+    e = sdb_launch_commit(&h->view, h->n_agents, static_cast<uint32_t>(base), h->rx_big_list, h->rx_big_count + 1, h->sm_count, h->stream, &h->prof);
+    h->launches += 2;
   }
   if (e != cudaSuccess) return fail(h, SDB_ECUDA, std::string("enqueue launch: ") + cudaGetErrorString(e));
   h->next_seq += s->total_recs;
@@ -944,8 +944,8 @@ int sdb_import_wire_ptrs(sdb_handle h, uint32_t n_src, const void* const* wire_p
     e = sdb_launch_pull(&h->view, &pv, h->xs_descs, h->n_agents, base, n_other ? 0 : 1, h->stream, &h->prof);
   }
   if (e == cudaSuccess && n_other) {     // p2p / broadcast copies claimed their slots with atomics: sort them into place
-    e = sdb_launch_commit(&h->view, h->n_agents, static_cast<uint32_t>(base), h->stream, &h->prof);
-    h->launches += 1;
+    e = sdb_launch_commit(&h->view, h->n_agents, static_cast<uint32_t>(base), h->rx_big_list, h->rx_big_count + 1, h->sm_count, h->stream, &h->prof);
+    h->launches += 2;
   }
   h->launches += nl + 2;
   if (e != cudaSuccess) return fail(h, SDB_ECUDA, std::string("import launch: ") + cudaGetErrorString(e));

@@ -530,7 +530,8 @@ k_pull_index(sdb_dev_view v, sdb_pull_view pv, const sdb_send_desc* __restrict__
 // publish ctail = tail.
 // ------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256)
-k_commit(sdb_dev_view v, uint32_t n_agents, uint32_t batch_base32) {
+k_commit(sdb_dev_view v, uint32_t n_agents, uint32_t batch_base32, uint32_t* __restrict__ big_list,
+         uint32_t* __restrict__ big_count) {
   const uint32_t a = blockIdx.x * blockDim.x + threadIdx.x;
   if (a >= n_agents) return;
   const uint64_t st = v.ring_state[a];
@@ -573,21 +574,74 @@ k_commit(sdb_dev_view v, uint32_t n_agents, uint32_t batch_base32) {
           if (i < cnt) { hs[(ct + i) & mask] = k[i] + batch_base32; ms[(ct + i) & mask] = m[i]; }
       }
     } else {
-      // rare: many records for one agent in one batch -> in-place insertion sort (mostly sorted input)
-      for (uint32_t i = 1; i < cnt; ++i) {
-        const uint32_t hk = hs[(ct + i) & mask]; const uint16_t mk = ms[(ct + i) & mask];
-        const uint32_t key = hk - batch_base32;
-        uint32_t j = i;
-        while (j > 0 && hs[(ct + j - 1) & mask] - batch_base32 > key) {
-          hs[(ct + j) & mask] = hs[(ct + j - 1) & mask];
-          ms[(ct + j) & mask] = ms[(ct + j - 1) & mask];
-          --j;
-        }
-        if (j != i) { hs[(ct + j) & mask] = hk; ms[(ct + j) & mask] = mk; }
-      }
+      // many records for one agent in one batch: a whole CTA sorts them (k_commit_big); ctail is published there
+      const uint32_t slot = atomicAdd(big_count, 1u);
+      big_list[slot] = a;
+      return;
     }
   }
   v.ctail[a] = tail;
+}
+
+// one CTA per agent that received more than 16 records in the batch: bitonic sort of (arena position, meta)
+// pairs, in shared memory up to 4096 entries, in place in the ring (L2-resident) beyond that
+#define SDB_COMMIT_SMEM 4096u
+__global__ void __launch_bounds__(256)
+k_commit_big(sdb_dev_view v, uint32_t batch_base32, const uint32_t* __restrict__ big_list,
+             const uint32_t* __restrict__ big_count) {
+  __shared__ uint32_t s_key[SDB_COMMIT_SMEM];
+  __shared__ uint16_t s_meta[SDB_COMMIT_SMEM];
+  const uint32_t n_big = *big_count;
+  const uint32_t R = v.ring_slots, mask = R - 1;
+  for (uint32_t w = blockIdx.x; w < n_big; w += gridDim.x) {
+    const uint32_t a = big_list[w];
+    const uint64_t st = v.ring_state[a];
+    const uint32_t tail = static_cast<uint32_t>(st >> 32), ct = v.ctail[a];
+    const uint32_t cnt = tail - ct;
+    uint32_t* hs = v.ring_handle + (static_cast<size_t>(a) << v.ring_shift);
+    uint16_t* ms = v.ring_meta + (static_cast<size_t>(a) << v.ring_shift);
+    uint32_t N = 1; while (N < cnt) N <<= 1;
+    if (N <= SDB_COMMIT_SMEM) {
+      for (uint32_t i = threadIdx.x; i < N; i += blockDim.x) {
+        s_key[i] = i < cnt ? hs[(ct + i) & mask] - batch_base32 : 0xFFFFFFFFu;
+        s_meta[i] = i < cnt ? ms[(ct + i) & mask] : 0;
+      }
+      __syncthreads();
+      for (uint32_t k = 2; k <= N; k <<= 1)
+        for (uint32_t j = k >> 1; j > 0; j >>= 1) {
+          for (uint32_t i = threadIdx.x; i < N; i += blockDim.x) {
+            const uint32_t l = i ^ j;
+            if (l > i) {
+              const bool up = (i & k) == 0;
+              const uint32_t ki = s_key[i], kl = s_key[l];
+              if ((ki > kl) == up) { s_key[i] = kl; s_key[l] = ki; const uint16_t t = s_meta[i]; s_meta[i] = s_meta[l]; s_meta[l] = t; }
+            }
+          }
+          __syncthreads();
+        }
+      for (uint32_t i = threadIdx.x; i < cnt; i += blockDim.x) {
+        hs[(ct + i) & mask] = s_key[i] + batch_base32;
+        ms[(ct + i) & mask] = s_meta[i];
+      }
+    } else {
+      // rare (more than 4096 records for one agent in one batch): odd-even transposition sort in place in the
+      // ring (works for any length; the segment is L2-resident)
+      for (uint32_t round = 0; round < cnt; ++round) {
+        for (uint32_t i = (round & 1u) + 2u * threadIdx.x; i + 1 < cnt; i += 2u * blockDim.x) {
+          const uint32_t x = (ct + i) & mask, y = (ct + i + 1) & mask;
+          const uint32_t kx = hs[x] - batch_base32, ky = hs[y] - batch_base32;
+          if (kx > ky) {
+            hs[x] = ky + batch_base32; hs[y] = kx + batch_base32;
+            const uint16_t t = ms[x]; ms[x] = ms[y]; ms[y] = t;
+          }
+        }
+        __syncthreads();
+      }
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) v.ctail[a] = tail;
+    __syncthreads();
+  }
 }
 
 // ------------------------------------------------------------------------------------------
@@ -670,10 +724,15 @@ extern "C" cudaError_t sdb_launch_pull(const sdb_dev_view* v, const sdb_pull_vie
 }
 
 extern "C" cudaError_t sdb_launch_commit(const sdb_dev_view* v, uint32_t n_agents, uint32_t batch_base32,
+                                         uint32_t* big_list, uint32_t* big_count, int sm_count,
                                          cudaStream_t stream, sdb_profiler* prof) {
   if (n_agents == 0) return cudaSuccess;
   const int pi = sdb_prof_begin(prof, SDB_PK_COMMIT, stream);
-  k_commit<<<(n_agents + 255) / 256, 256, 0, stream>>>(*v, n_agents, batch_base32);
+  cudaMemsetAsync(big_count, 0, sizeof(uint32_t), stream);
+  k_commit<<<(n_agents + 255) / 256, 256, 0, stream>>>(*v, n_agents, batch_base32, big_list, big_count);
+  uint32_t bg = static_cast<uint32_t>(sm_count) * 4u;
+  if (bg > n_agents) bg = n_agents;
+  k_commit_big<<<bg, 256, 0, stream>>>(*v, batch_base32, big_list, big_count);
   sdb_prof_end(prof, pi, stream);
   return cudaGetLastError();
 }

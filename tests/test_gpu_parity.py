@@ -287,3 +287,23 @@ def test_ring_handles_wrap_at_2_pow_32_granules():
         _same(g.receive_batch(idx, 4, flags), c.receive_batch(idx, 4, flags))       # leaves a backlog that straddles the wrap
     _same(g.receive_batch(idx, 10000), c.receive_batch(idx, 10000))
     assert g.stats()["arena_tail_bytes"] > (1 << 32) * 32
+
+
+@pytest.mark.parametrize("per_agent", [40, 1500, 5000])
+def test_many_records_for_one_agent_in_one_batch(per_agent):
+    """commit must order a hot receiver's entries: register network (<=16), shared-memory bitonic sort
+    (<=4096) and the in-ring odd-even sort beyond that."""
+    rng = np.random.default_rng(per_agent)
+    A = 64
+    g, c = _pair(A, ring_slots=16384, arena_bytes=1 << 26, max_batch_sends=3 * per_agent, max_batch_payload=3 * per_agent * 32 + 64,
+                 max_recv_records=1 << 16)
+    n = 3 * per_agent
+    recv = np.concatenate([np.full(per_agent, 5), np.full(per_agent, 9), rng.integers(0, A, per_agent)])
+    rng.shuffle(recv)
+    lens, off, buf = _mk_payloads(rng, n, 32)
+    s = rng.integers(0, A, n); prio = rng.integers(0, 4, n)
+    for _ in range(2):
+        g.send_batch(s, recv, prio, None, lens, off, buf); c.send_batch(s, recv, prio, None, lens, off, buf)
+    idx = np.arange(A, dtype=np.uint32)
+    _same(g.receive_batch(idx, 100000), c.receive_batch(idx, 100000))
+    assert g.stats()["ring_overflow"] == 0
