@@ -382,38 +382,56 @@ k_group_fanout_warp(sdb_dev_view v, const sdb_send_desc* __restrict__ descs, uin
 __global__ void __launch_bounds__(256)
 k_enqueue_p2p(sdb_dev_view v, const sdb_send_desc* __restrict__ descs, uint32_t n,
               const uint8_t* __restrict__ payload, uint64_t seq_base, uint64_t arena_base) {
-  const uint32_t lane = threadIdx.x & 31;
-  const uint32_t wid = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  // 8 lanes per record, 4 records per warp step; every lane keeps up to three 16-byte chunks in flight
+  const uint32_t lane = threadIdx.x & 31, sub = lane >> 3, l8 = lane & 7;
+  const uint32_t gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const uint32_t nw = (gridDim.x * blockDim.x) >> 5;
+  const uint64_t pol = sdb_policy_evict_first();
   uint32_t n_enq = 0, n_ovf = 0;
-  for (uint32_t i = wid; i < n; i += nw) {
-    const sdb_send_desc d = load_desc(descs + i);
-    const uint32_t a = d.mstart;
+  for (uint32_t i0 = gw * 4u; i0 < n; i0 += nw * 4u) {
+    const uint32_t i = i0 + sub;
+    if (i >= n) continue;
+    // the 8 lanes of a record read its descriptor: q0 (payload_off, timestamp), q1 (gran0, sender, rgran, len|prio|type), q2 (rec0, receiver, ..)
+    const uint4* dq = reinterpret_cast<const uint4*>(descs + i);
+    const uint4 q0 = __ldg(dq), q1 = __ldg(dq + 1), q2 = __ldg(dq + 2);
+    const uint32_t a = q2.y;                       // mstart = receiver index
     if (a >= v.max_agents) continue;
-    const uint32_t padlen = (d.rgran - 1u) * SDB_GRANULE;
+    const uint64_t payload_off = (static_cast<uint64_t>(q0.y) << 32) | q0.x;
+    const double ts = __longlong_as_double((static_cast<long long>(q0.w) << 32) | q0.z);
+    const uint32_t rgran = q1.z, len = q1.w & 0xFFFFu, prio = (q1.w >> 16) & 0xFFu, type = q1.w >> 24;
+    const uint32_t padlen = (rgran - 1u) * SDB_GRANULE;
     const uint32_t nchunk = 2u + (padlen >> 4);
-    const uint64_t apos = arena_base + d.gran0;
+    const uint64_t apos = arena_base + q1.x;
     uint8_t* rec = sdb_arena_ptr(v, apos);
-    const uint8_t* src = payload + d.payload_off;
-    for (uint32_t c = lane; c < nchunk; c += 32) {
-      uint4 x;
-      if (c == 0) x = sdb_header_lo(seq_base + d.rec0, d.timestamp);
-      else if (c == 1) x = sdb_header_hi(d.sender, a, d.group, d.len, d.prio, d.type);
-      else {
-        x = sdb_ld_stream(src + ((c - 2u) << 4));
-        const uint32_t b0 = (c - 2u) << 4;                 // zero pad bytes beyond len
-        if (b0 + 16u > d.len) {
-          uint8_t* xb = reinterpret_cast<uint8_t*>(&x);
+    const uint8_t* src = payload + payload_off;
+    for (uint32_t c = l8; c < nchunk; c += 24) {
+      uint4 x[3]; uint32_t cc[3] = {c, c + 8, c + 16};
 #pragma unroll
-          for (int k = 0; k < 16; ++k) if (b0 + k >= d.len) xb[k] = 0;
+      for (int u = 0; u < 3; ++u) {
+        if (cc[u] >= nchunk) continue;
+        if (cc[u] == 0) x[u] = sdb_header_lo(seq_base + q2.x, ts);
+        else if (cc[u] == 1) x[u] = sdb_header_hi(q1.y, a, SDB_NO_GROUP, static_cast<uint16_t>(len), static_cast<uint8_t>(prio), static_cast<uint8_t>(type));
+        else {
+          x[u] = sdb_ld_stream(src + ((cc[u] - 2u) << 4));
+          const uint32_t b0 = (cc[u] - 2u) << 4;               // zero the pad bytes beyond len
+          if (b0 + 16u > len) {
+            uint8_t* xb = reinterpret_cast<uint8_t*>(&x[u]);
+#pragma unroll
+            for (int k = 0; k < 16; ++k) if (b0 + k >= len) xb[k] = 0;
+          }
         }
       }
-      sdb_st_stream(rec + (c << 4), x);
+#pragma unroll
+      for (int u = 0; u < 3; ++u) if (cc[u] < nchunk) sdb_st_stream_pol(rec + (cc[u] << 4), x[u], pol);
     }
-    if (lane == 0) {
-      const uint16_t meta = static_cast<uint16_t>((static_cast<uint32_t>(d.prio) << 14) | d.rgran);
+    if (l8 == 0) {
+      const uint16_t meta = static_cast<uint16_t>((prio << 14) | rgran);
       if (sdb_ring_append(v, a, static_cast<uint32_t>(apos), meta)) ++n_enq; else ++n_ovf;
     }
+  }
+  for (int o = 16; o; o >>= 1) {
+    n_enq += __shfl_xor_sync(0xFFFFFFFFu, n_enq, o);
+    n_ovf += __shfl_xor_sync(0xFFFFFFFFu, n_ovf, o);
   }
   if (lane == 0) {
     if (n_enq) atomicAdd(&v.ctr->enqueued, n_enq);
@@ -651,8 +669,8 @@ extern "C" cudaError_t sdb_launch_p2p(const sdb_dev_view* v, const sdb_send_desc
                                       const uint8_t* payload, uint64_t seq_base, uint64_t arena_base,
                                       int sm_count, cudaStream_t stream, sdb_profiler* prof) {
   if (n == 0) return cudaSuccess;
-  const uint32_t warps_per_cta = 8;
-  uint32_t grid = (n + warps_per_cta - 1) / warps_per_cta;
+  const uint32_t recs_per_cta = 8 * 4;                            // 8 warps x 4 records per step
+  uint32_t grid = (n + recs_per_cta - 1) / recs_per_cta;
   const uint32_t cap = static_cast<uint32_t>(sm_count) * 8u * 4u;   // ~4 waves of 8 CTAs/SM, grid-stride beyond
   if (grid > cap) grid = cap;
   const int pi = sdb_prof_begin(prof, SDB_PK_P2P, stream);
