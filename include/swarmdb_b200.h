@@ -248,6 +248,15 @@ int sdb_export_mixed_batch(sdb_handle h, uint32_t n,
                            const uint8_t* prio, const uint8_t* type, const uint16_t* len,
                            const uint64_t* payload_off, const uint8_t* payload, uint64_t payload_bytes,
                            const double* timestamp, void* wire_dev, uint64_t wire_cap);
+/* Same, but the exporter numbers its sends itself, starting at `seq_base` (non-zero).  Front-ends that must
+ * return message ids at send time - before the collective flush - use a composite number
+ * (round << 40 | rank << 32 | local index), which keeps the global (round, rank, local) delivery order. */
+int sdb_export_mixed_batch_seq(sdb_handle h, uint64_t seq_base, uint32_t n,
+                               const uint32_t* sender, const uint8_t* kind, const uint32_t* target,
+                               uint32_t n_lists, const uint64_t* list_off, const uint32_t* list_idx,
+                               const uint8_t* prio, const uint8_t* type, const uint16_t* len,
+                               const uint64_t* payload_off, const uint8_t* payload, uint64_t payload_bytes,
+                               const double* timestamp, void* wire_dev, uint64_t wire_cap);
 int sdb_import_wire_batches(sdb_handle h, uint32_t n_src, const void* wire_dev_all, uint64_t wire_stride,
                             uint64_t* seq_base_out);
 /* Peer-memory transport (no collective): each rank exports into a buffer allocated with

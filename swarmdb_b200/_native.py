@@ -57,7 +57,7 @@ EXPORTS = ["sdb_abi_version", "sdb_create", "sdb_destroy", "sdb_set_stream", "sd
            "sdb_get_stats", "sdb_debug_set_arena_pos", "sdb_profile", "sdb_profile_read", "sdb_register_agents", "sdb_deregister_agents", "sdb_create_group", "sdb_send_batch",
            "sdb_send_group_batch", "sdb_send_list_batch", "sdb_send_mixed_batch", "sdb_stage_batch", "sdb_submit_staged", "sdb_free_staged",
            "sdb_receive_batch", "sdb_last_receive_dev", "sdb_wire_bytes", "sdb_set_agent_shards",
-           "sdb_export_group_batch", "sdb_export_mixed_batch", "sdb_import_wire_batches", "sdb_wire_alloc", "sdb_wire_open",
+           "sdb_export_group_batch", "sdb_export_mixed_batch", "sdb_export_mixed_batch_seq", "sdb_import_wire_batches", "sdb_wire_alloc", "sdb_wire_open",
            "sdb_wire_close", "sdb_import_wire_ptrs", "sdb_set_backends", "sdb_get_backend_loads",
            "sdb_release_backends", "sdb_select_backend_batch"]
 
@@ -104,6 +104,8 @@ def load_library() -> C.CDLL:
     L.sdb_export_group_batch.restype = i32; L.sdb_export_group_batch.argtypes = [vp, u32] + [vp] * 7 + [u64, vp, vp, u64]
     L.sdb_export_mixed_batch.restype = i32
     L.sdb_export_mixed_batch.argtypes = [vp, u32, vp, vp, vp, u32] + [vp] * 7 + [u64, vp, vp, u64]
+    L.sdb_export_mixed_batch_seq.restype = i32
+    L.sdb_export_mixed_batch_seq.argtypes = [vp, u64, u32, vp, vp, vp, u32] + [vp] * 7 + [u64, vp, vp, u64]
     L.sdb_wire_alloc.restype = i32; L.sdb_wire_alloc.argtypes = [vp, u64, C.POINTER(vp), vp]
     L.sdb_wire_open.restype = i32; L.sdb_wire_open.argtypes = [vp, vp, C.POINTER(vp)]
     L.sdb_wire_close.restype = i32; L.sdb_wire_close.argtypes = [vp, vp, i32]
@@ -317,12 +319,18 @@ class Shard:
                                                    _p(pl), pl.nbytes, _p(ts), C.c_void_p(wire_dev), wire_cap))
 
     def export_mixed_batch(self, sender, kind, target, list_off, list_idx, prio, typ, lens, payload_off, payload,
-                           wire_dev: int, wire_cap: int, ts=None) -> None:
+                           wire_dev: int, wire_cap: int, ts=None, seq_base: int = 0) -> None:
+        """seq_base != 0: the exporter numbers its own sends from that (composite) sequence number."""
         s, k, t = _arr(sender, np.uint32), _arr(kind, np.uint8), _arr(target, np.uint32)
         lo = _arr(list_off if list_off is not None else [0], np.uint64)
         li = _arr(list_idx if list_idx is not None else [], np.uint32)
         prio, typ, lens, po, pl, ts = self._common(len(s), prio, typ, lens, payload_off, payload, ts)
         self._keep = pl
+        if seq_base:
+            self._check(self._L.sdb_export_mixed_batch_seq(self._h, seq_base, len(s), _p(s), _p(k), _p(t), len(lo) - 1, _p(lo),
+                                                           _p(li), _p(prio), _p(typ), _p(lens), _p(po), _p(pl), pl.nbytes,
+                                                           _p(ts), C.c_void_p(wire_dev), wire_cap))
+            return
         self._check(self._L.sdb_export_mixed_batch(self._h, len(s), _p(s), _p(k), _p(t), len(lo) - 1, _p(lo), _p(li),
                                                    _p(prio), _p(typ), _p(lens), _p(po), _p(pl), pl.nbytes, _p(ts),
                                                    C.c_void_p(wire_dev), wire_cap))

@@ -146,7 +146,10 @@ class GpuConfig:
     max_recv_payload: int = 1 << 26
     priority_dequeue: bool = False        # True: receive in (priority desc, arrival) order - extension
     deterministic_ids: bool = False       # True: ids are uuid.UUID(int=seq) (tests / reproducibility)
+    id_nonce: Optional[int] = None        # high 64 bits of every id (must match across the ranks of a sharded deployment)
     fanout_variant: int = 2
+    shard_id: int = 0                     # multi-GPU: this process's shard / total shards (see sharded.ShardedSwarmsDB)
+    num_shards: int = 1
 
 
 def _encode_content(content: Any) -> (bytes, int):
@@ -168,19 +171,20 @@ class SwarmsDB:
         max_messages_per_file: int = 10000,
         token_counter: Optional[Callable[[str], int]] = None,
         gpu_config: Optional[GpuConfig] = None,
+        _shard: Any = None,
     ):
         self.base_topic = base_topic
         self.config = config or KafkaConfig()
         self.gpu_config = gpu_config or GpuConfig()
         g = self.gpu_config
         # the transport: constructing it fails loudly when the CUDA library or a device is missing
-        self.shard = Shard(
+        self.shard = _shard if _shard is not None else Shard(
             max_agents=g.max_agents, ring_slots=g.ring_slots, arena_bytes=g.arena_bytes,
             max_payload_bytes=g.max_payload_bytes, max_groups=g.max_groups,
             member_pool_entries=g.member_pool_entries or 4 * g.max_agents, max_backends=g.max_backends,
             max_batch_sends=max(g.flush_threshold, 1), max_batch_payload=max(1 << 22, 2 * pad32(g.max_payload_bytes)),
             max_recv_records=g.max_recv_records, max_recv_payload=g.max_recv_payload, device=g.device,
-            fanout_variant=g.fanout_variant)
+            fanout_variant=g.fanout_variant, shard_id=g.shard_id, num_shards=g.num_shards)
 
         # local state, same names as the reference (M:210-233)
         self.messages: Dict[str, Message] = {}
@@ -206,7 +210,7 @@ class SwarmsDB:
         self._group_snapshot: List[List[str]] = []
         self._backend_idx: Dict[str, int] = {}
         self._backend_name: List[str] = []
-        self._id_hi = 0 if g.deterministic_ids else (secrets.randbits(63) << 64)
+        self._id_hi = 0 if g.deterministic_ids else (((g.id_nonce if g.id_nonce is not None else secrets.randbits(63)) & ((1 << 63) - 1)) << 64)
         self._next_seq = 1                      # mirror of the handle's sequence counter
         self._seq_to_id: Dict[int, str] = {}
         self._reset_buffer()
@@ -530,6 +534,9 @@ class SwarmsDB:
             logger.warning(f"Agent {agent_id} not registered, registering now")
             self.register_agent(agent_id)
         self.flush()
+        return self._receive_local(agent_id, max_messages)
+
+    def _receive_local(self, agent_id: str, max_messages: int) -> List[Message]:
         if max_messages <= 0:
             return []
         flags = RECV_PRIORITY if self.gpu_config.priority_dequeue else 0

@@ -739,7 +739,8 @@ int sdb_set_agent_shards(sdb_handle h, uint32_t n, const uint8_t* shard_of) {
 static int export_common(sdb_ctx* h, uint32_t n, const uint32_t* sender, const uint8_t* kind, const uint32_t* target,
                          uint32_t n_lists, const uint64_t* list_off, const uint32_t* list_idx, const uint8_t* prio,
                          const uint8_t* type, const uint16_t* len, const uint64_t* payload_off, const uint8_t* payload,
-                         uint64_t payload_bytes, const double* timestamp, void* wire_dev, uint64_t wire_cap) {
+                         uint64_t payload_bytes, const double* timestamp, void* wire_dev, uint64_t wire_cap,
+                         uint64_t explicit_seq_base = 0) {
   if (!h || !wire_dev) return SDB_EINVAL;
   if (n && (!sender || !target || !len)) return fail(h, SDB_EINVAL, "null array");
   if (n > h->cfg.max_batch_sends) return fail(h, SDB_ECAPACITY, "n exceeds max_batch_sends");
@@ -803,6 +804,7 @@ static int export_common(sdb_ctx* h, uint32_t n, const uint32_t* sender, const u
   wh->desc_off = desc_off; wh->payload_off = pay_off; wh->max_padlen = max_padlen; wh->n_other = n_other;
   wh->list_off = l_off; wh->n_list = static_cast<uint32_t>(n_list);
   wh->n_group_sends = n_group; wh->gs_off_off = gso_off; wh->gs_idx_off = gsi_off; wh->max_groups = G;
+  wh->explicit_seq = explicit_seq_base ? 1u : 0u; wh->seq_base = explicit_seq_base;
   uint8_t* w = static_cast<uint8_t*>(wire_dev);
   CUDA_TRY(h, cudaMemcpyAsync(w, h->wire_host, l_off, cudaMemcpyHostToDevice, h->stream));
   if (n_list) {
@@ -828,6 +830,17 @@ int sdb_export_mixed_batch(sdb_handle h, uint32_t n, const uint32_t* sender, con
   if (h && n && !kind) return fail(h, SDB_EINVAL, "null kind array");
   return export_common(h, n, sender, kind, target, n_lists, list_off, list_idx, prio, type, len, payload_off, payload, payload_bytes,
                        timestamp, wire_dev, wire_cap);
+}
+
+int sdb_export_mixed_batch_seq(sdb_handle h, uint64_t seq_base, uint32_t n, const uint32_t* sender, const uint8_t* kind,
+                               const uint32_t* target, uint32_t n_lists, const uint64_t* list_off, const uint32_t* list_idx,
+                               const uint8_t* prio, const uint8_t* type, const uint16_t* len, const uint64_t* payload_off,
+                               const uint8_t* payload, uint64_t payload_bytes, const double* timestamp, void* wire_dev,
+                               uint64_t wire_cap) {
+  if (h && n && !kind) return fail(h, SDB_EINVAL, "null kind array");
+  if (h && seq_base == 0) return fail(h, SDB_EINVAL, "explicit seq_base must be non-zero");
+  return export_common(h, n, sender, kind, target, n_lists, list_off, list_idx, prio, type, len, payload_off, payload, payload_bytes,
+                       timestamp, wire_dev, wire_cap, seq_base);
 }
 
 // ---- peer-memory transport: export buffers that other ranks map with CUDA IPC ---------------------
@@ -912,11 +925,12 @@ int sdb_import_wire_ptrs(sdb_handle h, uint32_t n_src, const void* const* wire_p
   for (uint32_t k = 0; k < n_src; ++k)
     CUDA_TRY(h, cudaMemcpyAsync(h->hdrs_host + k, wire_ptrs[k], sizeof(sdb_wire_header), cudaMemcpyDeviceToHost, h->stream));
   CUDA_TRY(h, cudaStreamSynchronize(h->stream));
-  uint64_t total_recs = 0, n_other = 0; uint32_t max_padlen = 0;
+  uint64_t total_recs = 0, n_other = 0, explicit_end = 0; uint32_t max_padlen = 0;
   if (h->totals_host[5] > a.list_cap) return fail(h, SDB_ECAPACITY, "owned recipients of this import exceed list_pool_entries");
   for (uint32_t s = 0; s < n_src; ++s) {
     const sdb_wire_header& wh = h->hdrs_host[s];
     n_other += wh.n_other;
+    if (wh.magic == SDB_WIRE_MAGIC && wh.explicit_seq) explicit_end = std::max<uint64_t>(explicit_end, wh.seq_base + wh.total_recs);
     if (wh.magic != SDB_WIRE_MAGIC) return fail(h, SDB_EINVAL, "wire batch without magic (not exported by sdb_export_group_batch?)");
     if (wh.n_sends > h->cfg.max_batch_sends) return fail(h, SDB_ECAPACITY, "wire batch larger than max_batch_sends");
     total_recs += wh.total_recs; max_padlen = std::max(max_padlen, wh.max_padlen);
@@ -949,7 +963,7 @@ int sdb_import_wire_ptrs(sdb_handle h, uint32_t n_src, const void* const* wire_p
   }
   h->launches += nl + 2;
   if (e != cudaSuccess) return fail(h, SDB_ECUDA, std::string("import launch: ") + cudaGetErrorString(e));
-  h->next_seq += total_recs;
+  h->next_seq = std::max<uint64_t>(h->next_seq + (explicit_end ? 0 : total_recs), explicit_end);
   h->arena_tail = base + total_grans;
   return SDB_OK;
 }

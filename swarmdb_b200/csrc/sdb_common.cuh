@@ -51,7 +51,8 @@ struct __align__(16) sdb_send_desc {
   uint32_t group;        // group index or SDB_NO_GROUP
   // q3
   uint32_t flags;        // SDB_DESC_*
-  uint32_t pad[3];
+  uint32_t pad0;
+  uint64_t seq_abs;      // SDB_DESC_ABS_SEQ: absolute sequence number of member position 0 (instead of seq_base + rec0)
 };
 static_assert(sizeof(sdb_send_desc) == 64, "desc must be 64 bytes");
 static_assert(sizeof(sdb_msg_header) == 32, "header must be 32 bytes");
@@ -62,6 +63,7 @@ static_assert(sizeof(sdb_msg_header) == 32, "header must be 32 bytes");
 #define SDB_DESC_PULL 8u          // ring entries are built by k_pull_index, not by the fan-out kernel
 #define SDB_DESC_POS 16u          // seq offset of member k is member_pos[mstart + k] (sharded: original group position)
 #define SDB_DESC_P2P 32u          // wire batches only: point-to-point send, mstart = receiver index
+#define SDB_DESC_ABS_SEQ 64u      // seq_abs holds the sequence number (sources that number their own sends)
 
 // cross-shard wire batch (device memory, moved between ranks by the caller):
 //   [sdb_wire_header 128 B][n_sends x sdb_send_desc 64 B][group buckets][broadcast lists][payload bytes]
@@ -82,7 +84,9 @@ struct __align__(16) sdb_wire_header {
   uint64_t gs_off_off;     // group-send buckets of THIS batch: offsets [max_groups + 1] ...
   uint64_t gs_idx_off;     // ... and send indices, ascending inside a bucket (built by the exporter)
   uint32_t max_groups;
-  uint32_t pad[11];
+  uint32_t explicit_seq;   // 1: this batch's sends are numbered from seq_base (assigned by the exporter at send time)
+  uint64_t seq_base;
+  uint32_t pad[8];
 };
 static_assert(sizeof(sdb_wire_header) == 128, "wire header must be 128 bytes");
 #define SDB_WIRE_MAGIC 0x57424453u
@@ -156,6 +160,7 @@ struct sdb_src_tab {
   uint64_t rec_base[SDB_MAX_SRC];    // sequence offset of each source inside the global batch
   uint64_t desc_off[SDB_MAX_SRC], list_off[SDB_MAX_SRC], payload_off[SDB_MAX_SRC];
   uint64_t gs_off_off[SDB_MAX_SRC], gs_idx_off[SDB_MAX_SRC];
+  uint32_t explicit_seq[SDB_MAX_SRC];   // rec_base[s] is then an absolute sequence number
 };
 struct sdb_import_args {
   const sdb_src_tab* tab;

@@ -78,7 +78,7 @@ k_group_fanout_st(sdb_dev_view v, const sdb_send_desc* __restrict__ descs, uint3
       if (deliver) {
         const uint64_t apos = apos0 + static_cast<uint64_t>(j) * d.rgran;
         const uint32_t pj = (d.flags & SDB_DESC_POS) ? __ldg(v.member_pos + d.mstart + j) : j;
-        const uint64_t seq = seq_base + d.rec0 + ((d.flags & SDB_DESC_SHARED_SEQ) ? 0u : pj);
+        const uint64_t seq = ((d.flags & SDB_DESC_ABS_SEQ) ? d.seq_abs : seq_base + d.rec0) + ((d.flags & SDB_DESC_SHARED_SEQ) ? 0u : pj);
         const uint32_t rcv = (d.flags & SDB_DESC_SHARED_SEQ) ? SDB_NO_RECEIVER : a;
         uint4* dst = reinterpret_cast<uint4*>(sdb_arena_ptr(v, apos));
         sdb_st_stream(dst, sdb_header_lo(seq, d.timestamp));
@@ -179,7 +179,7 @@ k_group_fanout_tma(sdb_dev_view v, const sdb_send_desc* __restrict__ descs, uint
       if (skip || a >= v.max_agents) continue;
       const uint64_t apos = apos0 + static_cast<uint64_t>(j) * d.rgran;
       const uint32_t pj = (d.flags & SDB_DESC_POS) ? __ldg(v.member_pos + d.mstart + j) : j;
-      const uint64_t seq = seq_base + d.rec0 + ((d.flags & SDB_DESC_SHARED_SEQ) ? 0u : pj);
+      const uint64_t seq = ((d.flags & SDB_DESC_ABS_SEQ) ? d.seq_abs : seq_base + d.rec0) + ((d.flags & SDB_DESC_SHARED_SEQ) ? 0u : pj);
       const uint32_t rcv = (d.flags & SDB_DESC_SHARED_SEQ) ? SDB_NO_RECEIVER : a;
       uint8_t* rec = sdb_arena_ptr(v, apos);
       if (padlen) sdb_tma_store(rec + 32, s_payload, padlen);
@@ -319,7 +319,7 @@ k_group_fanout_warp(sdb_dev_view v, const sdb_send_desc* __restrict__ descs, uin
       const uint32_t q32 = q32_c, r32 = r32_c;
       uint32_t rec = rec_c, ch = ch_c;
       uint8_t* const tb = base + static_cast<size_t>(tile) * rbytes;
-      const uint64_t seq0 = seq_base + d.rec0;
+      const uint64_t seq0 = (d.flags & SDB_DESC_ABS_SEQ) ? d.seq_abs : seq_base + d.rec0;
       const uint4 hdr_hi = sdb_header_hi(d.sender, SDB_NO_RECEIVER, d.group, d.len, d.prio, d.type);
       // record j occupies chunks [j*PC, (j+1)*PC) of the send's region, so flat chunk f lands at tb + 16 f
       uint8_t* dst = tb + (static_cast<size_t>(lane) << 4);

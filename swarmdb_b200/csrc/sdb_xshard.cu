@@ -38,7 +38,8 @@ __global__ void k_wire_table(sdb_import_args a, sdb_src_tab* tab) {
   for (uint32_t s = 0; s < a.n_src; ++s) {
     const sdb_wire_header* h = wire_hdr(a, s);
     const bool ok = h->magic == SDB_WIRE_MAGIC;
-    tab->first[s] = first; tab->rec_base[s] = rb;
+    const bool ex = ok && h->explicit_seq;
+    tab->first[s] = first; tab->rec_base[s] = ex ? h->seq_base : rb; tab->explicit_seq[s] = ex ? 1u : 0u;
     tab->desc_off[s] = ok ? h->desc_off : 0; tab->list_off[s] = ok ? h->list_off : 0; tab->payload_off[s] = ok ? h->payload_off : 0;
     tab->gs_off_off[s] = (ok && h->max_groups == a.max_groups) ? h->gs_off_off : 0; tab->gs_idx_off[s] = ok ? h->gs_idx_off : 0;
     first += ok ? min(h->n_sends, a.max_sends) : 0u;
@@ -117,16 +118,18 @@ k_wire_localize(sdb_import_args a, uint32_t n_total) {
   out.payload_off = reinterpret_cast<uint64_t>(a.wire[src]) + a.tab->payload_off[src] + d->payload_off;
   out.gran0 = a.w_local[gi] + a.w_tops[gi / SDB_SCAN_TILE];
   out.rec0 = static_cast<uint32_t>(rb + d->rec0);
+  const bool abs_seq = a.tab->explicit_seq[src] != 0;
+  out.seq_abs = abs_seq ? rb + d->rec0 : 0ull;
   if (d->flags & (SDB_DESC_P2P | SDB_DESC_LIST_TEMP)) {
     const uint32_t own = a.lw[gi];
     uint32_t lo = a.lw_local[gi] + a.lw_tops[gi / SDB_SCAN_TILE];
     const bool fits = static_cast<uint64_t>(lo) + own <= a.list_cap;      // checked on the host before launch
     out.mstart = lo; out.mcount = fits ? own : 0u; out.group = SDB_NO_GROUP;
     if (d->flags & SDB_DESC_P2P) {
-      out.flags = SDB_DESC_LIST_TEMP;
+      out.flags = SDB_DESC_LIST_TEMP | (abs_seq ? SDB_DESC_ABS_SEQ : 0u);
       if (own && fits) a.tmp_list[lo] = d->mstart;
     } else {
-      out.flags = SDB_DESC_LIST_TEMP | SDB_DESC_SHARED_SEQ;
+      out.flags = SDB_DESC_LIST_TEMP | SDB_DESC_SHARED_SEQ | (abs_seq ? SDB_DESC_ABS_SEQ : 0u);
       if (fits) {
         const uint32_t* l = wire_list(a, src) + d->mstart;
         for (uint32_t k = 0; k < d->mcount; ++k) { const uint32_t x = l[k]; if (x < a.max_agents && a.shard_of[x] == a.shard_id) a.tmp_list[lo++] = x; }
@@ -139,7 +142,7 @@ k_wire_localize(sdb_import_args a, uint32_t n_total) {
   const uint32_t lc = g < a.max_groups ? a.lcount[g] : 0u;
   out.mstart = lc ? a.lstart[g] : 0u;
   out.mcount = lc;
-  out.flags = SDB_DESC_SKIP_SENDER | SDB_DESC_PULL | SDB_DESC_POS;
+  out.flags = SDB_DESC_SKIP_SENDER | SDB_DESC_PULL | SDB_DESC_POS | (abs_seq ? SDB_DESC_ABS_SEQ : 0u);
   a.descs[gi] = out;
 }
 

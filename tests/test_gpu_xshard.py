@@ -178,3 +178,136 @@ def test_sharded_mixed_traffic_equals_single_shard(world):
     for s in shards:
         assert s.stats()["ring_overflow"] == 0
         s.close()
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_explicit_sequence_bases_equal_replayed_oracle(world):
+    """sdb_export_mixed_batch_seq: each rank stamps its own (round, rank, local) sequence numbers at
+    export; after import every shard's streams equal an oracle replay that assigns the same numbers."""
+    import torch
+    from swarmdb_b200._native import Shard
+    from swarmdb_b200.sharded import composite_seq, shard_map_numbered
+    from tests.fake_shard import OracleShard
+
+    rng = np.random.default_rng(910 + world)
+    A, G, S = 500, 8, 120
+    smap = shard_map_numbered("agent_", 7, A, world)
+    groups = [rng.choice(A, size=int(rng.integers(1, 48)), replace=False) for _ in range(G)]
+    cap_pay = S * 128 + 64 + 4 * 512                       # payload + room for the recipient lists
+    shards = []
+    for r in range(world):
+        s = Shard(max_agents=A, max_groups=G, ring_slots=4096, arena_bytes=1 << 26, max_batch_sends=S,
+                  max_batch_payload=cap_pay, shard_id=r, num_shards=world, max_recv_records=1 << 17,
+                  max_payload_bytes=128, list_pool_entries=1 << 16)
+        s.set_agent_shards(smap)
+        for g, m in enumerate(groups):
+            s.create_group(g, m)
+        shards.append(s)
+    ref = OracleShard(A, G, 0, 1)
+    for g, m in enumerate(groups):
+        ref.create_group(g, m)
+    wire_bytes = shards[0].wire_bytes(S, cap_pay)
+    wire = torch.zeros(world * wire_bytes, dtype=torch.uint8, device="cuda")
+    ref_bytes = ref.wire_bytes(S, cap_pay + 8 * 4 * 200)
+    ref_wire = np.zeros(world * ref_bytes, np.uint8)
+    all_agents = np.arange(A, dtype=np.uint32)
+    for step in range(3):
+        for r in range(world):
+            n = S if (step + r) % 3 else 0                   # an empty batch from some rank in some round
+            kind = rng.integers(0, 3, n).astype(np.uint8)
+            sender = rng.integers(0, A, n)
+            lists = [rng.choice(A, size=int(rng.integers(0, 100)), replace=False) for _ in range(4)]
+            lo = np.zeros(5, np.uint64); lo[1:] = np.cumsum([len(x) for x in lists])
+            li = np.concatenate(lists).astype(np.uint32)
+            target = np.where(kind == 0, rng.integers(0, A, n), np.where(kind == 1, rng.integers(0, G, n), rng.integers(0, 4, n)))
+            prio = rng.integers(0, 4, n); typ = rng.integers(0, 7, n)
+            lens = rng.integers(0, 129, n).astype(np.uint16)
+            off = np.arange(n, dtype=np.uint64) * 128
+            buf = rng.integers(48, 123, n * 128 + 64).astype(np.uint8)
+            ts = rng.random(n)
+            base = composite_seq(step + 1, r)
+            shards[r].export_mixed_batch(sender, kind, target, lo, li, prio, typ, lens, off, buf,
+                                         wire.data_ptr() + r * wire_bytes, wire_bytes, ts, seq_base=base)
+            shards[r].sync()
+            ref.export_mixed_batch(sender, kind, target, lo, li, prio, typ, lens, off, buf,
+                                   ref_wire[r * ref_bytes:(r + 1) * ref_bytes], ref_bytes, ts, seq_base=base)
+        for s in shards:
+            s.import_wire_batches(world, wire.data_ptr(), wire_bytes)
+        ref.import_wire_batches(world, ref_wire, ref_bytes)
+        k = [3, 5000, 5000][step]
+        for flags in ((0,) if step != 1 else (1,)):
+            merged = {}
+            for r, s in enumerate(shards):
+                local = np.nonzero(smap == r)[0].astype(np.uint32)
+                merged.update(_per_agent(*s.receive_batch(local, k, flags), local))
+            want = _per_agent(*ref.o.receive_batch(all_agents, k, flags, rec_cap=1 << 18), all_agents)
+            for a in range(A):
+                assert merged[a] == want[a], (step, a)
+    for s in shards:
+        st = s.stats()
+        assert st["ring_overflow"] == 0 and st["next_seq"] == ref.o.next_seq
+        s.close()
+
+
+def test_sharded_frontend_two_ranks_on_one_gpu(tmp_path):
+    """ShardedSwarmsDB x2 in one process (one handle per emulated rank, wire slots in one CUDA buffer):
+    rank-local sends with immediate ids, collective flush phases, owner-local receives - against a
+    plain single-handle SwarmsDB fed the same calls in (round, rank, call) order."""
+    import torch
+    import swarmdb_b200 as sdb
+    from swarmdb_b200 import sharded
+    from tests.test_sharded_frontend_cpu import AGENTS, _play, _script, _setup, _view
+
+    world = 2
+    cfg = sdb.GpuConfig(max_agents=64, max_groups=8, flush_threshold=64, max_payload_bytes=1024, ring_slots=1024,
+                        arena_bytes=1 << 24, deterministic_ids=True)
+    slots = {}
+
+    class Loop:                                             # the exchange of a 1-process, 1-GPU "cluster"
+        def __init__(self, shard, rank, world_, max_sends, max_payload):
+            self.shard, self.rank = shard, rank
+            self.bytes = shard.wire_bytes(max_sends, max_payload)
+            slots.setdefault("wire", torch.zeros(world_ * self.bytes, dtype=torch.uint8, device="cuda"))
+            # add_agent_group flushes (collectively, in a real deployment); here the emulated ranks run their
+            # setup one after the other, so every slot starts out holding a valid empty batch
+            e = np.zeros(0, np.uint32)
+            shard.export_mixed_batch(e, e, e, None, None, e, e, e, e, np.zeros(32, np.uint8),
+                                     slots["wire"].data_ptr() + rank * self.bytes, self.bytes)
+            shard.sync()
+
+        def export_mixed(self, *a, seq_base=0):
+            *cols, ts = a
+            self.shard.export_mixed_batch(*cols, slots["wire"].data_ptr() + self.rank * self.bytes, self.bytes, ts, seq_base)
+            self.shard.sync()
+
+        def exchange(self): pass
+        def import_all(self): return self.shard.import_wire_batches(world, slots["wire"].data_ptr(), self.bytes)
+
+    dbs = [sharded.make_sharded_swarmsdb(r, world, exchange_factory=Loop, save_dir=str(tmp_path / f"r{r}"),
+                                         auto_save=False, gpu_config=cfg) for r in range(world)]
+    single = sdb.SwarmsDB(save_dir=str(tmp_path / "single"), auto_save=False, gpu_config=cfg)
+    for d in dbs + [single]:
+        _setup(d)
+    script = _script(np.random.default_rng(23), world, 6)
+    got, sent_ids = {}, []
+    for per_rank in script:
+        for r, d in enumerate(dbs):
+            sent_ids += _play(d, per_rank[r]); _play(single, per_rank[r])
+        for d in dbs:
+            d._flush_export()
+        for d in dbs:
+            d._flush_import()
+        for a in AGENTS:
+            d = dbs[dbs[0].owner(a)]
+            got.setdefault(a, []).extend(d.receive_messages(a, 4))
+    seen = set()
+    for a in AGENTS:
+        got[a].extend(dbs[dbs[0].owner(a)].receive_messages(a, 100000))
+        want = [_view(m) for m in single.receive_messages(a, 100000)]
+        assert [_view(m) for m in got[a]] == want, a
+        seen |= {m.id for m in got[a]}
+    assert len(sent_ids) == len(set(sent_ids)) and seen <= set(sent_ids) and len(seen) > 50
+    with pytest.raises(KeyError):
+        dbs[0].send_message(AGENTS[0], "x", "stranger")
+    for d in dbs + [single]:
+        d.close()
