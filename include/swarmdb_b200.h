@@ -77,7 +77,8 @@ typedef struct sdb_config {
   uint64_t max_recv_records;    /* receive output capacity, records per call */
   uint64_t max_recv_payload;    /* receive output capacity, payload bytes per call (0: records x 256) */
   uint64_t list_pool_entries;   /* per-batch broadcast recipient-list capacity (0: 2 x max_agents) */
-  uint32_t fanout_variant;      /* 2 (recommended): warp-per-send, TMA-in / coalesced stores; 0: CTA-per-send; 1: TMA-in / TMA-out */
+  uint32_t fanout_variant;      /* 2 (recommended): warp-per-send, TMA-in / coalesced stores - imports of wire batches use the deep-prefetch form;
+                                   3: deep-prefetch warp-per-send everywhere (payloads <= 480 B); 0: CTA-per-send; 1: TMA-in / TMA-out */
   uint32_t flags;               /* reserved, 0 */
 } sdb_config;
 

@@ -139,6 +139,10 @@ def pad32(n):
     return (n + 31) & ~31
 
 
+# kernel variant used when the caller does not choose one (SDB_FANOUT_VARIANT overrides, for A/B runs)
+DEFAULT_FANOUT_VARIANT = int(os.environ.get("SDB_FANOUT_VARIANT", "2"))
+
+
 class Shard:
     """One GPU-resident shard: per-agent rings + message arena + backend table on one device."""
 
@@ -146,7 +150,7 @@ class Shard:
                  max_payload_bytes: int = 256, max_groups: int = 1, member_pool_entries: int = 0,
                  max_backends: int = 256, max_batch_sends: int = 65536, max_batch_payload: int = 0,
                  max_recv_records: int = 1 << 20, max_recv_payload: int = 0, list_pool_entries: int = 0,
-                 device: int = 0, shard_id: int = 0, num_shards: int = 1, fanout_variant: int = 2) -> None:
+                 device: int = 0, shard_id: int = 0, num_shards: int = 1, fanout_variant: Optional[int] = None) -> None:
         self._L = load_library()
         cfg = SdbConfig()
         cfg.struct_bytes = C.sizeof(SdbConfig)
@@ -156,7 +160,7 @@ class Shard:
         cfg.member_pool_entries = member_pool_entries or max(1024, 2 * max_agents)
         cfg.max_backends, cfg.max_batch_sends, cfg.max_batch_payload = max_backends, max_batch_sends, max_batch_payload
         cfg.max_recv_records, cfg.max_recv_payload, cfg.list_pool_entries = max_recv_records, max_recv_payload, list_pool_entries
-        cfg.fanout_variant = fanout_variant
+        cfg.fanout_variant = DEFAULT_FANOUT_VARIANT if fanout_variant is None else fanout_variant
         self.cfg = cfg
         self.max_agents = max_agents
         self._h = C.c_void_p()

@@ -147,7 +147,7 @@ class GpuConfig:
     priority_dequeue: bool = False        # True: receive in (priority desc, arrival) order - extension
     deterministic_ids: bool = False       # True: ids are uuid.UUID(int=seq) (tests / reproducibility)
     id_nonce: Optional[int] = None        # high 64 bits of every id (must match across the ranks of a sharded deployment)
-    fanout_variant: int = 2
+    fanout_variant: Optional[int] = None      # None: the library default (_native.DEFAULT_FANOUT_VARIANT)
     shard_id: int = 0                     # multi-GPU: this process's shard / total shards (see sharded.ShardedSwarmsDB)
     num_shards: int = 1
 

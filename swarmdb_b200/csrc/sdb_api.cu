@@ -427,7 +427,7 @@ int sdb_create(const sdb_config* cfg, sdb_handle* out) {
   if (c.max_recv_records > 0xFFFFFFF0ull) return fail(h, SDB_EINVAL, "max_recv_records too large");
   if (c.max_recv_payload == 0) c.max_recv_payload = c.max_recv_records * 256ull;
   if (c.list_pool_entries == 0) c.list_pool_entries = 2ull * c.max_agents + 1024;
-  if (c.fanout_variant > 2) return fail(h, SDB_EINVAL, "fanout_variant must be 0, 1 or 2");
+  if (c.fanout_variant > 3) return fail(h, SDB_EINVAL, "fanout_variant must be 0, 1, 2 or 3");
 
   int ndev = 0;
   if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
@@ -950,7 +950,8 @@ int sdb_import_wire_ptrs(sdb_handle h, uint32_t n_src, const void* const* wire_p
     if (e == cudaSuccess) CUDA_TRY(h, cudaEventRecord(h->ev_join, h->side));
   }
   if (e == cudaSuccess)
-    e = sdb_launch_fanout(&h->view, h->xs_descs, n_cap, nullptr, h->scratch.list_dev, h->next_seq, base, max_padlen, 2, h->sm_count, h->stream, &h->prof);
+    e = sdb_launch_fanout(&h->view, h->xs_descs, n_cap, nullptr, h->scratch.list_dev, h->next_seq, base, max_padlen,
+                          h->cfg.fanout_variant >= 2 ? 3 : static_cast<int>(h->cfg.fanout_variant), h->sm_count, h->stream, &h->prof);
   if (e == cudaSuccess && overlap) {
     CUDA_TRY(h, cudaStreamWaitEvent(h->stream, h->ev_join, 0));
   } else if (e == cudaSuccess) {

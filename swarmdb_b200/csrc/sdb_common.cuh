@@ -322,6 +322,21 @@ __device__ __forceinline__ void sdb_fence_proxy_async() {
 __device__ __forceinline__ void sdb_mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(sdb_smem_u32(bar)), "r"(bytes) : "memory");
 }
+__device__ __forceinline__ void sdb_mbar_wait_bounded(uint64_t* bar, uint32_t phase) {
+  // bounded spin: a phase-accounting bug must surface as a launch failure (trap), never as a hung GPU
+  const uint32_t addr = sdb_smem_u32(bar);
+  for (uint32_t spins = 0;; ++spins) {
+    uint32_t done;
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+        "selp.u32 %0, 1, 0, p;\n"
+        "}\n" : "=r"(done) : "r"(addr), "r"(phase) : "memory");
+    if (done) return;
+    if (spins > (1u << 22)) __trap();
+  }
+}
 __device__ __forceinline__ void sdb_mbar_wait(uint64_t* bar, uint32_t phase) {
   asm volatile(
       "{\n"

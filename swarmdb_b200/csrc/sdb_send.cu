@@ -375,6 +375,163 @@ k_group_fanout_warp(sdb_dev_view v, const sdb_send_desc* __restrict__ descs, uin
 }
 
 // ------------------------------------------------------------------------------------------
+// K2, variant D ("deep"): warp per send like variant C, for batches of many small sends (a
+// shard's share of a group at N = 8 is ~8 records; payloads up to 480 bytes).  Everything a send
+// needs arrives through shared-memory rings filled by TMA well ahead of its use:
+//   * descriptor ring (16 deep) and payload ring (8 deep) per warp, refilled FOUR sends at a time
+//     by four lanes in parallel, so the issue cost of the loads is paid once per four sends and
+//     5-8 payloads are always in flight per warp: that covers the NVLink round trip when the wire
+//     batch lives in a peer GPU, and no descriptor field is held in registers across iterations;
+//   * a payload stage is [32-byte header template | payload]: the warp stores straight out of
+//     shared memory, one LDS.128 + STG.128 per 16-byte chunk, patching only the sequence number
+//     (chunk 0) and the receiver (chunk 1) with predicated arithmetic - no branches in the walk;
+//   * members are walked in tiles of 32 with the next tile's ids (same send or next send)
+//     prefetched into registers while the current tile is written.
+// Same flat (record, chunk) walk and the same output bytes as variant C.
+// ------------------------------------------------------------------------------------------
+constexpr int SDB_DEEP_PAY = 8, SDB_DEEP_DESC = 16, SDB_DEEP_REFILL = 4;
+template <int WARPS>
+__global__ void __launch_bounds__(WARPS * 32, 8)
+k_group_fanout_deep(sdb_dev_view v, const sdb_send_desc* __restrict__ descs, uint32_t n,
+                    const uint8_t* __restrict__ payload, const uint32_t* __restrict__ tmp_list,
+                    uint64_t seq_base, uint64_t arena_base, uint32_t stage_bytes) {
+  constexpr uint32_t PAY = SDB_DEEP_PAY, DESC = SDB_DEEP_DESC, REFILL = SDB_DEEP_REFILL;
+  static_assert(DESC == PAY + 2 * REFILL && PAY == 2 * REFILL, "refill schedule below assumes these distances");
+  extern __shared__ __align__(128) uint8_t s_dyn[];          // per warp: DESC descriptors, then PAY stages of stage_bytes
+  __shared__ __align__(8) uint64_t s_dbar[WARPS][DESC];
+  __shared__ __align__(8) uint64_t s_pbar[WARPS][PAY];
+  const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const size_t per_warp = static_cast<size_t>(DESC) * sizeof(sdb_send_desc) + static_cast<size_t>(PAY) * stage_bytes;
+  uint8_t* const wbase = s_dyn + warp * per_warp;
+  const sdb_send_desc* const s_desc = reinterpret_cast<const sdb_send_desc*>(wbase);
+  uint8_t* const s_pay = wbase + DESC * sizeof(sdb_send_desc);
+  if (lane < DESC) sdb_mbar_init(&s_dbar[warp][lane], 1);
+  if (lane < PAY) sdb_mbar_init(&s_pbar[warp][lane], 1);
+  sdb_fence_barrier_init();
+  __syncwarp();
+  const uint32_t gw = blockIdx.x * WARPS + warp, nw = gridDim.x * WARPS;
+  const uint64_t pol_stream = sdb_policy_evict_first();
+  uint32_t n_enq = 0, n_ovf = 0, n_skip = 0;
+  if (gw >= n) return;
+  const uint32_t mine = (n - gw + nw - 1) / nw;              // sends this warp handles: gw, gw + nw, ...
+
+  auto want_desc = [&](uint32_t t) {                         // one lane: request descriptor t into its ring slot
+    uint64_t* bar = &s_dbar[warp][t & (DESC - 1)];
+    sdb_mbar_expect_tx(bar, sizeof(sdb_send_desc));
+    sdb_tma_load(wbase + (t & (DESC - 1)) * sizeof(sdb_send_desc), descs + (gw + static_cast<size_t>(t) * nw), sizeof(sdb_send_desc), bar);
+  };
+  auto wait_desc = [&](uint32_t t) { sdb_mbar_wait_bounded(&s_dbar[warp][t & (DESC - 1)], (t / DESC) & 1u); };
+  auto want_payload = [&](uint32_t t) {                      // one lane: descriptor t is in shared memory
+    const sdb_send_desc& x = s_desc[t & (DESC - 1)];
+    const uint32_t pl = (x.rgran - 1u) * SDB_GRANULE;
+    if (x.mcount && pl) {
+      uint64_t* bar = &s_pbar[warp][t & (PAY - 1)];
+      sdb_mbar_expect_tx(bar, pl);
+      sdb_tma_load(s_pay + (t & (PAY - 1)) * static_cast<size_t>(stage_bytes) + 32, payload + x.payload_off, pl, bar);
+    }
+  };
+  auto fetch_tile = [&](const sdb_send_desc& x, uint32_t tile, uint32_t& a, uint32_t& q) {
+    const uint32_t j = tile + lane;
+    const uint32_t* m = ((x.flags & SDB_DESC_LIST_TEMP) ? tmp_list : v.members) + x.mstart;
+    a = j < x.mcount ? __ldg(m + j) : 0xFFFFFFFFu;
+    q = (x.flags & SDB_DESC_POS) ? (j < x.mcount ? __ldg(v.member_pos + x.mstart + j) : 0u) : j;
+  };
+
+  // prologue: lanes request the first descriptors / payloads in parallel
+  if (lane < DESC && lane < mine) want_desc(lane);
+  if (lane < PAY && lane < mine) { wait_desc(lane); want_payload(lane); }
+  wait_desc(0);
+  uint32_t a, q;
+  fetch_tile(s_desc[0], 0, a, q);
+  uint32_t pc_c = 0, q32_c = 0, r32_c = 0, rec_c = 0, ch_c = 0;         // cached (record, chunk) walk parameters
+  uint32_t pay_phase = 0;           // bit s = parity of payload slot s: a slot's phase advances only for sends that have a payload AND recipients
+
+  for (uint32_t t = 0; t < mine; ++t) {
+    const sdb_send_desc& d = s_desc[t & (DESC - 1)];
+    const uint32_t mcount = d.mcount, flags = d.flags, rgran = d.rgran;
+    const bool have_next = t + 1 < mine;
+    if (have_next) wait_desc(t + 1);                       // requested at least 9 sends ago
+    if (mcount == 0) {
+      if (have_next) fetch_tile(s_desc[(t + 1) & (DESC - 1)], 0, a, q);
+    } else {
+      const uint32_t padlen = (rgran - 1u) * SDB_GRANULE;
+      const uint32_t PC = (padlen >> 4) + 2u;              // 16-byte chunks per record: 2 header + payload
+      const uint32_t rbytes = rgran * SDB_GRANULE;
+      const uint64_t apos0 = arena_base + d.gran0;
+      uint8_t* const base = sdb_arena_ptr(v, apos0);       // the batch region never wraps
+      const uint32_t sender = d.sender;
+      const bool shared_seq = (flags & SDB_DESC_SHARED_SEQ) != 0;
+      uint8_t* const my = s_pay + (t & (PAY - 1)) * static_cast<size_t>(stage_bytes);
+      uint4* const my4 = reinterpret_cast<uint4*>(my);
+      // record image: header template in front of the payload the TMA put at +32
+      if (lane == 0) my4[0] = sdb_header_lo((flags & SDB_DESC_ABS_SEQ) ? d.seq_abs : seq_base + d.rec0, d.timestamp);
+      if (lane == 1) my4[1] = sdb_header_hi(sender, SDB_NO_RECEIVER, d.group, d.len, d.prio, d.type);
+      if (padlen) {
+        sdb_mbar_wait_bounded(&s_pbar[warp][t & (PAY - 1)], (pay_phase >> (t & (PAY - 1))) & 1u);
+        pay_phase ^= 1u << (t & (PAY - 1));
+        if (d.len + lane < padlen) my[32u + d.len + lane] = 0;   // deterministic pad bytes
+      }
+      __syncwarp();
+      if (PC != pc_c) { pc_c = PC; q32_c = 32u / PC; r32_c = 32u % PC; rec_c = lane / PC; ch_c = lane % PC; }
+      for (uint32_t tile = 0; tile < mcount; tile += 32) {
+        uint32_t na = 0xFFFFFFFFu, nq = 0;
+        if (tile + 32 < mcount) fetch_tile(d, tile + 32, na, nq);
+        else if (have_next) fetch_tile(s_desc[(t + 1) & (DESC - 1)], 0, na, nq);
+        const uint32_t j = tile + lane;
+        const bool skip = j < mcount && (flags & SDB_DESC_SKIP_SENDER) && a == sender;
+        const bool deliver = j < mcount && !skip && a < v.max_agents;
+        n_skip += skip;
+        if (!(flags & SDB_DESC_PULL) && deliver) {           // small / non-group batches: ring slots claimed here, sorted by k_commit
+          const uint16_t meta = static_cast<uint16_t>((static_cast<uint32_t>(d.prio) << 14) | rgran);
+          if (sdb_ring_append(v, a, static_cast<uint32_t>(apos0 + static_cast<uint64_t>(j) * rgran), meta)) ++n_enq; else ++n_ovf;
+        }
+        const uint32_t m = __ballot_sync(0xFFFFFFFFu, deliver);
+        const uint32_t rcv = shared_seq ? SDB_NO_RECEIVER : a;       // header fields that differ per record
+        const uint32_t sq = shared_seq ? 0u : q;
+        const uint32_t nrec = min(32u, mcount - tile);
+        const uint32_t total = nrec * PC;
+        uint32_t rec = rec_c, ch = ch_c;
+        uint8_t* dst = base + static_cast<size_t>(tile) * rbytes + (static_cast<size_t>(lane) << 4);
+        for (uint32_t done = 0; done < total; done += 32, dst += 512) {
+          const uint32_t src = rec & 31u;
+          const uint32_t r_rcv = __shfl_sync(0xFFFFFFFFu, rcv, src), r_sq = __shfl_sync(0xFFFFFFFFu, sq, src);
+          if (rec < nrec && ((m >> src) & 1u)) {
+            uint4 x = my4[ch];
+            const uint32_t add = ch == 0 ? r_sq : 0u;        // chunk 0 starts with the 64-bit sequence number
+            const uint32_t lo = x.x + add;
+            const uint32_t hi = x.y + (lo < add ? 1u : 0u);
+            x.x = lo;
+            x.y = ch == 1 ? r_rcv : hi;                        // chunk 1 is {sender, receiver, group, len|prio|type}
+            sdb_st_stream_pol(dst, x, pol_stream);
+          }
+          ch += r32_c; rec += q32_c;
+          if (ch >= PC) { ch -= PC; ++rec; }
+        }
+        a = na; q = nq;
+      }
+    }
+    __syncwarp();                                           // every lane is done with descriptor t and payload stage t
+    if ((t & (REFILL - 1)) == REFILL - 1 && lane < REFILL) {
+      // sends t-3..t have retired: their payload stages take sends t+5..t+8 (descriptors arrived long ago),
+      // their descriptor slots take sends t+13..t+16
+      const uint32_t u = t + PAY - REFILL + 1 + lane, w = t + DESC - REFILL + 1 + lane;
+      if (u < mine) { wait_desc(u); want_payload(u); }
+      if (w < mine) want_desc(w);
+    }
+  }
+  for (int o = 16; o; o >>= 1) {
+    n_enq += __shfl_xor_sync(0xFFFFFFFFu, n_enq, o);
+    n_ovf += __shfl_xor_sync(0xFFFFFFFFu, n_ovf, o);
+    n_skip += __shfl_xor_sync(0xFFFFFFFFu, n_skip, o);
+  }
+  if (lane == 0) {
+    if (n_enq) atomicAdd(&v.ctr->enqueued, n_enq);
+    if (n_ovf) atomicAdd(&v.ctr->ring_overflow, n_ovf);
+    if (n_skip) atomicAdd(&v.ctr->skipped_sender, n_skip);
+  }
+}
+
+// ------------------------------------------------------------------------------------------
 // K1: point-to-point enqueue.  One warp per record: lanes 0-1 build the header, lanes 2.. copy
 // payload chunks global -> global with streaming 16-byte accesses; lane 0 claims the ring slot.
 // Algorithmic bytes: 2 (L+H) per record.
@@ -685,7 +842,25 @@ extern "C" cudaError_t sdb_launch_fanout(const sdb_dev_view* v, const sdb_send_d
                                          int variant, int sm_count, cudaStream_t stream, sdb_profiler* prof) {
   if (n == 0) return cudaSuccess;
   const int pi = sdb_prof_begin(prof, SDB_PK_FANOUT, stream);
-  if (variant == 2 && max_padlen <= 4096) {
+  if (variant == 3 && max_padlen <= 480) {
+    constexpr int WARPS = 4;
+    const uint32_t stage = (max_padlen + 32u + 127u) & ~127u;       // header template + payload
+    const size_t smem = static_cast<size_t>(WARPS) * (SDB_DEEP_DESC * sizeof(sdb_send_desc) + static_cast<size_t>(SDB_DEEP_PAY) * stage);
+    static bool attr_set = false;
+    if (!attr_set) {
+      cudaFuncSetAttribute(k_group_fanout_deep<WARPS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                           WARPS * (SDB_DEEP_DESC * 64 + SDB_DEEP_PAY * 512));
+      attr_set = true;
+    }
+    uint32_t per_sm = 8;
+    while (per_sm > 1 && per_sm * (smem + 1024) > 200 * 1024) per_sm >>= 1;
+    static int mult = 0;                                    // CTA waves per SM slot: > 1 lets the block scheduler even out the tail
+    if (!mult) { const char* e = getenv("SDB_FANOUT_WAVES"); mult = e ? atoi(e) : 4; if (mult < 1) mult = 1; }
+    uint32_t grid = static_cast<uint32_t>(sm_count) * per_sm * static_cast<uint32_t>(mult);
+    const uint32_t need = (n + WARPS - 1) / WARPS;
+    if (grid > need) grid = need;
+    k_group_fanout_deep<WARPS><<<grid, WARPS * 32, smem, stream>>>(*v, descs, n, payload, tmp_list, seq_base, arena_base, stage);
+  } else if ((variant == 2 || variant == 3) && max_padlen <= 4096) {
     constexpr int WARPS = 4;
     const uint32_t stage = ((max_padlen ? max_padlen : 16) + 127u) & ~127u;
     const size_t smem = static_cast<size_t>(WARPS) * 2 * stage;
@@ -700,7 +875,7 @@ extern "C" cudaError_t sdb_launch_fanout(const sdb_dev_view* v, const sdb_send_d
     const uint32_t need = (n + WARPS - 1) / WARPS;
     if (grid > need) grid = need;
     k_group_fanout_warp<WARPS><<<grid, WARPS * 32, smem, stream>>>(*v, descs, n, payload, tmp_list, seq_base, arena_base, stage);
-  } else if (variant == 0 || variant == 2) {
+  } else if (variant == 0 || variant == 2 || variant == 3) {
     constexpr int T = 256;
     const size_t smem = max_padlen ? max_padlen : 16;
     static bool attr_set = false;

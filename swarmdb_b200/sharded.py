@@ -196,7 +196,7 @@ def run_sharded_bench(args, rank: int, world: int, local_rank: int, wl):
     shard = Shard(max_agents=wl.A, ring_slots=ring_slots, arena_bytes=1 << 33,
                   max_payload_bytes=wl.L, max_groups=1 << 14, member_pool_entries=wl.A + 1024, max_batch_sends=wl.S,
                   max_batch_payload=wl.S * wl.L, max_recv_records=recv_cap, max_recv_payload=recv_cap * wl.L,
-                  device=local_rank, shard_id=rank, num_shards=world, fanout_variant=2)
+                  device=local_rank, shard_id=rank, num_shards=world, fanout_variant=args.variant)
     shard.set_stream(stream.cuda_stream)
     smap = shard_map_numbered("agent_", 7, wl.A, world)
     shard.set_agent_shards(smap)

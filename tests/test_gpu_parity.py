@@ -40,7 +40,7 @@ def _pair(max_agents, max_groups=8, **kw):
     return g, c
 
 
-@pytest.mark.parametrize("variant", [0, 1, 2])
+@pytest.mark.parametrize("variant", [0, 1, 2, 3])
 def test_p2p_then_drain(variant):
     rng = np.random.default_rng(11)
     A = 200
@@ -61,7 +61,7 @@ def test_p2p_then_drain(variant):
     assert st["enqueued"] == 9000 and st["delivered"] == 9000 and st["ring_overflow"] == 0
 
 
-@pytest.mark.parametrize("variant", [0, 1, 2])
+@pytest.mark.parametrize("variant", [0, 1, 2, 3])
 @pytest.mark.parametrize("fixed", [True, False])
 def test_group_fanout_parity(variant, fixed):
     rng = np.random.default_rng(5 + variant)
@@ -245,7 +245,7 @@ def test_large_payloads_all_kernel_variants(max_len):
     """Payloads above 4 KiB leave the warp-per-send kernel for the CTA-per-send variants."""
     rng = np.random.default_rng(max_len)
     A, G = 300, 6
-    for variant in (0, 1, 2):
+    for variant in (0, 1, 2, 3):
         g, c = _pair(A, max_groups=G, fanout_variant=variant, max_payload_bytes=max_len, arena_bytes=1 << 28,
                      max_batch_sends=64, max_batch_payload=64 * ((max_len + 31) & ~31) + 64, ring_slots=256,
                      max_recv_records=4096, max_recv_payload=1 << 28)

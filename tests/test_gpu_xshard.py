@@ -311,3 +311,53 @@ def test_sharded_frontend_two_ranks_on_one_gpu(tmp_path):
         dbs[0].send_message(AGENTS[0], "x", "stranger")
     for d in dbs + [single]:
         d.close()
+
+
+@pytest.mark.parametrize("variant", [2, 3])
+def test_many_narrow_sends_with_empty_shares_and_empty_payloads(variant):
+    """Every fan-out warp walks more sends than its prefetch rings are deep, and many of them have no
+    local recipient (tiny groups, 4 shards) or no payload bytes: slot/phase accounting of the pipelines."""
+    import torch
+    from oracle.cpu_ref import CpuOracle
+    from swarmdb_b200._native import Shard
+    from swarmdb_b200.sharded import shard_map_numbered
+
+    world, A, G, S = 4, 4096, 2000, 30000
+    rng = np.random.default_rng(77)
+    smap = shard_map_numbered("agent_", 7, A, world)
+    groups = [rng.choice(A, size=int(rng.integers(1, 4)), replace=False) for _ in range(G)]
+    cap = S * 64 + 64
+    shards = []
+    for r in range(world):
+        s = Shard(max_agents=A, max_groups=G, ring_slots=512, arena_bytes=1 << 27, max_batch_sends=S, max_payload_bytes=64,
+                  max_batch_payload=cap, shard_id=r, num_shards=world, max_recv_records=1 << 18, fanout_variant=variant)
+        s.set_agent_shards(smap)
+        for g, m in enumerate(groups):
+            s.create_group(g, m)
+        shards.append(s)
+    oracle = CpuOracle(A, G)
+    for g, m in enumerate(groups):
+        oracle.create_group(g, m)
+    wire_bytes = shards[0].wire_bytes(S, cap)
+    wire = torch.zeros(world * wire_bytes, dtype=torch.uint8, device="cuda")
+    for step in range(2):
+        for r in range(world):
+            sender = rng.integers(0, A, S); grp = rng.integers(0, G, S)
+            prio = rng.integers(0, 4, S); typ = rng.integers(0, 7, S)
+            lens = rng.integers(0, 65, S).astype(np.uint16)
+            lens[rng.random(S) < 0.3] = 0                       # a third of the sends carry no payload at all
+            off = np.arange(S, dtype=np.uint64) * 64
+            buf = rng.integers(48, 123, S * 64 + 64).astype(np.uint8)
+            shards[r].export_group_batch(sender, grp, prio, typ, lens, off, buf, wire.data_ptr() + r * wire_bytes, wire_bytes)
+            shards[r].sync()
+            oracle.send_group_batch(sender, grp, prio, typ, lens, off, buf)
+        for s in shards:
+            s.import_wire_batches(world, wire.data_ptr(), wire_bytes)
+        for r, s in enumerate(shards):
+            local = np.nonzero(smap == r)[0].astype(np.uint32)
+            cg, hg, pg = s.receive_batch(local, 1000)
+            cc, hc, pc = oracle.receive_batch(local, 1000, rec_cap=1 << 18)
+            assert np.array_equal(cg, cc) and hg.tobytes() == hc.tobytes() and pg.tobytes() == pc.tobytes(), (step, r)
+    for s in shards:
+        assert s.stats()["ring_overflow"] == 0
+        s.close()
