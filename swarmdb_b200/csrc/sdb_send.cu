@@ -375,36 +375,55 @@ k_group_fanout_warp(sdb_dev_view v, const sdb_send_desc* __restrict__ descs, uin
 }
 
 // ------------------------------------------------------------------------------------------
-// K2, variant D ("deep"): warp per send like variant C, for batches of many small sends (a
-// shard's share of a group at N = 8 is ~8 records; payloads up to 480 bytes).  Everything a send
-// needs arrives through shared-memory rings filled by TMA well ahead of its use:
-//   * descriptor ring (16 deep) and payload ring (8 deep) per warp, refilled FOUR sends at a time
-//     by four lanes in parallel, so the issue cost of the loads is paid once per four sends and
-//     5-8 payloads are always in flight per warp: that covers the NVLink round trip when the wire
-//     batch lives in a peer GPU, and no descriptor field is held in registers across iterations;
-//   * a payload stage is [32-byte header template | payload]: the warp stores straight out of
-//     shared memory, one LDS.128 + STG.128 per 16-byte chunk, patching only the sequence number
-//     (chunk 0) and the receiver (chunk 1) with predicated arithmetic - no branches in the walk;
-//   * members are walked in tiles of 32 with the next tile's ids (same send or next send)
-//     prefetched into registers while the current tile is written.
-// Same flat (record, chunk) walk and the same output bytes as variant C.
+// K2, variant D ("span"): for batches of many small sends (a shard's share of a group at N = 8
+// is ~8 records; payloads up to 512 bytes), where variant C's ~400 warp-instructions of per-send
+// bookkeeping - not HBM - set the pace.  Two ideas:
+//   * everything a send needs arrives through shared-memory rings filled by TMA well ahead of
+//     its use: a 16-deep descriptor ring and an 8-deep payload ring per warp, refilled FOUR sends
+//     at a time by four lanes in parallel.  5-8 payloads are in flight per warp, which covers the
+//     NVLink round trip when the wire batch lives in a peer GPU, and no descriptor field is held
+//     in registers across iterations;
+//   * the unit of work is a TILE of up to 32 records that may span several sends (whole sends of
+//     one refill group, or 32 members of a wide send).  Lane r prepares record r - descriptor
+//     fields, member id, ring claim, the 32-byte header, destination - IN PARALLEL and parks it in
+//     a per-warp table; the copy loop then walks the tile's 16-byte chunks flat, one LDS.128 for
+//     the table entry, one for the data (header table or staged payload), one STG.128.  The
+//     per-send scalar work of variant C becomes per-tile SIMD work.
+// The next tile's plan and member ids are computed/loaded while the current tile is written.
+// Output bytes are identical to variants A-C.
 // ------------------------------------------------------------------------------------------
-constexpr int SDB_DEEP_PAY = 8, SDB_DEEP_DESC = 16, SDB_DEEP_REFILL = 4;
+constexpr uint32_t SDB_SPAN_PAY = 8, SDB_SPAN_DESC = 16, SDB_SPAN_GROUP = 4;
+constexpr uint32_t SDB_SPAN_TABLES = 32 * 32 + 32 * 16;          // header table + record table, bytes per warp
+
+__device__ __forceinline__ uint4 sdb_lds128(uint32_t saddr) {
+  uint4 r;
+  asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "r"(saddr) : "memory");
+  return r;
+}
+__device__ __forceinline__ uint32_t sdb_lds32(uint32_t saddr) {
+  uint32_t r;
+  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(r) : "r"(saddr) : "memory");
+  return r;
+}
+
 template <int WARPS>
 __global__ void __launch_bounds__(WARPS * 32, 8)
-k_group_fanout_deep(sdb_dev_view v, const sdb_send_desc* __restrict__ descs, uint32_t n,
+k_group_fanout_span(sdb_dev_view v, const sdb_send_desc* __restrict__ descs, uint32_t n,
                     const uint8_t* __restrict__ payload, const uint32_t* __restrict__ tmp_list,
                     uint64_t seq_base, uint64_t arena_base, uint32_t stage_bytes) {
-  constexpr uint32_t PAY = SDB_DEEP_PAY, DESC = SDB_DEEP_DESC, REFILL = SDB_DEEP_REFILL;
-  static_assert(DESC == PAY + 2 * REFILL && PAY == 2 * REFILL, "refill schedule below assumes these distances");
-  extern __shared__ __align__(128) uint8_t s_dyn[];          // per warp: DESC descriptors, then PAY stages of stage_bytes
+  constexpr uint32_t PAY = SDB_SPAN_PAY, DESC = SDB_SPAN_DESC, GROUP = SDB_SPAN_GROUP, NONE = 0xFFFFFFFFu;
+  static_assert(DESC == 4 * GROUP && PAY == 2 * GROUP, "refill schedule below assumes these distances");
+  extern __shared__ __align__(128) uint8_t s_dyn[];          // per warp: descriptors | header table | record table | payload stages
   __shared__ __align__(8) uint64_t s_dbar[WARPS][DESC];
   __shared__ __align__(8) uint64_t s_pbar[WARPS][PAY];
   const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const size_t per_warp = static_cast<size_t>(DESC) * sizeof(sdb_send_desc) + static_cast<size_t>(PAY) * stage_bytes;
+  const size_t per_warp = DESC * sizeof(sdb_send_desc) + SDB_SPAN_TABLES + static_cast<size_t>(PAY) * stage_bytes;
   uint8_t* const wbase = s_dyn + warp * per_warp;
   const sdb_send_desc* const s_desc = reinterpret_cast<const sdb_send_desc*>(wbase);
-  uint8_t* const s_pay = wbase + DESC * sizeof(sdb_send_desc);
+  uint4* const s_hdr = reinterpret_cast<uint4*>(wbase + DESC * sizeof(sdb_send_desc));            // [32][2]
+  uint4* const s_rec = s_hdr + 64;                                                                  // [32] {dst lo, dst hi, payload smem addr, chunks}
+  uint8_t* const s_pay = wbase + DESC * sizeof(sdb_send_desc) + SDB_SPAN_TABLES;
+  const uint32_t hdr_sa = sdb_smem_u32(s_hdr), rec_sa = sdb_smem_u32(s_rec), pay_sa = sdb_smem_u32(s_pay);
   if (lane < DESC) sdb_mbar_init(&s_dbar[warp][lane], 1);
   if (lane < PAY) sdb_mbar_init(&s_pbar[warp][lane], 1);
   sdb_fence_barrier_init();
@@ -427,97 +446,140 @@ k_group_fanout_deep(sdb_dev_view v, const sdb_send_desc* __restrict__ descs, uin
     if (x.mcount && pl) {
       uint64_t* bar = &s_pbar[warp][t & (PAY - 1)];
       sdb_mbar_expect_tx(bar, pl);
-      sdb_tma_load(s_pay + (t & (PAY - 1)) * static_cast<size_t>(stage_bytes) + 32, payload + x.payload_off, pl, bar);
+      sdb_tma_load(s_pay + (t & (PAY - 1)) * static_cast<size_t>(stage_bytes), payload + x.payload_off, pl, bar);
     }
   };
-  auto fetch_tile = [&](const sdb_send_desc& x, uint32_t tile, uint32_t& a, uint32_t& q) {
-    const uint32_t j = tile + lane;
-    const uint32_t* m = ((x.flags & SDB_DESC_LIST_TEMP) ? tmp_list : v.members) + x.mstart;
-    a = j < x.mcount ? __ldg(m + j) : 0xFFFFFFFFu;
-    q = (x.flags & SDB_DESC_POS) ? (j < x.mcount ? __ldg(v.member_pos + x.mstart + j) : 0u) : j;
+
+  // ---- tile plan: (t, joff) uniform -> this lane's record (send ts, member j), the tile's record count, the next tile's start
+  uint32_t ts, j, a = NONE, q = 0, nrec, t_next, joff_next;
+  auto plan = [&](uint32_t t, uint32_t joff) {
+    ts = NONE; j = 0; nrec = 0; a = NONE; q = 0;
+    if (t >= mine) { t_next = t; joff_next = 0; return; }
+    const uint32_t gend = min((t & ~(GROUP - 1)) + GROUP, mine);
+    if ((t & (GROUP - 1)) == 0 && joff == 0)                  // first tile of a refill group: its descriptors were requested >= 8 sends ago
+      for (uint32_t u = t; u < gend; ++u) wait_desc(u);
+    uint32_t tt = t;
+    const uint32_t rem = s_desc[tt & (DESC - 1)].mcount - joff;
+    if (rem > 32u) { ts = tt; j = joff + lane; nrec = 32u; t_next = tt; joff_next = joff + 32u; }
+    else {
+      if (lane < rem) { ts = tt; j = joff + lane; }
+      nrec = rem; ++tt;
+      while (tt < gend) {                                    // whole following sends of the group while they fit
+        const uint32_t m = s_desc[tt & (DESC - 1)].mcount;
+        if (nrec + m > 32u) break;
+        if (lane >= nrec && lane < nrec + m) { ts = tt; j = lane - nrec; }
+        nrec += m; ++tt;
+      }
+      t_next = tt; joff_next = 0;
+    }
+    if (ts != NONE) {                                        // member id (and original group position) of this lane's record
+      const sdb_send_desc& x = s_desc[ts & (DESC - 1)];
+      const uint32_t fl = x.flags, ms = x.mstart;
+      a = __ldg(((fl & SDB_DESC_LIST_TEMP) ? tmp_list : v.members) + ms + j);
+      q = (fl & SDB_DESC_POS) ? __ldg(v.member_pos + ms + j) : j;
+    }
   };
 
   // prologue: lanes request the first descriptors / payloads in parallel
   if (lane < DESC && lane < mine) want_desc(lane);
   if (lane < PAY && lane < mine) { wait_desc(lane); want_payload(lane); }
-  wait_desc(0);
-  uint32_t a, q;
-  fetch_tile(s_desc[0], 0, a, q);
-  uint32_t pc_c = 0, q32_c = 0, r32_c = 0, rec_c = 0, ch_c = 0;         // cached (record, chunk) walk parameters
   uint32_t pay_phase = 0;           // bit s = parity of payload slot s: a slot's phase advances only for sends that have a payload AND recipients
+  uint32_t pc_c = 0, q32_c = 0, r32_c = 0, rec_c = 0, ch_c = 0;         // cached walk parameters of uniform tiles
+  uint32_t t_first = 0, joff_first = 0;
+  plan(0, 0);
 
-  for (uint32_t t = 0; t < mine; ++t) {
-    const sdb_send_desc& d = s_desc[t & (DESC - 1)];
-    const uint32_t mcount = d.mcount, flags = d.flags, rgran = d.rgran;
-    const bool have_next = t + 1 < mine;
-    if (have_next) wait_desc(t + 1);                       // requested at least 9 sends ago
-    if (mcount == 0) {
-      if (have_next) fetch_tile(s_desc[(t + 1) & (DESC - 1)], 0, a, q);
-    } else {
-      const uint32_t padlen = (rgran - 1u) * SDB_GRANULE;
-      const uint32_t PC = (padlen >> 4) + 2u;              // 16-byte chunks per record: 2 header + payload
-      const uint32_t rbytes = rgran * SDB_GRANULE;
-      const uint64_t apos0 = arena_base + d.gran0;
-      uint8_t* const base = sdb_arena_ptr(v, apos0);       // the batch region never wraps
-      const uint32_t sender = d.sender;
-      const bool shared_seq = (flags & SDB_DESC_SHARED_SEQ) != 0;
-      uint8_t* const my = s_pay + (t & (PAY - 1)) * static_cast<size_t>(stage_bytes);
-      uint4* const my4 = reinterpret_cast<uint4*>(my);
-      // record image: header template in front of the payload the TMA put at +32
-      if (lane == 0) my4[0] = sdb_header_lo((flags & SDB_DESC_ABS_SEQ) ? d.seq_abs : seq_base + d.rec0, d.timestamp);
-      if (lane == 1) my4[1] = sdb_header_hi(sender, SDB_NO_RECEIVER, d.group, d.len, d.prio, d.type);
-      if (padlen) {
-        sdb_mbar_wait_bounded(&s_pbar[warp][t & (PAY - 1)], (pay_phase >> (t & (PAY - 1))) & 1u);
-        pay_phase ^= 1u << (t & (PAY - 1));
-        if (d.len + lane < padlen) my[32u + d.len + lane] = 0;   // deterministic pad bytes
-      }
-      __syncwarp();
-      if (PC != pc_c) { pc_c = PC; q32_c = 32u / PC; r32_c = 32u % PC; rec_c = lane / PC; ch_c = lane % PC; }
-      for (uint32_t tile = 0; tile < mcount; tile += 32) {
-        uint32_t na = 0xFFFFFFFFu, nq = 0;
-        if (tile + 32 < mcount) fetch_tile(d, tile + 32, na, nq);
-        else if (have_next) fetch_tile(s_desc[(t + 1) & (DESC - 1)], 0, na, nq);
-        const uint32_t j = tile + lane;
-        const bool skip = j < mcount && (flags & SDB_DESC_SKIP_SENDER) && a == sender;
-        const bool deliver = j < mcount && !skip && a < v.max_agents;
-        n_skip += skip;
-        if (!(flags & SDB_DESC_PULL) && deliver) {           // small / non-group batches: ring slots claimed here, sorted by k_commit
-          const uint16_t meta = static_cast<uint16_t>((static_cast<uint32_t>(d.prio) << 14) | rgran);
-          if (sdb_ring_append(v, a, static_cast<uint32_t>(apos0 + static_cast<uint64_t>(j) * rgran), meta)) ++n_enq; else ++n_ovf;
-        }
-        const uint32_t m = __ballot_sync(0xFFFFFFFFu, deliver);
-        const uint32_t rcv = shared_seq ? SDB_NO_RECEIVER : a;       // header fields that differ per record
-        const uint32_t sq = shared_seq ? 0u : q;
-        const uint32_t nrec = min(32u, mcount - tile);
-        const uint32_t total = nrec * PC;
-        uint32_t rec = rec_c, ch = ch_c;
-        uint8_t* dst = base + static_cast<size_t>(tile) * rbytes + (static_cast<size_t>(lane) << 4);
-        for (uint32_t done = 0; done < total; done += 32, dst += 512) {
-          const uint32_t src = rec & 31u;
-          const uint32_t r_rcv = __shfl_sync(0xFFFFFFFFu, rcv, src), r_sq = __shfl_sync(0xFFFFFFFFu, sq, src);
-          if (rec < nrec && ((m >> src) & 1u)) {
-            uint4 x = my4[ch];
-            const uint32_t add = ch == 0 ? r_sq : 0u;        // chunk 0 starts with the 64-bit sequence number
-            const uint32_t lo = x.x + add;
-            const uint32_t hi = x.y + (lo < add ? 1u : 0u);
-            x.x = lo;
-            x.y = ch == 1 ? r_rcv : hi;                        // chunk 1 is {sender, receiver, group, len|prio|type}
-            sdb_st_stream_pol(dst, x, pol_stream);
-          }
-          ch += r32_c; rec += q32_c;
-          if (ch >= PC) { ch -= PC; ++rec; }
-        }
-        a = na; q = nq;
+  while (t_first < mine) {
+    // this tile: lanes [0, c_nrec) hold (c_ts, c_j, c_a, c_q); it ends before send c_tnext (or inside it when c_jnext != 0)
+    const uint32_t c_ts = ts, c_j = j, c_a = a, c_q = q, c_nrec = nrec, c_tnext = t_next, c_jnext = joff_next;
+    const uint32_t t_last = c_jnext ? c_tnext : c_tnext - 1u;
+
+    // 1. payloads of the sends that start in this tile must have landed; zero their pad bytes
+    for (uint32_t u = t_first + (joff_first ? 1u : 0u); u <= t_last && u < mine; ++u) {
+      const sdb_send_desc& x = s_desc[u & (DESC - 1)];
+      const uint32_t padlen = (x.rgran - 1u) * SDB_GRANULE;
+      if (x.mcount && padlen) {
+        sdb_mbar_wait_bounded(&s_pbar[warp][u & (PAY - 1)], (pay_phase >> (u & (PAY - 1))) & 1u);
+        pay_phase ^= 1u << (u & (PAY - 1));
+        const uint32_t b = x.len + lane;
+        if (b < padlen) s_pay[(u & (PAY - 1)) * static_cast<size_t>(stage_bytes) + b] = 0;
       }
     }
-    __syncwarp();                                           // every lane is done with descriptor t and payload stage t
-    if ((t & (REFILL - 1)) == REFILL - 1 && lane < REFILL) {
-      // sends t-3..t have retired: their payload stages take sends t+5..t+8 (descriptors arrived long ago),
-      // their descriptor slots take sends t+13..t+16
-      const uint32_t u = t + PAY - REFILL + 1 + lane, w = t + DESC - REFILL + 1 + lane;
+
+    // 2. every lane prepares its record and parks it in the tables
+    uint32_t PC = 0;
+    if (c_ts != NONE) {
+      const uint4* dq = reinterpret_cast<const uint4*>(s_desc + (c_ts & (DESC - 1)));
+      const uint4 q0 = dq[0], q1 = dq[1], q2 = dq[2], q3 = dq[3];
+      const uint32_t flags = q3.x, rgran = q1.z, sender = q1.y;
+      const uint32_t lpt = q1.w;                              // len | prio << 16 | type << 24
+      const bool shared_seq = (flags & SDB_DESC_SHARED_SEQ) != 0;
+      const bool skip = (flags & SDB_DESC_SKIP_SENDER) && c_a == sender;
+      const bool deliver = !skip && c_a < v.max_agents;
+      n_skip += skip;
+      const uint64_t apos = arena_base + q1.x + static_cast<uint64_t>(c_j) * rgran;
+      if (!(flags & SDB_DESC_PULL) && deliver) {              // small / non-group batches: ring slots claimed here, sorted by k_commit
+        const uint16_t meta = static_cast<uint16_t>((((lpt >> 16) & 0xFFu) << 14) | rgran);
+        if (sdb_ring_append(v, c_a, static_cast<uint32_t>(apos), meta)) ++n_enq; else ++n_ovf;
+      }
+      const uint64_t seq0 = (flags & SDB_DESC_ABS_SEQ) ? ((static_cast<uint64_t>(q3.w) << 32) | q3.z) : seq_base + q2.x;
+      const uint64_t seq = seq0 + (shared_seq ? 0u : c_q);
+      s_hdr[2 * lane] = make_uint4(static_cast<uint32_t>(seq), static_cast<uint32_t>(seq >> 32), q0.z, q0.w);
+      s_hdr[2 * lane + 1] = make_uint4(sender, shared_seq ? SDB_NO_RECEIVER : c_a, q2.w, lpt);
+      PC = ((rgran - 1u) << 1) + 2u;                          // 16-byte chunks: 2 header + 2 per payload granule
+      const unsigned long long dst = deliver ? reinterpret_cast<unsigned long long>(sdb_arena_ptr(v, apos)) : 0ull;
+      s_rec[lane] = make_uint4(static_cast<uint32_t>(dst), static_cast<uint32_t>(dst >> 32),
+                               pay_sa + (c_ts & (PAY - 1)) * stage_bytes, PC);
+    }
+    const uint32_t PC0 = __shfl_sync(0xFFFFFFFFu, PC, 0);
+    const bool uniform = __all_sync(0xFFFFFFFFu, lane >= c_nrec || PC == PC0);
+    uint32_t total = c_nrec * PC0;
+    if (!uniform) {
+      total = PC;
+      for (int o = 16; o; o >>= 1) total += __shfl_xor_sync(0xFFFFFFFFu, total, o);
+    }
+    __syncwarp();
+
+    // 3. plan the next tile now: its member ids travel while this tile is written
+    plan(c_tnext, c_jnext);
+
+    // 4. flat walk over the tile's chunks, 512 bytes per warp step
+    if (c_nrec) {
+      uint32_t rec, ch;
+      auto advance = [&](uint32_t adv) {                     // generic (record, chunk) += adv for tiles with mixed record sizes
+        while (rec < c_nrec) {
+          const uint32_t pc = sdb_lds32(rec_sa + rec * 16u + 12u);
+          if (ch + adv < pc) { ch += adv; return; }
+          adv -= pc - ch; ++rec; ch = 0;
+        }
+      };
+      if (uniform) {
+        if (PC0 != pc_c) { pc_c = PC0; q32_c = 32u / PC0; r32_c = 32u % PC0; rec_c = lane / PC0; ch_c = lane % PC0; }
+        rec = rec_c; ch = ch_c;
+      } else { rec = 0; ch = 0; advance(lane); }
+      for (uint32_t done = 0; done < total; done += 32) {
+        if (rec < c_nrec) {
+          const uint4 e = sdb_lds128(rec_sa + rec * 16u);
+          if (e.x | e.y) {
+            const uint32_t src = ch < 2u ? hdr_sa + rec * 32u + ch * 16u : e.z + (ch - 2u) * 16u;
+            const uint4 x = sdb_lds128(src);
+            uint8_t* dst = reinterpret_cast<uint8_t*>((static_cast<unsigned long long>(e.y) << 32) | e.x) + ch * 16u;
+            sdb_st_stream_pol(dst, x, pol_stream);
+          }
+        }
+        if (uniform) { ch += r32_c; rec += q32_c; if (ch >= PC0) { ch -= PC0; ++rec; } }
+        else advance(32u);
+      }
+    }
+    __syncwarp();                                           // tables and (at a group end) stages are free again
+
+    // 5. a refill group has retired: its payload stages take sends g+8..g+11, its descriptor slots g+16..g+19
+    if (c_jnext == 0 && ((c_tnext & (GROUP - 1)) == 0 || c_tnext >= mine) && lane < GROUP) {
+      const uint32_t g0 = t_first & ~(GROUP - 1);
+      const uint32_t u = g0 + PAY + lane, w = g0 + DESC + lane;
       if (u < mine) { wait_desc(u); want_payload(u); }
       if (w < mine) want_desc(w);
     }
+    t_first = c_tnext; joff_first = c_jnext;
   }
   for (int o = 16; o; o >>= 1) {
     n_enq += __shfl_xor_sync(0xFFFFFFFFu, n_enq, o);
@@ -842,24 +904,24 @@ extern "C" cudaError_t sdb_launch_fanout(const sdb_dev_view* v, const sdb_send_d
                                          int variant, int sm_count, cudaStream_t stream, sdb_profiler* prof) {
   if (n == 0) return cudaSuccess;
   const int pi = sdb_prof_begin(prof, SDB_PK_FANOUT, stream);
-  if (variant == 3 && max_padlen <= 480) {
+  if (variant == 3 && max_padlen <= 512) {
     constexpr int WARPS = 4;
-    const uint32_t stage = (max_padlen + 32u + 127u) & ~127u;       // header template + payload
-    const size_t smem = static_cast<size_t>(WARPS) * (SDB_DEEP_DESC * sizeof(sdb_send_desc) + static_cast<size_t>(SDB_DEEP_PAY) * stage);
+    const uint32_t stage = ((max_padlen ? max_padlen : 16) + 127u) & ~127u;
+    const size_t smem = static_cast<size_t>(WARPS) * (SDB_SPAN_DESC * sizeof(sdb_send_desc) + SDB_SPAN_TABLES + static_cast<size_t>(SDB_SPAN_PAY) * stage);
     static bool attr_set = false;
     if (!attr_set) {
-      cudaFuncSetAttribute(k_group_fanout_deep<WARPS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                           WARPS * (SDB_DEEP_DESC * 64 + SDB_DEEP_PAY * 512));
+      cudaFuncSetAttribute(k_group_fanout_span<WARPS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                           WARPS * (SDB_SPAN_DESC * 64 + SDB_SPAN_TABLES + SDB_SPAN_PAY * 512));
       attr_set = true;
     }
     uint32_t per_sm = 8;
-    while (per_sm > 1 && per_sm * (smem + 1024) > 200 * 1024) per_sm >>= 1;
+    while (per_sm > 1 && per_sm * (smem + 1024) > 200 * 1024) --per_sm;
     static int mult = 0;                                    // CTA waves per SM slot: > 1 lets the block scheduler even out the tail
     if (!mult) { const char* e = getenv("SDB_FANOUT_WAVES"); mult = e ? atoi(e) : 4; if (mult < 1) mult = 1; }
     uint32_t grid = static_cast<uint32_t>(sm_count) * per_sm * static_cast<uint32_t>(mult);
     const uint32_t need = (n + WARPS - 1) / WARPS;
     if (grid > need) grid = need;
-    k_group_fanout_deep<WARPS><<<grid, WARPS * 32, smem, stream>>>(*v, descs, n, payload, tmp_list, seq_base, arena_base, stage);
+    k_group_fanout_span<WARPS><<<grid, WARPS * 32, smem, stream>>>(*v, descs, n, payload, tmp_list, seq_base, arena_base, stage);
   } else if ((variant == 2 || variant == 3) && max_padlen <= 4096) {
     constexpr int WARPS = 4;
     const uint32_t stage = ((max_padlen ? max_padlen : 16) + 127u) & ~127u;
