@@ -7,7 +7,6 @@
 #include <cuda_runtime.h>
 
 #include <algorithm>
-#include <cstdlib>
 #include <cstdio>
 #include <cstring>
 #include <new>
@@ -18,6 +17,7 @@
 
 extern "C" {
 cudaError_t sdb_launch_p2p(const sdb_dev_view*, const sdb_send_desc*, uint32_t, const uint8_t*, uint64_t, uint64_t, int, cudaStream_t, sdb_profiler*);
+cudaError_t sdb_send_prepare_device();
 cudaError_t sdb_launch_fanout(const sdb_dev_view*, const sdb_send_desc*, uint32_t, const uint8_t*, const uint32_t*,
                               uint64_t, uint64_t, uint32_t, int, int, cudaStream_t, sdb_profiler*);
 cudaError_t sdb_launch_commit(const sdb_dev_view*, uint32_t, uint32_t, uint32_t*, uint32_t*, int, cudaStream_t, sdb_profiler*);
@@ -434,6 +434,7 @@ int sdb_create(const sdb_config* cfg, sdb_handle* out) {
     return fail(h, SDB_ECUDA, "no CUDA device: swarmdb_b200 has no CPU fallback");
   if (c.device < 0 || c.device >= ndev) return fail(h, SDB_EINVAL, "device ordinal out of range");
   CUDA_TRY(h, cudaSetDevice(c.device));
+  CUDA_TRY(h, sdb_send_prepare_device());
   cudaDeviceProp prop;
   CUDA_TRY(h, cudaGetDeviceProperties(&prop, c.device));
   h->sm_count = prop.multiProcessorCount;

@@ -898,6 +898,16 @@ extern "C" cudaError_t sdb_launch_p2p(const sdb_dev_view* v, const sdb_send_desc
   return cudaGetLastError();
 }
 
+// dynamic shared memory limits are per device and per function: set once for the device a handle is created on
+extern "C" cudaError_t sdb_send_prepare_device() {
+  cudaError_t e;
+  if ((e = cudaFuncSetAttribute(k_group_fanout_span<4>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                4 * (SDB_SPAN_DESC * 64 + SDB_SPAN_TABLES + SDB_SPAN_PAY * 512))) != cudaSuccess) return e;
+  if ((e = cudaFuncSetAttribute(k_group_fanout_warp<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * 4 * 4096 + 512)) != cudaSuccess) return e;
+  if ((e = cudaFuncSetAttribute(k_group_fanout_st<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, 65536 + 1024)) != cudaSuccess) return e;
+  return cudaFuncSetAttribute(k_group_fanout_tma<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * 65536 + 1024);
+}
+
 extern "C" cudaError_t sdb_launch_fanout(const sdb_dev_view* v, const sdb_send_desc* descs, uint32_t n,
                                          const uint8_t* payload, const uint32_t* tmp_list,
                                          uint64_t seq_base, uint64_t arena_base, uint32_t max_padlen,
@@ -908,12 +918,6 @@ extern "C" cudaError_t sdb_launch_fanout(const sdb_dev_view* v, const sdb_send_d
     constexpr int WARPS = 4;
     const uint32_t stage = ((max_padlen ? max_padlen : 16) + 127u) & ~127u;
     const size_t smem = static_cast<size_t>(WARPS) * (SDB_SPAN_DESC * sizeof(sdb_send_desc) + SDB_SPAN_TABLES + static_cast<size_t>(SDB_SPAN_PAY) * stage);
-    static bool attr_set = false;
-    if (!attr_set) {
-      cudaFuncSetAttribute(k_group_fanout_span<WARPS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                           WARPS * (SDB_SPAN_DESC * 64 + SDB_SPAN_TABLES + SDB_SPAN_PAY * 512));
-      attr_set = true;
-    }
     uint32_t per_sm = 8;
     while (per_sm > 1 && per_sm * (smem + 1024) > 200 * 1024) --per_sm;
     static int mult = 0;                                    // CTA waves per SM slot: > 1 lets the block scheduler even out the tail
@@ -926,11 +930,6 @@ extern "C" cudaError_t sdb_launch_fanout(const sdb_dev_view* v, const sdb_send_d
     constexpr int WARPS = 4;
     const uint32_t stage = ((max_padlen ? max_padlen : 16) + 127u) & ~127u;
     const size_t smem = static_cast<size_t>(WARPS) * 2 * stage;
-    static bool attr_set = false;
-    if (!attr_set) {
-      cudaFuncSetAttribute(k_group_fanout_warp<WARPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * 4 * 4096 + 512);
-      attr_set = true;
-    }
     uint32_t per_sm = 16;
     while (per_sm > 1 && per_sm * (smem + 256) > 200 * 1024) per_sm >>= 1;
     uint32_t grid = static_cast<uint32_t>(sm_count) * per_sm;
@@ -940,22 +939,12 @@ extern "C" cudaError_t sdb_launch_fanout(const sdb_dev_view* v, const sdb_send_d
   } else if (variant == 0 || variant == 2 || variant == 3) {
     constexpr int T = 256;
     const size_t smem = max_padlen ? max_padlen : 16;
-    static bool attr_set = false;
-    if (!attr_set) {
-      cudaFuncSetAttribute(k_group_fanout_st<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, 65536 + 1024);
-      attr_set = true;
-    }
     uint32_t grid = static_cast<uint32_t>(sm_count) * 8u;           // persistent: 8 CTAs of 256 threads per SM
     if (grid > n) grid = n;
     k_group_fanout_st<T><<<grid, T, smem, stream>>>(*v, descs, n, payload, tmp_list, seq_base, arena_base);
   } else {
     constexpr int T = 64;
     const uint32_t stage = ((max_padlen ? max_padlen : 16) + 127u) & ~127u;
-    static bool attr_set = false;
-    if (!attr_set) {
-      cudaFuncSetAttribute(k_group_fanout_tma<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * 65536 + 1024);
-      attr_set = true;
-    }
     uint32_t per_sm = 16;
     const size_t smem = 2ull * stage;
     while (per_sm > 1 && per_sm * (smem + 1024) > 200 * 1024) per_sm >>= 1;
