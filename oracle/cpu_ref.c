@@ -220,36 +220,28 @@ uint64_t orc_send_list_batch(orc* o, uint32_t n, const uint32_t* sender, const u
   return base;
 }
 
-/* receive_messages for a list of agents, M:521-601.  Output format of sdb_receive_batch. */
+/* receive_messages for a list of agents, M:521-601.  Output format of sdb_receive_batch.
+ * SDB_RECV_PEEK (extension, include/swarmdb_b200.h): the same selection, nothing is consumed. */
 uint64_t orc_receive_batch(orc* o, uint32_t n_agents, const uint32_t* agent_idx, uint32_t max_messages, uint32_t flags,
                            uint32_t* count_out, sdb_msg_header* hdr_out, uint8_t* payload_out, uint64_t* payload_bytes) {
   uint64_t total = 0, pbytes = 0;
+  const int peek = (flags & SDB_RECV_PEEK) != 0;
   if (!agent_idx) n_agents = o->watermark;
   for (uint32_t q = 0; q < n_agents; ++q) {
     const uint32_t a = agent_idx ? agent_idx[q] : q;
     orc_inbox* in = &o->inbox[a];
     uint32_t got = 0;
-    if (flags & SDB_RECV_PRIORITY) {
-      for (int L = 3; L >= 0 && got < max_messages; --L)
-        for (uint64_t p = in->head; p < in->n && got < max_messages; ++p) {
-          if (in->done[p]) continue;
-          const orc_rec* r = &o->recs[in->idx[p]];
-          if (r->hdr.prio != (uint8_t)L) continue;
-          in->done[p] = 1;
-          if (hdr_out) hdr_out[total] = r->hdr;
-          if (payload_out) memcpy(payload_out + pbytes, o->store + r->pay_off, pad32(r->hdr.len));
-          pbytes += pad32(r->hdr.len); ++total; ++got;
-        }
-    } else {
-      for (uint64_t p = in->head; p < in->n && got < max_messages; ++p) {      /* stream order */
+    /* stream order = one pass; priority order = one pass per level, highest first (App. A rule 9) */
+    for (int L = (flags & SDB_RECV_PRIORITY) ? 3 : 0; L >= 0 && got < max_messages; --L)
+      for (uint64_t p = in->head; p < in->n && got < max_messages; ++p) {
         if (in->done[p]) continue;
         const orc_rec* r = &o->recs[in->idx[p]];
-        in->done[p] = 1;
+        if ((flags & SDB_RECV_PRIORITY) && r->hdr.prio != (uint8_t)L) continue;
+        if (!peek) in->done[p] = 1;
         if (hdr_out) hdr_out[total] = r->hdr;
         if (payload_out) memcpy(payload_out + pbytes, o->store + r->pay_off, pad32(r->hdr.len));
         pbytes += pad32(r->hdr.len); ++total; ++got;
       }
-    }
     while (in->head < in->n && in->done[in->head]) in->head++;
     if (count_out) count_out[q] = got;
   }

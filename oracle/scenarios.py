@@ -18,6 +18,7 @@ from __future__ import annotations
 
 import hashlib
 import json
+import os
 from typing import Any, Dict, List, Optional
 
 import numpy as np
@@ -207,9 +208,11 @@ def canon_message(m: Any, id_rank: Dict[str, int]) -> list:
             _enum_val(m.status), m.metadata, m.token_count, sorted(m.visible_to)]
 
 
-def run_ops(db: Any, ops: List[list], enums: Any, recv_timeout: float = 1.0e6) -> List[Any]:
-    """Execute `ops` on `db`; `enums` provides MessageType / MessagePriority for that db."""
-    id_rank: Dict[str, int] = {}
+def run_ops(db: Any, ops: List[list], enums: Any, recv_timeout: float = 1.0e6,
+            id_rank: Dict[str, int] = None) -> List[Any]:
+    """Execute `ops` on `db`; `enums` provides MessageType / MessagePriority for that db.
+    Pass an `id_rank` dict to keep the id -> first-seen-rank map (history_state needs it)."""
+    id_rank = {} if id_rank is None else id_rank
     out: List[Any] = []
     for op in ops:
         kind = op[0]
@@ -253,6 +256,29 @@ def final_state(db: Any) -> Dict[str, Any]:
         "inbox_len": {a: len(v) for a, v in sorted(db.agent_inbox.items())},
         "message_count": db.message_count,
     }
+
+
+def history_state(db: Any, id_rank: Dict[str, int]) -> Dict[str, Any]:
+    """The history file `save_message_history` writes (schema M:878-884), canonicalised: message ids
+    replaced by their first-seen rank, timestamps dropped, sets sorted.  `keys` pins the field order
+    of a stored message (M:54-111)."""
+    name = "golden_history_probe.json"
+    db.save_message_history(name)
+    path = os.path.join(str(db.save_dir), name)
+    with open(path) as f:
+        h = json.load(f)
+    os.remove(path)
+    rank = lambda mid: id_rank.setdefault(mid, len(id_rank))          # noqa: E731
+    msgs = {}
+    keys = None
+    for mid, d in h["messages"].items():
+        assert d["id"] == mid
+        keys = keys or list(d.keys())
+        msgs[str(rank(mid))] = [d["sender_id"], d["receiver_id"], d["content"], d["type"], d["priority"], d["status"],
+                                d["metadata"], d["token_count"], sorted(d["visible_to"])]
+    return {"top_keys": sorted(h.keys()), "keys": keys, "messages": msgs,
+            "agent_inbox": {a: [rank(i) for i in v] for a, v in sorted(h["agent_inbox"].items())},
+            "registered_agents": sorted(h["registered_agents"]), "message_count": h["message_count"]}
 
 
 def digest(obj: Any) -> str:

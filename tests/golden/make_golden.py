@@ -27,15 +27,18 @@ def main() -> None:
         mod = ref_loader.load_reference(deterministic=True)
         with tempfile.TemporaryDirectory() as d:
             db = ref_loader.make_reference_db(mod, d, num_partitions=1)
-            expected = scenarios.run_ops(db, ops, mod, recv_timeout=1.0e6)
+            id_rank = {}
+            expected = scenarios.run_ops(db, ops, mod, recv_timeout=1.0e6, id_rank=id_rank)
             final = scenarios.final_state(db)
+            history = scenarios.history_state(db, id_rank)      # N2: the on-disk schema either side of the path
         n_delivered = sum(len(r) for op, r in zip(ops, expected) if op[0] == "recv")
         if name in scenarios.HASHED:
             doc = {"scenario": name, "ops_digest": scenarios.digest(ops),
-                   "expected_digest": scenarios.digest(expected), "n_delivered": n_delivered, "final": final}
+                   "expected_digest": scenarios.digest(expected), "n_delivered": n_delivered, "final": final,
+                   "history_digest": scenarios.digest(history)}
         else:
             doc = {"scenario": name, "ops": ops, "expected": expected, "n_delivered": n_delivered,
-                   "final": final}
+                   "final": final, "history": history}
         (out_dir / f"{name}.json").write_text(json.dumps(doc, indent=None, sort_keys=True) + "\n")
         print(f"{name}: {len(ops)} ops, {n_delivered} delivered")
 

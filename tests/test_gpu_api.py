@@ -23,16 +23,20 @@ def test_surface_matches_reference_golden(golden_dir, tmp_path, name):
     ops = scenarios.SCENARIOS[name]()
     sdb, db = _db(tmp_path)
     try:
-        got = scenarios.run_ops(db, ops, sdb)
+        id_rank = {}
+        got = scenarios.run_ops(db, ops, sdb, id_rank=id_rank)
         final = scenarios.final_state(db)
+        history = json.loads(json.dumps(scenarios.history_state(db, id_rank)))      # N2: the reference's history file
     finally:
         db.close()
     if name in scenarios.HASHED:
         assert scenarios.digest(got) == doc["expected_digest"]
+        assert scenarios.digest(history) == doc["history_digest"]
     else:
         got = json.loads(json.dumps(got))
         for i, (g, e) in enumerate(zip(got, doc["expected"])):
             assert g == e, (i, ops[i])
+        assert history == doc["history"]
     assert json.loads(json.dumps(final)) == doc["final"]
 
 

@@ -136,7 +136,7 @@ def test_broadcast_lists_share_one_seq():
 
 def test_priority_receive_matches_oracle_and_equal_priority_is_fifo():
     rng = np.random.default_rng(21)
-    from swarmdb_b200._native import RECV_PRIORITY
+    from swarmdb_b200._native import RECV_PEEK, RECV_PRIORITY
     A = 64
     g, c = _pair(A, ring_slots=4096)
     idx = np.arange(A, dtype=np.uint32)
@@ -148,8 +148,10 @@ def test_priority_receive_matches_oracle_and_equal_priority_is_fifo():
         lens, off, buf = _mk_payloads(rng, n, 64)
         g.send_batch(s, r, prio, None, lens, off, buf); c.send_batch(s, r, prio, None, lens, off, buf)
         for k in (1, 5, 33, 100):
+            _same(g.receive_batch(idx, k, RECV_PRIORITY | RECV_PEEK), c.receive_batch(idx, k, RECV_PRIORITY | RECV_PEEK))
             _same(g.receive_batch(idx, k, RECV_PRIORITY), c.receive_batch(idx, k, RECV_PRIORITY))
-        # stream-order receive while holes exist
+        # stream-order receive while holes exist (peek first: same selection, nothing retired)
+        _same(g.receive_batch(idx, 17, RECV_PEEK), c.receive_batch(idx, 17, RECV_PEEK))
         _same(g.receive_batch(idx, 17, 0), c.receive_batch(idx, 17, 0))
     while True:
         rg, rc = g.receive_batch(idx, 100, RECV_PRIORITY), c.receive_batch(idx, 100, RECV_PRIORITY)
