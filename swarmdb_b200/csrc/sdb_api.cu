@@ -74,7 +74,8 @@ struct sdb_ctx {
   uint32_t* members = nullptr;
   sdb_dev_counters* ctr = nullptr;
   // staging for non-staged sends
-  sdb_send_desc* descs_host = nullptr;   // pinned
+  sdb_send_desc* descs_host = nullptr;   // pinned [desc_cap]
+  uint64_t desc_cap = 0;                 // max_batch_sends + room for the chunks of long broadcast lists
   sdb_staged scratch;                    // device descs/payload/list owned by the handle
   uint32_t* list_host = nullptr;         // pinned
   uint32_t* gs_host = nullptr;           // pinned [max_groups + 1 + max_batch_sends]
@@ -192,10 +193,15 @@ struct SendArrays {
 
 // Build descriptors into `out` (host).  kind 0: second = receiver; 1: second = group idx;
 // 2: list (list_off/list base offsets supplied).  Returns totals through the staged object.
+// A broadcast list longer than SDB_LIST_CHUNK recipients is emitted as several descriptors (same payload, same
+// sequence number, consecutive arena regions) so that one warp never owns a million-record fan-out; `out` therefore
+// holds s->n >= n descriptors, bounded by `out_cap`.
+static const uint32_t SDB_LIST_CHUNK = 1024;
 int build_descs(sdb_ctx* h, uint32_t batch_kind, uint32_t n, SendArrays& a, const uint64_t* list_off,
-                uint64_t payload_bytes, sdb_send_desc* out, sdb_staged* s, uint32_t* gs_out = nullptr,
+                uint64_t payload_bytes, sdb_send_desc* out, uint64_t out_cap, sdb_staged* s, uint32_t* gs_out = nullptr,
                 uint32_t* n_gs_out = nullptr) {
   uint64_t rec = 0, gran = 0, group_recs = 0;
+  uint64_t o = 0;                      // output cursor (descriptors emitted)
   uint32_t max_padlen = 0;
   uint32_t n_group_sends = 0, n_other = 0;
   const uint32_t A = h->cfg.max_agents;
@@ -236,7 +242,8 @@ int build_descs(sdb_ctx* h, uint32_t batch_kind, uint32_t n, SendArrays& a, cons
         a.p2p_list_used++;
         rec += 1; gran += d.rgran;
         ++n_other;
-        out[i] = d;
+        if (o >= out_cap) return fail(h, SDB_ECAPACITY, "descriptor staging exhausted");
+        out[o++] = d;
         continue;
       }
       if (kind == 2 && a.second[i] >= a.n_lists) return fail(h, SDB_EINVAL, "list number out of range");
@@ -258,14 +265,26 @@ int build_descs(sdb_ctx* h, uint32_t batch_kind, uint32_t n, SendArrays& a, cons
       const uint32_t li = batch_kind == 3 ? a.second[i] : i;
       const uint64_t b = list_off[li], e = list_off[li + 1];
       if (e < b || e - b > 0xFFFFFFFFull) return fail(h, SDB_EINVAL, "bad list_off");
-      d.mstart = static_cast<uint32_t>(b); d.mcount = static_cast<uint32_t>(e - b);
       d.flags = SDB_DESC_SHARED_SEQ | SDB_DESC_LIST_TEMP;
-      rec += 1; gran += static_cast<uint64_t>(d.mcount) * d.rgran;
+      const uint64_t cnt = e - b;
+      rec += 1; ++n_other;
+      for (uint64_t c0 = 0; c0 == 0 || c0 < cnt; c0 += SDB_LIST_CHUNK) {      // at least one descriptor, even for an empty list
+        if (gran > 0xFFFFFFFFull) return fail(h, SDB_ECAPACITY, "batch exceeds 2^32 granules");
+        d.mstart = static_cast<uint32_t>(b + c0);
+        d.mcount = static_cast<uint32_t>(std::min<uint64_t>(SDB_LIST_CHUNK, cnt - c0));
+        d.gran0 = static_cast<uint32_t>(gran);
+        gran += static_cast<uint64_t>(d.mcount) * d.rgran;
+        if (o >= out_cap) return fail(h, SDB_ECAPACITY, "descriptor staging exhausted");
+        out[o++] = d;
+      }
+      continue;
     }
     if (kind != 1) ++n_other;
-    out[i] = d;
+    if (o >= out_cap) return fail(h, SDB_ECAPACITY, "descriptor staging exhausted");
+    out[o++] = d;
   }
-  s->kind = batch_kind; s->n = n; s->total_recs = rec; s->total_grans = gran; s->max_padlen = max_padlen;
+  const uint32_t n_out = static_cast<uint32_t>(o);
+  s->kind = batch_kind; s->n = n_out; s->total_recs = rec; s->total_grans = gran; s->max_padlen = max_padlen;
   s->has_pull = false; s->has_atomic = true;
   if (gs_out && group_recs >= SDB_PULL_THRESHOLD) {
     // bucket the group sends by group (counting sort, ascending send index inside a bucket)
@@ -273,10 +292,10 @@ int build_descs(sdb_ctx* h, uint32_t batch_kind, uint32_t n, SendArrays& a, cons
     uint32_t* off = gs_out;            // [G + 1]
     uint32_t* idx = gs_out + G + 1;    // [n_group_sends]
     std::memset(off, 0, (static_cast<size_t>(G) + 1) * sizeof(uint32_t));
-    for (uint32_t i = 0; i < n; ++i) if (out[i].flags & SDB_DESC_SKIP_SENDER) off[out[i].group + 1]++;
+    for (uint32_t i = 0; i < n_out; ++i) if (out[i].flags & SDB_DESC_SKIP_SENDER) off[out[i].group + 1]++;
     for (uint32_t g = 0; g < G; ++g) off[g + 1] += off[g];
     std::vector<uint32_t> cur(off, off + G);
-    for (uint32_t i = 0; i < n; ++i) if (out[i].flags & SDB_DESC_SKIP_SENDER) { idx[cur[out[i].group]++] = i; out[i].flags |= SDB_DESC_PULL; }
+    for (uint32_t i = 0; i < n_out; ++i) if (out[i].flags & SDB_DESC_SKIP_SENDER) { idx[cur[out[i].group]++] = i; out[i].flags |= SDB_DESC_PULL; }
     s->has_pull = true; s->has_atomic = n_other != 0;
     *n_gs_out = n_group_sends;
   }
@@ -377,7 +396,7 @@ int send_common(sdb_ctx* h, uint32_t kind, uint32_t n, SendArrays& a, const uint
     a.p2p_list = h->list_host + list_total; a.p2p_list_base = list_total; a.p2p_list_cap = cap - list_total;
   }
   uint32_t n_gs = 0;
-  int rc = build_descs(h, kind, n, a, list_off, payload_bytes, h->descs_host, s, h->gs_host, &n_gs);
+  int rc = build_descs(h, kind, n, a, list_off, payload_bytes, h->descs_host, h->desc_cap, s, h->gs_host, &n_gs);
   if (rc != SDB_OK) return rc;
   if (s->has_pull) {
     const size_t G1 = static_cast<size_t>(h->cfg.max_groups) + 1;
@@ -387,7 +406,7 @@ int send_common(sdb_ctx* h, uint32_t kind, uint32_t n, SendArrays& a, const uint
   list_total += a.p2p_list_used;
   if (list_total)
     CUDA_TRY(h, cudaMemcpyAsync(s->list_dev, h->list_host, list_total * sizeof(uint32_t), cudaMemcpyHostToDevice, h->stream));
-  CUDA_TRY(h, cudaMemcpyAsync(s->descs_dev, h->descs_host, static_cast<size_t>(n) * sizeof(sdb_send_desc),
+  CUDA_TRY(h, cudaMemcpyAsync(s->descs_dev, h->descs_host, static_cast<size_t>(s->n) * sizeof(sdb_send_desc),
                               cudaMemcpyHostToDevice, h->stream));
   if (payload_bytes)   // straight from the caller's buffer (pinned memory makes this a true async DMA)
     CUDA_TRY(h, cudaMemcpyAsync(s->payload_dev, payload, payload_bytes, cudaMemcpyHostToDevice, h->stream));
@@ -462,9 +481,10 @@ int sdb_create(const sdb_config* cfg, sdb_handle* out) {
   CUDA_TRY(h, cudaMemsetAsync(h->ctr, 0, sizeof(sdb_dev_counters), h->stream));
 
   // send staging
-  CUDA_TRY(h, cudaHostAlloc(reinterpret_cast<void**>(&h->descs_host), static_cast<size_t>(c.max_batch_sends) * sizeof(sdb_send_desc), cudaHostAllocDefault));
+  h->desc_cap = static_cast<uint64_t>(c.max_batch_sends) + c.list_pool_entries / SDB_LIST_CHUNK + 1;
+  CUDA_TRY(h, cudaHostAlloc(reinterpret_cast<void**>(&h->descs_host), static_cast<size_t>(h->desc_cap) * sizeof(sdb_send_desc), cudaHostAllocDefault));
   CUDA_TRY(h, cudaHostAlloc(reinterpret_cast<void**>(&h->list_host), c.list_pool_entries * sizeof(uint32_t), cudaHostAllocDefault));
-  CUDA_TRY(h, dmalloc(&h->scratch.descs_dev, c.max_batch_sends));
+  CUDA_TRY(h, dmalloc(&h->scratch.descs_dev, h->desc_cap));
   CUDA_TRY(h, dmalloc(&h->scratch.payload_dev, c.max_batch_payload + 64));
   CUDA_TRY(h, dmalloc(&h->scratch.list_dev, c.list_pool_entries));
   CUDA_TRY(h, dmalloc(&h->scratch.gs_off_dev, static_cast<size_t>(c.max_groups) + 1));
@@ -1016,7 +1036,7 @@ int sdb_stage_batch(sdb_handle h, uint32_t kind, uint32_t n, const uint32_t* sen
   std::vector<uint32_t> gs(static_cast<size_t>(h->cfg.max_groups) + 1 + n);
   uint32_t n_gs = 0;
   SendArrays a{sender, second, prio, type, len, payload_off, timestamp};
-  int rc = build_descs(h, kind, n, a, nullptr, payload_bytes, descs.data(), s, gs.data(), &n_gs);
+  int rc = build_descs(h, kind, n, a, nullptr, payload_bytes, descs.data(), n, s, gs.data(), &n_gs);
   if (rc != SDB_OK) { delete s; return rc; }
   cudaError_t e = dmalloc(&s->descs_dev, n);
   if (e == cudaSuccess && s->has_pull) {

@@ -309,3 +309,42 @@ def test_many_records_for_one_agent_in_one_batch(per_agent):
     idx = np.arange(A, dtype=np.uint32)
     _same(g.receive_batch(idx, 100000), c.receive_batch(idx, 100000))
     assert g.stats()["ring_overflow"] == 0
+
+
+def test_long_broadcast_lists_are_chunked_without_changing_results():
+    """Lists longer than the descriptor chunk (1024 recipients) are split into several descriptors on the host:
+    same sequence number on every copy, same per-recipient order against p2p traffic before and after."""
+    rng = np.random.default_rng(31)
+    A = 6000
+    g, c = _pair(A, list_pool_entries=1 << 16, ring_slots=64, arena_bytes=1 << 27, max_recv_records=1 << 17)
+    idx = np.arange(A, dtype=np.uint32)
+    g.register(idx); c.register(idx)
+    sizes = [0, 1, 1023, 1024, 1025, 2048, 5000, 6000]
+    lists = [rng.choice(A, size=k, replace=False) for k in sizes]
+    n = len(lists)
+    lo = np.zeros(n + 1, np.uint64); lo[1:] = np.cumsum(sizes)
+    li = np.concatenate(lists).astype(np.uint32)
+    s = rng.integers(0, A, n); prio = rng.integers(0, 4, n); typ = rng.integers(0, 7, n)
+    lens, off, buf = _mk_payloads(rng, n, 200)
+    lens[3] = 0                                              # one long list without payload bytes
+    l2, o2, b2 = _mk_payloads(rng, 300, 64)
+    s2 = rng.integers(0, A, 300); r2 = rng.integers(0, A, 300)
+    for sys in (g, c):
+        sys.send_batch(s2, r2, None, None, l2, o2, b2)
+        assert sys.send_list_batch(s, lo, li, prio, typ, lens, off, buf) == 301      # one sequence number per broadcast
+        sys.send_batch(r2, s2, None, None, l2, o2, b2)
+    assert g.stats()["next_seq"] == c.next_seq == 301 + n + 300
+    _same(g.receive_batch(idx, 3), c.receive_batch(idx, 3))
+    _same(g.receive_batch(idx, 1000, 1), c.receive_batch(idx, 1000, 1))
+    # the same through a mixed batch (kind 2 = list number)
+    kind = np.array([2, 0, 2, 2], np.uint8); target = np.array([6, 17, 7, 0], np.uint32)
+    lens4, off4, buf4 = _mk_payloads(rng, 4, 96)
+    g.send_mixed_batch([1, 2, 3, 4], kind, target, lo, li, None, None, lens4, off4, buf4)
+    for i in range(4):                                       # the oracle takes the same sends one by one
+        one = slice(i, i + 1)
+        if kind[i] == 0:
+            c.send_batch([i + 1], target[one], None, None, lens4[one], off4[one], buf4)
+        else:
+            t = int(target[i])
+            c.send_list_batch([i + 1], [0, sizes[t]], lists[t], None, None, lens4[one], off4[one], buf4)
+    _same(g.receive_batch(idx, 1000), c.receive_batch(idx, 1000))
