@@ -255,29 +255,34 @@ def run_gpu(args, rank, world, local_rank):
     per_step_msgs = wl.S * wl.F
 
     def device_step(i):
+        # device-resident step: fan-out + index build + full drain are only ENQUEUED (SDB_RECV_ASYNC); the records a
+        # step delivered are read back from the device counters after the timed region, not step by step
         shard.submit(staged[i % n_distinct])
-        _, total, _ = shard.receive_batch(None, 100, 0, copy_out=False)
-        return total
+        shard.receive_batch(None, 100, 0, copy_out=False, wait=False)
 
     with torch.cuda.stream(stream):
         for i in range(W):
-            assert device_step(i) == per_step_msgs
-        launches0 = shard.stats()["kernel_launches"]
+            device_step(i)
+            assert shard.last_receive_totals()[0] == per_step_msgs
+        st0 = shard.stats()
+        launches0 = st0["kernel_launches"]
         shard.profile(True)
         clocks = ClockSampler(local_rank); clocks.start()
         ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         torch.cuda.synchronize()
         ev0.record(stream)
-        delivered = 0
         for i in range(K):
-            delivered += device_step(W + i)
+            device_step(W + i)
         ev1.record(stream)
         torch.cuda.synchronize()
         clk = clocks.stop()
         ms_total = ev0.elapsed_time(ev1)
         prof = shard.profile_read()
         shard.profile(False)
-        launches = shard.stats()["kernel_launches"] - launches0
+        st1 = shard.stats()
+        launches = st1["kernel_launches"] - launches0
+        delivered = st1["delivered"] - st0["delivered"]          # counted on the device by the receive kernels
+        assert st1["ring_overflow"] == 0 and shard.last_receive_totals()[0] == per_step_msgs
     assert delivered == K * per_step_msgs, (delivered, K * per_step_msgs)
     value = delivered / (ms_total * 1e-3)
 

@@ -209,6 +209,9 @@ int sdb_free_staged(sdb_handle h, sdb_staged_t s);
  */
 #define SDB_RECV_PRIORITY 1u
 #define SDB_RECV_PEEK 2u                /* return what a receive would deliver, retire nothing (history snapshots, M:852-892) */
+#define SDB_RECV_ASYNC 4u               /* device-resident consumers: enqueue the receive and return at once; all host output
+                                           pointers must be NULL, results stay in the buffers of sdb_last_receive_dev (valid in
+                                           stream order), totals through sdb_last_receive_totals */
 int sdb_receive_batch(sdb_handle h, uint32_t n_agents, const uint32_t* agent_idx,
                       uint32_t max_messages, uint32_t flags,
                       uint32_t* count_out, sdb_msg_header* hdr_out, uint64_t hdr_cap,
@@ -217,6 +220,8 @@ int sdb_receive_batch(sdb_handle h, uint32_t n_agents, const uint32_t* agent_idx
 /* Device-resident results of the LAST receive call (valid until the next one). */
 int sdb_last_receive_dev(sdb_handle h, const uint32_t** count_dev, const sdb_msg_header** hdr_dev,
                          const uint8_t** payload_dev);
+/* Records and payload bytes of the LAST receive call; waits for it (the host side of SDB_RECV_ASYNC). */
+int sdb_last_receive_totals(sdb_handle h, uint64_t* total_out, uint64_t* payload_bytes_out);
 
 /* ---- cross-shard delivery (one handle per GPU, one process per GPU) ----------------------------
  * Replaces the partitioned topic: _get_partition (M:309-312, salted hash() % num_partitions) and

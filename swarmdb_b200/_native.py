@@ -24,6 +24,7 @@ NO_GROUP = 0xFFFFFFFF
 NO_RECEIVER = 0xFFFFFFFF
 RECV_PRIORITY = 1
 RECV_PEEK = 2
+RECV_ASYNC = 4
 TYPEF_JSON = 0x08
 TYPEF_EXTRAS = 0x10
 TYPE_MASK = 0x07
@@ -56,7 +57,7 @@ class SdbStats(C.Structure):
 EXPORTS = ["sdb_abi_version", "sdb_create", "sdb_destroy", "sdb_set_stream", "sdb_sync", "sdb_last_error",
            "sdb_get_stats", "sdb_debug_set_arena_pos", "sdb_profile", "sdb_profile_read", "sdb_register_agents", "sdb_deregister_agents", "sdb_create_group", "sdb_send_batch",
            "sdb_send_group_batch", "sdb_send_list_batch", "sdb_send_mixed_batch", "sdb_stage_batch", "sdb_submit_staged", "sdb_free_staged",
-           "sdb_receive_batch", "sdb_last_receive_dev", "sdb_wire_bytes", "sdb_set_agent_shards",
+           "sdb_receive_batch", "sdb_last_receive_dev", "sdb_last_receive_totals", "sdb_wire_bytes", "sdb_set_agent_shards",
            "sdb_export_group_batch", "sdb_export_mixed_batch", "sdb_export_mixed_batch_seq", "sdb_import_wire_batches", "sdb_wire_alloc", "sdb_wire_open",
            "sdb_wire_close", "sdb_import_wire_ptrs", "sdb_set_backends", "sdb_get_backend_loads",
            "sdb_release_backends", "sdb_select_backend_batch"]
@@ -99,6 +100,7 @@ def load_library() -> C.CDLL:
     L.sdb_receive_batch.restype = i32
     L.sdb_receive_batch.argtypes = [vp, u32, vp, u32, u32, vp, vp, u64, vp, u64, vp, vp]
     L.sdb_last_receive_dev.restype = i32; L.sdb_last_receive_dev.argtypes = [vp, vp, vp, vp]
+    L.sdb_last_receive_totals.restype = i32; L.sdb_last_receive_totals.argtypes = [vp, vp, vp]
     L.sdb_wire_bytes.restype = u64; L.sdb_wire_bytes.argtypes = [vp, u32, u64]
     L.sdb_set_agent_shards.restype = i32; L.sdb_set_agent_shards.argtypes = [vp, u32, vp]
     L.sdb_export_group_batch.restype = i32; L.sdb_export_group_batch.argtypes = [vp, u32] + [vp] * 7 + [u64, vp, vp, u64]
@@ -371,9 +373,15 @@ class Shard:
 
     # ------------------------------------------------------------------ dequeue
     def receive_batch(self, agents, max_messages: int, flags: int = 0, copy_out: bool = True,
-                      out_hdr: Optional[np.ndarray] = None, out_payload: Optional[np.ndarray] = None):
+                      out_hdr: Optional[np.ndarray] = None, out_payload: Optional[np.ndarray] = None, wait: bool = True):
         """Returns (counts[n_agents], headers[total], payload bytes) - views into reusable buffers
-        unless explicit output arrays are given.  copy_out=False leaves results on the device."""
+        unless explicit output arrays are given.  copy_out=False leaves results on the device and returns
+        (None, total, payload_bytes); with wait=False the call only enqueues the receive (SDB_RECV_ASYNC,
+        totals later through last_receive_totals()) and returns (None, None, None)."""
+        if not wait:
+            if copy_out:
+                raise ValueError("wait=False needs copy_out=False")
+            flags |= RECV_ASYNC
         if agents is None:
             a, n = None, 0
             counts = np.zeros(self.max_agents, np.uint32) if copy_out else None
@@ -391,11 +399,19 @@ class Shard:
         self._check(self._L.sdb_receive_batch(self._h, n, _p(a), max_messages, flags, _p(counts), _p(hdr), hdr_cap,
                                               _p(pay), pay_cap, C.cast(C.byref(total), C.c_void_p),
                                               C.cast(C.byref(pbytes), C.c_void_p)))
+        if not wait:
+            return None, None, None
         if not copy_out:
             return None, total.value, pbytes.value
         if agents is None:
             counts = counts[: self.stats_n_agents()]
         return counts, hdr[: total.value], pay[: pbytes.value]
+
+    def last_receive_totals(self):
+        """(records, payload bytes) of the last receive call; waits for it."""
+        total, pbytes = C.c_uint64(0), C.c_uint64(0)
+        self._check(self._L.sdb_last_receive_totals(self._h, C.cast(C.byref(total), C.c_void_p), C.cast(C.byref(pbytes), C.c_void_p)))
+        return total.value, pbytes.value
 
     def receive_one(self, agent: int, max_messages: int = 100, flags: int = 0):
         """Latency path for a single agent (one kernel launch, one D2H): returns (headers, payload)

@@ -1128,8 +1128,11 @@ int sdb_receive_batch(sdb_handle h, uint32_t n_agents, const uint32_t* agent_idx
   if (agent_idx) {
     CUDA_TRY(h, cudaMemcpyAsync(h->rx_agent, agent_idx, static_cast<size_t>(n_agents) * sizeof(uint32_t), cudaMemcpyHostToDevice, h->stream));
   }
+  const bool async = (flags & SDB_RECV_ASYNC) != 0;
+  if (async && (count_out || hdr_out || payload_out)) return fail(h, SDB_EINVAL, "SDB_RECV_ASYNC takes no host output buffers");
   sdb_recv_args r{};
-  r.agent_idx = agent_idx ? h->rx_agent : nullptr; r.n = n_agents; r.max_messages = max_messages; r.flags = flags;
+  r.agent_idx = agent_idx ? h->rx_agent : nullptr; r.n = n_agents; r.max_messages = max_messages;
+  r.flags = flags & (SDB_RECV_PRIORITY | SDB_RECV_PEEK);
   r.cnt = h->rx_cnt; r.rec_local = h->rx_rec_local; r.rec_tops = h->rx_rec_tops;
   r.plan_handle = h->rx_plan_handle; r.plan_glen = h->rx_plan_glen; r.plan_local = h->rx_plan_local;
   r.plan_tops = h->rx_plan_tops; r.totals = h->rx_totals; r.big_list = h->rx_big_list; r.big_count = h->rx_big_count;
@@ -1145,6 +1148,7 @@ int sdb_receive_batch(sdb_handle h, uint32_t n_agents, const uint32_t* agent_idx
   cudaError_t e = sdb_launch_receive(&h->view, &r, h->stream, &nl, &h->prof, h->sm_count);
   h->launches += nl;
   if (e != cudaSuccess) return fail(h, SDB_ECUDA, std::string("receive launch: ") + cudaGetErrorString(e));
+  if (async) return SDB_OK;          // the caller consumes on the device (stream order) or asks sdb_last_receive_totals later
   CUDA_TRY(h, cudaMemcpyAsync(h->totals_host, h->rx_totals, 2 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, h->stream));
   if (count_out)
     CUDA_TRY(h, cudaMemcpyAsync(count_out, h->rx_count, static_cast<size_t>(n_agents) * sizeof(uint32_t), cudaMemcpyDeviceToHost, h->stream));
@@ -1165,6 +1169,15 @@ int sdb_last_receive_dev(sdb_handle h, const uint32_t** count_dev, const sdb_msg
   if (count_dev) *count_dev = h->rx_count;
   if (hdr_dev) *hdr_dev = h->rx_hdr;
   if (payload_dev) *payload_dev = h->rx_payload;
+  return SDB_OK;
+}
+
+int sdb_last_receive_totals(sdb_handle h, uint64_t* total_out, uint64_t* payload_bytes_out) {
+  if (!h) return SDB_EINVAL;
+  CUDA_TRY(h, cudaMemcpyAsync(h->totals_host, h->rx_totals, 2 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, h->stream));
+  CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+  if (total_out) *total_out = h->totals_host[0];
+  if (payload_bytes_out) *payload_bytes_out = h->totals_host[1] * SDB_GRANULE;
   return SDB_OK;
 }
 

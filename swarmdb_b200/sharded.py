@@ -251,24 +251,23 @@ def run_sharded_bench(args, rank: int, world: int, local_rank: int, wl):
             if timed:
                 evs[3].record(stream)
             # non-local agents have empty rings on this shard: draining "all" needs no index upload
-            _, total, _ = shard.receive_batch(None, 100, 0, copy_out=False)
+            shard.receive_batch(None, 100, 0, copy_out=False, wait=False)    # enqueued only: counted on the device
             if timed:
                 evs[4].record(stream)
                 phase_ev.append(evs)
-            return total
 
         for i in range(W):
             device_step(i)
-        launches0 = shard.stats()["kernel_launches"]
+        st0 = shard.stats()
+        launches0 = st0["kernel_launches"]
         shard.profile(True)
         from bench import ALG_BYTES_FANOUT, ClockSampler, hbm_peak, traffic_note
         clocks = ClockSampler(local_rank); clocks.start()
         dist.barrier(); torch.cuda.synchronize()
         ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         ev0.record(stream)
-        delivered = 0
         for i in range(K):
-            delivered += device_step(W + i, timed=True)
+            device_step(W + i, timed=True)
         ev1.record(stream)
         torch.cuda.synchronize(); dist.barrier()
         clk = clocks.stop()
@@ -278,6 +277,7 @@ def run_sharded_bench(args, rank: int, world: int, local_rank: int, wl):
         phases = {n: float(np.mean([e[k].elapsed_time(e[k + 1]) for e in phase_ev])) for k, n in enumerate(names)}
         st_end = shard.stats()
         launches = st_end["kernel_launches"] - launches0
+        delivered = st_end["delivered"] - st0["delivered"]
         assert st_end["ring_overflow"] == 0, f"ring overflow on rank {rank}: {st_end['ring_overflow']} records (ring_slots={ring_slots})"
 
         # ---- e2e: host buffers in (export H2D), results out (D2H into pinned buffers)

@@ -348,3 +348,31 @@ def test_long_broadcast_lists_are_chunked_without_changing_results():
             t = int(target[i])
             c.send_list_batch([i + 1], [0, sizes[t]], lists[t], None, None, lens4[one], off4[one], buf4)
     _same(g.receive_batch(idx, 1000), c.receive_batch(idx, 1000))
+
+
+def test_async_receive_enqueues_and_reports_totals_later():
+    """SDB_RECV_ASYNC: the receive is only enqueued; totals and device-resident results are read afterwards."""
+    from swarmdb_b200._native import HDR_DTYPE, RECV_ASYNC, SdbError
+    rng = np.random.default_rng(41)
+    A, n = 300, 4000
+    g, c = _pair(A, ring_slots=256)
+    idx = np.arange(A, dtype=np.uint32)
+    g.register(idx); c.register(idx)
+    s = rng.integers(0, A, n); r = rng.integers(0, A, n)
+    lens, off, buf = _mk_payloads(rng, n, 96)
+    g.send_batch(s, r, None, None, lens, off, buf); c.send_batch(s, r, None, None, lens, off, buf)
+    assert g.receive_batch(None, 5, 0, copy_out=False, wait=False) == (None, None, None)
+    cc, hc, pc = c.receive_batch(idx, 5)
+    total, pbytes = g.last_receive_totals()
+    assert total == len(hc) and pbytes == len(pc)
+    cnt_dev, hdr_dev, pay_dev = g.last_receive_dev()
+    from cuda.bindings import runtime as cudart                              # cuda-python: plain D2H of the device-resident results
+    hdr = np.zeros(total, HDR_DTYPE); pay = np.zeros(pbytes, np.uint8)
+    d2h = cudart.cudaMemcpyKind.cudaMemcpyDeviceToHost
+    assert cudart.cudaMemcpy(hdr.ctypes.data, hdr_dev, hdr.nbytes, d2h)[0] == cudart.cudaError_t.cudaSuccess
+    assert cudart.cudaMemcpy(pay.ctypes.data, pay_dev, pay.nbytes, d2h)[0] == cudart.cudaError_t.cudaSuccess
+    assert hdr.tobytes() == hc.tobytes() and pay.tobytes() == pc.tobytes()
+    _same(g.receive_batch(idx, 1000), c.receive_batch(idx, 1000))            # the rest, synchronously
+    assert g.stats()["delivered"] == n
+    with pytest.raises(SdbError):                                            # host outputs and ASYNC exclude each other
+        g.receive_batch(idx, 5, RECV_ASYNC)
