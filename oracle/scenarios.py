@@ -184,6 +184,85 @@ def scenario_group_fanout(seed: int = 7, n_agents: int = 128, group_size: int = 
     return ops
 
 
+def scenario_bookkeeping(seed: int = 5, n_agents: int = 10, n_ops: int = 260) -> List[list]:
+    """The host-side bookkeeping methods of the surface (M:603-850, M:973-1206) interleaved with traffic:
+    get_message, get_agent_messages, mark_message_as_processed, query_messages, search_messages,
+    get_conversation, get_unread_message_count, get_agent_load, get_stats, delete_message,
+    flush_old_messages, resend_failed_messages.  Message arguments are RANKS (first-seen order of ids);
+    timestamp bounds are given as the rank of the message whose timestamp is the bound, and are always
+    point-to-point or broadcast messages: the copies of one group send are stamped microseconds apart by
+    the reference (independent send_message calls, M:1267-1277) and share one stamp in a batched fan-out."""
+    rng = np.random.default_rng(seed)
+    agents = [f"b{i}" for i in range(n_agents)]
+    team = agents[2:7]
+    ops: List[list] = [["register", a] for a in agents[:6]]
+    ops.append(["group", "team", team])
+    solo: List[int] = []              # ranks of p2p / broadcast messages
+    n_ranks = 0
+
+    def pick() -> str:
+        return agents[int(rng.integers(0, n_agents))]
+
+    def rank() -> int:
+        return int(rng.integers(0, max(n_ranks, 1)))
+
+    def bound() -> Optional[int]:
+        return solo[int(rng.integers(0, len(solo)))] if solo else None
+
+    words = ["alpha", "Beta", "gamma", "DELTA", "eps"]
+    for _ in range(n_ops):
+        r = float(rng.random())
+        typ = TYPES[int(rng.integers(0, len(TYPES)))]
+        text = " ".join(words[int(k)] for k in rng.integers(0, len(words), 3))
+        content: Any = text if rng.random() < 0.8 else {"note": text, "k": [1, 2]}
+        if r < 0.30:
+            ops.append(["send", pick(), content, pick(), typ, int(rng.integers(0, 4)), None, None])
+            solo.append(n_ranks); n_ranks += 1
+        elif r < 0.36:
+            sender = pick()
+            ops.append(["send_group", sender, "team", content, typ, 1, {"t": 1}])
+            n_ranks += len(team) - (sender in team)
+        elif r < 0.40:
+            ops.append(["broadcast", pick(), content, typ, 2, None, None])
+            solo.append(n_ranks); n_ranks += 1
+        elif r < 0.50:
+            ops.append(["recv", pick(), int(rng.choice([1, 3, 100]))])
+        elif r < 0.55:
+            ops.append(["get_message", rank()])
+        elif r < 0.62:
+            st = [None, "delivered", "read", "processed"][int(rng.integers(0, 4))]
+            ops.append(["agent_messages", pick(), st, int(rng.choice([2, 5, 100])), int(rng.integers(0, 3))])
+        elif r < 0.67:
+            ops.append(["mark_processed", rank() if rng.random() < 0.8 else -1])
+        elif r < 0.76:
+            q = {"sender": pick() if rng.random() < 0.5 else None, "receiver": pick() if rng.random() < 0.5 else None,
+                 "type": typ if rng.random() < 0.3 else None,
+                 "status": [None, "delivered", "read", "processed", "failed"][int(rng.integers(0, 5))],
+                 "after": bound() if rng.random() < 0.3 else None, "before": bound() if rng.random() < 0.3 else None,
+                 "limit": int(rng.choice([1, 4, 100]))}
+            ops.append(["query", q])
+        elif r < 0.81:
+            ops.append(["search", words[int(rng.integers(0, len(words)))].lower(), bool(rng.random() < 0.5), int(rng.choice([3, 100]))])
+        elif r < 0.85:
+            ops.append(["conversation", pick(), pick(), int(rng.choice([2, 7, 100]))])
+        elif r < 0.89:
+            ops.append(["unread", pick()])
+        elif r < 0.92:
+            ops.append(["agent_load", pick()])
+        elif r < 0.95:
+            ops.append(["stats"])
+        elif r < 0.97:
+            ops.append(["delete", rank() if rng.random() < 0.8 else -1])
+        else:
+            ops.append(["force_status", rank(), "failed"])
+    # resends create ids whose number depends on run-time state: keep them after every rank-addressed op
+    ops += [["flush_old", bound()], ["stats"], ["force_status", solo[0], "failed"], ["resend_failed"], ["stats"], ["flush_old", None]]
+    for a in agents:
+        ops.append(["recv", a, 1000])
+    ops.append(["stats"])
+    return ops
+
+
 SCENARIOS = {
     "example_main": scenario_example_main,
     "appendix_a": scenario_appendix_a,
@@ -192,7 +271,11 @@ SCENARIOS = {
     "random_3": lambda: scenario_random(3, n_agents=40, n_ops=600),
     "c1_p2p_1k": scenario_c1,
     "group_fanout_small": scenario_group_fanout,
+    "bookkeeping": scenario_bookkeeping,
 }
+# scenarios that exercise host-side bookkeeping methods only the full surface has (not the path oracles)
+SURFACE_ONLY = {"bookkeeping"}
+PATH_SCENARIOS = sorted(set(SCENARIOS) - SURFACE_ONLY)
 # scenarios whose full expected output is too bulky to commit: only a digest is stored
 HASHED = {"c1_p2p_1k", "group_fanout_small"}
 
@@ -240,9 +323,67 @@ def run_ops(db: Any, ops: List[list], enums: Any, recv_timeout: float = 1.0e6,
         elif kind == "recv":
             msgs = db.receive_messages(op[1], max_messages=op[2], timeout=recv_timeout)
             out.append([canon_message(m, id_rank) for m in msgs])
-        else:  # pragma: no cover
-            raise ValueError(kind)
+        else:
+            out.append(_bookkeeping_op(db, op, enums, id_rank))
     return out
+
+
+def _bookkeeping_op(db: Any, op: list, enums: Any, id_rank: Dict[str, int]) -> Any:
+    """Host-side bookkeeping methods (M:603-850, M:973-1206); message arguments are ranks."""
+    kind = op[0]
+    by_rank = {r: i for i, r in id_rank.items()}
+
+    def mid(r: Any) -> str:
+        return by_rank.get(r, "no-such-message-id")
+
+    def ranks(msgs: List[Any]) -> list:
+        return [[id_rank.setdefault(m.id, len(id_rank)), _enum_val(m.status)] for m in msgs]
+
+    def stamp(r: Any) -> Any:
+        m = db.get_message(mid(r)) if r is not None else None
+        return None if m is None else m.timestamp
+
+    if kind == "get_message":
+        m = db.get_message(mid(op[1]))
+        return None if m is None else canon_message(m, id_rank)
+    if kind == "agent_messages":
+        st = None if op[2] is None else enums.MessageStatus(op[2])
+        return ranks(db.get_agent_messages(op[1], status=st, limit=op[3], skip=op[4]))
+    if kind == "mark_processed":
+        return db.mark_message_as_processed(mid(op[1]))
+    if kind == "query":
+        q = op[1]
+        return ranks(db.query_messages(
+            sender_id=q["sender"], receiver_id=q["receiver"],
+            message_type=None if q["type"] is None else enums.MessageType(q["type"]),
+            status=None if q["status"] is None else enums.MessageStatus(q["status"]),
+            after_timestamp=stamp(q["after"]), before_timestamp=stamp(q["before"]), limit=q["limit"]))
+    if kind == "search":
+        return ranks(db.search_messages(op[1], case_sensitive=op[2], limit=op[3]))
+    if kind == "conversation":
+        return ranks(db.get_conversation(op[1], op[2], limit=op[3]))
+    if kind == "unread":
+        return db.get_unread_message_count(op[1])
+    if kind == "agent_load":
+        d = dict(db.get_agent_load(op[1]))
+        d["processing_rate"] = round(d["processing_rate"] * 60)          # messages in the last minute (all of them here)
+        return d
+    if kind == "stats":
+        st = db.get_stats()
+        return {k: st[k] for k in ("total_messages", "active_agents", "messages_by_type", "messages_by_status")} | {
+            "messages_by_agent": {a: st["messages_by_agent"][a] for a in sorted(st["messages_by_agent"])}}
+    if kind == "delete":
+        return db.delete_message(mid(op[1]))
+    if kind == "flush_old":
+        return db.flush_old_messages(stamp(op[1]) if op[1] is not None else None)
+    if kind == "force_status":            # white-box: what a failed produce leaves behind (M:501-519)
+        m = db.get_message(mid(op[1]))
+        if m is not None:
+            m.status = enums.MessageStatus(op[2])
+        return m is not None
+    if kind == "resend_failed":
+        return [id_rank.setdefault(i, len(id_rank)) for i in db.resend_failed_messages()]
+    raise ValueError(kind)  # pragma: no cover
 
 
 def _copy(x: Any) -> Any:
