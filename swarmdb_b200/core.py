@@ -158,6 +158,20 @@ def _encode_content(content: Any) -> (bytes, int):
     return json.dumps(content).encode("utf-8"), TYPEF_JSON
 
 
+class _TransportAdmin:
+    """What callers probe through `db.admin_client` (the REST health check lists topics as a liveness test,
+    api.py:798): here the "topic" is the device queue and its "partitions" are the shards."""
+
+    def __init__(self, db: "SwarmsDB") -> None:
+        self._db = db
+
+    def list_topics(self, timeout: Optional[float] = None):
+        from types import SimpleNamespace
+        self._db.shard.stats()                     # raises if the device transport is gone
+        parts = {i: SimpleNamespace(id=i) for i in range(max(1, self._db.gpu_config.num_shards))}
+        return SimpleNamespace(topics={self._db.base_topic: SimpleNamespace(partitions=parts)})
+
+
 class SwarmsDB:
     """Agent message queue + LLM-backend balancer; reference-compatible surface (see module doc)."""
 
@@ -215,6 +229,7 @@ class SwarmsDB:
         self._seq_to_id: Dict[int, str] = {}
         self._reset_buffer()
         self._closed = False
+        self.admin_client = _TransportAdmin(self)          # M:202-204: callers only list topics through it
         logger.info(f"SwarmsDB (B200) initialized with base topic: {base_topic}")
 
     # ------------------------------------------------------------------ helpers
