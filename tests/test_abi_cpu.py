@@ -70,3 +70,29 @@ def test_wire_codec_roundtrip_is_host_only():
     d = m.to_dict()
     assert d["type"] == "chat" and d["priority"] == 1 and d["status"] == "pending"
     assert core.Message.from_dict(d).sender_id == "a"
+
+
+def _build_c_demo(tmp_path):
+    import shutil
+    import subprocess
+    from pathlib import Path
+    if shutil.which("gcc") is None:
+        pytest.skip("gcc not available")
+    root = Path(__file__).resolve().parents[1]
+    exe = tmp_path / "c_abi_demo"
+    subprocess.check_call(["gcc", "-std=c99", "-Wall", "-Wextra", "-Werror", "-pedantic", f"-I{root / 'include'}",
+                           str(root / "examples" / "c_abi_demo.c"), f"-L{root / 'swarmdb_b200' / 'csrc'}", "-lswarmdb_b200",
+                           f"-Wl,-rpath,{root / 'swarmdb_b200' / 'csrc'}", "-o", str(exe)])
+    return exe
+
+
+def test_header_is_plain_c_and_a_c_caller_fails_loudly_without_a_device(tmp_path):
+    """include/swarmdb_b200.h compiles as strict C99 and links against the library; without a CUDA device the
+    caller gets SDB_ECUDA and a message - never a silent CPU path."""
+    import subprocess
+    import torch
+    exe = _build_c_demo(tmp_path)
+    if torch.cuda.is_available():
+        pytest.skip("a device is present: covered by tests/test_gpu_api.py::test_plain_c_caller")
+    p = subprocess.run([str(exe)], capture_output=True, text=True)
+    assert p.returncode == 3 and "sizeof(sdb_config)=96" in p.stdout and "no CPU fallback" in p.stdout, p.stdout

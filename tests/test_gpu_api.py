@@ -143,3 +143,11 @@ def test_peek_and_device_history_snapshot(tmp_path):
             db2.close()
     finally:
         db.close()
+
+
+def test_plain_c_caller(tmp_path):
+    """examples/c_abi_demo.c (strict C99) creates a shard, fans one message out to a group and drains a member."""
+    import subprocess
+    from tests.test_abi_cpu import _build_c_demo
+    p = subprocess.run([str(_build_c_demo(tmp_path))], capture_output=True, text=True)
+    assert p.returncode == 0 and 'agent 2 got 1 message(s)' in p.stdout and '"hello"' in p.stdout, p.stdout + p.stderr
