@@ -568,9 +568,14 @@ class SwarmsDB:
                 break
         return out
 
+    def _pre_read(self) -> None:
+        """Make buffered sends visible before a read (a sharded front-end reads only what earlier collective
+        flushes delivered, so it overrides this with a no-op)."""
+        self.flush()
+
     def peek_messages(self, agent_id: str, max_messages: int = 100) -> List[Message]:
         """What `receive_messages` would return next, without consuming it (device PEEK receive)."""
-        self.flush()
+        self._pre_read()
         flags = RECV_PEEK | (RECV_PRIORITY if self.gpu_config.priority_dequeue else 0)
         hdr, pay, _ = self.shard.receive_one(self._index(agent_id), max_messages, flags)
         return self._decode(hdr, pay, agent_id, record=False, status=MessageStatus.DELIVERED)
@@ -578,7 +583,7 @@ class SwarmsDB:
     def pending_snapshot(self, per_agent: int = 1024) -> Dict[str, List[Message]]:
         """Every message still queued on the device, per agent, in delivery order (non-destructive).
         This is the D2H ring dump behind `save_message_history(include_device=True)`."""
-        self.flush()
+        self._pre_read()
         n = len(self._agent_name)
         out: Dict[str, List[Message]] = {}
         if n == 0:

@@ -527,8 +527,19 @@ def make_sharded_swarmsdb(rank: int, world: int, exchange_factory=None, shard=No
                 return []
             return self._receive_local(agent_id, max_messages)
 
+        def _pre_read(self) -> None:
+            return None                              # reads see what earlier collective flushes delivered
+
         def peek_messages(self, agent_id: str, max_messages: int = 100):
-            raise NotImplementedError("peek is not available on the sharded front-end yet")
+            if self.owner(agent_id) != self.rank:
+                raise ValueError(f"agent {agent_id!r} lives on shard {self.owner(agent_id)}, not on rank {self.rank}")
+            if agent_id not in self._agent_idx:
+                return []
+            return super().peek_messages(agent_id, max_messages)
+
+        def deregister_agent(self, agent_id: str) -> None:
+            """REPLICATED, like register_agent (the registry must agree on every rank)."""
+            super().deregister_agent(agent_id)
 
         def close(self) -> None:
             try:

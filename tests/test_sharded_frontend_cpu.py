@@ -87,8 +87,14 @@ def _worker(rank, world, port, q, tmp):
             for a in mine:
                 lim = 3 if rnd % 2 == 0 else 1000                  # partial drains in between
                 got.setdefault(a, []).extend((m.id, _view(m)) for m in db.receive_messages(a, lim))
+        # peek and the device snapshot are rank-local reads: they show what the next receive returns and consume nothing
+        snap = db.pending_snapshot()
+        peeks_ok = True
         for a in mine:
-            got[a].extend((m.id, _view(m)) for m in db.receive_messages(a, 100000))
+            peek = [(m.id, _view(m)) for m in db.peek_messages(a, 100000)]
+            rest = [(m.id, _view(m)) for m in db.receive_messages(a, 100000)]
+            peeks_ok &= [i for i, _ in peek] == [i for i, _ in rest] == [m.id for m in snap.get(a, [])]
+            got[a].extend(rest)
         # strictness: unknown agents cannot be introduced by a rank-local call
         try:
             db.send_message(AGENTS[0], "x", "nobody")
@@ -101,7 +107,8 @@ def _worker(rank, world, port, q, tmp):
             strict = False
         except ValueError:
             pass
-        allgot, allsent = [None] * world, [None] * world
+        allgot, allsent, allpeeks = [None] * world, [None] * world, [None] * world
+        dist.all_gather_object(allpeeks, peeks_ok)
         dist.all_gather_object(allgot, got)
         dist.all_gather_object(allsent, sent)
         db.close()
@@ -124,7 +131,7 @@ def _worker(rank, world, port, q, tmp):
             # every id a receiver saw was returned by exactly one send call on some rank
             ids_sent = [i for per in allsent for rnd in per for i in rnd]
             ids_seen = {i for d in allgot for lst in d.values() for i, _ in lst}
-            q.put({"bad": bad, "strict": strict, "unique": len(ids_sent) == len(set(ids_sent)),
+            q.put({"bad": bad, "strict": strict, "peeks": all(allpeeks), "unique": len(ids_sent) == len(set(ids_sent)),
                    "seen_subset": ids_seen <= set(ids_sent), "n_seen": len(ids_seen),
                    "n_msgs": sum(len(v) for v in merged.values())})
             single.close()
@@ -144,7 +151,7 @@ def test_sharded_frontend_matches_single_process(tmp_path):
         p.join(timeout=240)
         assert p.exitcode == 0
     res = q.get(timeout=5)
-    assert res["bad"] == [] and res["strict"] and res["unique"] and res["seen_subset"], res
+    assert res["bad"] == [] and res["strict"] and res["peeks"] and res["unique"] and res["seen_subset"], res
     assert res["n_msgs"] > 100 and res["n_seen"] > 50, res
 
 
