@@ -576,6 +576,7 @@ k_group_fanout_span(sdb_dev_view v, const sdb_send_desc* __restrict__ descs, uin
     if (c_jnext == 0 && ((c_tnext & (GROUP - 1)) == 0 || c_tnext >= mine) && lane < GROUP) {
       const uint32_t g0 = t_first & ~(GROUP - 1);
       const uint32_t u = g0 + PAY + lane, w = g0 + DESC + lane;
+      sdb_fence_proxy_async();                              // the stages were written (pad bytes) and read through the generic proxy
       if (u < mine) { wait_desc(u); want_payload(u); }
       if (w < mine) want_desc(w);
     }
