@@ -59,3 +59,31 @@ def test_history_file_round_trip(tmp_path):
     assert db2.message_count == db.message_count
     assert db2.get_message(next(iter(before))).status in (sdb.MessageStatus.READ, sdb.MessageStatus.DELIVERED)
     db.close(); db2.close()
+
+
+@pytest.mark.parametrize("seed", range(40, 52))
+def test_random_interleavings_match_the_pinned_oracle_on_cpu(tmp_path, seed):
+    """Seeded random op mixes (register / p2p / visible_to / groups / broadcasts / partial drains) through the surface
+    versus oracle/pyref.py, which is itself pinned to the reference's goldens."""
+    from oracle import pyref
+    ops = scenarios.scenario_random(seed, n_agents=8 + seed % 9, n_ops=150)
+    want = json.loads(json.dumps(scenarios.run_ops(pyref.OracleSwarmsDB(id_factory=pyref.counter_ids()), ops, pyref)))
+    sdb, db = _db(tmp_path)
+    try:
+        got = json.loads(json.dumps(scenarios.run_ops(db, ops, sdb)))
+        final = scenarios.final_state(db)
+    finally:
+        db.close()
+    for i, (g, w) in enumerate(zip(got, want)):
+        assert g == w, (seed, i, ops[i])
+    assert final["message_count"] > 0
+
+
+def test_priority_dequeue_and_flush_threshold_on_cpu(tmp_path):
+    sdb, db = _db(tmp_path, priority_dequeue=True, flush_threshold=4)
+    for i, p in enumerate([0, 3, 1, 3, 2, 0]):
+        db.send_message("s", f"m{i}", "r", priority=sdb.MessagePriority(p))      # crosses the flush threshold
+    assert [m.content for m in db.peek_messages("r", 3)] == ["m1", "m3", "m4"]
+    assert [m.content for m in db.receive_messages("r", 4)] == ["m1", "m3", "m4", "m2"]
+    assert [m.content for m in db.receive_messages("r", 4)] == ["m0", "m5"]
+    db.close()
