@@ -26,7 +26,6 @@ import sys
 import types
 import uuid as _uuid
 from pathlib import Path
-from typing import Optional
 
 REFERENCE_ROOT = Path(os.environ.get("SWARMDB_REFERENCE_ROOT", "/root/reference"))
 REFERENCE_MAIN = REFERENCE_ROOT / "swarmdb" / " main.py"   # the filename really starts with a space

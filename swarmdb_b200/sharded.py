@@ -8,9 +8,13 @@ in the sm_100a kernels of each shard - see csrc/sdb_xshard.cu).
 """
 from __future__ import annotations
 
-from typing import Iterable, Optional
+import dataclasses
+from typing import Iterable
 
 import numpy as np
+
+from ._native import SdbError
+from .core import GpuConfig, MessagePriority, MessageStatus, MessageType, SwarmsDB
 
 FNV_OFFSET = 0xCBF29CE484222325
 FNV_PRIME = 0x100000001B3
@@ -360,193 +364,188 @@ def composite_seq(round_no: int, rank: int, local: int = 0) -> int:
     return (round_no << 40) | (rank << 32) | local
 
 
-def make_sharded_swarmsdb(rank: int, world: int, exchange_factory=None, shard=None, **kw):
-    """Build a `ShardedSwarmsDB` (defined lazily so importing this module does not load the CUDA library)."""
-    from ._native import SdbError
-    from .core import GpuConfig, MessageStatus, SwarmsDB
-    import dataclasses
+class ShardedSwarmsDB(SwarmsDB):
+    """The reference's surface for a multi-GPU deployment (one process per GPU, like the reference's
+    independent gunicorn workers, api.py:66, but sharing ONE queue):
 
-    class ShardedSwarmsDB(SwarmsDB):
-        """The reference's surface for a multi-GPU deployment (one process per GPU, like the reference's
-        independent gunicorn workers, api.py:66, but sharing ONE queue):
+      * registry and group calls (`register_agent(s)`, `deregister_agent`, `add_agent_group`) are
+        REPLICATED - every rank makes them identically and in the same order (agent indices must agree);
+      * `send_message` / `send_to_group` / `broadcast_message` are LOCAL - each rank ingests its own
+        traffic and returns message ids immediately (composite sequence numbers);
+      * `flush()` is COLLECTIVE - every rank calls it; wire batches are exchanged and imported;
+      * `receive_messages(agent)` is LOCAL to the rank that owns the agent
+        (`shard_of_agent(agent_id, world)`), and returns what earlier flushes delivered.
+    """
 
-          * registry and group calls (`register_agent(s)`, `deregister_agent`, `add_agent_group`) are
-            REPLICATED - every rank makes them identically and in the same order (agent indices must agree);
-          * `send_message` / `send_to_group` / `broadcast_message` are LOCAL - each rank ingests its own
-            traffic and returns message ids immediately (composite sequence numbers);
-          * `flush()` is COLLECTIVE - every rank calls it; wire batches are exchanged and imported;
-          * `receive_messages(agent)` is LOCAL to the rank that owns the agent
-            (`shard_of_agent(agent_id, world)`), and returns what earlier flushes delivered.
-        """
+    def __init__(self, rank: int, world: int, *a, exchange_factory=None, shard=None, **k):
+        g = k.get("gpu_config") or GpuConfig()
+        if g.id_nonce is None and not g.deterministic_ids:
+            g = dataclasses.replace(g, deterministic_ids=True)       # ids must agree across ranks
+        g = dataclasses.replace(g, shard_id=rank, num_shards=world)
+        k["gpu_config"] = g
+        super().__init__(*a, _shard=shard, **k)
+        self.rank, self.world = rank, world
+        self._round = 1
+        self._next_seq = self._b_first_seq = composite_seq(1, rank)
+        self._map_dirty = True
+        self._replicated = 0
+        self._seen_overflow = 0
+        self._round_msgs = []
+        g2 = self.gpu_config
+        self.exchange = (exchange_factory or self._default_exchange)(self.shard, rank, world, max(g2.flush_threshold, 1),
+                                                                      max(1 << 22, 2 * (g2.max_payload_bytes + 31)))
 
-        def __init__(self, *a, **k):
-            g = k.get("gpu_config") or GpuConfig()
-            if g.id_nonce is None and not g.deterministic_ids:
-                g = dataclasses.replace(g, deterministic_ids=True)       # ids must agree across ranks
-            g = dataclasses.replace(g, shard_id=rank, num_shards=world)
-            k["gpu_config"] = g
-            super().__init__(*a, _shard=shard, **k)
-            self.rank, self.world = rank, world
-            self._round = 1
-            self._next_seq = self._b_first_seq = composite_seq(1, rank)
+    @staticmethod
+    def _default_exchange(shard_, rank_, world_, max_sends, max_payload):
+        import torch
+        return PeerExchange(shard_, rank_, world_, max_sends, max_payload, torch.device("cuda", torch.cuda.current_device()))
+
+    def owner(self, agent_id: str) -> int:
+        return shard_of_agent(agent_id, self.world)
+
+    # ---- replicated calls: the only place where new agent indices may be created
+    def _index(self, agent_id: str) -> int:
+        i = self._agent_idx.get(agent_id)
+        if i is None:
+            if not self._replicated:
+                raise KeyError(f"agent {agent_id!r} is unknown on rank {self.rank}: in a sharded deployment agents are "
+                               f"introduced by register_agent(s) / add_agent_group, called identically on every rank")
+            i = super()._index(agent_id)
             self._map_dirty = True
-            self._replicated = 0
-            self._seen_overflow = 0
-            self._round_msgs = []
-            g2 = self.gpu_config
-            self.exchange = (exchange_factory or self._default_exchange)(self.shard, rank, world, max(g2.flush_threshold, 1),
-                                                                          max(1 << 22, 2 * (g2.max_payload_bytes + 31)))
+        return i
 
-        @staticmethod
-        def _default_exchange(shard_, rank_, world_, max_sends, max_payload):
-            import torch
-            return PeerExchange(shard_, rank_, world_, max_sends, max_payload, torch.device("cuda", torch.cuda.current_device()))
+    def register_agent(self, agent_id: str) -> None:
+        self._replicated += 1
+        try:
+            super().register_agent(agent_id)
+        finally:
+            self._replicated -= 1
 
-        def owner(self, agent_id: str) -> int:
-            return shard_of_agent(agent_id, self.world)
+    def register_agents(self, agent_ids):
+        self._replicated += 1
+        try:
+            return super().register_agents(list(agent_ids))
+        finally:
+            self._replicated -= 1
 
-        # ---- replicated calls: the only place where new agent indices may be created
-        def _index(self, agent_id: str) -> int:
-            i = self._agent_idx.get(agent_id)
-            if i is None:
-                if not self._replicated:
-                    raise KeyError(f"agent {agent_id!r} is unknown on rank {self.rank}: in a sharded deployment agents are "
-                                   f"introduced by register_agent(s) / add_agent_group, called identically on every rank")
-                i = super()._index(agent_id)
-                self._map_dirty = True
-            return i
-
-        def register_agent(self, agent_id: str) -> None:
-            self._replicated += 1
-            try:
-                super().register_agent(agent_id)
-            finally:
-                self._replicated -= 1
-
-        def register_agents(self, agent_ids):
-            self._replicated += 1
-            try:
-                return super().register_agents(list(agent_ids))
-            finally:
-                self._replicated -= 1
-
-        def add_agent_group(self, group_name: str, agent_ids) -> None:
-            self._replicated += 1
-            try:
-                self._push_shard_map()
-                super().add_agent_group(group_name, agent_ids)
-            finally:
-                self._replicated -= 1
-
-        create_group = add_agent_group
-
-        def _push_shard_map(self) -> None:
-            if self._map_dirty and self._agent_name:
-                self.shard.set_agent_shards(shard_map_for_names(self._agent_name, self.world))
-                self._map_dirty = False
-
-        def _sync_group(self, group_name: str) -> int:
-            self._push_shard_map()              # ownership must be known before the group is filtered
-            return super()._sync_group(group_name)
-
-        # ---- local sends: every agent they name must already be known everywhere
-        def _require_known(self, *agent_ids) -> None:
-            for a in agent_ids:
-                if a is not None and a not in self._agent_idx:
-                    raise KeyError(f"agent {a!r} must be registered (on every rank) before it is used in a send")
-
-        def send_message(self, sender_id, content, receiver_id=None, message_type=None, priority=None, metadata=None,
-                         visible_to=None, **kw):
-            self._require_known(sender_id, receiver_id, *(visible_to or []))
-            from .core import MessagePriority, MessageType
-            return super().send_message(sender_id, content, receiver_id, message_type or MessageType.CHAT,
-                                        priority if priority is not None else MessagePriority.NORMAL, metadata, visible_to, **kw)
-
-        def send_to_group(self, sender_id, group_name, content, message_type=None, priority=None, metadata=None):
-            self._require_known(sender_id)
-            from .core import MessagePriority, MessageType
-            return super().send_to_group(sender_id, group_name, content, message_type or MessageType.CHAT,
-                                         priority if priority is not None else MessagePriority.NORMAL, metadata)
-
-        # ---- collective flush: export (local) -> exchange (collective) -> import (local)
-        def flush(self) -> None:
-            try:
-                self._flush_export()
-                self.exchange.exchange()
-            except Exception as e:
-                self._fail_round(e)
-                raise
-            self._flush_import()
-
-        def _fail_round(self, e: Exception) -> None:
-            for m in self._round_msgs:
-                m.status = MessageStatus.FAILED
-                m.metadata["error"] = str(e)
-            self._round_msgs = []
-
-        def _flush_export(self) -> None:
+    def add_agent_group(self, group_name: str, agent_ids) -> None:
+        self._replicated += 1
+        try:
             self._push_shard_map()
-            self._round_msgs = self._b_msgs
-            try:
-                payload = np.frombuffer(bytes(self._b_payload) + bytes(32), dtype=np.uint8)
-                self.exchange.export_mixed(
-                    np.asarray(self._b_sender, np.uint32), np.asarray(self._b_kind, np.uint8),
-                    np.asarray(self._b_target, np.uint32), np.asarray(self._b_list_off, np.uint64),
-                    np.asarray(self._b_list_idx, np.uint32), np.asarray(self._b_prio, np.uint8),
-                    np.asarray(self._b_type, np.uint8), np.asarray(self._b_len, np.uint16),
-                    np.asarray(self._b_off, np.uint64), payload, np.asarray(self._b_ts, np.float64),
-                    seq_base=composite_seq(self._round, self.rank))
-            finally:
-                self._round += 1
-                self._next_seq = composite_seq(self._round, self.rank)
-                self._reset_buffer()
+            super().add_agent_group(group_name, agent_ids)
+        finally:
+            self._replicated -= 1
 
-        def _flush_import(self) -> None:
-            try:
-                self.exchange.import_all()
-                lost = self.shard.stats()["ring_overflow"] - self._seen_overflow
-                if lost > 0:
-                    self._seen_overflow += lost
-                    raise SdbError(-4, f"{lost} message(s) not enqueued on shard {self.rank}: a receiver's ring is full "
-                                       f"(GpuConfig.ring_slots={self.gpu_config.ring_slots})")
-            except Exception as e:
-                self._fail_round(e)
-                raise
-            self._round_msgs = []
+    create_group = add_agent_group
 
-        def _after_send(self) -> None:
-            # no automatic flush: it is a collective; the caller decides when every rank flushes
-            if len(self._b_sender) >= self.gpu_config.flush_threshold:
-                raise RuntimeError("send buffer full: call flush() (collectively) more often or raise flush_threshold")
+    def _push_shard_map(self) -> None:
+        if self._map_dirty and self._agent_name:
+            self.shard.set_agent_shards(shard_map_for_names(self._agent_name, self.world))
+            self._map_dirty = False
 
-        # ---- local receive on the owner
-        def receive_messages(self, agent_id: str, max_messages: int = 100, timeout: float = 1.0):
-            if self.owner(agent_id) != self.rank:
-                raise ValueError(f"agent {agent_id!r} lives on shard {self.owner(agent_id)}, not on rank {self.rank}")
-            if agent_id not in self._agent_idx:
-                return []
-            return self._receive_local(agent_id, max_messages)
+    def _sync_group(self, group_name: str) -> int:
+        self._push_shard_map()              # ownership must be known before the group is filtered
+        return super()._sync_group(group_name)
 
-        def _pre_read(self) -> None:
-            return None                              # reads see what earlier collective flushes delivered
+    # ---- local sends: every agent they name must already be known everywhere
+    def _require_known(self, *agent_ids) -> None:
+        for a in agent_ids:
+            if a is not None and a not in self._agent_idx:
+                raise KeyError(f"agent {a!r} must be registered (on every rank) before it is used in a send")
 
-        def peek_messages(self, agent_id: str, max_messages: int = 100):
-            if self.owner(agent_id) != self.rank:
-                raise ValueError(f"agent {agent_id!r} lives on shard {self.owner(agent_id)}, not on rank {self.rank}")
-            if agent_id not in self._agent_idx:
-                return []
-            return super().peek_messages(agent_id, max_messages)
+    def send_message(self, sender_id, content, receiver_id=None, message_type=None, priority=None, metadata=None,
+                     visible_to=None, **kw):
+        self._require_known(sender_id, receiver_id, *(visible_to or []))
+        return super().send_message(sender_id, content, receiver_id, message_type or MessageType.CHAT,
+                                    priority if priority is not None else MessagePriority.NORMAL, metadata, visible_to, **kw)
 
-        def deregister_agent(self, agent_id: str) -> None:
-            """REPLICATED, like register_agent (the registry must agree on every rank)."""
-            super().deregister_agent(agent_id)
+    def send_to_group(self, sender_id, group_name, content, message_type=None, priority=None, metadata=None):
+        self._require_known(sender_id)
+        return super().send_to_group(sender_id, group_name, content, message_type or MessageType.CHAT,
+                                     priority if priority is not None else MessagePriority.NORMAL, metadata)
 
-        def close(self) -> None:
-            try:
-                if hasattr(self.exchange, "close"):
-                    self.exchange.close()
-            finally:
-                self._b_sender = []                      # nothing is flushed on close: flush() is collective
-                super().close()
+    # ---- collective flush: export (local) -> exchange (collective) -> import (local)
+    def flush(self) -> None:
+        try:
+            self._flush_export()
+            self.exchange.exchange()
+        except Exception as e:
+            self._fail_round(e)
+            raise
+        self._flush_import()
 
-    return ShardedSwarmsDB(**kw)
+    def _fail_round(self, e: Exception) -> None:
+        for m in self._round_msgs:
+            m.status = MessageStatus.FAILED
+            m.metadata["error"] = str(e)
+        self._round_msgs = []
+
+    def _flush_export(self) -> None:
+        self._push_shard_map()
+        self._round_msgs = self._b_msgs
+        try:
+            payload = np.frombuffer(bytes(self._b_payload) + bytes(32), dtype=np.uint8)
+            self.exchange.export_mixed(
+                np.asarray(self._b_sender, np.uint32), np.asarray(self._b_kind, np.uint8),
+                np.asarray(self._b_target, np.uint32), np.asarray(self._b_list_off, np.uint64),
+                np.asarray(self._b_list_idx, np.uint32), np.asarray(self._b_prio, np.uint8),
+                np.asarray(self._b_type, np.uint8), np.asarray(self._b_len, np.uint16),
+                np.asarray(self._b_off, np.uint64), payload, np.asarray(self._b_ts, np.float64),
+                seq_base=composite_seq(self._round, self.rank))
+        finally:
+            self._round += 1
+            self._next_seq = composite_seq(self._round, self.rank)
+            self._reset_buffer()
+
+    def _flush_import(self) -> None:
+        try:
+            self.exchange.import_all()
+            lost = self.shard.stats()["ring_overflow"] - self._seen_overflow
+            if lost > 0:
+                self._seen_overflow += lost
+                raise SdbError(-4, f"{lost} message(s) not enqueued on shard {self.rank}: a receiver's ring is full "
+                                   f"(GpuConfig.ring_slots={self.gpu_config.ring_slots})")
+        except Exception as e:
+            self._fail_round(e)
+            raise
+        self._round_msgs = []
+
+    def _after_send(self) -> None:
+        # no automatic flush: it is a collective; the caller decides when every rank flushes
+        if len(self._b_sender) >= self.gpu_config.flush_threshold:
+            raise RuntimeError("send buffer full: call flush() (collectively) more often or raise flush_threshold")
+
+    # ---- local receive on the owner
+    def receive_messages(self, agent_id: str, max_messages: int = 100, timeout: float = 1.0):
+        if self.owner(agent_id) != self.rank:
+            raise ValueError(f"agent {agent_id!r} lives on shard {self.owner(agent_id)}, not on rank {self.rank}")
+        if agent_id not in self._agent_idx:
+            return []
+        return self._receive_local(agent_id, max_messages)
+
+    def _pre_read(self) -> None:
+        return None                              # reads see what earlier collective flushes delivered
+
+    def peek_messages(self, agent_id: str, max_messages: int = 100):
+        if self.owner(agent_id) != self.rank:
+            raise ValueError(f"agent {agent_id!r} lives on shard {self.owner(agent_id)}, not on rank {self.rank}")
+        if agent_id not in self._agent_idx:
+            return []
+        return super().peek_messages(agent_id, max_messages)
+
+    def deregister_agent(self, agent_id: str) -> None:
+        """REPLICATED, like register_agent (the registry must agree on every rank)."""
+        super().deregister_agent(agent_id)
+
+    def close(self) -> None:
+        try:
+            if hasattr(self.exchange, "close"):
+                self.exchange.close()
+        finally:
+            self._b_sender = []                      # nothing is flushed on close: flush() is collective
+            super().close()
+
+
+def make_sharded_swarmsdb(rank: int, world: int, exchange_factory=None, shard=None, **kw) -> ShardedSwarmsDB:
+    """Factory kept for callers that pass everything by keyword: `ShardedSwarmsDB(rank, world, ...)`."""
+    return ShardedSwarmsDB(rank, world, exchange_factory=exchange_factory, shard=shard, **kw)

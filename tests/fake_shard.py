@@ -3,7 +3,7 @@ It lets the host-side multi-GPU logic (swarmdb_b200/sharded.py) run under gloo o
 numpy blobs, `import` replays them into oracle/cpu_ref.c with the shard's ownership filter."""
 import numpy as np
 
-from oracle.cpu_ref import HDR_DTYPE, CpuOracle
+from oracle.cpu_ref import CpuOracle
 
 MAGIC = 0x57424453
 

@@ -6,7 +6,6 @@ import os
 import socket
 
 import numpy as np
-import pytest
 
 from swarmdb_b200 import sharded
 
