@@ -62,22 +62,33 @@ class Workload:
     def members(self, g):
         return self.perm[g * self.F:(g + 1) * self.F]
 
-    def batch(self):
+    def batch(self, rng_send=None, rng_pay=None, var_len=False):
         S = self.S
-        grp = self.rng_send.integers(0, self.G, S).astype(np.uint32)
-        snd = self.rng_send.integers(0, self.A, S).astype(np.uint32)
+        rs = rng_send if rng_send is not None else self.rng_send
+        rp = rng_pay if rng_pay is not None else self.rng_pay
+        grp = rs.integers(0, self.G, S).astype(np.uint32)
+        snd = rs.integers(0, self.A, S).astype(np.uint32)
         while True:                                    # resample senders that are members of their group
             bad = self.group_of[snd] == grp
             nb = int(bad.sum())
             if nb == 0:
                 break
-            snd[bad] = self.rng_send.integers(0, self.A, nb).astype(np.uint32)
-        prio = self.rng_send.integers(0, 4, S).astype(np.uint8)
+            snd[bad] = rs.integers(0, self.A, nb).astype(np.uint32)
+        prio = rs.integers(0, 4, S).astype(np.uint8)
         typ = np.zeros(S, np.uint8)
-        lens = np.full(S, self.L, np.uint16)
+        lens = rs.integers(1, self.L + 1, S).astype(np.uint16) if var_len else np.full(S, self.L, np.uint16)
         off = np.arange(S, dtype=np.uint64) * self.L
-        payload = ALNUM[self.rng_pay.integers(0, 62, S * self.L)]
+        payload = ALNUM[rp.integers(0, 62, S * self.L)]
         return snd, grp, prio, typ, lens, off, payload
+
+    # ---- verified steps (outside every timed region): batches any rank can regenerate
+    PARITY_STEPS = 2
+
+    def parity_batch(self, step, rank):
+        """Step 0 has the timed shape (fixed 256-byte payloads), step 1 SURVEY 8d's correctness variant (lengths
+        U[1,256]).  Seeded by (step, rank) so rank 0 can rebuild every rank's batch for the oracle."""
+        seed = 7700 + 64 * step + rank
+        return self.batch(np.random.default_rng(seed), np.random.default_rng(seed + 32), var_len=(step % 2 == 1))
 
 
 # ------------------------------------------------------------------------------------ clocks
@@ -182,6 +193,39 @@ def cpu_roundtrip(wl: Workload, budget_s: float, max_batches: int):
     dt = time.perf_counter() - t0
     o.close()
     return routed / dt, cores, k, per_batch_ms
+
+
+def oracle_parity_digests(wl: Workload, world: int, seq_base: int):
+    """Ground truth for the verified steps: ONE queue (oracle/cpu_ref.c) fed every rank's parity batches in
+    (step, rank) order - the order the shards import them - and drained; returns (per-agent stream digests, records).
+    Uses the oracle's multi-threaded path (same streams as its single-threaded path: tests/test_oracle_c.py)."""
+    from oracle.cpu_ref import CpuOracle
+    cores = os.cpu_count() or 1
+    o = CpuOracle(wl.A, wl.G)
+    for g in range(wl.G):
+        o.create_group(g, wl.members(g))
+    o.digest_enable()
+    o.next_seq = seq_base
+    records = 0
+    for step in range(wl.PARITY_STEPS):
+        for r in range(world):
+            routed, drained, _ = o.mt_group_roundtrip(cores, *wl.parity_batch(step, r), max_messages=1 << 30)
+            assert routed == drained
+            records += drained
+    dg = o.digest_read()
+    o.close()
+    return dg, records
+
+
+def parity_report(got: np.ndarray, delivered: int, wl: Workload, world: int, seq_base: int, how: str) -> dict:
+    want, records = oracle_parity_digests(wl, world, seq_base)
+    bad = np.nonzero(got != want)[0]
+    return {"checked": True, "match": bool(len(bad) == 0 and delivered == records), "agents": int(wl.A),
+            "agents_with_records": int((want != 0).sum()), "records": int(records), "records_delivered": int(delivered),
+            "mismatching_agents": int(len(bad)), "steps": wl.PARITY_STEPS, "n_gpus": world,
+            "stream_digest_xor": "%016x" % int(np.bitwise_xor.reduce(got)), "oracle": "oracle/cpu_ref.c (all host threads)",
+            "what": "per-agent order-sensitive digest of every delivered record (32-byte header + padded payload), "
+                    "include/swarmdb_b200.h 'stream digests'; " + how}
 
 
 def run_reference(args, rank, world):
@@ -339,6 +383,27 @@ def run_gpu(args, rank, world, local_rank):
     p99 = float(np.percentile(lat, 99)) if lat else None
     shard.receive_batch(None, 100, 0, copy_out=False)          # drain the rest
 
+    # ---- content parity at the benchmarked size (outside every timed region): two verified steps through the same
+    # calls, every agent's stream digested on the device, against one oracle queue fed the same batches
+    while shard.receive_batch(None, 100, 0, copy_out=False)[1]:
+        pass
+    shard.digest_reset()
+    seq_base = shard.stats()["next_seq"]
+    p_delivered = 0
+    for step in range(wl.PARITY_STEPS):
+        shard.send_group_batch(*wl.parity_batch(step, 0))
+        _, t, _ = shard.receive_batch(None, 100, 0, copy_out=False)
+        shard.digest_fold()
+        p_delivered += t
+    while True:
+        _, t, _ = shard.receive_batch(None, 100, 0, copy_out=False)
+        shard.digest_fold()
+        if t == 0:
+            break
+        p_delivered += t
+    parity = parity_report(shard.digest_read(), p_delivered, wl, 1, seq_base,
+                           "sdb_send_group_batch + sdb_receive_batch on one GPU")
+
     # ---- roofline of the dominant kernel (group fan-out)
     peak, peak_src = hbm_peak()
     fan_ms, fan_n = prof["fanout"]
@@ -371,6 +436,7 @@ def run_gpu(args, rank, world, local_rank):
                 "steps": Ke, "ms_per_step": e2e_ms / Ke},
         "gpu_launches": int(launches),
         "p50_dequeue_us": p50, "p99_dequeue_us": p99,
+        "parity": parity,
         "roofline": {"kernel": "k_group_fanout", "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                      "frac": achieved / peak, "traffic": traffic_note(), "peak_source": peak_src,
                      "algorithmic_bytes_per_msg": ALG_BYTES_FANOUT, "msgs_per_launch": per_step_msgs,

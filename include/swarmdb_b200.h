@@ -121,6 +121,10 @@ int sdb_get_stats(sdb_handle h, sdb_stats* out);
 /* Test hook: move the (empty) arena's write position, e.g. next to the 2^32-granule boundary where the
  * 32-bit ring handles wrap.  Only valid while no message is pending. */
 int sdb_debug_set_arena_pos(sdb_handle h, uint64_t granules);
+/* Move the sequence counter FORWARD to `next_seq` (no-op when it is already there or beyond).  A front-end that
+ * hands out message ids at send time (ids are derived from sequence numbers, replacing uuid4 M:72) calls this when a
+ * batch was refused, so the ids of the failed messages (M:501-519: marked FAILED, kept) are never issued twice. */
+int sdb_advance_seq(sdb_handle h, uint64_t next_seq);
 
 /* Per-kernel device timing (CUDA events on the handle's stream), used by bench.py for the
  * roofline: enable, run, then read accumulated milliseconds and launch counts per kernel class. */
@@ -222,6 +226,21 @@ int sdb_last_receive_dev(sdb_handle h, const uint32_t** count_dev, const sdb_msg
                          const uint8_t** payload_dev);
 /* Records and payload bytes of the LAST receive call; waits for it (the host side of SDB_RECV_ASYNC). */
 int sdb_last_receive_totals(sdb_handle h, uint64_t* total_out, uint64_t* payload_bytes_out);
+
+/* ---- stream digests: per-agent delivery order + content, checkable at any scale ---------------------------------
+ * What the reference promises a consumer is the ORDER and CONTENT of its own stream (drain loop M:553-601, filter
+ * M:579-585).  A digest per agent captures exactly that without moving the records off the device:
+ *   rec_hash = sum over the 64-bit little-endian words w_k (k = 0, 1, ..) of [sdb_msg_header | payload padded to
+ *              SDB_GRANULE] of fmix64(w_k ^ ((k + 1) * 0x9E3779B97F4A7C15))  mod 2^64   (fmix64 = MurmurHash3 finaliser)
+ *   chain    : d[a] <- (rotl64(d[a], 5) ^ rec_hash) * 0x9E3779B97F4A7C15, for every record delivered to agent a, in
+ *              delivery order; d[a] starts at 0.
+ * sdb_digest_fold folds the device-resident results of the LAST sdb_receive_batch call (bulk path; not the
+ * <= 8-agent latency path) into d[]; it is stream-ordered and does not synchronise.  sdb_digest_read copies
+ * d[agent_idx[i]] (agent_idx == NULL: agents 0..n-1) to the host.  Used by tests and by bench.py's parity check
+ * (1M agents, 1..8 GPUs) against the same definition in oracle/cpu_ref.c. */
+int sdb_digest_reset(sdb_handle h);
+int sdb_digest_fold(sdb_handle h);
+int sdb_digest_read(sdb_handle h, uint32_t n, const uint32_t* agent_idx, uint64_t* digest_out);
 
 /* ---- cross-shard delivery (one handle per GPU, one process per GPU) ----------------------------
  * Replaces the partitioned topic: _get_partition (M:309-312, salted hash() % num_partitions) and

@@ -54,6 +54,8 @@ typedef struct orc {
   uint32_t** gposv;       /* optional: position of each kept member in the full (unsharded) list */
   uint64_t next_seq;
   uint32_t watermark;
+  void* mt;               /* persistent context of the multi-threaded baseline path */
+  uint64_t* digest;       /* optional [max_agents]: order-sensitive digest of every record delivered to the agent */
   /* balancer */
   uint32_t n_backends; uint32_t* weight; uint64_t* load;
   uint32_t logtab[257];
@@ -74,6 +76,31 @@ static void build_log2_table(uint32_t* tab) {
   tab[256] = 1u << 24;
 }
 
+/* ---- per-agent stream digest (definition: include/swarmdb_b200.h, "stream digest") -------------------------
+ * rec_hash = sum over the 64-bit little-endian words w_k (k = 0..) of [32-byte header | payload padded to 32 bytes]
+ *            of fmix64(w_k ^ ((k + 1) * 0x9E3779B97F4A7C15)),  mod 2^64   (position-keyed, so word order matters)
+ * chain    : d <- (rotl64(d, 5) ^ rec_hash) * 0x9E3779B97F4A7C15,  d starts at 0   (so delivery order matters)
+ * It is how per-agent delivery order + every header field + every payload byte are compared at sizes where
+ * keeping both full result sets is impractical (1M agents, 10^7..10^8 records, several GPUs). */
+static uint64_t fmix64(uint64_t x) {
+  x ^= x >> 33; x *= 0xFF51AFD7ED558CCDull; x ^= x >> 33; x *= 0xC4CEB9FE1A85EC53ull; x ^= x >> 33;
+  return x;
+}
+static uint64_t rec_hash(const sdb_msg_header* h, const uint8_t* payload_padded) {
+  uint64_t w[4], acc = 0;
+  memcpy(w, h, 32);
+  for (uint32_t k = 0; k < 4; ++k) acc += fmix64(w[k] ^ ((uint64_t)(k + 1) * 0x9E3779B97F4A7C15ull));
+  const uint32_t nw = pad32(h->len) / 8;
+  for (uint32_t k = 0; k < nw; ++k) {
+    uint64_t x; memcpy(&x, payload_padded + 8ull * k, 8);
+    acc += fmix64(x ^ ((uint64_t)(k + 5) * 0x9E3779B97F4A7C15ull));
+  }
+  return acc;
+}
+static uint64_t digest_chain(uint64_t d, uint64_t rh) {
+  return (((d << 5) | (d >> 59)) ^ rh) * 0x9E3779B97F4A7C15ull;
+}
+
 orc* orc_create(uint32_t max_agents, uint32_t max_groups) {
   orc* o = (orc*)calloc(1, sizeof(orc));
   o->max_agents = max_agents; o->max_groups = max_groups ? max_groups : 1;
@@ -87,12 +114,14 @@ orc* orc_create(uint32_t max_agents, uint32_t max_groups) {
   return o;
 }
 
+static void mt_free_any(void* m);
 void orc_destroy(orc* o) {
   if (!o) return;
+  mt_free_any(o->mt);
   for (uint32_t a = 0; a < o->max_agents; ++a) { free(o->inbox[a].idx); free(o->inbox[a].done); }
   for (uint32_t g = 0; g < o->max_groups; ++g) { free(o->gmem[g]); free(o->gposv[g]); }
   free(o->gposv); free(o->inbox); free(o->gmem); free(o->gcnt); free(o->gdef); free(o->recs); free(o->store);
-  free(o->weight); free(o->load); free(o);
+  free(o->weight); free(o->load); free(o->digest); free(o);
 }
 
 void orc_register(orc* o, uint32_t a) { if (a < o->max_agents && a + 1 > o->watermark) o->watermark = a + 1; }
@@ -238,6 +267,7 @@ uint64_t orc_receive_batch(orc* o, uint32_t n_agents, const uint32_t* agent_idx,
         const orc_rec* r = &o->recs[in->idx[p]];
         if ((flags & SDB_RECV_PRIORITY) && r->hdr.prio != (uint8_t)L) continue;
         if (!peek) in->done[p] = 1;
+        if (o->digest) o->digest[a] = digest_chain(o->digest[a], rec_hash(&r->hdr, o->store + r->pay_off));
         if (hdr_out) hdr_out[total] = r->hdr;
         if (payload_out) memcpy(payload_out + pbytes, o->store + r->pay_off, pad32(r->hdr.len));
         pbytes += pad32(r->hdr.len); ++total; ++got;
@@ -254,6 +284,15 @@ uint64_t orc_pending(orc* o, uint32_t a) {
   uint64_t c = 0;
   for (uint64_t p = in->head; p < in->n; ++p) c += !in->done[p];
   return c;
+}
+
+/* digests: enable (allocates, zeroed) / reset / read.  Folding happens inside orc_receive_batch and the MT drain. */
+void orc_digest_enable(orc* o) {
+  if (!o->digest) o->digest = (uint64_t*)calloc(o->max_agents, 8);
+  else memset(o->digest, 0, (size_t)o->max_agents * 8);
+}
+void orc_digest_read(orc* o, uint32_t n, const uint32_t* agent_idx, uint64_t* out) {
+  for (uint32_t q = 0; q < n; ++q) { const uint32_t a = agent_idx ? agent_idx[q] : q; out[q] = (o->digest && a < o->max_agents) ? o->digest[a] : 0; }
 }
 
 /* ---- balancer (definition in include/swarmdb_b200.h; the reference has none, M:1281-1325) ---- */
@@ -307,33 +346,74 @@ void orc_select_backend_batch(orc* o, uint32_t n_req, const uint32_t* cost, uint
 }
 
 /* ---- multi-threaded group fan-out + drain for the CPU baseline --------------------------------
- * Threads own disjoint receiver sets (receiver % T == tid), so every inbox is appended by exactly
- * one thread in send order: same streams as the single-threaded path, no locks.  Records are
- * materialised per delivery (header + payload copy) - the work a CPU queue does per routed
- * message - into per-thread arenas, then drained per agent into per-thread output buffers. */
+ * A three-phase pipeline over T threads, all buffers persistent across calls (no allocation in the timed path
+ * after the first batch):
+ *   route        thread k takes the k-th contiguous slice of the sends and, for every member != sender (M:1268),
+ *                pushes (send, position) into bucket[k][receiver % T]          - every membership touched once;
+ *   materialise  thread d walks bucket[0..T-1][d] in that order (= global send order) and writes each record
+ *                (32-byte header + padded payload - the work a CPU queue does per routed message) into its own
+ *                arena, appending the record to the receiver's list: every inbox has exactly one writer, in send
+ *                order, so the streams equal the single-threaded path - no locks;
+ *   drain        thread d copies the first max_messages records of each of its agents to an output buffer
+ *                (and folds them into the stream digests when those are enabled). */
+typedef struct { uint32_t send, pos; } mt_ref;
+typedef struct { mt_ref* v; uint32_t n, cap; } mt_bucket;
 typedef struct {
-  orc* o; uint32_t tid, T, n; const uint32_t* sender; const uint32_t* group; const uint8_t* prio; const uint8_t* type;
-  const uint16_t* len; const uint64_t* payload_off; const uint8_t* payload; uint64_t seq_base; const uint64_t* rec0;
+  struct orc_mt* m; uint32_t tid;
   uint8_t* arena; uint64_t arena_cap, arena_used; uint64_t** lists; uint32_t* lcnt; uint32_t* lcap;
-  uint64_t routed, drained, checksum; uint32_t max_messages; uint8_t* out; uint64_t out_cap;
+  uint64_t routed, drained, checksum; uint8_t* out; uint64_t out_cap;
 } mt_task;
+typedef struct orc_mt {
+  orc* o; uint32_t T, slots;
+  mt_task* ts; pthread_t* th; mt_bucket* bucket;         /* bucket[k * T + d] */
+  uint64_t* rec0; uint32_t rec0_cap;
+  /* the batch being processed */
+  uint32_t n; const uint32_t* sender; const uint32_t* group; const uint8_t* prio; const uint8_t* type;
+  const uint16_t* len; const uint64_t* payload_off; const uint8_t* payload; uint64_t seq_base; uint32_t max_messages;
+} orc_mt;
 
-static void* mt_fanout(void* p) {
-  mt_task* t = (mt_task*)p; orc* o = t->o;
-  for (uint32_t i = 0; i < t->n; ++i) {
-    const uint32_t g = t->group[i];
-    const uint32_t pl = pad32(t->len[i]);
+static void* mt_route(void* p) {
+  mt_task* t = (mt_task*)p; orc_mt* m = t->m; orc* o = m->o;
+  const uint32_t T = m->T;
+  const uint32_t lo = (uint32_t)((uint64_t)m->n * t->tid / T), hi = (uint32_t)((uint64_t)m->n * (t->tid + 1) / T);
+  mt_bucket* row = m->bucket + (size_t)t->tid * T;
+  for (uint32_t d = 0; d < T; ++d) row[d].n = 0;
+  for (uint32_t i = lo; i < hi; ++i) {
+    const uint32_t g = m->group[i];
+    const uint32_t* mem = o->gmem[g];
     for (uint32_t j = 0; j < o->gcnt[g]; ++j) {
-      const uint32_t a = o->gmem[g][j];
-      if (a % t->T != t->tid || a == t->sender[i]) continue;
-      if (t->arena_used + 32 + pl > t->arena_cap) continue;      /* sized by the caller; never hit */
+      const uint32_t a = mem[j];
+      if (a == m->sender[i]) continue;                             /* M:1268 */
+      mt_bucket* b = &row[a % T];
+      if (b->n == b->cap) { b->cap = b->cap * 2 + 64; b->v = (mt_ref*)xrealloc(b->v, (size_t)b->cap * sizeof(mt_ref)); }
+      b->v[b->n].send = i; b->v[b->n].pos = j; b->n++;
+    }
+  }
+  return NULL;
+}
+
+static void* mt_materialise(void* p) {
+  mt_task* t = (mt_task*)p; orc_mt* m = t->m; orc* o = m->o;
+  const uint32_t T = m->T;
+  uint64_t need = 0;
+  for (uint32_t k = 0; k < T; ++k) {
+    const mt_bucket* b = &m->bucket[(size_t)k * T + t->tid];
+    for (uint32_t e = 0; e < b->n; ++e) need += 32 + pad32(m->len[b->v[e].send]);
+  }
+  if (need > t->arena_cap) { t->arena_cap = need + need / 4 + (1u << 20); t->arena = (uint8_t*)xrealloc(t->arena, t->arena_cap); }
+  t->arena_used = 0; t->routed = 0;
+  for (uint32_t k = 0; k < T; ++k) {
+    const mt_bucket* b = &m->bucket[(size_t)k * T + t->tid];
+    for (uint32_t e = 0; e < b->n; ++e) {
+      const uint32_t i = b->v[e].send, j = b->v[e].pos, g = m->group[i], a = o->gmem[g][j];
+      const uint32_t pl = pad32(m->len[i]);
       uint8_t* rec = t->arena + t->arena_used;
-      sdb_msg_header h; h.seq = t->seq_base + t->rec0[i] + j; h.timestamp = 0.0; h.sender = t->sender[i]; h.receiver = a;
-      h.group = g; h.len = t->len[i]; h.prio = t->prio[i]; h.type = t->type[i];
+      sdb_msg_header h; h.seq = m->seq_base + m->rec0[i] + j; h.timestamp = 0.0; h.sender = m->sender[i]; h.receiver = a;
+      h.group = g; h.len = m->len[i]; h.prio = m->prio[i]; h.type = m->type[i];
       memcpy(rec, &h, 32);
-      memcpy(rec + 32, t->payload + t->payload_off[i], t->len[i]);
-      memset(rec + 32 + t->len[i], 0, pl - t->len[i]);
-      const uint32_t slot = a / t->T;
+      memcpy(rec + 32, m->payload + m->payload_off[i], m->len[i]);
+      memset(rec + 32 + m->len[i], 0, pl - m->len[i]);
+      const uint32_t slot = a / T;
       if (t->lcnt[slot] == t->lcap[slot]) {
         t->lcap[slot] = t->lcap[slot] * 2 + 8;
         t->lists[slot] = (uint64_t*)xrealloc(t->lists[slot], (size_t)t->lcap[slot] * 8);
@@ -347,17 +427,18 @@ static void* mt_fanout(void* p) {
 }
 
 static void* mt_drain(void* p) {
-  mt_task* t = (mt_task*)p;
-  const uint32_t slots = (t->o->max_agents + t->T - 1) / t->T;
+  mt_task* t = (mt_task*)p; orc_mt* m = t->m;
   uint64_t used = 0, sum = 0;
-  for (uint32_t s = 0; s < slots; ++s) {
-    const uint32_t k = t->lcnt[s] < t->max_messages ? t->lcnt[s] : t->max_messages;
+  t->drained = 0;
+  for (uint32_t s = 0; s < m->slots; ++s) {
+    const uint32_t k = t->lcnt[s] < m->max_messages ? t->lcnt[s] : m->max_messages;
     for (uint32_t e = 0; e < k; ++e) {
       const uint8_t* rec = t->arena + t->lists[s][e];
       const sdb_msg_header* h = (const sdb_msg_header*)rec;
       const uint32_t sz = 32 + pad32(h->len);
       if (used + sz > t->out_cap) used = 0;                       /* ring the output buffer */
       memcpy(t->out + used, rec, sz);
+      if (m->o->digest) { uint64_t* d = &m->o->digest[(uint64_t)s * m->T + t->tid]; *d = digest_chain(*d, rec_hash(h, rec + 32)); }
       used += sz; sum += h->seq; t->drained++;
     }
     t->lcnt[s] = 0;
@@ -366,38 +447,55 @@ static void* mt_drain(void* p) {
   return NULL;
 }
 
+static void mt_free(orc_mt* m) {
+  if (!m) return;
+  for (uint32_t k = 0; k < m->T; ++k) {
+    for (uint32_t s = 0; s < m->slots; ++s) free(m->ts[k].lists[s]);
+    free(m->ts[k].lists); free(m->ts[k].lcnt); free(m->ts[k].lcap); free(m->ts[k].arena); free(m->ts[k].out);
+  }
+  for (size_t b = 0; b < (size_t)m->T * m->T; ++b) free(m->bucket[b].v);
+  free(m->bucket); free(m->ts); free(m->th); free(m->rec0); free(m);
+}
+
+static void mt_run(orc_mt* m, void* (*fn)(void*)) {
+  for (uint32_t k = 0; k < m->T; ++k) pthread_create(&m->th[k], NULL, fn, &m->ts[k]);
+  for (uint32_t k = 0; k < m->T; ++k) pthread_join(m->th[k], NULL);
+}
+
 /* Returns routed records; *drained_out and *checksum_out (sum of seq of drained records) verify the work. */
 uint64_t orc_mt_group_roundtrip(orc* o, uint32_t T, uint32_t n, const uint32_t* sender, const uint32_t* group,
                                 const uint8_t* prio, const uint8_t* type, const uint16_t* len, const uint64_t* payload_off,
                                 const uint8_t* payload, uint32_t max_messages, uint64_t* drained_out, uint64_t* checksum_out) {
   if (T == 0) T = 1;
-  uint64_t* rec0 = (uint64_t*)malloc((size_t)n * 8);
-  uint64_t rec = 0, bytes = 0;
-  for (uint32_t i = 0; i < n; ++i) { rec0[i] = rec; rec += o->gcnt[group[i]]; bytes += (uint64_t)o->gcnt[group[i]] * (32 + pad32(len[i])); }
-  mt_task* ts = (mt_task*)calloc(T, sizeof(mt_task));
-  pthread_t* th = (pthread_t*)calloc(T, sizeof(pthread_t));
-  const uint32_t slots = (o->max_agents + T - 1) / T;
-  for (uint32_t k = 0; k < T; ++k) {
-    mt_task* t = &ts[k];
-    t->o = o; t->tid = k; t->T = T; t->n = n; t->sender = sender; t->group = group; t->prio = prio; t->type = type; t->len = len;
-    t->payload_off = payload_off; t->payload = payload; t->seq_base = o->next_seq; t->rec0 = rec0;
-    t->arena_cap = bytes / T * 2 + (1u << 20); t->arena = (uint8_t*)malloc(t->arena_cap);
-    t->lists = (uint64_t**)calloc(slots, sizeof(uint64_t*)); t->lcnt = (uint32_t*)calloc(slots, 4); t->lcap = (uint32_t*)calloc(slots, 4);
-    t->max_messages = max_messages; t->out_cap = 64u << 20; t->out = (uint8_t*)malloc(t->out_cap);
+  orc_mt* m = (orc_mt*)o->mt;
+  if (m && m->T != T) { mt_free(m); m = NULL; }
+  if (!m) {
+    m = (orc_mt*)calloc(1, sizeof(orc_mt));
+    m->o = o; m->T = T; m->slots = (o->max_agents + T - 1) / T;
+    m->ts = (mt_task*)calloc(T, sizeof(mt_task)); m->th = (pthread_t*)calloc(T, sizeof(pthread_t));
+    m->bucket = (mt_bucket*)calloc((size_t)T * T, sizeof(mt_bucket));
+    for (uint32_t k = 0; k < T; ++k) {
+      mt_task* t = &m->ts[k];
+      t->m = m; t->tid = k;
+      t->lists = (uint64_t**)calloc(m->slots, sizeof(uint64_t*)); t->lcnt = (uint32_t*)calloc(m->slots, 4); t->lcap = (uint32_t*)calloc(m->slots, 4);
+      t->out_cap = 64u << 20; t->out = (uint8_t*)malloc(t->out_cap);
+    }
+    o->mt = m;
   }
-  for (uint32_t k = 0; k < T; ++k) pthread_create(&th[k], NULL, mt_fanout, &ts[k]);
-  for (uint32_t k = 0; k < T; ++k) pthread_join(th[k], NULL);
-  for (uint32_t k = 0; k < T; ++k) pthread_create(&th[k], NULL, mt_drain, &ts[k]);
-  for (uint32_t k = 0; k < T; ++k) pthread_join(th[k], NULL);
+  if (n > m->rec0_cap) { m->rec0_cap = n; m->rec0 = (uint64_t*)xrealloc(m->rec0, (size_t)n * 8); }
+  uint64_t rec = 0;
+  for (uint32_t i = 0; i < n; ++i) { m->rec0[i] = rec; rec += o->gcnt[group[i]]; }
+  m->n = n; m->sender = sender; m->group = group; m->prio = prio; m->type = type; m->len = len;
+  m->payload_off = payload_off; m->payload = payload; m->seq_base = o->next_seq; m->max_messages = max_messages;
+  mt_run(m, mt_route);
+  mt_run(m, mt_materialise);
+  mt_run(m, mt_drain);
   uint64_t routed = 0, drained = 0, sum = 0;
-  for (uint32_t k = 0; k < T; ++k) {
-    routed += ts[k].routed; drained += ts[k].drained; sum += ts[k].checksum;
-    for (uint32_t s = 0; s < slots; ++s) free(ts[k].lists[s]);
-    free(ts[k].lists); free(ts[k].lcnt); free(ts[k].lcap); free(ts[k].arena); free(ts[k].out);
-  }
+  for (uint32_t k = 0; k < T; ++k) { routed += m->ts[k].routed; drained += m->ts[k].drained; sum += m->ts[k].checksum; }
   o->next_seq += rec;
-  free(ts); free(th); free(rec0);
   if (drained_out) *drained_out = drained;
   if (checksum_out) *checksum_out = sum;
   return routed;
 }
+
+static void mt_free_any(void* m) { mt_free((orc_mt*)m); }

@@ -53,6 +53,8 @@ def lib():
         L.orc_set_backends.argtypes = [vp, u32, vp, vp]
         L.orc_get_backend_loads.argtypes = [vp, vp]
         L.orc_select_backend_batch.argtypes = [vp, u32, vp, u32, u64, vp]
+        L.orc_digest_enable.argtypes = [vp]
+        L.orc_digest_read.argtypes = [vp, u32, vp, vp]
         L.orc_mt_group_roundtrip.restype = u64
         L.orc_mt_group_roundtrip.argtypes = [vp, u32, u32] + [vp] * 7 + [u32, vp, vp]
     return _lib
@@ -154,6 +156,32 @@ class CpuOracle:
         total = lib().orc_receive_batch(self._h, n, _p(a), max_messages, flags, _p(counts), _p(hdr), _p(pay),
                                         C.cast(C.byref(pb), C.c_void_p))
         return counts, hdr[:total].copy(), pay[:pb.value].copy()
+
+    def digest_enable(self) -> None:
+        """Start (or restart from zero) folding every delivered record into per-agent stream digests."""
+        lib().orc_digest_enable(self._h)
+
+    def digest_read(self, agents=None) -> np.ndarray:
+        if agents is None:
+            n, a = self.max_agents, None
+        else:
+            a = _arr(agents, np.uint32)
+            n = len(a)
+        out = np.zeros(n, np.uint64)
+        lib().orc_digest_read(self._h, n, _p(a), _p(out))
+        return out
+
+    def receive_counts(self, agents, max_messages: int, flags: int = 0) -> Tuple[np.ndarray, int]:
+        """Receive without materialising the records (at-scale runs: digests carry the content)."""
+        if agents is None:
+            n, a = 0, None
+            counts = np.zeros(self.max_agents, np.uint32)
+        else:
+            a = _arr(agents, np.uint32)
+            n = len(a)
+            counts = np.zeros(n, np.uint32)
+        total = lib().orc_receive_batch(self._h, n, _p(a), max_messages, flags, _p(counts), None, None, None)
+        return counts, int(total)
 
     def pending(self, a: int) -> int:
         return lib().orc_pending(self._h, a)

@@ -3,7 +3,7 @@
 mkdir -p gpurun_out
 timeout 200 python -m pytest tests/test_gpu_xshard.py tests/test_gpu_parity.py -m gpu -x -q 2>&1 | tail -4
 run() {  # variant waves
-  SDB_FANOUT_VARIANT=$1 SDB_FANOUT_WAVES=$2 timeout 60 python scripts/dbg_import8.py 2>&1 | tail -1 | sed "s/^/v$1 w$2 proxy: /"
+  SDB_FANOUT_VARIANT=$1 SDB_FANOUT_WAVES=$2 timeout 60 python scripts/proxy_import8.py 2>&1 | tail -1 | sed "s/^/v$1 w$2 proxy: /"
 }
 bench() {
   SDB_FANOUT_WAVES=$2 timeout 100 python bench.py --steps 32 --warmup 4 --variant $1 --cpu-budget 0 > gpurun_out/ab.json 2> gpurun_out/ab.err

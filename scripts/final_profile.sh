@@ -12,6 +12,6 @@ timeout 300 ncu --set full --import-source on --clock-control none \
     -k 'regex:k_group_fanout_warp|k_recv_gather|k_pull_index|k_recv_select' -s 10 -c 5 -o $out/prof_n1 -f \
     python bench.py --steps 4 --warmup 3 --cpu-budget 0 > $out/ncu_n1.log 2>&1
 timeout 200 ncu --set full --import-source on --clock-control none -k regex:k_group_fanout_span -s 2 -c 1 -o $out/prof_span_w8 -f \
-    python scripts/dbg_import8.py > $out/ncu_span.log 2>&1
+    python scripts/proxy_import8.py > $out/ncu_span.log 2>&1
 cat $out/pytest_gpu.txt $out/pytest_gpu_variant3.txt $out/smoke.txt
 tail -c 600 $out/bench_n1.json

@@ -55,9 +55,10 @@ class SdbStats(C.Structure):
 
 
 EXPORTS = ["sdb_abi_version", "sdb_create", "sdb_destroy", "sdb_set_stream", "sdb_sync", "sdb_last_error",
-           "sdb_get_stats", "sdb_debug_set_arena_pos", "sdb_profile", "sdb_profile_read", "sdb_register_agents", "sdb_deregister_agents", "sdb_create_group", "sdb_send_batch",
+           "sdb_get_stats", "sdb_debug_set_arena_pos", "sdb_advance_seq", "sdb_profile", "sdb_profile_read", "sdb_register_agents", "sdb_deregister_agents", "sdb_create_group", "sdb_send_batch",
            "sdb_send_group_batch", "sdb_send_list_batch", "sdb_send_mixed_batch", "sdb_stage_batch", "sdb_submit_staged", "sdb_free_staged",
-           "sdb_receive_batch", "sdb_last_receive_dev", "sdb_last_receive_totals", "sdb_wire_bytes", "sdb_set_agent_shards",
+           "sdb_receive_batch", "sdb_last_receive_dev", "sdb_last_receive_totals",
+           "sdb_digest_reset", "sdb_digest_fold", "sdb_digest_read", "sdb_wire_bytes", "sdb_set_agent_shards",
            "sdb_export_group_batch", "sdb_export_mixed_batch", "sdb_export_mixed_batch_seq", "sdb_import_wire_batches", "sdb_wire_alloc", "sdb_wire_open",
            "sdb_wire_close", "sdb_import_wire_ptrs", "sdb_set_backends", "sdb_get_backend_loads",
            "sdb_release_backends", "sdb_select_backend_batch"]
@@ -84,6 +85,7 @@ def load_library() -> C.CDLL:
     L.sdb_last_error.restype = C.c_char_p; L.sdb_last_error.argtypes = [vp]
     L.sdb_get_stats.restype = i32; L.sdb_get_stats.argtypes = [vp, C.POINTER(SdbStats)]
     L.sdb_debug_set_arena_pos.restype = i32; L.sdb_debug_set_arena_pos.argtypes = [vp, u64]
+    L.sdb_advance_seq.restype = i32; L.sdb_advance_seq.argtypes = [vp, u64]
     L.sdb_profile.restype = i32; L.sdb_profile.argtypes = [vp, i32]
     L.sdb_profile_read.restype = i32; L.sdb_profile_read.argtypes = [vp, vp, vp]
     L.sdb_register_agents.restype = i32; L.sdb_register_agents.argtypes = [vp, u32, vp]
@@ -101,6 +103,9 @@ def load_library() -> C.CDLL:
     L.sdb_receive_batch.argtypes = [vp, u32, vp, u32, u32, vp, vp, u64, vp, u64, vp, vp]
     L.sdb_last_receive_dev.restype = i32; L.sdb_last_receive_dev.argtypes = [vp, vp, vp, vp]
     L.sdb_last_receive_totals.restype = i32; L.sdb_last_receive_totals.argtypes = [vp, vp, vp]
+    L.sdb_digest_reset.restype = i32; L.sdb_digest_reset.argtypes = [vp]
+    L.sdb_digest_fold.restype = i32; L.sdb_digest_fold.argtypes = [vp]
+    L.sdb_digest_read.restype = i32; L.sdb_digest_read.argtypes = [vp, u32, vp, vp]
     L.sdb_wire_bytes.restype = u64; L.sdb_wire_bytes.argtypes = [vp, u32, u64]
     L.sdb_set_agent_shards.restype = i32; L.sdb_set_agent_shards.argtypes = [vp, u32, vp]
     L.sdb_export_group_batch.restype = i32; L.sdb_export_group_batch.argtypes = [vp, u32] + [vp] * 7 + [u64, vp, vp, u64]
@@ -209,6 +214,10 @@ class Shard:
 
     def debug_set_arena_pos(self, granules: int) -> None:
         self._check(self._L.sdb_debug_set_arena_pos(self._h, granules))
+
+    def advance_seq(self, next_seq: int) -> None:
+        """Move the handle's sequence counter forward (ids of a refused batch are never reissued)."""
+        self._check(self._L.sdb_advance_seq(self._h, next_seq))
 
     PROFILE_KINDS = ["p2p", "fanout", "commit", "recv_count", "recv_scan", "recv_select", "recv_gather",
                      "arena_floor", "pick", "xshard", "index"]
@@ -412,6 +421,24 @@ class Shard:
         total, pbytes = C.c_uint64(0), C.c_uint64(0)
         self._check(self._L.sdb_last_receive_totals(self._h, C.cast(C.byref(total), C.c_void_p), C.cast(C.byref(pbytes), C.c_void_p)))
         return total.value, pbytes.value
+
+    # stream digests (definition in include/swarmdb_b200.h): order + content of every agent's stream, on the device
+    def digest_reset(self) -> None:
+        self._check(self._L.sdb_digest_reset(self._h))
+
+    def digest_fold(self) -> None:
+        """Fold the records of the last bulk receive (still on the device) into the per-agent digests."""
+        self._check(self._L.sdb_digest_fold(self._h))
+
+    def digest_read(self, agents=None) -> np.ndarray:
+        if agents is None:
+            a, n = None, self.max_agents
+        else:
+            a = _arr(agents, np.uint32)
+            n = len(a)
+        out = np.zeros(n, np.uint64)
+        self._check(self._L.sdb_digest_read(self._h, n, _p(a), _p(out)))
+        return out
 
     def receive_one(self, agent: int, max_messages: int = 100, flags: int = 0):
         """Latency path for a single agent (one kernel launch, one D2H): returns (headers, payload)

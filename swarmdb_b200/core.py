@@ -226,6 +226,7 @@ class SwarmsDB:
         self._backend_name: List[str] = []
         self._id_hi = 0 if g.deterministic_ids else (((g.id_nonce if g.id_nonce is not None else secrets.randbits(63)) & ((1 << 63) - 1)) << 64)
         self._next_seq = 1                      # mirror of the handle's sequence counter
+        self._list_cap = 2 * g.max_agents + 1024 - 8      # the handle's default list_pool_entries, minus slack
         self._seq_to_id: Dict[int, str] = {}
         self._reset_buffer()
         self._closed = False
@@ -308,7 +309,8 @@ class SwarmsDB:
             for m in msgs:
                 m.status = MessageStatus.FAILED
                 m.metadata["error"] = str(e)
-            self._next_seq = self.shard.stats()["next_seq"]
+            # ids already handed out stay used: the device counter moves up to the host's, never the other way
+            self.shard.advance_seq(self._next_seq)
             self._reset_buffer()
             raise
         self._reset_buffer()
@@ -388,7 +390,7 @@ class SwarmsDB:
         if md:
             extras["m"] = md
         if message.visible_to:
-            extras["v"] = message.visible_to
+            extras.update(self._encode_visibility(message.visible_to))
         if token_count is not None:
             extras["t"] = token_count
         if extras:
@@ -424,7 +426,35 @@ class SwarmsDB:
         self._after_send()
         return message.id
 
+    def _encode_visibility(self, visible_to: List[str]) -> Dict[str, Any]:
+        """How `visible_to` (M:82) travels inside each copy's payload.  Short lists go as names ("v").  A broadcast
+        to (nearly) everybody would put O(agents) bytes into every one of O(agents) copies, so long lists travel
+        as their COMPLEMENT over the dense agent indices known at send time: "vc" = [n, [indices < n that are NOT
+        visible]] (sender, excluded and not-yet/no-longer registered agents).  Indices agree on every rank of a
+        sharded deployment (the registry is replicated), so any receiver reconstructs the exact set."""
+        if len(visible_to) <= 32:
+            return {"v": visible_to}
+        n = len(self._agent_name)
+        vis = {self._agent_idx[a] for a in visible_to if a in self._agent_idx}
+        if len(vis) != len(set(visible_to)):                  # names the registry has never seen: keep them literal
+            return {"v": visible_to}
+        comp = [i for i in range(n) if i not in vis]
+        if len(comp) >= len(visible_to):
+            return {"v": visible_to}
+        return {"vc": [n, comp]}
+
+    def _decode_visibility(self, extras: Dict[str, Any]) -> List[str]:
+        if "vc" in extras:
+            n, comp = extras["vc"]
+            skip = set(comp)
+            return [self._agent_name[i] for i in range(min(n, len(self._agent_name))) if i not in skip]
+        return list(extras.get("v", []))
+
     def _stage_list(self, sender: int, recips: List[int], prio: int, type_code: int, payload: bytes, ts: float) -> None:
+        # recipient lists (and the one-entry lists of buffered point-to-point sends) share the device's per-batch
+        # list pool: flush first if this list would not fit beside what is already buffered
+        if self._b_sender and len(self._b_list_idx) + len(recips) + len(self._b_sender) + 1 > self._list_cap:
+            self.flush()
         self._stage(2, sender, len(self._b_list_off) - 1, prio, type_code, payload, ts)
         self._b_list_idx.extend(recips)
         self._b_list_off.append(len(self._b_list_idx))
@@ -639,7 +669,7 @@ class SwarmsDB:
                 receiver_id=None if receiver == _native.NO_RECEIVER else names[receiver],
                 content=content, type=_TYPE_BY_CODE[t & TYPE_MASK], priority=MessagePriority(prios[k]),
                 timestamp=stamps[k], status=status, metadata=metadata,
-                token_count=extras.get("t") if extras else None, visible_to=list(extras.get("v", [])) if extras else [])
+                token_count=extras.get("t") if extras else None, visible_to=self._decode_visibility(extras) if extras else [])
             if record:
                 self.messages[m.id] = m                    # M:587-588
             msgs.append(m)

@@ -26,6 +26,7 @@ cudaError_t sdb_launch_pull(const sdb_dev_view*, const sdb_pull_view*, const sdb
 cudaError_t sdb_launch_receive(const sdb_dev_view*, const sdb_recv_args*, cudaStream_t, int*, sdb_profiler*, int);
 cudaError_t sdb_launch_receive_small(const sdb_dev_view*, const uint32_t*, uint32_t, uint32_t, uint32_t, uint32_t, uint32_t*,
                                      uint32_t*, uint8_t*, cudaStream_t, sdb_profiler*);
+cudaError_t sdb_launch_digest(const sdb_recv_args*, uint32_t, unsigned long long*, int, cudaStream_t);
 cudaError_t sdb_launch_arena_floor(const sdb_dev_view*, uint32_t, uint32_t, unsigned long long*, cudaStream_t);
 cudaError_t sdb_launch_pick(int mode, uint32_t n_backends, const uint32_t* weight_dev, unsigned long long* load_dev,
                             uint32_t n_req, const uint32_t* cost_dev, uint64_t seed, uint32_t* out_dev,
@@ -114,6 +115,8 @@ struct sdb_ctx {
   uint8_t* small_host = nullptr;               // pinned mirror
   uint64_t small_bytes = 0;
   uint64_t pay_cap_gran = 0;
+  sdb_recv_args last_rx{}; bool last_rx_valid = false;   // the last bulk receive (sdb_digest_fold reads its device results)
+  unsigned long long* digest = nullptr;                  // [max_agents] stream digests, allocated on first use
   // backends
   uint32_t* be_weight = nullptr; unsigned long long* be_load = nullptr; uint32_t n_backends = 0;
   uint32_t* be_req_cost = nullptr; uint32_t* be_out = nullptr; unsigned long long* be_scratch = nullptr;
@@ -575,7 +578,7 @@ int sdb_destroy(sdb_handle h) {
                  h->xs_lw_tops, h->xs_tab, h->xs_meta, h->shard_of_dev, h->rx_agent, h->rx_cnt,
                  h->rx_rec_local, h->rx_rec_tops, h->rx_plan_handle, h->rx_plan_glen, h->rx_plan_local, h->rx_plan_tops,
                  h->rx_totals, h->rx_big_list, h->rx_big_count, h->rx_count, h->rx_hdr, h->rx_payload,
-                 h->be_weight, h->be_load, h->be_scratch, h->be_logtab, h->be_req_cost, h->be_out};
+                 h->be_weight, h->be_load, h->be_scratch, h->be_logtab, h->be_req_cost, h->be_out, h->digest};
   for (void* p : dev) if (p) cudaFree(p);
   if (h->descs_host) cudaFreeHost(h->descs_host);
   if (h->list_host) cudaFreeHost(h->list_host);
@@ -659,6 +662,12 @@ int sdb_debug_set_arena_pos(sdb_handle h, uint64_t granules) {
   if (rc != SDB_OK) return rc;
   if (st.enqueued != st.delivered + 0 && st.enqueued - st.delivered != 0) return fail(h, SDB_EINVAL, "messages pending");
   h->arena_tail = granules; h->arena_floor = granules;
+  return SDB_OK;
+}
+
+int sdb_advance_seq(sdb_handle h, uint64_t next_seq) {
+  if (!h) return SDB_EINVAL;
+  if (next_seq > h->next_seq) h->next_seq = next_seq;
   return SDB_OK;
 }
 
@@ -1098,6 +1107,7 @@ int sdb_receive_batch(sdb_handle h, uint32_t n_agents, const uint32_t* agent_idx
     const uint64_t max_rec_bytes = pad32(h->cfg.max_payload_bytes);
     uint64_t rec_cap = std::min<uint64_t>(1024, std::min<uint64_t>(hdr_cap, payload_cap / max_rec_bytes));
     if (rec_cap == 0) return fail(h, SDB_EOUTPUT, "output buffers cannot hold a single maximum-size record");
+    h->last_rx_valid = false;
     cudaError_t e = sdb_launch_receive_small(&h->view, agent_idx, n_agents, max_messages, flags, static_cast<uint32_t>(rec_cap),
                                              h->rx_plan_handle, h->rx_plan_glen, h->rx_small, h->stream, &h->prof);
     h->launches += 1;
@@ -1147,6 +1157,7 @@ int sdb_receive_batch(sdb_handle h, uint32_t n_agents, const uint32_t* agent_idx
   int nl = 0;
   cudaError_t e = sdb_launch_receive(&h->view, &r, h->stream, &nl, &h->prof, h->sm_count);
   h->launches += nl;
+  h->last_rx = r; h->last_rx_valid = (e == cudaSuccess);
   if (e != cudaSuccess) return fail(h, SDB_ECUDA, std::string("receive launch: ") + cudaGetErrorString(e));
   if (async) return SDB_OK;          // the caller consumes on the device (stream order) or asks sdb_last_receive_totals later
   CUDA_TRY(h, cudaMemcpyAsync(h->totals_host, h->rx_totals, 2 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, h->stream));
@@ -1178,6 +1189,54 @@ int sdb_last_receive_totals(sdb_handle h, uint64_t* total_out, uint64_t* payload
   CUDA_TRY(h, cudaStreamSynchronize(h->stream));
   if (total_out) *total_out = h->totals_host[0];
   if (payload_bytes_out) *payload_bytes_out = h->totals_host[1] * SDB_GRANULE;
+  return SDB_OK;
+}
+
+// ---- stream digests -------------------------------------------------------------------------
+static int digest_ensure(sdb_ctx* h) {
+  if (h->digest) return SDB_OK;
+  CUDA_TRY(h, dmalloc(&h->digest, h->cfg.max_agents));
+  CUDA_TRY(h, cudaMemsetAsync(h->digest, 0, static_cast<size_t>(h->cfg.max_agents) * sizeof(unsigned long long), h->stream));
+  return SDB_OK;
+}
+
+int sdb_digest_reset(sdb_handle h) {
+  if (!h) return SDB_EINVAL;
+  int rc = digest_ensure(h);
+  if (rc != SDB_OK) return rc;
+  CUDA_TRY(h, cudaMemsetAsync(h->digest, 0, static_cast<size_t>(h->cfg.max_agents) * sizeof(unsigned long long), h->stream));
+  return SDB_OK;
+}
+
+int sdb_digest_fold(sdb_handle h) {
+  if (!h) return SDB_EINVAL;
+  if (!h->last_rx_valid) return fail(h, SDB_EINVAL, "sdb_digest_fold: no bulk receive to fold (the <= 8-agent latency path keeps no device results)");
+  int rc = digest_ensure(h);
+  if (rc != SDB_OK) return rc;
+  cudaError_t e = sdb_launch_digest(&h->last_rx, h->cfg.max_agents, h->digest, h->sm_count, h->stream);
+  h->launches += 1;
+  if (e != cudaSuccess) return fail(h, SDB_ECUDA, std::string("digest launch: ") + cudaGetErrorString(e));
+  return SDB_OK;
+}
+
+int sdb_digest_read(sdb_handle h, uint32_t n, const uint32_t* agent_idx, uint64_t* digest_out) {
+  if (!h || (n && !digest_out)) return SDB_EINVAL;
+  if (n == 0) return SDB_OK;
+  int rc = digest_ensure(h);
+  if (rc != SDB_OK) return rc;
+  if (!agent_idx) {
+    if (n > h->cfg.max_agents) return fail(h, SDB_EINVAL, "n > max_agents");
+    CUDA_TRY(h, cudaMemcpyAsync(digest_out, h->digest, static_cast<size_t>(n) * sizeof(uint64_t), cudaMemcpyDeviceToHost, h->stream));
+    CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+    return SDB_OK;
+  }
+  std::vector<unsigned long long> all(h->cfg.max_agents);
+  CUDA_TRY(h, cudaMemcpyAsync(all.data(), h->digest, all.size() * sizeof(unsigned long long), cudaMemcpyDeviceToHost, h->stream));
+  CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+  for (uint32_t i = 0; i < n; ++i) {
+    if (agent_idx[i] >= h->cfg.max_agents) return fail(h, SDB_EINVAL, "agent index out of range");
+    digest_out[i] = all[agent_idx[i]];
+  }
   return SDB_OK;
 }
 

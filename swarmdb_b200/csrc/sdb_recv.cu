@@ -503,6 +503,57 @@ k_recv_gather(sdb_dev_view v, sdb_recv_args r) {
 }
 
 // ------------------------------------------------------------------------------------------
+// stream digests (definition in include/swarmdb_b200.h): one warp per request slot folds the records the last
+// receive delivered to that agent, in delivery order, into digest[agent].  Lanes hash the 64-bit words of a
+// record in parallel (the per-word terms are position-keyed and summed), lane 0 chains the records.
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ unsigned long long sdb_fmix64(unsigned long long x) {
+  x ^= x >> 33; x *= 0xFF51AFD7ED558CCDull; x ^= x >> 33; x *= 0xC4CEB9FE1A85EC53ull; x ^= x >> 33;
+  return x;
+}
+__global__ void __launch_bounds__(256)
+k_recv_digest(sdb_recv_args r, uint32_t max_agents, unsigned long long* __restrict__ digest) {
+  const uint32_t lane = threadIdx.x & 31;
+  const uint32_t gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const uint32_t nw = (gridDim.x * blockDim.x) >> 5;
+  const unsigned long long K = 0x9E3779B97F4A7C15ull;
+  for (uint32_t q = gw; q < r.n; q += nw) {
+    const uint32_t cnt = r.count_out[q];
+    if (cnt == 0) continue;
+    const uint32_t a = r.agent_idx ? r.agent_idx[q] : q;
+    if (a >= max_agents) continue;
+    const uint32_t roff = r.rec_local[q] + r.rec_tops[q / SDB_SCAN_TILE];
+    unsigned long long d = digest[a];
+    for (uint32_t j = 0; j < cnt; ++j) {
+      const uint32_t rec = roff + j;
+      const unsigned long long* hw = reinterpret_cast<const unsigned long long*>(r.hdr_out + rec);
+      const uint32_t len = r.hdr_out[rec].len;
+      const uint32_t nwords = 4u + (((len + 31u) & ~31u) >> 3);
+      const unsigned long long po = (static_cast<unsigned long long>(r.plan_local[rec]) + r.plan_tops[rec / SDB_SCAN_TILE]) << 5;
+      const unsigned long long* pw = reinterpret_cast<const unsigned long long*>(r.payload_out + po);
+      unsigned long long acc = 0;
+      for (uint32_t k = lane; k < nwords; k += 32) {
+        const unsigned long long w = k < 4u ? hw[k] : pw[k - 4u];
+        acc += sdb_fmix64(w ^ (static_cast<unsigned long long>(k + 1u) * K));
+      }
+      for (int o = 16; o; o >>= 1) acc += __shfl_xor_sync(0xFFFFFFFFu, acc, o);
+      d = (((d << 5) | (d >> 59)) ^ acc) * K;
+    }
+    if (lane == 0) digest[a] = d;
+  }
+}
+
+extern "C" cudaError_t sdb_launch_digest(const sdb_recv_args* r, uint32_t max_agents, unsigned long long* digest,
+                                         int sm_count, cudaStream_t stream) {
+  if (r->n == 0) return cudaSuccess;
+  uint32_t grid = static_cast<uint32_t>(sm_count) * 8u;
+  const uint32_t need = (r->n + 7) / 8;
+  if (grid > need) grid = need;
+  k_recv_digest<<<grid, 256, 0, stream>>>(*r, max_agents, digest);
+  return cudaGetLastError();
+}
+
+// ------------------------------------------------------------------------------------------
 // latency path: up to 8 agents, up to 1024 records, ONE launch (count, scan, select, retire, gather).
 // Output block: u64 total records | u64 total granules | u32 counts[8] | pad to 64 B | the records
 // back to back in arena format (32-B header + padded payload), so the host needs one D2H.

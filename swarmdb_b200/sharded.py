@@ -97,10 +97,14 @@ class PeerExchange:
     pull descriptors and payloads straight out of the exporting GPUs' memory over NVLink.
     """
 
-    def __init__(self, shard, rank: int, world: int, max_sends: int, max_payload: int, device):
+    def __init__(self, shard, rank: int, world: int, max_sends: int, max_payload: int, device, stream=None):
         import torch
         import torch.distributed as dist
         self.shard, self.rank, self.world = shard, rank, world
+        # ONE stream carries the shard's copies/kernels AND the cross-rank barrier: a rank can only start reading
+        # its peers' export buffers after the barrier, and the barrier only completes after its own export
+        self.stream = stream if stream is not None else torch.cuda.Stream(device)
+        shard.set_stream(self.stream.cuda_stream)
         self.wire_bytes = shard.wire_bytes(max_sends, max_payload)
         self.mine = [shard.wire_alloc(self.wire_bytes) for _ in range(2)]          # (ptr, ipc handle)
         handles = [None] * world
@@ -116,7 +120,8 @@ class PeerExchange:
                     p = shard.wire_open(handles[r][b])
                     self.ptrs[b][r] = p
                     self.opened.append(p)
-        self.flag = torch.zeros(1, device=device)
+        with torch.cuda.stream(self.stream):
+            self.flag = torch.zeros(1, device=device)
         self.step_no = 0
 
     @property
@@ -134,8 +139,10 @@ class PeerExchange:
 
     def exchange(self) -> None:
         if self.world > 1:
+            import torch
             import torch.distributed as dist
-            dist.all_reduce(self.flag)                     # stream-ordered barrier: every rank's export is complete
+            with torch.cuda.stream(self.stream):
+                dist.all_reduce(self.flag)                 # stream-ordered barrier: every rank's export is complete
 
     def import_all(self) -> int:
         base = self.shard.import_wire_ptrs(self.ptrs[self.cur])
@@ -148,6 +155,12 @@ class PeerExchange:
         return self.import_all()
 
     def close(self) -> None:
+        if self.world > 1 and self.mine:
+            import torch
+            import torch.distributed as dist
+            with torch.cuda.stream(self.stream):
+                dist.all_reduce(self.flag)                 # nobody is still reading this rank's buffers
+            self.stream.synchronize()
         for p in self.opened:
             self.shard.wire_close(p, True)
         for p, _ in self.mine:
@@ -156,21 +169,27 @@ class PeerExchange:
 
 
 class TorchCudaBackend:
-    """Wire buffers in CUDA memory, exchanged with NCCL (torch.distributed), on torch's current stream."""
+    """Wire buffers in CUDA memory, exchanged with NCCL (torch.distributed) on ONE stream shared with the shard
+    (pass the shard so its copies/kernels and the collective are ordered against each other)."""
 
-    def __init__(self, device):
+    def __init__(self, device, shard=None, stream=None):
         import torch
         self.torch, self.device = torch, device
+        self.stream = stream if stream is not None else torch.cuda.Stream(device)
+        if shard is not None:
+            shard.set_stream(self.stream.cuda_stream)
 
     def alloc(self, nbytes: int):
-        return self.torch.zeros(nbytes, dtype=self.torch.uint8, device=self.device)
+        with self.torch.cuda.stream(self.stream):          # zero-fill ordered before the first export into it
+            return self.torch.zeros(nbytes, dtype=self.torch.uint8, device=self.device)
 
     def ptr(self, t) -> int:
         return t.data_ptr()
 
     def all_gather(self, out, inp) -> None:
         import torch.distributed as dist
-        dist.all_gather_into_tensor(out, inp)
+        with self.torch.cuda.stream(self.stream):
+            dist.all_gather_into_tensor(out, inp)
 
 
 def run_sharded_bench(args, rank: int, world: int, local_rank: int, wl):
@@ -212,9 +231,9 @@ def run_sharded_bench(args, rank: int, world: int, local_rank: int, wl):
     transport = os.environ.get("SDB_XSHARD", "peer")
     with torch.cuda.stream(stream):
         if transport == "peer":
-            ex = PeerExchange(shard, rank, world, wl.S, wl.S * wl.L, dev)
+            ex = PeerExchange(shard, rank, world, wl.S, wl.S * wl.L, dev, stream=stream)
         else:
-            ex = ShardExchange(shard, rank, world, wl.S, wl.S * wl.L, TorchCudaBackend(dev))
+            ex = ShardExchange(shard, rank, world, wl.S, wl.S * wl.L, TorchCudaBackend(dev, shard, stream))
         # each rank draws its own slice of the global batch: advance the generators by rank
         for _ in range(rank):
             wl.batch()
@@ -265,7 +284,7 @@ def run_sharded_bench(args, rank: int, world: int, local_rank: int, wl):
         st0 = shard.stats()
         launches0 = st0["kernel_launches"]
         shard.profile(True)
-        from bench import ALG_BYTES_FANOUT, ClockSampler, hbm_peak, traffic_note
+        from bench import ALG_BYTES_FANOUT, ClockSampler, hbm_peak, parity_report, traffic_note
         clocks = ClockSampler(local_rank); clocks.start()
         dist.barrier(); torch.cuda.synchronize()
         ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -307,6 +326,33 @@ def run_sharded_bench(args, rank: int, world: int, local_rank: int, wl):
         torch.cuda.synchronize(); dist.barrier()
         e2e_ms = (time.perf_counter() - t0) * 1e3
 
+        # ---- content parity on the real transport (outside every timed region): two verified steps with a FRESH
+        # export each (both export buffers in use), every shard digests the streams of the agents it owns on the
+        # device, rank 0 compares the union with ONE oracle queue fed all ranks' batches in (step, rank) order
+        while shard.receive_batch(None, 100, 0, copy_out=False)[1]:
+            pass
+        shard.digest_reset()
+        seq_base = shard.stats()["next_seq"]
+        p_delivered = 0
+        for step in range(wl.PARITY_STEPS):
+            ex.step(*wl.parity_batch(step, rank))
+            _, tt, _ = shard.receive_batch(None, 100, 0, copy_out=False)
+            shard.digest_fold()
+            p_delivered += tt
+        while True:
+            _, tt, _ = shard.receive_batch(None, 100, 0, copy_out=False)
+            shard.digest_fold()
+            if tt == 0:
+                break
+            p_delivered += tt
+        dg = shard.digest_read()
+        foreign_ok = not dg[smap != rank].any()
+        dsum = torch.from_numpy(dg.view(np.int64).copy()).to(dev)
+        dist.all_reduce(dsum)                                # owners are disjoint: the sum is the union
+        pstat = torch.tensor([p_delivered, 0 if foreign_ok else 1, seq_base], dtype=torch.int64, device=dev)
+        pmax = pstat.clone(); dist.all_reduce(pmax, op=dist.ReduceOp.MAX)
+        dist.all_reduce(pstat)
+
     t = torch.tensor([ms, float(delivered), e2e_ms, float(got), float(launches)], dtype=torch.float64, device=dev)
     mx = t.clone(); dist.all_reduce(mx, op=dist.ReduceOp.MAX)
     sm = t.clone(); dist.all_reduce(sm, op=dist.ReduceOp.SUM)
@@ -314,6 +360,11 @@ def run_sharded_bench(args, rank: int, world: int, local_rank: int, wl):
         ms_max, e2e_max = float(mx[0]), float(mx[2])
         total_delivered, total_got = float(sm[1]), float(sm[3])
         assert int(total_delivered) == K * per_rank_msgs * world, (total_delivered, K * per_rank_msgs * world)
+        parity = parity_report(dsum.cpu().numpy().view(np.uint64), int(pstat[0]), wl, world, seq_base,
+                               f"{transport} transport, fresh export per step, {world} GPUs")
+        if int(pstat[1]) or int(pmax[2]) * world != int(pstat[2]):
+            parity["match"] = False
+            parity["note"] = "a shard delivered to agents it does not own, or sequence bases diverged across ranks"
         peak, peak_src = hbm_peak()
         fan_ms, fan_n = prof["fanout"]
         fan_avg = fan_ms / max(fan_n, 1)
@@ -345,6 +396,7 @@ def run_sharded_bench(args, rank: int, world: int, local_rank: int, wl):
                          "ms_per_launch": fan_avg, "note": "rank 0's shard; per-send local fan-out is world-times narrower"},
             "kernels": {k: {"ms_per_launch": v[0] / v[1], "launches": v[1]} for k, v in prof.items() if v[1]},
             "phases_ms_rank0": phases,
+            "parity": parity,
             "cpu_baseline": None,
         }
         print(json.dumps(line), flush=True)
@@ -395,10 +447,11 @@ class ShardedSwarmsDB(SwarmsDB):
         self.exchange = (exchange_factory or self._default_exchange)(self.shard, rank, world, max(g2.flush_threshold, 1),
                                                                       max(1 << 22, 2 * (g2.max_payload_bytes + 31)))
 
-    @staticmethod
-    def _default_exchange(shard_, rank_, world_, max_sends, max_payload):
+    def _default_exchange(self, shard_, rank_, world_, max_sends, max_payload):
         import torch
-        return PeerExchange(shard_, rank_, world_, max_sends, max_payload, torch.device("cuda", torch.cuda.current_device()))
+        dev = torch.device("cuda", self.gpu_config.device)      # the shard's device, not whatever is current
+        torch.cuda.set_device(dev)
+        return PeerExchange(shard_, rank_, world_, max_sends, max_payload, dev)
 
     def owner(self, agent_id: str) -> int:
         return shard_of_agent(agent_id, self.world)
@@ -538,12 +591,20 @@ class ShardedSwarmsDB(SwarmsDB):
         super().deregister_agent(agent_id)
 
     def close(self) -> None:
+        """Collective like flush(): every rank closes.  Buffered sends are NOT flushed here (a flush is a collective
+        the caller schedules); the exchange's buffers are released only after their last reader is done."""
+        if self._closed:
+            return
         try:
-            if hasattr(self.exchange, "close"):
-                self.exchange.close()
+            if self.auto_save:
+                self.save_message_history()
         finally:
-            self._b_sender = []                      # nothing is flushed on close: flush() is collective
-            super().close()
+            try:
+                if hasattr(self.exchange, "close"):
+                    self.exchange.close()
+            finally:
+                self.shard.close()
+                self._closed = True
 
 
 def make_sharded_swarmsdb(rank: int, world: int, exchange_factory=None, shard=None, **kw) -> ShardedSwarmsDB:

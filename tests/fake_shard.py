@@ -20,6 +20,8 @@ class OracleShard:
     def deregister(self, idx): pass
     def sync(self): pass
     def close(self): self.o.close()
+    def advance_seq(self, next_seq): self.o.next_seq = max(self.o.next_seq, next_seq)
+
     def stats(self): return {"next_seq": self.o.next_seq, "ring_overflow": 0, "n_agents": self.max_agents}
 
     def set_agent_shards(self, shard_of):
@@ -61,7 +63,8 @@ class OracleShard:
         (wire if isinstance(wire, np.ndarray) else wire.numpy())[:len(blob)] = blob
 
     def send_mixed_batch(self, sender, kind, target, list_off, list_idx, prio, typ, lens, payload_off, payload, ts=None):
-        cap = self.wire_bytes(len(sender), len(payload))
+        cap = self.wire_bytes(len(sender), len(payload)) + 4 * len(list_idx if list_idx is not None else []) + \
+            8 * len(list_off if list_off is not None else [0])
         buf = np.zeros(cap, np.uint8)
         self.export_mixed_batch(sender, kind, target, list_off, list_idx, prio, typ, lens, payload_off, payload, buf, cap, ts)
         return self.import_wire_batches(1, buf, cap)
