@@ -228,23 +228,66 @@ def parity_report(got: np.ndarray, delivered: int, wl: Workload, world: int, seq
                     "include/swarmdb_b200.h 'stream digests'; " + how}
 
 
+WORKLOAD_C2 = ("c2: 1M agents, 15625 groups x 64, 65536 group sends/step (4,194,304 routed msgs), "
+               "256-byte payloads, full drain (receive_batch all agents, max_messages=100) each step")
+
+
+def workload_c3(world: int) -> str:
+    return (f"c3: c2's workload (1M agents, 15625 groups x 64, 256-byte payloads) with agents hash-sharded "
+            f"(fnv1a64 % {world}) over {world} GPUs; every rank ingests 65536 group sends/step; each shard drains its agents")
+
+
+def reference_python_leg(budget_s: float):
+    """BASELINE.md section 3 'reference-python': the reference's own class (staged by oracle/build_ref.py) over the
+    in-memory broker stub, one core: c1 exactly + a reduced c2.  None when the reference file is not available."""
+    if budget_s <= 0:
+        return None
+    try:
+        from oracle import ref_bench
+        return ref_bench.run_all(budget_s)
+    except Exception as e:  # pragma: no cover  (reported, never fatal for the GPU line)
+        return {"kind": "reference", "unavailable": repr(e)}
+
+
 def run_reference(args, rank, world):
+    """Reference arm: the CPU restatement of the path (oracle/cpu_ref.c, all host threads) on the arm's own
+    workload, `--warmup` untimed batches then `--steps` timed ones; the reference's own Python class is timed
+    beside it on a bounded sample (`cpu_baseline_reference`)."""
     if rank != 0:
         return
+    from oracle.cpu_ref import CpuOracle
     wl = Workload()
-    batches = max(args.steps, 1)
-    value, cores, k, per = cpu_roundtrip(wl, budget_s=120.0, max_batches=batches)
-    sample = (f"{k} full c2 batch(es) of {wl.S} group sends x {wl.F} (= {wl.S * wl.F} routed msgs each), fan-out + "
-              f"drain, {cores} threads partitioned by receiver")
+    cores = os.cpu_count() or 1
+    o = CpuOracle(wl.A, wl.G)
+    for g in range(wl.G):
+        o.create_group(g, wl.members(g))
+    batches = [wl.batch() for _ in range(2)]
+    for i in range(max(args.warmup, 1)):                                  # untimed: page faults, allocator, thread start
+        o.mt_group_roundtrip(cores, *batches[i % 2], max_messages=100)
+    per, routed = [], 0
+    t0 = time.perf_counter()
+    k = 0
+    while k < max(args.steps, 1) and (time.perf_counter() - t0) < 150.0:
+        t1 = time.perf_counter()
+        r, drained, _ = o.mt_group_roundtrip(cores, *batches[k % 2], max_messages=100)
+        per.append((time.perf_counter() - t1) * 1e3)
+        assert r == drained == wl.S * wl.F, (r, drained)
+        routed += drained; k += 1
+    value = routed / (time.perf_counter() - t0)
+    o.close()
+    sample = (f"{k} full c2 batch(es) of {wl.S} group sends x {wl.F} (= {wl.S * wl.F} routed msgs each): route + "
+              f"materialise + drain, {cores} threads, each inbox written by one thread")
     line = {
         "impl": "reference", "metric": "messages/sec routed (send->receive) at 1M agents, 64-way fanout",
-        "value": value, "unit": "messages/s", "n_gpus": args.gpus, "steps": k, "warmup": 1,
+        "value": value, "unit": "messages/s", "n_gpus": args.gpus, "steps": k, "warmup": max(args.warmup, 1),
         "ms_per_step": float(np.mean(per)) if per else None, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "u8", "data": "synthetic",
-        "config": {"workload": "c2: 1M agents, 15625 groups x 64, 65536 group sends/step, 256-byte payloads, full drain",
-                   "impl_detail": "oracle port of the reference path (oracle/cpu_ref.c); the Python reference and "
-                                  "its Kafka broker cannot run on the GPU box"},
+        "config": {"workload": WORKLOAD_C2 if args.gpus == 1 else workload_c3(args.gpus),
+                   "impl_detail": "CPU restatement of the reference path (oracle/cpu_ref.c, pinned to goldens produced by "
+                                  "the unmodified reference); one host, all threads; at --gpus N the CPU arm still runs "
+                                  "one c2 batch per step on this host"},
         "cpu_baseline": {"value": value, "unit": "messages/s", "cores": cores, "kind": "port", "sample": sample},
+        "cpu_baseline_reference": reference_python_leg(args.ref_budget),
         "e2e": {"value": value, "unit": "messages/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -330,6 +373,10 @@ def run_gpu(args, rank, world, local_rank):
     assert delivered == K * per_step_msgs, (delivered, K * per_step_msgs)
     value = delivered / (ms_total * 1e-3)
 
+    if args.no_extras:
+        print(json.dumps({"value": value, "ms_per_step": ms_total / K, "steps": K, "clocks": clk,
+                          "kernels": {k: (v[0] / v[1] if v[1] else None) for k, v in prof.items() if v[1]}}), flush=True)
+        return
     # ---- e2e: host buffers through the public bulk API, H2D and D2H inside the timed region
     rec_cap = per_step_msgs + (1 << 16)
     from swarmdb_b200._native import HDR_DTYPE
@@ -426,8 +473,7 @@ def run_gpu(args, rank, world, local_rank):
         "value": value, "unit": "messages/s", "n_gpus": 1, "steps": K, "warmup": W,
         "ms_per_step": ms_total / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "u8", "data": "synthetic",
-        "config": {"workload": "c2: 1M agents, 15625 groups x 64, 65536 group sends/step (4,194,304 routed msgs), "
-                               "256-byte payloads, full drain (receive_batch all agents, max_messages=100) each step",
+        "config": {"workload": WORKLOAD_C2,
                    "l2": "inputs larger than L2: each step writes 1.2 GB of records into an 8 GiB arena and reads "
                          "them back; no explicit flush needed",
                    "fanout_variant": args.variant, "ring_slots": ring_slots, "arena_bytes": 1 << 33},
@@ -443,8 +489,9 @@ def run_gpu(args, rank, world, local_rank):
                      "ms_per_launch": fan_avg_ms},
         "kernels": kernels,
         "cpu_baseline": {"value": cpu_value, "unit": "messages/s", "cores": cores, "kind": "port",
-                         "sample": f"{kb} full c2 batch(es) (4,194,304 routed msgs each), fan-out + drain, "
+                         "sample": f"{kb} full c2 batch(es) (4,194,304 routed msgs each), route + materialise + drain, "
                                    f"oracle/cpu_ref.c on {cores} threads"},
+        "cpu_baseline_reference": reference_python_leg(args.ref_budget),
     }
     print(json.dumps(line), flush=True)
     for s in staged:
@@ -460,6 +507,9 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--variant", type=int, default=int(os.environ.get("SDB_FANOUT_VARIANT", "2")))
     ap.add_argument("--cpu-budget", type=float, default=15.0)
+    ap.add_argument("--ref-budget", type=float, default=20.0,
+                    help="seconds for the reference-python leg (the reference's own class on one core); 0 = skip")
+    ap.add_argument("--no-extras", action="store_true", help="profiling runs: only the device-resident timed region")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))

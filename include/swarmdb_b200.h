@@ -129,7 +129,7 @@ int sdb_advance_seq(sdb_handle h, uint64_t next_seq);
 /* Per-kernel device timing (CUDA events on the handle's stream), used by bench.py for the
  * roofline: enable, run, then read accumulated milliseconds and launch counts per kernel class. */
 enum { SDB_PK_P2P = 0, SDB_PK_FANOUT, SDB_PK_COMMIT, SDB_PK_RECV_COUNT, SDB_PK_RECV_SCAN, SDB_PK_RECV_SELECT,
-       SDB_PK_RECV_GATHER, SDB_PK_ARENA_FLOOR, SDB_PK_PICK, SDB_PK_XSHARD, SDB_PK_INDEX, SDB_PK_N = 16 };
+       SDB_PK_RECV_GATHER, SDB_PK_ARENA_FLOOR, SDB_PK_PICK, SDB_PK_XSHARD, SDB_PK_INDEX, SDB_PK_XWAIT, SDB_PK_N = 16 };
 int sdb_profile(sdb_handle h, int enable);
 int sdb_profile_read(sdb_handle h, double* ms_out /* [SDB_PK_N] */, uint64_t* count_out /* [SDB_PK_N] */);
 
@@ -294,6 +294,29 @@ int sdb_wire_alloc(sdb_handle h, uint64_t bytes, void** dev_out, void* ipc_handl
 int sdb_wire_open(sdb_handle h, const void* ipc_handle, void** dev_out);
 int sdb_wire_close(sdb_handle h, void* dev, int opened /* 1: from sdb_wire_open, 0: from sdb_wire_alloc */);
 int sdb_import_wire_ptrs(sdb_handle h, uint32_t n_src, const void* const* wire_ptrs, uint64_t* seq_base_out);
+/* Flag-synchronised, host-asynchronous form of the peer-memory transport: no collective and no host round trip.
+ * Every export buffer of `wire_bytes` (as sized by sdb_wire_bytes) ends in a 128-byte control block with two
+ * counters: `ready` (last step whose export into the buffer is complete) and `done` (last step for which the
+ * buffer's OWNER finished importing every rank's buffer of that parity).  Steps count 1, 2, 3 ...; with two
+ * alternating buffers per rank, buffer step & 1 is used for step.
+ *   sdb_wire_wait_done     stream-ordered wait until every listed buffer's owner reports done >= step; call it with
+ *                          (step - 2) before exporting `step` into a buffer that peers read two steps ago
+ *   sdb_wire_publish       stream-ordered: ready = step (after the export's copies, which run on the same stream)
+ *   sdb_import_wire_ptrs_async
+ *                          waits ON THE DEVICE for ready >= step of every source (peer flags are polled over NVLink),
+ *                          then places and expands the import entirely on the device - arena position, sequence base
+ *                          and totals never visit the host (a device-resident cursor is the authority until the next
+ *                          call that needs them on the host) - and finally reports done = step in this rank's own
+ *                          buffer (wire_ptrs[shard_id]).  Three kernels do the work: one fused localize (wire headers,
+ *                          descriptors and group buckets read straight out of the exporting GPUs, decoupled
+ *                          look-back scan, placement), the fan-out (TMA pulls of the payloads over NVLink), the
+ *                          group-parallel index build.  An import that does not fit (arena / list pool) is dropped
+ *                          WHOLE and reported by the next host-synchronising call (SDB_EARENA_FULL / SDB_ECAPACITY).
+ *                          Traffic outside the fast shape (payloads above 512 bytes, agents in several groups) takes
+ *                          the synchronous import between the same flags. */
+int sdb_wire_wait_done(sdb_handle h, uint32_t n_src, const void* const* wire_ptrs, uint64_t wire_bytes, uint32_t step);
+int sdb_wire_publish(sdb_handle h, void* wire_dev, uint64_t wire_bytes, uint32_t step);
+int sdb_import_wire_ptrs_async(sdb_handle h, uint32_t n_src, const void* const* wire_ptrs, uint64_t wire_bytes, uint32_t step);
 
 /* ---- LLM backend balancer: set_llm_load_balancing / assign_llm_backend / get_llm_backend
  * (M:1281-1325).  The reference stores a flag and a dict and has NO pick algorithm

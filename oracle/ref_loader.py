@@ -1,9 +1,10 @@
 """Load the UNMODIFIED reference `SwarmsDB` class for oracle pinning (TEST INFRASTRUCTURE ONLY).
 
-Only usable where /root/reference exists (the build container, never the GPU box).  It is
-used by `tests/golden/make_golden.py` to generate the committed golden fixtures and by the
-CPU tests that re-check the restatement (`oracle/cpu_ref.c`, `oracle/pyref.py`) against the
-live reference when it is present.
+Loads /root/reference/swarmdb/" main.py" where that exists (the build container) and otherwise the
+byte-identical copy that `oracle/build_ref.py` staged under oracle/_ref/ (git-ignored; it travels to
+the GPU box with the snapshot).  It is used by `tests/golden/make_golden.py` to generate the committed
+golden fixtures, by the CPU tests that re-check the restatement (`oracle/cpu_ref.c`, `oracle/pyref.py`)
+against the live reference, and by `bench.py`'s reference-python timing leg.
 
 The reference cannot run as shipped; exactly two shims are applied and
 nothing else:
@@ -29,11 +30,21 @@ from pathlib import Path
 
 REFERENCE_ROOT = Path(os.environ.get("SWARMDB_REFERENCE_ROOT", "/root/reference"))
 REFERENCE_MAIN = REFERENCE_ROOT / "swarmdb" / " main.py"   # the filename really starts with a space
+STAGED_MAIN = Path(__file__).resolve().parent / "_ref" / "swarmdb_reference_main.py"    # oracle/build_ref.py
 _STUB_DIR = Path(__file__).resolve().parent / "kafka_stub"
 
 
+def reference_path():
+    """The unmodified reference file: in place when /root/reference exists, else the staged copy, else None."""
+    if REFERENCE_MAIN.is_file():
+        return REFERENCE_MAIN
+    if STAGED_MAIN.is_file():
+        return STAGED_MAIN
+    return None
+
+
 def reference_available() -> bool:
-    return REFERENCE_MAIN.is_file()
+    return reference_path() is not None
 
 
 class _DetUuid(types.ModuleType):
@@ -62,14 +73,15 @@ class _DetTime(types.ModuleType):
 
 def load_reference(deterministic: bool = True, module_name: str = "swarmdb_reference_main"):
     """Return the reference module object (fresh load each call, fresh stub broker)."""
-    if not reference_available():
-        raise FileNotFoundError(f"reference not present at {REFERENCE_MAIN}")
+    src = reference_path()
+    if src is None:
+        raise FileNotFoundError(f"reference not present at {REFERENCE_MAIN} and not staged at {STAGED_MAIN}")
     if str(_STUB_DIR) not in sys.path:
         sys.path.insert(0, str(_STUB_DIR))
     import confluent_kafka  # the stub
 
     confluent_kafka.reset_broker()
-    spec = importlib.util.spec_from_file_location(module_name, str(REFERENCE_MAIN))
+    spec = importlib.util.spec_from_file_location(module_name, str(src))
     mod = importlib.util.module_from_spec(spec)
     import warnings
 

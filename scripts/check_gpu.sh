@@ -1,11 +1,12 @@
 #!/bin/bash
 # short GPU check: full GPU suite + smoke + N=1 bench line (each under its own timeout)
 mkdir -p gpurun_out
-timeout 300 python -m pytest tests -m gpu -q -x 2>&1 | tail -6
+timeout 900 python -m pytest tests -m gpu -q -x --durations=8 2>&1 | tail -25
 timeout 120 python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -1
-timeout 200 python bench.py --steps 64 --warmup 4 > gpurun_out/bench_async.json 2> gpurun_out/bench_async.err; tail -3 gpurun_out/bench_async.err | cut -c1-400
+timeout 400 python bench.py --steps 32 --warmup 4 > gpurun_out/bench_n1.json 2> gpurun_out/bench_n1.err; tail -3 gpurun_out/bench_n1.err | cut -c1-400
 python - <<PY
 import json
-d=json.loads(open("gpurun_out/bench_async.json").read().strip().splitlines()[-1])
+d=json.loads(open("gpurun_out/bench_n1.json").read().strip().splitlines()[-1])
 print(round(d["value"]/1e9,3), round(d["ms_per_step"],4), {k:round(x["ms_per_launch"],4) for k,x in d["kernels"].items()}, round(d["roofline"]["frac"],4), "e2e", round(d["e2e"]["value"]/1e6,1), "launches", d["gpu_launches"], "p50", d["p50_dequeue_us"])
+print("parity", d.get("parity"))
 PY

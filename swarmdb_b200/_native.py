@@ -60,7 +60,7 @@ EXPORTS = ["sdb_abi_version", "sdb_create", "sdb_destroy", "sdb_set_stream", "sd
            "sdb_receive_batch", "sdb_last_receive_dev", "sdb_last_receive_totals",
            "sdb_digest_reset", "sdb_digest_fold", "sdb_digest_read", "sdb_wire_bytes", "sdb_set_agent_shards",
            "sdb_export_group_batch", "sdb_export_mixed_batch", "sdb_export_mixed_batch_seq", "sdb_import_wire_batches", "sdb_wire_alloc", "sdb_wire_open",
-           "sdb_wire_close", "sdb_import_wire_ptrs", "sdb_set_backends", "sdb_get_backend_loads",
+           "sdb_wire_close", "sdb_import_wire_ptrs", "sdb_wire_wait_done", "sdb_wire_publish", "sdb_import_wire_ptrs_async", "sdb_set_backends", "sdb_get_backend_loads",
            "sdb_release_backends", "sdb_select_backend_batch"]
 
 _lib = None
@@ -117,6 +117,9 @@ def load_library() -> C.CDLL:
     L.sdb_wire_open.restype = i32; L.sdb_wire_open.argtypes = [vp, vp, C.POINTER(vp)]
     L.sdb_wire_close.restype = i32; L.sdb_wire_close.argtypes = [vp, vp, i32]
     L.sdb_import_wire_ptrs.restype = i32; L.sdb_import_wire_ptrs.argtypes = [vp, u32, vp, vp]
+    L.sdb_wire_wait_done.restype = i32; L.sdb_wire_wait_done.argtypes = [vp, u32, vp, u64, u32]
+    L.sdb_wire_publish.restype = i32; L.sdb_wire_publish.argtypes = [vp, vp, u64, u32]
+    L.sdb_import_wire_ptrs_async.restype = i32; L.sdb_import_wire_ptrs_async.argtypes = [vp, u32, vp, u64, u32]
     L.sdb_import_wire_batches.restype = i32; L.sdb_import_wire_batches.argtypes = [vp, u32, vp, u64, vp]
     L.sdb_set_backends.restype = i32; L.sdb_set_backends.argtypes = [vp, u32, vp, vp]
     L.sdb_get_backend_loads.restype = i32; L.sdb_get_backend_loads.argtypes = [vp, u32, vp]
@@ -220,7 +223,7 @@ class Shard:
         self._check(self._L.sdb_advance_seq(self._h, next_seq))
 
     PROFILE_KINDS = ["p2p", "fanout", "commit", "recv_count", "recv_scan", "recv_select", "recv_gather",
-                     "arena_floor", "pick", "xshard", "index"]
+                     "arena_floor", "pick", "xshard", "index", "xwait"]
 
     def profile(self, enable: bool) -> None:
         self._check(self._L.sdb_profile(self._h, 1 if enable else 0))
@@ -372,6 +375,25 @@ class Shard:
         base = C.c_uint64(0)
         self._check(self._L.sdb_import_wire_ptrs(self._h, len(ptrs), C.cast(arr, C.c_void_p), C.cast(C.byref(base), C.c_void_p)))
         return base.value
+
+    # flag-synchronised, host-asynchronous peer transport (see include/swarmdb_b200.h)
+    @staticmethod
+    def _ptr_table(ptrs):
+        return (C.c_void_p * len(ptrs))(*[C.c_void_p(int(x)) for x in ptrs])
+
+    def wire_wait_done(self, ptrs, wire_bytes: int, step: int) -> None:
+        """Stream-ordered wait until the owner of every listed buffer has finished importing `step`."""
+        arr = self._ptr_table(ptrs)
+        self._check(self._L.sdb_wire_wait_done(self._h, len(ptrs), C.cast(arr, C.c_void_p), wire_bytes, step))
+
+    def wire_publish(self, wire_dev: int, wire_bytes: int, step: int) -> None:
+        """Stream-ordered: this buffer now holds the complete export of `step`."""
+        self._check(self._L.sdb_wire_publish(self._h, C.c_void_p(wire_dev), wire_bytes, step))
+
+    def import_wire_ptrs_async(self, ptrs, wire_bytes: int, step: int) -> None:
+        """Wait on the device for every source's `step`, import without a host round trip, report done."""
+        arr = self._ptr_table(ptrs)
+        self._check(self._L.sdb_import_wire_ptrs_async(self._h, len(ptrs), C.cast(arr, C.c_void_p), wire_bytes, step))
 
     def import_wire_batches(self, n_src: int, wire_dev_all: int, stride: int) -> int:
         """Expand the wire batches of `n_src` ranks (rank order, `stride` bytes apart) for the agents this shard owns."""

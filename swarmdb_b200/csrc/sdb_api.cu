@@ -19,13 +19,16 @@ extern "C" {
 cudaError_t sdb_launch_p2p(const sdb_dev_view*, const sdb_send_desc*, uint32_t, const uint8_t*, uint64_t, uint64_t, int, cudaStream_t, sdb_profiler*);
 cudaError_t sdb_send_prepare_device();
 cudaError_t sdb_launch_fanout(const sdb_dev_view*, const sdb_send_desc*, uint32_t, const uint8_t*, const uint32_t*,
-                              uint64_t, uint64_t, uint32_t, int, int, cudaStream_t, sdb_profiler*);
-cudaError_t sdb_launch_commit(const sdb_dev_view*, uint32_t, uint32_t, uint32_t*, uint32_t*, int, cudaStream_t, sdb_profiler*);
-cudaError_t sdb_launch_pull(const sdb_dev_view*, const sdb_pull_view*, const sdb_send_desc*, uint32_t, uint64_t, int,
-                            cudaStream_t, sdb_profiler*);
-cudaError_t sdb_launch_receive(const sdb_dev_view*, const sdb_recv_args*, cudaStream_t, int*, sdb_profiler*, int);
-cudaError_t sdb_launch_receive_small(const sdb_dev_view*, const uint32_t*, uint32_t, uint32_t, uint32_t, uint32_t, uint32_t*,
-                                     uint32_t*, uint8_t*, cudaStream_t, sdb_profiler*);
+                              uint64_t, uint64_t, uint32_t, int, int, cudaStream_t, sdb_profiler*, const sdb_batch_base*);
+cudaError_t sdb_launch_commit(const sdb_dev_view*, uint32_t, uint32_t, uint32_t*, uint32_t*, int, cudaStream_t, sdb_profiler*,
+                              const sdb_batch_base*);
+cudaError_t sdb_launch_pull(const sdb_dev_view*, const sdb_pull_view*, const sdb_send_desc*, uint32_t, uint32_t, const uint8_t*,
+                            uint32_t, uint32_t, const uint32_t*, const uint32_t*, uint64_t, int, cudaStream_t, sdb_profiler*, int*,
+                            const sdb_batch_base*);
+cudaError_t sdb_launch_receive(const sdb_dev_view*, const sdb_recv_args*, cudaStream_t, int*, sdb_profiler*, int, uint32_t);
+cudaError_t sdb_recv_prepare_device();
+cudaError_t sdb_launch_receive_small(const sdb_dev_view*, const uint32_t*, uint32_t, uint32_t, uint32_t, uint32_t, uint4*,
+                                     uint8_t*, cudaStream_t, sdb_profiler*);
 cudaError_t sdb_launch_digest(const sdb_recv_args*, uint32_t, unsigned long long*, int, cudaStream_t);
 cudaError_t sdb_launch_arena_floor(const sdb_dev_view*, uint32_t, uint32_t, unsigned long long*, cudaStream_t);
 cudaError_t sdb_launch_pick(int mode, uint32_t n_backends, const uint32_t* weight_dev, unsigned long long* load_dev,
@@ -36,6 +39,10 @@ void sdb_build_log2_table(uint32_t* tab257);
 cudaError_t sdb_launch_import_measure(const sdb_import_args*, uint32_t, uint32_t*, uint32_t*, uint32_t*, uint32_t*, uint32_t*,
                                       uint32_t*, uint32_t*, unsigned long long*, cudaStream_t, sdb_profiler*, int*);
 cudaError_t sdb_launch_import_localize(const sdb_import_args*, uint32_t, const uint32_t*, uint32_t*, cudaStream_t, sdb_profiler*, int*);
+cudaError_t sdb_launch_wire_wait(const uint32_t* const*, uint32_t, uint32_t, cudaStream_t);
+cudaError_t sdb_launch_wire_set(uint32_t*, uint32_t, cudaStream_t);
+cudaError_t sdb_launch_import_fused(const sdb_import2_args*, cudaStream_t, sdb_profiler*, int*);
+cudaError_t sdb_launch_arena_floor_cur(const sdb_dev_view*, uint32_t, sdb_cursor*, cudaStream_t);
 }
 
 #define SDB_SCAN_TILE 4096u
@@ -67,11 +74,8 @@ struct sdb_ctx {
   sdb_dev_view view{};
   // device buffers
   uint8_t* arena = nullptr;
-  uint64_t* ring_state = nullptr;
-  uint32_t* ring_handle = nullptr;
-  uint16_t* ring_meta = nullptr;
-  uint32_t* ctail = nullptr;
-  uint32_t* ntomb = nullptr;
+  sdb_ring_hdr* ring_hdr = nullptr;
+  uint2* ring = nullptr;
   uint32_t* members = nullptr;
   sdb_dev_counters* ctr = nullptr;
   // staging for non-staged sends
@@ -83,6 +87,8 @@ struct sdb_ctx {
   // inverse group table (agent -> memberships), rebuilt lazily from `ghost`
   uint32_t* memb_off_dev = nullptr; uint32_t* memb_grp_dev = nullptr; uint32_t* memb_pos_dev = nullptr;
   bool memb_dirty = true;
+  uint8_t* gexcl_dev = nullptr;          // [max_groups] 1: every member of the group belongs to that group only
+  uint32_t n_excl_groups = 0, n_shared_agents = 0;
   // sharding (one handle = one shard): owner of each agent, full group lists, local positions
   std::vector<uint8_t> shard_of; bool sharded = false;
   std::vector<std::vector<uint32_t>> gfull;    // full member lists as given by the caller
@@ -99,6 +105,13 @@ struct sdb_ctx {
   sdb_src_tab* xs_tab = nullptr;
   uint8_t* xs_meta = nullptr; uint64_t xs_meta_stride = 0;   // local copies of remote headers + descriptors
   uint8_t* shard_of_dev = nullptr;
+  // asynchronous import: device-resident twin of {arena_tail, arena_floor, next_seq} + one import's placement
+  sdb_cursor* cursor_dev = nullptr; sdb_batch_base* bb_dev = nullptr;
+  sdb_cursor* cursor_host = nullptr;          // pinned
+  bool host_stale = false;                     // the device cursor moved (async import): host counters must be refreshed first
+  bool dev_stale = true;                       // the host counters moved: push them before the next async import
+  uint32_t* xs_gs_off_src = nullptr; uint32_t* xs_gs_idx_src = nullptr; uint32_t* xs_first = nullptr;
+  unsigned long long* xs_lb = nullptr;
   uint8_t* wire_host = nullptr;                // pinned: header + descriptors of an export
   sdb_wire_header* hdrs_host = nullptr;        // pinned [num_shards]
   cudaEvent_t staging_free = nullptr;    // previous H2D of pinned staging has completed
@@ -106,7 +119,7 @@ struct sdb_ctx {
   cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
   // receive scratch + outputs
   uint32_t* rx_agent = nullptr; uint32_t* rx_cnt = nullptr; uint32_t* rx_rec_local = nullptr; uint32_t* rx_rec_tops = nullptr;
-  uint32_t* rx_plan_handle = nullptr; uint32_t* rx_plan_glen = nullptr; uint32_t* rx_plan_local = nullptr;
+  uint4* rx_plan = nullptr; uint32_t* rx_rec_off = nullptr; unsigned long long* rx_lb = nullptr;
   uint32_t* rx_plan_tops = nullptr; unsigned long long* rx_totals = nullptr;
   uint32_t* rx_big_list = nullptr; uint32_t* rx_big_count = nullptr;
   uint32_t* rx_count = nullptr; sdb_msg_header* rx_hdr = nullptr; uint8_t* rx_payload = nullptr;
@@ -161,6 +174,34 @@ inline uint32_t pad32(uint32_t len) { return (len + 31u) & ~31u; }
 
 template <typename T>
 cudaError_t dmalloc(T** p, size_t n) { return cudaMalloc(reinterpret_cast<void**>(p), n * sizeof(T)); }
+
+// The asynchronous import advances arena / sequence counters on the device.  Before host code uses its own copies
+// it pulls the device's (one small D2H + sync), and reports an import the device had to refuse.
+int cursor_to_host(sdb_ctx* h) {
+  if (!h->host_stale) return SDB_OK;
+  CUDA_TRY(h, cudaMemcpyAsync(h->cursor_host, h->cursor_dev, sizeof(sdb_cursor), cudaMemcpyDeviceToHost, h->stream));
+  CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+  h->host_stale = false;
+  h->arena_tail = h->cursor_host->arena_tail; h->next_seq = h->cursor_host->next_seq;
+  if (h->cursor_host->arena_floor > h->arena_floor) h->arena_floor = h->cursor_host->arena_floor;
+  if (h->cursor_host->error) {
+    const unsigned long long err = h->cursor_host->error;
+    CUDA_TRY(h, cudaMemsetAsync(&h->cursor_dev->error, 0, sizeof(unsigned long long), h->stream));
+    if (err & 1ull) return fail(h, SDB_EARENA_FULL, "an asynchronous import did not fit the message arena and was dropped whole "
+                                                    "(unconsumed messages pin the log: receive or enlarge arena_bytes)");
+    if (err & 2ull) return fail(h, SDB_ECAPACITY, "an asynchronous import's owned recipients exceeded list_pool_entries; it was dropped whole");
+    return fail(h, SDB_ECAPACITY, "an asynchronous import carried payloads above 512 bytes (use the synchronous import)");
+  }
+  return SDB_OK;
+}
+int cursor_to_dev(sdb_ctx* h) {
+  if (!h->dev_stale) return SDB_OK;
+  h->cursor_host->arena_tail = h->arena_tail; h->cursor_host->arena_floor = h->arena_floor; h->cursor_host->next_seq = h->next_seq;
+  CUDA_TRY(h, cudaMemcpyAsync(h->cursor_dev, h->cursor_host, 3 * sizeof(unsigned long long), cudaMemcpyHostToDevice, h->stream));
+  CUDA_TRY(h, cudaEventRecord(h->staging_free, h->stream));
+  h->dev_stale = false;
+  return SDB_OK;
+}
 
 // Make room for `need` granules in the arena; may run the floor-reclaim kernel (synchronises).
 int arena_reserve(sdb_ctx* h, uint64_t need, uint64_t* base_out) {
@@ -318,7 +359,22 @@ int rebuild_inverse(sdb_ctx* h) {
     const std::vector<uint32_t>& ms = h->ghost[g];
     for (uint32_t j = 0; j < ms.size(); ++j) { const uint32_t c = cur[ms[j]]++; grp[c] = g; pos[c] = j; }
   }
+  // a group is "exclusive" when each of its members belongs to that group only (and appears in it once): all members
+  // then receive exactly the group's sends and the index build runs group-parallel (k_pull_index_group)
+  std::vector<uint8_t> excl(G, 0);
+  uint32_t n_excl = 0, n_shared = 0;
+  for (uint32_t g = 0; g < G; ++g) if (h->gdefined[g]) {
+    bool ex = true;
+    for (uint32_t m : h->ghost[g]) if (off[m + 1] - off[m] != 1) { ex = false; break; }
+    excl[g] = ex ? 1 : 0; n_excl += ex ? 1 : 0;
+  }
+  for (uint32_t a = 0; a < A; ++a) {
+    const uint32_t nk = off[a + 1] - off[a];
+    if (nk > 1 || (nk == 1 && !excl[grp[off[a]]])) ++n_shared;
+  }
+  h->n_excl_groups = n_excl; h->n_shared_agents = n_shared;
   CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+  CUDA_TRY(h, cudaMemcpy(h->gexcl_dev, excl.data(), G, cudaMemcpyHostToDevice));
   CUDA_TRY(h, cudaMemcpy(h->memb_off_dev, off.data(), off.size() * sizeof(uint32_t), cudaMemcpyHostToDevice));
   if (total) {
     CUDA_TRY(h, cudaMemcpy(h->memb_grp_dev, grp.data(), total * sizeof(uint32_t), cudaMemcpyHostToDevice));
@@ -328,10 +384,24 @@ int rebuild_inverse(sdb_ctx* h) {
   return SDB_OK;
 }
 
+// device copy of the local group table (start, count per group): index build and cross-shard import read it
+int ensure_ltab(sdb_ctx* h) {
+  if (!h->ltab_dirty) return SDB_OK;
+  CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+  std::vector<uint32_t> st(h->cfg.max_groups), ct(h->cfg.max_groups);
+  for (uint32_t g = 0; g < h->cfg.max_groups; ++g) { st[g] = static_cast<uint32_t>(h->gstart[g]); ct[g] = h->gdefined[g] ? h->gcount[g] : 0; }
+  CUDA_TRY(h, cudaMemcpy(h->lstart_dev, st.data(), st.size() * sizeof(uint32_t), cudaMemcpyHostToDevice));
+  CUDA_TRY(h, cudaMemcpy(h->lcount_dev, ct.data(), ct.size() * sizeof(uint32_t), cudaMemcpyHostToDevice));
+  h->ltab_dirty = false;
+  return SDB_OK;
+}
+
 int submit(sdb_ctx* h, const sdb_staged* s, uint64_t* seq_base_out) {
+  { int rcc = cursor_to_host(h); if (rcc != SDB_OK) return rcc; }
   if (seq_base_out) *seq_base_out = h->next_seq;
   if (s->n == 0) return SDB_OK;
   if (s->has_pull && h->memb_dirty) { int rc0 = rebuild_inverse(h); if (rc0 != SDB_OK) return rc0; }
+  if (s->has_pull) { int rc1 = ensure_ltab(h); if (rc1 != SDB_OK) return rc1; }
   uint64_t base = 0;
   int rc = arena_reserve(h, s->total_grans, &base);
   if (rc != SDB_OK) return rc;
@@ -345,40 +415,45 @@ int submit(sdb_ctx* h, const sdb_staged* s, uint64_t* seq_base_out) {
   if (overlap) {
     CUDA_TRY(h, cudaEventRecord(h->ev_fork, h->stream));
     CUDA_TRY(h, cudaStreamWaitEvent(h->side, h->ev_fork, 0));
-    sdb_pull_view pv{h->memb_off_dev, h->memb_grp_dev, h->memb_pos_dev, s->gs_off_dev, s->gs_idx_dev};
-    e = sdb_launch_pull(&h->view, &pv, s->descs_dev, h->n_agents, base, 1, h->side, &h->prof);
+    sdb_pull_view pv{h->memb_off_dev, h->memb_grp_dev, h->memb_pos_dev, s->gs_off_dev, s->gs_idx_dev, 1u, 0u, 0u, nullptr};
+    int nlp = 0;
+    e = sdb_launch_pull(&h->view, &pv, s->descs_dev, h->n_agents, h->cfg.max_groups, h->gexcl_dev, h->n_excl_groups,
+                        h->n_shared_agents, h->lstart_dev, h->lcount_dev, base, 1, h->side, &h->prof, &nlp, nullptr);
     if (e != cudaSuccess) return fail(h, SDB_ECUDA, std::string("index launch: ") + cudaGetErrorString(e));
     CUDA_TRY(h, cudaEventRecord(h->ev_join, h->side));
-    h->launches += 1;
+    h->launches += nlp;
   }
   if (s->kind == 0) {
     e = sdb_launch_p2p(&h->view, s->descs_dev, s->n, s->payload_dev, h->next_seq, base, h->sm_count, h->stream, &h->prof);
   } else {
     e = sdb_launch_fanout(&h->view, s->descs_dev, s->n, s->payload_dev, s->list_dev, h->next_seq, base,
-                          s->max_padlen, static_cast<int>(h->cfg.fanout_variant), h->sm_count, h->stream, &h->prof);
+                          s->max_padlen, static_cast<int>(h->cfg.fanout_variant), h->sm_count, h->stream, &h->prof, nullptr);
   }
   h->launches += 1;
   if (e == cudaSuccess && overlap) {
     CUDA_TRY(h, cudaStreamWaitEvent(h->stream, h->ev_join, 0));
   } else if (e == cudaSuccess && s->has_pull) {
-    sdb_pull_view pv{h->memb_off_dev, h->memb_grp_dev, h->memb_pos_dev, s->gs_off_dev, s->gs_idx_dev};
-    e = sdb_launch_pull(&h->view, &pv, s->descs_dev, h->n_agents, base, s->has_atomic ? 0 : 1, h->stream, &h->prof);
-    h->launches += 1;
+    sdb_pull_view pv{h->memb_off_dev, h->memb_grp_dev, h->memb_pos_dev, s->gs_off_dev, s->gs_idx_dev, 1u, 0u, 0u, nullptr};
+    int nlp = 0;
+    e = sdb_launch_pull(&h->view, &pv, s->descs_dev, h->n_agents, h->cfg.max_groups, h->gexcl_dev, h->n_excl_groups,
+                        h->n_shared_agents, h->lstart_dev, h->lcount_dev, base, s->has_atomic ? 0 : 1, h->stream, &h->prof, &nlp, nullptr);
+    h->launches += nlp;
   }
   if (e == cudaSuccess && s->has_atomic) {
-    e = sdb_launch_commit(&h->view, h->n_agents, static_cast<uint32_t>(base), h->rx_big_list, h->rx_big_count + 1, h->sm_count, h->stream, &h->prof);
+    e = sdb_launch_commit(&h->view, h->n_agents, static_cast<uint32_t>(base), h->rx_big_list, h->rx_big_count + 1, h->sm_count, h->stream, &h->prof, nullptr);
     h->launches += 2;
   }
   if (e != cudaSuccess) return fail(h, SDB_ECUDA, std::string("enqueue launch: ") + cudaGetErrorString(e));
   h->next_seq += s->total_recs;
   h->arena_tail = base + s->total_grans;
+  h->dev_stale = true;
   return SDB_OK;
 }
 
 int send_common(sdb_ctx* h, uint32_t kind, uint32_t n, SendArrays& a, const uint64_t* list_off,
                 const uint32_t* list_idx, const uint8_t* payload, uint64_t payload_bytes, uint64_t* seq_base_out) {
   if (!h) return SDB_EINVAL;
-  if (n == 0) { if (seq_base_out) *seq_base_out = h->next_seq; return SDB_OK; }
+  if (n == 0) { int rcc = cursor_to_host(h); if (seq_base_out) *seq_base_out = h->next_seq; return rcc; }
   if (!a.sender || !a.len || (kind != 2 && !a.second) || (kind == 3 && !a.kind)) return fail(h, SDB_EINVAL, "null array");
   if (n > h->cfg.max_batch_sends) return fail(h, SDB_ECAPACITY, "n exceeds max_batch_sends");
   if (payload_bytes > h->cfg.max_batch_payload) return fail(h, SDB_ECAPACITY, "payload_bytes exceeds max_batch_payload");
@@ -446,7 +521,7 @@ int sdb_create(const sdb_config* cfg, sdb_handle* out) {
   if (c.max_batch_sends == 0) c.max_batch_sends = 65536;
   if (c.max_batch_payload == 0) c.max_batch_payload = static_cast<uint64_t>(c.max_batch_sends) * pad32(std::min(c.max_payload_bytes, 256u));
   if (c.max_recv_records == 0) c.max_recv_records = 1u << 20;
-  if (c.max_recv_records > 0xFFFFFFF0ull) return fail(h, SDB_EINVAL, "max_recv_records too large");
+  if (c.max_recv_records >= 0x7FFFFFF0ull) return fail(h, SDB_EINVAL, "max_recv_records too large (< 2^31)");
   if (c.max_recv_payload == 0) c.max_recv_payload = c.max_recv_records * 256ull;
   if (c.list_pool_entries == 0) c.list_pool_entries = 2ull * c.max_agents + 1024;
   if (c.fanout_variant > 3) return fail(h, SDB_EINVAL, "fanout_variant must be 0, 1, 2 or 3");
@@ -457,6 +532,7 @@ int sdb_create(const sdb_config* cfg, sdb_handle* out) {
   if (c.device < 0 || c.device >= ndev) return fail(h, SDB_EINVAL, "device ordinal out of range");
   CUDA_TRY(h, cudaSetDevice(c.device));
   CUDA_TRY(h, sdb_send_prepare_device());
+  CUDA_TRY(h, sdb_recv_prepare_device());
   cudaDeviceProp prop;
   CUDA_TRY(h, cudaGetDeviceProperties(&prop, c.device));
   h->sm_count = prop.multiProcessorCount;
@@ -470,17 +546,12 @@ int sdb_create(const sdb_config* cfg, sdb_handle* out) {
   const size_t A = c.max_agents, R = c.ring_slots;
   h->arena_grans = c.arena_bytes / SDB_GRANULE;
   CUDA_TRY(h, dmalloc(&h->arena, c.arena_bytes));
-  CUDA_TRY(h, dmalloc(&h->ring_state, A));
-  CUDA_TRY(h, dmalloc(&h->ring_handle, A * R));
-  CUDA_TRY(h, dmalloc(&h->ring_meta, A * R));
-  CUDA_TRY(h, dmalloc(&h->ctail, A));
-  CUDA_TRY(h, dmalloc(&h->ntomb, A));
+  CUDA_TRY(h, dmalloc(&h->ring_hdr, A));
+  CUDA_TRY(h, dmalloc(&h->ring, A * R));
   CUDA_TRY(h, dmalloc(&h->members, c.member_pool_entries));
   CUDA_TRY(h, dmalloc(&h->ctr, 1));
-  CUDA_TRY(h, cudaMemsetAsync(h->ring_state, 0, A * sizeof(uint64_t), h->stream));
-  CUDA_TRY(h, cudaMemsetAsync(h->ring_meta, 0xFF, A * R * sizeof(uint16_t), h->stream));
-  CUDA_TRY(h, cudaMemsetAsync(h->ctail, 0, A * sizeof(uint32_t), h->stream));
-  CUDA_TRY(h, cudaMemsetAsync(h->ntomb, 0, A * sizeof(uint32_t), h->stream));
+  CUDA_TRY(h, cudaMemsetAsync(h->ring_hdr, 0, A * sizeof(sdb_ring_hdr), h->stream));
+  CUDA_TRY(h, cudaMemsetAsync(h->ring, 0xFF, A * R * sizeof(uint2), h->stream));          // every slot "consumed"
   CUDA_TRY(h, cudaMemsetAsync(h->ctr, 0, sizeof(sdb_dev_counters), h->stream));
 
   // send staging
@@ -496,6 +567,8 @@ int sdb_create(const sdb_config* cfg, sdb_handle* out) {
   CUDA_TRY(h, dmalloc(&h->memb_off_dev, static_cast<size_t>(c.max_agents) + 1));
   CUDA_TRY(h, dmalloc(&h->memb_grp_dev, c.member_pool_entries));
   CUDA_TRY(h, dmalloc(&h->memb_pos_dev, c.member_pool_entries));
+  CUDA_TRY(h, dmalloc(&h->gexcl_dev, c.max_groups));
+  CUDA_TRY(h, cudaMemsetAsync(h->gexcl_dev, 0, c.max_groups, h->stream));
   CUDA_TRY(h, cudaMemsetAsync(h->scratch.payload_dev, 0, c.max_batch_payload + 64, h->stream));
 
   // receive scratch
@@ -503,13 +576,15 @@ int sdb_create(const sdb_config* cfg, sdb_handle* out) {
   CUDA_TRY(h, dmalloc(&h->rx_agent, A)); CUDA_TRY(h, dmalloc(&h->rx_cnt, A));
   CUDA_TRY(h, dmalloc(&h->rx_rec_local, A)); CUDA_TRY(h, dmalloc(&h->rx_rec_tops, tiles));
   const size_t rtiles = (c.max_recv_records + SDB_SCAN_TILE - 1) / SDB_SCAN_TILE + 1;
-  CUDA_TRY(h, dmalloc(&h->rx_plan_handle, c.max_recv_records + 4)); CUDA_TRY(h, dmalloc(&h->rx_plan_glen, c.max_recv_records + 4));
-  CUDA_TRY(h, dmalloc(&h->rx_plan_local, c.max_recv_records + 4)); CUDA_TRY(h, dmalloc(&h->rx_plan_tops, rtiles));
+  CUDA_TRY(h, dmalloc(&h->rx_plan, c.max_recv_records + 4)); CUDA_TRY(h, dmalloc(&h->rx_rec_off, A));
+  CUDA_TRY(h, dmalloc(&h->rx_plan_tops, rtiles));
+  CUDA_TRY(h, dmalloc(&h->rx_lb, sdb_lb_words(static_cast<uint32_t>(A / 256 + 2)) + 4));
   CUDA_TRY(h, dmalloc(&h->rx_totals, 8));
   CUDA_TRY(h, dmalloc(&h->rx_big_list, A)); CUDA_TRY(h, dmalloc(&h->rx_big_count, 4));
   CUDA_TRY(h, dmalloc(&h->rx_count, A));
   CUDA_TRY(h, dmalloc(&h->rx_hdr, c.max_recv_records));
   h->pay_cap_gran = (c.max_recv_payload + SDB_GRANULE - 1) / SDB_GRANULE;
+  if (h->pay_cap_gran >= 0x7FFFFFF0ull) return fail(h, SDB_EINVAL, "max_recv_payload too large (< 64 GiB per call)");
   CUDA_TRY(h, dmalloc(&h->rx_payload, h->pay_cap_gran * SDB_GRANULE));
   CUDA_TRY(h, cudaHostAlloc(reinterpret_cast<void**>(&h->totals_host), 8 * sizeof(unsigned long long), cudaHostAllocDefault));
   h->small_bytes = 64 + 1024ull * (32 + pad32(c.max_payload_bytes));
@@ -550,6 +625,12 @@ int sdb_create(const sdb_config* cfg, sdb_handle* out) {
     CUDA_TRY(h, dmalloc(&h->xs_descs, n));
     CUDA_TRY(h, dmalloc(&h->xs_lw, n)); CUDA_TRY(h, dmalloc(&h->xs_lw_local, n)); CUDA_TRY(h, dmalloc(&h->xs_lw_tops, wt));
     CUDA_TRY(h, dmalloc(&h->xs_tab, 1));
+    CUDA_TRY(h, dmalloc(&h->xs_gs_off_src, G1 * c.num_shards)); CUDA_TRY(h, dmalloc(&h->xs_gs_idx_src, n));
+    CUDA_TRY(h, dmalloc(&h->xs_first, SDB_MAX_SRC + 1)); CUDA_TRY(h, dmalloc(&h->xs_lb, sdb_lb_words(static_cast<uint32_t>(n / 256 + 2)) + 4));
+    CUDA_TRY(h, dmalloc(&h->cursor_dev, 1)); CUDA_TRY(h, dmalloc(&h->bb_dev, 1));
+    CUDA_TRY(h, cudaMemset(h->cursor_dev, 0, sizeof(sdb_cursor))); CUDA_TRY(h, cudaMemset(h->bb_dev, 0, sizeof(sdb_batch_base)));
+    CUDA_TRY(h, cudaHostAlloc(reinterpret_cast<void**>(&h->cursor_host), sizeof(sdb_cursor), cudaHostAllocDefault));
+    std::memset(h->cursor_host, 0, sizeof(sdb_cursor));
     h->xs_meta_stride = wire_meta_bytes(c.max_batch_sends, c.max_groups);
     CUDA_TRY(h, dmalloc(&h->xs_meta, h->xs_meta_stride * c.num_shards));
     CUDA_TRY(h, dmalloc(&h->shard_of_dev, c.max_agents));
@@ -559,8 +640,7 @@ int sdb_create(const sdb_config* cfg, sdb_handle* out) {
   }
 
   sdb_dev_view& v = h->view;
-  v.arena = h->arena; v.ring_state = h->ring_state; v.ring_handle = h->ring_handle; v.ring_meta = h->ring_meta;
-  v.ctail = h->ctail; v.ntomb = h->ntomb; v.members = h->members; v.member_pos = h->member_pos_dev; v.ctr = h->ctr;
+  v.arena = h->arena; v.ring_hdr = h->ring_hdr; v.ring = h->ring; v.members = h->members; v.member_pos = h->member_pos_dev; v.ctr = h->ctr;
   v.gmask = h->arena_grans - 1; v.ring_slots = c.ring_slots; v.ring_shift = ilog2(c.ring_slots); v.max_agents = c.max_agents;
   CUDA_TRY(h, cudaStreamSynchronize(h->stream));
   return SDB_OK;
@@ -570,13 +650,14 @@ int sdb_destroy(sdb_handle h) {
   if (!h) return SDB_EINVAL;
   cudaSetDevice(h->cfg.device);
   if (h->stream) cudaStreamSynchronize(h->stream);
-  void* dev[] = {h->arena, h->ring_state, h->ring_handle, h->ring_meta, h->ctail, h->ntomb, h->members, h->ctr,
+  void* dev[] = {h->arena, h->ring_hdr, h->ring, h->members, h->ctr, h->gexcl_dev, h->rx_rec_off, h->rx_lb,
+                 h->xs_gs_off_src, h->xs_gs_idx_src, h->xs_first, h->xs_lb, h->cursor_dev, h->bb_dev,
                  h->scratch.descs_dev, h->scratch.payload_dev, h->scratch.list_dev, h->scratch.gs_off_dev,
                  h->scratch.gs_idx_dev, h->memb_off_dev, h->memb_grp_dev, h->memb_pos_dev, h->member_pos_dev,
                  h->lstart_dev, h->lcount_dev, h->xs_w, h->xs_w_local, h->xs_w_tops, h->xs_gs_cnt, h->xs_gs_local,
                  h->xs_gs_tops, h->xs_gs_cur, h->xs_gs_off, h->xs_gs_idx, h->xs_descs, h->xs_lw, h->xs_lw_local,
                  h->xs_lw_tops, h->xs_tab, h->xs_meta, h->shard_of_dev, h->rx_agent, h->rx_cnt,
-                 h->rx_rec_local, h->rx_rec_tops, h->rx_plan_handle, h->rx_plan_glen, h->rx_plan_local, h->rx_plan_tops,
+                 h->rx_rec_local, h->rx_rec_tops, h->rx_plan, h->rx_plan_tops,
                  h->rx_totals, h->rx_big_list, h->rx_big_count, h->rx_count, h->rx_hdr, h->rx_payload,
                  h->be_weight, h->be_load, h->be_scratch, h->be_logtab, h->be_req_cost, h->be_out, h->digest};
   for (void* p : dev) if (p) cudaFree(p);
@@ -585,6 +666,7 @@ int sdb_destroy(sdb_handle h) {
   if (h->gs_host) cudaFreeHost(h->gs_host);
   if (h->wire_host) cudaFreeHost(h->wire_host);
   if (h->hdrs_host) cudaFreeHost(h->hdrs_host);
+  if (h->cursor_host) cudaFreeHost(h->cursor_host);
   if (h->totals_host) cudaFreeHost(h->totals_host);
   if (h->small_host) cudaFreeHost(h->small_host);
   if (h->rx_small) cudaFree(h->rx_small);
@@ -645,6 +727,7 @@ int sdb_profile_read(sdb_handle h, double* ms_out, uint64_t* count_out) {
 
 int sdb_get_stats(sdb_handle h, sdb_stats* out) {
   if (!h || !out) return SDB_EINVAL;
+  { int rcc = cursor_to_host(h); if (rcc != SDB_OK) return rcc; }
   sdb_dev_counters c;
   CUDA_TRY(h, cudaMemcpyAsync(&c, h->ctr, sizeof(c), cudaMemcpyDeviceToHost, h->stream));
   CUDA_TRY(h, cudaStreamSynchronize(h->stream));
@@ -662,12 +745,14 @@ int sdb_debug_set_arena_pos(sdb_handle h, uint64_t granules) {
   if (rc != SDB_OK) return rc;
   if (st.enqueued != st.delivered + 0 && st.enqueued - st.delivered != 0) return fail(h, SDB_EINVAL, "messages pending");
   h->arena_tail = granules; h->arena_floor = granules;
+  h->dev_stale = true;
   return SDB_OK;
 }
 
 int sdb_advance_seq(sdb_handle h, uint64_t next_seq) {
   if (!h) return SDB_EINVAL;
-  if (next_seq > h->next_seq) h->next_seq = next_seq;
+  { int rcc = cursor_to_host(h); if (rcc != SDB_OK) return rcc; }
+  if (next_seq > h->next_seq) { h->next_seq = next_seq; h->dev_stale = true; }
   return SDB_OK;
 }
 
@@ -745,7 +830,8 @@ int sdb_create_group(sdb_handle h, uint32_t g, uint32_t n_members, const uint32_
 uint64_t sdb_wire_bytes(sdb_handle h, uint32_t max_sends, uint64_t max_payload_bytes) {
   // header + descriptors + group buckets + payload (+ slack); broadcast recipient lists count towards max_payload_bytes
   const uint32_t G = h ? h->cfg.max_groups : 0;
-  return wire_meta_bytes(max_sends, G) + ((max_payload_bytes + 256 + 127) & ~127ull);
+  // ... + the cross-rank control block (sdb_wire_ctrl) in the last 128 bytes, outside everything an export writes
+  return wire_meta_bytes(max_sends, G) + ((max_payload_bytes + 256 + 127) & ~127ull) + sizeof(sdb_wire_ctrl);
 }
 
 int sdb_set_agent_shards(sdb_handle h, uint32_t n, const uint8_t* shard_of) {
@@ -783,7 +869,7 @@ static int export_common(sdb_ctx* h, uint32_t n, const uint32_t* sender, const u
   const uint64_t gsi_off = gso_off + (static_cast<uint64_t>(G) + 1) * 4;
   const uint64_t l_off = gsi_off + static_cast<uint64_t>(n) * 4;            // room for every send being a group send
   const uint64_t pay_off = (l_off + n_list * sizeof(uint32_t) + 63) & ~63ull;
-  if (pay_off + payload_bytes + 64 > wire_cap) return fail(h, SDB_ECAPACITY, "wire buffer too small (sdb_wire_bytes)");
+  if (pay_off + payload_bytes + 64 + sizeof(sdb_wire_ctrl) > wire_cap) return fail(h, SDB_ECAPACITY, "wire buffer too small (sdb_wire_bytes)");
   CUDA_TRY(h, cudaEventSynchronize(h->staging_free));
   sdb_wire_header* wh = reinterpret_cast<sdb_wire_header*>(h->wire_host);
   sdb_send_desc* wd = reinterpret_cast<sdb_send_desc*>(h->wire_host + desc_off);
@@ -913,16 +999,10 @@ int sdb_import_wire_batches(sdb_handle h, uint32_t n_src, const void* wire_dev_a
 
 int sdb_import_wire_ptrs(sdb_handle h, uint32_t n_src, const void* const* wire_ptrs, uint64_t* seq_base_out) {
   if (!h || !wire_ptrs || n_src == 0) return SDB_EINVAL;
+  { int rcc = cursor_to_host(h); if (rcc != SDB_OK) return rcc; }
   if (seq_base_out) *seq_base_out = h->next_seq;
   if (n_src > h->cfg.num_shards || n_src > SDB_MAX_SRC) return fail(h, SDB_EINVAL, "n_src > num_shards (or > 16)");
-  if (h->ltab_dirty) {      // device copy of the local group table (start, count per group)
-    CUDA_TRY(h, cudaStreamSynchronize(h->stream));
-    std::vector<uint32_t> st(h->cfg.max_groups), ct(h->cfg.max_groups);
-    for (uint32_t g = 0; g < h->cfg.max_groups; ++g) { st[g] = static_cast<uint32_t>(h->gstart[g]); ct[g] = h->gdefined[g] ? h->gcount[g] : 0; }
-    CUDA_TRY(h, cudaMemcpy(h->lstart_dev, st.data(), st.size() * sizeof(uint32_t), cudaMemcpyHostToDevice));
-    CUDA_TRY(h, cudaMemcpy(h->lcount_dev, ct.data(), ct.size() * sizeof(uint32_t), cudaMemcpyHostToDevice));
-    h->ltab_dirty = false;
-  }
+  { int rc1 = ensure_ltab(h); if (rc1 != SDB_OK) return rc1; }
   if (h->memb_dirty) { int rc0 = rebuild_inverse(h); if (rc0 != SDB_OK) return rc0; }
   const uint32_t n_cap = n_src * h->cfg.max_batch_sends;
   sdb_import_args a{};
@@ -975,27 +1055,111 @@ int sdb_import_wire_ptrs(sdb_handle h, uint32_t n_src, const void* const* wire_p
   if (e == cudaSuccess && overlap) {
     CUDA_TRY(h, cudaEventRecord(h->ev_fork, h->stream));
     CUDA_TRY(h, cudaStreamWaitEvent(h->side, h->ev_fork, 0));
-    sdb_pull_view pv{h->memb_off_dev, h->memb_grp_dev, h->memb_pos_dev, h->xs_gs_off, h->xs_gs_idx};
-    e = sdb_launch_pull(&h->view, &pv, h->xs_descs, h->n_agents, base, 1, h->side, &h->prof);
+    sdb_pull_view pv{h->memb_off_dev, h->memb_grp_dev, h->memb_pos_dev, h->xs_gs_off, h->xs_gs_idx, 1u, 0u, 0u, nullptr};
+    e = sdb_launch_pull(&h->view, &pv, h->xs_descs, h->n_agents, h->cfg.max_groups, h->gexcl_dev, h->n_excl_groups,
+                        h->n_shared_agents, h->lstart_dev, h->lcount_dev, base, 1, h->side, &h->prof, &nl, nullptr);
     if (e == cudaSuccess) CUDA_TRY(h, cudaEventRecord(h->ev_join, h->side));
   }
   if (e == cudaSuccess)
     e = sdb_launch_fanout(&h->view, h->xs_descs, n_cap, nullptr, h->scratch.list_dev, h->next_seq, base, max_padlen,
-                          h->cfg.fanout_variant >= 2 ? 3 : static_cast<int>(h->cfg.fanout_variant), h->sm_count, h->stream, &h->prof);
+                          h->cfg.fanout_variant >= 2 ? 3 : static_cast<int>(h->cfg.fanout_variant), h->sm_count, h->stream, &h->prof, nullptr);
   if (e == cudaSuccess && overlap) {
     CUDA_TRY(h, cudaStreamWaitEvent(h->stream, h->ev_join, 0));
   } else if (e == cudaSuccess) {
-    sdb_pull_view pv{h->memb_off_dev, h->memb_grp_dev, h->memb_pos_dev, h->xs_gs_off, h->xs_gs_idx};
-    e = sdb_launch_pull(&h->view, &pv, h->xs_descs, h->n_agents, base, n_other ? 0 : 1, h->stream, &h->prof);
+    sdb_pull_view pv{h->memb_off_dev, h->memb_grp_dev, h->memb_pos_dev, h->xs_gs_off, h->xs_gs_idx, 1u, 0u, 0u, nullptr};
+    e = sdb_launch_pull(&h->view, &pv, h->xs_descs, h->n_agents, h->cfg.max_groups, h->gexcl_dev, h->n_excl_groups,
+                        h->n_shared_agents, h->lstart_dev, h->lcount_dev, base, n_other ? 0 : 1, h->stream, &h->prof, &nl, nullptr);
   }
   if (e == cudaSuccess && n_other) {     // p2p / broadcast copies claimed their slots with atomics: sort them into place
-    e = sdb_launch_commit(&h->view, h->n_agents, static_cast<uint32_t>(base), h->rx_big_list, h->rx_big_count + 1, h->sm_count, h->stream, &h->prof);
+    e = sdb_launch_commit(&h->view, h->n_agents, static_cast<uint32_t>(base), h->rx_big_list, h->rx_big_count + 1, h->sm_count, h->stream, &h->prof, nullptr);
     h->launches += 2;
   }
-  h->launches += nl + 2;
+  h->launches += nl + 1;
   if (e != cudaSuccess) return fail(h, SDB_ECUDA, std::string("import launch: ") + cudaGetErrorString(e));
   h->next_seq = std::max<uint64_t>(h->next_seq + (explicit_end ? 0 : total_recs), explicit_end);
   h->arena_tail = base + total_grans;
+  h->dev_stale = true;
+  return SDB_OK;
+}
+
+// ---- flags + asynchronous import -------------------------------------------------------------------------------
+static uint32_t* ctrl_word(const void* wire, uint64_t wire_bytes, int which) {
+  uint8_t* c = static_cast<uint8_t*>(const_cast<void*>(wire)) + wire_bytes - sizeof(sdb_wire_ctrl);
+  return reinterpret_cast<uint32_t*>(c) + which;           // 0 = ready, 1 = done
+}
+
+int sdb_wire_publish(sdb_handle h, void* wire_dev, uint64_t wire_bytes, uint32_t step) {
+  if (!h || !wire_dev || wire_bytes < sizeof(sdb_wire_ctrl)) return SDB_EINVAL;
+  CUDA_TRY(h, sdb_launch_wire_set(ctrl_word(wire_dev, wire_bytes, 0), step, h->stream));
+  h->launches += 1;
+  return SDB_OK;
+}
+
+int sdb_wire_wait_done(sdb_handle h, uint32_t n_src, const void* const* wire_ptrs, uint64_t wire_bytes, uint32_t step) {
+  if (!h || !wire_ptrs || n_src == 0 || n_src > SDB_MAX_SRC || wire_bytes < sizeof(sdb_wire_ctrl)) return SDB_EINVAL;
+  const uint32_t* flags[SDB_MAX_SRC];
+  for (uint32_t k = 0; k < n_src; ++k) flags[k] = ctrl_word(wire_ptrs[k], wire_bytes, 1);
+  CUDA_TRY(h, sdb_launch_wire_wait(flags, n_src, step, h->stream));
+  h->launches += 1;
+  return SDB_OK;
+}
+
+int sdb_import_wire_ptrs_async(sdb_handle h, uint32_t n_src, const void* const* wire_ptrs, uint64_t wire_bytes, uint32_t step) {
+  if (!h || !wire_ptrs || n_src == 0 || wire_bytes < sizeof(sdb_wire_ctrl)) return SDB_EINVAL;
+  if (n_src > h->cfg.num_shards || n_src > SDB_MAX_SRC) return fail(h, SDB_EINVAL, "n_src > num_shards (or > 16)");
+  for (uint32_t k = 0; k < n_src; ++k) if (!wire_ptrs[k]) return fail(h, SDB_EINVAL, "null wire pointer");
+  { int rc1 = ensure_ltab(h); if (rc1 != SDB_OK) return rc1; }
+  if (h->memb_dirty) { int rc0 = rebuild_inverse(h); if (rc0 != SDB_OK) return rc0; }
+  // 1. wait (on the stream, not on the host) until every source's export of this step is complete
+  const uint32_t* ready[SDB_MAX_SRC];
+  for (uint32_t k = 0; k < n_src; ++k) ready[k] = ctrl_word(wire_ptrs[k], wire_bytes, 0);
+  const int pw = sdb_prof_begin(&h->prof, SDB_PK_XWAIT, h->stream);
+  CUDA_TRY(h, sdb_launch_wire_wait(ready, n_src, step, h->stream));
+  sdb_prof_end(&h->prof, pw, h->stream);
+  h->launches += 1;
+  uint32_t* my_done = ctrl_word(wire_ptrs[h->cfg.shard_id < n_src ? h->cfg.shard_id : 0], wire_bytes, 1);
+  const bool fast = pad32(h->cfg.max_payload_bytes) <= 512 && h->n_shared_agents == 0 && h->n_excl_groups != 0 &&
+                    h->cfg.fanout_variant >= 2;
+  if (!fast) {
+    // general traffic shapes (payloads above 512 bytes, agents in several groups): the synchronous import body
+    int rc = sdb_import_wire_ptrs(h, n_src, wire_ptrs, nullptr);
+    if (rc != SDB_OK) return rc;
+    CUDA_TRY(h, sdb_launch_wire_set(my_done, step, h->stream));
+    h->launches += 1;
+    return SDB_OK;
+  }
+  // 2. everything else happens on the device
+  { int rc2 = cursor_to_dev(h); if (rc2 != SDB_OK) return rc2; }
+  CUDA_TRY(h, sdb_launch_arena_floor_cur(&h->view, h->n_agents, h->cursor_dev, h->stream));
+  sdb_import2_args a{};
+  for (uint32_t k = 0; k < n_src; ++k) a.wire[k] = static_cast<const uint8_t*>(wire_ptrs[k]);
+  a.n_src = n_src; a.max_sends = h->cfg.max_batch_sends; a.max_groups = h->cfg.max_groups; a.shard_id = h->cfg.shard_id;
+  a.max_agents = h->cfg.max_agents; a.lcount = h->lcount_dev; a.lstart = h->lstart_dev; a.shard_of = h->shard_of_dev;
+  a.descs = h->xs_descs; a.gs_off_src = h->xs_gs_off_src; a.gs_idx_src = h->xs_gs_idx_src; a.first = h->xs_first;
+  a.tmp_list = h->scratch.list_dev; a.list_cap = static_cast<uint32_t>(std::min<uint64_t>(h->cfg.list_pool_entries, 0x7FFFFFF0ull));
+  a.lb = h->xs_lb; a.cur = h->cursor_dev; a.bb = h->bb_dev; a.arena_grans = h->arena_grans;
+  int nl = 1;
+  cudaError_t e = sdb_launch_import_fused(&a, h->stream, &h->prof, &nl);
+  const uint32_t n_cap = n_src * h->cfg.max_batch_sends;
+  if (e == cudaSuccess)
+    e = sdb_launch_fanout(&h->view, h->xs_descs, n_cap, nullptr, h->scratch.list_dev, 0, 0, pad32(h->cfg.max_payload_bytes), 3,
+                          h->sm_count, h->stream, &h->prof, h->bb_dev);
+  if (e == cudaSuccess) {
+    sdb_pull_view pv{h->memb_off_dev, h->memb_grp_dev, h->memb_pos_dev, h->xs_gs_off_src, h->xs_gs_idx_src, n_src,
+                     h->cfg.max_groups + 1, h->cfg.max_batch_sends, h->xs_first};
+    e = sdb_launch_pull(&h->view, &pv, h->xs_descs, h->n_agents, h->cfg.max_groups, h->gexcl_dev, h->n_excl_groups, 0,
+                        h->lstart_dev, h->lcount_dev, 0, 0, h->stream, &h->prof, &nl, h->bb_dev);
+  }
+  // point-to-point / broadcast copies claimed their slots with atomics: sort them into place (the kernels return at
+  // once when the import carried none); the group-parallel build leaves ctail to the commit
+  if (e == cudaSuccess)
+    e = sdb_launch_commit(&h->view, h->n_agents, 0, h->rx_big_list, h->rx_big_count + 1, h->sm_count, h->stream, &h->prof, h->bb_dev);
+  h->launches += nl + 3;
+  if (e != cudaSuccess) return fail(h, SDB_ECUDA, std::string("async import launch: ") + cudaGetErrorString(e));
+  h->host_stale = true;
+  // 3. tell the exporters that this rank is done reading their buffers of this parity
+  CUDA_TRY(h, sdb_launch_wire_set(my_done, step, h->stream));
+  h->launches += 1;
   return SDB_OK;
 }
 
@@ -1109,7 +1273,7 @@ int sdb_receive_batch(sdb_handle h, uint32_t n_agents, const uint32_t* agent_idx
     if (rec_cap == 0) return fail(h, SDB_EOUTPUT, "output buffers cannot hold a single maximum-size record");
     h->last_rx_valid = false;
     cudaError_t e = sdb_launch_receive_small(&h->view, agent_idx, n_agents, max_messages, flags, static_cast<uint32_t>(rec_cap),
-                                             h->rx_plan_handle, h->rx_plan_glen, h->rx_small, h->stream, &h->prof);
+                                             h->rx_plan, h->rx_small, h->stream, &h->prof);
     h->launches += 1;
     if (e != cudaSuccess) return fail(h, SDB_ECUDA, std::string("receive launch: ") + cudaGetErrorString(e));
     const uint64_t window = std::min<uint64_t>(h->small_bytes, 16384);
@@ -1144,7 +1308,7 @@ int sdb_receive_batch(sdb_handle h, uint32_t n_agents, const uint32_t* agent_idx
   r.agent_idx = agent_idx ? h->rx_agent : nullptr; r.n = n_agents; r.max_messages = max_messages;
   r.flags = flags & (SDB_RECV_PRIORITY | SDB_RECV_PEEK);
   r.cnt = h->rx_cnt; r.rec_local = h->rx_rec_local; r.rec_tops = h->rx_rec_tops;
-  r.plan_handle = h->rx_plan_handle; r.plan_glen = h->rx_plan_glen; r.plan_local = h->rx_plan_local;
+  r.rec_off = h->rx_rec_off; r.plan = h->rx_plan; r.lb = h->rx_lb;
   r.plan_tops = h->rx_plan_tops; r.totals = h->rx_totals; r.big_list = h->rx_big_list; r.big_count = h->rx_big_count;
   r.count_out = h->rx_count; r.hdr_out = h->rx_hdr; r.payload_out = h->rx_payload;
   // record capacity: bounded so that even maximum-size payloads fit the payload buffers
@@ -1155,8 +1319,9 @@ int sdb_receive_batch(sdb_handle h, uint32_t n_agents, const uint32_t* agent_idx
   if (rec_cap == 0) return fail(h, SDB_EOUTPUT, "output buffers cannot hold a single maximum-size record");
   r.rec_cap = rec_cap;
   int nl = 0;
-  cudaError_t e = sdb_launch_receive(&h->view, &r, h->stream, &nl, &h->prof, h->sm_count);
+  cudaError_t e = sdb_launch_receive(&h->view, &r, h->stream, &nl, &h->prof, h->sm_count, 32u + pad32(h->cfg.max_payload_bytes));
   h->launches += nl;
+  if (!(r.flags & SDB_RECV_PRIORITY)) r.plan_tops = nullptr;       // single-pass path: plan offsets are absolute
   h->last_rx = r; h->last_rx_valid = (e == cudaSuccess);
   if (e != cudaSuccess) return fail(h, SDB_ECUDA, std::string("receive launch: ") + cudaGetErrorString(e));
   if (async) return SDB_OK;          // the caller consumes on the device (stream order) or asks sdb_last_receive_totals later

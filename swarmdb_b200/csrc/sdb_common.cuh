@@ -8,13 +8,15 @@
 //                                         position `apos` (granules, monotonic u64);
 //                                         byte address = arena + ((apos & gmask) << 5);
 //                                         a batch never straddles the wrap point.
-//   ring_state   uint64 [max_agents]      {tail:hi32, head:lo32} monotonic per-agent cursors.
-//                                         ONE 64-bit atomicAdd(1<<32) claims a slot and
-//                                         returns head in the same L2 transaction.
-//   ring_handle  uint32 [max_agents][R]   (uint32)apos of each pending record
-//   ring_meta    uint16 [max_agents][R]   prio<<14 | record_granules ; 0xFFFF = consumed
-//   ctail        uint32 [max_agents]      tail as of the last commit (published prefix)
-//   ntomb        uint32 [max_agents]      consumed entries still inside [head, tail)
+//   ring_hdr     16 B   [max_agents]      {head, tail, ctail, ntomb}: monotonic per-agent cursors, ONE 16-byte
+//                                         load per agent for every kernel.  {head, tail} is also one aligned 64-bit
+//                                         word: an atomicAdd(1<<32) on it claims a slot and returns head in the
+//                                         same L2 transaction (enqueue paths that are not rank-ordered).
+//                                         ctail = tail as of the last commit; ntomb = consumed entries still
+//                                         inside [head, tail) (holes left by priority receives).
+//   ring         8 B    [max_agents][R]   one entry per pending record: {handle = (uint32)apos,
+//                                         meta = prio<<14 | record_granules, 0xFFFF = consumed}.  Interleaved so
+//                                         the few entries an agent gains/loses per batch share one 32-byte sector.
 //   members      uint32 [member_pool]     group member lists (CSR kept on the host)
 //
 // Ordering contract: after `commit`, every ring is sorted by handle, i.e. by arena
@@ -97,8 +99,12 @@ struct sdb_pull_view {
   const uint32_t* memb_off;   // [max_agents + 1]
   const uint32_t* memb_grp;   // [memberships]
   const uint32_t* memb_pos;   // [memberships] position of the agent inside that group's member list
-  const uint32_t* gs_off;     // [max_groups + 1] bucket offsets into gs_idx
-  const uint32_t* gs_idx;     // [group sends of the batch] send indices, ascending inside a bucket
+  const uint32_t* gs_off;     // [n_src][gs_off_stride] bucket offsets into gs_idx, one table per source
+  const uint32_t* gs_idx;     // [n_src][gs_idx_stride] send indices (relative to the source's first send), ascending inside a bucket
+  // The group-parallel index build walks the sources' buckets in source order (= global send order), so a
+  // cross-shard import never concatenates them.  One source (n_src = 1, first[0] = 0) is the single-GPU case.
+  uint32_t n_src, gs_off_stride, gs_idx_stride;
+  const uint32_t* first;      // [n_src] global descriptor index of each source's first send (device), or nullptr = {0}
 };
 
 struct sdb_dev_counters {   // device-resident, updated with atomics
@@ -111,13 +117,13 @@ struct sdb_dev_counters {   // device-resident, updated with atomics
 };
 
 // everything a kernel needs about the shard, passed by value
+struct __align__(16) sdb_ring_hdr { uint32_t head, tail, ctail, ntomb; };
+static_assert(sizeof(sdb_ring_hdr) == 16, "ring header must be 16 bytes");
+
 struct sdb_dev_view {
   uint8_t*  arena;
-  uint64_t* ring_state;
-  uint32_t* ring_handle;
-  uint16_t* ring_meta;
-  uint32_t* ctail;
-  uint32_t* ntomb;
+  sdb_ring_hdr* ring_hdr;       // [max_agents]
+  uint2*    ring;               // [max_agents][R]  .x = handle, .y = meta (SDB_META_TOMB: consumed)
   const uint32_t* members;
   const uint32_t* member_pos;   // sharded mode: original group position of members[k]; else nullptr
   sdb_dev_counters* ctr;
@@ -133,23 +139,55 @@ struct sdb_recv_args {
   uint32_t n;
   uint32_t max_messages;
   uint32_t flags;
-  uint32_t* cnt;               // [n] records selected per agent
-  uint32_t* rec_local;         // [n] scan of cnt (block-local part)
-  uint32_t* rec_tops;          // [tiles] scan of cnt (per-block part)
-  // per-record plan, indexed by output record number r = rec_off[agent] + rank
-  uint32_t* plan_handle;       // [rec_cap] arena handle of record r
-  uint32_t* plan_glen;         // [rec_cap] payload granules of record r
-  uint32_t* plan_local;        // [rec_cap] scan of plan_glen (block-local part)
-  uint32_t* plan_tops;         // [rec tiles]
-  unsigned long long* totals;  // [0] records delivered, [1] payload granules delivered
+  uint32_t* cnt;               // [n] records selected per agent                 (multi-kernel path scratch)
+  uint32_t* rec_local;         // [n] scan of cnt (block-local part)             (multi-kernel path scratch)
+  uint32_t* rec_tops;          // [tiles] scan of cnt (per-block part)           (multi-kernel path scratch)
+  uint32_t* rec_off;           // [n] index of the agent's first output record (both paths)
+  // per-record plan, indexed by output record number r = rec_off[slot] + rank:
+  //   .x arena handle, .y payload offset in the packed output (granules; the multi-kernel path stores the
+  //   tile-local part and adds plan_tops[r / tile]), .z payload granules, .w request slot
+  uint4* plan;                 // [rec_cap]
+  uint32_t* plan_tops;         // [rec tiles] or nullptr (single-pass path: .y is already absolute)
+  unsigned long long* totals;  // [0] records delivered, [1] payload granules delivered, [2..] scratch
   uint32_t* big_list;          // [n] request slots that need the warp-per-agent selector
   uint32_t* big_count;         // [1]
+  unsigned long long* lb;      // [tiles + 2] single-pass path: decoupled look-back status words (zero between calls),
+                               //             then the tile ticket counter and the packed totals (see k_recv_plan)
   // outputs
   uint32_t* count_out;         // [n]
   sdb_msg_header* hdr_out;     // [rec_cap]
   uint8_t* payload_out;        // [rec_cap * pad32(max_payload)]
   uint64_t rec_cap;
 };
+
+// ---- asynchronous import (sdb_import_wire_ptrs_async): everything the host used to learn through a sync lives on
+// the device.  `sdb_cursor` is the device-resident twin of the host's arena / sequence counters (whoever advanced
+// them last marks the other side stale); `sdb_batch_base` carries one import's placement from the kernel that
+// computes it (k_import_fused) to the kernels that follow (fan-out, index build, commit).
+struct sdb_cursor {
+  unsigned long long arena_tail;    // granules, monotonic
+  unsigned long long arena_floor;   // granules: everything below is reclaimed
+  unsigned long long next_seq;
+  unsigned long long error;         // sticky bits: 1 = an import did not fit the arena (dropped whole), 2 = recipient-list pool exhausted
+  unsigned long long floor_dist;    // scratch of the floor scan: max distance of a pending record below the tail
+  unsigned long long pad[3];
+};
+struct sdb_batch_base {
+  unsigned long long arena_base;    // granule position of the import's first record
+  unsigned long long seq_base;      // sequence number the import's relative numbers count from
+  uint32_t n_total;                 // localized descriptors (sends) of the import
+  uint32_t n_other;                 // point-to-point / broadcast sends among them (their ring entries need the commit sort)
+  uint32_t skip;                    // 1: refused (see sdb_cursor.error) - the following kernels do nothing
+  uint32_t max_padlen;
+  unsigned long long total_grans, total_recs;
+};
+// cross-rank flags of an export buffer (last 128 bytes of the buffer, never touched by an export's copies)
+struct sdb_wire_ctrl {
+  uint32_t ready;                   // last step whose export into this buffer is complete (written by the owner)
+  uint32_t done;                    // last step for which the OWNER, as an importer, finished reading every rank's buffer of this parity
+  uint32_t pad[30];
+};
+static_assert(sizeof(sdb_wire_ctrl) == 128, "wire ctrl block must be 128 bytes");
 
 // arguments of one cross-shard import (sdb_xshard.cu)
 #define SDB_MAX_SRC 16
@@ -190,6 +228,22 @@ struct sdb_import_args {
   uint32_t list_cap;
 };
 
+// arguments of the asynchronous import's fused kernel (sdb_xshard.cu: k_import_fused)
+struct sdb_import2_args {
+  const uint8_t* wire[SDB_MAX_SRC];   // one wire batch per source rank; may point into PEER GPU memory (NVLink)
+  uint32_t n_src, max_sends, max_groups, shard_id, max_agents;
+  const uint32_t* lcount; const uint32_t* lstart;
+  const uint8_t* shard_of;
+  sdb_send_desc* descs;               // out [n_src * max_sends]
+  uint32_t* gs_off_src;               // out [n_src][max_groups + 1]
+  uint32_t* gs_idx_src;               // out [n_src][max_sends]
+  uint32_t* first;                    // out [SDB_MAX_SRC + 1]
+  uint32_t* tmp_list; uint32_t list_cap;
+  unsigned long long* lb;             // [tiles + 2]: look-back status words, tile ticket (zeroed before the launch)
+  sdb_cursor* cur; sdb_batch_base* bb;
+  unsigned long long arena_grans;
+};
+
 // ---- optional per-kernel timing with CUDA events on the launching stream (bench / roofline) ----
 struct sdb_profiler {
   int enabled;
@@ -218,15 +272,18 @@ __device__ __forceinline__ uint8_t* sdb_arena_ptr(const sdb_dev_view& v, uint64_
 // Claim the next slot of agent a's ring and publish (handle, meta) into it.
 // Returns false when the ring is full (nothing is written; the commit kernel clamps tail).
 __device__ __forceinline__ bool sdb_ring_append(const sdb_dev_view& v, uint32_t a, uint32_t handle, uint16_t meta) {
-  unsigned long long old = atomicAdd(reinterpret_cast<unsigned long long*>(v.ring_state + a), 1ull << 32);
+  unsigned long long old = atomicAdd(reinterpret_cast<unsigned long long*>(v.ring_hdr + a), 1ull << 32);
   uint32_t e = static_cast<uint32_t>(old >> 32);
   uint32_t head = static_cast<uint32_t>(old);
   if (e - head >= v.ring_slots) return false;
   size_t slot = (static_cast<size_t>(a) << v.ring_shift) + (e & (v.ring_slots - 1));
-  v.ring_handle[slot] = handle;
-  v.ring_meta[slot] = meta;
+  v.ring[slot] = make_uint2(handle, meta);
   return true;
 }
+__device__ __forceinline__ uint2* sdb_ring_of(const sdb_dev_view& v, uint32_t a) {
+  return v.ring + (static_cast<size_t>(a) << v.ring_shift);
+}
+__device__ __forceinline__ uint32_t sdb_meta(const uint2& e) { return e.y & 0xFFFFu; }
 
 __device__ __forceinline__ uint4 sdb_header_lo(uint64_t seq, double ts) {
   uint4 r;
@@ -366,6 +423,110 @@ __device__ __forceinline__ void sdb_tma_wait_read() {
 template <int N>
 __device__ __forceinline__ void sdb_tma_wait_all() {
   asm volatile("cp.async.bulk.wait_group %0;" :: "n"(N) : "memory");
+}
+
+// ---- hierarchical decoupled look-back over pairs (a, b) of 31-bit-saturating sums ------------------------------------
+// Single-pass kernels (k_recv_plan, k_import_fused) need, per tile, the exclusive prefix of a pair over all earlier
+// tiles.  A flat look-back chain advances 32 tiles per L2 round trip, which for thousands of small tiles IS the
+// kernel's duration; wider windows drown the L2 in polling.  Two levels instead:
+//   * every tile publishes its aggregate at once (no dependency) and bumps its super-tile's counter (32 tiles each);
+//   * the tile that completes a super-tile (its "finalizer") sums the 32 aggregates, publishes the super-tile
+//     aggregate, looks back over SUPER-TILE words only (tiles / 32 of them: a handful of hops), and publishes the
+//     super-tile's exclusive prefix;
+//   * a tile's prefix = its super-tile's exclusive prefix + the aggregates of the earlier tiles of its super-tile.
+// Words: [63:62] status, [61:31] a, [30:0] b (saturating: a saturated prefix lies beyond every capacity check).
+// Layout of the scratch array `lb` (zeroed before the launch), T tiles, S = ceil(T / 32) super-tiles:
+//   [0, T) tile aggregates | [T, T+S) super-tile status | [T+S, T+2S) super-tile exclusive prefix | [T+2S, T+3S) counters
+//   | [T+3S] tile ticket | [T+3S+1] kernel-specific
+// Tiles must be numbered by an atomic ticket (a tile's predecessors are then running or done).  Call with warp 0.
+__device__ __forceinline__ unsigned long long sdb_lb_pack(uint32_t st, unsigned long long a, unsigned long long b) {
+  const unsigned long long SAT = 0x7FFFFFFFull;
+  return (static_cast<unsigned long long>(st) << 62) | ((a < SAT ? a : SAT) << 31) | (b < SAT ? b : SAT);
+}
+__device__ __forceinline__ unsigned long long sdb_lb_ld(const unsigned long long* p) {
+  unsigned long long x;
+  asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(x) : "l"(p) : "memory");
+  return x;
+}
+__device__ __forceinline__ void sdb_lb_st(unsigned long long* p, unsigned long long x) {
+  asm volatile("st.release.gpu.global.u64 [%0], %1;" :: "l"(p), "l"(x) : "memory");
+}
+__host__ __device__ static inline size_t sdb_lb_words(uint32_t tiles) { return static_cast<size_t>(tiles) + 3 * ((tiles + 31) / 32) + 2; }
+
+// ta/tb: this tile's aggregate.  Returns the exclusive prefix in ea/eb (every lane).  *is_last tells the caller's lane 0
+// whether this tile saw the grand total (ga/gb) - exactly one tile does.
+__device__ __forceinline__ void sdb_lb_prefix(unsigned long long* lb, uint32_t tile, uint32_t tiles, unsigned long long ta,
+                                              unsigned long long tb, uint32_t lane, unsigned long long& ea, unsigned long long& eb,
+                                              bool& is_last, unsigned long long& ga, unsigned long long& gb) {
+  const unsigned long long SAT = 0x7FFFFFFFull;
+  const uint32_t S = (tiles + 31) / 32;
+  unsigned long long* agg = lb;
+  unsigned long long* sst = lb + tiles;
+  unsigned long long* sex = lb + tiles + S;
+  unsigned int* scnt = reinterpret_cast<unsigned int*>(lb + tiles + 2 * static_cast<size_t>(S));   // one 64-bit slot per counter
+  const uint32_t st = tile >> 5, ti = tile & 31u;
+  const uint32_t first = st << 5;
+  const uint32_t msize = min(32u, tiles - first);
+  is_last = false; ga = 0; gb = 0;
+  uint32_t finalizer = 0;
+  if (lane == 0) {
+    sdb_lb_st(agg + tile, sdb_lb_pack(1u, ta, tb));
+    __threadfence();
+    finalizer = atomicAdd(scnt + 2 * st, 1u) == msize - 1 ? 1u : 0u;
+  }
+  finalizer = __shfl_sync(0xFFFFFFFFu, finalizer, 0);
+  if (finalizer) {
+    __threadfence();
+    // every member has published: sum the super-tile
+    const unsigned long long w = lane < msize ? sdb_lb_ld(agg + first + lane) : 0ull;
+    unsigned long long sa = (w >> 31) & SAT, sb = w & SAT;
+    for (int o = 16; o; o >>= 1) { sa += __shfl_xor_sync(0xFFFFFFFFu, sa, o); sb += __shfl_xor_sync(0xFFFFFFFFu, sb, o); }
+    unsigned long long xa = 0, xb = 0;
+    if (st == 0) {
+      if (lane == 0) sdb_lb_st(sst, sdb_lb_pack(2u, sa, sb));
+    } else {
+      if (lane == 0) sdb_lb_st(sst + st, sdb_lb_pack(1u, sa, sb));
+      int32_t idx = static_cast<int32_t>(st) - 1 - static_cast<int32_t>(lane);
+      for (;;) {
+        unsigned long long w2; uint32_t dm, upto;
+        for (;;) {
+          w2 = idx >= 0 ? sdb_lb_ld(sst + idx) : sdb_lb_pack(2u, 0, 0);
+          const uint32_t s2 = static_cast<uint32_t>(w2 >> 62);
+          dm = __ballot_sync(0xFFFFFFFFu, s2 == 2u);
+          const uint32_t zm = __ballot_sync(0xFFFFFFFFu, s2 == 0u);
+          upto = dm ? static_cast<uint32_t>(__ffs(dm)) : 32u;
+          const uint32_t need = upto >= 32u ? 0xFFFFFFFFu : ((1u << upto) - 1u);
+          if ((zm & need) == 0) break;
+          __nanosleep(40);
+        }
+        unsigned long long va = lane < upto ? ((w2 >> 31) & SAT) : 0ull, vb = lane < upto ? (w2 & SAT) : 0ull;
+        for (int o = 16; o; o >>= 1) { va += __shfl_xor_sync(0xFFFFFFFFu, va, o); vb += __shfl_xor_sync(0xFFFFFFFFu, vb, o); }
+        xa += va; xb += vb;
+        if (dm) break;
+        idx -= 32;
+      }
+      __threadfence();
+      if (lane == 0) sdb_lb_st(sst + st, sdb_lb_pack(2u, xa + sa, xb + sb));
+    }
+    if (lane == 0) sdb_lb_st(sex + st, sdb_lb_pack(1u, xa, xb));
+    if (st == S - 1) { is_last = true; ga = xa + sa; gb = xb + sb; }
+  }
+  // every tile: super-tile prefix + earlier tiles of the super-tile
+  unsigned long long pw = 0;
+  for (;;) {
+    const unsigned long long w = lane < ti ? sdb_lb_ld(agg + first + lane) : sdb_lb_pack(1u, 0, 0);
+    if (lane == 0) pw = sdb_lb_ld(sex + st);
+    const bool missing = (w >> 62) == 0 || (lane == 0 && (pw >> 62) == 0);
+    if (!__any_sync(0xFFFFFFFFu, missing)) {
+      unsigned long long va = (w >> 31) & SAT, vb = w & SAT;
+      if (lane == 0) { va += (pw >> 31) & SAT; vb += pw & SAT; }
+      for (int o = 16; o; o >>= 1) { va += __shfl_xor_sync(0xFFFFFFFFu, va, o); vb += __shfl_xor_sync(0xFFFFFFFFu, vb, o); }
+      ea = va; eb = vb;
+      break;
+    }
+    __nanosleep(40);
+  }
+  __threadfence();
 }
 
 #endif  // __CUDACC__

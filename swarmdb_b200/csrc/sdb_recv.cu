@@ -2,7 +2,15 @@
 // loop M:553-601 and its filter M:579-585 are replaced by per-agent rings that only ever
 // hold records addressed to that agent).
 //
-// Pipeline of one sdb_receive_batch call (all stream-ordered, no host round trip inside):
+// Stream order (the reference's behaviour) takes the SINGLE-PASS path: k_recv_plan + k_recv_gather.
+//   k_recv_plan     one thread per requested agent: one 16-byte ring-header load, the agent's entries (8 bytes
+//                   each, one sector for the usual handful), then ONE decoupled look-back over 256-agent tiles
+//                   carrying {records, payload granules} together gives every record its output index and
+//                   payload offset; the per-record plan is written, heads advance.  No separate count / scan /
+//                   select / scan kernels and no second read of the ring.
+//   k_recv_gather   flat over records: copy header + payload from the arena to the packed output
+// Priority order (extension, SURVEY App. A rule 9) keeps the multi-kernel pipeline (all stream-ordered, no host
+// round trip inside):
 //   k_recv_count    cnt[q]   = min(max_messages, live(agent q))
 //   scan            rec_off  = exclusive scan of cnt             (k_scan_local + k_scan_tops)
 //   k_recv_select   per agent: choose WHICH pending entries are delivered, write the per-record
@@ -19,6 +27,7 @@
 //
 // Roofline: HBM-bound.  Algorithmic bytes per agent-call: P*1 priority bytes scanned (we scan
 // 2-byte ring_meta entries) + 2*k*(L+H) gather+emit.
+#include <cstdlib>
 #include "sdb_common.cuh"
 
 #define SDB_SCAN_TILE 4096u   // elements per scan block (1024 threads x 4)
@@ -132,9 +141,8 @@ k_recv_count(sdb_dev_view v, sdb_recv_args r) {
   const uint32_t a = r.agent_idx ? r.agent_idx[q] : q;
   uint32_t c = 0;
   if (a < v.max_agents) {
-    const uint64_t st = v.ring_state[a];
-    const uint32_t live = static_cast<uint32_t>(st >> 32) - static_cast<uint32_t>(st) - v.ntomb[a];
-    c = min(live, r.max_messages);
+    const uint4 h = *reinterpret_cast<const uint4*>(v.ring_hdr + a);      // head, tail, ctail, ntomb
+    c = min(h.y - h.x - h.w, r.max_messages);
   }
   r.cnt[q] = c;
 }
@@ -152,124 +160,114 @@ __device__ __forceinline__ uint32_t lane_prefix(uint32_t ballot, uint32_t lane) 
 }
 
 // one agent, whole warp: choose the C entries to deliver from the window [H, T), write their plan at
-// output index RO.., retire them (advance head / tombstone).  Stream order when !prio_mode.
-__device__ __forceinline__ void select_agent_warp(const sdb_dev_view& v, uint32_t* plan_handle, uint32_t* plan_glen,
+// output index RO.., retire them (advance head / tombstone).  Stream order when !prio_mode.  The plan's payload
+// offsets (.y) are filled later (record-level scan / fill_offsets_warp).
+__device__ __forceinline__ void select_agent_warp(const sdb_dev_view& v, uint4* plan, uint32_t slot,
                                                   bool prio_mode, uint32_t A, uint32_t H, uint32_t T, uint32_t NT,
                                                   uint32_t C, uint32_t RO, uint32_t lane, bool retire) {
   const uint32_t mask = v.ring_slots - 1;
-    uint16_t* ms = v.ring_meta + (static_cast<size_t>(A) << v.ring_shift);
-    const uint32_t* hs = v.ring_handle + (static_cast<size_t>(A) << v.ring_shift);
+  uint2* rs = sdb_ring_of(v, A);
 
-    if (!prio_mode && NT == 0) {
-      // long contiguous run [H, H+C)
-      for (uint32_t j = lane; j < C; j += 32) {
-        plan_handle[RO + j] = hs[(H + j) & mask];
-        plan_glen[RO + j] = (ms[(H + j) & mask] & SDB_META_GLEN_MASK) - 1u;
-      }
-      if (lane == 0 && retire) reinterpret_cast<uint32_t*>(v.ring_state + A)[0] = H + C;
-      return;
+  if (!prio_mode && NT == 0) {
+    // long contiguous run [H, H+C)
+    for (uint32_t j = lane; j < C; j += 32) {
+      const uint2 e = rs[(H + j) & mask];
+      plan[RO + j] = make_uint4(e.x, 0u, (sdb_meta(e) & SDB_META_GLEN_MASK) - 1u, slot);
     }
-    // ---- pass 1: histogram of live entries per priority level over the window [H, T)
-    uint32_t h0 = 0, h1 = 0, h2 = 0, h3 = 0;
-    if (prio_mode) {
-      if (v.ring_slots >= 8) {
-        // 8 metas (16 bytes) per lane per load, 4 independent loads in flight per lane (1024 entries per
-        // warp step), aligned groups of the circular window
-        for (uint32_t b8 = (H & ~7u) + (lane << 3); static_cast<int32_t>(T - b8) > 0; b8 += 1024) {
-          uint4 q[4];
+    if (lane == 0 && retire) v.ring_hdr[A].head = H + C;
+    return;
+  }
+  // ---- pass 1: histogram of live entries per priority level over the window [H, T)
+  uint32_t h0 = 0, h1 = 0, h2 = 0, h3 = 0;
+  if (prio_mode) {
+    // 2 entries (16 bytes) per lane per load, 4 independent loads in flight per lane (256 entries per warp
+    // step), aligned pairs of the circular window
+    for (uint32_t b2 = (H & ~1u) + (lane << 1); static_cast<int32_t>(T - b2) > 0; b2 += 256) {
+      uint4 q[4];
 #pragma unroll
-          for (int u = 0; u < 4; ++u) {
-            const uint32_t p8 = b8 + u * 256;
-            q[u] = static_cast<int32_t>(T - p8) > 0 ? *reinterpret_cast<const uint4*>(ms + (p8 & mask)) : make_uint4(~0u, ~0u, ~0u, ~0u);
-          }
+      for (int u = 0; u < 4; ++u) {
+        const uint32_t p2 = b2 + u * 64;
+        q[u] = static_cast<int32_t>(T - p2) > 0 ? *reinterpret_cast<const uint4*>(rs + (p2 & mask)) : make_uint4(0u, ~0u, 0u, ~0u);
+      }
 #pragma unroll
-          for (int u = 0; u < 4; ++u) {
-            const uint32_t p8 = b8 + u * 256;
-            const uint32_t w[4] = {q[u].x, q[u].y, q[u].z, q[u].w};
+      for (int u = 0; u < 4; ++u) {
+        const uint32_t p2 = b2 + u * 64;
 #pragma unroll
-            for (int k = 0; k < 8; ++k) {
-              const uint32_t p = p8 + k;
-              const uint32_t m = (w[k >> 1] >> ((k & 1) * 16)) & 0xFFFFu;
-              if (static_cast<int32_t>(p - H) >= 0 && static_cast<int32_t>(T - p) > 0 && m != SDB_META_TOMB) {
-                const uint32_t L = m >> 14;
-                h0 += (L == 0); h1 += (L == 1); h2 += (L == 2); h3 += (L == 3);
-              }
-            }
+        for (int k = 0; k < 2; ++k) {
+          const uint32_t p = p2 + k;
+          const uint32_t m = (k ? q[u].w : q[u].y) & 0xFFFFu;
+          if (static_cast<int32_t>(p - H) >= 0 && static_cast<int32_t>(T - p) > 0 && m != SDB_META_TOMB) {
+            const uint32_t L = m >> 14;
+            h0 += (L == 0); h1 += (L == 1); h2 += (L == 2); h3 += (L == 3);
           }
         }
-      } else {
-        for (uint32_t p = H + lane; static_cast<int32_t>(T - p) > 0; p += 32) {
-          const uint16_t m = ms[p & mask];
-          if (m == SDB_META_TOMB) continue;
-          const uint32_t L = m >> 14;
-          h0 += (L == 0); h1 += (L == 1); h2 += (L == 2); h3 += (L == 3);
-        }
-      }
-      unsigned long long lo = (static_cast<unsigned long long>(h1) << 32) | h0;
-      unsigned long long hi = (static_cast<unsigned long long>(h3) << 32) | h2;
-      for (int o = 16; o; o >>= 1) {
-        lo += __shfl_xor_sync(0xFFFFFFFFu, lo, o);
-        hi += __shfl_xor_sync(0xFFFFFFFFu, hi, o);
-      }
-      h0 = static_cast<uint32_t>(lo); h1 = static_cast<uint32_t>(lo >> 32);
-      h2 = static_cast<uint32_t>(hi); h3 = static_cast<uint32_t>(hi >> 32);
-    } else {
-      h0 = (T - H) - NT;     // single level: every live entry
-    }
-    // ---- cut: take every entry of the levels above the cut, and the first `quota` of the cut level
-    uint32_t hist[4] = {h0, h1, h2, h3};
-    uint32_t quota[4] = {0, 0, 0, 0}, basek[4] = {0, 0, 0, 0};
-    {
-      uint32_t need = C, acc = 0;
-      for (int L = 3; L >= 0; --L) {
-        const uint32_t take = min(hist[L], need);
-        quota[L] = take; basek[L] = acc; acc += take; need -= take;
       }
     }
-    // ---- pass 2: stable compaction of the selected positions, window order within a level
-    uint32_t taken[4] = {0, 0, 0, 0};
-    uint32_t first_unsel = T;      // first live entry left behind
-    uint32_t got = 0;
-    uint32_t p0 = H;
-    for (; static_cast<int32_t>(T - p0) > 0 && got < C; p0 += 32) {
-      const uint32_t p = p0 + lane;
-      const bool in = static_cast<int32_t>(T - p) > 0;
-      const uint16_t m = in ? ms[p & mask] : SDB_META_TOMB;
-      const bool live = m != SDB_META_TOMB;
-      const uint32_t L = (live && prio_mode) ? (m >> 14) : 0u;
-      bool sel = false; uint32_t rank = 0;
+    unsigned long long lo = (static_cast<unsigned long long>(h1) << 32) | h0;
+    unsigned long long hi = (static_cast<unsigned long long>(h3) << 32) | h2;
+    for (int o = 16; o; o >>= 1) {
+      lo += __shfl_xor_sync(0xFFFFFFFFu, lo, o);
+      hi += __shfl_xor_sync(0xFFFFFFFFu, hi, o);
+    }
+    h0 = static_cast<uint32_t>(lo); h1 = static_cast<uint32_t>(lo >> 32);
+    h2 = static_cast<uint32_t>(hi); h3 = static_cast<uint32_t>(hi >> 32);
+  } else {
+    h0 = (T - H) - NT;     // single level: every live entry
+  }
+  // ---- cut: take every entry of the levels above the cut, and the first `quota` of the cut level
+  uint32_t hist[4] = {h0, h1, h2, h3};
+  uint32_t quota[4] = {0, 0, 0, 0}, basek[4] = {0, 0, 0, 0};
+  {
+    uint32_t need = C, acc = 0;
+    for (int L = 3; L >= 0; --L) {
+      const uint32_t take = min(hist[L], need);
+      quota[L] = take; basek[L] = acc; acc += take; need -= take;
+    }
+  }
+  // ---- pass 2: stable compaction of the selected positions, window order within a level
+  uint32_t taken[4] = {0, 0, 0, 0};
+  uint32_t first_unsel = T;      // first live entry left behind
+  uint32_t got = 0;
+  uint32_t p0 = H;
+  for (; static_cast<int32_t>(T - p0) > 0 && got < C; p0 += 32) {
+    const uint32_t p = p0 + lane;
+    const bool in = static_cast<int32_t>(T - p) > 0;
+    const uint2 e = in ? rs[p & mask] : make_uint2(0u, SDB_META_TOMB);
+    const uint32_t m = sdb_meta(e);
+    const bool live = m != SDB_META_TOMB;
+    const uint32_t L = (live && prio_mode) ? (m >> 14) : 0u;
+    bool sel = false; uint32_t rank = 0;
 #pragma unroll
-      for (uint32_t lev = 0; lev < 4; ++lev) {
-        const uint32_t b = __ballot_sync(0xFFFFFFFFu, live && L == lev);
-        if (live && L == lev) {
-          const uint32_t k = taken[lev] + lane_prefix(b, lane);
-          if (k < quota[lev]) { sel = true; rank = basek[lev] + k; }
-        }
-        taken[lev] += __popc(b);
+    for (uint32_t lev = 0; lev < 4; ++lev) {
+      const uint32_t b = __ballot_sync(0xFFFFFFFFu, live && L == lev);
+      if (live && L == lev) {
+        const uint32_t k = taken[lev] + lane_prefix(b, lane);
+        if (k < quota[lev]) { sel = true; rank = basek[lev] + k; }
       }
-      if (sel) {
-        plan_handle[RO + rank] = hs[p & mask];
-        plan_glen[RO + rank] = (m & SDB_META_GLEN_MASK) - 1u;
-        if (retire) ms[p & mask] = SDB_META_TOMB;
-      }
-      const uint32_t bs = __ballot_sync(0xFFFFFFFFu, sel);
-      got += __popc(bs);
-      const uint32_t bu = __ballot_sync(0xFFFFFFFFu, live && !sel);
-      if (bu && first_unsel == T) first_unsel = p0 + (__ffs(bu) - 1);
+      taken[lev] += __popc(b);
     }
-    const uint32_t scan_end = static_cast<int32_t>(T - p0) > 0 ? p0 : T;
-    uint32_t nh = first_unsel;
-    if (static_cast<int32_t>(nh - scan_end) > 0) nh = scan_end;
-    if (lane == 0 && retire) {
-      reinterpret_cast<uint32_t*>(v.ring_state + A)[0] = nh;
-      v.ntomb[A] = NT + got - (nh - H);
+    if (sel) {
+      plan[RO + rank] = make_uint4(e.x, 0u, (m & SDB_META_GLEN_MASK) - 1u, slot);
+      if (retire) rs[p & mask].y = SDB_META_TOMB;
     }
+    const uint32_t bs = __ballot_sync(0xFFFFFFFFu, sel);
+    got += __popc(bs);
+    const uint32_t bu = __ballot_sync(0xFFFFFFFFu, live && !sel);
+    if (bu && first_unsel == T) first_unsel = p0 + (__ffs(bu) - 1);
+  }
+  const uint32_t scan_end = static_cast<int32_t>(T - p0) > 0 ? p0 : T;
+  uint32_t nh = first_unsel;
+  if (static_cast<int32_t>(nh - scan_end) > 0) nh = scan_end;
+  if (lane == 0 && retire) {
+    v.ring_hdr[A].head = nh;
+    v.ring_hdr[A].ntomb = NT + got - (nh - H);
+  }
 }
 
 __global__ void __launch_bounds__(256)
 k_recv_select(sdb_dev_view v, sdb_recv_args r) {
-  // one lane per requested agent: short contiguous runs (the common drain case) are planned and
-  // retired here; everything else is queued for k_recv_select_big (one warp per agent)
+  // one lane per requested agent: short contiguous runs are planned and retired here; everything else is
+  // queued for k_recv_select_big (one warp per agent)
   const uint32_t lane = threadIdx.x & 31;
   const uint32_t q = blockIdx.x * blockDim.x + threadIdx.x;
   const bool valid = q < r.n;
@@ -285,9 +283,10 @@ k_recv_select(sdb_dev_view v, sdb_recv_args r) {
       cnt = 0;
     }
     r.count_out[q] = cnt;
+    r.rec_off[q] = roff;
     if (cnt) {
-      head = static_cast<uint32_t>(v.ring_state[a]);
-      nt = v.ntomb[a];
+      const uint4 h = *reinterpret_cast<const uint4*>(v.ring_hdr + a);
+      head = h.x; nt = h.w;
     }
   }
   const bool prio_mode = (r.flags & SDB_RECV_PRIORITY) != 0;
@@ -295,18 +294,18 @@ k_recv_select(sdb_dev_view v, sdb_recv_args r) {
   const bool small = valid && cnt && !prio_mode && nt == 0 && cnt <= SMALL;
   if (small) {
     const uint64_t pol = sdb_policy_evict_last();
-    const uint16_t* ms = v.ring_meta + (static_cast<size_t>(a) << v.ring_shift);
-    const uint32_t* hs = v.ring_handle + (static_cast<size_t>(a) << v.ring_shift);
+    const uint2* rs = sdb_ring_of(v, a);
     for (uint32_t b = 0; b < cnt; b += CH) {
-      uint32_t hv[CH]; uint16_t mv[CH];
+      uint64_t ev[CH];
 #pragma unroll
       for (uint32_t j = 0; j < CH; ++j)       // all loads of the chunk first, then the stores
-        if (b + j < cnt) { hv[j] = sdb_ld_u32_pol(hs + ((head + b + j) & mask), pol); mv[j] = sdb_ld_u16_pol(ms + ((head + b + j) & mask), pol); }
+        if (b + j < cnt) ev[j] = sdb_ld_u64_pol(reinterpret_cast<const uint64_t*>(rs + ((head + b + j) & mask)), pol);
 #pragma unroll
       for (uint32_t j = 0; j < CH; ++j)
-        if (b + j < cnt) { r.plan_handle[roff + b + j] = hv[j]; r.plan_glen[roff + b + j] = (mv[j] & SDB_META_GLEN_MASK) - 1u; }
+        if (b + j < cnt)
+          r.plan[roff + b + j] = make_uint4(static_cast<uint32_t>(ev[j]), 0u, (static_cast<uint32_t>(ev[j] >> 32) & SDB_META_GLEN_MASK) - 1u, q);
     }
-    if (!(r.flags & SDB_RECV_PEEK)) reinterpret_cast<uint32_t*>(v.ring_state + a)[0] = head + cnt;    // low word = head (little endian)
+    if (!(r.flags & SDB_RECV_PEEK)) v.ring_hdr[a].head = head + cnt;
   }
   // everything else (long runs, holes, priority order) goes to the warp-per-agent kernel
   const bool big = valid && cnt && !small;
@@ -327,29 +326,28 @@ k_recv_select(sdb_dev_view v, sdb_recv_args r) {
 // ballot-prefix ranks) in shared memory; stop as soon as the top level alone fills the quota -
 // with mixed priorities that happens after a few hundred entries instead of the whole window.
 #define SDB_CAND 128u
-__device__ __forceinline__ void select_agent_warp_bounded(const sdb_dev_view& v, uint32_t* plan_handle, uint32_t* plan_glen,
+__device__ __forceinline__ void select_agent_warp_bounded(const sdb_dev_view& v, uint4* plan, uint32_t slot,
                                                           bool prio_mode, uint32_t A, uint32_t H, uint32_t T, uint32_t NT,
                                                           uint32_t C, uint32_t RO, uint32_t lane, bool retire,
                                                           uint32_t (*cand)[SDB_CAND]) {
   const uint32_t mask = v.ring_slots - 1;
-  uint16_t* ms = v.ring_meta + (static_cast<size_t>(A) << v.ring_shift);
-  const uint32_t* hs = v.ring_handle + (static_cast<size_t>(A) << v.ring_shift);
+  uint2* rs = sdb_ring_of(v, A);
   const uint32_t top = prio_mode ? 3u : 0u;
   uint32_t cnt[4] = {0, 0, 0, 0};
   uint32_t p0 = H;
   while (static_cast<int32_t>(T - p0) > 0 && cnt[top] < C) {
     // four chunks of 32 entries in flight per step (the loads do not depend on the running counts)
-    uint16_t mm[4];
+    uint32_t mm[4];
 #pragma unroll
     for (uint32_t u = 0; u < 4; ++u) {
       const uint32_t p = p0 + u * 32u + lane;
-      mm[u] = static_cast<int32_t>(T - p) > 0 ? ms[p & mask] : SDB_META_TOMB;
+      mm[u] = static_cast<int32_t>(T - p) > 0 ? (rs[p & mask].y & 0xFFFFu) : SDB_META_TOMB;
     }
 #pragma unroll
     for (uint32_t u = 0; u < 4; ++u) {
       if (static_cast<int32_t>(T - p0) <= 0 || cnt[top] >= C) break;       // warp-uniform
       const uint32_t p = p0 + lane;
-      const uint16_t m = mm[u];
+      const uint32_t m = mm[u];
       const bool live = m != SDB_META_TOMB;
       const uint32_t L = (live && prio_mode) ? (m >> 14) : 0u;
 #pragma unroll
@@ -373,9 +371,9 @@ __device__ __forceinline__ void select_agent_warp_bounded(const sdb_dev_view& v,
     const uint32_t take = min(have, need);
     for (uint32_t k = lane; k < take; k += 32) {
       const uint32_t p = cand[lev][k];
-      plan_handle[RO + acc + k] = hs[p & mask];
-      plan_glen[RO + acc + k] = (ms[p & mask] & SDB_META_GLEN_MASK) - 1u;
-      if (retire) ms[p & mask] = SDB_META_TOMB;
+      const uint2 e = rs[p & mask];
+      plan[RO + acc + k] = make_uint4(e.x, 0u, (sdb_meta(e) & SDB_META_GLEN_MASK) - 1u, slot);
+      if (retire) rs[p & mask].y = SDB_META_TOMB;
     }
     acc += take; need -= take; got += take;
   }
@@ -385,13 +383,13 @@ __device__ __forceinline__ void select_agent_warp_bounded(const sdb_dev_view& v,
   uint32_t nh = scan_end;
   for (uint32_t q0 = H; static_cast<int32_t>(scan_end - q0) > 0; q0 += 32) {
     const uint32_t p = q0 + lane;
-    const bool live = static_cast<int32_t>(scan_end - p) > 0 && ms[p & mask] != SDB_META_TOMB;
+    const bool live = static_cast<int32_t>(scan_end - p) > 0 && (rs[p & mask].y & 0xFFFFu) != SDB_META_TOMB;
     const uint32_t b = __ballot_sync(0xFFFFFFFFu, live);
     if (b) { nh = q0 + (__ffs(b) - 1); break; }
   }
   if (lane == 0) {
-    reinterpret_cast<uint32_t*>(v.ring_state + A)[0] = nh;
-    v.ntomb[A] = NT + got - (nh - H);
+    v.ring_hdr[A].head = nh;
+    v.ring_hdr[A].ntomb = NT + got - (nh - H);
   }
 }
 
@@ -410,34 +408,28 @@ k_recv_select_big(sdb_dev_view v, sdb_recv_args r) {
     const uint32_t a = r.agent_idx ? r.agent_idx[q] : q;
     const uint32_t cnt = r.count_out[q];
     const uint32_t roff = r.rec_local[q] + r.rec_tops[q / SDB_SCAN_TILE];
-    const uint64_t st = v.ring_state[a];
-    const uint32_t H = static_cast<uint32_t>(st), T = static_cast<uint32_t>(st >> 32), NT = v.ntomb[a];
+    const uint4 hd = *reinterpret_cast<const uint4*>(v.ring_hdr + a);
+    const uint32_t H = hd.x, T = hd.y, NT = hd.w;
     if (cnt <= SDB_CAND && (prio_mode || NT != 0))
-      select_agent_warp_bounded(v, r.plan_handle, r.plan_glen, prio_mode, a, H, T, NT, cnt, roff, lane, retire,
-                                s_cand[threadIdx.x >> 5]);
+      select_agent_warp_bounded(v, r.plan, q, prio_mode, a, H, T, NT, cnt, roff, lane, retire, s_cand[threadIdx.x >> 5]);
     else
-      select_agent_warp(v, r.plan_handle, r.plan_glen, prio_mode, a, H, T, NT, cnt, roff, lane, retire);
+      select_agent_warp(v, r.plan, q, prio_mode, a, H, T, NT, cnt, roff, lane, retire);
     __syncwarp();
   }
 }
 
-// scan over the per-record payload sizes; the element count lives on the device (totals[0])
+// scan over the per-record payload sizes (plan[].z) of the multi-kernel path; the tile-local exclusive prefix is
+// stored back into plan[].y and the per-tile totals into `tops`.  The element count lives on the device (totals[0]).
 __global__ void __launch_bounds__(1024)
-k_scan_plan(const uint32_t* __restrict__ in, uint32_t* __restrict__ local, uint32_t* __restrict__ tops,
-            const unsigned long long* __restrict__ n_dev) {
+k_scan_plan(uint4* __restrict__ plan, uint32_t* __restrict__ tops, const unsigned long long* __restrict__ n_dev) {
   __shared__ uint32_t s_warp[32];
   const uint32_t n = static_cast<uint32_t>(*n_dev);
   const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const uint32_t base = blockIdx.x * SDB_SCAN_TILE + tid * 4u;
   if (blockIdx.x * SDB_SCAN_TILE >= n) { if (tid == 0) tops[blockIdx.x] = 0; return; }
   uint32_t x[4];
-  if (base + 3 < n) {
-    const uint4 q = *reinterpret_cast<const uint4*>(in + base);
-    x[0] = q.x; x[1] = q.y; x[2] = q.z; x[3] = q.w;
-  } else {
 #pragma unroll
-    for (int k = 0; k < 4; ++k) x[k] = (base + k < n) ? in[base + k] : 0u;
-  }
+  for (int k = 0; k < 4; ++k) x[k] = (base + k < n) ? plan[base + k].z : 0u;
   const uint32_t tsum = x[0] + x[1] + x[2] + x[3];
   uint32_t incl = tsum;
 #pragma unroll
@@ -460,46 +452,303 @@ k_scan_plan(const uint32_t* __restrict__ in, uint32_t* __restrict__ local, uint3
   }
   __syncthreads();
   uint32_t run = s_warp[warp] + incl - tsum;
-  uint4 o4; o4.x = run; o4.y = run + x[0]; o4.z = o4.y + x[1]; o4.w = o4.z + x[2];
-  if (base + 3 < n) *reinterpret_cast<uint4*>(local + base) = o4;
-  else {
-    if (base < n) local[base] = o4.x;
-    if (base + 1 < n) local[base + 1] = o4.y;
-    if (base + 2 < n) local[base + 2] = o4.z;
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    if (base + k < n) plan[base + k].y = run;
+    run += x[k];
   }
+}
+
+// ------------------------------------------------------------------------------------------
+// SINGLE-PASS receive plan for stream order (the reference's order): count + both scans + select + retire in one
+// kernel.  One thread per request slot, 256 slots per tile, tiles ordered by an atomic ticket; one hierarchical
+// decoupled look-back (sdb_common.cuh: sdb_lb_prefix) carries {records, payload granules} as a 31+31-bit pair, so a
+// record's output index and its payload offset come out of the same pass.
+// Agents whose window holds consumed entries (holes left by earlier priority receives) are walked by their warp.
+// Capacity: an agent whose records would run past rec_cap is left untouched together with every agent after it
+// (whole-agent truncation, nothing is ever lost); the totals are lowered with an atomic min on the packed pair.
+//   r.lb               look-back scratch (layout in sdb_common.cuh, zeroed by the launcher), then the tile ticket, then
+//                      ~(records << 32 | granules) of the call, maintained with atomicMax (= min of the value)
+// ------------------------------------------------------------------------------------------
+#define SDB_PLAN_TILE 256u                      // request slots per tile (one per thread)
+#define SDB_PLAN_STAGE 256u                     // plan entries staged per warp before a coalesced write
+// sum of the payload granules of the first C live entries of the window [H, T), whole warp
+__device__ __forceinline__ uint32_t holey_sum_warp(const uint2* rs, uint32_t mask, uint32_t H, uint32_t T, uint32_t C, uint32_t lane) {
+  uint32_t taken = 0, sum = 0;
+  for (uint32_t p0 = H; static_cast<int32_t>(T - p0) > 0 && taken < C; p0 += 32) {
+    const uint32_t p = p0 + lane;
+    const uint32_t m = static_cast<int32_t>(T - p) > 0 ? (rs[p & mask].y & 0xFFFFu) : SDB_META_TOMB;
+    const bool live = m != SDB_META_TOMB;
+    const uint32_t b = __ballot_sync(0xFFFFFFFFu, live);
+    if (live && taken + lane_prefix(b, lane) < C) sum += (m & SDB_META_GLEN_MASK) - 1u;
+    taken += __popc(b);
+  }
+  for (int o = 16; o; o >>= 1) sum += __shfl_xor_sync(0xFFFFFFFFu, sum, o);
+  return sum;
+}
+// payload offsets of C freshly planned records [RO, RO + C): running sum of .z from g0, whole warp
+__device__ __forceinline__ void fill_offsets_warp(uint4* plan, uint32_t RO, uint32_t C, uint32_t g0, uint32_t lane) {
+  uint32_t run = g0;
+  for (uint32_t j0 = 0; j0 < C; j0 += 32) {
+    const uint32_t j = j0 + lane;
+    const uint32_t g = j < C ? plan[RO + j].z : 0u;
+    uint32_t incl = g;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { const uint32_t y = __shfl_up_sync(0xFFFFFFFFu, incl, o); if (lane >= o) incl += y; }
+    if (j < C) plan[RO + j].y = run + incl - g;
+    run += __shfl_sync(0xFFFFFFFFu, incl, 31);
+  }
+}
+
+__global__ void __launch_bounds__(256)
+k_recv_plan(sdb_dev_view v, sdb_recv_args r, uint32_t tiles) {
+  __shared__ uint32_t s_tile;
+  __shared__ unsigned long long s_wr[8], s_wg[8];
+  __shared__ unsigned long long s_br, s_bg;
+  __shared__ uint4 s_stage[8][SDB_PLAN_STAGE];                // per warp: plan entries on their way out (32 KB)
+  const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const size_t ticket_at = static_cast<size_t>(tiles) + 3 * ((tiles + 31) / 32), totals_at = ticket_at + 1;
+  if (tid == 0) s_tile = atomicAdd(reinterpret_cast<unsigned int*>(r.lb + ticket_at), 1u);
+  __syncthreads();
+  const uint32_t tile = s_tile;
+  const uint32_t q = tile * SDB_PLAN_TILE + tid;
+  const bool valid = q < r.n;
+  const bool retire = !(r.flags & SDB_RECV_PEEK);
+  const uint32_t R = v.ring_slots, mask = R - 1;
+  constexpr uint32_t KEEP = 8;
+  const uint64_t pol = sdb_policy_evict_last();
+
+  uint32_t a = 0, head = 0, tail = 0, nt = 0, cnt = 0;
+  uint4 h4 = make_uint4(0, 0, 0, 0);
+  if (valid) {
+    a = r.agent_idx ? r.agent_idx[q] : q;
+    if (a < v.max_agents) {
+      h4 = *reinterpret_cast<const uint4*>(v.ring_hdr + a);                 // head, tail, ctail, ntomb
+      head = h4.x; tail = h4.y; nt = h4.w;
+      cnt = min(tail - head - nt, r.max_messages);
+    }
+  }
+  const bool holey = cnt && nt != 0;
+  const bool simple = cnt && !holey;
+  const uint2* rs = sdb_ring_of(v, valid && a < v.max_agents ? a : 0u);
+  uint64_t ev[KEEP];
+  uint32_t gsum = 0;
+  if (simple) {
+    if (cnt <= KEEP) {
+#pragma unroll
+      for (uint32_t j = 0; j < KEEP; ++j)
+        if (j < cnt) ev[j] = sdb_ld_u64_pol(reinterpret_cast<const uint64_t*>(rs + ((head + j) & mask)), pol);
+#pragma unroll
+      for (uint32_t j = 0; j < KEEP; ++j)
+        if (j < cnt) gsum += (static_cast<uint32_t>(ev[j] >> 32) & SDB_META_GLEN_MASK) - 1u;
+    } else {
+      for (uint32_t j = 0; j < cnt; ++j) gsum += (rs[(head + j) & mask].y & SDB_META_GLEN_MASK) - 1u;
+    }
+  }
+  // agents with holes: their warp walks the window (rare: stream-order receive after priority receives)
+  for (uint32_t hb = __ballot_sync(0xFFFFFFFFu, holey); hb; hb &= hb - 1) {
+    const uint32_t src = __ffs(hb) - 1;
+    const uint32_t A_ = __shfl_sync(0xFFFFFFFFu, a, src), H_ = __shfl_sync(0xFFFFFFFFu, head, src);
+    const uint32_t T_ = __shfl_sync(0xFFFFFFFFu, tail, src), C_ = __shfl_sync(0xFFFFFFFFu, cnt, src);
+    const uint32_t sum = holey_sum_warp(sdb_ring_of(v, A_), mask, H_, T_, C_, lane);
+    if (lane == src) gsum = sum;
+  }
+
+  // ---- tile scan of {records, granules} (two 64-bit sums: a pathological tile may exceed 32 bits before truncation)
+  unsigned long long ir = cnt, ig = gsum;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const unsigned long long yr = __shfl_up_sync(0xFFFFFFFFu, ir, o), yg = __shfl_up_sync(0xFFFFFFFFu, ig, o);
+    if (lane >= o) { ir += yr; ig += yg; }
+  }
+  if (lane == 31) { s_wr[warp] = ir; s_wg[warp] = ig; }
+  __syncthreads();
+  if (warp == 0) {
+    const unsigned long long wr = lane < 8 ? s_wr[lane] : 0ull, wg = lane < 8 ? s_wg[lane] : 0ull;
+    unsigned long long cr = wr, cg = wg;
+#pragma unroll
+    for (int o = 1; o < 8; o <<= 1) {
+      const unsigned long long yr = __shfl_up_sync(0xFFFFFFFFu, cr, o), yg = __shfl_up_sync(0xFFFFFFFFu, cg, o);
+      if (lane >= o) { cr += yr; cg += yg; }
+    }
+    const unsigned long long tr = __shfl_sync(0xFFFFFFFFu, cr, 7), tg = __shfl_sync(0xFFFFFFFFu, cg, 7);   // tile aggregate
+    if (lane < 8) { s_wr[lane] = cr - wr; s_wg[lane] = cg - wg; }                                           // exclusive warp offsets
+    // ---- hierarchical decoupled look-back (sdb_common.cuh): exclusive prefix of {records, granules} over earlier tiles
+    unsigned long long er, eg, ga, gb; bool last;
+    sdb_lb_prefix(r.lb, tile, tiles, tr, tg, lane, er, eg, last, ga, gb);
+    if (lane == 0) {
+      s_br = er; s_bg = eg;
+      if (last)                    // grand total of the call (before truncation; truncation only lowers it)
+        atomicMax(r.lb + totals_at, ~((min(ga, 0xFFFFFFFFull) << 32) | min(gb, 0xFFFFFFFFull)));
+    }
+  }
+  __syncthreads();
+  const unsigned long long pr = s_br + s_wr[warp] + ir - cnt, pg = s_bg + s_wg[warp] + ig - gsum;   // exclusive prefix of this slot
+  const uint32_t roff = static_cast<uint32_t>(min(pr, 0xFFFFFFFFull));
+  const uint32_t goff = static_cast<uint32_t>(min(pg, 0xFFFFFFFFull));
+  if (cnt && pr + cnt > r.rec_cap) {                                            // does not fit: stays queued
+    atomicMax(r.lb + totals_at, ~((static_cast<unsigned long long>(roff) << 32) | goff));
+    cnt = 0;
+  }
+  if (valid) { r.count_out[q] = cnt; r.rec_off[q] = roff; }
+
+  // ---- plan entries of the warp's simple agents: staged in shared memory, written as whole 32-byte sectors
+  // (per-thread 16-byte stores to scattered places would make the L2 fetch every sector before merging it)
+  {
+    const uint32_t mycnt = (cnt && simple) ? cnt : 0u;
+    uint32_t winc = mycnt;                                                      // inclusive scan over the warp
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { const uint32_t y = __shfl_up_sync(0xFFFFFFFFu, winc, o); if (lane >= o) winc += y; }
+    const uint32_t wtotal = __shfl_sync(0xFFFFFFFFu, winc, 31);
+    // the warp's simple records are NOT contiguous in the plan when it also holds holey or truncated agents; they are
+    // contiguous per agent, so stage (destination, entry) pairs: destination index travels in a side array
+    __shared__ uint32_t s_dst[8][SDB_PLAN_STAGE];
+    const uint32_t lbase = winc - mycnt;                                        // local index of this lane's first entry
+    for (uint32_t c0 = 0; c0 < wtotal; c0 += SDB_PLAN_STAGE) {
+      uint32_t g0 = goff;
+      if (mycnt) {
+        for (uint32_t j = 0; j < mycnt; ++j) {
+          uint64_t e;
+          if (cnt <= KEEP) {
+            e = ev[0];
+#pragma unroll
+            for (uint32_t u = 1; u < KEEP; ++u) if (j == u) e = ev[u];
+          } else {
+            e = sdb_ld_u64_pol(reinterpret_cast<const uint64_t*>(rs + ((head + j) & mask)), pol);
+          }
+          const uint32_t g = (static_cast<uint32_t>(e >> 32) & SDB_META_GLEN_MASK) - 1u;
+          const uint32_t li = lbase + j;
+          if (li >= c0 && li < c0 + SDB_PLAN_STAGE) {
+            s_stage[warp][li - c0] = make_uint4(static_cast<uint32_t>(e), g0, g, q);
+            s_dst[warp][li - c0] = roff + j;
+          }
+          g0 += g;
+        }
+      }
+      __syncwarp();
+      const uint32_t nst = min(SDB_PLAN_STAGE, wtotal - c0);
+      for (uint32_t i = lane; i < nst; i += 32) r.plan[s_dst[warp][i]] = s_stage[warp][i];
+      __syncwarp();
+    }
+    // the whole 16-byte header goes back in one store: neighbouring agents' headers then leave as full sectors
+    // (a 4-byte store per agent is a partial-sector write the L2 has to merge)
+    if (mycnt && retire) { h4.x = head + cnt; *reinterpret_cast<uint4*>(v.ring_hdr + a) = h4; }
+  }
+  for (uint32_t hb = __ballot_sync(0xFFFFFFFFu, holey && cnt); hb; hb &= hb - 1) {
+    const uint32_t src = __ffs(hb) - 1;
+    const uint32_t A_ = __shfl_sync(0xFFFFFFFFu, a, src), H_ = __shfl_sync(0xFFFFFFFFu, head, src);
+    const uint32_t T_ = __shfl_sync(0xFFFFFFFFu, tail, src), C_ = __shfl_sync(0xFFFFFFFFu, cnt, src);
+    const uint32_t N_ = __shfl_sync(0xFFFFFFFFu, nt, src), RO_ = __shfl_sync(0xFFFFFFFFu, roff, src);
+    const uint32_t G_ = __shfl_sync(0xFFFFFFFFu, goff, src), Q_ = __shfl_sync(0xFFFFFFFFu, q, src);
+    select_agent_warp(v, r.plan, Q_, false, A_, H_, T_, N_, C_, RO_, lane, retire);
+    __threadfence_block();
+    __syncwarp();
+    fill_offsets_warp(r.plan, RO_, C_, G_, lane);
+  }
+  uint32_t n_deliv = retire ? cnt : 0u;
+  for (int o = 16; o; o >>= 1) n_deliv += __shfl_xor_sync(0xFFFFFFFFu, n_deliv, o);
+  if (lane == 0 && n_deliv) atomicAdd(&v.ctr->delivered, static_cast<unsigned long long>(n_deliv));
 }
 
 // ------------------------------------------------------------------------------------------
 // gather: flat over output records, 8 lanes per record (4 records per warp step), all loads of a
 // step issued before its stores.  Pure indexed copy: arena record -> hdr_out[r] + payload_out.
+// The first thread also publishes the call's totals where the host (and the digest kernel) read them.
 // ------------------------------------------------------------------------------------------
+__device__ __forceinline__ void gather_record(const sdb_dev_view& v, const sdb_recv_args& r, uint32_t rec, uint32_t l8, uint64_t pol) {
+  const uint4 pe = __ldg(r.plan + rec);                        // handle, payload offset, payload granules, slot
+  const uint32_t g = pe.z;
+  const uint64_t po = static_cast<uint64_t>(pe.y) + (r.plan_tops ? r.plan_tops[rec / SDB_SCAN_TILE] : 0u);
+  const uint8_t* src = v.arena + ((static_cast<uint64_t>(pe.x) & v.gmask) << 5);
+  uint8_t* hdst = reinterpret_cast<uint8_t*>(r.hdr_out + rec);
+  uint8_t* pdst = r.payload_out + (po << 5) - 32;          // chunk c >= 2 lands at pdst + 16 c
+  const uint32_t nchunk = 2u + (g << 1);
+  for (uint32_t c = l8; c < nchunk; c += 24) {
+    const uint32_t c1 = c + 8, c2 = c + 16;
+    uint4 x0 = sdb_ld_stream_pol(src + (c << 4), pol), x1, x2;
+    if (c1 < nchunk) x1 = sdb_ld_stream_pol(src + (c1 << 4), pol);
+    if (c2 < nchunk) x2 = sdb_ld_stream_pol(src + (c2 << 4), pol);
+    sdb_st_stream_pol((c < 2 ? hdst : pdst) + (c << 4), x0, pol);
+    if (c1 < nchunk) sdb_st_stream_pol(pdst + (c1 << 4), x1, pol);
+    if (c2 < nchunk) sdb_st_stream_pol(pdst + (c2 << 4), x2, pol);
+  }
+}
+__device__ __forceinline__ uint32_t gather_total(const sdb_recv_args& r, const unsigned long long* packed_inv) {
+  if (!packed_inv) return static_cast<uint32_t>(r.totals[0]);
+  const unsigned long long pk = ~*packed_inv;
+  if (blockIdx.x == 0 && threadIdx.x == 0) { r.totals[0] = pk >> 32; r.totals[1] = pk & 0xFFFFFFFFull; }
+  return static_cast<uint32_t>(pk >> 32);
+}
+
 __global__ void __launch_bounds__(256)
-k_recv_gather(sdb_dev_view v, sdb_recv_args r) {
-  const uint32_t total = static_cast<uint32_t>(r.totals[0]);
+k_recv_gather(sdb_dev_view v, sdb_recv_args r, const unsigned long long* __restrict__ packed_inv) {
+  const uint32_t total = gather_total(r, packed_inv);
   const uint32_t lane = threadIdx.x & 31, sub = lane >> 3, l8 = lane & 7;
   const uint64_t pol = sdb_policy_evict_first();
   const uint32_t gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const uint32_t nw = (gridDim.x * blockDim.x) >> 5;
   for (uint32_t r0 = gw * 4u; r0 < total; r0 += nw * 4u) {
     const uint32_t rec = r0 + sub;
-    if (rec >= total) continue;
-    const uint32_t handle = r.plan_handle[rec];
-    const uint32_t g = r.plan_glen[rec];
-    const uint64_t po = static_cast<uint64_t>(r.plan_local[rec]) + r.plan_tops[rec / SDB_SCAN_TILE];
-    const uint8_t* src = v.arena + ((static_cast<uint64_t>(handle) & v.gmask) << 5);
-    uint8_t* hdst = reinterpret_cast<uint8_t*>(r.hdr_out + rec);
-    uint8_t* pdst = r.payload_out + (po << 5) - 32;          // chunk c >= 2 lands at pdst + 16 c
-    const uint32_t nchunk = 2u + (g << 1);
-    for (uint32_t c = l8; c < nchunk; c += 24) {
-      const uint32_t c1 = c + 8, c2 = c + 16;
-      uint4 x0 = sdb_ld_stream_pol(src + (c << 4), pol), x1, x2;
-      if (c1 < nchunk) x1 = sdb_ld_stream_pol(src + (c1 << 4), pol);
-      if (c2 < nchunk) x2 = sdb_ld_stream_pol(src + (c2 << 4), pol);
-      sdb_st_stream_pol((c < 2 ? hdst : pdst) + (c << 4), x0, pol);
-      if (c1 < nchunk) sdb_st_stream_pol(pdst + (c1 << 4), x1, pol);
-      if (c2 < nchunk) sdb_st_stream_pol(pdst + (c2 << 4), x2, pol);
-    }
+    if (rec < total) gather_record(v, r, rec, l8, pol);
   }
+}
+
+// The same copy with the TMA engine doing the moving: every lane owns one record per step and issues ONE bulk load of the
+// whole record (header + padded payload, 32-byte granules) into its shared-memory slot, completion counted on the
+// warp's mbarrier; when a step has landed the lane issues two bulk stores (header -> hdr_out[r], payload -> the packed
+// stream).  Two stages per warp: while step i is being stored, step i + 1 is already in flight.  A lane never touches
+// the bytes, so the kernel needs few registers, and a CTA keeps stage_bytes x 32 lanes x 2 stages x warps in flight -
+// several times what 16-byte loads held in registers can.  Used when a record fits the per-lane slot.
+template <int WARPS>
+__global__ void __launch_bounds__(WARPS * 32)
+k_recv_gather_tma(sdb_dev_view v, sdb_recv_args r, const unsigned long long* __restrict__ packed_inv, uint32_t slot_bytes) {
+  extern __shared__ __align__(128) uint8_t s_dyn[];          // [WARPS][2][32][slot_bytes]
+  __shared__ __align__(8) uint64_t s_bar[WARPS][2];
+  const uint32_t total = gather_total(r, packed_inv);
+  const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  uint8_t* const wbase = s_dyn + static_cast<size_t>(warp) * 2u * 32u * slot_bytes;
+  if (lane == 0) { sdb_mbar_init(&s_bar[warp][0], 1); sdb_mbar_init(&s_bar[warp][1], 1); sdb_fence_barrier_init(); }
+  __syncwarp();
+  const uint32_t gw = blockIdx.x * WARPS + warp, nw = gridDim.x * WARPS;
+  uint32_t phase = 0;                                        // bit s = parity of stage s
+  // per-lane state of the two stages
+  uint32_t g0 = 0, g1 = 0, rc0 = 0, rc1 = 0; uint64_t po0 = 0, po1 = 0; bool hv0 = false, hv1 = false;
+  auto issue = [&](uint32_t st, uint32_t r0) {               // all lanes: request step r0 into stage st
+    const uint32_t rec = r0 + lane;
+    const bool have = rec < total;
+    uint32_t bytes = 0; uint4 pe = make_uint4(0, 0, 0, 0);
+    if (have) { pe = __ldg(r.plan + rec); bytes = 32u + (pe.z << 5); }
+    uint32_t sum = bytes;
+    for (int o = 16; o; o >>= 1) sum += __shfl_xor_sync(0xFFFFFFFFu, sum, o);
+    if (lane == 0) sdb_mbar_expect_tx(&s_bar[warp][st], sum);
+    __syncwarp();
+    if (have) {
+      const uint8_t* src = v.arena + ((static_cast<uint64_t>(pe.x) & v.gmask) << 5);
+      sdb_tma_load(wbase + (static_cast<size_t>(st) * 32u + lane) * slot_bytes, src, bytes, &s_bar[warp][st]);
+    }
+    const uint64_t po = static_cast<uint64_t>(pe.y) + ((have && r.plan_tops) ? r.plan_tops[rec / SDB_SCAN_TILE] : 0u);
+    if (st) { g1 = pe.z; rc1 = rec; hv1 = have; po1 = po; } else { g0 = pe.z; rc0 = rec; hv0 = have; po0 = po; }
+  };
+  uint32_t r0 = gw * 32u;
+  if (r0 < total) issue(0, r0);
+  uint32_t st = 0;
+  for (; r0 < total; r0 += nw * 32u, st ^= 1u) {
+    const uint32_t rn = r0 + nw * 32u;
+    // the other stage was last read by the bulk stores of the step before this one: they must have finished reading it
+    sdb_tma_wait_read<0>();
+    __syncwarp();
+    if (rn < total) issue(st ^ 1u, rn);
+    sdb_mbar_wait_bounded(&s_bar[warp][st], (phase >> st) & 1u);
+    phase ^= 1u << st;
+    if (st ? hv1 : hv0) {
+      const uint8_t* slot = wbase + (static_cast<size_t>(st) * 32u + lane) * slot_bytes;
+      const uint32_t g = st ? g1 : g0;
+      sdb_tma_store(r.hdr_out + (st ? rc1 : rc0), slot, 32u);
+      if (g) sdb_tma_store(r.payload_out + ((st ? po1 : po0) << 5), slot + 32, g << 5);
+    }
+    sdb_tma_commit();
+  }
+  sdb_tma_wait_all<0>();
 }
 
 // ------------------------------------------------------------------------------------------
@@ -522,14 +771,14 @@ k_recv_digest(sdb_recv_args r, uint32_t max_agents, unsigned long long* __restri
     if (cnt == 0) continue;
     const uint32_t a = r.agent_idx ? r.agent_idx[q] : q;
     if (a >= max_agents) continue;
-    const uint32_t roff = r.rec_local[q] + r.rec_tops[q / SDB_SCAN_TILE];
+    const uint32_t roff = r.rec_off[q];
     unsigned long long d = digest[a];
     for (uint32_t j = 0; j < cnt; ++j) {
       const uint32_t rec = roff + j;
       const unsigned long long* hw = reinterpret_cast<const unsigned long long*>(r.hdr_out + rec);
       const uint32_t len = r.hdr_out[rec].len;
       const uint32_t nwords = 4u + (((len + 31u) & ~31u) >> 3);
-      const unsigned long long po = (static_cast<unsigned long long>(r.plan_local[rec]) + r.plan_tops[rec / SDB_SCAN_TILE]) << 5;
+      const unsigned long long po = (static_cast<unsigned long long>(r.plan[rec].y) + (r.plan_tops ? r.plan_tops[rec / SDB_SCAN_TILE] : 0u)) << 5;
       const unsigned long long* pw = reinterpret_cast<const unsigned long long*>(r.payload_out + po);
       unsigned long long acc = 0;
       for (uint32_t k = lane; k < nwords; k += 32) {
@@ -564,7 +813,7 @@ struct sdb_small_agents { uint32_t idx[SDB_SMALL_AGENTS]; };
 
 __global__ void __launch_bounds__(256)
 k_recv_small(sdb_dev_view v, sdb_small_agents ag, uint32_t n, uint32_t max_messages, uint32_t flags, uint32_t rec_cap,
-             uint32_t* __restrict__ plan_handle, uint32_t* __restrict__ plan_glen, uint8_t* __restrict__ out) {
+             uint4* __restrict__ plan, uint8_t* __restrict__ out) {
   __shared__ uint32_t s_cnt[SDB_SMALL_AGENTS], s_roff[SDB_SMALL_AGENTS + 1], s_goff[SDB_SMALL_RECS + 1];
   __shared__ uint32_t s_total;
   const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -574,8 +823,8 @@ k_recv_small(sdb_dev_view v, sdb_small_agents ag, uint32_t n, uint32_t max_messa
   if (lane == 0) {
     uint32_t c = 0;
     if (mine && a < v.max_agents) {
-      const uint64_t st = v.ring_state[a];
-      head = static_cast<uint32_t>(st); tail = static_cast<uint32_t>(st >> 32); nt = v.ntomb[a];
+      const uint4 h = *reinterpret_cast<const uint4*>(v.ring_hdr + a);
+      head = h.x; tail = h.y; nt = h.w;
       c = min(tail - head - nt, max_messages);
     }
     s_cnt[warp] = c;
@@ -597,7 +846,7 @@ k_recv_small(sdb_dev_view v, sdb_small_agents ag, uint32_t n, uint32_t max_messa
   if (cnt) {
     const uint32_t H = __shfl_sync(0xFFFFFFFFu, head, 0), T = __shfl_sync(0xFFFFFFFFu, tail, 0);
     const uint32_t NT = __shfl_sync(0xFFFFFFFFu, nt, 0);
-    select_agent_warp(v, plan_handle, plan_glen, (flags & SDB_RECV_PRIORITY) != 0, a, H, T, NT, cnt, roff, lane,
+    select_agent_warp(v, plan, warp, (flags & SDB_RECV_PRIORITY) != 0, a, H, T, NT, cnt, roff, lane,
                       !(flags & SDB_RECV_PEEK));
   }
   __syncthreads();
@@ -606,7 +855,7 @@ k_recv_small(sdb_dev_view v, sdb_small_agents ag, uint32_t n, uint32_t max_messa
     uint32_t run = 0;
     for (uint32_t r0 = 0; r0 < total; r0 += 32) {
       const uint32_t r = r0 + lane;
-      const uint32_t g = r < total ? plan_glen[r] + 1u : 0u;
+      const uint32_t g = r < total ? plan[r].z + 1u : 0u;
       uint32_t incl = g;
 #pragma unroll
       for (int o = 1; o < 32; o <<= 1) { const uint32_t y = __shfl_up_sync(0xFFFFFFFFu, incl, o); if (lane >= o) incl += y; }
@@ -623,8 +872,9 @@ k_recv_small(sdb_dev_view v, sdb_small_agents ag, uint32_t n, uint32_t max_messa
   __syncthreads();
   const uint32_t l8 = tid & 7;
   for (uint32_t r = tid >> 3; r < total; r += 32) {
-    const uint32_t g = plan_glen[r];
-    const uint8_t* src = v.arena + ((static_cast<uint64_t>(plan_handle[r]) & v.gmask) << 5);
+    const uint4 pe = plan[r];
+    const uint32_t g = pe.z;
+    const uint8_t* src = v.arena + ((static_cast<uint64_t>(pe.x) & v.gmask) << 5);
     uint8_t* dst = out + 64 + (static_cast<size_t>(s_goff[r]) << 5);
     const uint32_t nchunk = 2u + (g << 1);
     for (uint32_t c = l8; c < nchunk; c += 8) sdb_st_stream(dst + (c << 4), sdb_ld_stream(src + (c << 4)));
@@ -633,24 +883,76 @@ k_recv_small(sdb_dev_view v, sdb_small_agents ag, uint32_t n, uint32_t max_messa
 
 extern "C" cudaError_t sdb_launch_receive_small(const sdb_dev_view* v, const uint32_t* agents_host, uint32_t n,
                                                 uint32_t max_messages, uint32_t flags, uint32_t rec_cap,
-                                                uint32_t* plan_handle, uint32_t* plan_glen, uint8_t* out,
+                                                uint4* plan, uint8_t* out,
                                                 cudaStream_t stream, sdb_profiler* prof) {
   sdb_small_agents ag{};
   for (uint32_t i = 0; i < n && i < SDB_SMALL_AGENTS; ++i) ag.idx[i] = agents_host[i];
   const int pi = sdb_prof_begin(prof, SDB_PK_RECV_GATHER, stream);
   k_recv_small<<<1, 256, 0, stream>>>(*v, ag, n, max_messages, flags, rec_cap < SDB_SMALL_RECS ? rec_cap : SDB_SMALL_RECS,
-                                      plan_handle, plan_glen, out);
+                                      plan, out);
   sdb_prof_end(prof, pi, stream);
   return cudaGetLastError();
 }
 
 // ------------------------------------------------------------------------------------------
-extern "C" cudaError_t sdb_launch_receive(const sdb_dev_view* v, const sdb_recv_args* r, cudaStream_t stream,
-                                          int* n_launches, sdb_profiler* prof, int sm_count) {
-  if (r->n == 0) return cudaSuccess;
+// max_rec_bytes: largest record (32-byte header + padded payload) this handle can hold; the TMA gather keeps one
+// shared-memory slot of that size per lane and stage, so it is used for records up to 544 bytes (512-byte payloads)
+static cudaError_t launch_gather(const sdb_dev_view* v, const sdb_recv_args* r, const unsigned long long* packed_inv,
+                                 uint64_t bound, uint32_t max_rec_bytes, int sm_count, cudaStream_t stream,
+                                 sdb_profiler* prof, int* n_launches) {
+  static int use_tma = -1;
+  if (use_tma < 0) { const char* e = getenv("SDB_GATHER_TMA"); use_tma = e ? atoi(e) : 1; }
+  const int pi = sdb_prof_begin(prof, SDB_PK_RECV_GATHER, stream);
+  if (use_tma && max_rec_bytes <= 544 && bound >= 4096) {
+    constexpr int WARPS = 4;
+    const size_t smem = static_cast<size_t>(WARPS) * 2u * 32u * max_rec_bytes;
+    uint32_t per_sm = static_cast<uint32_t>((200u * 1024u) / (smem + 1024));
+    if (per_sm < 1) per_sm = 1;
+    if (per_sm > 8) per_sm = 8;
+    uint64_t grid = static_cast<uint64_t>(sm_count) * per_sm * 4;                  // a few waves: the tail evens out
+    const uint64_t need = (bound + WARPS * 32 - 1) / (WARPS * 32);
+    if (grid > need) grid = need;
+    k_recv_gather_tma<WARPS><<<static_cast<uint32_t>(grid), WARPS * 32, smem, stream>>>(*v, *r, packed_inv, max_rec_bytes);
+  } else {
+    uint64_t gwarps = (bound + 3) / 4;
+    uint64_t gblocks = (gwarps + 7) / 8;
+    const uint64_t cap = static_cast<uint64_t>(sm_count) * 8 * 4;                // grid-stride beyond ~4 waves
+    if (gblocks > cap) gblocks = cap;
+    if (gblocks == 0) gblocks = 1;
+    k_recv_gather<<<static_cast<uint32_t>(gblocks), 256, 0, stream>>>(*v, *r, packed_inv);
+  }
+  sdb_prof_end(prof, pi, stream);
+  if (n_launches) *n_launches += 1;
+  return cudaGetLastError();
+}
+
+extern "C" cudaError_t sdb_recv_prepare_device() {
+  return cudaFuncSetAttribute(k_recv_gather_tma<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 4 * 2 * 32 * 544);
+}
+
+extern "C" cudaError_t sdb_launch_receive(const sdb_dev_view* v, const sdb_recv_args* r0, cudaStream_t stream,
+                                          int* n_launches, sdb_profiler* prof, int sm_count, uint32_t max_rec_bytes) {
+  if (r0->n == 0) return cudaSuccess;
+  sdb_recv_args ra = *r0;
+  sdb_recv_args* r = &ra;
   const uint32_t n = r->n;
+  // upper bound on records: min(rec_cap, n * max_messages); grids sized from it, kernels read the true count
+  uint64_t bound = static_cast<uint64_t>(n) * r->max_messages;
+  if (bound > r->rec_cap) bound = r->rec_cap;
+  int pi;
+  if (!(r->flags & SDB_RECV_PRIORITY)) {
+    // ---- stream order: single-pass plan + gather
+    const uint32_t tiles = (n + SDB_PLAN_TILE - 1) / SDB_PLAN_TILE;
+    r->plan_tops = nullptr;
+    pi = sdb_prof_begin(prof, SDB_PK_RECV_SELECT, stream);
+    cudaMemsetAsync(r->lb, 0, sdb_lb_words(tiles) * sizeof(unsigned long long), stream);
+    k_recv_plan<<<tiles, 256, 0, stream>>>(*v, *r, tiles);
+    sdb_prof_end(prof, pi, stream);
+    if (n_launches) *n_launches += 1;
+    return launch_gather(v, r, r->lb + sdb_lb_words(tiles) - 1, bound, max_rec_bytes, sm_count, stream, prof, n_launches);
+  }
   const uint32_t tiles = (n + SDB_SCAN_TILE - 1) / SDB_SCAN_TILE;
-  int pi = sdb_prof_begin(prof, SDB_PK_RECV_COUNT, stream);
+  pi = sdb_prof_begin(prof, SDB_PK_RECV_COUNT, stream);
   k_recv_count<<<(n + 255) / 256, 256, 0, stream>>>(*v, *r);
   sdb_prof_end(prof, pi, stream);
   pi = sdb_prof_begin(prof, SDB_PK_RECV_SCAN, stream);
@@ -667,24 +969,13 @@ extern "C" cudaError_t sdb_launch_receive(const sdb_dev_view* v, const sdb_recv_
     k_recv_select_big<<<bg, 256, 0, stream>>>(*v, *r);
   }
   sdb_prof_end(prof, pi, stream);
-  // upper bound on records: min(rec_cap, n * max_messages); grids sized from it, kernels read the true count
-  uint64_t bound = static_cast<uint64_t>(n) * r->max_messages;
-  if (bound > r->rec_cap) bound = r->rec_cap;
   const uint32_t rtiles = static_cast<uint32_t>((bound + SDB_SCAN_TILE - 1) / SDB_SCAN_TILE);
   pi = sdb_prof_begin(prof, SDB_PK_RECV_SCAN, stream);
-  k_scan_plan<<<rtiles, 1024, 0, stream>>>(r->plan_glen, r->plan_local, r->plan_tops, r->totals);
+  k_scan_plan<<<rtiles, 1024, 0, stream>>>(r->plan, r->plan_tops, r->totals);
   k_scan_tops<<<1, 1024, 0, stream>>>(r->plan_tops, rtiles, r->totals + 1);    // totals[1] = payload granules
   sdb_prof_end(prof, pi, stream);
-  uint64_t gwarps = (bound + 3) / 4;
-  uint64_t gblocks = (gwarps + 7) / 8;
-  const uint64_t cap = static_cast<uint64_t>(sm_count) * 8 * 4;                // grid-stride beyond ~4 waves
-  if (gblocks > cap) gblocks = cap;
-  if (gblocks == 0) gblocks = 1;
-  pi = sdb_prof_begin(prof, SDB_PK_RECV_GATHER, stream);
-  k_recv_gather<<<static_cast<uint32_t>(gblocks), 256, 0, stream>>>(*v, *r);
-  sdb_prof_end(prof, pi, stream);
-  if (n_launches) *n_launches += 8;
-  return cudaGetLastError();
+  if (n_launches) *n_launches += 7;
+  return launch_gather(v, r, nullptr, bound, max_rec_bytes, sm_count, stream, prof, n_launches);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -695,18 +986,40 @@ __global__ void __launch_bounds__(256)
 k_arena_floor(sdb_dev_view v, uint32_t n_agents, uint32_t tail32, unsigned long long* max_dist) {
   const uint32_t a = blockIdx.x * blockDim.x + threadIdx.x;
   if (a >= n_agents) return;
-  const uint64_t st = v.ring_state[a];
-  const uint32_t head = static_cast<uint32_t>(st), tail = static_cast<uint32_t>(st >> 32);
+  const uint4 h = *reinterpret_cast<const uint4*>(v.ring_hdr + a);
+  const uint32_t head = h.x, tail = h.y;
   const uint32_t mask = v.ring_slots - 1;
-  const uint16_t* ms = v.ring_meta + (static_cast<size_t>(a) << v.ring_shift);
-  const uint32_t* hs = v.ring_handle + (static_cast<size_t>(a) << v.ring_shift);
+  const uint2* rs = sdb_ring_of(v, a);
   for (uint32_t p = head; p != tail; ++p) {
-    if (ms[p & mask] != SDB_META_TOMB) {
-      const uint32_t dist = tail32 - hs[p & mask];      // granules below the arena tail (mod 2^32)
+    const uint2 e = rs[p & mask];
+    if (sdb_meta(e) != SDB_META_TOMB) {
+      const uint32_t dist = tail32 - e.x;               // granules below the arena tail (mod 2^32)
       atomicMax(max_dist, static_cast<unsigned long long>(dist));
       return;                                           // rings are sorted: first live entry is the oldest
     }
   }
+}
+
+// same scan for the asynchronous import: the tail comes from the device cursor, the result goes to cursor.floor_dist
+__global__ void __launch_bounds__(256)
+k_arena_floor_cur(sdb_dev_view v, uint32_t n_agents, sdb_cursor* cur) {
+  const uint32_t a = blockIdx.x * blockDim.x + threadIdx.x;
+  if (a >= n_agents) return;
+  const uint4 h = *reinterpret_cast<const uint4*>(v.ring_hdr + a);
+  const uint32_t head = h.x, tail = h.y;
+  if (head == tail) return;
+  const uint32_t tail32 = static_cast<uint32_t>(cur->arena_tail);
+  const uint32_t mask = v.ring_slots - 1;
+  const uint2* rs = sdb_ring_of(v, a);
+  for (uint32_t p = head; p != tail; ++p) {
+    const uint2 e = rs[p & mask];
+    if (sdb_meta(e) != SDB_META_TOMB) { atomicMax(&cur->floor_dist, static_cast<unsigned long long>(tail32 - e.x)); return; }
+  }
+}
+extern "C" cudaError_t sdb_launch_arena_floor_cur(const sdb_dev_view* v, uint32_t n_agents, sdb_cursor* cur, cudaStream_t stream) {
+  cudaMemsetAsync(&cur->floor_dist, 0, sizeof(unsigned long long), stream);
+  if (n_agents) k_arena_floor_cur<<<(n_agents + 255) / 256, 256, 0, stream>>>(*v, n_agents, cur);
+  return cudaGetLastError();
 }
 
 extern "C" cudaError_t sdb_launch_arena_floor(const sdb_dev_view* v, uint32_t n_agents, uint32_t tail32,

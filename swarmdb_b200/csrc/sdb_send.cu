@@ -410,7 +410,11 @@ template <int WARPS>
 __global__ void __launch_bounds__(WARPS * 32, 8)
 k_group_fanout_span(sdb_dev_view v, const sdb_send_desc* __restrict__ descs, uint32_t n,
                     const uint8_t* __restrict__ payload, const uint32_t* __restrict__ tmp_list,
-                    uint64_t seq_base, uint64_t arena_base, uint32_t stage_bytes) {
+                    uint64_t seq_base, uint64_t arena_base, uint32_t stage_bytes, const sdb_batch_base* __restrict__ bb) {
+  if (bb) {                                                  // asynchronous import: placement computed on the device
+    if (bb->skip) return;
+    n = bb->n_total; seq_base = bb->seq_base; arena_base = bb->arena_base;
+  }
   constexpr uint32_t PAY = SDB_SPAN_PAY, DESC = SDB_SPAN_DESC, GROUP = SDB_SPAN_GROUP, NONE = 0xFFFFFFFFu;
   static_assert(DESC == 4 * GROUP && PAY == 2 * GROUP, "refill schedule below assumes these distances");
   extern __shared__ __align__(128) uint8_t s_dyn[];          // per warp: descriptors | header table | record table | payload stages
@@ -660,13 +664,143 @@ k_enqueue_p2p(sdb_dev_view v, const sdb_send_desc* __restrict__ descs, uint32_t 
 }
 
 // ------------------------------------------------------------------------------------------
-// pull index build: one thread per agent.  For large group batches the ring entries are not
-// claimed by the fan-out kernel (4 M random atomics + small scattered stores cost 2x the payload
-// stream); instead every agent walks the batch's sends to the groups it belongs to - bucketed
-// by group on the host, ascending send index inside a bucket - and appends its own entries in
-// global send order: no atomics, no sort, writes of adjacent agents land in adjacent rings.
-// An agent in several groups (or several times in one) merges its buckets by (send, position).
+// pull index build.  For large group batches the ring entries are not claimed by the fan-out kernel (4 M random
+// atomics + small scattered stores cost 2x the payload stream); they are appended in global send order by
+// kernels that own whole rings, from the batch's sends bucketed by group (ascending send index inside a bucket,
+// built by the exporter): no atomics, no sort.
+//
+//   k_pull_index_group  one WARP per group whose members all belong to that group only ("exclusive" groups - the
+//                       usual case: teams).  Every member of such a group receives the same sends, so the warp
+//                       loads the bucket's descriptors once (coalesced), each lane owns members lane, lane + 32, ..
+//                       (ONE 16-byte ring-header load per member) and appends one 8-byte entry per send: the
+//                       entries of a member are consecutive (one sector for the usual handful).  The dependent
+//                       chain bucket -> descriptor is paid once per group instead of once per (agent, send).
+//   k_pull_index        four lanes per agent, for agents with several memberships (merged by (send, position)) or
+//                       in groups that are not exclusive.
 // ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128)
+k_pull_index_group(sdb_dev_view v, sdb_pull_view pv, const sdb_send_desc* __restrict__ descs, uint32_t n_groups,
+                   const uint8_t* __restrict__ gexcl, const uint32_t* __restrict__ lstart, const uint32_t* __restrict__ lcount,
+                   uint64_t arena_base, uint32_t set_ctail, const sdb_batch_base* __restrict__ bb) {
+  // Dependent-load depth 3: {bucket bounds of every source, member table} -> {send indices, member ids} ->
+  // {descriptors, ring headers} (the kernel is latency-bound: every level is issued for the whole warp - 2 members
+  // per lane - at once).  The group's bucket is the concatenation of the sources' buckets in source order.
+  const uint32_t lane = threadIdx.x & 31;
+  const uint32_t g = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  uint32_t n_enq = 0, n_ovf = 0;
+  if (bb) {
+    if (bb->skip) return;
+    arena_base = bb->arena_base;
+    set_ctail = bb->n_other == 0 ? 1u : 0u;            // with p2p / broadcast sends in the import the commit sort publishes ctail
+  }
+  if (g < n_groups && gexcl[g]) {
+    // level 1: lane s holds source s's bucket [o, e) and the global index of its first send
+    uint32_t o = 0, e = 0, f = 0;
+    if (lane < pv.n_src) {
+      const uint32_t* go = pv.gs_off + static_cast<size_t>(lane) * pv.gs_off_stride;
+      o = go[g]; e = go[g + 1];
+      f = pv.first ? pv.first[lane] : 0u;
+    }
+    const uint32_t mstart = __ldg(lstart + g), mcount = __ldg(lcount + g);
+    uint32_t incl = e - o;                                   // prefix over sources: where each source's sends start in the bucket
+#pragma unroll
+    for (int d = 1; d < SDB_MAX_SRC; d <<= 1) { const uint32_t y = __shfl_up_sync(0xFFFFFFFFu, incl, d); if (lane >= static_cast<uint32_t>(d)) incl += y; }
+    const uint32_t total = __shfl_sync(0xFFFFFFFFu, incl, SDB_MAX_SRC - 1 < 31 ? SDB_MAX_SRC - 1 : 31);
+    const uint32_t excl = incl - (e - o);
+    if (total && mcount) {
+      const uint64_t pol = sdb_policy_evict_first();        // measured: 8 us faster than evict_last (the entries are read once, a kernel later)
+      const uint32_t R = v.ring_slots, mask = R - 1;
+      auto send_of = [&](uint32_t p) -> uint32_t {           // bucket position -> global descriptor index (warp-uniform shuffles)
+        uint32_t idx = 0xFFFFFFFFu;
+        for (uint32_t s = 0; s < pv.n_src; ++s) {
+          const uint32_t xs = __shfl_sync(0xFFFFFFFFu, excl, s), cs = __shfl_sync(0xFFFFFFFFu, e - o, s);
+          const uint32_t os = __shfl_sync(0xFFFFFFFFu, o, s), fs = __shfl_sync(0xFFFFFFFFu, f, s);
+          if (p >= xs && p < xs + cs) idx = fs + pv.gs_idx[static_cast<size_t>(s) * pv.gs_idx_stride + os + (p - xs)];
+        }
+        return idx;
+      };
+      for (uint32_t m0 = 0; m0 < mcount; m0 += 64) {
+        const uint32_t j0 = m0 + lane, j1 = j0 + 32;      // positions in the (local) member list = record slots in a send's region
+        // level 2
+        uint32_t sidx = send_of(lane);
+        const uint32_t a0 = j0 < mcount ? __ldg(v.members + mstart + j0) : 0xFFFFFFFFu;
+        const uint32_t a1 = j1 < mcount ? __ldg(v.members + mstart + j1) : 0xFFFFFFFFu;
+        // level 3
+        uint4 q1 = make_uint4(0, 0, 0, 0);
+        if (sidx != 0xFFFFFFFFu) q1 = __ldg(reinterpret_cast<const uint4*>(descs + sidx) + 1);   // gran0, sender, rgran, len|prio|type
+        const bool ok0 = a0 < v.max_agents, ok1 = a1 < v.max_agents;
+        uint4 hd0 = make_uint4(0, 0, 0, 0), hd1 = make_uint4(0, 0, 0, 0);
+        if (ok0) hd0 = *reinterpret_cast<const uint4*>(v.ring_hdr + a0);                     // head, tail, ctail, ntomb
+        if (ok1) hd1 = *reinterpret_cast<const uint4*>(v.ring_hdr + a1);
+        uint32_t t0 = hd0.y, t1 = hd1.y;
+        // Stores: a QUAD of lanes writes up to four consecutive entries of ONE member in one instruction, so the
+        // memory system sees one or two sector writes per member instead of one partial-sector write per entry
+        // (measured on B200, 1M random agents: 4 x 8-byte stores 72 us, one coalesced sector 15 us).  Per warp step:
+        // 8 members x 4 sends; the members' ids / heads / tails travel by shuffle from the lanes that loaded them.
+        const uint32_t quad = lane >> 2, sub = lane & 3u, qb = lane & ~3u;
+        for (uint32_t k0 = 0; k0 < total; k0 += 32) {
+          if (k0) {                                                                          // buckets deeper than 32 sends
+            sidx = send_of(k0 + lane);
+            q1 = make_uint4(0, 0, 0, 0);
+            if (sidx != 0xFFFFFFFFu) q1 = __ldg(reinterpret_cast<const uint4*>(descs + sidx) + 1);
+          }
+          const uint32_t nk = min(32u, total - k0);
+          for (uint32_t c0 = 0; c0 < nk; c0 += 4) {                                          // four sends per step
+            const uint32_t t = c0 + sub;
+            const uint32_t gran0 = __shfl_sync(0xFFFFFFFFu, q1.x, t & 31u), sender = __shfl_sync(0xFFFFFFFFu, q1.y, t & 31u);
+            const uint32_t rgran = __shfl_sync(0xFFFFFFFFu, q1.z, t & 31u), lpt = __shfl_sync(0xFFFFFFFFu, q1.w, t & 31u);
+            const bool have_send = t < nk;
+            for (uint32_t mb = 0; mb < 64; mb += 8) {                                        // eight members per step
+              const uint32_t mi = mb + quad;                                                 // member slot 0..63 of this block of 64
+              const uint32_t srcl = mi & 31u;
+              const uint32_t am = __shfl_sync(0xFFFFFFFFu, mi < 32 ? a0 : a1, srcl);
+              const uint32_t hm = __shfl_sync(0xFFFFFFFFu, mi < 32 ? hd0.x : hd1.x, srcl);
+              const uint32_t tm = __shfl_sync(0xFFFFFFFFu, mi < 32 ? t0 : t1, srcl);
+              const bool okm = am < v.max_agents;
+              const bool keep = have_send && okm && sender != am;                            // member == sender (M:1268)
+              const uint32_t bal = __ballot_sync(0xFFFFFFFFu, keep);
+              const uint32_t qbits = (bal >> qb) & 0xFu;
+              const uint32_t pos = tm + __popc(qbits & ((1u << sub) - 1u));
+              if (keep) {
+                if (pos - hm >= R) ++n_ovf;
+                else {
+                  const uint32_t jm = m0 + mi;
+                  const uint64_t meta_hi = static_cast<uint64_t>((((lpt >> 16) & 0xFFu) << 14) | rgran) << 32;
+                  sdb_st_u64_pol(reinterpret_cast<uint64_t*>(sdb_ring_of(v, am) + (pos & mask)),
+                                 meta_hi | static_cast<uint32_t>(arena_base + gran0 + static_cast<uint64_t>(jm) * rgran), pol);
+                  ++n_enq;
+                }
+              }
+              // the lane that owns this member advances its tail by the quad's kept entries
+              const uint32_t add_lo = __popc((bal >> ((lane & 7u) << 2)) & 0xFu);             // quad (lane & 7) of THIS step
+              // member slot handled by quad q in this step is mb + q: its owner lane is (mb + q) & 31, in half (mb + q) >> 5
+              if ((lane >> 3) == ((mb >> 3) & 3u) ) {                                        // lanes [mb & 31, (mb & 31) + 8) own the 8 members
+                if (mb < 32) t0 += add_lo; else t1 += add_lo;
+              }
+            }
+          }
+        }
+        if (ok0 && t0 != hd0.y) {
+          if (t0 - hd0.x > R) t0 = hd0.x + R;                                               // dropped entries were counted, never written
+          hd0.y = t0; if (set_ctail) hd0.z = t0; *reinterpret_cast<uint4*>(v.ring_hdr + a0) = hd0;
+        }
+        if (ok1 && t1 != hd1.y) {
+          if (t1 - hd1.x > R) t1 = hd1.x + R;
+          hd1.y = t1; if (set_ctail) hd1.z = t1; *reinterpret_cast<uint4*>(v.ring_hdr + a1) = hd1;
+        }
+      }
+    }
+  }
+  for (int o2 = 16; o2; o2 >>= 1) {
+    n_enq += __shfl_xor_sync(0xFFFFFFFFu, n_enq, o2);
+    n_ovf += __shfl_xor_sync(0xFFFFFFFFu, n_ovf, o2);
+  }
+  if (lane == 0) {
+    if (n_enq) atomicAdd(&v.ctr->enqueued, n_enq);
+    if (n_ovf) atomicAdd(&v.ctr->ring_overflow, n_ovf);
+  }
+}
+
 __device__ __forceinline__ void pull_emit(const sdb_dev_view& v, const sdb_send_desc* descs, uint32_t s, uint32_t j,
                                           uint32_t a, uint64_t arena_base, uint32_t head, uint32_t& tail,
                                           uint32_t& n_enq, uint32_t& n_ovf, uint64_t pol) {
@@ -674,19 +808,19 @@ __device__ __forceinline__ void pull_emit(const sdb_dev_view& v, const sdb_send_
   if (q1.y == a) return;                                                     // member == sender (M:1268)
   if (tail - head >= v.ring_slots) { ++n_ovf; return; }
   const uint32_t prio = (q1.w >> 16) & 0xFFu;
-  const size_t slot = (static_cast<size_t>(a) << v.ring_shift) + (tail & (v.ring_slots - 1));
-  sdb_st_u32_pol(v.ring_handle + slot, static_cast<uint32_t>(arena_base + q1.x + static_cast<uint64_t>(j) * q1.z), pol);
-  sdb_st_u16_pol(v.ring_meta + slot, static_cast<uint16_t>((prio << 14) | q1.z), pol);
+  const uint32_t handle = static_cast<uint32_t>(arena_base + q1.x + static_cast<uint64_t>(j) * q1.z);
+  sdb_st_u64_pol(reinterpret_cast<uint64_t*>(sdb_ring_of(v, a) + (tail & (v.ring_slots - 1))),
+                 (static_cast<uint64_t>((prio << 14) | q1.z) << 32) | handle, pol);
   ++tail; ++n_enq;
 }
 
 // Four lanes per agent ("quad"): the lanes of a quad take consecutive sends of the agent's bucket,
 // so the dependent loads (bucket entry -> descriptor) of one agent run in parallel and its new
-// ring entries leave in one coalesced store per array.  Agents with several memberships are
-// merged serially by the quad's first lane.
+// ring entries leave in one coalesced store.  Agents with several memberships are merged serially by the
+// quad's first lane.  `gexcl` (nullable): agents whose single group is exclusive were served by k_pull_index_group.
 __global__ void __launch_bounds__(256)
 k_pull_index(sdb_dev_view v, sdb_pull_view pv, const sdb_send_desc* __restrict__ descs, uint32_t n_agents,
-             uint64_t arena_base, uint32_t set_ctail) {
+             const uint8_t* __restrict__ gexcl, uint64_t arena_base, uint32_t set_ctail) {
   const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
   const uint32_t a = t >> 2, sub = t & 3u, lane = threadIdx.x & 31, qb = lane & ~3u;
   uint32_t n_enq = 0, n_ovf = 0;
@@ -694,16 +828,18 @@ k_pull_index(sdb_dev_view v, sdb_pull_view pv, const sdb_send_desc* __restrict__
   const bool valid = a < n_agents;
   uint32_t k0 = 0, k1 = 0;
   if (valid) { k0 = pv.memb_off[a]; k1 = pv.memb_off[a + 1]; }
-  const uint32_t nk = k1 - k0;
+  uint32_t nk = k1 - k0;
+  if (nk == 1 && gexcl && gexcl[pv.memb_grp[k0]]) nk = 0;            // done by the group-parallel kernel
   uint32_t head = 0, tail = 0, tail0 = 0;
   if (nk) {
-    const uint64_t st = sdb_ld_u64_pol(v.ring_state + a, pol);
-    head = static_cast<uint32_t>(st); tail = tail0 = static_cast<uint32_t>(st >> 32);
+    const uint4 hd = *reinterpret_cast<const uint4*>(v.ring_hdr + a);
+    head = hd.x; tail = tail0 = hd.y;
   }
-  // ---- single membership: the common case, quad-parallel
+  // ---- single membership: quad-parallel
   uint32_t b0 = 0, b1 = 0, j = 0;
   if (nk == 1) { const uint32_t g = pv.memb_grp[k0]; j = pv.memb_pos[k0]; b0 = pv.gs_off[g]; b1 = pv.gs_off[g + 1]; }
   const uint32_t R = v.ring_slots;
+  uint2* rs = sdb_ring_of(v, valid ? a : 0u);
   for (uint32_t p = b0 + sub; __any_sync(0xFFFFFFFFu, p - sub < b1); p += 4) {
     const bool act = p < b1;
     uint4 q1 = make_uint4(0, 0, 0, 0);
@@ -715,9 +851,9 @@ k_pull_index(sdb_dev_view v, sdb_pull_view pv, const sdb_send_desc* __restrict__
     if (keep) {
       if (pos - head >= R) ++n_ovf;
       else {
-        const size_t slot = (static_cast<size_t>(a) << v.ring_shift) + (pos & (R - 1));
-        sdb_st_u32_pol(v.ring_handle + slot, static_cast<uint32_t>(arena_base + q1.x + static_cast<uint64_t>(j) * q1.z), pol);
-        sdb_st_u16_pol(v.ring_meta + slot, static_cast<uint16_t>((((q1.w >> 16) & 0xFFu) << 14) | q1.z), pol);
+        const uint32_t handle = static_cast<uint32_t>(arena_base + q1.x + static_cast<uint64_t>(j) * q1.z);
+        sdb_st_u64_pol(reinterpret_cast<uint64_t*>(rs + (pos & (R - 1))),
+                       (static_cast<uint64_t>((((q1.w >> 16) & 0xFFu) << 14) | q1.z) << 32) | handle, pol);
         ++n_enq;
       }
     }
@@ -748,8 +884,8 @@ k_pull_index(sdb_dev_view v, sdb_pull_view pv, const sdb_send_desc* __restrict__
     }
   }
   if (sub == 0 && tail != tail0) {
-    sdb_st_u64_pol(v.ring_state + a, (static_cast<uint64_t>(tail) << 32) | head, pol);
-    if (set_ctail) sdb_st_u32_pol(v.ctail + a, tail, pol);
+    v.ring_hdr[a].tail = tail;
+    if (set_ctail) v.ring_hdr[a].ctail = tail;
   }
   for (int o = 16; o; o >>= 1) {
     n_enq += __shfl_xor_sync(0xFFFFFFFFu, n_enq, o);
@@ -769,29 +905,31 @@ k_pull_index(sdb_dev_view v, sdb_pull_view pv, const sdb_send_desc* __restrict__
 // ------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256)
 k_commit(sdb_dev_view v, uint32_t n_agents, uint32_t batch_base32, uint32_t* __restrict__ big_list,
-         uint32_t* __restrict__ big_count) {
+         uint32_t* __restrict__ big_count, const sdb_batch_base* __restrict__ bb) {
   const uint32_t a = blockIdx.x * blockDim.x + threadIdx.x;
   if (a >= n_agents) return;
-  const uint64_t st = v.ring_state[a];
-  uint32_t tail = static_cast<uint32_t>(st >> 32);
-  const uint32_t head = static_cast<uint32_t>(st);
-  const uint32_t ct = v.ctail[a];
+  if (bb) {                                      // asynchronous import: nothing to sort unless it carried p2p / broadcast sends
+    if (bb->skip || bb->n_other == 0) return;
+    batch_base32 = static_cast<uint32_t>(bb->arena_base);
+  }
+  const uint4 hd = *reinterpret_cast<const uint4*>(v.ring_hdr + a);
+  uint32_t tail = hd.y;
+  const uint32_t head = hd.x, ct = hd.z;
   if (tail == ct) return;
   const uint32_t R = v.ring_slots, mask = R - 1;
   if (tail - head > R) {                       // overflowed claims were never written
     tail = head + R;
-    v.ring_state[a] = (static_cast<uint64_t>(tail) << 32) | head;
+    v.ring_hdr[a].tail = tail;
   }
   const uint32_t cnt = tail - ct;
-  uint32_t* hs = v.ring_handle + (static_cast<size_t>(a) << v.ring_shift);
-  uint16_t* ms = v.ring_meta + (static_cast<size_t>(a) << v.ring_shift);
+  uint2* rs = sdb_ring_of(v, a);
   if (cnt > 1) {
     constexpr uint32_t LOCAL = 16;
     if (cnt <= LOCAL) {
-      uint32_t k[LOCAL]; uint16_t m[LOCAL];
+      uint32_t k[LOCAL]; uint32_t m[LOCAL];
 #pragma unroll
       for (uint32_t i = 0; i < LOCAL; ++i)
-        if (i < cnt) { k[i] = hs[(ct + i) & mask] - batch_base32; m[i] = ms[(ct + i) & mask]; }
+        if (i < cnt) { const uint2 e = rs[(ct + i) & mask]; k[i] = e.x - batch_base32; m[i] = e.y; }
       bool sorted = true;
 #pragma unroll
       for (uint32_t i = 1; i < LOCAL; ++i) if (i < cnt && k[i] < k[i - 1]) sorted = false;
@@ -803,13 +941,13 @@ k_commit(sdb_dev_view v, uint32_t n_agents, uint32_t batch_base32, uint32_t* __r
           for (uint32_t i = (r & 1); i + 1 < LOCAL; i += 2) {
             if (i + 1 < cnt && k[i + 1] < k[i]) {
               uint32_t tk = k[i]; k[i] = k[i + 1]; k[i + 1] = tk;
-              uint16_t tm = m[i]; m[i] = m[i + 1]; m[i + 1] = tm;
+              uint32_t tm = m[i]; m[i] = m[i + 1]; m[i + 1] = tm;
             }
           }
         }
 #pragma unroll
         for (uint32_t i = 0; i < LOCAL; ++i)
-          if (i < cnt) { hs[(ct + i) & mask] = k[i] + batch_base32; ms[(ct + i) & mask] = m[i]; }
+          if (i < cnt) rs[(ct + i) & mask] = make_uint2(k[i] + batch_base32, m[i]);
       }
     } else {
       // many records for one agent in one batch: a whole CTA sorts them (k_commit_big); ctail is published there
@@ -818,7 +956,7 @@ k_commit(sdb_dev_view v, uint32_t n_agents, uint32_t batch_base32, uint32_t* __r
       return;
     }
   }
-  v.ctail[a] = tail;
+  v.ring_hdr[a].ctail = tail;
 }
 
 // one CTA per agent that received more than 16 records in the batch: bitonic sort of (arena position, meta)
@@ -826,23 +964,24 @@ k_commit(sdb_dev_view v, uint32_t n_agents, uint32_t batch_base32, uint32_t* __r
 #define SDB_COMMIT_SMEM 4096u
 __global__ void __launch_bounds__(256)
 k_commit_big(sdb_dev_view v, uint32_t batch_base32, const uint32_t* __restrict__ big_list,
-             const uint32_t* __restrict__ big_count) {
+             const uint32_t* __restrict__ big_count, const sdb_batch_base* __restrict__ bb) {
+  if (bb) batch_base32 = static_cast<uint32_t>(bb->arena_base);
   __shared__ uint32_t s_key[SDB_COMMIT_SMEM];
   __shared__ uint16_t s_meta[SDB_COMMIT_SMEM];
   const uint32_t n_big = *big_count;
   const uint32_t R = v.ring_slots, mask = R - 1;
   for (uint32_t w = blockIdx.x; w < n_big; w += gridDim.x) {
     const uint32_t a = big_list[w];
-    const uint64_t st = v.ring_state[a];
-    const uint32_t tail = static_cast<uint32_t>(st >> 32), ct = v.ctail[a];
+    const uint4 hd = *reinterpret_cast<const uint4*>(v.ring_hdr + a);
+    const uint32_t tail = hd.y, ct = hd.z;
     const uint32_t cnt = tail - ct;
-    uint32_t* hs = v.ring_handle + (static_cast<size_t>(a) << v.ring_shift);
-    uint16_t* ms = v.ring_meta + (static_cast<size_t>(a) << v.ring_shift);
+    uint2* rs = sdb_ring_of(v, a);
     uint32_t N = 1; while (N < cnt) N <<= 1;
     if (N <= SDB_COMMIT_SMEM) {
       for (uint32_t i = threadIdx.x; i < N; i += blockDim.x) {
-        s_key[i] = i < cnt ? hs[(ct + i) & mask] - batch_base32 : 0xFFFFFFFFu;
-        s_meta[i] = i < cnt ? ms[(ct + i) & mask] : 0;
+        const uint2 e = i < cnt ? rs[(ct + i) & mask] : make_uint2(0u, 0u);
+        s_key[i] = i < cnt ? e.x - batch_base32 : 0xFFFFFFFFu;
+        s_meta[i] = static_cast<uint16_t>(e.y);
       }
       __syncthreads();
       for (uint32_t k = 2; k <= N; k <<= 1)
@@ -857,27 +996,22 @@ k_commit_big(sdb_dev_view v, uint32_t batch_base32, const uint32_t* __restrict__
           }
           __syncthreads();
         }
-      for (uint32_t i = threadIdx.x; i < cnt; i += blockDim.x) {
-        hs[(ct + i) & mask] = s_key[i] + batch_base32;
-        ms[(ct + i) & mask] = s_meta[i];
-      }
+      for (uint32_t i = threadIdx.x; i < cnt; i += blockDim.x)
+        rs[(ct + i) & mask] = make_uint2(s_key[i] + batch_base32, s_meta[i]);
     } else {
       // rare (more than 4096 records for one agent in one batch): odd-even transposition sort in place in the
       // ring (works for any length; the segment is L2-resident)
       for (uint32_t round = 0; round < cnt; ++round) {
         for (uint32_t i = (round & 1u) + 2u * threadIdx.x; i + 1 < cnt; i += 2u * blockDim.x) {
           const uint32_t x = (ct + i) & mask, y = (ct + i + 1) & mask;
-          const uint32_t kx = hs[x] - batch_base32, ky = hs[y] - batch_base32;
-          if (kx > ky) {
-            hs[x] = ky + batch_base32; hs[y] = kx + batch_base32;
-            const uint16_t t = ms[x]; ms[x] = ms[y]; ms[y] = t;
-          }
+          const uint2 ex = rs[x], ey = rs[y];
+          if (ex.x - batch_base32 > ey.x - batch_base32) { rs[x] = ey; rs[y] = ex; }
         }
         __syncthreads();
       }
     }
     __syncthreads();
-    if (threadIdx.x == 0) v.ctail[a] = tail;
+    if (threadIdx.x == 0) v.ring_hdr[a].ctail = tail;
     __syncthreads();
   }
 }
@@ -909,10 +1043,13 @@ extern "C" cudaError_t sdb_send_prepare_device() {
   return cudaFuncSetAttribute(k_group_fanout_tma<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * 65536 + 1024);
 }
 
+// bb (nullable): the import's placement lives on the device (asynchronous import) - span kernel only
 extern "C" cudaError_t sdb_launch_fanout(const sdb_dev_view* v, const sdb_send_desc* descs, uint32_t n,
                                          const uint8_t* payload, const uint32_t* tmp_list,
                                          uint64_t seq_base, uint64_t arena_base, uint32_t max_padlen,
-                                         int variant, int sm_count, cudaStream_t stream, sdb_profiler* prof) {
+                                         int variant, int sm_count, cudaStream_t stream, sdb_profiler* prof,
+                                         const sdb_batch_base* bb) {
+  if (bb && !(variant == 3 && max_padlen <= 512)) return cudaErrorInvalidValue;
   if (n == 0) return cudaSuccess;
   const int pi = sdb_prof_begin(prof, SDB_PK_FANOUT, stream);
   if (variant == 3 && max_padlen <= 512) {
@@ -926,7 +1063,7 @@ extern "C" cudaError_t sdb_launch_fanout(const sdb_dev_view* v, const sdb_send_d
     uint32_t grid = static_cast<uint32_t>(sm_count) * per_sm * static_cast<uint32_t>(mult);
     const uint32_t need = (n + WARPS - 1) / WARPS;
     if (grid > need) grid = need;
-    k_group_fanout_span<WARPS><<<grid, WARPS * 32, smem, stream>>>(*v, descs, n, payload, tmp_list, seq_base, arena_base, stage);
+    k_group_fanout_span<WARPS><<<grid, WARPS * 32, smem, stream>>>(*v, descs, n, payload, tmp_list, seq_base, arena_base, stage, bb);
   } else if ((variant == 2 || variant == 3) && max_padlen <= 4096) {
     constexpr int WARPS = 4;
     const uint32_t stage = ((max_padlen ? max_padlen : 16) + 127u) & ~127u;
@@ -957,27 +1094,40 @@ extern "C" cudaError_t sdb_launch_fanout(const sdb_dev_view* v, const sdb_send_d
   return cudaGetLastError();
 }
 
+// gexcl: per-group "exclusive" flags; n_groups: groups covered by the bucket table; n_shared: how many agents sit in
+// non-exclusive groups or in several groups (0: the agent-parallel kernel is not needed at all)
 extern "C" cudaError_t sdb_launch_pull(const sdb_dev_view* v, const sdb_pull_view* pv, const sdb_send_desc* descs,
-                                       uint32_t n_agents, uint64_t arena_base, int set_ctail, cudaStream_t stream,
-                                       sdb_profiler* prof) {
+                                       uint32_t n_agents, uint32_t n_groups, const uint8_t* gexcl, uint32_t n_excl_groups,
+                                       uint32_t n_shared, const uint32_t* lstart, const uint32_t* lcount,
+                                       uint64_t arena_base, int set_ctail, cudaStream_t stream,
+                                       sdb_profiler* prof, int* n_launches, const sdb_batch_base* bb) {
+  if (bb && (n_shared || !n_excl_groups)) return cudaErrorInvalidValue;      // device-side placement: group-parallel build only
   if (n_agents == 0) return cudaSuccess;
   const int pi = sdb_prof_begin(prof, SDB_PK_INDEX, stream);
-  const uint64_t threads = static_cast<uint64_t>(n_agents) * 4;
-  k_pull_index<<<static_cast<uint32_t>((threads + 255) / 256), 256, 0, stream>>>(*v, *pv, descs, n_agents, arena_base, set_ctail ? 1u : 0u);
+  if (n_excl_groups && n_groups) {
+    const uint64_t threads = static_cast<uint64_t>(n_groups) * 32;
+    k_pull_index_group<<<static_cast<uint32_t>((threads + 127) / 128), 128, 0, stream>>>(*v, *pv, descs, n_groups, gexcl, lstart, lcount, arena_base, set_ctail ? 1u : 0u, bb);
+    if (n_launches) *n_launches += 1;
+  }
+  if (n_shared || !n_excl_groups) {
+    const uint64_t threads = static_cast<uint64_t>(n_agents) * 4;
+    k_pull_index<<<static_cast<uint32_t>((threads + 255) / 256), 256, 0, stream>>>(*v, *pv, descs, n_agents, n_excl_groups ? gexcl : nullptr, arena_base, set_ctail ? 1u : 0u);
+    if (n_launches) *n_launches += 1;
+  }
   sdb_prof_end(prof, pi, stream);
   return cudaGetLastError();
 }
 
 extern "C" cudaError_t sdb_launch_commit(const sdb_dev_view* v, uint32_t n_agents, uint32_t batch_base32,
                                          uint32_t* big_list, uint32_t* big_count, int sm_count,
-                                         cudaStream_t stream, sdb_profiler* prof) {
+                                         cudaStream_t stream, sdb_profiler* prof, const sdb_batch_base* bb) {
   if (n_agents == 0) return cudaSuccess;
   const int pi = sdb_prof_begin(prof, SDB_PK_COMMIT, stream);
   cudaMemsetAsync(big_count, 0, sizeof(uint32_t), stream);
-  k_commit<<<(n_agents + 255) / 256, 256, 0, stream>>>(*v, n_agents, batch_base32, big_list, big_count);
+  k_commit<<<(n_agents + 255) / 256, 256, 0, stream>>>(*v, n_agents, batch_base32, big_list, big_count, bb);
   uint32_t bg = static_cast<uint32_t>(sm_count) * 4u;
   if (bg > n_agents) bg = n_agents;
-  k_commit_big<<<bg, 256, 0, stream>>>(*v, batch_base32, big_list, big_count);
+  k_commit_big<<<bg, 256, 0, stream>>>(*v, batch_base32, big_list, big_count, bb);
   sdb_prof_end(prof, pi, stream);
   return cudaGetLastError();
 }

@@ -215,3 +215,257 @@ extern "C" cudaError_t sdb_launch_import_localize(const sdb_import_args* a, uint
   if (n_launches) *n_launches += 2;
   return cudaGetLastError();
 }
+
+// ==========================================================================================
+// Asynchronous import (sdb_import_wire_ptrs_async): no host round trip, no collective.
+//
+//   k_wire_wait      one warp: spins until every source's export buffer carries ready >= step (sources in peer GPUs
+//                    are polled over NVLink with volatile loads: peer addresses bypass the local L2, B300_MICROARCH)
+//   k_arena_floor    (sdb_recv.cu) distance of the oldest pending record below the arena tail -> cursor.floor_dist
+//   k_import_fused   everything k_wire_table / k_wire_measure / 3 scans / k_bucket_sizes / k_wire_localize /
+//                    k_bucket_fill did in ~15 launches plus a host sync, in ONE pass:
+//                      * every block reads the <= 16 wire headers itself (no leader, no table kernel)
+//                      * one thread per wire send: reads the 64-byte descriptor where the source exported it
+//                        (straight out of the peer GPU), counts this shard's share, and a decoupled look-back over
+//                        256-send tiles (wide window, {arena granules, temporary-list entries} as a 31+31-bit
+//                        pair) gives the send its place in the arena; the localized descriptor is written
+//                      * the sources' group buckets are copied next to the descriptors (the group-parallel
+//                        index build walks them source by source: nothing is concatenated or sorted)
+//                      * the LAST tile places the whole import: arena base from the device cursor (wrap rule,
+//                        floor check), sequence base, totals -> sdb_batch_base for the kernels that follow
+//   k_wire_done      publishes done = step in this rank's own buffer (its exporter may then be overwritten by peers'
+//                    view: see sdb_wire_ctrl)
+// ==========================================================================================
+__device__ __forceinline__ uint32_t ld_volatile_u32(const uint32_t* p) {
+  uint32_t x;
+  asm volatile("ld.volatile.global.u32 %0, [%1];" : "=r"(x) : "l"(p) : "memory");
+  return x;
+}
+
+struct sdb_wait_args { const uint32_t* flag[SDB_MAX_SRC]; uint32_t n; };
+__global__ void k_wire_wait(sdb_wait_args w, uint32_t step) {
+  const uint32_t lane = threadIdx.x;
+  if (lane < w.n) {
+    // bounded: a peer that never publishes must surface as a launch failure, not as a hung GPU
+    unsigned long long t0;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+    for (;;) {
+      if (static_cast<int32_t>(ld_volatile_u32(w.flag[lane]) - step) >= 0) break;
+      unsigned long long t1;
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+      if (t1 - t0 > 120ull * 1000000000ull) __trap();       // two minutes: the peer is gone
+      __nanosleep(100);
+    }
+  }
+  __syncwarp();
+  __threadfence_system();
+}
+__global__ void k_wire_set(uint32_t* flag, uint32_t step) {
+  __threadfence_system();                      // everything this stream wrote before is visible to peers first
+  *reinterpret_cast<volatile uint32_t*>(flag) = step;
+  __threadfence_system();
+}
+
+#define SDB_IMP_TILE 256u
+
+__global__ void __launch_bounds__(256)
+k_import_fused(sdb_import2_args a, uint32_t tiles_cap) {
+  __shared__ uint32_t s_tile;
+  __shared__ uint32_t s_first[SDB_MAX_SRC + 1], s_nsend[SDB_MAX_SRC], s_ok[SDB_MAX_SRC], s_explicit[SDB_MAX_SRC];
+  __shared__ uint32_t s_nother[SDB_MAX_SRC], s_ngs[SDB_MAX_SRC], s_maxpad[SDB_MAX_SRC];
+  __shared__ unsigned long long s_recbase[SDB_MAX_SRC], s_totalrecs[SDB_MAX_SRC], s_desc_off[SDB_MAX_SRC], s_list_off[SDB_MAX_SRC];
+  __shared__ unsigned long long s_pay_off[SDB_MAX_SRC], s_gso_off[SDB_MAX_SRC], s_gsi_off[SDB_MAX_SRC], s_seqbase[SDB_MAX_SRC];
+  __shared__ unsigned long long s_wa[8], s_wb[8], s_ba, s_bb;
+  const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  if (tid == 0) s_tile = atomicAdd(reinterpret_cast<unsigned int*>(a.lb + sdb_lb_words(tiles_cap) - 2), 1u);
+  // ---- every block reads the wire headers itself (128 bytes each; remote ones over NVLink)
+  if (tid < a.n_src) {
+    const sdb_wire_header* h = reinterpret_cast<const sdb_wire_header*>(a.wire[tid]);
+    const uint4* hq = reinterpret_cast<const uint4*>(h);
+    union { uint4 q[8]; sdb_wire_header hd; } u;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) u.q[k] = hq[k];
+    const bool ok = u.hd.magic == SDB_WIRE_MAGIC;
+    s_ok[tid] = ok ? 1u : 0u;
+    s_nsend[tid] = ok ? min(u.hd.n_sends, a.max_sends) : 0u;
+    s_totalrecs[tid] = ok ? u.hd.total_recs : 0ull;
+    s_explicit[tid] = (ok && u.hd.explicit_seq) ? 1u : 0u;
+    s_seqbase[tid] = u.hd.seq_base;
+    s_desc_off[tid] = u.hd.desc_off; s_list_off[tid] = u.hd.list_off; s_pay_off[tid] = u.hd.payload_off;
+    s_gso_off[tid] = (ok && u.hd.max_groups == a.max_groups) ? u.hd.gs_off_off : 0ull; s_gsi_off[tid] = u.hd.gs_idx_off;
+    s_nother[tid] = ok ? u.hd.n_other : 0u; s_ngs[tid] = ok ? min(u.hd.n_group_sends, a.max_sends) : 0u;
+    s_maxpad[tid] = ok ? u.hd.max_padlen : 0u;
+  }
+  __syncthreads();
+  if (tid == 0) {
+    uint32_t f = 0; unsigned long long rb = 0;
+    for (uint32_t s = 0; s < a.n_src; ++s) {
+      s_first[s] = f; s_recbase[s] = s_explicit[s] ? s_seqbase[s] : rb;
+      f += s_nsend[s]; rb += s_totalrecs[s];
+    }
+    s_first[a.n_src] = f;
+  }
+  __syncthreads();
+  const uint32_t tile = s_tile;
+  const uint32_t n_total = s_first[a.n_src];
+  const uint32_t n_tiles = n_total ? (n_total + SDB_IMP_TILE - 1) / SDB_IMP_TILE : 1u;     // tiles that take part in the scan
+
+  // ---- copies of the sources' group buckets (grid-stride over all blocks; coalesced remote reads)
+  {
+    const uint32_t G1 = a.max_groups + 1;
+    const size_t nthreads = static_cast<size_t>(gridDim.x) * blockDim.x;
+    const size_t gt = static_cast<size_t>(tile) * blockDim.x + tid;
+    for (uint32_t s = 0; s < a.n_src; ++s) {
+      uint32_t* dst_o = a.gs_off_src + static_cast<size_t>(s) * G1;
+      if (s_gso_off[s]) {
+        const uint32_t* src_o = reinterpret_cast<const uint32_t*>(a.wire[s] + s_gso_off[s]);
+        for (size_t i = gt; i < G1; i += nthreads) dst_o[i] = src_o[i];
+        const uint32_t* src_i = reinterpret_cast<const uint32_t*>(a.wire[s] + s_gsi_off[s]);
+        uint32_t* dst_i = a.gs_idx_src + static_cast<size_t>(s) * a.max_sends;
+        for (size_t i = gt; i < s_ngs[s]; i += nthreads) dst_i[i] = src_i[i];
+      } else {
+        for (size_t i = gt; i < G1; i += nthreads) dst_o[i] = 0u;                          // no usable buckets: empty
+      }
+    }
+    if (tile == 0 && tid <= a.n_src) a.first[tid] = s_first[tid];
+  }
+  if (tile >= n_tiles) return;
+
+  // ---- one wire send per thread
+  const uint32_t gi = tile * SDB_IMP_TILE + tid;
+  sdb_send_desc d;
+  uint32_t src = 0, lc = 0, own = 0;
+  bool have = gi < n_total;
+  if (have) {
+    while (src + 1 < a.n_src && gi >= s_first[src + 1]) ++src;
+    const uint32_t i = gi - s_first[src];
+    const uint4* dq = reinterpret_cast<const uint4*>(a.wire[src] + s_desc_off[src]) + static_cast<size_t>(i) * 4;
+    uint4* o = reinterpret_cast<uint4*>(&d);
+    o[0] = dq[0]; o[1] = dq[1]; o[2] = dq[2]; o[3] = dq[3];
+    if (d.flags & SDB_DESC_P2P) {                                   // delivered by the receiver's owner only
+      own = (d.mstart < a.max_agents && a.shard_of[d.mstart] == a.shard_id) ? 1u : 0u;
+      lc = own;
+    } else if (d.flags & SDB_DESC_LIST_TEMP) {                      // broadcast: the recipients this shard owns
+      const uint32_t* l = reinterpret_cast<const uint32_t*>(a.wire[src] + s_list_off[src]) + d.mstart;
+      for (uint32_t k = 0; k < d.mcount; ++k) { const uint32_t x = l[k]; own += (x < a.max_agents && a.shard_of[x] == a.shard_id); }
+      lc = own;
+    } else {
+      lc = d.group < a.max_groups ? a.lcount[d.group] : 0u;
+    }
+  }
+  const unsigned long long wa = have ? static_cast<unsigned long long>(lc) * d.rgran : 0ull;     // arena granules written here
+  const unsigned long long wb = own;                                                            // temporary-list entries
+
+  // ---- tile scan + decoupled look-back of the pair
+  unsigned long long ia = wa, ib = wb;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const unsigned long long ya = __shfl_up_sync(0xFFFFFFFFu, ia, o), yb = __shfl_up_sync(0xFFFFFFFFu, ib, o);
+    if (lane >= o) { ia += ya; ib += yb; }
+  }
+  if (lane == 31) { s_wa[warp] = ia; s_wb[warp] = ib; }
+  __syncthreads();
+  if (warp == 0) {
+    const unsigned long long xa = lane < 8 ? s_wa[lane] : 0ull, xb = lane < 8 ? s_wb[lane] : 0ull;
+    unsigned long long ca = xa, cb = xb;
+#pragma unroll
+    for (int o = 1; o < 8; o <<= 1) {
+      const unsigned long long ya = __shfl_up_sync(0xFFFFFFFFu, ca, o), yb = __shfl_up_sync(0xFFFFFFFFu, cb, o);
+      if (lane >= o) { ca += ya; cb += yb; }
+    }
+    const unsigned long long ta = __shfl_sync(0xFFFFFFFFu, ca, 7), tb = __shfl_sync(0xFFFFFFFFu, cb, 7);
+    if (lane < 8) { s_wa[lane] = ca - xa; s_wb[lane] = cb - xb; }
+    unsigned long long ea, eb, ga, gb; bool last;
+    sdb_lb_prefix(a.lb, tile, n_tiles, ta, tb, lane, ea, eb, last, ga, gb);
+    if (lane == 0) {
+      s_ba = ea; s_bb = eb;
+      if (last) {
+        // ---- place the whole import (the grand totals are known here and only here)
+        const unsigned long long need = ga, lists = gb;
+        sdb_cursor* c = a.cur;
+        const unsigned long long G = a.arena_grans;
+        unsigned long long tail = c->arena_tail;
+        const unsigned long long floor_now = tail - c->floor_dist;          // floor scan ran just before this kernel
+        if (floor_now > c->arena_floor) c->arena_floor = floor_now;
+        if ((tail & (G - 1)) + need > G) tail = (tail + G - 1) & ~(G - 1);      // an import never straddles the wrap
+        unsigned long long total_recs = 0, explicit_end = 0; uint32_t n_other = 0, maxpad = 0;
+        for (uint32_t s = 0; s < a.n_src; ++s) {
+          total_recs += s_totalrecs[s]; n_other += s_nother[s]; maxpad = max(maxpad, s_maxpad[s]);
+          if (s_explicit[s]) explicit_end = max(explicit_end, s_seqbase[s] + s_totalrecs[s]);
+        }
+        uint32_t skip = 0;
+        if (need > G || tail + need - c->arena_floor > G) { skip = 1; c->error |= 1ull; }
+        if (lists > a.list_cap) { skip = 1; c->error |= 2ull; }
+        if (maxpad > 512) { skip = 1; c->error |= 4ull; }                    // the asynchronous path only drives the span kernel
+        sdb_batch_base* b = a.bb;
+        b->arena_base = tail; b->seq_base = c->next_seq; b->n_total = n_total; b->n_other = n_other; b->skip = skip;
+        b->max_padlen = maxpad; b->total_grans = need; b->total_recs = total_recs;
+        if (!skip) {
+          c->arena_tail = tail + need;
+          const unsigned long long ns = c->next_seq + (explicit_end ? 0ull : total_recs);
+          c->next_seq = ns > explicit_end ? ns : explicit_end;
+        }
+      }
+    }
+  }
+  __syncthreads();
+  if (!have) return;
+  const unsigned long long pa = s_ba + s_wa[warp] + ia - wa, pb = s_bb + s_wb[warp] + ib - wb;
+
+  // ---- localized descriptor
+  const sdb_send_desc w = d;
+  sdb_send_desc out = d;
+  // absolute address (the fan-out kernel is launched with a null payload base): the payload stays where the source
+  // rank exported it - possibly in a peer GPU's memory - and is pulled by the fan-out's TMA loads
+  out.payload_off = reinterpret_cast<uint64_t>(a.wire[src]) + s_pay_off[src] + w.payload_off;
+  out.gran0 = static_cast<uint32_t>(pa);
+  const unsigned long long rb = s_recbase[src];
+  out.rec0 = static_cast<uint32_t>(rb + w.rec0);
+  const bool abs_seq = s_explicit[src] != 0;
+  out.seq_abs = abs_seq ? rb + w.rec0 : 0ull;
+  if (w.flags & (SDB_DESC_P2P | SDB_DESC_LIST_TEMP)) {
+    uint32_t lo = static_cast<uint32_t>(pb);
+    const bool fits = pb + own <= a.list_cap;
+    out.mstart = lo; out.mcount = fits ? own : 0u; out.group = SDB_NO_GROUP;
+    if (w.flags & SDB_DESC_P2P) {
+      out.flags = SDB_DESC_LIST_TEMP | (abs_seq ? SDB_DESC_ABS_SEQ : 0u);
+      if (own && fits) a.tmp_list[lo] = w.mstart;
+    } else {
+      out.flags = SDB_DESC_LIST_TEMP | SDB_DESC_SHARED_SEQ | (abs_seq ? SDB_DESC_ABS_SEQ : 0u);
+      if (fits) {
+        const uint32_t* l = reinterpret_cast<const uint32_t*>(a.wire[src] + s_list_off[src]) + w.mstart;
+        for (uint32_t k = 0; k < w.mcount; ++k) { const uint32_t x = l[k]; if (x < a.max_agents && a.shard_of[x] == a.shard_id) a.tmp_list[lo++] = x; }
+      }
+    }
+  } else {
+    const uint32_t g = w.group;
+    out.mstart = lc ? a.lstart[g] : 0u;
+    out.mcount = lc;
+    out.flags = SDB_DESC_SKIP_SENDER | SDB_DESC_PULL | SDB_DESC_POS | (abs_seq ? SDB_DESC_ABS_SEQ : 0u);
+  }
+  uint4* o4 = reinterpret_cast<uint4*>(a.descs + gi);
+  const uint4* i4 = reinterpret_cast<const uint4*>(&out);
+  o4[0] = i4[0]; o4[1] = i4[1]; o4[2] = i4[2]; o4[3] = i4[3];
+}
+
+extern "C" cudaError_t sdb_launch_wire_wait(const uint32_t* const* flags, uint32_t n, uint32_t step, cudaStream_t stream) {
+  sdb_wait_args w{};
+  w.n = n;
+  for (uint32_t i = 0; i < n && i < SDB_MAX_SRC; ++i) w.flag[i] = flags[i];
+  k_wire_wait<<<1, 32, 0, stream>>>(w, step);
+  return cudaGetLastError();
+}
+extern "C" cudaError_t sdb_launch_wire_set(uint32_t* flag, uint32_t step, cudaStream_t stream) {
+  k_wire_set<<<1, 1, 0, stream>>>(flag, step);
+  return cudaGetLastError();
+}
+extern "C" cudaError_t sdb_launch_import_fused(const sdb_import2_args* a, cudaStream_t stream, sdb_profiler* prof, int* n_launches) {
+  const uint32_t n_cap = a->n_src * a->max_sends;
+  const uint32_t tiles = (n_cap + SDB_IMP_TILE - 1) / SDB_IMP_TILE;
+  const int pi = sdb_prof_begin(prof, SDB_PK_XSHARD, stream);
+  cudaMemsetAsync(a->lb, 0, sdb_lb_words(tiles) * sizeof(unsigned long long), stream);
+  k_import_fused<<<tiles, 256, 0, stream>>>(*a, tiles);
+  sdb_prof_end(prof, pi, stream);
+  if (n_launches) *n_launches += 1;
+  return cudaGetLastError();
+}

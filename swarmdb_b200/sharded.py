@@ -89,24 +89,27 @@ class ShardExchange:
 
 
 class PeerExchange:
-    """Peer-memory transport: no collective moves message bytes.
+    """Peer-memory transport: no collective moves message bytes and none is used as a barrier.
 
-    Every rank exports into its own CUDA-IPC-shared buffer (two of them, alternating per step);
-    `exchange()` is a one-element all-reduce used purely as a stream-ordered cross-rank barrier;
-    `import_all()` hands the shard the table of peer pointers, and the import + fan-out kernels
-    pull descriptors and payloads straight out of the exporting GPUs' memory over NVLink.
+    Every rank exports into its own CUDA-IPC-shared buffer (two of them, alternating per step) whose last 128 bytes
+    hold two counters, `ready` and `done` (include/swarmdb_b200.h).  Ranks synchronise through those flags, on
+    their streams, never on the host:
+      export      waits until every peer has finished importing the step that used this buffer before (done >= step-2),
+                  copies the wire batch, publishes ready = step
+      import_all  the import's first kernel spins until every source's ready >= step (peer flags polled over NVLink),
+                  then the import + fan-out kernels pull descriptors and payloads straight out of the exporting GPUs'
+                  memory; afterwards done = step
     """
 
     def __init__(self, shard, rank: int, world: int, max_sends: int, max_payload: int, device, stream=None):
         import torch
         import torch.distributed as dist
         self.shard, self.rank, self.world = shard, rank, world
-        # ONE stream carries the shard's copies/kernels AND the cross-rank barrier: a rank can only start reading
-        # its peers' export buffers after the barrier, and the barrier only completes after its own export
+        # the shard's copies, kernels and flag updates all run on this one stream
         self.stream = stream if stream is not None else torch.cuda.Stream(device)
         shard.set_stream(self.stream.cuda_stream)
         self.wire_bytes = shard.wire_bytes(max_sends, max_payload)
-        self.mine = [shard.wire_alloc(self.wire_bytes) for _ in range(2)]          # (ptr, ipc handle)
+        self.mine = [shard.wire_alloc(self.wire_bytes) for _ in range(2)]          # (ptr, ipc handle); zero-filled: ready = done = 0
         handles = [None] * world
         if world > 1:
             dist.all_gather_object(handles, [h for _, h in self.mine])
@@ -120,47 +123,60 @@ class PeerExchange:
                     p = shard.wire_open(handles[r][b])
                     self.ptrs[b][r] = p
                     self.opened.append(p)
-        with torch.cuda.stream(self.stream):
-            self.flag = torch.zeros(1, device=device)
-        self.step_no = 0
+        self.step_no = 0                       # steps completed; the next one is step_no + 1 and uses buffer (step_no + 1) & 1
+
+    @property
+    def next_step(self) -> int:
+        return self.step_no + 1
 
     @property
     def cur(self) -> int:
-        return self.step_no & 1
+        return self.next_step & 1
+
+    def _begin_export(self) -> int:
+        k = self.next_step
+        if k > 2:                              # peers read this buffer during step k - 2: wait (on the stream) until they are done
+            self.shard.wire_wait_done(self.ptrs[k & 1], self.wire_bytes, k - 2)
+        return k
 
     def export(self, sender, group, prio, typ, lens, payload_off, payload, ts=None) -> None:
+        k = self._begin_export()
         self.shard.export_group_batch(sender, group, prio, typ, lens, payload_off, payload,
-                                      self.mine[self.cur][0], self.wire_bytes, ts)
+                                      self.mine[k & 1][0], self.wire_bytes, ts)
+        self.shard.wire_publish(self.mine[k & 1][0], self.wire_bytes, k)
 
     def export_mixed(self, sender, kind, target, list_off, list_idx, prio, typ, lens, payload_off, payload, ts=None,
                      seq_base: int = 0) -> None:
+        k = self._begin_export()
         self.shard.export_mixed_batch(sender, kind, target, list_off, list_idx, prio, typ, lens, payload_off, payload,
-                                      self.mine[self.cur][0], self.wire_bytes, ts, seq_base)
+                                      self.mine[k & 1][0], self.wire_bytes, ts, seq_base)
+        self.shard.wire_publish(self.mine[k & 1][0], self.wire_bytes, k)
+
+    def republish(self) -> None:
+        """Benchmarks with device-resident inputs: the buffer of this parity already holds a wire batch (exported
+        before the timed region); declare it ready for the next step without copying anything."""
+        k = self.next_step
+        self.shard.wire_publish(self.mine[k & 1][0], self.wire_bytes, k)
 
     def exchange(self) -> None:
-        if self.world > 1:
-            import torch
-            import torch.distributed as dist
-            with torch.cuda.stream(self.stream):
-                dist.all_reduce(self.flag)                 # stream-ordered barrier: every rank's export is complete
+        return None                            # nothing to do: import_all waits for the sources' flags on the device
 
-    def import_all(self) -> int:
-        base = self.shard.import_wire_ptrs(self.ptrs[self.cur])
-        self.step_no += 1                                   # the other buffer is free: its readers passed the barrier above
-        return base
+    def import_all(self) -> None:
+        k = self.next_step
+        self.shard.import_wire_ptrs_async(self.ptrs[k & 1], self.wire_bytes, k)
+        self.step_no = k
 
-    def step(self, *batch, ts=None) -> int:
+    def step(self, *batch, ts=None) -> None:
         self.export(*batch, ts=ts)
-        self.exchange()
-        return self.import_all()
+        self.import_all()
 
     def close(self) -> None:
-        if self.world > 1 and self.mine:
-            import torch
+        if not self.mine:
+            return
+        self.stream.synchronize()
+        if self.world > 1:
             import torch.distributed as dist
-            with torch.cuda.stream(self.stream):
-                dist.all_reduce(self.flag)                 # nobody is still reading this rank's buffers
-            self.stream.synchronize()
+            dist.barrier()                     # host-level: nobody is still reading this rank's buffers
         for p in self.opened:
             self.shard.wire_close(p, True)
         for p, _ in self.mine:
@@ -246,10 +262,8 @@ def run_sharded_bench(args, rank: int, world: int, local_rank: int, wl):
         # device-resident inputs: wire batches exported once, before the timed region
         wires = []
         if transport == "peer":
-            for k, b in enumerate(batches):                 # batch k lives in this rank's export buffer k
-                ex.step_no = k
-                ex.export(*b)
-            ex.step_no = 0
+            for k, b in enumerate(batches):                 # batch k lives in this rank's export buffer k (no flags yet)
+                shard.export_group_batch(*b, ex.mine[k][0], ex.wire_bytes)
             torch.cuda.synchronize(); dist.barrier()
         else:
             for b in batches:
@@ -267,7 +281,10 @@ def run_sharded_bench(args, rank: int, world: int, local_rank: int, wl):
                 ex.send_buf.copy_(wires[i % n_distinct], non_blocking=True)   # HBM -> HBM staging of this step's input
             if timed:
                 evs[1].record(stream)
-            ex.exchange()
+            if transport == "peer":
+                ex.republish()                              # this step's (pre-exported) wire batch is ready: flag only
+            else:
+                ex.exchange()
             if timed:
                 evs[2].record(stream)
             ex.import_all()
@@ -284,7 +301,7 @@ def run_sharded_bench(args, rank: int, world: int, local_rank: int, wl):
         st0 = shard.stats()
         launches0 = st0["kernel_launches"]
         shard.profile(True)
-        from bench import ALG_BYTES_FANOUT, ClockSampler, hbm_peak, parity_report, traffic_note
+        from bench import ALG_BYTES_FANOUT, ClockSampler, hbm_peak, parity_report, traffic_note, workload_c3
         clocks = ClockSampler(local_rank); clocks.start()
         dist.barrier(); torch.cuda.synchronize()
         ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -375,13 +392,14 @@ def run_sharded_bench(args, rank: int, world: int, local_rank: int, wl):
             "value": total_delivered / (ms_max * 1e-3), "unit": "messages/s", "n_gpus": world, "steps": K, "warmup": W,
             "ms_per_step": ms_max / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "u8", "data": "synthetic",
-            "config": {"workload": f"c3: c2's workload (1M agents, 15625 groups x 64, 256-byte payloads) with agents "
-                                   f"hash-sharded (fnv1a64 % {world}) over {world} GPUs; every rank ingests 65536 group "
-                                   f"sends/step; " + ("peer-memory transport: import/fan-out kernels pull descriptors and "
-                                   "payloads from the exporting GPUs over NVLink (one-element all-reduce as barrier)"
-                                   if transport == "peer" else "wire batches all-gathered over NCCL/NVLink") +
-                                   "; each shard drains its agents",
+            "config": {"workload": workload_c3(world),
                        "transport": transport,
+                       "transport_detail": ("peer memory: import/fan-out kernels pull descriptors and payloads from the "
+                                            "exporting GPUs over NVLink" if transport == "peer"
+                                            else "wire batches all-gathered over NCCL/NVLink"),
+                       "timed_region": "exchange barrier + import (localize, fan-out, index) + receive; the wire batches "
+                                       "are exported to HBM before the timed region (device-resident inputs, like N=1's "
+                                       "staged batches); the export (host descriptor build + H2D) is inside `e2e` only",
                        "l2": "inputs larger than L2 (each shard writes and reads back ~1.2 GB of records per step)",
                        "parallelism": f"shard{world}", "ring_slots": ring_slots},
             "clocks": clk,

@@ -9,8 +9,8 @@ ROOT = Path(__file__).resolve().parents[1]
 
 
 def test_reference_arm_line():
-    p = subprocess.run([sys.executable, str(ROOT / "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "1"],
-                       capture_output=True, text=True, timeout=600, cwd=str(ROOT))
+    p = subprocess.run([sys.executable, str(ROOT / "bench.py"), "--impl", "reference", "--steps", "2", "--warmup", "3",
+                        "--ref-budget", "6"], capture_output=True, text=True, timeout=900, cwd=str(ROOT))
     assert p.returncode == 0, p.stderr[-2000:]
     lines = [ln for ln in p.stdout.splitlines() if ln.strip()]
     assert len(lines) == 1                                   # exactly one JSON line on stdout
@@ -20,7 +20,18 @@ def test_reference_arm_line():
     cb = d["cpu_baseline"]
     assert cb["kind"] == "port" and cb["cores"] >= 1 and cb["value"] == d["value"] and "sample" in cb
     assert d["e2e"] == {"value": d["value"], "unit": "messages/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
-    assert "workload" in d["config"] and d["data"] == "synthetic" and d["dtype"] == "u8"
+    assert d["data"] == "synthetic" and d["dtype"] == "u8"
+    # same workload wording and step accounting as the GPU arm (the driver compares them)
+    sys.path.insert(0, str(ROOT))
+    import bench
+    assert d["config"]["workload"] == bench.WORKLOAD_C2 and d["steps"] == 2 and d["warmup"] == 3
+    ref = d["cpu_baseline_reference"]
+    from oracle import ref_loader
+    if ref_loader.reference_available():                     # the reference's own class, timed on one core
+        assert ref["kind"] == "reference" and ref["cores"] == 1 and ref["c1"]["messages"] == 1000
+        assert ref["reduced_c2"]["value"] > 0 and ref["value"] == ref["reduced_c2"]["value"]
+    else:
+        assert ref is None
 
 
 def test_reference_arm_other_ranks_exit_quietly():

@@ -361,3 +361,163 @@ def test_many_narrow_sends_with_empty_shares_and_empty_payloads(variant):
     for s in shards:
         assert s.stats()["ring_overflow"] == 0
         s.close()
+
+
+# ------------------------------------------------------------------------------------------------
+# flag-synchronised, host-asynchronous import (sdb_import_wire_ptrs_async): shards emulated on ONE GPU, every shard
+# with its own stream, synchronised only through the ready / done counters at the end of the export buffers
+# ------------------------------------------------------------------------------------------------
+def _async_cluster(world, A, G, S, groups, max_payload=256, **kw):
+    from swarmdb_b200._native import Shard
+    from swarmdb_b200.sharded import shard_map_numbered
+    smap = shard_map_numbered("agent_", 7, A, world)
+    shards = []
+    for r in range(world):
+        s = Shard(max_agents=A, max_groups=G, ring_slots=1024, arena_bytes=kw.get("arena_bytes", 1 << 27), max_batch_sends=S,
+                  max_batch_payload=S * max_payload + 64, shard_id=r, num_shards=world, max_recv_records=1 << 18,
+                  max_payload_bytes=max_payload, list_pool_entries=1 << 16)
+        s.set_agent_shards(smap)
+        for g, m in enumerate(groups):
+            s.create_group(g, m)
+        shards.append(s)
+    wb = shards[0].wire_bytes(S, S * max_payload + 64 + 4 * 4096)
+    bufs = [[shards[r].wire_alloc(wb)[0] for r in range(world)] for _ in range(2)]      # bufs[parity][rank]
+    return smap, shards, wb, bufs
+
+
+@pytest.mark.parametrize("world", [1, 2, 4])
+def test_async_import_group_traffic_equals_single_queue(world):
+    """The fast shape (exclusive groups, payloads <= 512 B): the import is placed entirely on the device - fused
+    localize + span fan-out + group-parallel index build - and the host never learns the arena position in between."""
+    from oracle.cpu_ref import CpuOracle
+    rng = np.random.default_rng(300 + world)
+    A, G, F, S = 4096, 64, 64, 500
+    perm = rng.permutation(A)
+    groups = [perm[g * F:(g + 1) * F] for g in range(G)]
+    smap, shards, wb, bufs = _async_cluster(world, A, G, S, groups)
+    oracle = CpuOracle(A, G)
+    for g, m in enumerate(groups):
+        oracle.create_group(g, m)
+    all_agents = np.arange(A, dtype=np.uint32)
+    for step in range(1, 7):
+        par = step & 1
+        for r in range(world):                            # every rank ingests its own slice, in rank order
+            n = S if (step, r) != (3, world - 1) else 0     # an empty export once
+            sender = rng.integers(0, A, n); grp = rng.integers(0, G, n)
+            prio = rng.integers(0, 4, n); typ = rng.integers(0, 7, n)
+            lens, off, buf = _payloads(rng, max(n, 1), 256)
+            lens, off = lens[:n], off[:n]
+            ts = rng.random(n)
+            if step > 2:
+                shards[r].wire_wait_done(bufs[par], wb, step - 2)
+            shards[r].export_group_batch(sender, grp, prio, typ, lens, off, buf, bufs[par][r], wb, ts)
+            shards[r].wire_publish(bufs[par][r], wb, step)
+            if n:
+                oracle.send_group_batch(sender, grp, prio, typ, lens, off, buf, ts)
+        for s in shards:
+            s.import_wire_ptrs_async(bufs[par], wb, step)
+        k = [3, 1000, 2, 1000, 1000, 1000][step - 1]
+        merged = {}
+        for r, s in enumerate(shards):
+            local = np.nonzero(smap == r)[0].astype(np.uint32)
+            merged.update(_per_agent(*s.receive_batch(local, k), local))
+        want = _per_agent(*oracle.receive_batch(all_agents, k, rec_cap=1 << 18), all_agents)
+        for a in range(A):
+            assert merged[a] == want[a], (step, a)
+    assert len({s.stats()["next_seq"] for s in shards}) == 1 and shards[0].stats()["next_seq"] == oracle.next_seq
+    for s in shards:
+        st = s.stats()
+        assert st["ring_overflow"] == 0 and st["enqueued"] == st["delivered"]
+        s.close()
+
+
+def test_async_import_mixed_traffic_and_direct_sends_in_between():
+    """Point-to-point and broadcast sends inside asynchronously imported batches (their ring entries go through the
+    commit sort, driven by the device-side batch record), interleaved with ordinary direct sends on a 1-shard handle:
+    host and device counters hand over to each other in both directions."""
+    from oracle.cpu_ref import CpuOracle
+    from tests.fake_shard import OracleShard
+    rng = np.random.default_rng(41)
+    world, A, G, S = 2, 600, 6, 150
+    perm = rng.permutation(A)
+    groups = [perm[g * 64:(g + 1) * 64] for g in range(G)]
+    smap, shards, wb, bufs = _async_cluster(world, A, G, S, groups, max_payload=128)
+    ref = OracleShard(A, G, 0, 1)
+    for g, m in enumerate(groups):
+        ref.create_group(g, m)
+    ref_bytes = ref.wire_bytes(S, S * 128 + 8 * 4 * 200 + 4096)
+    ref_wire = np.zeros(world * ref_bytes, np.uint8)
+    all_agents = np.arange(A, dtype=np.uint32)
+    for step in range(1, 5):
+        par = step & 1
+        for r in range(world):
+            n = S
+            kind = rng.integers(0, 3, n).astype(np.uint8)
+            sender = rng.integers(0, A, n)
+            lists = [rng.choice(A, size=int(rng.integers(0, 100)), replace=False) for _ in range(4)]
+            lo = np.zeros(5, np.uint64); lo[1:] = np.cumsum([len(x) for x in lists])
+            li = np.concatenate(lists).astype(np.uint32)
+            target = np.where(kind == 0, rng.integers(0, A, n), np.where(kind == 1, rng.integers(0, G, n), rng.integers(0, 4, n)))
+            prio = rng.integers(0, 4, n); typ = rng.integers(0, 7, n)
+            lens = rng.integers(0, 129, n).astype(np.uint16)
+            off = np.arange(n, dtype=np.uint64) * 128
+            buf = rng.integers(48, 123, n * 128 + 64).astype(np.uint8)
+            ts = rng.random(n)
+            if step > 2:
+                shards[r].wire_wait_done(bufs[par], wb, step - 2)
+            shards[r].export_mixed_batch(sender, kind, target, lo, li, prio, typ, lens, off, buf, bufs[par][r], wb, ts)
+            shards[r].wire_publish(bufs[par][r], wb, step)
+            ref.export_mixed_batch(sender, kind, target, lo, li, prio, typ, lens, off, buf,
+                                   ref_wire[r * ref_bytes:(r + 1) * ref_bytes], ref_bytes, ts)
+        for s in shards:
+            s.import_wire_ptrs_async(bufs[par], wb, step)
+        ref.import_wire_batches(world, ref_wire, ref_bytes)
+        k = [2, 1000, 5, 1000][step - 1]
+        for flags in ((1,) if step == 2 else (0,)):
+            merged = {}
+            for r, s in enumerate(shards):
+                local = np.nonzero(smap == r)[0].astype(np.uint32)
+                merged.update(_per_agent(*s.receive_batch(local, k, flags), local))
+            want = _per_agent(*ref.o.receive_batch(all_agents, k, flags, rec_cap=1 << 18), all_agents)
+            for a in range(A):
+                assert merged[a] == want[a], (step, a)
+    for s in shards:
+        st = s.stats()
+        assert st["ring_overflow"] == 0 and st["next_seq"] == ref.o.next_seq
+        s.close()
+
+
+def test_async_import_that_does_not_fit_is_dropped_whole_and_reported():
+    """Arena too small for an import: nothing of it is delivered, earlier traffic is intact, and the next
+    host-synchronising call reports SDB_EARENA_FULL (never a silent drop)."""
+    from swarmdb_b200._native import SdbError
+    rng = np.random.default_rng(9)
+    A, G, F, S = 1024, 16, 64, 200
+    perm = rng.permutation(A)
+    groups = [perm[g * F:(g + 1) * F] for g in range(G)]
+    smap, shards, wb, bufs = _async_cluster(1, A, G, S, groups, arena_bytes=1 << 22)      # 4 MiB arena: ~1.1 imports of this size
+    s = shards[0]
+
+    def export(step):
+        sender = rng.integers(0, A, S); grp = rng.integers(0, G, S)
+        lens = np.full(S, 256, np.uint16); off = np.arange(S, dtype=np.uint64) * 256
+        buf = rng.integers(48, 123, S * 256 + 64).astype(np.uint8)
+        s.export_group_batch(sender, grp, None, None, lens, off, buf, bufs[step & 1][0], wb)
+        s.wire_publish(bufs[step & 1][0], wb, step)
+    export(1)
+    s.import_wire_ptrs_async(bufs[1], wb, 1)
+    first = s.stats()["enqueued"]
+    assert first > 0
+    export(2)
+    s.import_wire_ptrs_async(bufs[0], wb, 2)              # the first import is still unconsumed: this one cannot fit
+    with pytest.raises(SdbError) as ei:
+        s.stats()
+    assert ei.value.code == -5
+    st = s.stats()                                         # reported once; the queue keeps working
+    assert st["enqueued"] == first
+    cnt, hdr, _ = s.receive_batch(np.arange(A, dtype=np.uint32), 1000)
+    assert len(hdr) == first
+    export(3)
+    s.import_wire_ptrs_async(bufs[1], wb, 3)              # room again after the drain
+    assert s.stats()["enqueued"] > first
+    s.close()
