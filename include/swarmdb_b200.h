@@ -216,6 +216,9 @@ int sdb_free_staged(sdb_handle h, sdb_staged_t s);
 #define SDB_RECV_ASYNC 4u               /* device-resident consumers: enqueue the receive and return at once; all host output
                                            pointers must be NULL, results stay in the buffers of sdb_last_receive_dev (valid in
                                            stream order), totals through sdb_last_receive_totals */
+#define SDB_RECV_OWNED 8u               /* sharded handles, agent_idx == NULL: the agents THIS shard owns (ascending index; count_out has
+                                           one entry per owned agent) instead of every index below the watermark - the other agents'
+                                           rings are empty here by construction, so nothing is lost and 1/num_shards of the work is done */
 int sdb_receive_batch(sdb_handle h, uint32_t n_agents, const uint32_t* agent_idx,
                       uint32_t max_messages, uint32_t flags,
                       uint32_t* count_out, sdb_msg_header* hdr_out, uint64_t hdr_cap,

@@ -25,6 +25,7 @@ NO_RECEIVER = 0xFFFFFFFF
 RECV_PRIORITY = 1
 RECV_PEEK = 2
 RECV_ASYNC = 4
+RECV_OWNED = 8
 TYPEF_JSON = 0x08
 TYPEF_EXTRAS = 0x10
 TYPE_MASK = 0x07
@@ -326,6 +327,9 @@ class Shard:
     def set_agent_shards(self, shard_of) -> None:
         s = _arr(shard_of, np.uint8)
         self._check(self._L.sdb_set_agent_shards(self._h, len(s), _p(s)))
+        full = np.full(self.max_agents, int(self.cfg.shard_id), np.uint8)
+        full[: len(s)] = s
+        self.n_owned = int((full == int(self.cfg.shard_id)).sum()) if int(self.cfg.num_shards) > 1 else None
 
     def export_group_batch(self, sender, group, prio, typ, lens, payload_off, payload, wire_dev: int, wire_cap: int,
                            ts=None) -> None:
@@ -435,7 +439,8 @@ class Shard:
         if not copy_out:
             return None, total.value, pbytes.value
         if agents is None:
-            counts = counts[: self.stats_n_agents()]
+            owned = (flags & RECV_OWNED) and getattr(self, "n_owned", None) is not None
+            counts = counts[: self.n_owned if owned else self.stats_n_agents()]
         return counts, hdr[: total.value], pay[: pbytes.value]
 
     def last_receive_totals(self):

@@ -39,7 +39,7 @@ void sdb_build_log2_table(uint32_t* tab257);
 cudaError_t sdb_launch_import_measure(const sdb_import_args*, uint32_t, uint32_t*, uint32_t*, uint32_t*, uint32_t*, uint32_t*,
                                       uint32_t*, uint32_t*, unsigned long long*, cudaStream_t, sdb_profiler*, int*);
 cudaError_t sdb_launch_import_localize(const sdb_import_args*, uint32_t, const uint32_t*, uint32_t*, cudaStream_t, sdb_profiler*, int*);
-cudaError_t sdb_launch_wire_wait(const uint32_t* const*, uint32_t, uint32_t, cudaStream_t);
+cudaError_t sdb_launch_wire_wait(const uint32_t* const*, uint32_t, uint32_t, cudaStream_t, const void* const*, sdb_wire_header*);
 cudaError_t sdb_launch_wire_set(uint32_t*, uint32_t, cudaStream_t);
 cudaError_t sdb_launch_import_fused(const sdb_import2_args*, cudaStream_t, sdb_profiler*, int*);
 cudaError_t sdb_launch_arena_floor_cur(const sdb_dev_view*, uint32_t, sdb_cursor*, cudaStream_t);
@@ -105,13 +105,14 @@ struct sdb_ctx {
   sdb_src_tab* xs_tab = nullptr;
   uint8_t* xs_meta = nullptr; uint64_t xs_meta_stride = 0;   // local copies of remote headers + descriptors
   uint8_t* shard_of_dev = nullptr;
+  uint32_t* owned_dev = nullptr; uint32_t n_owned = 0;     // agents this shard owns, ascending (SDB_RECV_OWNED)
   // asynchronous import: device-resident twin of {arena_tail, arena_floor, next_seq} + one import's placement
   sdb_cursor* cursor_dev = nullptr; sdb_batch_base* bb_dev = nullptr;
   sdb_cursor* cursor_host = nullptr;          // pinned
   bool host_stale = false;                     // the device cursor moved (async import): host counters must be refreshed first
   bool dev_stale = true;                       // the host counters moved: push them before the next async import
   uint32_t* xs_gs_off_src = nullptr; uint32_t* xs_gs_idx_src = nullptr; uint32_t* xs_first = nullptr;
-  unsigned long long* xs_lb = nullptr;
+  unsigned long long* xs_lb = nullptr; sdb_wire_header* xs_hdrs = nullptr;
   uint8_t* wire_host = nullptr;                // pinned: header + descriptors of an export
   sdb_wire_header* hdrs_host = nullptr;        // pinned [num_shards]
   cudaEvent_t staging_free = nullptr;    // previous H2D of pinned staging has completed
@@ -627,7 +628,7 @@ int sdb_create(const sdb_config* cfg, sdb_handle* out) {
     CUDA_TRY(h, dmalloc(&h->xs_tab, 1));
     CUDA_TRY(h, dmalloc(&h->xs_gs_off_src, G1 * c.num_shards)); CUDA_TRY(h, dmalloc(&h->xs_gs_idx_src, n));
     CUDA_TRY(h, dmalloc(&h->xs_first, SDB_MAX_SRC + 1)); CUDA_TRY(h, dmalloc(&h->xs_lb, sdb_lb_words(static_cast<uint32_t>(n / 256 + 2)) + 4));
-    CUDA_TRY(h, dmalloc(&h->cursor_dev, 1)); CUDA_TRY(h, dmalloc(&h->bb_dev, 1));
+    CUDA_TRY(h, dmalloc(&h->cursor_dev, 1)); CUDA_TRY(h, dmalloc(&h->bb_dev, 1)); CUDA_TRY(h, dmalloc(&h->xs_hdrs, SDB_MAX_SRC));
     CUDA_TRY(h, cudaMemset(h->cursor_dev, 0, sizeof(sdb_cursor))); CUDA_TRY(h, cudaMemset(h->bb_dev, 0, sizeof(sdb_batch_base)));
     CUDA_TRY(h, cudaHostAlloc(reinterpret_cast<void**>(&h->cursor_host), sizeof(sdb_cursor), cudaHostAllocDefault));
     std::memset(h->cursor_host, 0, sizeof(sdb_cursor));
@@ -651,7 +652,7 @@ int sdb_destroy(sdb_handle h) {
   cudaSetDevice(h->cfg.device);
   if (h->stream) cudaStreamSynchronize(h->stream);
   void* dev[] = {h->arena, h->ring_hdr, h->ring, h->members, h->ctr, h->gexcl_dev, h->rx_rec_off, h->rx_lb,
-                 h->xs_gs_off_src, h->xs_gs_idx_src, h->xs_first, h->xs_lb, h->cursor_dev, h->bb_dev,
+                 h->xs_gs_off_src, h->xs_gs_idx_src, h->xs_first, h->xs_lb, h->cursor_dev, h->bb_dev, h->xs_hdrs, h->owned_dev,
                  h->scratch.descs_dev, h->scratch.payload_dev, h->scratch.list_dev, h->scratch.gs_off_dev,
                  h->scratch.gs_idx_dev, h->memb_off_dev, h->memb_grp_dev, h->memb_pos_dev, h->member_pos_dev,
                  h->lstart_dev, h->lcount_dev, h->xs_w, h->xs_w_local, h->xs_w_tops, h->xs_gs_cnt, h->xs_gs_local,
@@ -845,6 +846,13 @@ int sdb_set_agent_shards(sdb_handle h, uint32_t n, const uint8_t* shard_of) {
   if (h->sharded) h->n_agents = h->cfg.max_agents;   // receivers are named by other ranks: sweeps cover the whole index space
   CUDA_TRY(h, cudaStreamSynchronize(h->stream));
   CUDA_TRY(h, cudaMemcpy(h->shard_of_dev, h->shard_of.data(), h->cfg.max_agents, cudaMemcpyHostToDevice));
+  {
+    std::vector<uint32_t> owned;
+    for (uint32_t i = 0; i < h->cfg.max_agents; ++i) if (h->shard_of[i] == h->cfg.shard_id) owned.push_back(i);
+    if (!h->owned_dev) CUDA_TRY(h, dmalloc(&h->owned_dev, h->cfg.max_agents));
+    if (!owned.empty()) CUDA_TRY(h, cudaMemcpy(h->owned_dev, owned.data(), owned.size() * sizeof(uint32_t), cudaMemcpyHostToDevice));
+    h->n_owned = static_cast<uint32_t>(owned.size());
+  }
   // groups created earlier are re-filtered against the new ownership map
   bool any = false;
   for (uint32_t g = 0; g < h->cfg.max_groups; ++g) if (h->gdefined[g]) { localize_group(h, g); any = true; }
@@ -1099,7 +1107,7 @@ int sdb_wire_wait_done(sdb_handle h, uint32_t n_src, const void* const* wire_ptr
   if (!h || !wire_ptrs || n_src == 0 || n_src > SDB_MAX_SRC || wire_bytes < sizeof(sdb_wire_ctrl)) return SDB_EINVAL;
   const uint32_t* flags[SDB_MAX_SRC];
   for (uint32_t k = 0; k < n_src; ++k) flags[k] = ctrl_word(wire_ptrs[k], wire_bytes, 1);
-  CUDA_TRY(h, sdb_launch_wire_wait(flags, n_src, step, h->stream));
+  CUDA_TRY(h, sdb_launch_wire_wait(flags, n_src, step, h->stream, nullptr, nullptr));
   h->launches += 1;
   return SDB_OK;
 }
@@ -1114,7 +1122,7 @@ int sdb_import_wire_ptrs_async(sdb_handle h, uint32_t n_src, const void* const* 
   const uint32_t* ready[SDB_MAX_SRC];
   for (uint32_t k = 0; k < n_src; ++k) ready[k] = ctrl_word(wire_ptrs[k], wire_bytes, 0);
   const int pw = sdb_prof_begin(&h->prof, SDB_PK_XWAIT, h->stream);
-  CUDA_TRY(h, sdb_launch_wire_wait(ready, n_src, step, h->stream));
+  CUDA_TRY(h, sdb_launch_wire_wait(ready, n_src, step, h->stream, wire_ptrs, h->xs_hdrs));
   sdb_prof_end(&h->prof, pw, h->stream);
   h->launches += 1;
   uint32_t* my_done = ctrl_word(wire_ptrs[h->cfg.shard_id < n_src ? h->cfg.shard_id : 0], wire_bytes, 1);
@@ -1138,6 +1146,7 @@ int sdb_import_wire_ptrs_async(sdb_handle h, uint32_t n_src, const void* const* 
   a.descs = h->xs_descs; a.gs_off_src = h->xs_gs_off_src; a.gs_idx_src = h->xs_gs_idx_src; a.first = h->xs_first;
   a.tmp_list = h->scratch.list_dev; a.list_cap = static_cast<uint32_t>(std::min<uint64_t>(h->cfg.list_pool_entries, 0x7FFFFFF0ull));
   a.lb = h->xs_lb; a.cur = h->cursor_dev; a.bb = h->bb_dev; a.arena_grans = h->arena_grans;
+  a.hdrs = h->xs_hdrs; a.commit_count = h->rx_big_count + 1;
   int nl = 1;
   cudaError_t e = sdb_launch_import_fused(&a, h->stream, &h->prof, &nl);
   const uint32_t n_cap = n_src * h->cfg.max_batch_sends;
@@ -1258,7 +1267,8 @@ int sdb_receive_batch(sdb_handle h, uint32_t n_agents, const uint32_t* agent_idx
   if (!h) return SDB_EINVAL;
   if (total_out) *total_out = 0;
   if (payload_bytes_out) *payload_bytes_out = 0;
-  if (!agent_idx) n_agents = h->n_agents;
+  const bool owned = (flags & SDB_RECV_OWNED) && !agent_idx && h->sharded && h->owned_dev;
+  if (!agent_idx) n_agents = owned ? h->n_owned : h->n_agents;
   if (n_agents == 0 || max_messages == 0) return SDB_OK;
   if (n_agents > h->cfg.max_agents) return fail(h, SDB_EINVAL, "n_agents > max_agents");
   if (agent_idx) {
@@ -1305,7 +1315,7 @@ int sdb_receive_batch(sdb_handle h, uint32_t n_agents, const uint32_t* agent_idx
   const bool async = (flags & SDB_RECV_ASYNC) != 0;
   if (async && (count_out || hdr_out || payload_out)) return fail(h, SDB_EINVAL, "SDB_RECV_ASYNC takes no host output buffers");
   sdb_recv_args r{};
-  r.agent_idx = agent_idx ? h->rx_agent : nullptr; r.n = n_agents; r.max_messages = max_messages;
+  r.agent_idx = agent_idx ? h->rx_agent : (owned ? h->owned_dev : nullptr); r.n = n_agents; r.max_messages = max_messages;
   r.flags = flags & (SDB_RECV_PRIORITY | SDB_RECV_PEEK);
   r.cnt = h->rx_cnt; r.rec_local = h->rx_rec_local; r.rec_tops = h->rx_rec_tops;
   r.rec_off = h->rx_rec_off; r.plan = h->rx_plan; r.lb = h->rx_lb;

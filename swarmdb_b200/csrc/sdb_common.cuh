@@ -242,6 +242,8 @@ struct sdb_import2_args {
   unsigned long long* lb;             // [tiles + 2]: look-back status words, tile ticket (zeroed before the launch)
   sdb_cursor* cur; sdb_batch_base* bb;
   unsigned long long arena_grans;
+  const sdb_wire_header* hdrs;        // [n_src] local copies of the wire headers (made by k_wire_wait)
+  uint32_t* commit_count;             // reset here for the commit sort that follows the fan-out
 };
 
 // ---- optional per-kernel timing with CUDA events on the launching stream (bench / roofline) ----

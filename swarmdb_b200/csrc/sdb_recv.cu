@@ -906,10 +906,12 @@ static cudaError_t launch_gather(const sdb_dev_view* v, const sdb_recv_args* r, 
   if (use_tma && max_rec_bytes <= 544 && bound >= 4096) {
     constexpr int WARPS = 4;
     const size_t smem = static_cast<size_t>(WARPS) * 2u * 32u * max_rec_bytes;
-    uint32_t per_sm = static_cast<uint32_t>((200u * 1024u) / (smem + 1024));
+    uint32_t per_sm = static_cast<uint32_t>((226u * 1024u) / (smem + 1024 + 128));
     if (per_sm < 1) per_sm = 1;
     if (per_sm > 8) per_sm = 8;
-    uint64_t grid = static_cast<uint64_t>(sm_count) * per_sm * 4;                  // a few waves: the tail evens out
+    static int waves = -1;
+    if (waves < 0) { const char* e = getenv("SDB_GATHER_WAVES"); waves = e ? atoi(e) : 8; if (waves < 1) waves = 1; }
+    uint64_t grid = static_cast<uint64_t>(sm_count) * per_sm * waves;              // a few waves: the tail evens out
     const uint64_t need = (bound + WARPS * 32 - 1) / (WARPS * 32);
     if (grid > need) grid = need;
     k_recv_gather_tma<WARPS><<<static_cast<uint32_t>(grid), WARPS * 32, smem, stream>>>(*v, *r, packed_inv, max_rec_bytes);

@@ -903,15 +903,8 @@ k_pull_index(sdb_dev_view v, sdb_pull_view pv, const sdb_send_desc* __restrict__
 // relative to the batch base (all of them belong to this batch), clamp an overflowed tail,
 // publish ctail = tail.
 // ------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256)
-k_commit(sdb_dev_view v, uint32_t n_agents, uint32_t batch_base32, uint32_t* __restrict__ big_list,
-         uint32_t* __restrict__ big_count, const sdb_batch_base* __restrict__ bb) {
-  const uint32_t a = blockIdx.x * blockDim.x + threadIdx.x;
-  if (a >= n_agents) return;
-  if (bb) {                                      // asynchronous import: nothing to sort unless it carried p2p / broadcast sends
-    if (bb->skip || bb->n_other == 0) return;
-    batch_base32 = static_cast<uint32_t>(bb->arena_base);
-  }
+__device__ __forceinline__ void commit_agent(const sdb_dev_view& v, uint32_t a, uint32_t batch_base32,
+                                             uint32_t* __restrict__ big_list, uint32_t* __restrict__ big_count) {
   const uint4 hd = *reinterpret_cast<const uint4*>(v.ring_hdr + a);
   uint32_t tail = hd.y;
   const uint32_t head = hd.x, ct = hd.z;
@@ -957,6 +950,20 @@ k_commit(sdb_dev_view v, uint32_t n_agents, uint32_t batch_base32, uint32_t* __r
     }
   }
   v.ring_hdr[a].ctail = tail;
+}
+
+
+// grid-stride over the agents: with a device-side batch record (asynchronous import) the grid is small and every
+// thread returns after ONE load when the import carried no point-to-point / broadcast sends
+__global__ void __launch_bounds__(256)
+k_commit(sdb_dev_view v, uint32_t n_agents, uint32_t batch_base32, uint32_t* __restrict__ big_list,
+         uint32_t* __restrict__ big_count, const sdb_batch_base* __restrict__ bb) {
+  if (bb) {
+    if (bb->skip || bb->n_other == 0) return;
+    batch_base32 = static_cast<uint32_t>(bb->arena_base);
+  }
+  for (uint32_t a = blockIdx.x * blockDim.x + threadIdx.x; a < n_agents; a += gridDim.x * blockDim.x)
+    commit_agent(v, a, batch_base32, big_list, big_count);
 }
 
 // one CTA per agent that received more than 16 records in the batch: bitonic sort of (arena position, meta)
@@ -1123,9 +1130,11 @@ extern "C" cudaError_t sdb_launch_commit(const sdb_dev_view* v, uint32_t n_agent
                                          cudaStream_t stream, sdb_profiler* prof, const sdb_batch_base* bb) {
   if (n_agents == 0) return cudaSuccess;
   const int pi = sdb_prof_begin(prof, SDB_PK_COMMIT, stream);
-  cudaMemsetAsync(big_count, 0, sizeof(uint32_t), stream);
-  k_commit<<<(n_agents + 255) / 256, 256, 0, stream>>>(*v, n_agents, batch_base32, big_list, big_count, bb);
-  uint32_t bg = static_cast<uint32_t>(sm_count) * 4u;
+  if (!bb) cudaMemsetAsync(big_count, 0, sizeof(uint32_t), stream);     // asynchronous import: k_import_fused reset it
+  uint32_t cg = (n_agents + 255) / 256;
+  if (bb && cg > static_cast<uint32_t>(sm_count) * 8u) cg = static_cast<uint32_t>(sm_count) * 8u;
+  k_commit<<<cg, 256, 0, stream>>>(*v, n_agents, batch_base32, big_list, big_count, bb);
+  uint32_t bg = static_cast<uint32_t>(sm_count) * (bb ? 1u : 4u);
   if (bg > n_agents) bg = n_agents;
   k_commit_big<<<bg, 256, 0, stream>>>(*v, batch_base32, big_list, big_count, bb);
   sdb_prof_end(prof, pi, stream);

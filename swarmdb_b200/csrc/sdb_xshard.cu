@@ -242,7 +242,7 @@ __device__ __forceinline__ uint32_t ld_volatile_u32(const uint32_t* p) {
   return x;
 }
 
-struct sdb_wait_args { const uint32_t* flag[SDB_MAX_SRC]; uint32_t n; };
+struct sdb_wait_args { const uint32_t* flag[SDB_MAX_SRC]; const uint8_t* wire[SDB_MAX_SRC]; sdb_wire_header* hdr_out; uint32_t n; };
 __global__ void k_wire_wait(sdb_wait_args w, uint32_t step) {
   const uint32_t lane = threadIdx.x;
   if (lane < w.n) {
@@ -259,6 +259,14 @@ __global__ void k_wire_wait(sdb_wait_args w, uint32_t step) {
   }
   __syncwarp();
   __threadfence_system();
+  // the sources' 128-byte wire headers, fetched once here (8 x 16 bytes per source, remote ones over NVLink) so that
+  // the thousands of blocks of the import kernel read them from local memory
+  if (w.hdr_out) {
+    for (uint32_t e = lane; e < w.n * 8u; e += 32) {
+      const uint32_t s = e >> 3, k = e & 7u;
+      reinterpret_cast<uint4*>(w.hdr_out + s)[k] = __ldcv(reinterpret_cast<const uint4*>(w.wire[s]) + k);
+    }
+  }
 }
 __global__ void k_wire_set(uint32_t* flag, uint32_t step) {
   __threadfence_system();                      // everything this stream wrote before is visible to peers first
@@ -278,9 +286,9 @@ k_import_fused(sdb_import2_args a, uint32_t tiles_cap) {
   __shared__ unsigned long long s_wa[8], s_wb[8], s_ba, s_bb;
   const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   if (tid == 0) s_tile = atomicAdd(reinterpret_cast<unsigned int*>(a.lb + sdb_lb_words(tiles_cap) - 2), 1u);
-  // ---- every block reads the wire headers itself (128 bytes each; remote ones over NVLink)
+  // ---- every block reads the wire headers itself (128 bytes each, from the local copies k_wire_wait made)
   if (tid < a.n_src) {
-    const sdb_wire_header* h = reinterpret_cast<const sdb_wire_header*>(a.wire[tid]);
+    const sdb_wire_header* h = a.hdrs + tid;                 // local copies made by k_wire_wait
     const uint4* hq = reinterpret_cast<const uint4*>(h);
     union { uint4 q[8]; sdb_wire_header hd; } u;
 #pragma unroll
@@ -310,22 +318,35 @@ k_import_fused(sdb_import2_args a, uint32_t tiles_cap) {
   const uint32_t n_total = s_first[a.n_src];
   const uint32_t n_tiles = n_total ? (n_total + SDB_IMP_TILE - 1) / SDB_IMP_TILE : 1u;     // tiles that take part in the scan
 
-  // ---- copies of the sources' group buckets (grid-stride over all blocks; coalesced remote reads)
+  // ---- copies of the sources' group buckets: one flat element space over (source, offsets | indices), every thread
+  // issues all its (remote, coalesced) loads before the first store so the NVLink round trips overlap
   {
     const uint32_t G1 = a.max_groups + 1;
+    const uint32_t per_src = G1 + a.max_sends;
     const size_t nthreads = static_cast<size_t>(gridDim.x) * blockDim.x;
+    const size_t E = static_cast<size_t>(a.n_src) * per_src;
     const size_t gt = static_cast<size_t>(tile) * blockDim.x + tid;
-    for (uint32_t s = 0; s < a.n_src; ++s) {
-      uint32_t* dst_o = a.gs_off_src + static_cast<size_t>(s) * G1;
-      if (s_gso_off[s]) {
-        const uint32_t* src_o = reinterpret_cast<const uint32_t*>(a.wire[s] + s_gso_off[s]);
-        for (size_t i = gt; i < G1; i += nthreads) dst_o[i] = src_o[i];
-        const uint32_t* src_i = reinterpret_cast<const uint32_t*>(a.wire[s] + s_gsi_off[s]);
-        uint32_t* dst_i = a.gs_idx_src + static_cast<size_t>(s) * a.max_sends;
-        for (size_t i = gt; i < s_ngs[s]; i += nthreads) dst_i[i] = src_i[i];
-      } else {
-        for (size_t i = gt; i < G1; i += nthreads) dst_o[i] = 0u;                          // no usable buckets: empty
+    constexpr int UN = 4;
+    for (size_t e0 = gt; e0 < E; e0 += nthreads * UN) {
+      uint32_t val[UN]; uint32_t* dst[UN];
+#pragma unroll
+      for (int u = 0; u < UN; ++u) {
+        const size_t e = e0 + static_cast<size_t>(u) * nthreads;
+        dst[u] = nullptr; val[u] = 0;
+        if (e < E) {
+          const uint32_t s = static_cast<uint32_t>(e / per_src), i = static_cast<uint32_t>(e % per_src);
+          const bool usable = s_gso_off[s] != 0;
+          if (i < G1) {
+            dst[u] = a.gs_off_src + static_cast<size_t>(s) * G1 + i;
+            if (usable) val[u] = reinterpret_cast<const uint32_t*>(a.wire[s] + s_gso_off[s])[i];
+          } else if (usable && i - G1 < s_ngs[s]) {
+            dst[u] = a.gs_idx_src + static_cast<size_t>(s) * a.max_sends + (i - G1);
+            val[u] = reinterpret_cast<const uint32_t*>(a.wire[s] + s_gsi_off[s])[i - G1];
+          }
+        }
       }
+#pragma unroll
+      for (int u = 0; u < UN; ++u) if (dst[u]) *dst[u] = val[u];
     }
     if (tile == 0 && tid <= a.n_src) a.first[tid] = s_first[tid];
   }
@@ -400,6 +421,7 @@ k_import_fused(sdb_import2_args a, uint32_t tiles_cap) {
         sdb_batch_base* b = a.bb;
         b->arena_base = tail; b->seq_base = c->next_seq; b->n_total = n_total; b->n_other = n_other; b->skip = skip;
         b->max_padlen = maxpad; b->total_grans = need; b->total_recs = total_recs;
+        if (a.commit_count) *a.commit_count = 0u;                          // worklist of the commit sort that follows
         if (!skip) {
           c->arena_tail = tail + need;
           const unsigned long long ns = c->next_seq + (explicit_end ? 0ull : total_recs);
@@ -448,10 +470,12 @@ k_import_fused(sdb_import2_args a, uint32_t tiles_cap) {
   o4[0] = i4[0]; o4[1] = i4[1]; o4[2] = i4[2]; o4[3] = i4[3];
 }
 
-extern "C" cudaError_t sdb_launch_wire_wait(const uint32_t* const* flags, uint32_t n, uint32_t step, cudaStream_t stream) {
+// wires / hdr_out (nullable): also copy each source's wire header to hdr_out[i] once the flags are up
+extern "C" cudaError_t sdb_launch_wire_wait(const uint32_t* const* flags, uint32_t n, uint32_t step, cudaStream_t stream,
+                                            const void* const* wires, sdb_wire_header* hdr_out) {
   sdb_wait_args w{};
-  w.n = n;
-  for (uint32_t i = 0; i < n && i < SDB_MAX_SRC; ++i) w.flag[i] = flags[i];
+  w.n = n; w.hdr_out = wires ? hdr_out : nullptr;
+  for (uint32_t i = 0; i < n && i < SDB_MAX_SRC; ++i) { w.flag[i] = flags[i]; w.wire[i] = wires ? static_cast<const uint8_t*>(wires[i]) : nullptr; }
   k_wire_wait<<<1, 32, 0, stream>>>(w, step);
   return cudaGetLastError();
 }

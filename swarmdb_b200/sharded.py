@@ -219,7 +219,7 @@ def run_sharded_bench(args, rank: int, world: int, local_rank: int, wl):
     import torch
     import torch.distributed as dist
 
-    from ._native import HDR_DTYPE, Shard
+    from ._native import HDR_DTYPE, RECV_OWNED, Shard
 
     dev = torch.device("cuda", local_rank)
     stream = torch.cuda.Stream()
@@ -290,8 +290,8 @@ def run_sharded_bench(args, rank: int, world: int, local_rank: int, wl):
             ex.import_all()
             if timed:
                 evs[3].record(stream)
-            # non-local agents have empty rings on this shard: draining "all" needs no index upload
-            shard.receive_batch(None, 100, 0, copy_out=False, wait=False)    # enqueued only: counted on the device
+            # SDB_RECV_OWNED: the device-resident list of the agents this shard owns (no index upload, 1/world of the slots)
+            shard.receive_batch(None, 100, RECV_OWNED, copy_out=False, wait=False)    # enqueued only: counted on the device
             if timed:
                 evs[4].record(stream)
                 phase_ev.append(evs)
@@ -331,7 +331,7 @@ def run_sharded_bench(args, rank: int, world: int, local_rank: int, wl):
 
         def e2e_step(i):
             ex.step(*pinned[i % n_distinct])
-            _, hdr, _ = shard.receive_batch(None, 100, 0, copy_out=True, out_hdr=pin_hdr, out_payload=pin_pay)
+            _, hdr, _ = shard.receive_batch(None, 100, RECV_OWNED, copy_out=True, out_hdr=pin_hdr, out_payload=pin_pay)
             return len(hdr)
 
         e2e_step(0); e2e_step(1)
@@ -353,7 +353,7 @@ def run_sharded_bench(args, rank: int, world: int, local_rank: int, wl):
         p_delivered = 0
         for step in range(wl.PARITY_STEPS):
             ex.step(*wl.parity_batch(step, rank))
-            _, tt, _ = shard.receive_batch(None, 100, 0, copy_out=False)
+            _, tt, _ = shard.receive_batch(None, 100, RECV_OWNED if step % 2 == 0 else 0, copy_out=False)
             shard.digest_fold()
             p_delivered += tt
         while True:

@@ -420,7 +420,13 @@ def test_async_import_group_traffic_equals_single_queue(world):
         merged = {}
         for r, s in enumerate(shards):
             local = np.nonzero(smap == r)[0].astype(np.uint32)
-            merged.update(_per_agent(*s.receive_batch(local, k), local))
+            if step % 2 == 0 and world > 1:               # SDB_RECV_OWNED: the shard's own device-resident agent list
+                from swarmdb_b200._native import RECV_OWNED
+                res = s.receive_batch(None, k, RECV_OWNED)
+                assert len(res[0]) == len(local)
+            else:
+                res = s.receive_batch(local, k)
+            merged.update(_per_agent(*res, local))
         want = _per_agent(*oracle.receive_batch(all_agents, k, rec_cap=1 << 18), all_agents)
         for a in range(A):
             assert merged[a] == want[a], (step, a)
