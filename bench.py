@@ -294,6 +294,150 @@ def run_reference(args, rank, world):
     print(json.dumps(line), flush=True)
 
 
+# ------------------------------------------------------------------------------------ the other BASELINE configs
+def config_c1(tmp="/tmp/sdb_bench_c1"):
+    """BASELINE config 1 through the drop-in Python surface: 2 agents, 1,000 point-to-point 128-byte messages
+    (content from default_rng(1)), then agent_b drains.  Check: delivered contents == sent contents, in order."""
+    import swarmdb_b200 as sdb
+    rng = np.random.default_rng(1)
+    contents = [ALNUM[rng.integers(0, 62, 128)].tobytes().decode() for _ in range(1000)]
+    db = sdb.SwarmsDB(save_dir=tmp, auto_save=False,
+                      gpu_config=sdb.GpuConfig(max_agents=1024, ring_slots=2048, arena_bytes=1 << 26))
+    db.register_agent("agent_a"); db.register_agent("agent_b")
+    for c in contents[:50]:                                   # warm-up (allocator, first launches)
+        db.send_message("agent_a", c, "agent_b")
+    db.receive_messages("agent_b", 100)
+    clocks = ClockSampler(0); clocks.start()
+    t0 = time.perf_counter()
+    for c in contents:
+        db.send_message("agent_a", c, "agent_b")
+    t1 = time.perf_counter()
+    got = db.receive_messages("agent_b", 2000)
+    t2 = time.perf_counter()
+    clk = clocks.stop()
+    ok = [m.content for m in got] == contents and all(m.sender_id == "agent_a" for m in got)
+    db.close()
+    return {"config": "c1: 2 agents, 1k point-to-point 128-byte messages through swarmdb_b200.SwarmsDB (buffered sends, "
+                      "one flush at receive)", "unit": "messages/s",
+            "send_msgs_per_s": 1000 / (t1 - t0), "receive_msgs_per_s": 1000 / (t2 - t1), "value": 1000 / (t2 - t0),
+            "check": {"what": "delivered contents and order == sent (M:553-601)", "ok": bool(ok)}, "clocks": clk}
+
+
+def config_c4(sweeps=4):
+    """BASELINE config 4: 10,048 agents (157 groups x 64) x 10,000 pending 256-byte records each, 4 priority levels;
+    receive_batch(all agents, max_messages=100, PRIORITY).  Check: the per-agent stream digests of 8 sampled groups
+    (512 agents) after the timed sweeps against oracle/cpu_ref.c fed the same sends with the same sequence numbers."""
+    from oracle.cpu_ref import CpuOracle
+    from swarmdb_b200._native import RECV_PRIORITY, Shard
+    peak, src = hbm_peak()
+    G, F, depth, L = 157, 64, 10_000, 256
+    A = G * F
+    S = 65536
+    shard = Shard(max_agents=A, ring_slots=16384, arena_bytes=1 << 35, max_payload_bytes=L, max_groups=G,
+                  max_batch_sends=S, max_batch_payload=S * L, max_recv_records=A * 100 + 4096,
+                  max_recv_payload=(A * 100 + 4096) * L)
+    rng = np.random.default_rng(4)
+    perm = rng.permutation(A).astype(np.uint32)
+    group_of = np.empty(A, np.uint32); group_of[perm] = np.repeat(np.arange(G, dtype=np.uint32), F)
+    sample_groups = np.sort(rng.choice(G, 8, replace=False)).astype(np.uint32)
+    in_sample = np.zeros(G, bool); in_sample[sample_groups] = True
+    sample_agents = np.sort(np.concatenate([perm[g * F:(g + 1) * F] for g in sample_groups])).astype(np.uint32)
+    cpu = CpuOracle(A, G)
+    for g in range(G):
+        shard.create_group(g, perm[g * F:(g + 1) * F])
+        if in_sample[g]:
+            cpu.create_group(g, perm[g * F:(g + 1) * F])
+    cpu.digest_enable(); shard.digest_reset()
+    total_sends = G * depth
+    grp_all = np.repeat(np.arange(G, dtype=np.uint32), depth)
+    rng.shuffle(grp_all)
+    t0 = time.perf_counter()
+    for s0 in range(0, total_sends, S):
+        grp = grp_all[s0:s0 + S]
+        n = len(grp)
+        snd = rng.integers(0, A, n).astype(np.uint32)
+        bad = group_of[snd] == grp
+        while bad.any():                                      # sender outside its group: every member gets the record
+            snd[bad] = rng.integers(0, A, int(bad.sum())).astype(np.uint32)
+            bad = group_of[snd] == grp
+        prio = rng.integers(0, 4, n).astype(np.uint8)
+        lens = np.full(n, L, np.uint16)
+        off = np.arange(n, dtype=np.uint64) * L
+        pay = ALNUM[rng.integers(0, 62, n * L)]
+        base = shard.send_group_batch(snd, grp, prio, None, lens, off, pay)
+        keep = in_sample[grp]
+        if keep.any():                                        # the oracle sees only the sampled groups, same sequence numbers
+            idx = np.nonzero(keep)[0]
+            seq0 = (base + idx.astype(np.uint64) * F).astype(np.uint64)
+            cpu.send_group_seq(snd[idx], grp[idx], prio[idx], np.zeros(len(idx), np.uint8), lens[idx], off[idx], pay, seq0)
+    shard.sync()
+    load_s = time.perf_counter() - t0
+    st = shard.stats()
+    assert st["enqueued"] == A * depth and st["ring_overflow"] == 0, st
+    shard.profile(True)
+    clocks = ClockSampler(0); clocks.start()
+    wall = []
+    for _ in range(sweeps):
+        t1 = time.perf_counter()
+        _, total, _ = shard.receive_batch(None, 100, RECV_PRIORITY, copy_out=False)
+        wall.append((time.perf_counter() - t1) * 1e3)
+        assert total == A * 100
+        shard.digest_fold()
+    clk = clocks.stop()
+    prof = shard.profile_read()
+    for _ in range(sweeps):
+        cpu.receive_counts(sample_agents, 100, RECV_PRIORITY)
+    ok = bool(np.array_equal(shard.digest_read(sample_agents), cpu.digest_read(sample_agents)))
+    shard.close(); cpu.close()
+    k5_ms = sum(v[0] for k, v in prof.items() if k.startswith("recv")) / sweeps
+    alg = A * (depth * 1 + 2 * 100 * (L + 16))               # SURVEY 8d: 64,400 B per agent-call
+    return {"config": f"c4: {A} agents x {depth} pending {L}-byte records, 4 priorities, receive_batch(all, 100, PRIORITY)",
+            "preload_s": load_s, "sweep_wall_ms": wall, "p50_sweep_wall_ms": float(np.median(wall)),
+            "k5_kernels_ms_per_sweep": k5_ms,
+            "kernels_ms": {k: v[0] / v[1] for k, v in prof.items() if v[1]},
+            "per_agent_call_us": k5_ms * 1e3 / A, "value": A * 100 / (k5_ms * 1e-3), "unit": "messages/s dequeued",
+            "roofline": {"bound": "hbm", "algorithmic_bytes_per_sweep": alg, "achieved": alg / (k5_ms * 1e-3) / 1e9,
+                         "peak": peak, "unit": "GB/s", "frac": alg / (k5_ms * 1e-3) / 1e9 / peak, "peak_source": src},
+            "check": {"what": f"stream digests of {len(sample_agents)} agents (8 sampled groups) after {sweeps} priority sweeps "
+                              "== oracle/cpu_ref.c (priority desc, arrival asc; App. A rule 9)", "ok": ok},
+            "clocks": clk}
+
+
+def config_c5(n_req=1_000_000, n_backends=256):
+    """BASELINE config 5: 1M unit-cost requests over 256 backends, weights U{1..8}; both pick modes, bit-exact against
+    the oracle's sequential definition (include/swarmdb_b200.h)."""
+    from oracle.cpu_ref import CpuOracle
+    from swarmdb_b200._native import Shard
+    rng = np.random.default_rng(5)
+    w = rng.integers(1, 9, n_backends)
+    out = {"config": f"c5: {n_req} unit-cost requests over {n_backends} backends, weights U{{1..8}}, load0 = 0",
+           "unit": "picks/s", "note": "not HBM-bound: the 256-entry table lives in shared memory / L1 (SURVEY 8d)"}
+    clocks = ClockSampler(0); clocks.start()
+    ok = True
+    for mode, name in ((0, "weighted_least_load"), (1, "weighted_random")):
+        g = Shard(max_agents=16)
+        g.set_backends(w)
+        g.select_backends(1000, None, mode, 6)                   # warm-up
+        g.set_backends(w)
+        t0 = time.perf_counter()
+        picks = g.select_backends(n_req, None, mode, 6)
+        wall = time.perf_counter() - t0
+        o = CpuOracle(16)
+        o.set_backends(w)
+        t1 = time.perf_counter()
+        ref = o.select_backends(n_req, None, mode, 6)
+        cpu_s = time.perf_counter() - t1
+        same = bool(np.array_equal(picks, ref) and np.array_equal(g.backend_loads(), o.backend_loads()))
+        ok = ok and same
+        out[name] = {"picks_per_s_end_to_end": n_req / wall, "wall_ms": wall * 1e3,
+                     "cpu_oracle_picks_per_s_1_core": n_req / cpu_s, "bit_exact_vs_oracle": same}
+        g.close(); o.close()
+    out["clocks"] = clocks.stop()
+    out["value"] = out["weighted_least_load"]["picks_per_s_end_to_end"]
+    out["check"] = {"what": "picks and final loads == oracle (sequential greedy / exponential race)", "ok": ok}
+    return out
+
+
 # ------------------------------------------------------------------------------------ GPU arm
 def run_gpu(args, rank, world, local_rank):
     import torch
@@ -419,6 +563,7 @@ def run_gpu(args, rank, world, local_rank):
     shard.sync()
     probe = np.random.default_rng(99).permutation(wl.A)[:2200].astype(np.uint32)
     lat = []
+    clocks_p50 = ClockSampler(local_rank); clocks_p50.start()
     for k, a in enumerate(probe):
         ai = int(a)
         t1 = time.perf_counter()
@@ -426,6 +571,7 @@ def run_gpu(args, rank, world, local_rank):
         dt = time.perf_counter() - t1
         if k >= 200 and len(h):
             lat.append(dt * 1e6)
+    clk_p50 = clocks_p50.stop()
     p50 = float(np.percentile(lat, 50)) if lat else None
     p99 = float(np.percentile(lat, 99)) if lat else None
     shard.receive_batch(None, 100, 0, copy_out=False)          # drain the rest
@@ -493,10 +639,23 @@ def run_gpu(args, rank, world, local_rank):
                                    f"oracle/cpu_ref.c on {cores} threads"},
         "cpu_baseline_reference": reference_python_leg(args.ref_budget),
     }
-    print(json.dumps(line), flush=True)
     for s in staged:
         shard.free_staged(s)
     shard.close()
+    # ---- the other BASELINE configs, each with its own clock record and oracle check (the c2 shard is gone: c4 alone
+    # keeps 29 GB of records in HBM)
+    configs = {"c2": {"see": "top level of this line"},
+               "p50_dequeue": {"config": "one receive_batch([agent], max_messages=100) through ctypes -> kernel -> D2H with >= 1 "
+                                         "message pending, 2000 agents of the c2 queue", "p50_us": p50, "p99_us": p99,
+                               "clocks": clk_p50, "check": {"what": "every probe returned its pending records", "ok": bool(lat)}}}
+    if not args.skip_configs:
+        for name, fn in (("c1", config_c1), ("c4", config_c4), ("c5", config_c5)):
+            try:
+                configs[name] = fn()
+            except Exception as e:  # pragma: no cover  (reported in the line, never fatal for c2)
+                configs[name] = {"error": repr(e)}
+    line["configs"] = configs
+    print(json.dumps(line), flush=True)
 
 
 def main():
@@ -509,6 +668,7 @@ def main():
     ap.add_argument("--cpu-budget", type=float, default=15.0)
     ap.add_argument("--ref-budget", type=float, default=20.0,
                     help="seconds for the reference-python leg (the reference's own class on one core); 0 = skip")
+    ap.add_argument("--skip-configs", action="store_true", help="skip the c1 / c4 / c5 legs of the N=1 line")
     ap.add_argument("--no-extras", action="store_true", help="profiling runs: only the device-resident timed region")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
