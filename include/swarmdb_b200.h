@@ -321,6 +321,34 @@ int sdb_wire_wait_done(sdb_handle h, uint32_t n_src, const void* const* wire_ptr
 int sdb_wire_publish(sdb_handle h, void* wire_dev, uint64_t wire_bytes, uint32_t step);
 int sdb_import_wire_ptrs_async(sdb_handle h, uint32_t n_src, const void* const* wire_ptrs, uint64_t wire_bytes, uint32_t step);
 
+/* ---- inbox / load queries on the device: get_agent_load, get_unread_message_count (M:1026-1094), get_stats (M:973-1024)
+ * The reference answers these by walking its host dictionaries (`messages`, `agent_inbox`); the queue itself now lives
+ * in HBM, so the same questions are answered from the rings.  Mapping of the reference's fields:
+ *   inbox_size    (len(agent_inbox[a]), M:1076)            = received      records ever enqueued for the agent
+ *   unread_count  (status == DELIVERED in the inbox, M:1040) = pending       records still queued (not yet received)
+ *   READ / PROCESSED side                                   = received - pending
+ * sdb_agent_loads fills one sdb_agent_load per listed agent (agent_idx == NULL: agents 0..n-1).
+ * sdb_queue_stats reduces over every agent below the watermark: totals, the pending records per priority level (a
+ * histogram over the ring metadata), the deepest queue.  Both synchronise (they return data). */
+typedef struct sdb_agent_load {
+  uint32_t received;             /* records enqueued for the agent so far (mod 2^32) */
+  uint32_t pending;              /* records waiting in its ring */
+  uint32_t pending_by_prio[4];   /* ... by priority level (M:35-41) */
+  uint32_t pending_granules;     /* 32-byte granules of pending payload (without headers) */
+  uint32_t reserved;
+} sdb_agent_load;
+typedef struct sdb_queue_summary {
+  uint64_t agents_with_pending;
+  uint64_t pending;
+  uint64_t pending_by_prio[4];
+  uint64_t pending_granules;
+  uint64_t received;             /* sum over agents of `received` */
+  uint64_t max_pending;          /* deepest queue */
+  uint64_t max_pending_agent;
+} sdb_queue_summary;
+int sdb_agent_loads(sdb_handle h, uint32_t n, const uint32_t* agent_idx, sdb_agent_load* out);
+int sdb_queue_stats(sdb_handle h, sdb_queue_summary* out);
+
 /* ---- LLM backend balancer: set_llm_load_balancing / assign_llm_backend / get_llm_backend
  * (M:1281-1325).  The reference stores a flag and a dict and has NO pick algorithm
  * (SURVEY 0.5); the per-agent sticky map stays in the Python layer, and these entry points
@@ -337,6 +365,13 @@ int sdb_get_backend_loads(sdb_handle h, uint32_t n, uint64_t* load_out);
 int sdb_release_backends(sdb_handle h, uint32_t n, const uint32_t* backend, const uint32_t* cost /* NULL = 1 */);
 int sdb_select_backend_batch(sdb_handle h, uint32_t n_req, const uint32_t* cost, uint32_t mode,
                              uint64_t seed, uint32_t* backend_out);
+/* "get_agent_load is the only load signal" (SURVEY 8a R10, M:1049-1094): feed the balancer from the queue itself.
+ * sdb_assign_agent_backends is the device copy of the sticky agent -> backend map (assign_llm_backend, M:1293-1311;
+ * backend index, or 0xFFFFFFFF = none).  sdb_backend_loads_from_queues sets load[b] = sum of the pending records of the
+ * agents assigned to b (one pass over the ring headers, stream-ordered, no host round trip); picks then see real
+ * backlog.  Call it before sdb_select_backend_batch whenever the loads should track the queues. */
+int sdb_assign_agent_backends(sdb_handle h, uint32_t n, const uint32_t* agent_idx, const uint32_t* backend_idx);
+int sdb_backend_loads_from_queues(sdb_handle h);
 
 #ifdef __cplusplus
 }

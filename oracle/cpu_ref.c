@@ -286,6 +286,24 @@ uint64_t orc_pending(orc* o, uint32_t a) {
   return c;
 }
 
+/* inbox / load queries (include/swarmdb_b200.h sdb_agent_loads; reference: get_agent_load M:1049-1094, get_unread_message_count
+ * M:1026-1047): received = records ever enqueued for the agent (len(agent_inbox[a]), M:1076), pending = not yet received */
+void orc_agent_loads(orc* o, uint32_t n, const uint32_t* agent_idx, sdb_agent_load* out) {
+  for (uint32_t q = 0; q < n; ++q) {
+    const uint32_t a = agent_idx ? agent_idx[q] : q;
+    sdb_agent_load r; memset(&r, 0, sizeof(r));
+    if (a < o->max_agents) {
+      const orc_inbox* in = &o->inbox[a];
+      r.received = (uint32_t)in->n;
+      for (uint64_t p = in->head; p < in->n; ++p) if (!in->done[p]) {
+        const orc_rec* rec = &o->recs[in->idx[p]];
+        r.pending++; r.pending_by_prio[rec->hdr.prio & 3]++; r.pending_granules += pad32(rec->hdr.len) / 32;
+      }
+    }
+    out[q] = r;
+  }
+}
+
 /* digests: enable (allocates, zeroed) / reset / read.  Folding happens inside orc_receive_batch and the MT drain. */
 void orc_digest_enable(orc* o) {
   if (!o->digest) o->digest = (uint64_t*)calloc(o->max_agents, 8);

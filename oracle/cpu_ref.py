@@ -53,6 +53,7 @@ def lib():
         L.orc_set_backends.argtypes = [vp, u32, vp, vp]
         L.orc_get_backend_loads.argtypes = [vp, vp]
         L.orc_select_backend_batch.argtypes = [vp, u32, vp, u32, u64, vp]
+        L.orc_agent_loads.argtypes = [vp, u32, vp, vp]
         L.orc_digest_enable.argtypes = [vp]
         L.orc_digest_read.argtypes = [vp, u32, vp, vp]
         L.orc_mt_group_roundtrip.restype = u64
@@ -156,6 +157,29 @@ class CpuOracle:
         total = lib().orc_receive_batch(self._h, n, _p(a), max_messages, flags, _p(counts), _p(hdr), _p(pay),
                                         C.cast(C.byref(pb), C.c_void_p))
         return counts, hdr[:total].copy(), pay[:pb.value].copy()
+
+    def agent_loads(self, agents=None, n=None) -> np.ndarray:
+        """Restatement of sdb_agent_loads: inbox size / unread count / priority histogram per agent."""
+        dt = np.dtype([("received", "<u4"), ("pending", "<u4"), ("pending_by_prio", "<u4", (4,)), ("pending_granules", "<u4"),
+                       ("reserved", "<u4")])
+        if agents is None:
+            a, cnt = None, int(n if n is not None else self.max_agents)
+        else:
+            a = _arr(agents, np.uint32)
+            cnt = len(a)
+        out = np.zeros(cnt, dt)
+        lib().orc_agent_loads(self._h, cnt, _p(a), _p(out))
+        return out
+
+    def queue_stats(self, n=None) -> dict:
+        ld = self.agent_loads(None, n)
+        pend = ld["pending"].astype(np.int64)
+        deepest = int(pend.max()) if len(pend) else 0
+        return {"agents_with_pending": int((pend > 0).sum()), "pending": int(pend.sum()),
+                "pending_by_prio": [int(x) for x in ld["pending_by_prio"].astype(np.int64).sum(axis=0)] if len(pend) else [0, 0, 0, 0],
+                "pending_granules": int(ld["pending_granules"].astype(np.int64).sum()),
+                "received": int(ld["received"].astype(np.int64).sum()), "max_pending": deepest,
+                "max_pending_agent": int(np.argmax(pend)) if deepest else 0}
 
     def digest_enable(self) -> None:
         """Start (or restart from zero) folding every delivered record into per-agent stream digests."""

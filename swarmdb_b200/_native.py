@@ -16,6 +16,10 @@ import numpy as np
 _CSRC = Path(__file__).resolve().parent / "csrc"
 LIB_PATH = _CSRC / "libswarmdb_b200.so"
 
+LOAD_DTYPE = np.dtype([("received", "<u4"), ("pending", "<u4"), ("pending_by_prio", "<u4", (4,)), ("pending_granules", "<u4"),
+                       ("reserved", "<u4")])
+QSTATS_FIELDS = ["agents_with_pending", "pending", "p0", "p1", "p2", "p3", "pending_granules", "received", "max_pending",
+                 "max_pending_agent"]
 HDR_DTYPE = np.dtype([("seq", "<u8"), ("timestamp", "<f8"), ("sender", "<u4"), ("receiver", "<u4"),
                       ("group", "<u4"), ("len", "<u2"), ("prio", "u1"), ("type", "u1")])
 assert HDR_DTYPE.itemsize == 32
@@ -62,7 +66,8 @@ EXPORTS = ["sdb_abi_version", "sdb_create", "sdb_destroy", "sdb_set_stream", "sd
            "sdb_digest_reset", "sdb_digest_fold", "sdb_digest_read", "sdb_wire_bytes", "sdb_set_agent_shards",
            "sdb_export_group_batch", "sdb_export_mixed_batch", "sdb_export_mixed_batch_seq", "sdb_import_wire_batches", "sdb_wire_alloc", "sdb_wire_open",
            "sdb_wire_close", "sdb_import_wire_ptrs", "sdb_wire_wait_done", "sdb_wire_publish", "sdb_import_wire_ptrs_async", "sdb_set_backends", "sdb_get_backend_loads",
-           "sdb_release_backends", "sdb_select_backend_batch"]
+           "sdb_release_backends", "sdb_select_backend_batch", "sdb_agent_loads", "sdb_queue_stats",
+           "sdb_assign_agent_backends", "sdb_backend_loads_from_queues"]
 
 _lib = None
 
@@ -126,6 +131,10 @@ def load_library() -> C.CDLL:
     L.sdb_get_backend_loads.restype = i32; L.sdb_get_backend_loads.argtypes = [vp, u32, vp]
     L.sdb_release_backends.restype = i32; L.sdb_release_backends.argtypes = [vp, u32, vp, vp]
     L.sdb_select_backend_batch.restype = i32; L.sdb_select_backend_batch.argtypes = [vp, u32, vp, u32, u64, vp]
+    L.sdb_agent_loads.restype = i32; L.sdb_agent_loads.argtypes = [vp, u32, vp, vp]
+    L.sdb_queue_stats.restype = i32; L.sdb_queue_stats.argtypes = [vp, vp]
+    L.sdb_assign_agent_backends.restype = i32; L.sdb_assign_agent_backends.argtypes = [vp, u32, vp, vp]
+    L.sdb_backend_loads_from_queues.restype = i32; L.sdb_backend_loads_from_queues.argtypes = [vp]
     if L.sdb_abi_version() != 1:
         raise ImportError("swarmdb_b200 ABI version mismatch")
     _lib = L
@@ -506,6 +515,33 @@ class Shard:
         c, h, p = C.c_void_p(), C.c_void_p(), C.c_void_p()
         self._check(self._L.sdb_last_receive_dev(self._h, C.byref(c), C.byref(h), C.byref(p)))
         return c.value, h.value, p.value
+
+    # ------------------------------------------------------------------ inbox / load queries from the rings (N3)
+    def agent_loads(self, agents=None, n: Optional[int] = None) -> np.ndarray:
+        """Per-agent `received` (inbox size), `pending` (unread) and its priority histogram, computed on the device."""
+        if agents is None:
+            a, cnt = None, int(n if n is not None else self.stats_n_agents())
+        else:
+            a = _arr(agents, np.uint32)
+            cnt = len(a)
+        out = np.zeros(cnt, LOAD_DTYPE)
+        self._check(self._L.sdb_agent_loads(self._h, cnt, _p(a), _p(out)))
+        return out
+
+    def queue_stats(self) -> dict:
+        raw = np.zeros(10, np.uint64)
+        self._check(self._L.sdb_queue_stats(self._h, _p(raw)))
+        d = {k: int(v) for k, v in zip(QSTATS_FIELDS, raw)}
+        d["pending_by_prio"] = [d.pop("p0"), d.pop("p1"), d.pop("p2"), d.pop("p3")]
+        return d
+
+    def assign_agent_backends(self, agents, backends) -> None:
+        a, b = _arr(agents, np.uint32), _arr(backends, np.uint32)
+        self._check(self._L.sdb_assign_agent_backends(self._h, len(a), _p(a), _p(b)))
+
+    def backend_loads_from_queues(self) -> None:
+        """load[b] = pending records of the agents assigned to backend b (stream-ordered, no host round trip)."""
+        self._check(self._L.sdb_backend_loads_from_queues(self._h))
 
     # ------------------------------------------------------------------ backends
     def set_backends(self, weight, load0=None) -> None:

@@ -699,6 +699,9 @@ class SwarmsDB:
 
     def assign_llm_backend(self, agent_id: str, backend_id: str) -> None:
         self.metadata.setdefault("llm_backends", {})[agent_id] = backend_id
+        b = self._backend_idx.get(backend_id)
+        if b is not None and agent_id in self._agent_idx:      # device copy of the sticky map: backs queue-fed loads
+            self.shard.assign_agent_backends([self._agent_idx[agent_id]], [b])
 
     def get_llm_backend(self, agent_id: str) -> Optional[str]:
         return self.metadata.get("llm_backends", {}).get(agent_id)
@@ -731,6 +734,13 @@ class SwarmsDB:
 
     def release_llm_backend(self, backend_id: str, cost: int = 1) -> None:
         self.shard.release_backends([self._backend_idx[backend_id]], [cost])
+
+    def refresh_llm_backend_loads(self) -> Dict[str, int]:
+        """Set every backend's load to the backlog of the agents assigned to it - the reference's only load signal is
+        get_agent_load (M:1049-1094); here it is one pass over the ring headers on the device."""
+        self._pre_read()
+        self.shard.backend_loads_from_queues()
+        return self.llm_backend_loads()
 
     def llm_backend_loads(self) -> Dict[str, int]:
         return {b: int(l) for b, l in zip(self._backend_name, self.shard.backend_loads())}
@@ -811,6 +821,17 @@ class SwarmsDB:
         return {"registered": True, "message_count": involved, "inbox_size": len(self.agent_inbox.get(agent_id, [])),
                 "unread_count": self.get_unread_message_count(agent_id), "processing_rate": recent / 60}
 
+    def get_agent_queue_load(self, agent_id: str) -> Dict[str, Any]:
+        """get_agent_load's inbox_size / unread_count (M:1076-1080) answered by the device queue itself: works for
+        traffic that never had a host-side record (bulk index-level sends, messages ingested by other ranks)."""
+        if agent_id not in self._agent_idx:
+            return {"registered": False, "inbox_size": 0, "unread_count": 0, "unread_by_priority": [0, 0, 0, 0], "unread_bytes": 0}
+        self._pre_read()
+        ld = self.shard.agent_loads([self._agent_idx[agent_id]])[0]
+        return {"registered": agent_id in self.registered_agents, "inbox_size": int(ld["received"]),
+                "unread_count": int(ld["pending"]), "unread_by_priority": [int(x) for x in ld["pending_by_prio"]],
+                "unread_bytes": int(ld["pending_granules"]) * 32}
+
     def get_stats(self) -> Dict[str, Any]:
         by_type = {t.value: 0 for t in MessageType}
         by_status = {s.value: 0 for s in MessageStatus}
@@ -826,7 +847,8 @@ class SwarmsDB:
                     for a in self.registered_agents}
         return {"total_messages": self.message_count, "active_agents": len(self.registered_agents),
                 "messages_by_type": by_type, "messages_by_status": by_status, "messages_by_agent": by_agent,
-                "last_save_time": self.last_save_time, "device": self.shard.stats()}
+                "last_save_time": self.last_save_time, "device": self.shard.stats(),
+                "queue": self.shard.queue_stats()}            # pending totals / priority histogram / deepest inbox, computed on the device
 
     def resend_failed_messages(self) -> List[str]:
         resent: List[str] = []

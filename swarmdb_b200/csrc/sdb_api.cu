@@ -36,6 +36,9 @@ cudaError_t sdb_launch_pick(int mode, uint32_t n_backends, const uint32_t* weigh
                             unsigned long long* scratch_dev, const uint32_t* log_tab_dev,
                             cudaStream_t stream, int* n_launches);
 void sdb_build_log2_table(uint32_t* tab257);
+cudaError_t sdb_launch_agent_loads(const sdb_dev_view*, const uint32_t*, uint32_t, sdb_agent_load*, int, cudaStream_t);
+cudaError_t sdb_launch_queue_stats(const sdb_dev_view*, uint32_t, unsigned long long*, cudaStream_t);
+cudaError_t sdb_launch_backend_loads_from_queues(const sdb_dev_view*, uint32_t, const uint32_t*, uint32_t, unsigned long long*, cudaStream_t);
 cudaError_t sdb_launch_import_measure(const sdb_import_args*, uint32_t, uint32_t*, uint32_t*, uint32_t*, uint32_t*, uint32_t*,
                                       uint32_t*, uint32_t*, unsigned long long*, cudaStream_t, sdb_profiler*, int*);
 cudaError_t sdb_launch_import_localize(const sdb_import_args*, uint32_t, const uint32_t*, uint32_t*, cudaStream_t, sdb_profiler*, int*);
@@ -135,6 +138,7 @@ struct sdb_ctx {
   uint32_t* be_weight = nullptr; unsigned long long* be_load = nullptr; uint32_t n_backends = 0;
   uint32_t* be_req_cost = nullptr; uint32_t* be_out = nullptr; unsigned long long* be_scratch = nullptr;
   uint32_t* be_logtab = nullptr; uint32_t be_req_cap = 0;
+  uint32_t* agent_backend_dev = nullptr;      // [max_agents] sticky agent -> backend map on the device (0xFFFFFFFF = none)
   // host state
   uint64_t next_seq = 1;       // ids start at 1 like the deterministic-uuid reference counter
   uint64_t arena_tail = 0;     // granules, monotonic
@@ -652,7 +656,7 @@ int sdb_destroy(sdb_handle h) {
   cudaSetDevice(h->cfg.device);
   if (h->stream) cudaStreamSynchronize(h->stream);
   void* dev[] = {h->arena, h->ring_hdr, h->ring, h->members, h->ctr, h->gexcl_dev, h->rx_rec_off, h->rx_lb,
-                 h->xs_gs_off_src, h->xs_gs_idx_src, h->xs_first, h->xs_lb, h->cursor_dev, h->bb_dev, h->xs_hdrs, h->owned_dev,
+                 h->xs_gs_off_src, h->xs_gs_idx_src, h->xs_first, h->xs_lb, h->cursor_dev, h->bb_dev, h->xs_hdrs, h->owned_dev, h->agent_backend_dev,
                  h->scratch.descs_dev, h->scratch.payload_dev, h->scratch.list_dev, h->scratch.gs_off_dev,
                  h->scratch.gs_idx_dev, h->memb_off_dev, h->memb_grp_dev, h->memb_pos_dev, h->member_pos_dev,
                  h->lstart_dev, h->lcount_dev, h->xs_w, h->xs_w_local, h->xs_w_tops, h->xs_gs_cnt, h->xs_gs_local,
@@ -1364,6 +1368,69 @@ int sdb_last_receive_totals(sdb_handle h, uint64_t* total_out, uint64_t* payload
   CUDA_TRY(h, cudaStreamSynchronize(h->stream));
   if (total_out) *total_out = h->totals_host[0];
   if (payload_bytes_out) *payload_bytes_out = h->totals_host[1] * SDB_GRANULE;
+  return SDB_OK;
+}
+
+// ---- N3: inbox / load queries from the rings ---------------------------------------------------
+int sdb_agent_loads(sdb_handle h, uint32_t n, const uint32_t* agent_idx, sdb_agent_load* out) {
+  if (!h || (n && !out)) return SDB_EINVAL;
+  if (n == 0) return SDB_OK;
+  if (n > h->cfg.max_agents) return fail(h, SDB_EINVAL, "n > max_agents");
+  if (agent_idx) {
+    for (uint32_t i = 0; i < n; ++i) if (agent_idx[i] >= h->cfg.max_agents) return fail(h, SDB_EINVAL, "agent index out of range");
+    CUDA_TRY(h, cudaMemcpyAsync(h->rx_agent, agent_idx, static_cast<size_t>(n) * sizeof(uint32_t), cudaMemcpyHostToDevice, h->stream));
+  }
+  // the receive plan buffer doubles as scratch (32 bytes per agent; it holds max_recv_records + 4 16-byte entries)
+  sdb_agent_load* tmp = nullptr;
+  CUDA_TRY(h, cudaMallocAsync(reinterpret_cast<void**>(&tmp), static_cast<size_t>(n) * sizeof(sdb_agent_load), h->stream));
+  cudaError_t e = sdb_launch_agent_loads(&h->view, agent_idx ? h->rx_agent : nullptr, n, tmp, h->sm_count, h->stream);
+  h->launches += 1;
+  if (e == cudaSuccess) e = cudaMemcpyAsync(out, tmp, static_cast<size_t>(n) * sizeof(sdb_agent_load), cudaMemcpyDeviceToHost, h->stream);
+  if (e == cudaSuccess) e = cudaFreeAsync(tmp, h->stream);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
+  if (e != cudaSuccess) return fail(h, SDB_ECUDA, std::string("agent loads: ") + cudaGetErrorString(e));
+  return SDB_OK;
+}
+
+int sdb_queue_stats(sdb_handle h, sdb_queue_summary* out) {
+  if (!h || !out) return SDB_EINVAL;
+  unsigned long long* acc = h->be_scratch;                 // >= 16 words, free between picks
+  cudaError_t e = sdb_launch_queue_stats(&h->view, h->n_agents, acc, h->stream);
+  h->launches += 1;
+  unsigned long long host[10];
+  if (e == cudaSuccess) e = cudaMemcpyAsync(host, acc, sizeof(host), cudaMemcpyDeviceToHost, h->stream);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
+  if (e != cudaSuccess) return fail(h, SDB_ECUDA, std::string("queue stats: ") + cudaGetErrorString(e));
+  out->agents_with_pending = host[0]; out->pending = host[1];
+  for (int k = 0; k < 4; ++k) out->pending_by_prio[k] = host[2 + k];
+  out->pending_granules = host[6]; out->received = host[7];
+  out->max_pending = host[8] >> 32; out->max_pending_agent = host[8] ? 0xFFFFFFFFull - (host[8] & 0xFFFFFFFFull) : 0;
+  return SDB_OK;
+}
+
+int sdb_assign_agent_backends(sdb_handle h, uint32_t n, const uint32_t* agent_idx, const uint32_t* backend_idx) {
+  if (!h || (n && (!agent_idx || !backend_idx))) return SDB_EINVAL;
+  if (!h->agent_backend_dev) {
+    CUDA_TRY(h, dmalloc(&h->agent_backend_dev, h->cfg.max_agents));
+    CUDA_TRY(h, cudaMemsetAsync(h->agent_backend_dev, 0xFF, static_cast<size_t>(h->cfg.max_agents) * sizeof(uint32_t), h->stream));
+  }
+  for (uint32_t i = 0; i < n; ++i) {
+    if (agent_idx[i] >= h->cfg.max_agents) return fail(h, SDB_EINVAL, "agent index out of range");
+    if (backend_idx[i] != 0xFFFFFFFFu && backend_idx[i] >= h->cfg.max_backends) return fail(h, SDB_ENOTFOUND, "backend index out of range");
+    // assignments are rare and small (one per agent when it first asks): element-wise stream-ordered copies
+    CUDA_TRY(h, cudaMemcpyAsync(h->agent_backend_dev + agent_idx[i], backend_idx + i, sizeof(uint32_t), cudaMemcpyHostToDevice, h->stream));
+  }
+  if (n) CUDA_TRY(h, cudaStreamSynchronize(h->stream));     // the source array is the caller's
+  return SDB_OK;
+}
+
+int sdb_backend_loads_from_queues(sdb_handle h) {
+  if (!h) return SDB_EINVAL;
+  if (h->n_backends == 0) return fail(h, SDB_ENOTFOUND, "no backends configured (sdb_set_backends)");
+  if (!h->agent_backend_dev) return fail(h, SDB_ENOTFOUND, "no agent is assigned to a backend (sdb_assign_agent_backends)");
+  cudaError_t e = sdb_launch_backend_loads_from_queues(&h->view, h->n_agents, h->agent_backend_dev, h->n_backends, h->be_load, h->stream);
+  h->launches += 1;
+  if (e != cudaSuccess) return fail(h, SDB_ECUDA, std::string("backend loads: ") + cudaGetErrorString(e));
   return SDB_OK;
 }
 

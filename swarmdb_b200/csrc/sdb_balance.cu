@@ -235,3 +235,112 @@ extern "C" cudaError_t sdb_launch_pick(int mode, uint32_t B, const uint32_t* wei
   }
   return cudaGetLastError();
 }
+
+
+// ------------------------------------------------------------------------------------------
+// N3: inbox / load queries answered from the rings (get_agent_load M:1049-1094, get_unread_message_count
+// M:1026-1047, get_stats M:973-1024) and the balancer fed by the queue backlog.
+// ------------------------------------------------------------------------------------------
+// one warp per listed agent: header fields + a histogram of the pending window's ring metadata
+__global__ void __launch_bounds__(256)
+k_agent_loads(sdb_dev_view v, const uint32_t* __restrict__ agent_idx, uint32_t n, sdb_agent_load* __restrict__ out) {
+  const uint32_t lane = threadIdx.x & 31;
+  const uint32_t gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nw = (gridDim.x * blockDim.x) >> 5;
+  for (uint32_t q = gw; q < n; q += nw) {
+    const uint32_t a = agent_idx ? agent_idx[q] : q;
+    uint32_t h[4] = {0, 0, 0, 0}, gran = 0, head = 0, tail = 0;
+    if (a < v.max_agents) {
+      const uint4 hd = *reinterpret_cast<const uint4*>(v.ring_hdr + a);
+      head = hd.x; tail = hd.y;
+      const uint2* rs = sdb_ring_of(v, a);
+      const uint32_t mask = v.ring_slots - 1;
+      for (uint32_t p = head + lane; static_cast<int32_t>(tail - p) > 0; p += 32) {
+        const uint32_t m = rs[p & mask].y & 0xFFFFu;
+        if (m != SDB_META_TOMB) { h[m >> 14] += 1; gran += (m & SDB_META_GLEN_MASK) - 1u; }
+      }
+    }
+#pragma unroll
+    for (int k = 0; k < 4; ++k) for (int o = 16; o; o >>= 1) h[k] += __shfl_xor_sync(0xFFFFFFFFu, h[k], o);
+    for (int o = 16; o; o >>= 1) gran += __shfl_xor_sync(0xFFFFFFFFu, gran, o);
+    if (lane == 0) {
+      sdb_agent_load r;
+      r.received = tail; r.pending = h[0] + h[1] + h[2] + h[3];
+      r.pending_by_prio[0] = h[0]; r.pending_by_prio[1] = h[1]; r.pending_by_prio[2] = h[2]; r.pending_by_prio[3] = h[3];
+      r.pending_granules = gran; r.reserved = 0;
+      out[q] = r;
+    }
+  }
+}
+
+// every agent below the watermark: thread per agent for the header part; agents with pending entries walk their
+// window (short in the steady state); block-level reduction, one atomic per block and field
+__global__ void __launch_bounds__(256)
+k_queue_stats(sdb_dev_view v, uint32_t n_agents, unsigned long long* __restrict__ acc /* [10] */) {
+  __shared__ unsigned long long s_acc[9];
+  __shared__ unsigned long long s_max;
+  if (threadIdx.x < 9) s_acc[threadIdx.x] = 0;
+  if (threadIdx.x == 0) s_max = 0;
+  __syncthreads();
+  const uint32_t a = blockIdx.x * blockDim.x + threadIdx.x;
+  if (a < n_agents) {
+    const uint4 hd = *reinterpret_cast<const uint4*>(v.ring_hdr + a);
+    const uint32_t live = hd.y - hd.x - hd.w;
+    atomicAdd(&s_acc[7], static_cast<unsigned long long>(hd.y));
+    if (live) {
+      uint32_t h[4] = {0, 0, 0, 0}, gran = 0;
+      const uint2* rs = sdb_ring_of(v, a);
+      const uint32_t mask = v.ring_slots - 1;
+      for (uint32_t p = hd.x; p != hd.y; ++p) {
+        const uint32_t m = rs[p & mask].y & 0xFFFFu;
+        if (m != SDB_META_TOMB) { h[m >> 14] += 1; gran += (m & SDB_META_GLEN_MASK) - 1u; }
+      }
+      atomicAdd(&s_acc[0], 1ull); atomicAdd(&s_acc[1], static_cast<unsigned long long>(live));
+      for (int k = 0; k < 4; ++k) if (h[k]) atomicAdd(&s_acc[2 + k], static_cast<unsigned long long>(h[k]));
+      atomicAdd(&s_acc[6], static_cast<unsigned long long>(gran));
+      atomicMax(&s_max, (static_cast<unsigned long long>(live) << 32) | (0xFFFFFFFFu - a));   // deepest queue, lowest index on ties
+    }
+  }
+  __syncthreads();
+  if (threadIdx.x < 8 && s_acc[threadIdx.x]) atomicAdd(acc + threadIdx.x, s_acc[threadIdx.x]);
+  if (threadIdx.x == 8 && s_max) atomicMax(acc + 8, s_max);
+}
+
+// load[b] = pending records of the agents assigned to b (thread per agent, shared-memory histogram per block)
+__global__ void __launch_bounds__(256)
+k_backend_loads_from_queues(sdb_dev_view v, uint32_t n_agents, const uint32_t* __restrict__ agent_backend, uint32_t B,
+                            unsigned long long* __restrict__ load) {
+  extern __shared__ unsigned long long s_load[];
+  for (uint32_t b = threadIdx.x; b < B; b += blockDim.x) s_load[b] = 0;
+  __syncthreads();
+  const uint32_t a = blockIdx.x * blockDim.x + threadIdx.x;
+  if (a < n_agents) {
+    const uint32_t b = agent_backend[a];
+    if (b < B) {
+      const uint4 hd = *reinterpret_cast<const uint4*>(v.ring_hdr + a);
+      const uint32_t live = hd.y - hd.x - hd.w;
+      if (live) atomicAdd(&s_load[b], static_cast<unsigned long long>(live));
+    }
+  }
+  __syncthreads();
+  for (uint32_t b = threadIdx.x; b < B; b += blockDim.x) if (s_load[b]) atomicAdd(load + b, s_load[b]);
+}
+
+extern "C" cudaError_t sdb_launch_agent_loads(const sdb_dev_view* v, const uint32_t* agent_idx_dev, uint32_t n, sdb_agent_load* out_dev,
+                                              int sm_count, cudaStream_t stream) {
+  if (n == 0) return cudaSuccess;
+  uint32_t grid = static_cast<uint32_t>(sm_count) * 8u;
+  if (grid > (n + 7) / 8) grid = (n + 7) / 8;
+  k_agent_loads<<<grid, 256, 0, stream>>>(*v, agent_idx_dev, n, out_dev);
+  return cudaGetLastError();
+}
+extern "C" cudaError_t sdb_launch_queue_stats(const sdb_dev_view* v, uint32_t n_agents, unsigned long long* acc_dev, cudaStream_t stream) {
+  cudaMemsetAsync(acc_dev, 0, 10 * sizeof(unsigned long long), stream);
+  if (n_agents) k_queue_stats<<<(n_agents + 255) / 256, 256, 0, stream>>>(*v, n_agents, acc_dev);
+  return cudaGetLastError();
+}
+extern "C" cudaError_t sdb_launch_backend_loads_from_queues(const sdb_dev_view* v, uint32_t n_agents, const uint32_t* agent_backend_dev,
+                                                            uint32_t B, unsigned long long* load_dev, cudaStream_t stream) {
+  cudaMemsetAsync(load_dev, 0, static_cast<size_t>(B) * sizeof(unsigned long long), stream);
+  if (n_agents && B) k_backend_loads_from_queues<<<(n_agents + 255) / 256, 256, B * sizeof(unsigned long long), stream>>>(*v, n_agents, agent_backend_dev, B, load_dev);
+  return cudaGetLastError();
+}

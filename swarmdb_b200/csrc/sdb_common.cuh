@@ -382,8 +382,11 @@ __device__ __forceinline__ void sdb_mbar_expect_tx(uint64_t* bar, uint32_t bytes
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(sdb_smem_u32(bar)), "r"(bytes) : "memory");
 }
 __device__ __forceinline__ void sdb_mbar_wait_bounded(uint64_t* bar, uint32_t phase) {
-  // bounded spin: a phase-accounting bug must surface as a launch failure (trap), never as a hung GPU
+  // bounded spin: a phase-accounting bug must surface as a launch failure (trap), never as a hung GPU.  The bound is
+  // wall time (30 s on %globaltimer, polled every 4096 spins), not a spin count: under compute-sanitizer or with a
+  // payload arriving from a busy peer GPU a legitimate wait can take many more iterations than on an idle device.
   const uint32_t addr = sdb_smem_u32(bar);
+  unsigned long long t0 = 0;
   for (uint32_t spins = 0;; ++spins) {
     uint32_t done;
     asm volatile(
@@ -393,20 +396,16 @@ __device__ __forceinline__ void sdb_mbar_wait_bounded(uint64_t* bar, uint32_t ph
         "selp.u32 %0, 1, 0, p;\n"
         "}\n" : "=r"(done) : "r"(addr), "r"(phase) : "memory");
     if (done) return;
-    if (spins > (1u << 22)) __trap();
+    if ((spins & 4095u) == 4095u) {
+      unsigned long long t1;
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+      if (t0 == 0) t0 = t1;
+      else if (t1 - t0 > 30ull * 1000000000ull) __trap();
+    }
   }
 }
-__device__ __forceinline__ void sdb_mbar_wait(uint64_t* bar, uint32_t phase) {
-  asm volatile(
-      "{\n"
-      ".reg .pred p;\n"
-      "WAIT_LOOP:\n"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
-      "@p bra DONE;\n"
-      "bra WAIT_LOOP;\n"
-      "DONE:\n"
-      "}\n" :: "r"(sdb_smem_u32(bar)), "r"(phase) : "memory");
-}
+// every mbarrier wait in this library is the bounded one: a phase-accounting bug must trap, never hang the GPU
+__device__ __forceinline__ void sdb_mbar_wait(uint64_t* bar, uint32_t phase) { sdb_mbar_wait_bounded(bar, phase); }
 // global -> shared bulk copy, completion counted on an mbarrier (SASS: UBLKCP)
 __device__ __forceinline__ void sdb_tma_load(void* smem_dst, const void* gsrc, uint32_t bytes, uint64_t* bar) {
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"

@@ -544,6 +544,43 @@ class ShardedSwarmsDB(SwarmsDB):
             self._fail_round(e)
             raise
         self._flush_import()
+        self.sync_llm_backends()
+
+    # ---- one balancer for all shards: every rank picks from its own copy of the table; the per-backend
+    # load changes each rank made since the last flush are summed across ranks (256 values) and applied everywhere
+    def register_llm_backends(self, backend_ids, weights=None, loads=None) -> None:
+        """REPLICATED (every rank, identically)."""
+        super().register_llm_backends(backend_ids, weights, loads)
+        self._be_weights = np.asarray(weights if weights is not None else [1] * len(backend_ids), np.uint32)
+        self._be_synced = np.asarray(loads if loads is not None else [0] * len(backend_ids), np.int64).copy()
+
+    def _all_reduce_i64(self, x: np.ndarray) -> np.ndarray:
+        import torch
+        import torch.distributed as dist
+        if self.world == 1 or not dist.is_initialized():
+            return x
+        dev = torch.device("cuda", self.gpu_config.device) if dist.get_backend() == "nccl" else torch.device("cpu")
+        t = torch.from_numpy(np.ascontiguousarray(x, np.int64)).to(dev)
+        dist.all_reduce(t)
+        return t.cpu().numpy()
+
+    def sync_llm_backends(self) -> None:
+        """COLLECTIVE (part of flush): after it every rank's table holds base + the sum of all ranks' changes."""
+        if not getattr(self, "_backend_name", None) or not hasattr(self, "_be_synced"):
+            return
+        local = self.shard.backend_loads().astype(np.int64)
+        total = self._be_synced + self._all_reduce_i64(local - self._be_synced)
+        total = np.maximum(total, 0)
+        self.shard.set_backends(self._be_weights, total.astype(np.uint64))
+        self._be_synced = total
+
+    def refresh_llm_backend_loads(self):
+        """COLLECTIVE: backlog of the agents assigned to each backend, summed over the shards that own them."""
+        self.shard.backend_loads_from_queues()
+        total = self._all_reduce_i64(self.shard.backend_loads().astype(np.int64))
+        self.shard.set_backends(self._be_weights, total.astype(np.uint64))
+        self._be_synced = total
+        return self.llm_backend_loads()
 
     def _fail_round(self, e: Exception) -> None:
         for m in self._round_msgs:

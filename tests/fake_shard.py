@@ -20,6 +20,34 @@ class OracleShard:
     def deregister(self, idx): pass
     def sync(self): pass
     def close(self): self.o.close()
+    def agent_loads(self, agents=None, n=None): return self.o.agent_loads(agents, n)
+    def queue_stats(self): return self.o.queue_stats()
+
+    def assign_agent_backends(self, agents, backends):
+        self._ab = getattr(self, "_ab", {})
+        self._ab.update({int(a): int(b) for a, b in zip(agents, backends)})
+
+    def backend_loads_from_queues(self):
+        ld = self.o.agent_loads(None, self.max_agents)["pending"]
+        loads = np.zeros(self.o._nb, np.uint64)
+        for a, b in getattr(self, "_ab", {}).items():
+            if b < self.o._nb:
+                loads[b] += int(ld[a])
+        self.o.set_backends(self._w, loads)
+
+    def set_backends(self, weight, load0=None):
+        self._w = np.asarray(weight, np.uint32)
+        self.o.set_backends(self._w, load0)
+
+    def backend_loads(self): return self.o.backend_loads()
+    def select_backends(self, n_req, cost=None, mode=0, seed=0): return self.o.select_backends(n_req, cost, mode, seed)
+    def release_backends(self, backend, cost=None):
+        l = self.o.backend_loads()
+        for i, b in enumerate(backend):
+            c = 1 if cost is None else int(cost[i])
+            l[b] = l[b] - c if l[b] >= c else 0
+        self.o.set_backends(self._w, l)
+
     def advance_seq(self, next_seq): self.o.next_seq = max(self.o.next_seq, next_seq)
 
     def stats(self): return {"next_seq": self.o.next_seq, "ring_overflow": 0, "n_agents": self.max_agents}

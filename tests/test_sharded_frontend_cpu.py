@@ -159,3 +159,57 @@ def test_composite_seq_layout():
     assert sharded.composite_seq(1, 0) == 1 << 40
     assert sharded.composite_seq(3, 5, 7) == (3 << 40) | (5 << 32) | 7
     assert sharded.composite_seq(2, 0) > sharded.composite_seq(1, 255, (1 << 32) - 1)
+
+
+def _balancer_worker(rank, world, port, q, tmp):
+    import torch.distributed as dist
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from swarmdb_b200.core import GpuConfig
+        cfg = GpuConfig(max_agents=64, max_groups=8, flush_threshold=64, max_payload_bytes=1024, deterministic_ids=True)
+        db = sharded.make_sharded_swarmsdb(
+            rank, world, shard=OracleShard(64, 8, rank, world),
+            exchange_factory=lambda sh, r, w, ms, mp: sharded.ShardExchange(sh, r, w, ms, mp, CpuBackend()),
+            save_dir=f"{tmp}/r{rank}", auto_save=False, gpu_config=cfg)
+        _setup(db)
+        db.register_llm_backends(["b0", "b1", "b2", "b3"], [1, 2, 3, 1])
+        picks = db.select_llm_backends(10 + 5 * rank)                   # rank-local picks change the rank's own table
+        local_after_picks = db.llm_backend_loads()
+        db.flush()                                                       # collective: the 4 load deltas are summed across ranks
+        synced = db.llm_backend_loads()
+        # queue-fed loads: agents are assigned identically everywhere, only their owner knows their backlog
+        for i, a in enumerate(AGENTS[:16]):
+            db.assign_llm_backend(a, f"b{i % 4}")
+        for i in range(12):
+            db.send_message(AGENTS[20 + rank], f"x{i}", AGENTS[i % 16])
+        db.flush()
+        from_queues = db.refresh_llm_backend_loads()
+        allv = [None] * world
+        dist.all_gather_object(allv, (len(picks), local_after_picks, synced, from_queues))
+        db.close()
+        if rank == 0:
+            q.put(allv)
+    finally:
+        dist.destroy_process_group()
+
+
+def test_one_balancer_for_all_shards(tmp_path):
+    """backend loads are global - after a collective flush every rank holds base + the sum of all ranks'
+    changes; queue-fed loads are summed over the owners of the assigned agents."""
+    import torch.multiprocessing as mp
+    s = socket.socket(); s.bind(("127.0.0.1", 0)); port = s.getsockname()[1]; s.close()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_balancer_worker, args=(r, 2, port, q, str(tmp_path))) for r in range(2)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(timeout=240)
+        assert p.exitcode == 0
+    res = q.get(timeout=5)
+    (n0, l0, s0, f0), (n1, l1, s1, f1) = res
+    assert sum(l0.values()) == n0 and sum(l1.values()) == n1 and n0 != n1          # ranks diverged before the flush ...
+    assert s0 == s1 and sum(s0.values()) == n0 + n1                                # ... and agree afterwards
+    assert {b: l0[b] + l1[b] for b in l0} == s0
+    assert f0 == f1 and sum(f0.values()) == 24                                     # 12 messages per rank, all to assigned agents
