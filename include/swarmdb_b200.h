@@ -224,6 +224,16 @@ int sdb_receive_batch(sdb_handle h, uint32_t n_agents, const uint32_t* agent_idx
                       uint32_t* count_out, sdb_msg_header* hdr_out, uint64_t hdr_cap,
                       uint8_t* payload_out, uint64_t payload_cap,
                       uint64_t* total_out, uint64_t* payload_bytes_out);
+/* Low-latency dequeue server (opt-in): receive_messages (M:521-601) for ONE agent in a few microseconds.
+ * enable = 1 starts a persistent single-CTA kernel on its own stream that polls a mailbox in mapped pinned host memory;
+ * sdb_receive_batch calls naming exactly one agent with host outputs (what the Python surface's receive_messages makes)
+ * then post a request there and read the answer - count, headers and payloads - from pinned host memory the kernel wrote
+ * directly: no kernel launch, no cudaStreamSynchronize, no cudaMemcpy on the path.  Results are identical to the
+ * ordinary path (same selection code).  enable = 0 stops it (also done by sdb_destroy).  While it runs the handle
+ * stops it around its own calls that free device memory (cudaFree waits for running kernels) and restarts it on the
+ * next single-agent receive; callers must likewise not call cudaDeviceSynchronize / cudaFree from outside while it runs. */
+int sdb_latency_server(sdb_handle h, int enable);
+
 /* Device-resident results of the LAST receive call (valid until the next one). */
 int sdb_last_receive_dev(sdb_handle h, const uint32_t** count_dev, const sdb_msg_header** hdr_dev,
                          const uint8_t** payload_dev);

@@ -62,7 +62,7 @@ class SdbStats(C.Structure):
 EXPORTS = ["sdb_abi_version", "sdb_create", "sdb_destroy", "sdb_set_stream", "sdb_sync", "sdb_last_error",
            "sdb_get_stats", "sdb_debug_set_arena_pos", "sdb_advance_seq", "sdb_profile", "sdb_profile_read", "sdb_register_agents", "sdb_deregister_agents", "sdb_create_group", "sdb_send_batch",
            "sdb_send_group_batch", "sdb_send_list_batch", "sdb_send_mixed_batch", "sdb_stage_batch", "sdb_submit_staged", "sdb_free_staged",
-           "sdb_receive_batch", "sdb_last_receive_dev", "sdb_last_receive_totals",
+           "sdb_receive_batch", "sdb_latency_server", "sdb_last_receive_dev", "sdb_last_receive_totals",
            "sdb_digest_reset", "sdb_digest_fold", "sdb_digest_read", "sdb_wire_bytes", "sdb_set_agent_shards",
            "sdb_export_group_batch", "sdb_export_mixed_batch", "sdb_export_mixed_batch_seq", "sdb_import_wire_batches", "sdb_wire_alloc", "sdb_wire_open",
            "sdb_wire_close", "sdb_import_wire_ptrs", "sdb_wire_wait_done", "sdb_wire_publish", "sdb_import_wire_ptrs_async", "sdb_set_backends", "sdb_get_backend_loads",
@@ -107,6 +107,7 @@ def load_library() -> C.CDLL:
     L.sdb_free_staged.restype = i32; L.sdb_free_staged.argtypes = [vp, vp]
     L.sdb_receive_batch.restype = i32
     L.sdb_receive_batch.argtypes = [vp, u32, vp, u32, u32, vp, vp, u64, vp, u64, vp, vp]
+    L.sdb_latency_server.restype = i32; L.sdb_latency_server.argtypes = [vp, i32]
     L.sdb_last_receive_dev.restype = i32; L.sdb_last_receive_dev.argtypes = [vp, vp, vp, vp]
     L.sdb_last_receive_totals.restype = i32; L.sdb_last_receive_totals.argtypes = [vp, vp, vp]
     L.sdb_digest_reset.restype = i32; L.sdb_digest_reset.argtypes = [vp]
@@ -451,6 +452,10 @@ class Shard:
             owned = (flags & RECV_OWNED) and getattr(self, "n_owned", None) is not None
             counts = counts[: self.n_owned if owned else self.stats_n_agents()]
         return counts, hdr[: total.value], pay[: pbytes.value]
+
+    def latency_server(self, enable: bool) -> None:
+        """Start / stop the persistent low-latency dequeue server (single-agent receives then skip launch, sync and D2H)."""
+        self._check(self._L.sdb_latency_server(self._h, 1 if enable else 0))
 
     def last_receive_totals(self):
         """(records, payload bytes) of the last receive call; waits for it."""

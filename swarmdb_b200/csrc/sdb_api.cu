@@ -31,6 +31,7 @@ cudaError_t sdb_launch_receive_small(const sdb_dev_view*, const uint32_t*, uint3
                                      uint8_t*, cudaStream_t, sdb_profiler*);
 cudaError_t sdb_launch_digest(const sdb_recv_args*, uint32_t, unsigned long long*, int, cudaStream_t);
 cudaError_t sdb_launch_arena_floor(const sdb_dev_view*, uint32_t, uint32_t, unsigned long long*, cudaStream_t);
+cudaError_t sdb_launch_latency_server(const sdb_dev_view*, sdb_ls_mailbox*, uint8_t*, uint32_t, uint4*, cudaStream_t);
 cudaError_t sdb_launch_pick(int mode, uint32_t n_backends, const uint32_t* weight_dev, unsigned long long* load_dev,
                             uint32_t n_req, const uint32_t* cost_dev, uint64_t seed, uint32_t* out_dev,
                             unsigned long long* scratch_dev, const uint32_t* log_tab_dev,
@@ -132,6 +133,10 @@ struct sdb_ctx {
   uint8_t* small_host = nullptr;               // pinned mirror
   uint64_t small_bytes = 0;
   uint64_t pay_cap_gran = 0;
+  // low-latency dequeue server (sdb_latency_server): mailbox + answer block in mapped pinned host memory
+  sdb_ls_mailbox* ls_mbox = nullptr; uint8_t* ls_out = nullptr; uint32_t ls_out_cap = 0; uint4* ls_plan = nullptr;
+  cudaStream_t ls_stream = nullptr; bool ls_wanted = false, ls_running = false; uint32_t ls_seq = 0;
+  bool stream_busy = false;                    // work was enqueued on `stream` since the last synchronisation
   sdb_recv_args last_rx{}; bool last_rx_valid = false;   // the last bulk receive (sdb_digest_fold reads its device results)
   unsigned long long* digest = nullptr;                  // [max_agents] stream digests, allocated on first use
   // backends
@@ -179,6 +184,37 @@ inline uint32_t pad32(uint32_t len) { return (len + 31u) & ~31u; }
 
 template <typename T>
 cudaError_t dmalloc(T** p, size_t n) { return cudaMalloc(reinterpret_cast<void**>(p), n * sizeof(T)); }
+
+// ---- low-latency dequeue server ----------------------------------------------------------------------------------
+int ls_stop(sdb_ctx* h) {
+  if (!h->ls_running) return SDB_OK;
+  __atomic_store_n(&h->ls_mbox->flags, 0x80000000u, __ATOMIC_RELEASE);     // quit bit, fetched with the request words
+  CUDA_TRY(h, cudaStreamSynchronize(h->ls_stream));
+  h->ls_running = false;
+  return SDB_OK;
+}
+int ls_start(sdb_ctx* h) {
+  if (h->ls_running) return SDB_OK;
+  if (!h->ls_mbox) {
+    h->ls_out_cap = 64u + 1024u * 64u;                                       // k_recv_small's block: 64-byte head + records
+    const uint64_t need = 64ull + 1024ull * (32ull + pad32(h->cfg.max_payload_bytes));
+    if (need < (4ull << 20)) h->ls_out_cap = static_cast<uint32_t>(need); else h->ls_out_cap = 4u << 20;
+    CUDA_TRY(h, cudaHostAlloc(reinterpret_cast<void**>(&h->ls_mbox), sizeof(sdb_ls_mailbox), cudaHostAllocMapped));
+    CUDA_TRY(h, cudaHostAlloc(reinterpret_cast<void**>(&h->ls_out), h->ls_out_cap, cudaHostAllocMapped));
+    CUDA_TRY(h, dmalloc(&h->ls_plan, 1024 + 4));
+    CUDA_TRY(h, cudaStreamCreateWithFlags(&h->ls_stream, cudaStreamNonBlocking));
+    std::memset(h->ls_mbox, 0, sizeof(sdb_ls_mailbox));
+  }
+  h->ls_mbox->quit = 0; h->ls_mbox->flags = 0; h->ls_mbox->req_seq = h->ls_seq; h->ls_mbox->done_seq = h->ls_seq;
+  __sync_synchronize();
+  sdb_ls_mailbox* mb_dev = nullptr; uint8_t* out_dev = nullptr;
+  CUDA_TRY(h, cudaHostGetDevicePointer(reinterpret_cast<void**>(&mb_dev), h->ls_mbox, 0));
+  CUDA_TRY(h, cudaHostGetDevicePointer(reinterpret_cast<void**>(&out_dev), h->ls_out, 0));
+  CUDA_TRY(h, sdb_launch_latency_server(&h->view, mb_dev, out_dev, h->ls_out_cap, h->ls_plan, h->ls_stream));
+  h->launches += 1;
+  h->ls_running = true;
+  return SDB_OK;
+}
 
 // The asynchronous import advances arena / sequence counters on the device.  Before host code uses its own copies
 // it pulls the device's (one small D2H + sync), and reports an import the device had to refuse.
@@ -452,6 +488,7 @@ int submit(sdb_ctx* h, const sdb_staged* s, uint64_t* seq_base_out) {
   h->next_seq += s->total_recs;
   h->arena_tail = base + s->total_grans;
   h->dev_stale = true;
+  h->stream_busy = true;
   return SDB_OK;
 }
 
@@ -654,6 +691,11 @@ int sdb_create(const sdb_config* cfg, sdb_handle* out) {
 int sdb_destroy(sdb_handle h) {
   if (!h) return SDB_EINVAL;
   cudaSetDevice(h->cfg.device);
+  ls_stop(h);
+  if (h->ls_stream) cudaStreamDestroy(h->ls_stream);
+  if (h->ls_mbox) cudaFreeHost(h->ls_mbox);
+  if (h->ls_out) cudaFreeHost(h->ls_out);
+  if (h->ls_plan) cudaFree(h->ls_plan);
   if (h->stream) cudaStreamSynchronize(h->stream);
   void* dev[] = {h->arena, h->ring_hdr, h->ring, h->members, h->ctr, h->gexcl_dev, h->rx_rec_off, h->rx_lb,
                  h->xs_gs_off_src, h->xs_gs_idx_src, h->xs_first, h->xs_lb, h->cursor_dev, h->bb_dev, h->xs_hdrs, h->owned_dev, h->agent_backend_dev,
@@ -699,6 +741,7 @@ int sdb_set_stream(sdb_handle h, void* cuda_stream) {
 int sdb_sync(sdb_handle h) {
   if (!h) return SDB_EINVAL;
   CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+  h->stream_busy = false;
   return SDB_OK;
 }
 
@@ -997,6 +1040,7 @@ int sdb_wire_open(sdb_handle h, const void* ipc_handle, void** dev_out) {
 
 int sdb_wire_close(sdb_handle h, void* dev, int opened) {
   if (!h || !dev) return SDB_EINVAL;
+  ls_stop(h);
   CUDA_TRY(h, cudaStreamSynchronize(h->stream));
   if (opened) CUDA_TRY(h, cudaIpcCloseMemHandle(dev)); else CUDA_TRY(h, cudaFree(dev));
   return SDB_OK;
@@ -1091,6 +1135,7 @@ int sdb_import_wire_ptrs(sdb_handle h, uint32_t n_src, const void* const* wire_p
   h->next_seq = std::max<uint64_t>(h->next_seq + (explicit_end ? 0 : total_recs), explicit_end);
   h->arena_tail = base + total_grans;
   h->dev_stale = true;
+  h->stream_busy = true;
   return SDB_OK;
 }
 
@@ -1169,7 +1214,7 @@ int sdb_import_wire_ptrs_async(sdb_handle h, uint32_t n_src, const void* const* 
     e = sdb_launch_commit(&h->view, h->n_agents, 0, h->rx_big_list, h->rx_big_count + 1, h->sm_count, h->stream, &h->prof, h->bb_dev);
   h->launches += nl + 3;
   if (e != cudaSuccess) return fail(h, SDB_ECUDA, std::string("async import launch: ") + cudaGetErrorString(e));
-  h->host_stale = true;
+  h->host_stale = true; h->stream_busy = true;
   // 3. tell the exporters that this rank is done reading their buffers of this parity
   CUDA_TRY(h, sdb_launch_wire_set(my_done, step, h->stream));
   h->launches += 1;
@@ -1255,6 +1300,7 @@ int sdb_submit_staged(sdb_handle h, sdb_staged_t s, uint64_t* seq_base_out) {
 
 int sdb_free_staged(sdb_handle h, sdb_staged_t s) {
   if (!h || !s) return SDB_EINVAL;
+  ls_stop(h);
   cudaStreamSynchronize(h->stream);
   if (s->owns) {
     cudaFree(s->descs_dev); cudaFree(s->payload_dev);
@@ -1263,6 +1309,31 @@ int sdb_free_staged(sdb_handle h, sdb_staged_t s) {
   }
   delete s;
   return SDB_OK;
+}
+
+int sdb_latency_server(sdb_handle h, int enable) {
+  if (!h) return SDB_EINVAL;
+  h->ls_wanted = enable != 0;
+  return enable ? ls_start(h) : ls_stop(h);
+}
+
+// unpack the latency paths' output block (u64 total | u64 granules | u32 counts[8] | pad to 64 B | records) into the caller's arrays
+static void unpack_small(const uint8_t* block, uint32_t n_agents, uint32_t* count_out, sdb_msg_header* hdr_out, uint8_t* payload_out,
+                         uint64_t* total_out, uint64_t* payload_bytes_out) {
+  const unsigned long long* t = reinterpret_cast<const unsigned long long*>(block);
+  const uint64_t total = t[0];
+  if (count_out) std::memcpy(count_out, block + 16, static_cast<size_t>(n_agents) * sizeof(uint32_t));
+  const uint8_t* p = block + 64;
+  uint64_t poff = 0;
+  for (uint64_t r = 0; r < total; ++r) {
+    const sdb_msg_header* hd = reinterpret_cast<const sdb_msg_header*>(p);
+    hdr_out[r] = *hd;
+    const uint32_t pl = pad32(hd->len);
+    std::memcpy(payload_out + poff, p + 32, pl);
+    poff += pl; p += 32 + pl;
+  }
+  if (total_out) *total_out = total;
+  if (payload_bytes_out) *payload_bytes_out = poff;
 }
 
 int sdb_receive_batch(sdb_handle h, uint32_t n_agents, const uint32_t* agent_idx, uint32_t max_messages, uint32_t flags,
@@ -1286,6 +1357,28 @@ int sdb_receive_batch(sdb_handle h, uint32_t n_agents, const uint32_t* agent_idx
     uint64_t rec_cap = std::min<uint64_t>(1024, std::min<uint64_t>(hdr_cap, payload_cap / max_rec_bytes));
     if (rec_cap == 0) return fail(h, SDB_EOUTPUT, "output buffers cannot hold a single maximum-size record");
     h->last_rx_valid = false;
+    bool served = false;
+    if (h->ls_wanted && n_agents == 1) {
+      { int rcl = ls_start(h); if (rcl != SDB_OK) return rcl; }
+      const uint64_t want = std::min<uint64_t>(max_messages, rec_cap);
+      served = 64ull + want * (32 + max_rec_bytes) <= h->ls_out_cap;      // the whole answer must fit the pinned block
+    }
+    if (served) {
+      // ---- the persistent server: post the request in mapped pinned memory, read the answer from pinned memory
+      if (h->stream_busy) { CUDA_TRY(h, cudaStreamSynchronize(h->stream)); h->stream_busy = false; }   // earlier sends are complete and visible
+      sdb_ls_mailbox* mb = h->ls_mbox;
+      mb->agent = agent_idx[0]; mb->max_messages = static_cast<uint32_t>(std::min<uint64_t>(max_messages, rec_cap));
+      mb->flags = flags & 0x7FFFFFFFu;
+      const uint32_t seq = ++h->ls_seq;
+      __atomic_store_n(&mb->req_seq, seq, __ATOMIC_RELEASE);
+      uint64_t spins = 0;
+      while (__atomic_load_n(&mb->done_seq, __ATOMIC_ACQUIRE) != seq) {
+        if (++spins > (1ull << 33)) return fail(h, SDB_ECUDA, "latency server did not answer");
+        __builtin_ia32_pause();
+      }
+      unpack_small(h->ls_out, 1, count_out, hdr_out, payload_out, total_out, payload_bytes_out);
+      return SDB_OK;
+    }
     cudaError_t e = sdb_launch_receive_small(&h->view, agent_idx, n_agents, max_messages, flags, static_cast<uint32_t>(rec_cap),
                                              h->rx_plan, h->rx_small, h->stream, &h->prof);
     h->launches += 1;
@@ -1299,18 +1392,8 @@ int sdb_receive_batch(sdb_handle h, uint32_t n_agents, const uint32_t* agent_idx
       CUDA_TRY(h, cudaMemcpyAsync(h->small_host + window, h->rx_small + window, bytes - window, cudaMemcpyDeviceToHost, h->stream));
       CUDA_TRY(h, cudaStreamSynchronize(h->stream));
     }
-    if (count_out) std::memcpy(count_out, h->small_host + 16, static_cast<size_t>(n_agents) * sizeof(uint32_t));
-    const uint8_t* p = h->small_host + 64;
-    uint64_t poff = 0;
-    for (uint64_t r = 0; r < total; ++r) {
-      const sdb_msg_header* hd = reinterpret_cast<const sdb_msg_header*>(p);
-      hdr_out[r] = *hd;
-      const uint32_t pl = pad32(hd->len);
-      std::memcpy(payload_out + poff, p + 32, pl);
-      poff += pl; p += 32 + pl;
-    }
-    if (total_out) *total_out = total;
-    if (payload_bytes_out) *payload_bytes_out = poff;
+    unpack_small(h->small_host, n_agents, count_out, hdr_out, payload_out, total_out, payload_bytes_out);
+    (void)total;
     return SDB_OK;
   }
   if (agent_idx) {
@@ -1338,6 +1421,7 @@ int sdb_receive_batch(sdb_handle h, uint32_t n_agents, const uint32_t* agent_idx
   if (!(r.flags & SDB_RECV_PRIORITY)) r.plan_tops = nullptr;       // single-pass path: plan offsets are absolute
   h->last_rx = r; h->last_rx_valid = (e == cudaSuccess);
   if (e != cudaSuccess) return fail(h, SDB_ECUDA, std::string("receive launch: ") + cudaGetErrorString(e));
+  h->stream_busy = async;
   if (async) return SDB_OK;          // the caller consumes on the device (stream order) or asks sdb_last_receive_totals later
   CUDA_TRY(h, cudaMemcpyAsync(h->totals_host, h->rx_totals, 2 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, h->stream));
   if (count_out)
@@ -1507,6 +1591,7 @@ int sdb_get_backend_loads(sdb_handle h, uint32_t n, uint64_t* load_out) {
 
 static int ensure_req_cap(sdb_ctx* h, uint32_t n) {
   if (n <= h->be_req_cap) return SDB_OK;
+  { int rcl = ls_stop(h); if (rcl != SDB_OK) return rcl; }      // cudaFree below waits for running kernels
   CUDA_TRY(h, cudaStreamSynchronize(h->stream));
   if (h->be_req_cost) cudaFree(h->be_req_cost);
   if (h->be_out) cudaFree(h->be_out);

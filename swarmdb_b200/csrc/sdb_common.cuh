@@ -181,6 +181,13 @@ struct sdb_batch_base {
   uint32_t max_padlen;
   unsigned long long total_grans, total_recs;
 };
+// mailbox of the low-latency dequeue server (mapped pinned host memory; request and completion words on separate lines)
+struct sdb_ls_mailbox {
+  uint32_t req_seq, agent, max_messages, flags, quit, pad0[27];
+  uint32_t done_seq, pad1[31];
+};
+static_assert(sizeof(sdb_ls_mailbox) == 256, "latency mailbox must be 256 bytes");
+
 // cross-rank flags of an export buffer (last 128 bytes of the buffer, never touched by an export's copies)
 struct sdb_wire_ctrl {
   uint32_t ready;                   // last step whose export into this buffer is complete (written by the owner)

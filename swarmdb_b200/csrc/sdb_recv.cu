@@ -881,6 +881,127 @@ k_recv_small(sdb_dev_view v, sdb_small_agents ag, uint32_t n, uint32_t max_messa
   }
 }
 
+// ------------------------------------------------------------------------------------------
+// Low-latency dequeue SERVER: the same single-launch receive as k_recv_small for one agent, as a persistent CTA that
+// polls a mailbox in mapped pinned host memory and writes its answer (the k_recv_small output block) into pinned host
+// memory.  Request: {req_seq, agent, max_messages, flags}; the host bumps req_seq last.  Answer complete when
+// done_seq == req_seq.  quit != 0 ends the kernel.  Mailbox layout: sdb_ls_mailbox (sdb_common.cuh).
+// A persistent kernel sees other kernels' writes only through the L2: every request starts with a gpu-scope fence,
+// which also invalidates this SM's L1 (B300_MICROARCH: fence scope >= cluster emits CCTL.IVALL), and the ring header
+// is read with volatile loads.
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256, 1)
+k_latency_server(sdb_dev_view v, sdb_ls_mailbox* mb, uint8_t* out, uint32_t out_cap_bytes, uint4* plan) {
+  __shared__ uint32_t s_req[4];         // seq, agent, max_messages, flags
+  __shared__ uint32_t s_quit, s_cnt, s_total;
+  __shared__ uint32_t s_goff[SDB_SMALL_RECS + 1];
+  __shared__ uint2 s_fast[32];          // fast path: {arena handle, payload granules} of up to 32 records
+  const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  uint32_t served = 0;
+  if (tid == 0) served = *reinterpret_cast<volatile uint32_t*>(&mb->done_seq);
+  for (;;) {
+    if (tid == 0) {
+      // ONE 16-byte read per poll fetches the whole request {req_seq, agent, max_messages, flags}: every access to the
+      // mailbox is a PCIe round trip, so the fields must not be fetched one by one.  flags bit 31 = quit.
+      uint4 rq;
+      for (;;) {
+        asm volatile("ld.volatile.global.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(rq.x), "=r"(rq.y), "=r"(rq.z), "=r"(rq.w) : "l"(mb) : "memory");
+        if (rq.x != served || (rq.w & 0x80000000u)) break;
+        __nanosleep(20);
+      }
+      s_req[0] = rq.x; s_req[1] = rq.y; s_req[2] = rq.z; s_req[3] = rq.w & 0x7FFFFFFFu;
+      s_quit = rq.w >> 31;
+    }
+    __syncthreads();
+    if (s_quit) return;
+    __threadfence();                                    // fresh view of the rings and the arena (L1 invalidated)
+    const uint32_t a = s_req[1], max_messages = s_req[2], flags = s_req[3];
+    const uint32_t rec_cap = min(SDB_SMALL_RECS, out_cap_bytes / 64u);
+    uint32_t head = 0, tail = 0, nt = 0;
+    if (tid < 32) {                                     // warp 0: header, then (short stream-order answers) the entries themselves
+      uint32_t c = 0;
+      if (a < v.max_agents) {
+        const uint4 hd = __ldcv(reinterpret_cast<const uint4*>(v.ring_hdr + a));
+        head = hd.x; tail = hd.y; nt = hd.w;
+        c = min(min(tail - head - nt, max_messages), rec_cap);
+      }
+      const bool fast = c && c <= 32u && nt == 0 && !(flags & SDB_RECV_PRIORITY);
+      if (fast) {
+        // lane j owns record j: entry -> arena handle and size; offsets by a shuffle scan; nothing goes through memory
+        uint2 e = make_uint2(0u, 1u);
+        if (lane < c) e = __ldcv(sdb_ring_of(v, a) + ((head + lane) & (v.ring_slots - 1)));
+        const uint32_t g = lane < c ? (sdb_meta(e) & SDB_META_GLEN_MASK) : 0u;       // granules incl. the header
+        uint32_t incl = g;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { const uint32_t y = __shfl_up_sync(0xFFFFFFFFu, incl, o); if (lane >= o) incl += y; }
+        if (lane < c) { s_goff[lane] = incl - g; s_fast[lane] = make_uint2(e.x, g - 1u); }
+        if (lane == c - 1) s_goff[c] = incl;
+        if (lane == 0) {
+          s_total = c; s_cnt = 0xFFFFFFFFu;                                          // marker: plan lives in shared memory
+          if (!(flags & SDB_RECV_PEEK)) v.ring_hdr[a].head = head + c;
+        }
+      } else if (lane == 0) {
+        s_cnt = c;
+      }
+    }
+    __syncthreads();
+    const bool fastpath = s_cnt == 0xFFFFFFFFu;
+    const uint32_t cnt = fastpath ? 0u : s_cnt;
+    if (warp == 0 && cnt) {
+      const uint32_t H = __shfl_sync(0xFFFFFFFFu, head, 0), T = __shfl_sync(0xFFFFFFFFu, tail, 0);
+      const uint32_t NT = __shfl_sync(0xFFFFFFFFu, nt, 0);
+      select_agent_warp(v, plan, 0u, (flags & SDB_RECV_PRIORITY) != 0, a, H, T, NT, cnt, 0u, lane, !(flags & SDB_RECV_PEEK));
+      __threadfence_block();
+      __syncwarp();
+      // record offsets (granules, header included)
+      uint32_t run = 0;
+      for (uint32_t r0 = 0; r0 < cnt; r0 += 32) {
+        const uint32_t r = r0 + lane;
+        const uint32_t g = r < cnt ? plan[r].z + 1u : 0u;
+        uint32_t incl = g;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { const uint32_t y = __shfl_up_sync(0xFFFFFFFFu, incl, o); if (lane >= o) incl += y; }
+        if (r < cnt) s_goff[r] = run + incl - g;
+        run += __shfl_sync(0xFFFFFFFFu, incl, 31);
+      }
+      if (lane == 0) { s_goff[cnt] = run; s_total = cnt; }
+    }
+    if (tid == 0 && !cnt && !fastpath) { s_total = 0; s_goff[0] = 0; }
+    __syncthreads();
+    const uint32_t total = s_total;
+    const uint32_t l8 = tid & 7;
+    for (uint32_t r = tid >> 3; r < total; r += 32) {
+      uint32_t handle, g;
+      if (fastpath) { handle = s_fast[r].x; g = s_fast[r].y; } else { const uint4 pe = plan[r]; handle = pe.x; g = pe.z; }
+      const uint8_t* src = v.arena + ((static_cast<uint64_t>(handle) & v.gmask) << 5);
+      uint8_t* dst = out + 64 + (static_cast<size_t>(s_goff[r]) << 5);
+      const uint32_t nchunk = 2u + (g << 1);
+      for (uint32_t c = l8; c < nchunk; c += 8) *reinterpret_cast<uint4*>(dst + (c << 4)) = sdb_ld_stream(src + (c << 4));
+    }
+    if (tid == 0) {
+      // totals | granules | count: one 32-byte store group at the head of the answer block
+      reinterpret_cast<unsigned long long*>(out)[0] = total;
+      reinterpret_cast<unsigned long long*>(out)[1] = s_goff[total];
+      reinterpret_cast<uint32_t*>(out + 16)[0] = total;
+      if (total && !(flags & SDB_RECV_PEEK)) atomicAdd(&v.ctr->delivered, static_cast<unsigned long long>(total));
+    }
+    __threadfence_system();                              // the answer is in host memory before the completion flag
+    __syncthreads();
+    if (tid == 0) {
+      *reinterpret_cast<volatile uint32_t*>(&mb->done_seq) = s_req[0];
+      __threadfence_system();
+    }
+    served = s_req[0];
+    __syncthreads();
+  }
+}
+
+extern "C" cudaError_t sdb_launch_latency_server(const sdb_dev_view* v, sdb_ls_mailbox* mb_dev, uint8_t* out_dev, uint32_t out_cap,
+                                                 uint4* plan, cudaStream_t stream) {
+  k_latency_server<<<1, 256, 0, stream>>>(*v, mb_dev, out_dev, out_cap, plan);
+  return cudaGetLastError();
+}
+
 extern "C" cudaError_t sdb_launch_receive_small(const sdb_dev_view* v, const uint32_t* agents_host, uint32_t n,
                                                 uint32_t max_messages, uint32_t flags, uint32_t rec_cap,
                                                 uint4* plan, uint8_t* out,

@@ -376,3 +376,39 @@ def test_async_receive_enqueues_and_reports_totals_later():
     assert g.stats()["delivered"] == n
     with pytest.raises(SdbError):                                            # host outputs and ASYNC exclude each other
         g.receive_batch(idx, 5, RECV_ASYNC)
+
+
+def test_latency_server_answers_like_the_ordinary_path():
+    """sdb_latency_server: single-agent receives served by the persistent kernel (mailbox + answer in pinned host memory)
+    return exactly what the launched path returns - stream and priority order, peeks, empty queues, traffic arriving
+    between requests, and a stop/restart around a call that frees device memory."""
+    rng = np.random.default_rng(77)
+    A = 300
+    g, c = _pair(A, ring_slots=512)
+    idx = np.arange(A, dtype=np.uint32)
+    g.register(idx); c.register(idx)
+    g.latency_server(True)
+    from swarmdb_b200._native import RECV_PEEK, RECV_PRIORITY
+    for rnd in range(4):
+        n = 2000
+        s = rng.integers(0, A, n); r = rng.integers(0, A, n)
+        prio = rng.integers(0, 4, n); typ = rng.integers(0, 7, n)
+        lens, off, buf = _mk_payloads(rng, n, 256)
+        ts = rng.random(n)
+        assert g.send_batch(s, r, prio, typ, lens, off, buf, ts) == c.send_batch(s, r, prio, typ, lens, off, buf, ts)
+        for a in rng.integers(0, A, 60):
+            flags = [0, RECV_PRIORITY, RECV_PEEK, RECV_PEEK | RECV_PRIORITY][int(rng.integers(0, 4))]
+            k = int(rng.integers(1, 9))
+            hg, pg, _ = g.receive_one(int(a), k, flags)
+            cc, hc, pc = c.receive_batch([int(a)], k, flags)
+            assert hg.tobytes() == hc.tobytes() and pg.tobytes() == pc.tobytes(), (rnd, a, flags)
+        if rnd == 1:
+            st = g.stage(0, s[:10], r[:10], prio[:10], typ[:10], lens[:10], off[:10], buf)
+            g.free_staged(st)                                   # cudaFree inside: the server is stopped and restarted
+    _same(g.receive_batch(idx, 10000), c.receive_batch(idx, 10000))       # the bulk path sees the same queue state
+    hg, pg, _ = g.receive_one(5, 10, 0)
+    assert len(hg) == 0
+    g.latency_server(False)
+    st = g.stats()
+    assert st["enqueued"] == st["delivered"] == 8000
+    g.close(); c.close()
