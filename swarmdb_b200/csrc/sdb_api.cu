@@ -573,6 +573,16 @@ int sdb_create(const sdb_config* cfg, sdb_handle* out) {
     return fail(h, SDB_ECUDA, "no CUDA device: swarmdb_b200 has no CPU fallback");
   if (c.device < 0 || c.device >= ndev) return fail(h, SDB_EINVAL, "device ordinal out of range");
   CUDA_TRY(h, cudaSetDevice(c.device));
+  {
+    // L2 fetch granularity 64 bytes (device-wide limit of this process; SDB_L2_FETCH=128 restores the default, 0 leaves
+    // the limit alone).  The receive gather reads 288-byte records at 32-byte alignment in receiver order: with the
+    // default 128-byte granularity every record costs three full lines (1.37x its bytes, ncu); at 64 bytes the
+    // gather's DRAM reads drop from 1.66 GB to 1.40 GB per c2 step and it runs 4.5 % faster (0.464 -> 0.443 ms), the
+    // fan-out loses 1 % - measured on B200, profiles/README.md.
+    const char* fg = getenv("SDB_L2_FETCH");
+    const int gran = fg ? atoi(fg) : 64;
+    if (gran > 0) cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, static_cast<size_t>(gran));
+  }
   CUDA_TRY(h, sdb_send_prepare_device());
   CUDA_TRY(h, sdb_recv_prepare_device());
   cudaDeviceProp prop;
@@ -620,7 +630,7 @@ int sdb_create(const sdb_config* cfg, sdb_handle* out) {
   const size_t rtiles = (c.max_recv_records + SDB_SCAN_TILE - 1) / SDB_SCAN_TILE + 1;
   CUDA_TRY(h, dmalloc(&h->rx_plan, c.max_recv_records + 4)); CUDA_TRY(h, dmalloc(&h->rx_rec_off, A));
   CUDA_TRY(h, dmalloc(&h->rx_plan_tops, rtiles));
-  CUDA_TRY(h, dmalloc(&h->rx_lb, sdb_lb_words(static_cast<uint32_t>(A / 256 + 2)) + 4));
+  CUDA_TRY(h, dmalloc(&h->rx_lb, sdb_lb_words(static_cast<uint32_t>(A / 64 + 2)) + 4));
   CUDA_TRY(h, dmalloc(&h->rx_totals, 8));
   CUDA_TRY(h, dmalloc(&h->rx_big_list, A)); CUDA_TRY(h, dmalloc(&h->rx_big_count, 4));
   CUDA_TRY(h, dmalloc(&h->rx_count, A));

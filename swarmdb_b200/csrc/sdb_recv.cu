@@ -470,7 +470,10 @@ k_scan_plan(uint4* __restrict__ plan, uint32_t* __restrict__ tops, const unsigne
 //   r.lb               look-back scratch (layout in sdb_common.cuh, zeroed by the launcher), then the tile ticket, then
 //                      ~(records << 32 | granules) of the call, maintained with atomicMax (= min of the value)
 // ------------------------------------------------------------------------------------------
-#define SDB_PLAN_TILE 256u                      // request slots per tile (one per thread)
+#ifndef SDB_PLAN_WARPS
+#define SDB_PLAN_WARPS 8u
+#endif
+#define SDB_PLAN_TILE (32u * SDB_PLAN_WARPS)    // request slots per tile (one per thread)
 #define SDB_PLAN_STAGE 256u                     // plan entries staged per warp before a coalesced write
 // sum of the payload granules of the first C live entries of the window [H, T), whole warp
 __device__ __forceinline__ uint32_t holey_sum_warp(const uint2* rs, uint32_t mask, uint32_t H, uint32_t T, uint32_t C, uint32_t lane) {
@@ -500,12 +503,12 @@ __device__ __forceinline__ void fill_offsets_warp(uint4* plan, uint32_t RO, uint
   }
 }
 
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(SDB_PLAN_TILE)
 k_recv_plan(sdb_dev_view v, sdb_recv_args r, uint32_t tiles) {
   __shared__ uint32_t s_tile;
-  __shared__ unsigned long long s_wr[8], s_wg[8];
+  __shared__ unsigned long long s_wr[SDB_PLAN_WARPS], s_wg[SDB_PLAN_WARPS];
   __shared__ unsigned long long s_br, s_bg;
-  __shared__ uint4 s_stage[8][SDB_PLAN_STAGE];                // per warp: plan entries on their way out (32 KB)
+  __shared__ uint4 s_stage[SDB_PLAN_WARPS][SDB_PLAN_STAGE];                // per warp: plan entries on their way out (32 KB)
   const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const size_t ticket_at = static_cast<size_t>(tiles) + 3 * ((tiles + 31) / 32), totals_at = ticket_at + 1;
   if (tid == 0) s_tile = atomicAdd(reinterpret_cast<unsigned int*>(r.lb + ticket_at), 1u);
@@ -564,15 +567,15 @@ k_recv_plan(sdb_dev_view v, sdb_recv_args r, uint32_t tiles) {
   if (lane == 31) { s_wr[warp] = ir; s_wg[warp] = ig; }
   __syncthreads();
   if (warp == 0) {
-    const unsigned long long wr = lane < 8 ? s_wr[lane] : 0ull, wg = lane < 8 ? s_wg[lane] : 0ull;
+    const unsigned long long wr = lane < SDB_PLAN_WARPS ? s_wr[lane] : 0ull, wg = lane < SDB_PLAN_WARPS ? s_wg[lane] : 0ull;
     unsigned long long cr = wr, cg = wg;
 #pragma unroll
-    for (int o = 1; o < 8; o <<= 1) {
+    for (int o = 1; o < static_cast<int>(SDB_PLAN_WARPS); o <<= 1) {
       const unsigned long long yr = __shfl_up_sync(0xFFFFFFFFu, cr, o), yg = __shfl_up_sync(0xFFFFFFFFu, cg, o);
       if (lane >= o) { cr += yr; cg += yg; }
     }
-    const unsigned long long tr = __shfl_sync(0xFFFFFFFFu, cr, 7), tg = __shfl_sync(0xFFFFFFFFu, cg, 7);   // tile aggregate
-    if (lane < 8) { s_wr[lane] = cr - wr; s_wg[lane] = cg - wg; }                                           // exclusive warp offsets
+    const unsigned long long tr = __shfl_sync(0xFFFFFFFFu, cr, SDB_PLAN_WARPS - 1), tg = __shfl_sync(0xFFFFFFFFu, cg, SDB_PLAN_WARPS - 1);   // tile aggregate
+    if (lane < SDB_PLAN_WARPS) { s_wr[lane] = cr - wr; s_wg[lane] = cg - wg; }                                           // exclusive warp offsets
     // ---- hierarchical decoupled look-back (sdb_common.cuh): exclusive prefix of {records, granules} over earlier tiles
     unsigned long long er, eg, ga, gb; bool last;
     sdb_lb_prefix(r.lb, tile, tiles, tr, tg, lane, er, eg, last, ga, gb);
@@ -602,7 +605,7 @@ k_recv_plan(sdb_dev_view v, sdb_recv_args r, uint32_t tiles) {
     const uint32_t wtotal = __shfl_sync(0xFFFFFFFFu, winc, 31);
     // the warp's simple records are NOT contiguous in the plan when it also holds holey or truncated agents; they are
     // contiguous per agent, so stage (destination, entry) pairs: destination index travels in a side array
-    __shared__ uint32_t s_dst[8][SDB_PLAN_STAGE];
+    __shared__ uint32_t s_dst[SDB_PLAN_WARPS][SDB_PLAN_STAGE];
     const uint32_t lbase = winc - mycnt;                                        // local index of this lane's first entry
     for (uint32_t c0 = 0; c0 < wtotal; c0 += SDB_PLAN_STAGE) {
       uint32_t g0 = goff;
@@ -1069,7 +1072,7 @@ extern "C" cudaError_t sdb_launch_receive(const sdb_dev_view* v, const sdb_recv_
     r->plan_tops = nullptr;
     pi = sdb_prof_begin(prof, SDB_PK_RECV_SELECT, stream);
     cudaMemsetAsync(r->lb, 0, sdb_lb_words(tiles) * sizeof(unsigned long long), stream);
-    k_recv_plan<<<tiles, 256, 0, stream>>>(*v, *r, tiles);
+    k_recv_plan<<<tiles, SDB_PLAN_TILE, 0, stream>>>(*v, *r, tiles);
     sdb_prof_end(prof, pi, stream);
     if (n_launches) *n_launches += 1;
     return launch_gather(v, r, r->lb + sdb_lb_words(tiles) - 1, bound, max_rec_bytes, sm_count, stream, prof, n_launches);
