@@ -409,7 +409,7 @@ def run_sharded_bench(args, rank: int, world: int, local_rank: int, wl):
                     "ms_per_step": e2e_max / Ke},
             "gpu_launches": int(float(sm[4])),
             "roofline": {"kernel": "k_group_fanout", "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                         "frac": achieved / peak, "traffic": traffic_note(), "peak_source": peak_src,
+                         "frac": achieved / peak, "traffic": traffic_note("k_group_fanout_bytes_per_launch"), "peak_source": peak_src,
                          "algorithmic_bytes_per_msg": ALG_BYTES_FANOUT, "msgs_per_launch": local_msgs,
                          "ms_per_launch": fan_avg, "note": "rank 0's shard; per-send local fan-out is world-times narrower"},
             "kernels": {k: {"ms_per_launch": v[0] / v[1], "launches": v[1]} for k, v in prof.items() if v[1]},
