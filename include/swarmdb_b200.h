@@ -330,6 +330,15 @@ int sdb_import_wire_ptrs(sdb_handle h, uint32_t n_src, const void* const* wire_p
 int sdb_wire_wait_done(sdb_handle h, uint32_t n_src, const void* const* wire_ptrs, uint64_t wire_bytes, uint32_t step);
 int sdb_wire_publish(sdb_handle h, void* wire_dev, uint64_t wire_bytes, uint32_t step);
 int sdb_import_wire_ptrs_async(sdb_handle h, uint32_t n_src, const void* const* wire_ptrs, uint64_t wire_bytes, uint32_t step);
+/* Pipelining across steps: runs the flag wait and the localize pass of step `step` on a second stream of the handle,
+ * ordered after everything enqueued on the shard's stream so far and BESIDE what the caller enqueues next (typically
+ * the receive of the previous step, which is bound by HBM while the localize pass is bound by NVLink latency).  The
+ * following sdb_import_wire_ptrs_async(.., step) finds the batch localized and only places it (one single-thread
+ * kernel: arena base and sequence base still come from the device cursor, after the previous step's commit), then
+ * fans out and indexes as usual: delivery order and content are those of the unpipelined sequence.  Two buffer sets
+ * alternate by step parity.  The export buffers of `step` must not be rewritten and group membership / ownership must
+ * not change between the two calls.  A no-op for traffic outside the fast shape. */
+int sdb_import_prefetch(sdb_handle h, uint32_t n_src, const void* const* wire_ptrs, uint64_t wire_bytes, uint32_t step);
 
 /* ---- inbox / load queries on the device: get_agent_load, get_unread_message_count (M:1026-1094), get_stats (M:973-1024)
  * The reference answers these by walking its host dictionaries (`messages`, `agent_inbox`); the queue itself now lives

@@ -46,6 +46,7 @@ cudaError_t sdb_launch_import_localize(const sdb_import_args*, uint32_t, const u
 cudaError_t sdb_launch_wire_wait(const uint32_t* const*, uint32_t, uint32_t, cudaStream_t, const void* const*, sdb_wire_header*);
 cudaError_t sdb_launch_wire_set(uint32_t*, uint32_t, cudaStream_t);
 cudaError_t sdb_launch_import_fused(const sdb_import2_args*, cudaStream_t, sdb_profiler*, int*);
+cudaError_t sdb_launch_import_place(const sdb_import_totals*, sdb_cursor*, sdb_batch_base*, unsigned long long, uint32_t, uint32_t*, cudaStream_t);
 cudaError_t sdb_launch_arena_floor_cur(const sdb_dev_view*, uint32_t, sdb_cursor*, cudaStream_t);
 }
 
@@ -117,6 +118,14 @@ struct sdb_ctx {
   bool dev_stale = true;                       // the host counters moved: push them before the next async import
   uint32_t* xs_gs_off_src = nullptr; uint32_t* xs_gs_idx_src = nullptr; uint32_t* xs_first = nullptr;
   unsigned long long* xs_lb = nullptr; sdb_wire_header* xs_hdrs = nullptr;
+  // localized-import buffer sets: set 0 aliases the buffers above; set 1 exists once sdb_import_prefetch was used (an
+  // import of step k+1 is localized on `pf_stream` while step k's kernels still read the set of the other parity)
+  struct XsSet {
+    sdb_send_desc* descs = nullptr; uint32_t* gs_off_src = nullptr; uint32_t* gs_idx_src = nullptr; uint32_t* first = nullptr;
+    unsigned long long* lb = nullptr; sdb_wire_header* hdrs = nullptr; uint32_t* tmp_list = nullptr;
+    sdb_import_totals* totals = nullptr; cudaEvent_t ready = nullptr; uint32_t step = 0; bool pending = false;
+  } xset[2];
+  cudaStream_t pf_stream = nullptr; cudaEvent_t ev_pf_fork = nullptr;
   uint8_t* wire_host = nullptr;                // pinned: header + descriptors of an export
   sdb_wire_header* hdrs_host = nullptr;        // pinned [num_shards]
   cudaEvent_t staging_free = nullptr;    // previous H2D of pinned staging has completed
@@ -681,6 +690,13 @@ int sdb_create(const sdb_config* cfg, sdb_handle* out) {
     CUDA_TRY(h, dmalloc(&h->xs_first, SDB_MAX_SRC + 1)); CUDA_TRY(h, dmalloc(&h->xs_lb, sdb_lb_words(static_cast<uint32_t>(n / 256 + 2)) + 4));
     CUDA_TRY(h, dmalloc(&h->cursor_dev, 1)); CUDA_TRY(h, dmalloc(&h->bb_dev, 1)); CUDA_TRY(h, dmalloc(&h->xs_hdrs, SDB_MAX_SRC));
     CUDA_TRY(h, cudaMemset(h->cursor_dev, 0, sizeof(sdb_cursor))); CUDA_TRY(h, cudaMemset(h->bb_dev, 0, sizeof(sdb_batch_base)));
+    {
+      auto& S0 = h->xset[0];
+      S0.descs = h->xs_descs; S0.gs_off_src = h->xs_gs_off_src; S0.gs_idx_src = h->xs_gs_idx_src; S0.first = h->xs_first;
+      S0.lb = h->xs_lb; S0.hdrs = h->xs_hdrs; S0.tmp_list = h->scratch.list_dev;
+      CUDA_TRY(h, dmalloc(&S0.totals, 1));
+      CUDA_TRY(h, cudaEventCreateWithFlags(&S0.ready, cudaEventDisableTiming));
+    }
     CUDA_TRY(h, cudaHostAlloc(reinterpret_cast<void**>(&h->cursor_host), sizeof(sdb_cursor), cudaHostAllocDefault));
     std::memset(h->cursor_host, 0, sizeof(sdb_cursor));
     h->xs_meta_stride = wire_meta_bytes(c.max_batch_sends, c.max_groups);
@@ -707,6 +723,14 @@ int sdb_destroy(sdb_handle h) {
   if (h->ls_out) cudaFreeHost(h->ls_out);
   if (h->ls_plan) cudaFree(h->ls_plan);
   if (h->stream) cudaStreamSynchronize(h->stream);
+  if (h->pf_stream) { cudaStreamSynchronize(h->pf_stream); cudaStreamDestroy(h->pf_stream); }
+  if (h->ev_pf_fork) cudaEventDestroy(h->ev_pf_fork);
+  {
+    auto& S1 = h->xset[1];
+    void* own[] = {S1.descs, S1.gs_off_src, S1.gs_idx_src, S1.first, S1.lb, S1.hdrs, S1.tmp_list, S1.totals, h->xset[0].totals};
+    for (void* p : own) if (p) cudaFree(p);
+    for (auto& S : h->xset) if (S.ready) cudaEventDestroy(S.ready);
+  }
   void* dev[] = {h->arena, h->ring_hdr, h->ring, h->members, h->ctr, h->gexcl_dev, h->rx_rec_off, h->rx_lb,
                  h->xs_gs_off_src, h->xs_gs_idx_src, h->xs_first, h->xs_lb, h->cursor_dev, h->bb_dev, h->xs_hdrs, h->owned_dev, h->agent_backend_dev,
                  h->scratch.descs_dev, h->scratch.payload_dev, h->scratch.list_dev, h->scratch.gs_off_dev,
@@ -1171,51 +1195,115 @@ int sdb_wire_wait_done(sdb_handle h, uint32_t n_src, const void* const* wire_ptr
   return SDB_OK;
 }
 
-int sdb_import_wire_ptrs_async(sdb_handle h, uint32_t n_src, const void* const* wire_ptrs, uint64_t wire_bytes, uint32_t step) {
+// traffic shapes the device-only import handles (everything else takes the synchronous body between the same flags)
+static bool async_fast(const sdb_ctx* h) {
+  return pad32(h->cfg.max_payload_bytes) <= 512 && h->n_shared_agents == 0 && h->n_excl_groups != 0 && h->cfg.fanout_variant >= 2;
+}
+
+// wait for the sources' flags + fused localize into buffer set S, on stream `st`; `defer`: leave the placement to
+// k_import_place (the cursor belongs to the shard's stream)
+static int xs_localize(sdb_ctx* h, sdb_ctx::XsSet& S, uint32_t n_src, const void* const* wire_ptrs, uint64_t wire_bytes,
+                       uint32_t step, cudaStream_t st, bool defer) {
+  const uint32_t* ready[SDB_MAX_SRC];
+  for (uint32_t k = 0; k < n_src; ++k) ready[k] = ctrl_word(wire_ptrs[k], wire_bytes, 0);
+  const int pw = sdb_prof_begin(&h->prof, SDB_PK_XWAIT, st);
+  CUDA_TRY(h, sdb_launch_wire_wait(ready, n_src, step, st, wire_ptrs, S.hdrs));
+  sdb_prof_end(&h->prof, pw, st);
+  sdb_import2_args a{};
+  for (uint32_t k = 0; k < n_src; ++k) a.wire[k] = static_cast<const uint8_t*>(wire_ptrs[k]);
+  a.n_src = n_src; a.max_sends = h->cfg.max_batch_sends; a.max_groups = h->cfg.max_groups; a.shard_id = h->cfg.shard_id;
+  a.max_agents = h->cfg.max_agents; a.lcount = h->lcount_dev; a.lstart = h->lstart_dev; a.shard_of = h->shard_of_dev;
+  a.descs = S.descs; a.gs_off_src = S.gs_off_src; a.gs_idx_src = S.gs_idx_src; a.first = S.first;
+  a.tmp_list = S.tmp_list; a.list_cap = static_cast<uint32_t>(std::min<uint64_t>(h->cfg.list_pool_entries, 0x7FFFFFF0ull));
+  a.lb = S.lb; a.cur = h->cursor_dev; a.bb = h->bb_dev; a.arena_grans = h->arena_grans;
+  a.hdrs = S.hdrs; a.commit_count = h->rx_big_count + 1; a.totals = defer ? S.totals : nullptr;
+  int nl = 1;
+  cudaError_t e = sdb_launch_import_fused(&a, st, &h->prof, &nl);
+  h->launches += nl;
+  if (e != cudaSuccess) return fail(h, SDB_ECUDA, std::string("import localize launch: ") + cudaGetErrorString(e));
+  return SDB_OK;
+}
+
+static int import_args_check(sdb_handle h, uint32_t n_src, const void* const* wire_ptrs, uint64_t wire_bytes) {
   if (!h || !wire_ptrs || n_src == 0 || wire_bytes < sizeof(sdb_wire_ctrl)) return SDB_EINVAL;
   if (n_src > h->cfg.num_shards || n_src > SDB_MAX_SRC) return fail(h, SDB_EINVAL, "n_src > num_shards (or > 16)");
   for (uint32_t k = 0; k < n_src; ++k) if (!wire_ptrs[k]) return fail(h, SDB_EINVAL, "null wire pointer");
   { int rc1 = ensure_ltab(h); if (rc1 != SDB_OK) return rc1; }
   if (h->memb_dirty) { int rc0 = rebuild_inverse(h); if (rc0 != SDB_OK) return rc0; }
-  // 1. wait (on the stream, not on the host) until every source's export of this step is complete
-  const uint32_t* ready[SDB_MAX_SRC];
-  for (uint32_t k = 0; k < n_src; ++k) ready[k] = ctrl_word(wire_ptrs[k], wire_bytes, 0);
-  const int pw = sdb_prof_begin(&h->prof, SDB_PK_XWAIT, h->stream);
-  CUDA_TRY(h, sdb_launch_wire_wait(ready, n_src, step, h->stream, wire_ptrs, h->xs_hdrs));
-  sdb_prof_end(&h->prof, pw, h->stream);
+  return SDB_OK;
+}
+
+int sdb_import_prefetch(sdb_handle h, uint32_t n_src, const void* const* wire_ptrs, uint64_t wire_bytes, uint32_t step) {
+  { int rc = import_args_check(h, n_src, wire_ptrs, wire_bytes); if (rc != SDB_OK) return rc; }
+  if (!async_fast(h)) return SDB_OK;                  // the synchronous body has nothing to run ahead
+  if (!h->pf_stream) {
+    auto& S1 = h->xset[1];
+    const size_t n = h->xs_cap, G1 = static_cast<size_t>(h->cfg.max_groups) + 1;
+    CUDA_TRY(h, cudaStreamCreateWithFlags(&h->pf_stream, cudaStreamNonBlocking));
+    CUDA_TRY(h, cudaEventCreateWithFlags(&h->ev_pf_fork, cudaEventDisableTiming));
+    CUDA_TRY(h, dmalloc(&S1.descs, n)); CUDA_TRY(h, dmalloc(&S1.gs_off_src, G1 * h->cfg.num_shards)); CUDA_TRY(h, dmalloc(&S1.gs_idx_src, n));
+    CUDA_TRY(h, dmalloc(&S1.first, SDB_MAX_SRC + 1)); CUDA_TRY(h, dmalloc(&S1.lb, sdb_lb_words(static_cast<uint32_t>(n / 256 + 2)) + 4));
+    CUDA_TRY(h, dmalloc(&S1.hdrs, SDB_MAX_SRC)); CUDA_TRY(h, dmalloc(&S1.tmp_list, h->cfg.list_pool_entries));
+    CUDA_TRY(h, dmalloc(&S1.totals, 1));
+    CUDA_TRY(h, cudaEventCreateWithFlags(&S1.ready, cudaEventDisableTiming));
+  }
+  auto& S = h->xset[step & 1u];
+  if (S.pending) return S.step == step ? SDB_OK : fail(h, SDB_EINVAL, "a prefetched import of this parity has not been imported yet");
+  // the set's previous user (the import two steps ago) and the table uploads above are ordered before the prefetch;
+  // what the caller enqueues on the shard's stream AFTER this call (the receive of the current step) runs beside it
+  CUDA_TRY(h, cudaEventRecord(h->ev_pf_fork, h->stream));
+  CUDA_TRY(h, cudaStreamWaitEvent(h->pf_stream, h->ev_pf_fork, 0));
+  { int rc = xs_localize(h, S, n_src, wire_ptrs, wire_bytes, step, h->pf_stream, true); if (rc != SDB_OK) return rc; }
+  CUDA_TRY(h, cudaEventRecord(S.ready, h->pf_stream));
   h->launches += 1;
+  S.pending = true; S.step = step;
+  return SDB_OK;
+}
+
+int sdb_import_wire_ptrs_async(sdb_handle h, uint32_t n_src, const void* const* wire_ptrs, uint64_t wire_bytes, uint32_t step) {
+  { int rc = import_args_check(h, n_src, wire_ptrs, wire_bytes); if (rc != SDB_OK) return rc; }
   uint32_t* my_done = ctrl_word(wire_ptrs[h->cfg.shard_id < n_src ? h->cfg.shard_id : 0], wire_bytes, 1);
-  const bool fast = pad32(h->cfg.max_payload_bytes) <= 512 && h->n_shared_agents == 0 && h->n_excl_groups != 0 &&
-                    h->cfg.fanout_variant >= 2;
-  if (!fast) {
+  if (!async_fast(h)) {
     // general traffic shapes (payloads above 512 bytes, agents in several groups): the synchronous import body
+    // 1. wait (on the stream, not on the host) until every source's export of this step is complete
+    const uint32_t* ready[SDB_MAX_SRC];
+    for (uint32_t k = 0; k < n_src; ++k) ready[k] = ctrl_word(wire_ptrs[k], wire_bytes, 0);
+    const int pw = sdb_prof_begin(&h->prof, SDB_PK_XWAIT, h->stream);
+    CUDA_TRY(h, sdb_launch_wire_wait(ready, n_src, step, h->stream, wire_ptrs, h->xs_hdrs));
+    sdb_prof_end(&h->prof, pw, h->stream);
+    h->launches += 1;
     int rc = sdb_import_wire_ptrs(h, n_src, wire_ptrs, nullptr);
     if (rc != SDB_OK) return rc;
     CUDA_TRY(h, sdb_launch_wire_set(my_done, step, h->stream));
     h->launches += 1;
     return SDB_OK;
   }
-  // 2. everything else happens on the device
+  auto& S = h->xset[h->pf_stream ? (step & 1u) : 0u];
+  const bool prefetched = S.pending && S.step == step;
+  // everything happens on the device
   { int rc2 = cursor_to_dev(h); if (rc2 != SDB_OK) return rc2; }
   CUDA_TRY(h, sdb_launch_arena_floor_cur(&h->view, h->n_agents, h->cursor_dev, h->stream));
-  sdb_import2_args a{};
-  for (uint32_t k = 0; k < n_src; ++k) a.wire[k] = static_cast<const uint8_t*>(wire_ptrs[k]);
-  a.n_src = n_src; a.max_sends = h->cfg.max_batch_sends; a.max_groups = h->cfg.max_groups; a.shard_id = h->cfg.shard_id;
-  a.max_agents = h->cfg.max_agents; a.lcount = h->lcount_dev; a.lstart = h->lstart_dev; a.shard_of = h->shard_of_dev;
-  a.descs = h->xs_descs; a.gs_off_src = h->xs_gs_off_src; a.gs_idx_src = h->xs_gs_idx_src; a.first = h->xs_first;
-  a.tmp_list = h->scratch.list_dev; a.list_cap = static_cast<uint32_t>(std::min<uint64_t>(h->cfg.list_pool_entries, 0x7FFFFFF0ull));
-  a.lb = h->xs_lb; a.cur = h->cursor_dev; a.bb = h->bb_dev; a.arena_grans = h->arena_grans;
-  a.hdrs = h->xs_hdrs; a.commit_count = h->rx_big_count + 1;
-  int nl = 1;
-  cudaError_t e = sdb_launch_import_fused(&a, h->stream, &h->prof, &nl);
+  if (S.pending) { CUDA_TRY(h, cudaStreamWaitEvent(h->stream, S.ready, 0)); S.pending = false; }
+  if (prefetched) {
+    // 1. the flags were awaited and the batch localized ahead of time (sdb_import_prefetch): place it now
+    CUDA_TRY(h, sdb_launch_import_place(S.totals, h->cursor_dev, h->bb_dev, h->arena_grans,
+                                        static_cast<uint32_t>(std::min<uint64_t>(h->cfg.list_pool_entries, 0x7FFFFFF0ull)),
+                                        h->rx_big_count + 1, h->stream));
+    h->launches += 1;
+  } else {
+    // 1. wait (on the stream, not on the host) until every source's export of this step is complete; 2. localize + place
+    int rc = xs_localize(h, S, n_src, wire_ptrs, wire_bytes, step, h->stream, false);
+    if (rc != SDB_OK) return rc;
+    h->launches += 1;
+  }
+  int nl = 0;
   const uint32_t n_cap = n_src * h->cfg.max_batch_sends;
-  if (e == cudaSuccess)
-    e = sdb_launch_fanout(&h->view, h->xs_descs, n_cap, nullptr, h->scratch.list_dev, 0, 0, pad32(h->cfg.max_payload_bytes), 3,
-                          h->sm_count, h->stream, &h->prof, h->bb_dev);
+  cudaError_t e = sdb_launch_fanout(&h->view, S.descs, n_cap, nullptr, S.tmp_list, 0, 0, pad32(h->cfg.max_payload_bytes), 3,
+                                    h->sm_count, h->stream, &h->prof, h->bb_dev);
   if (e == cudaSuccess) {
-    sdb_pull_view pv{h->memb_off_dev, h->memb_grp_dev, h->memb_pos_dev, h->xs_gs_off_src, h->xs_gs_idx_src, n_src,
-                     h->cfg.max_groups + 1, h->cfg.max_batch_sends, h->xs_first};
-    e = sdb_launch_pull(&h->view, &pv, h->xs_descs, h->n_agents, h->cfg.max_groups, h->gexcl_dev, h->n_excl_groups, 0,
+    sdb_pull_view pv{h->memb_off_dev, h->memb_grp_dev, h->memb_pos_dev, S.gs_off_src, S.gs_idx_src, n_src,
+                     h->cfg.max_groups + 1, h->cfg.max_batch_sends, S.first};
+    e = sdb_launch_pull(&h->view, &pv, S.descs, h->n_agents, h->cfg.max_groups, h->gexcl_dev, h->n_excl_groups, 0,
                         h->lstart_dev, h->lcount_dev, 0, 0, h->stream, &h->prof, &nl, h->bb_dev);
   }
   // point-to-point / broadcast copies claimed their slots with atomics: sort them into place (the kernels return at

@@ -181,6 +181,12 @@ struct sdb_batch_base {
   uint32_t max_padlen;
   unsigned long long total_grans, total_recs;
 };
+// grand totals of one localized import, kept between a prefetch (k_import_fused on the prefetch stream, while the previous
+// step still runs) and its placement (k_import_place on the shard's stream, after the previous step's commit)
+struct sdb_import_totals {
+  unsigned long long need, lists, total_recs, explicit_end;
+  uint32_t n_total, n_other, maxpad, pad;
+};
 // mailbox of the low-latency dequeue server (mapped pinned host memory; request and completion words on separate lines)
 struct sdb_ls_mailbox {
   uint32_t req_seq, agent, max_messages, flags, quit, pad0[27];
@@ -251,6 +257,8 @@ struct sdb_import2_args {
   unsigned long long arena_grans;
   const sdb_wire_header* hdrs;        // [n_src] local copies of the wire headers (made by k_wire_wait)
   uint32_t* commit_count;             // reset here for the commit sort that follows the fan-out
+  sdb_import_totals* totals;          // prefetch mode (non-null): the grand totals go here and k_import_place places the
+                                      // import later, on the shard's stream (the cursor is not touched by this kernel)
 };
 
 // ---- optional per-kernel timing with CUDA events on the launching stream (bench / roofline) ----

@@ -276,6 +276,32 @@ __global__ void k_wire_set(uint32_t* flag, uint32_t step) {
 
 #define SDB_IMP_TILE 256u
 
+// Places one localized import: arena base from the device cursor (wrap rule, floor check), sequence base, totals ->
+// sdb_batch_base for the kernels that follow.  One thread; the floor scan ran just before on the same stream.
+__device__ __forceinline__ void sdb_place_import(const sdb_import_totals& t, sdb_cursor* c, sdb_batch_base* b,
+                                                 unsigned long long G, uint32_t list_cap, uint32_t* commit_count) {
+  unsigned long long tail = c->arena_tail;
+  const unsigned long long floor_now = tail - c->floor_dist;
+  if (floor_now > c->arena_floor) c->arena_floor = floor_now;
+  if ((tail & (G - 1)) + t.need > G) tail = (tail + G - 1) & ~(G - 1);      // an import never straddles the wrap
+  uint32_t skip = 0;
+  if (t.need > G || tail + t.need - c->arena_floor > G) { skip = 1; c->error |= 1ull; }
+  if (t.lists > list_cap) { skip = 1; c->error |= 2ull; }
+  if (t.maxpad > 512) { skip = 1; c->error |= 4ull; }                       // the asynchronous path only drives the span kernel
+  b->arena_base = tail; b->seq_base = c->next_seq; b->n_total = t.n_total; b->n_other = t.n_other; b->skip = skip;
+  b->max_padlen = t.maxpad; b->total_grans = t.need; b->total_recs = t.total_recs;
+  if (commit_count) *commit_count = 0u;                                     // worklist of the commit sort that follows
+  if (!skip) {
+    c->arena_tail = tail + t.need;
+    const unsigned long long ns = c->next_seq + (t.explicit_end ? 0ull : t.total_recs);
+    c->next_seq = ns > t.explicit_end ? ns : t.explicit_end;
+  }
+}
+__global__ void k_import_place(const sdb_import_totals* t, sdb_cursor* c, sdb_batch_base* b, unsigned long long G,
+                               uint32_t list_cap, uint32_t* commit_count) {
+  if (threadIdx.x == 0 && blockIdx.x == 0) sdb_place_import(*t, c, b, G, list_cap, commit_count);
+}
+
 __global__ void __launch_bounds__(256)
 k_import_fused(sdb_import2_args a, uint32_t tiles_cap) {
   __shared__ uint32_t s_tile;
@@ -401,32 +427,15 @@ k_import_fused(sdb_import2_args a, uint32_t tiles_cap) {
     if (lane == 0) {
       s_ba = ea; s_bb = eb;
       if (last) {
-        // ---- place the whole import (the grand totals are known here and only here)
-        const unsigned long long need = ga, lists = gb;
-        sdb_cursor* c = a.cur;
-        const unsigned long long G = a.arena_grans;
-        unsigned long long tail = c->arena_tail;
-        const unsigned long long floor_now = tail - c->floor_dist;          // floor scan ran just before this kernel
-        if (floor_now > c->arena_floor) c->arena_floor = floor_now;
-        if ((tail & (G - 1)) + need > G) tail = (tail + G - 1) & ~(G - 1);      // an import never straddles the wrap
-        unsigned long long total_recs = 0, explicit_end = 0; uint32_t n_other = 0, maxpad = 0;
+        // ---- the grand totals are known here and only here
+        sdb_import_totals t;
+        t.need = ga; t.lists = gb; t.total_recs = 0; t.explicit_end = 0; t.n_total = n_total; t.n_other = 0; t.maxpad = 0; t.pad = 0;
         for (uint32_t s = 0; s < a.n_src; ++s) {
-          total_recs += s_totalrecs[s]; n_other += s_nother[s]; maxpad = max(maxpad, s_maxpad[s]);
-          if (s_explicit[s]) explicit_end = max(explicit_end, s_seqbase[s] + s_totalrecs[s]);
+          t.total_recs += s_totalrecs[s]; t.n_other += s_nother[s]; t.maxpad = max(t.maxpad, s_maxpad[s]);
+          if (s_explicit[s]) t.explicit_end = max(t.explicit_end, s_seqbase[s] + s_totalrecs[s]);
         }
-        uint32_t skip = 0;
-        if (need > G || tail + need - c->arena_floor > G) { skip = 1; c->error |= 1ull; }
-        if (lists > a.list_cap) { skip = 1; c->error |= 2ull; }
-        if (maxpad > 512) { skip = 1; c->error |= 4ull; }                    // the asynchronous path only drives the span kernel
-        sdb_batch_base* b = a.bb;
-        b->arena_base = tail; b->seq_base = c->next_seq; b->n_total = n_total; b->n_other = n_other; b->skip = skip;
-        b->max_padlen = maxpad; b->total_grans = need; b->total_recs = total_recs;
-        if (a.commit_count) *a.commit_count = 0u;                          // worklist of the commit sort that follows
-        if (!skip) {
-          c->arena_tail = tail + need;
-          const unsigned long long ns = c->next_seq + (explicit_end ? 0ull : total_recs);
-          c->next_seq = ns > explicit_end ? ns : explicit_end;
-        }
+        if (a.totals) *a.totals = t;                                         // prefetched: placed later (k_import_place)
+        else sdb_place_import(t, a.cur, a.bb, a.arena_grans, a.list_cap, a.commit_count);
       }
     }
   }
@@ -483,6 +492,12 @@ extern "C" cudaError_t sdb_launch_wire_set(uint32_t* flag, uint32_t step, cudaSt
   k_wire_set<<<1, 1, 0, stream>>>(flag, step);
   return cudaGetLastError();
 }
+extern "C" cudaError_t sdb_launch_import_place(const sdb_import_totals* t, sdb_cursor* c, sdb_batch_base* b, unsigned long long G,
+                                               uint32_t list_cap, uint32_t* commit_count, cudaStream_t stream) {
+  k_import_place<<<1, 32, 0, stream>>>(t, c, b, G, list_cap, commit_count);
+  return cudaGetLastError();
+}
+
 extern "C" cudaError_t sdb_launch_import_fused(const sdb_import2_args* a, cudaStream_t stream, sdb_profiler* prof, int* n_launches) {
   const uint32_t n_cap = a->n_src * a->max_sends;
   const uint32_t tiles = (n_cap + SDB_IMP_TILE - 1) / SDB_IMP_TILE;

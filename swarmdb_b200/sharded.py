@@ -99,6 +99,10 @@ class PeerExchange:
       import_all  the import's first kernel spins until every source's ready >= step (peer flags polled over NVLink),
                   then the import + fan-out kernels pull descriptors and payloads straight out of the exporting GPUs'
                   memory; afterwards done = step
+      prefetch    optional, between an export and its import_all: the flag wait and the descriptor pull of the NEXT
+                  step run on a second stream beside whatever is enqueued afterwards (the receive of the current
+                  step); import_all then only places, fans out and indexes.  Pipelined producers call
+                  export(k+1); prefetch(); receive(k); import_all().
     """
 
     def __init__(self, shard, rank: int, world: int, max_sends: int, max_payload: int, device, stream=None):
@@ -124,6 +128,8 @@ class PeerExchange:
                     self.ptrs[b][r] = p
                     self.opened.append(p)
         self.step_no = 0                       # steps completed; the next one is step_no + 1 and uses buffer (step_no + 1) & 1
+        self._published = 0                    # last step whose export this rank published
+        self._prefetched = 0                   # last step handed to the shard's prefetch stream
 
     @property
     def next_step(self) -> int:
@@ -135,6 +141,8 @@ class PeerExchange:
 
     def _begin_export(self) -> int:
         k = self.next_step
+        if self._published >= k:
+            raise RuntimeError(f"step {k} was already exported; import it before exporting again")
         if k > 2:                              # peers read this buffer during step k - 2: wait (on the stream) until they are done
             self.shard.wire_wait_done(self.ptrs[k & 1], self.wire_bytes, k - 2)
         return k
@@ -144,6 +152,7 @@ class PeerExchange:
         self.shard.export_group_batch(sender, group, prio, typ, lens, payload_off, payload,
                                       self.mine[k & 1][0], self.wire_bytes, ts)
         self.shard.wire_publish(self.mine[k & 1][0], self.wire_bytes, k)
+        self._published = k
 
     def export_mixed(self, sender, kind, target, list_off, list_idx, prio, typ, lens, payload_off, payload, ts=None,
                      seq_base: int = 0) -> None:
@@ -151,12 +160,26 @@ class PeerExchange:
         self.shard.export_mixed_batch(sender, kind, target, list_off, list_idx, prio, typ, lens, payload_off, payload,
                                       self.mine[k & 1][0], self.wire_bytes, ts, seq_base)
         self.shard.wire_publish(self.mine[k & 1][0], self.wire_bytes, k)
+        self._published = k
 
     def republish(self) -> None:
         """Benchmarks with device-resident inputs: the buffer of this parity already holds a wire batch (exported
         before the timed region); declare it ready for the next step without copying anything."""
         k = self.next_step
+        if self._published >= k:
+            return
         self.shard.wire_publish(self.mine[k & 1][0], self.wire_bytes, k)
+        self._published = k
+
+    def prefetch(self) -> None:
+        """Start the next step's flag wait + descriptor pull on the shard's prefetch stream (this rank's own export of
+        that step must be published already: every rank waits for every source, itself included)."""
+        k = self.next_step
+        if self._published < k:
+            raise RuntimeError("prefetch before this rank exported the step")
+        if self._prefetched < k:
+            self.shard.import_prefetch(self.ptrs[k & 1], self.wire_bytes, k)
+            self._prefetched = k
 
     def exchange(self) -> None:
         return None                            # nothing to do: import_all waits for the sources' flags on the device
@@ -272,8 +295,11 @@ def run_sharded_bench(args, rank: int, world: int, local_rank: int, wl):
                 wires.append(ex.send_buf.clone())
 
         phase_ev = []
+        # cross-step pipelining (peer transport): while step k's receive runs, the flag wait and the descriptor pull of
+        # step k + 1 run on the shard's prefetch stream (PeerExchange.prefetch)
+        pipelined = transport == "peer" and world > 1 and os.environ.get("SDB_PIPELINE", "1") != "0"
 
-        def device_step(i, timed=False):
+        def device_step(i, timed=False, start_next=True):
             evs = [torch.cuda.Event(enable_timing=True) for _ in range(5)] if timed else None
             if timed:
                 evs[0].record(stream)
@@ -288,6 +314,9 @@ def run_sharded_bench(args, rank: int, world: int, local_rank: int, wl):
             if timed:
                 evs[2].record(stream)
             ex.import_all()
+            if pipelined and start_next:
+                ex.republish()                              # the next step's pre-exported wire batch: flag only
+                ex.prefetch()
             if timed:
                 evs[3].record(stream)
             # SDB_RECV_OWNED: the device-resident list of the agents this shard owns (no index upload, 1/world of the slots)
@@ -319,6 +348,9 @@ def run_sharded_bench(args, rank: int, world: int, local_rank: int, wl):
         launches = st_end["kernel_launches"] - launches0
         delivered = st_end["delivered"] - st0["delivered"]
         assert st_end["ring_overflow"] == 0, f"ring overflow on rank {rank}: {st_end['ring_overflow']} records (ring_slots={ring_slots})"
+        if pipelined:                                       # the step prefetched by the last timed one: import it, start no other
+            device_step(W + K, start_next=False)
+            torch.cuda.synchronize()
 
         # ---- e2e: host buffers in (export H2D), results out (D2H into pinned buffers)
         pin_hdr = torch.empty(recv_cap * 32, dtype=torch.uint8, pin_memory=True).numpy().view(HDR_DTYPE)
@@ -397,9 +429,12 @@ def run_sharded_bench(args, rank: int, world: int, local_rank: int, wl):
                        "transport_detail": ("peer memory: import/fan-out kernels pull descriptors and payloads from the "
                                             "exporting GPUs over NVLink" if transport == "peer"
                                             else "wire batches all-gathered over NCCL/NVLink"),
-                       "timed_region": "exchange barrier + import (localize, fan-out, index) + receive; the wire batches "
+                       "timed_region": "flag wait + import (localize, fan-out, index) + receive; the wire batches "
                                        "are exported to HBM before the timed region (device-resident inputs, like N=1's "
                                        "staged batches); the export (host descriptor build + H2D) is inside `e2e` only",
+                       "pipelined": ("the flag wait + descriptor pull of step k+1 run on a second stream beside step k's receive "
+                                     "(sdb_import_prefetch); every step still does all of its work inside the timed region"
+                                     if pipelined else False),
                        "l2": "inputs larger than L2 (each shard writes and reads back ~1.2 GB of records per step)",
                        "parallelism": f"shard{world}", "ring_slots": ring_slots},
             "clocks": clk,

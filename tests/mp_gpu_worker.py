@@ -3,7 +3,8 @@
 One process per GPU over NCCL.  Two checks, both against single-shard ground truth (tier T4):
 
   A. transport content parity: every rank ingests its own batches of group sends; wire batches travel through the
-     REAL cross-process transport (default: CUDA-IPC peer memory pulled by the import/fan-out kernels; `nccl`:
+     REAL cross-process transport (default: CUDA-IPC peer memory pulled by the import/fan-out kernels; `prefetch`:
+     the same with the next step's flag wait + descriptor pull running ahead on the prefetch stream; `nccl`:
      all-gather), alternating the two export buffers; every shard drains its agents and folds per-agent stream
      digests on the device; the digests of all shards together must equal oracle/cpu_ref.c's digests of ONE queue
      fed the concatenated rank-major batches (per-agent order, header fields, payload bytes).
@@ -40,7 +41,7 @@ def transport_parity(rank, world, dev, transport):
     shard.set_agent_shards(smap)
     for g in range(G):
         shard.create_group(g, perm[g * F:(g + 1) * F])
-    if transport == "peer":
+    if transport in ("peer", "prefetch"):
         ex = PeerExchange(shard, rank, world, S, S * L, dev)
     else:
         ex = ShardExchange(shard, rank, world, S, S * L, TorchCudaBackend(dev, shard))
@@ -61,8 +62,19 @@ def transport_parity(rank, world, dev, transport):
 
     shard.digest_reset()
     delivered = 0
+    if transport == "prefetch":
+        ex.export(*batch(0, rank))
     for step in range(STEPS):
-        ex.step(*batch(step, rank))
+        if transport == "prefetch":
+            # pipelined order: step's export is out already; import it, export the NEXT step and start its flag wait +
+            # descriptor pull on the prefetch stream, then drain - the streams must equal the unpipelined sequence
+            ex.import_all()
+            if step + 1 < STEPS:
+                ex.export(*batch(step + 1, rank))
+                if step != 1:                                 # one step without a prefetch: both paths alternate
+                    ex.prefetch()
+        else:
+            ex.step(*batch(step, rank))
         _, total, _ = shard.receive_batch(None, 7 if step % 2 == 0 else 1000, 0, copy_out=False)   # partial drains too
         shard.digest_fold()
         delivered += total
@@ -169,7 +181,7 @@ def main():
     box = [tmp]
     dist.broadcast_object_list(box, src=0)
     res = {}
-    for transport in os.environ.get("SDB_MP_TRANSPORTS", "peer,nccl").split(","):
+    for transport in os.environ.get("SDB_MP_TRANSPORTS", "peer,prefetch,nccl").split(","):
         res[transport] = transport_parity(rank, world, dev, transport)
         dist.barrier()
     res["frontend_msgs"] = frontend_parity(rank, world, dev, box[0])

@@ -493,6 +493,74 @@ def test_async_import_mixed_traffic_and_direct_sends_in_between():
         s.close()
 
 
+@pytest.mark.parametrize("world", [1, 2])
+def test_prefetched_import_equals_the_unpipelined_sequence(world):
+    """sdb_import_prefetch: the flag wait + localize pass of step k+1 run on the handle's second stream while step k is
+    still being received; the import then only places, fans out and indexes.  Mixed traffic (group, point-to-point,
+    broadcast: both buffer sets carry temporary recipient lists), one step left unprefetched, partial drains."""
+    from tests.fake_shard import OracleShard
+    rng = np.random.default_rng(77 + world)
+    A, G, S, T = 600, 6, 150, 7
+    perm = rng.permutation(A)
+    groups = [perm[g * 64:(g + 1) * 64] for g in range(G)]
+    smap, shards, wb, bufs = _async_cluster(world, A, G, S, groups, max_payload=128)
+    ref = OracleShard(A, G, 0, 1)
+    for g, m in enumerate(groups):
+        ref.create_group(g, m)
+    ref_bytes = ref.wire_bytes(S, S * 128 + 8 * 4 * 200 + 4096)
+    all_agents = np.arange(A, dtype=np.uint32)
+
+    def make(step, r):
+        g = np.random.default_rng(1000 * step + r)
+        n = S if (step, r) != (4, world - 1) else 0
+        kind = g.integers(0, 3, n).astype(np.uint8)
+        sender = g.integers(0, A, n)
+        lists = [g.choice(A, size=int(g.integers(0, 100)), replace=False) for _ in range(4)]
+        lo = np.zeros(5, np.uint64); lo[1:] = np.cumsum([len(x) for x in lists])
+        li = np.concatenate(lists).astype(np.uint32)
+        target = np.where(kind == 0, g.integers(0, A, n), np.where(kind == 1, g.integers(0, G, n), g.integers(0, 4, n)))
+        return (sender, kind, target, lo, li, g.integers(0, 4, n), g.integers(0, 7, n), g.integers(0, 129, n).astype(np.uint16),
+                np.arange(n, dtype=np.uint64) * 128, g.integers(48, 123, max(n, 1) * 128 + 64).astype(np.uint8)), g.random(n)
+
+    def export(step):
+        par = step & 1
+        for r in range(world):
+            b, ts = make(step, r)
+            if step > 2:
+                shards[r].wire_wait_done(bufs[par], wb, step - 2)
+            shards[r].export_mixed_batch(*b, bufs[par][r], wb, ts)
+            shards[r].wire_publish(bufs[par][r], wb, step)
+
+    export(1)
+    for step in range(1, T + 1):
+        for s in shards:
+            s.import_wire_ptrs_async(bufs[step & 1], wb, step)
+        if step < T:
+            export(step + 1)
+            if step != 3:                                   # step 4 is imported without a prefetch
+                for s in shards:
+                    s.import_prefetch(bufs[(step + 1) & 1], wb, step + 1)
+                    s.import_prefetch(bufs[(step + 1) & 1], wb, step + 1)     # idempotent
+        ref_wire = np.zeros(world * ref_bytes, np.uint8)
+        for r in range(world):
+            b, ts = make(step, r)
+            ref.export_mixed_batch(*b, ref_wire[r * ref_bytes:(r + 1) * ref_bytes], ref_bytes, ts)
+        ref.import_wire_batches(world, ref_wire, ref_bytes)
+        k = [2, 1000, 5, 1000, 1, 3, 1000][step - 1]
+        flags = 1 if step % 3 == 0 else 0
+        merged = {}
+        for r, s in enumerate(shards):
+            local = np.nonzero(smap == r)[0].astype(np.uint32)
+            merged.update(_per_agent(*s.receive_batch(local, k, flags), local))
+        want = _per_agent(*ref.o.receive_batch(all_agents, k, flags, rec_cap=1 << 18), all_agents)
+        for a in range(A):
+            assert merged[a] == want[a], (step, a)
+    for s in shards:
+        st = s.stats()
+        assert st["ring_overflow"] == 0 and st["next_seq"] == ref.o.next_seq
+        s.close()
+
+
 def test_async_import_that_does_not_fit_is_dropped_whole_and_reported():
     """Arena too small for an import: nothing of it is delivered, earlier traffic is intact, and the next
     host-synchronising call reports SDB_EARENA_FULL (never a silent drop)."""
