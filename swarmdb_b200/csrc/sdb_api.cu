@@ -16,7 +16,10 @@
 #include "sdb_common.cuh"
 
 extern "C" {
-cudaError_t sdb_launch_p2p(const sdb_dev_view*, const sdb_send_desc*, uint32_t, const uint8_t*, uint64_t, uint64_t, int, cudaStream_t, sdb_profiler*);
+cudaError_t sdb_launch_p2p(const sdb_dev_view*, const sdb_send_desc*, uint32_t, const uint8_t*, uint64_t, uint64_t, int, cudaStream_t, sdb_profiler*, uint32_t);
+cudaError_t sdb_launch_list_index(const sdb_dev_view*, const sdb_send_desc*, const uint32_t*, const uint32_t*, uint32_t, uint32_t, uint64_t,
+                                  cudaStream_t, sdb_profiler*);
+cudaError_t sdb_launch_commit_ranked(const sdb_dev_view*, const sdb_send_desc*, uint32_t, uint32_t, cudaStream_t, sdb_profiler*);
 cudaError_t sdb_send_prepare_device();
 cudaError_t sdb_launch_fanout(const sdb_dev_view*, const sdb_send_desc*, uint32_t, const uint8_t*, const uint32_t*,
                               uint64_t, uint64_t, uint32_t, int, int, cudaStream_t, sdb_profiler*, const sdb_batch_base*);
@@ -65,6 +68,9 @@ struct sdb_staged {
   uint32_t* gs_idx_dev = nullptr;   // [n]
   bool has_pull = false;      // group sends indexed by k_pull_index
   bool has_atomic = false;    // some sends claim ring slots with atomics -> k_commit must sort
+  bool ranked = false;        // pure point-to-point batch ranked per receiver at staging time: no atomics, no sort
+  bool list_pull = false;     // pure broadcast batch over pairwise disjoint lists: ring entries built by k_list_index
+  uint32_t lp_nd = 0, lp_max_count = 0, lp_words = 0;
   bool owns = false;          // device buffers owned by this object (else the handle's staging)
 };
 
@@ -94,6 +100,10 @@ struct sdb_ctx {
   bool memb_dirty = true;
   uint8_t* gexcl_dev = nullptr;          // [max_groups] 1: every member of the group belongs to that group only
   uint32_t n_excl_groups = 0, n_shared_agents = 0;
+  std::vector<uint32_t> rank_cnt;              // per-receiver counters of the point-to-point ranking (all zero between batches)
+  std::vector<uint32_t> lp_first;              // broadcast batches: first chunk descriptor of every send
+  std::vector<uint64_t> lp_begin, lp_end;      // broadcast batches: where each send's / list's recipients sit in the pool
+  uint32_t* lp_host = nullptr; uint32_t* lp_dev = nullptr; uint64_t lp_cap = 0;   // list-parallel index tables (pinned / device)
   // sharding (one handle = one shard): owner of each agent, full group lists, local positions
   std::vector<uint8_t> shard_of; bool sharded = false;
   std::vector<std::vector<uint32_t>> gfull;    // full member lists as given by the caller
@@ -283,6 +293,10 @@ struct SendArrays {
   uint32_t n_lists = 0;               // mixed batches only
   uint32_t* p2p_list = nullptr;       // mixed batches: where single receivers are appended (pinned list staging)
   uint64_t p2p_list_base = 0, p2p_list_cap = 0, p2p_list_used = 0;
+  // list batches: recipients of list li are list_pool[lbegin[li] .. lend[li]) (identical lists of a batch are stored once)
+  const uint64_t* lbegin = nullptr; const uint64_t* lend = nullptr;
+  const uint32_t* list_pool = nullptr;
+  uint32_t* lp_out = nullptr; uint64_t lp_cap = 0;     // staging of the list-parallel index tables (nullptr: not offered)
 };
 
 // Build descriptors into `out` (host).  kind 0: second = receiver; 1: second = group idx;
@@ -294,7 +308,9 @@ static const uint32_t SDB_LIST_CHUNK = 1024;
 int build_descs(sdb_ctx* h, uint32_t batch_kind, uint32_t n, SendArrays& a, const uint64_t* list_off,
                 uint64_t payload_bytes, sdb_send_desc* out, uint64_t out_cap, sdb_staged* s, uint32_t* gs_out = nullptr,
                 uint32_t* n_gs_out = nullptr) {
-  uint64_t rec = 0, gran = 0, group_recs = 0;
+  uint64_t rec = 0, gran = 0, group_recs = 0, list_copies = 0;
+  uint32_t n_list_sends = 0;
+  std::vector<uint32_t>& first_desc = h->lp_first;    // list sends: index of the send's first chunk descriptor
   uint64_t o = 0;                      // output cursor (descriptors emitted)
   uint32_t max_padlen = 0;
   uint32_t n_group_sends = 0, n_other = 0;
@@ -357,7 +373,10 @@ int build_descs(sdb_ctx* h, uint32_t batch_kind, uint32_t n, SendArrays& a, cons
       group_recs += d.mcount; ++n_group_sends;
     } else {
       const uint32_t li = batch_kind == 3 ? a.second[i] : i;
-      const uint64_t b = list_off[li], e = list_off[li + 1];
+      const uint64_t b = a.lbegin ? a.lbegin[li] : list_off[li], e = a.lend ? a.lend[li] : list_off[li + 1];
+      list_copies += e - b; ++n_list_sends;
+      if (first_desc.size() < n) first_desc.resize(n);
+      first_desc[i] = static_cast<uint32_t>(o);
       if (e < b || e - b > 0xFFFFFFFFull) return fail(h, SDB_EINVAL, "bad list_off");
       d.flags = SDB_DESC_SHARED_SEQ | SDB_DESC_LIST_TEMP;
       const uint64_t cnt = e - b;
@@ -379,7 +398,56 @@ int build_descs(sdb_ctx* h, uint32_t batch_kind, uint32_t n, SendArrays& a, cons
   }
   const uint32_t n_out = static_cast<uint32_t>(o);
   s->kind = batch_kind; s->n = n_out; s->total_recs = rec; s->total_grans = gran; s->max_padlen = max_padlen;
-  s->has_pull = false; s->has_atomic = true;
+  s->has_pull = false; s->has_atomic = true; s->ranked = false; s->list_pull = false;
+  if (n_list_sends == n && n && list_copies >= SDB_PULL_THRESHOLD && a.lp_out && a.lbegin && a.list_pool) {
+    // pure broadcast batch: if the lists it names are pairwise disjoint (and free of repeats), every member of a list
+    // receives exactly the sends naming it, in send order -> owner-computes index build (k_list_index), no atomics.
+    // Lists are identified by where they start in the pool (identical lists were stored once by the caller).
+    std::vector<std::pair<uint64_t, uint32_t>> key(n);                    // (list begin, send)
+    for (uint32_t i = 0; i < n; ++i) { const uint32_t li = batch_kind == 3 ? a.second[i] : i; key[i] = {a.lbegin[li], i}; }
+    std::stable_sort(key.begin(), key.end(), [](const auto& x, const auto& y) { return x.first < y.first; });
+    uint32_t nd = 0;
+    for (uint32_t k = 0; k < n; ++k) if (k == 0 || key[k].first != key[k - 1].first) ++nd;
+    const uint64_t words = 3ull * nd + 1 + n;
+    bool ok = nd <= 65535u && words <= a.lp_cap;
+    if (ok) {
+      uint32_t* start = a.lp_out; uint32_t* count = start + nd; uint32_t* off = count + nd; uint32_t* idx = off + nd + 1;
+      if (h->rank_cnt.size() != A) h->rank_cnt.assign(A, 0u);
+      std::vector<uint32_t>& seen = h->rank_cnt;                            // all zero between batches
+      uint32_t dcur = 0, max_count = 0;
+      std::vector<std::pair<uint64_t, uint64_t>> marked;
+      for (uint32_t k = 0; k < n && ok; ++k) {
+        const uint32_t i = key[k].second, li = batch_kind == 3 ? a.second[i] : i;
+        if (k == 0 || key[k].first != key[k - 1].first) {
+          const uint64_t b = a.lbegin[li], e = a.lend[li];
+          if (k) ++dcur;
+          start[dcur] = static_cast<uint32_t>(b); count[dcur] = static_cast<uint32_t>(e - b); off[dcur] = k;
+          max_count = std::max(max_count, count[dcur]);
+          marked.push_back({b, e});
+          for (uint64_t x = b; x < e; ++x) { uint32_t& c = seen[a.list_pool[x]]; if (c) { ok = false; marked.back().second = x; break; } c = 1; }
+        } else if (a.lend[li] - a.lbegin[li] != count[dcur]) ok = false;     // same start, different length: not the same list
+        idx[k] = first_desc[i];
+      }
+      off[nd] = n;
+      for (const auto& m : marked) for (uint64_t x = m.first; x < m.second; ++x) seen[a.list_pool[x]] = 0;
+      if (ok) {
+        for (uint32_t i = 0; i < n_out; ++i) out[i].flags |= SDB_DESC_PULL;
+        s->list_pull = true; s->has_atomic = false; s->lp_nd = nd; s->lp_max_count = max_count; s->lp_words = static_cast<uint32_t>(words);
+      }
+    }
+  }
+  if (batch_kind == 0 && n_out) {
+    // pure point-to-point batch: number the sends of every receiver 0, 1, 2 .. in send order, so that the enqueue
+    // kernel places ring entries at ctail + rank without atomics and in final order (no commit sort)
+    if (h->rank_cnt.size() != A) h->rank_cnt.assign(A, 0u);
+    std::vector<uint32_t>& cnt = h->rank_cnt;
+    for (uint32_t i = 0; i < n_out; ++i) { out[i].pad0 = cnt[out[i].mstart]++; out[i].flags |= SDB_DESC_RANKED; }
+    for (uint32_t i = n_out; i-- > 0;) {
+      uint32_t& c = cnt[out[i].mstart];
+      if (c) { out[i].flags |= SDB_DESC_RANK_LAST; c = 0; }      // first seen from the back = highest rank; resets the table
+    }
+    s->ranked = true;
+  }
   if (gs_out && group_recs >= SDB_PULL_THRESHOLD) {
     // bucket the group sends by group (counting sort, ascending send index inside a bucket)
     const uint32_t G = h->cfg.max_groups;
@@ -474,7 +542,11 @@ int submit(sdb_ctx* h, const sdb_staged* s, uint64_t* seq_base_out) {
     h->launches += nlp;
   }
   if (s->kind == 0) {
-    e = sdb_launch_p2p(&h->view, s->descs_dev, s->n, s->payload_dev, h->next_seq, base, h->sm_count, h->stream, &h->prof);
+    e = sdb_launch_p2p(&h->view, s->descs_dev, s->n, s->payload_dev, h->next_seq, base, h->sm_count, h->stream, &h->prof, s->max_padlen);
+    if (e == cudaSuccess && s->ranked) {      // entries are in send order already: publish them, nothing to sort
+      e = sdb_launch_commit_ranked(&h->view, s->descs_dev, s->n, h->n_agents, h->stream, &h->prof);
+      h->launches += 1;
+    }
   } else {
     e = sdb_launch_fanout(&h->view, s->descs_dev, s->n, s->payload_dev, s->list_dev, h->next_seq, base,
                           s->max_padlen, static_cast<int>(h->cfg.fanout_variant), h->sm_count, h->stream, &h->prof, nullptr);
@@ -489,7 +561,11 @@ int submit(sdb_ctx* h, const sdb_staged* s, uint64_t* seq_base_out) {
                         h->n_shared_agents, h->lstart_dev, h->lcount_dev, base, s->has_atomic ? 0 : 1, h->stream, &h->prof, &nlp, nullptr);
     h->launches += nlp;
   }
-  if (e == cudaSuccess && s->has_atomic) {
+  if (e == cudaSuccess && s->list_pull) {
+    e = sdb_launch_list_index(&h->view, s->descs_dev, s->list_dev, h->lp_dev, s->lp_nd, s->lp_max_count, base, h->stream, &h->prof);
+    h->launches += 1;
+  }
+  if (e == cudaSuccess && s->has_atomic && !s->ranked) {
     e = sdb_launch_commit(&h->view, h->n_agents, static_cast<uint32_t>(base), h->rx_big_list, h->rx_big_count + 1, h->sm_count, h->stream, &h->prof, nullptr);
     h->launches += 2;
   }
@@ -517,11 +593,34 @@ int send_common(sdb_ctx* h, uint32_t kind, uint32_t n, SendArrays& a, const uint
     list_total = (nl && list_off) ? list_off[nl] : 0;
     const uint64_t cap = h->cfg.list_pool_entries;
     if (list_total > cap) return fail(h, SDB_ECAPACITY, "recipient lists exceed list_pool_entries");
-    for (uint64_t k = 0; k < list_total; ++k) {
-      if (list_idx[k] >= h->cfg.max_agents) return fail(h, SDB_EINVAL, "recipient index out of range");
-      h->n_agents = std::max(h->n_agents, list_idx[k] + 1);
+    // identical consecutive lists (the same "everybody" list passed with every broadcast) are stored and uploaded once
+    h->lp_begin.assign(nl, 0); h->lp_end.assign(nl, 0);
+    uint64_t used = 0, prev_b = 0, prev_n = 0; bool have_prev = false;
+    for (uint32_t li = 0; li < nl; ++li) {
+      const uint64_t b = list_off[li], e = list_off[li + 1];
+      if (e < b || e > list_total) return fail(h, SDB_EINVAL, "bad list_off");
+      const uint64_t cnt = e - b;
+      if (have_prev && cnt == prev_n && cnt && std::memcmp(list_idx + b, h->list_host + prev_b, cnt * sizeof(uint32_t)) == 0) {
+        h->lp_begin[li] = prev_b; h->lp_end[li] = prev_b + cnt;
+        continue;
+      }
+      for (uint64_t k = b; k < e; ++k) {
+        if (list_idx[k] >= h->cfg.max_agents) return fail(h, SDB_EINVAL, "recipient index out of range");
+        h->n_agents = std::max(h->n_agents, list_idx[k] + 1);
+      }
+      if (cnt) std::memcpy(h->list_host + used, list_idx + b, cnt * sizeof(uint32_t));
+      h->lp_begin[li] = used; h->lp_end[li] = used + cnt;
+      prev_b = used; prev_n = cnt; have_prev = true;
+      used += cnt;
     }
-    if (list_total) std::memcpy(h->list_host, list_idx, list_total * sizeof(uint32_t));
+    list_total = used;
+    a.lbegin = h->lp_begin.data(); a.lend = h->lp_end.data(); a.list_pool = h->list_host;
+    if (!h->lp_host) {
+      h->lp_cap = 4ull * h->cfg.max_batch_sends + 8;
+      CUDA_TRY(h, cudaHostAlloc(reinterpret_cast<void**>(&h->lp_host), h->lp_cap * sizeof(uint32_t), cudaHostAllocDefault));
+      CUDA_TRY(h, dmalloc(&h->lp_dev, h->lp_cap));
+    }
+    a.lp_out = h->lp_host; a.lp_cap = h->lp_cap;
     a.p2p_list = h->list_host + list_total; a.p2p_list_base = list_total; a.p2p_list_cap = cap - list_total;
   }
   uint32_t n_gs = 0;
@@ -532,6 +631,8 @@ int send_common(sdb_ctx* h, uint32_t kind, uint32_t n, SendArrays& a, const uint
     CUDA_TRY(h, cudaMemcpyAsync(s->gs_off_dev, h->gs_host, G1 * sizeof(uint32_t), cudaMemcpyHostToDevice, h->stream));
     CUDA_TRY(h, cudaMemcpyAsync(s->gs_idx_dev, h->gs_host + G1, static_cast<size_t>(n_gs) * sizeof(uint32_t), cudaMemcpyHostToDevice, h->stream));
   }
+  if (s->list_pull)
+    CUDA_TRY(h, cudaMemcpyAsync(h->lp_dev, h->lp_host, static_cast<size_t>(s->lp_words) * sizeof(uint32_t), cudaMemcpyHostToDevice, h->stream));
   list_total += a.p2p_list_used;
   if (list_total)
     CUDA_TRY(h, cudaMemcpyAsync(s->list_dev, h->list_host, list_total * sizeof(uint32_t), cudaMemcpyHostToDevice, h->stream));
@@ -744,6 +845,8 @@ int sdb_destroy(sdb_handle h) {
   for (void* p : dev) if (p) cudaFree(p);
   if (h->descs_host) cudaFreeHost(h->descs_host);
   if (h->list_host) cudaFreeHost(h->list_host);
+  if (h->lp_host) cudaFreeHost(h->lp_host);
+  if (h->lp_dev) cudaFree(h->lp_dev);
   if (h->gs_host) cudaFreeHost(h->gs_host);
   if (h->wire_host) cudaFreeHost(h->wire_host);
   if (h->hdrs_host) cudaFreeHost(h->hdrs_host);

@@ -63,6 +63,8 @@ static_assert(sizeof(sdb_msg_header) == 32, "header must be 32 bytes");
 #define SDB_DESC_SHARED_SEQ 2u    // broadcast: every copy carries the same seq (one Message)
 #define SDB_DESC_LIST_TEMP 4u     // mstart indexes the per-batch temporary list buffer
 #define SDB_DESC_PULL 8u          // ring entries are built by k_pull_index, not by the fan-out kernel
+#define SDB_DESC_RANKED 32u       // p2p: pad0 = rank of this send among the batch's sends to the same receiver (ring slot = ctail + rank)
+#define SDB_DESC_RANK_LAST 64u    // p2p: highest rank for its receiver (count = rank + 1): this send publishes the ring tail
 #define SDB_DESC_POS 16u          // seq offset of member k is member_pos[mstart + k] (sharded: original group position)
 #define SDB_DESC_P2P 32u          // wire batches only: point-to-point send, mstart = receiver index
 #define SDB_DESC_ABS_SEQ 64u      // seq_abs holds the sequence number (sources that number their own sends)

@@ -650,7 +650,14 @@ k_enqueue_p2p(sdb_dev_view v, const sdb_send_desc* __restrict__ descs, uint32_t 
     }
     if (l8 == 0) {
       const uint16_t meta = static_cast<uint16_t>((prio << 14) | rgran);
-      if (sdb_ring_append(v, a, static_cast<uint32_t>(apos), meta)) ++n_enq; else ++n_ovf;
+      const uint4 q3 = __ldg(dq + 3);
+      if (q3.x & SDB_DESC_RANKED) {                    // ranked at staging time: slot = ctail + rank, no atomics (see the bulk-copy form)
+        const uint4 hd = __ldcg(reinterpret_cast<const uint4*>(v.ring_hdr + a));
+        const uint32_t room = v.ring_slots - (hd.z - hd.x);
+        if (q3.y < room) { sdb_ring_of(v, a)[(hd.z + q3.y) & (v.ring_slots - 1)] = make_uint2(static_cast<uint32_t>(apos), meta); ++n_enq; }
+        else ++n_ovf;
+        if (q3.x & SDB_DESC_RANK_LAST) v.ring_hdr[a].tail = hd.z + min(q3.y + 1u, room);
+      } else if (sdb_ring_append(v, a, static_cast<uint32_t>(apos), meta)) ++n_enq; else ++n_ovf;
     }
   }
   for (int o = 16; o; o >>= 1) {
@@ -661,6 +668,132 @@ k_enqueue_p2p(sdb_dev_view v, const sdb_send_desc* __restrict__ descs, uint32_t 
     if (n_enq) atomicAdd(&v.ctr->enqueued, n_enq);
     if (n_ovf) atomicAdd(&v.ctr->ring_overflow, n_ovf);
   }
+}
+
+// ------------------------------------------------------------------------------------------
+// K1, bulk-copy form (default for payloads up to 512 bytes): one LANE per record, 32 records per warp step, two
+// steps in flight per warp.
+//   * the lane reads its 64-byte descriptor (consecutive lanes -> consecutive descriptors), issues ONE TMA bulk load
+//     of the padded payload into its shared-memory slot, writes the 32-byte record header and the ring entry while
+//     the load is in flight, then zeroes the pad bytes in the slot and issues ONE bulk store into the arena record
+//   * ring slots are NOT claimed with atomics when the batch was ranked at staging time (SDB_DESC_RANKED: the host
+//     numbers the sends of one receiver 0, 1, 2 .. in send order): slot = ctail + rank, read-only on the ring header
+//     (nobody writes ctail during the kernel); the highest-ranked send publishes tail = ctail + count.  Entries land
+//     in send order, so the commit is k_commit_ranked (ctail = tail for the touched receivers): no sort.
+// The LSU form above kept one record's descriptor -> payload -> atomic chain per 8 lanes and was latency-bound
+// (ncu: 14 % issue active, 44 warps stalled on long scoreboard per issue, 2.5 TB/s).
+// ------------------------------------------------------------------------------------------
+template <int WARPS>
+__global__ void __launch_bounds__(WARPS * 32)
+k_enqueue_p2p_tma(sdb_dev_view v, const sdb_send_desc* __restrict__ descs, uint32_t n,
+                  const uint8_t* __restrict__ payload, uint64_t seq_base, uint64_t arena_base, uint32_t slot_bytes) {
+  extern __shared__ __align__(128) uint8_t s_dyn[];          // [WARPS][2][32][slot_bytes]
+  __shared__ __align__(8) uint64_t s_bar[WARPS][2];
+  const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  uint8_t* const wbase = s_dyn + static_cast<size_t>(warp) * 2u * 32u * slot_bytes;
+  if (lane == 0) { sdb_mbar_init(&s_bar[warp][0], 1); sdb_mbar_init(&s_bar[warp][1], 1); sdb_fence_barrier_init(); }
+  __syncwarp();
+  const uint32_t gw = blockIdx.x * WARPS + warp, stride = gridDim.x * WARPS * 32u;
+  uint32_t phase = 0;
+  uint32_t n_enq = 0, n_ovf = 0;
+  // Three steps of a warp are in flight, so that no load is consumed in the step that issues it:
+  //   A(k+2) descriptor loads   B(k+1) TMA payload load + record header + ring-header load   C(k) ring entry + bulk store
+  struct Desc { uint4 q0, q1, q2, q3; bool have; };
+  struct Rec { uint8_t* rec; uint4 hd; uint32_t padlen, len, a, apos32, rank, flags; uint16_t meta; bool valid; };
+  auto load_desc = [&](uint32_t i0) {
+    Desc d; d.q0 = d.q1 = d.q2 = d.q3 = make_uint4(0, 0, 0, 0);
+    const uint32_t i = i0 + lane;
+    d.have = i < n;
+    if (d.have) {
+      const uint4* dq = reinterpret_cast<const uint4*>(descs + i);
+      d.q0 = __ldg(dq); d.q1 = __ldg(dq + 1); d.q2 = __ldg(dq + 2); d.q3 = __ldg(dq + 3);
+    }
+    return d;
+  };
+  auto start = [&](const Desc& d, uint32_t st) {
+    Rec r; r.rec = nullptr; r.hd = make_uint4(0, 0, 0, 0); r.padlen = 0; r.len = 0; r.a = 0; r.apos32 = 0; r.rank = 0; r.flags = 0; r.meta = 0;
+    r.valid = d.have && d.q2.y < v.max_agents;
+    if (r.valid) { r.padlen = (d.q1.z - 1u) * SDB_GRANULE; r.len = d.q1.w & 0xFFFFu; }
+    uint32_t sum = r.padlen;
+    for (int o = 16; o; o >>= 1) sum += __shfl_xor_sync(0xFFFFFFFFu, sum, o);
+    if (lane == 0) sdb_mbar_expect_tx(&s_bar[warp][st], sum);
+    __syncwarp();
+    if (r.valid) {
+      const uint64_t payload_off = (static_cast<uint64_t>(d.q0.y) << 32) | d.q0.x;
+      if (r.padlen) sdb_tma_load(wbase + (static_cast<size_t>(st) * 32u + lane) * slot_bytes, payload + payload_off, r.padlen, &s_bar[warp][st]);
+      r.a = d.q2.y; r.flags = d.q3.x; r.rank = d.q3.y;
+      if (r.flags & SDB_DESC_RANKED) r.hd = __ldcg(reinterpret_cast<const uint4*>(v.ring_hdr + r.a));   // {head, tail, ctail, ntomb}: L2, not L1
+      const uint32_t prio = (d.q1.w >> 16) & 0xFFu, type = d.q1.w >> 24;
+      const double ts = __longlong_as_double((static_cast<long long>(d.q0.w) << 32) | d.q0.z);
+      const uint64_t apos = arena_base + d.q1.x;
+      r.apos32 = static_cast<uint32_t>(apos);
+      r.meta = static_cast<uint16_t>((prio << 14) | d.q1.z);
+      r.rec = sdb_arena_ptr(v, apos);
+      sdb_st_stream(reinterpret_cast<uint4*>(r.rec), sdb_header_lo(seq_base + d.q2.x, ts));
+      sdb_st_stream(reinterpret_cast<uint4*>(r.rec) + 1, sdb_header_hi(d.q1.y, r.a, SDB_NO_GROUP, static_cast<uint16_t>(r.len), static_cast<uint8_t>(prio), static_cast<uint8_t>(type)));
+    }
+    return r;
+  };
+  uint32_t i0 = gw * 32u;
+  if (i0 >= n) return;
+  Desc dn = load_desc(i0);
+  Rec cur = start(dn, 0);
+  dn = load_desc(i0 + stride);
+  uint32_t st = 0;
+  for (; i0 < n; i0 += stride, st ^= 1u) {
+    sdb_tma_wait_read<0>();                                   // the other stage's bulk stores have finished reading it
+    __syncwarp();
+    Rec nxt; nxt.valid = false; nxt.padlen = 0; nxt.len = 0; nxt.rec = nullptr;
+    if (i0 + stride < n) {                                    // (unsigned overflow impossible: n < 2^31 sends per batch)
+      nxt = start(dn, st ^ 1u);
+      dn = load_desc(i0 + 2u * stride);
+    }
+    if (cur.valid) {
+      if (cur.flags & SDB_DESC_RANKED) {
+        const uint32_t room = v.ring_slots - (cur.hd.z - cur.hd.x);                       // free slots at batch start
+        if (cur.rank < room) {
+          sdb_ring_of(v, cur.a)[(cur.hd.z + cur.rank) & (v.ring_slots - 1)] = make_uint2(cur.apos32, cur.meta);
+          ++n_enq;
+        } else ++n_ovf;
+        if (cur.flags & SDB_DESC_RANK_LAST) v.ring_hdr[cur.a].tail = cur.hd.z + min(cur.rank + 1u, room);
+      } else {
+        if (sdb_ring_append(v, cur.a, cur.apos32, cur.meta)) ++n_enq; else ++n_ovf;
+      }
+    }
+    sdb_mbar_wait_bounded(&s_bar[warp][st], (phase >> st) & 1u);
+    phase ^= 1u << st;
+    if (cur.padlen) {
+      uint8_t* slot = wbase + (static_cast<size_t>(st) * 32u + lane) * slot_bytes;
+      for (uint32_t b = cur.len; b < cur.padlen; ++b) slot[b] = 0;     // < 32 bytes: arena contents stay deterministic
+      sdb_fence_proxy_async();
+      sdb_tma_store(cur.rec + 32, slot, cur.padlen);
+    }
+    sdb_tma_commit();
+    cur = nxt;
+  }
+  sdb_tma_wait_all<0>();
+  for (int o = 16; o; o >>= 1) {
+    n_enq += __shfl_xor_sync(0xFFFFFFFFu, n_enq, o);
+    n_ovf += __shfl_xor_sync(0xFFFFFFFFu, n_ovf, o);
+  }
+  if (lane == 0) {
+    if (n_enq) atomicAdd(&v.ctr->enqueued, n_enq);
+    if (n_ovf) atomicAdd(&v.ctr->ring_overflow, n_ovf);
+  }
+}
+
+// commit of a ranked point-to-point batch: the entries are in send order already; publish ctail = tail for the
+// receivers the batch touched (one thread per send; only the highest-ranked send of a receiver acts)
+__global__ void __launch_bounds__(256)
+k_commit_ranked(sdb_dev_view v, const sdb_send_desc* __restrict__ descs, uint32_t n) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const uint4* dq = reinterpret_cast<const uint4*>(descs + i);
+  const uint4 q3 = __ldg(dq + 3);
+  if (!(q3.x & SDB_DESC_RANK_LAST)) return;
+  const uint32_t a = __ldg(dq + 2).y;
+  if (a >= v.max_agents) return;
+  v.ring_hdr[a].ctail = v.ring_hdr[a].tail;
 }
 
 // ------------------------------------------------------------------------------------------
@@ -790,6 +923,80 @@ k_pull_index_group(sdb_dev_view v, sdb_pull_view pv, const sdb_send_desc* __rest
         }
       }
     }
+  }
+  for (int o2 = 16; o2; o2 >>= 1) {
+    n_enq += __shfl_xor_sync(0xFFFFFFFFu, n_enq, o2);
+    n_ovf += __shfl_xor_sync(0xFFFFFFFFu, n_ovf, o2);
+  }
+  if (lane == 0) {
+    if (n_enq) atomicAdd(&v.ctr->enqueued, n_enq);
+    if (n_ovf) atomicAdd(&v.ctr->ring_overflow, n_ovf);
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// k_list_index: owner-computes index build for broadcast batches (M:449-463 / M:810-850).  A pure list batch whose
+// recipient lists are pairwise disjoint (the usual case is ONE list - "everybody" - shared by all broadcasts of the
+// batch) is the group case with temporary groups: every member of list d receives exactly the sends that name d, in
+// send order.  The fan-out kernel then writes records only (SDB_DESC_PULL) and this kernel appends the ring entries:
+// one warp per 64 members of a list, four consecutive entries of one member per quad store (full sectors), the
+// ring header of a member read and written once.  No atomics, no commit sort: the batch publishes ctail here.
+//   lists  [nd] {start in the batch's list pool, count}      bucket  off[nd + 1], idx[] = first-chunk descriptor
+//   of every send of the list in send order (record of member j of a send: gran0 + j * rgran: chunks are contiguous)
+// ------------------------------------------------------------------------------------------
+struct sdb_list_view { const uint32_t* pool; const uint32_t* start; const uint32_t* count; const uint32_t* off; const uint32_t* idx; uint32_t nd; };
+
+__global__ void __launch_bounds__(128)
+k_list_index(sdb_dev_view v, sdb_list_view lv, const sdb_send_desc* __restrict__ descs, uint64_t arena_base) {
+  const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const uint32_t d = blockIdx.y;
+  uint32_t n_enq = 0, n_ovf = 0;
+  const uint32_t mcount = __ldg(lv.count + d), mstart = __ldg(lv.start + d);
+  const uint32_t b0 = __ldg(lv.off + d), total = __ldg(lv.off + d + 1) - b0;
+  const uint32_t m0 = (blockIdx.x * 4u + warp) * 64u;
+  if (m0 < mcount && total) {
+    const uint64_t pol = sdb_policy_evict_first();
+    const uint32_t R = v.ring_slots, mask = R - 1;
+    const uint32_t j0 = m0 + lane, j1 = j0 + 32;
+    const uint32_t a0 = j0 < mcount ? __ldg(lv.pool + mstart + j0) : 0xFFFFFFFFu;
+    const uint32_t a1 = j1 < mcount ? __ldg(lv.pool + mstart + j1) : 0xFFFFFFFFu;
+    const bool ok0 = a0 < v.max_agents, ok1 = a1 < v.max_agents;
+    uint4 hd0 = make_uint4(0, 0, 0, 0), hd1 = make_uint4(0, 0, 0, 0);
+    if (ok0) hd0 = *reinterpret_cast<const uint4*>(v.ring_hdr + a0);                       // head, tail, ctail, ntomb
+    if (ok1) hd1 = *reinterpret_cast<const uint4*>(v.ring_hdr + a1);
+    uint32_t t0 = hd0.y, t1 = hd1.y;
+    const uint32_t quad = lane >> 2, sub = lane & 3u;
+    for (uint32_t k0 = 0; k0 < total; k0 += 32) {
+      uint4 q1 = make_uint4(0, 0, 0, 0);
+      if (k0 + lane < total) q1 = __ldg(reinterpret_cast<const uint4*>(descs + __ldg(lv.idx + b0 + k0 + lane)) + 1);   // gran0, sender, rgran, len|prio|type
+      const uint32_t nk = min(32u, total - k0);
+      for (uint32_t c0 = 0; c0 < nk; c0 += 4) {                                            // four sends per step
+        const uint32_t t = c0 + sub;
+        const uint32_t gran0 = __shfl_sync(0xFFFFFFFFu, q1.x, t & 31u);
+        const uint32_t rgran = __shfl_sync(0xFFFFFFFFu, q1.z, t & 31u), lpt = __shfl_sync(0xFFFFFFFFu, q1.w, t & 31u);
+        const bool have_send = t < nk;
+        const uint32_t nsend = min(4u, nk - c0);                                           // every member takes all of them
+        for (uint32_t mb = 0; mb < 64; mb += 8) {                                          // eight members per step
+          const uint32_t mi = mb + quad, srcl = mi & 31u;
+          const uint32_t am = __shfl_sync(0xFFFFFFFFu, mi < 32 ? a0 : a1, srcl);
+          const uint32_t hm = __shfl_sync(0xFFFFFFFFu, mi < 32 ? hd0.x : hd1.x, srcl);
+          const uint32_t tm = __shfl_sync(0xFFFFFFFFu, mi < 32 ? t0 : t1, srcl);
+          if (have_send && am < v.max_agents) {
+            const uint32_t pos = tm + sub;
+            if (pos - hm >= R) ++n_ovf;
+            else {
+              const uint64_t meta_hi = static_cast<uint64_t>((((lpt >> 16) & 0xFFu) << 14) | rgran) << 32;
+              sdb_st_u64_pol(reinterpret_cast<uint64_t*>(sdb_ring_of(v, am) + (pos & mask)),
+                             meta_hi | static_cast<uint32_t>(arena_base + gran0 + static_cast<uint64_t>(m0 + mi) * rgran), pol);
+              ++n_enq;
+            }
+          }
+        }
+        t0 += nsend; t1 += nsend;                                                          // (members that do not exist never store their tail)
+      }
+    }
+    if (ok0) { if (t0 - hd0.x > R) t0 = hd0.x + R; hd0.y = t0; hd0.z = t0; *reinterpret_cast<uint4*>(v.ring_hdr + a0) = hd0; }
+    if (ok1) { if (t1 - hd1.x > R) t1 = hd1.x + R; hd1.y = t1; hd1.z = t1; *reinterpret_cast<uint4*>(v.ring_hdr + a1) = hd1; }
   }
   for (int o2 = 16; o2; o2 >>= 1) {
     n_enq += __shfl_xor_sync(0xFFFFFFFFu, n_enq, o2);
@@ -1028,14 +1235,48 @@ k_commit_big(sdb_dev_view v, uint32_t batch_base32, const uint32_t* __restrict__
 // ------------------------------------------------------------------------------------------
 extern "C" cudaError_t sdb_launch_p2p(const sdb_dev_view* v, const sdb_send_desc* descs, uint32_t n,
                                       const uint8_t* payload, uint64_t seq_base, uint64_t arena_base,
-                                      int sm_count, cudaStream_t stream, sdb_profiler* prof) {
+                                      int sm_count, cudaStream_t stream, sdb_profiler* prof, uint32_t max_padlen) {
   if (n == 0) return cudaSuccess;
   const uint32_t recs_per_cta = 8 * 4;                            // 8 warps x 4 records per step
   uint32_t grid = (n + recs_per_cta - 1) / recs_per_cta;
   const uint32_t cap = static_cast<uint32_t>(sm_count) * 8u * 4u;   // ~4 waves of 8 CTAs/SM, grid-stride beyond
   if (grid > cap) grid = cap;
   const int pi = sdb_prof_begin(prof, SDB_PK_P2P, stream);
-  k_enqueue_p2p<<<grid, 256, 0, stream>>>(*v, descs, n, payload, seq_base, arena_base);
+  static const bool use_tma = !(getenv("SDB_P2P_TMA") && atoi(getenv("SDB_P2P_TMA")) == 0);
+  if (use_tma && max_padlen <= 512u) {
+    constexpr int WARPS = 4;
+    const uint32_t slot = max_padlen < 32u ? 32u : max_padlen;
+    const size_t smem = static_cast<size_t>(WARPS) * 2u * 32u * slot;
+    uint32_t per_sm = static_cast<uint32_t>((226u * 1024u) / (smem + 1152u));
+    if (per_sm > 8u) per_sm = 8u;
+    if (per_sm == 0) per_sm = 1;
+    uint64_t g = static_cast<uint64_t>(sm_count) * per_sm * 4u;
+    const uint64_t need = (static_cast<uint64_t>(n) + WARPS * 32 - 1) / (WARPS * 32);
+    if (g > need) g = need;
+    k_enqueue_p2p_tma<WARPS><<<static_cast<uint32_t>(g), WARPS * 32, smem, stream>>>(*v, descs, n, payload, seq_base, arena_base, slot);
+  } else {
+    k_enqueue_p2p<<<grid, 256, 0, stream>>>(*v, descs, n, payload, seq_base, arena_base);
+  }
+  sdb_prof_end(prof, pi, stream);
+  return cudaGetLastError();
+}
+
+// the same for batches that touch a large share of the agents: a coalesced sweep over the ring headers (16 bytes per
+// agent) instead of one random header access per receiver
+__global__ void __launch_bounds__(256)
+k_commit_ranked_sweep(sdb_dev_view v, uint32_t n_agents) {
+  const uint32_t a = blockIdx.x * blockDim.x + threadIdx.x;
+  if (a >= n_agents) return;
+  const uint4 hd = *reinterpret_cast<const uint4*>(v.ring_hdr + a);
+  if (hd.y != hd.z) v.ring_hdr[a].ctail = hd.y;
+}
+
+extern "C" cudaError_t sdb_launch_commit_ranked(const sdb_dev_view* v, const sdb_send_desc* descs, uint32_t n, uint32_t n_agents,
+                                                cudaStream_t stream, sdb_profiler* prof) {
+  if (n == 0) return cudaSuccess;
+  const int pi = sdb_prof_begin(prof, SDB_PK_COMMIT, stream);
+  if (static_cast<uint64_t>(n) * 8u >= n_agents) k_commit_ranked_sweep<<<(n_agents + 255) / 256, 256, 0, stream>>>(*v, n_agents);
+  else k_commit_ranked<<<(n + 255) / 256, 256, 0, stream>>>(*v, descs, n);
   sdb_prof_end(prof, pi, stream);
   return cudaGetLastError();
 }
@@ -1046,6 +1287,7 @@ extern "C" cudaError_t sdb_send_prepare_device() {
   if ((e = cudaFuncSetAttribute(k_group_fanout_span<4>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                 4 * (SDB_SPAN_DESC * 64 + SDB_SPAN_TABLES + SDB_SPAN_PAY * 512))) != cudaSuccess) return e;
   if ((e = cudaFuncSetAttribute(k_group_fanout_warp<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * 4 * 4096 + 512)) != cudaSuccess) return e;
+  if ((e = cudaFuncSetAttribute(k_enqueue_p2p_tma<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 4 * 2 * 32 * 512)) != cudaSuccess) return e;
   if ((e = cudaFuncSetAttribute(k_group_fanout_st<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, 65536 + 1024)) != cudaSuccess) return e;
   return cudaFuncSetAttribute(k_group_fanout_tma<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * 65536 + 1024);
 }
@@ -1121,6 +1363,20 @@ extern "C" cudaError_t sdb_launch_pull(const sdb_dev_view* v, const sdb_pull_vie
     k_pull_index<<<static_cast<uint32_t>((threads + 255) / 256), 256, 0, stream>>>(*v, *pv, descs, n_agents, n_excl_groups ? gexcl : nullptr, arena_base, set_ctail ? 1u : 0u);
     if (n_launches) *n_launches += 1;
   }
+  sdb_prof_end(prof, pi, stream);
+  return cudaGetLastError();
+}
+
+// tab: device array {start[nd], count[nd], off[nd + 1], idx[...]} (uint32) as staged by the host
+extern "C" cudaError_t sdb_launch_list_index(const sdb_dev_view* v, const sdb_send_desc* descs, const uint32_t* list_pool,
+                                             const uint32_t* tab, uint32_t nd, uint32_t max_count, uint64_t arena_base,
+                                             cudaStream_t stream, sdb_profiler* prof) {
+  if (nd == 0 || max_count == 0) return cudaSuccess;
+  if (nd > 65535u) return cudaErrorInvalidValue;
+  sdb_list_view lv{list_pool, tab, tab + nd, tab + 2u * nd, tab + 3u * nd + 1u, nd};
+  const int pi = sdb_prof_begin(prof, SDB_PK_INDEX, stream);
+  dim3 grid((max_count + 255u) / 256u, nd);
+  k_list_index<<<grid, 128, 0, stream>>>(*v, lv, descs, arena_base);
   sdb_prof_end(prof, pi, stream);
   return cudaGetLastError();
 }

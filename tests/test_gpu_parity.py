@@ -171,14 +171,51 @@ def test_ring_overflow_is_reported_not_silent():
     rng = np.random.default_rng(2)
     g, c = _pair(8, ring_slots=4)
     lens, off, buf = _mk_payloads(rng, 10, 16)
+    base0 = g.stats()["next_seq"]
     g.send_batch(np.zeros(10), np.ones(10), None, None, lens, off, buf)
     st = g.stats()
     assert st["enqueued"] == 4 and st["ring_overflow"] == 6
     cnt, hdr, pay = g.receive_batch([1], 100)
     assert cnt[0] == 4
+    assert hdr["seq"].tolist() == [base0 + k for k in range(4)]     # ranked enqueue: the FIRST sends of the batch are the ones kept
     # ring usable again afterwards
     g.send_batch(np.zeros(3), np.ones(3), None, None, lens[:3], off[:3], buf)
     assert g.receive_batch([1], 100)[0][0] == 3
+    # a partly filled ring: 3 pending + 5 more -> one slot left, four overflow; other receivers are not affected
+    g.send_batch(np.zeros(3), np.ones(3), None, None, lens[:3], off[:3], buf)
+    base = g.stats()["next_seq"]
+    g.send_batch(np.zeros(7), np.array([1, 2, 1, 1, 2, 1, 1]), None, None, lens[:7], off[:7], buf)
+    st2 = g.stats()
+    assert st2["ring_overflow"] == 6 + 4
+    cnt, hdr, _ = g.receive_batch([1, 2], 100)
+    assert cnt.tolist() == [4, 2]
+    assert hdr["seq"][3] == base and hdr["seq"][4:].tolist() == [base + 1, base + 4]
+
+
+def test_ranked_p2p_enqueue_many_per_receiver_and_staged_resubmit():
+    """Pure point-to-point batches are ranked per receiver at staging time (slot = ctail + rank, no atomics, no
+    commit sort): heavy fan-in on a few receivers, empty payloads, a staged batch submitted twice, receives in
+    between - every stream must equal the oracle's."""
+    from swarmdb_b200._native import RECV_PRIORITY
+    rng = np.random.default_rng(61)
+    A = 64
+    g, c = _pair(A, ring_slots=16384)
+    idx = np.arange(A, dtype=np.uint32)
+    for rnd in range(6):
+        n = 3000
+        s = rng.integers(0, A, n)
+        r = np.where(rng.random(n) < 0.7, rng.integers(0, 3, n), rng.integers(0, A, n))      # 70 % to three receivers
+        prio = rng.integers(0, 4, n)
+        lens, off, buf = _mk_payloads(rng, n, 256)
+        lens[rng.random(n) < 0.1] = 0
+        g.send_batch(s, r, prio, None, lens, off, buf); c.send_batch(s, r, prio, None, lens, off, buf)
+        if rnd % 2:
+            _same(g.receive_batch(idx, 500, RECV_PRIORITY if rnd == 3 else 0), c.receive_batch(idx, 500, RECV_PRIORITY if rnd == 3 else 0))
+    st = g.stage(0, s, r, prio, None, lens, off, buf)
+    for _ in range(2):
+        g.submit(st); c.send_batch(s, r, prio, None, lens, off, buf)
+    _same(g.receive_batch(idx, 100000), c.receive_batch(idx, 100000))
+    assert g.stats()["ring_overflow"] == 0
 
 
 def test_arena_wraps_and_reclaims():
@@ -412,3 +449,52 @@ def test_latency_server_answers_like_the_ordinary_path():
     st = g.stats()
     assert st["enqueued"] == st["delivered"] == 8000
     g.close(); c.close()
+
+
+@pytest.mark.parametrize("shape", ["one_shared_list", "disjoint_lists_mixed_api", "overlapping_lists"])
+def test_broadcast_batches_owner_computes_index_equals_oracle(shape):
+    """Pure broadcast batches whose recipient lists are pairwise disjoint (typically ONE list shared by every
+    broadcast of the batch) build their ring entries with k_list_index - no atomics, no commit sort; overlapping
+    lists keep the atomic path.  Either way every stream must equal the oracle's (M:449-463, M:810-850)."""
+    from swarmdb_b200._native import RECV_PRIORITY
+    rng = np.random.default_rng({"one_shared_list": 5, "disjoint_lists_mixed_api": 6, "overlapping_lists": 7}[shape])
+    A = 6000
+    g, c = _pair(A, ring_slots=256, list_pool_entries=1 << 18, max_recv_records=1 << 19)
+    idx = np.arange(A, dtype=np.uint32)
+    # something pending beforehand, so that the entries are appended behind existing ones
+    lens, off, buf = _mk_payloads(rng, 500, 64)
+    s0, r0 = rng.integers(0, A, 500), rng.integers(0, A, 500)
+    g.send_batch(s0, r0, None, None, lens, off, buf); c.send_batch(s0, r0, None, None, lens, off, buf)
+    g.profile(True)
+    for rnd in range(3):
+        n = 40
+        lens, off, buf = _mk_payloads(rng, n, 200)
+        sender = rng.integers(0, A, n); prio = rng.integers(0, 4, n); typ = rng.integers(0, 7, n)
+        if shape == "one_shared_list":
+            everybody = rng.permutation(A)[:3000].astype(np.uint32)
+            lo = np.arange(n + 1, dtype=np.uint64) * len(everybody)
+            li = np.tile(everybody, n)
+            g.send_list_batch(sender, lo, li, prio, typ, lens, off, buf); c.send_list_batch(sender, lo, li, prio, typ, lens, off, buf)
+        else:
+            perm = rng.permutation(A).astype(np.uint32)
+            if shape == "disjoint_lists_mixed_api":
+                lists = [perm[:2500], perm[2500:2501], perm[2600:4000], perm[5000:5000]]          # one single, one empty
+            else:
+                lists = [perm[:2500], perm[2400:4000], perm[3000:3100]]
+            lo = np.zeros(len(lists) + 1, np.uint64); lo[1:] = np.cumsum([len(x) for x in lists])
+            li = np.concatenate(lists)
+            which = rng.integers(0, 3 if shape != "disjoint_lists_mixed_api" else 4, n)
+            g.send_mixed_batch(sender, np.full(n, 2, np.uint8), which, lo, li, prio, typ, lens, off, buf)
+            lo2 = np.zeros(n + 1, np.uint64); lo2[1:] = np.cumsum([len(lists[w]) for w in which])
+            c.send_list_batch(sender, lo2, np.concatenate([lists[w] for w in which]) if lo2[-1] else np.zeros(0, np.uint32),
+                              prio, typ, lens, off, buf)
+        k = [5, 1000, 7][rnd]
+        _same(g.receive_batch(idx, k, RECV_PRIORITY if rnd == 2 else 0), c.receive_batch(idx, k, RECV_PRIORITY if rnd == 2 else 0, rec_cap=1 << 19))
+    _same(g.receive_batch(idx, 100000), c.receive_batch(idx, 100000, rec_cap=1 << 19))
+    prof = g.profile_read()
+    st = g.stats()
+    assert st["ring_overflow"] == 0 and st["enqueued"] == st["delivered"]
+    if shape == "overlapping_lists":
+        assert prof.get("index", (0, 0))[1] == 0 and prof["commit"][1] == 3          # atomic path + commit sort
+    else:
+        assert prof["index"][1] == 3 and prof.get("commit", (0, 0))[1] == 0          # owner-computes, nothing to sort
