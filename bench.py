@@ -515,6 +515,22 @@ def run_gpu(args, rank, world, local_rank):
         launches = st1["kernel_launches"] - launches0
         delivered = st1["delivered"] - st0["delivered"]          # counted on the device by the receive kernels
         assert st1["ring_overflow"] == 0 and shard.last_receive_totals()[0] == per_step_msgs
+        # sustained figure: the same step repeated for a few hundred milliseconds (clocks and power settle), timed as one block
+        sustained = None
+        if args.sustained_steps > 0:
+            Ks = args.sustained_steps
+            clocks_s = ClockSampler(local_rank); clocks_s.start()
+            torch.cuda.synchronize()
+            ev0.record(stream)
+            for i in range(Ks):
+                device_step(W + K + i)
+            ev1.record(stream)
+            torch.cuda.synchronize()
+            ms_s = ev0.elapsed_time(ev1)
+            st2 = shard.stats()
+            assert st2["delivered"] - st1["delivered"] == Ks * per_step_msgs and st2["ring_overflow"] == 0
+            sustained = {"steps": Ks, "ms_per_step": ms_s / Ks, "value": Ks * per_step_msgs / (ms_s * 1e-3), "unit": "messages/s",
+                         "clocks": clocks_s.stop()}
     assert delivered == K * per_step_msgs, (delivered, K * per_step_msgs)
     value = delivered / (ms_total * 1e-3)
 
@@ -639,6 +655,7 @@ def run_gpu(args, rank, world, local_rank):
                          "them back; no explicit flush needed",
                    "fanout_variant": args.variant, "ring_slots": ring_slots, "arena_bytes": 1 << 33},
         "clocks": clk,
+        "sustained": sustained,
         "e2e": {"value": e2e_value, "unit": "messages/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                 "steps": Ke, "ms_per_step": e2e_ms / Ke},
         "gpu_launches": int(launches),
@@ -690,6 +707,8 @@ def main():
     ap.add_argument("--ref-budget", type=float, default=20.0,
                     help="seconds for the reference-python leg (the reference's own class on one core); 0 = skip")
     ap.add_argument("--skip-configs", action="store_true", help="skip the c1 / c4 / c5 legs of the N=1 line")
+    ap.add_argument("--sustained-steps", type=int, default=300,
+                    help="extra block of steps after the K timed ones, timed as a whole and reported under `sustained` (0 = skip)")
     ap.add_argument("--no-extras", action="store_true", help="profiling runs: only the device-resident timed region")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
@@ -697,6 +716,8 @@ def main():
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     if args.warmup < 3:
         args.warmup = 3
+    if args.no_extras:
+        args.sustained_steps = 0
     if args.impl == "reference":
         run_reference(args, rank, world)
         return

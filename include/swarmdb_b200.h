@@ -340,6 +340,14 @@ int sdb_import_wire_ptrs_async(sdb_handle h, uint32_t n_src, const void* const* 
  * not change between the two calls.  A no-op for traffic outside the fast shape. */
 int sdb_import_prefetch(sdb_handle h, uint32_t n_src, const void* const* wire_ptrs, uint64_t wire_bytes, uint32_t step);
 
+/* ---- which records were lost to full rings (delivery report, M:374-391 / M:501-519)
+ * `ring_overflow` in sdb_stats says how many records found their receiver's ring full; this call says WHICH: up to
+ * `cap` (receiver agent, sequence number) pairs of records dropped since the previous call, in no particular order
+ * (the device logs the first 4096 per interval; *dropped_out = how many were dropped in the interval).  Reading
+ * clears the log.  Call it right after the batch that overflowed: the sequence number is read from the dropped
+ * record's image in the arena log, which is reclaimed like any other record. */
+int sdb_overflow_log(sdb_handle h, uint32_t cap, uint32_t* agent_out, uint64_t* seq_out, uint32_t* n_out, uint64_t* dropped_out);
+
 /* ---- inbox / load queries on the device: get_agent_load, get_unread_message_count (M:1026-1094), get_stats (M:973-1024)
  * The reference answers these by walking its host dictionaries (`messages`, `agent_inbox`); the queue itself now lives
  * in HBM, so the same questions are answered from the rings.  Mapping of the reference's fields:

@@ -7,6 +7,7 @@ producer/consumer layer replaced by GPU-resident per-agent rings driven through 
 include/swarmdb_b200.h.  No CPU fallback.
 """
 from .core import (GpuConfig, KafkaConfig, Message, MessagePriority, MessageStatus, MessageType,  # noqa: F401
-                   SwarmsDB)
+                   RingOverflow, SwarmsDB)
 
-__all__ = ["SwarmsDB", "KafkaConfig", "GpuConfig", "Message", "MessageType", "MessagePriority", "MessageStatus"]
+__all__ = ["SwarmsDB", "KafkaConfig", "GpuConfig", "Message", "MessageType", "MessagePriority", "MessageStatus",
+           "RingOverflow"]

@@ -65,7 +65,7 @@ EXPORTS = ["sdb_abi_version", "sdb_create", "sdb_destroy", "sdb_set_stream", "sd
            "sdb_receive_batch", "sdb_latency_server", "sdb_last_receive_dev", "sdb_last_receive_totals",
            "sdb_digest_reset", "sdb_digest_fold", "sdb_digest_read", "sdb_wire_bytes", "sdb_set_agent_shards",
            "sdb_export_group_batch", "sdb_export_mixed_batch", "sdb_export_mixed_batch_seq", "sdb_import_wire_batches", "sdb_wire_alloc", "sdb_wire_open",
-           "sdb_wire_close", "sdb_import_wire_ptrs", "sdb_wire_wait_done", "sdb_wire_publish", "sdb_import_wire_ptrs_async", "sdb_import_prefetch", "sdb_set_backends", "sdb_get_backend_loads",
+           "sdb_wire_close", "sdb_import_wire_ptrs", "sdb_wire_wait_done", "sdb_wire_publish", "sdb_import_wire_ptrs_async", "sdb_import_prefetch", "sdb_overflow_log", "sdb_set_backends", "sdb_get_backend_loads",
            "sdb_release_backends", "sdb_select_backend_batch", "sdb_agent_loads", "sdb_queue_stats",
            "sdb_assign_agent_backends", "sdb_backend_loads_from_queues"]
 
@@ -128,6 +128,7 @@ def load_library() -> C.CDLL:
     L.sdb_wire_publish.restype = i32; L.sdb_wire_publish.argtypes = [vp, vp, u64, u32]
     L.sdb_import_wire_ptrs_async.restype = i32; L.sdb_import_wire_ptrs_async.argtypes = [vp, u32, vp, u64, u32]
     L.sdb_import_prefetch.restype = i32; L.sdb_import_prefetch.argtypes = [vp, u32, vp, u64, u32]
+    L.sdb_overflow_log.restype = i32; L.sdb_overflow_log.argtypes = [vp, u32, vp, vp, vp, vp]
     L.sdb_import_wire_batches.restype = i32; L.sdb_import_wire_batches.argtypes = [vp, u32, vp, u64, vp]
     L.sdb_set_backends.restype = i32; L.sdb_set_backends.argtypes = [vp, u32, vp, vp]
     L.sdb_get_backend_loads.restype = i32; L.sdb_get_backend_loads.argtypes = [vp, u32, vp]
@@ -404,6 +405,15 @@ class Shard:
     def wire_publish(self, wire_dev: int, wire_bytes: int, step: int) -> None:
         """Stream-ordered: this buffer now holds the complete export of `step`."""
         self._check(self._L.sdb_wire_publish(self._h, C.c_void_p(wire_dev), wire_bytes, step))
+
+    def overflow_log(self, cap: int = 4096):
+        """(agents, seqs, dropped): the records that found their receiver's ring full since the last call
+        (include/swarmdb_b200.h: sdb_overflow_log); reading clears the log."""
+        ag = np.zeros(cap, np.uint32); sq = np.zeros(cap, np.uint64)
+        n = C.c_uint32(0); dropped = C.c_uint64(0)
+        self._check(self._L.sdb_overflow_log(self._h, cap, _p(ag), _p(sq), C.cast(C.byref(n), C.c_void_p),
+                                             C.cast(C.byref(dropped), C.c_void_p)))
+        return ag[:n.value].copy(), sq[:n.value].copy(), int(dropped.value)
 
     def import_prefetch(self, ptrs, wire_bytes: int, step: int) -> None:
         """Run the flag wait + localize pass of `step` on the handle's prefetch stream, beside what is enqueued next

@@ -40,6 +40,13 @@ from pydantic import BaseModel, Field
 from . import _native
 from ._native import NO_GROUP, RECV_PEEK, RECV_PRIORITY, TYPE_MASK, TYPEF_EXTRAS, TYPEF_JSON, SdbError, Shard, pad32
 
+
+class RingOverflow(SdbError):
+    """Some records of a flushed batch found their receiver's ring full.  `exact` tells whether the lost messages were
+    identified (only they are FAILED) or the whole batch had to be marked."""
+    exact = False
+
+
 try:  # the reference logs through loguru; keep the same logger object when it is installed
     from loguru import logger
 except Exception:  # pragma: no cover
@@ -303,17 +310,42 @@ class SwarmsDB:
             if st["ring_overflow"] > getattr(self, "_seen_overflow", 0):
                 lost = st["ring_overflow"] - getattr(self, "_seen_overflow", 0)
                 self._seen_overflow = st["ring_overflow"]
-                raise SdbError(-4, f"{lost} message(s) not enqueued: a receiver's ring is full "
-                                   f"(GpuConfig.ring_slots={self.gpu_config.ring_slots})")
+                err = RingOverflow(-4, f"{lost} message(s) not enqueued: a receiver's ring is full "
+                                       f"(GpuConfig.ring_slots={self.gpu_config.ring_slots})")
+                err.exact = self._mark_overflowed(msgs, str(err))
+                raise err
         except Exception as e:                  # M:501-519: mark FAILED, keep the error, re-raise
-            for m in msgs:
-                m.status = MessageStatus.FAILED
-                m.metadata["error"] = str(e)
+            if not (isinstance(e, RingOverflow) and e.exact):      # the device said which records were lost: only those failed
+                for m in msgs:
+                    m.status = MessageStatus.FAILED
+                    m.metadata["error"] = str(e)
             # ids already handed out stay used: the device counter moves up to the host's, never the other way
             self.shard.advance_seq(self._next_seq)
             self._reset_buffer()
             raise
         self._reset_buffer()
+
+    def _mark_overflowed(self, msgs: List[Message], error: str) -> bool:
+        """Delivery report for a batch that overflowed rings (M:374-391): the device logs (receiver, sequence number)
+        of every dropped record (sdb_overflow_log).  Point-to-point and group messages have one record each (id <->
+        sequence number): exactly those are marked FAILED, the rest of the batch stays DELIVERED.  A broadcast is one
+        message with many copies: it stays DELIVERED and names the receivers that missed it in
+        metadata["undelivered_to"].  Returns False when the log could not name every dropped record (more than its
+        capacity in one batch): the caller then fails the whole batch, as before."""
+        agents, seqs, dropped = self.shard.overflow_log()
+        if dropped != len(seqs):
+            return False
+        in_batch = {id(m) for m in msgs}
+        for a, sq in zip(agents.tolist(), seqs.tolist()):
+            m = self.messages.get(self._make_id(int(sq)))
+            if m is None or id(m) not in in_batch:
+                return False
+            if m.receiver_id is None:
+                m.metadata.setdefault("undelivered_to", []).append(self._agent_name[a] if a < len(self._agent_name) else a)
+            else:
+                m.status = MessageStatus.FAILED
+                m.metadata["error"] = error
+        return True
 
     # ------------------------------------------------------------------ registry
     def register_agent(self, agent_id: str) -> None:
@@ -618,13 +650,25 @@ class SwarmsDB:
         out: Dict[str, List[Message]] = {}
         if n == 0:
             return out
-        idx = np.arange(n, dtype=np.uint32)
         g = self.gpu_config
-        chunk = max(1, min(n, g.max_recv_records // max(per_agent, 1)))
         flags = RECV_PEEK | (RECV_PRIORITY if g.priority_dequeue else 0)
-        for b in range(0, n, chunk):
-            part = idx[b:b + chunk]
-            counts, hdr, pay = self.shard.receive_batch(part, per_agent, flags)
+        # A receive call holds min(max_recv_records, max_recv_payload / padded payload) records and leaves out whole
+        # agents beyond that; a PEEK consumes nothing, so a fixed chunking would silently skip them.  Chunks are packed
+        # from the agents' pending counts instead (one device query), so that every chunk fits.
+        max_recv_payload = g.max_recv_payload or g.max_recv_records * 256
+        cap = max(1, min(g.max_recv_records, max_recv_payload // pad32(g.max_payload_bytes)))
+        pending = np.minimum(self.shard.agent_loads(None, n)["pending"][:n].astype(np.int64), per_agent)
+        busy = np.nonzero(pending)[0]
+        b = 0
+        while b < len(busy):
+            e, room = b, cap
+            while e < len(busy) and (pending[busy[e]] <= room or e == b):
+                room -= int(pending[busy[e]]); e += 1
+            part = busy[b:e].astype(np.uint32)
+            if e == b + 1 and pending[busy[b]] > cap:
+                logger.warning(f"pending_snapshot: agent {self._agent_name[int(busy[b])]} has more pending messages than one "
+                               f"receive call holds ({cap}); the snapshot keeps the first {cap}")
+            counts, hdr, pay = self.shard.receive_batch(part, min(per_agent, cap), flags)
             offs = _native.payload_offsets(hdr)
             pos = 0
             for a, c in zip(part, counts):
@@ -634,6 +678,7 @@ class SwarmsDB:
                     sub_pay = pay[int(offs[pos]):] if pos < len(offs) else pay[:0]
                     out[name] = self._decode(hdr[pos:pos + c], sub_pay, name, record=False, status=MessageStatus.DELIVERED)
                 pos += c
+            b = e
         return out
 
     def _decode(self, hdr: np.ndarray, pay: np.ndarray, agent_id: str, record: bool = True,

@@ -17,6 +17,7 @@
 
 extern "C" {
 cudaError_t sdb_launch_p2p(const sdb_dev_view*, const sdb_send_desc*, uint32_t, const uint8_t*, uint64_t, uint64_t, int, cudaStream_t, sdb_profiler*, uint32_t);
+cudaError_t sdb_launch_ovf_resolve(const sdb_dev_view*, uint32_t, unsigned long long*, cudaStream_t);
 cudaError_t sdb_launch_list_index(const sdb_dev_view*, const sdb_send_desc*, const uint32_t*, const uint32_t*, uint32_t, uint32_t, uint64_t,
                                   cudaStream_t, sdb_profiler*);
 cudaError_t sdb_launch_commit_ranked(const sdb_dev_view*, const sdb_send_desc*, uint32_t, uint32_t, cudaStream_t, sdb_profiler*);
@@ -104,6 +105,7 @@ struct sdb_ctx {
   std::vector<uint32_t> lp_first;              // broadcast batches: first chunk descriptor of every send
   std::vector<uint64_t> lp_begin, lp_end;      // broadcast batches: where each send's / list's recipients sit in the pool
   uint32_t* lp_host = nullptr; uint32_t* lp_dev = nullptr; uint64_t lp_cap = 0;   // list-parallel index tables (pinned / device)
+  uint2* ovf_log = nullptr; unsigned long long* ovf_seq = nullptr;                  // overflow log + resolved sequence numbers
   // sharding (one handle = one shard): owner of each agent, full group lists, local positions
   std::vector<uint8_t> shard_of; bool sharded = false;
   std::vector<std::vector<uint32_t>> gfull;    // full member lists as given by the caller
@@ -592,7 +594,6 @@ int send_common(sdb_ctx* h, uint32_t kind, uint32_t n, SendArrays& a, const uint
     const uint32_t nl = kind == 2 ? n : a.n_lists;
     list_total = (nl && list_off) ? list_off[nl] : 0;
     const uint64_t cap = h->cfg.list_pool_entries;
-    if (list_total > cap) return fail(h, SDB_ECAPACITY, "recipient lists exceed list_pool_entries");
     // identical consecutive lists (the same "everybody" list passed with every broadcast) are stored and uploaded once
     h->lp_begin.assign(nl, 0); h->lp_end.assign(nl, 0);
     uint64_t used = 0, prev_b = 0, prev_n = 0; bool have_prev = false;
@@ -608,6 +609,7 @@ int send_common(sdb_ctx* h, uint32_t kind, uint32_t n, SendArrays& a, const uint
         if (list_idx[k] >= h->cfg.max_agents) return fail(h, SDB_EINVAL, "recipient index out of range");
         h->n_agents = std::max(h->n_agents, list_idx[k] + 1);
       }
+      if (used + cnt > cap) return fail(h, SDB_ECAPACITY, "recipient lists exceed list_pool_entries");
       if (cnt) std::memcpy(h->list_host + used, list_idx + b, cnt * sizeof(uint32_t));
       h->lp_begin[li] = used; h->lp_end[li] = used + cnt;
       prev_b = used; prev_n = cnt; have_prev = true;
@@ -715,6 +717,7 @@ int sdb_create(const sdb_config* cfg, sdb_handle* out) {
   CUDA_TRY(h, cudaMemsetAsync(h->ring_hdr, 0, A * sizeof(sdb_ring_hdr), h->stream));
   CUDA_TRY(h, cudaMemsetAsync(h->ring, 0xFF, A * R * sizeof(uint2), h->stream));          // every slot "consumed"
   CUDA_TRY(h, cudaMemsetAsync(h->ctr, 0, sizeof(sdb_dev_counters), h->stream));
+  CUDA_TRY(h, dmalloc(&h->ovf_log, SDB_OVF_LOG)); CUDA_TRY(h, dmalloc(&h->ovf_seq, SDB_OVF_LOG));
 
   // send staging
   h->desc_cap = static_cast<uint64_t>(c.max_batch_sends) + c.list_pool_entries / SDB_LIST_CHUNK + 1;
@@ -810,6 +813,7 @@ int sdb_create(const sdb_config* cfg, sdb_handle* out) {
 
   sdb_dev_view& v = h->view;
   v.arena = h->arena; v.ring_hdr = h->ring_hdr; v.ring = h->ring; v.members = h->members; v.member_pos = h->member_pos_dev; v.ctr = h->ctr;
+  v.ovf_log = h->ovf_log;
   v.gmask = h->arena_grans - 1; v.ring_slots = c.ring_slots; v.ring_shift = ilog2(c.ring_slots); v.max_agents = c.max_agents;
   CUDA_TRY(h, cudaStreamSynchronize(h->stream));
   return SDB_OK;
@@ -847,6 +851,8 @@ int sdb_destroy(sdb_handle h) {
   if (h->list_host) cudaFreeHost(h->list_host);
   if (h->lp_host) cudaFreeHost(h->lp_host);
   if (h->lp_dev) cudaFree(h->lp_dev);
+  if (h->ovf_log) cudaFree(h->ovf_log);
+  if (h->ovf_seq) cudaFree(h->ovf_seq);
   if (h->gs_host) cudaFreeHost(h->gs_host);
   if (h->wire_host) cudaFreeHost(h->wire_host);
   if (h->hdrs_host) cudaFreeHost(h->hdrs_host);
@@ -1419,6 +1425,30 @@ int sdb_import_wire_ptrs_async(sdb_handle h, uint32_t n_src, const void* const* 
   // 3. tell the exporters that this rank is done reading their buffers of this parity
   CUDA_TRY(h, sdb_launch_wire_set(my_done, step, h->stream));
   h->launches += 1;
+  return SDB_OK;
+}
+
+int sdb_overflow_log(sdb_handle h, uint32_t cap, uint32_t* agent_out, uint64_t* seq_out, uint32_t* n_out, uint64_t* dropped_out) {
+  if (!h || !n_out || (cap && (!agent_out || !seq_out))) return SDB_EINVAL;
+  *n_out = 0;
+  if (dropped_out) *dropped_out = 0;
+  CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+  unsigned long long logged = 0;
+  CUDA_TRY(h, cudaMemcpy(&logged, &h->ctr->ovf_logged, sizeof(logged), cudaMemcpyDeviceToHost));
+  if (dropped_out) *dropped_out = logged;
+  if (logged == 0) return SDB_OK;
+  const uint32_t n = static_cast<uint32_t>(std::min<unsigned long long>(std::min<unsigned long long>(logged, SDB_OVF_LOG), cap));
+  if (n) {
+    cudaError_t e = sdb_launch_ovf_resolve(&h->view, n, h->ovf_seq, h->stream);
+    if (e != cudaSuccess) return fail(h, SDB_ECUDA, std::string("overflow log: ") + cudaGetErrorString(e));
+    std::vector<uint2> log(n);
+    CUDA_TRY(h, cudaMemcpyAsync(log.data(), h->ovf_log, n * sizeof(uint2), cudaMemcpyDeviceToHost, h->stream));
+    CUDA_TRY(h, cudaMemcpyAsync(seq_out, h->ovf_seq, n * sizeof(uint64_t), cudaMemcpyDeviceToHost, h->stream));
+    CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+    for (uint32_t i = 0; i < n; ++i) agent_out[i] = log[i].x;
+  }
+  CUDA_TRY(h, cudaMemsetAsync(&h->ctr->ovf_logged, 0, sizeof(unsigned long long), h->stream));
+  *n_out = n;
   return SDB_OK;
 }
 

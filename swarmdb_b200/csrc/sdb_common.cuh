@@ -115,8 +115,10 @@ struct sdb_dev_counters {   // device-resident, updated with atomics
   unsigned long long ring_overflow;
   unsigned long long skipped_sender;
   unsigned long long backend_picks;
-  unsigned long long pad[3];
+  unsigned long long ovf_logged;    // records dropped since the overflow log was last read (the first SDB_OVF_LOG are logged)
+  unsigned long long pad[2];
 };
+#define SDB_OVF_LOG 4096u
 
 // everything a kernel needs about the shard, passed by value
 struct __align__(16) sdb_ring_hdr { uint32_t head, tail, ctail, ntomb; };
@@ -129,6 +131,7 @@ struct sdb_dev_view {
   const uint32_t* members;
   const uint32_t* member_pos;   // sharded mode: original group position of members[k]; else nullptr
   sdb_dev_counters* ctr;
+  uint2*    ovf_log;     // [SDB_OVF_LOG] {agent, arena handle} of records whose ring was full (sdb_overflow_log)
   uint64_t gmask;        // arena granules - 1
   uint32_t ring_slots;   // R
   uint32_t ring_shift;   // log2 R
@@ -290,11 +293,17 @@ __device__ __forceinline__ uint8_t* sdb_arena_ptr(const sdb_dev_view& v, uint64_
 
 // Claim the next slot of agent a's ring and publish (handle, meta) into it.
 // Returns false when the ring is full (nothing is written; the commit kernel clamps tail).
+// A record whose receiver's ring is full: it exists in the arena but no ring entry refers to it.  The (agent, handle)
+// pair is logged so that the host can tell WHICH messages were lost (sdb_overflow_log), not only how many.
+__device__ __forceinline__ void sdb_note_overflow(const sdb_dev_view& v, uint32_t a, uint32_t handle) {
+  const unsigned long long k = atomicAdd(&v.ctr->ovf_logged, 1ull);
+  if (k < SDB_OVF_LOG) v.ovf_log[k] = make_uint2(a, handle);
+}
 __device__ __forceinline__ bool sdb_ring_append(const sdb_dev_view& v, uint32_t a, uint32_t handle, uint16_t meta) {
   unsigned long long old = atomicAdd(reinterpret_cast<unsigned long long*>(v.ring_hdr + a), 1ull << 32);
   uint32_t e = static_cast<uint32_t>(old >> 32);
   uint32_t head = static_cast<uint32_t>(old);
-  if (e - head >= v.ring_slots) return false;
+  if (e - head >= v.ring_slots) { sdb_note_overflow(v, a, handle); return false; }
   size_t slot = (static_cast<size_t>(a) << v.ring_shift) + (e & (v.ring_slots - 1));
   v.ring[slot] = make_uint2(handle, meta);
   return true;

@@ -655,7 +655,7 @@ k_enqueue_p2p(sdb_dev_view v, const sdb_send_desc* __restrict__ descs, uint32_t 
         const uint4 hd = __ldcg(reinterpret_cast<const uint4*>(v.ring_hdr + a));
         const uint32_t room = v.ring_slots - (hd.z - hd.x);
         if (q3.y < room) { sdb_ring_of(v, a)[(hd.z + q3.y) & (v.ring_slots - 1)] = make_uint2(static_cast<uint32_t>(apos), meta); ++n_enq; }
-        else ++n_ovf;
+        else { ++n_ovf; sdb_note_overflow(v, a, static_cast<uint32_t>(apos)); }
         if (q3.x & SDB_DESC_RANK_LAST) v.ring_hdr[a].tail = hd.z + min(q3.y + 1u, room);
       } else if (sdb_ring_append(v, a, static_cast<uint32_t>(apos), meta)) ++n_enq; else ++n_ovf;
     }
@@ -754,7 +754,7 @@ k_enqueue_p2p_tma(sdb_dev_view v, const sdb_send_desc* __restrict__ descs, uint3
         if (cur.rank < room) {
           sdb_ring_of(v, cur.a)[(cur.hd.z + cur.rank) & (v.ring_slots - 1)] = make_uint2(cur.apos32, cur.meta);
           ++n_enq;
-        } else ++n_ovf;
+        } else { ++n_ovf; sdb_note_overflow(v, cur.a, cur.apos32); }
         if (cur.flags & SDB_DESC_RANK_LAST) v.ring_hdr[cur.a].tail = cur.hd.z + min(cur.rank + 1u, room);
       } else {
         if (sdb_ring_append(v, cur.a, cur.apos32, cur.meta)) ++n_enq; else ++n_ovf;
@@ -895,7 +895,7 @@ k_pull_index_group(sdb_dev_view v, sdb_pull_view pv, const sdb_send_desc* __rest
               const uint32_t qbits = (bal >> qb) & 0xFu;
               const uint32_t pos = tm + __popc(qbits & ((1u << sub) - 1u));
               if (keep) {
-                if (pos - hm >= R) ++n_ovf;
+                if (pos - hm >= R) { ++n_ovf; sdb_note_overflow(v, am, static_cast<uint32_t>(arena_base + gran0 + static_cast<uint64_t>(m0 + mi) * rgran)); }
                 else {
                   const uint32_t jm = m0 + mi;
                   const uint64_t meta_hi = static_cast<uint64_t>((((lpt >> 16) & 0xFFu) << 14) | rgran) << 32;
@@ -983,7 +983,7 @@ k_list_index(sdb_dev_view v, sdb_list_view lv, const sdb_send_desc* __restrict__
           const uint32_t tm = __shfl_sync(0xFFFFFFFFu, mi < 32 ? t0 : t1, srcl);
           if (have_send && am < v.max_agents) {
             const uint32_t pos = tm + sub;
-            if (pos - hm >= R) ++n_ovf;
+            if (pos - hm >= R) { ++n_ovf; sdb_note_overflow(v, am, static_cast<uint32_t>(arena_base + gran0 + static_cast<uint64_t>(m0 + mi) * rgran)); }
             else {
               const uint64_t meta_hi = static_cast<uint64_t>((((lpt >> 16) & 0xFFu) << 14) | rgran) << 32;
               sdb_st_u64_pol(reinterpret_cast<uint64_t*>(sdb_ring_of(v, am) + (pos & mask)),
@@ -1013,9 +1013,9 @@ __device__ __forceinline__ void pull_emit(const sdb_dev_view& v, const sdb_send_
                                           uint32_t& n_enq, uint32_t& n_ovf, uint64_t pol) {
   const uint4 q1 = __ldg(reinterpret_cast<const uint4*>(descs + s) + 1);   // gran0, sender, rgran, len|prio|type
   if (q1.y == a) return;                                                     // member == sender (M:1268)
-  if (tail - head >= v.ring_slots) { ++n_ovf; return; }
-  const uint32_t prio = (q1.w >> 16) & 0xFFu;
   const uint32_t handle = static_cast<uint32_t>(arena_base + q1.x + static_cast<uint64_t>(j) * q1.z);
+  if (tail - head >= v.ring_slots) { ++n_ovf; sdb_note_overflow(v, a, handle); return; }
+  const uint32_t prio = (q1.w >> 16) & 0xFFu;
   sdb_st_u64_pol(reinterpret_cast<uint64_t*>(sdb_ring_of(v, a) + (tail & (v.ring_slots - 1))),
                  (static_cast<uint64_t>((prio << 14) | q1.z) << 32) | handle, pol);
   ++tail; ++n_enq;
@@ -1056,7 +1056,7 @@ k_pull_index(sdb_dev_view v, sdb_pull_view pv, const sdb_send_desc* __restrict__
     const uint32_t qbits = (bal >> qb) & 0xFu;
     const uint32_t pos = tail + __popc(qbits & ((1u << sub) - 1u));
     if (keep) {
-      if (pos - head >= R) ++n_ovf;
+      if (pos - head >= R) { ++n_ovf; sdb_note_overflow(v, a, static_cast<uint32_t>(arena_base + q1.x + static_cast<uint64_t>(j) * q1.z)); }
       else {
         const uint32_t handle = static_cast<uint32_t>(arena_base + q1.x + static_cast<uint64_t>(j) * q1.z);
         sdb_st_u64_pol(reinterpret_cast<uint64_t*>(rs + (pos & (R - 1))),
@@ -1378,6 +1378,21 @@ extern "C" cudaError_t sdb_launch_list_index(const sdb_dev_view* v, const sdb_se
   dim3 grid((max_count + 255u) / 256u, nd);
   k_list_index<<<grid, 128, 0, stream>>>(*v, lv, descs, arena_base);
   sdb_prof_end(prof, pi, stream);
+  return cudaGetLastError();
+}
+
+// overflow log -> (agent, sequence number): the dropped records still sit in the arena (nothing refers to them), so the
+// sequence number is read from the record header
+__global__ void k_ovf_resolve(sdb_dev_view v, uint32_t n, unsigned long long* __restrict__ seq_out) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const uint2 e = v.ovf_log[i];
+  // the log keeps the low 32 bits of the arena position; arenas are at most 2^32 granules, so masking recovers the slot
+  seq_out[i] = *reinterpret_cast<const unsigned long long*>(v.arena + ((static_cast<uint64_t>(e.y) & v.gmask) << 5));
+}
+extern "C" cudaError_t sdb_launch_ovf_resolve(const sdb_dev_view* v, uint32_t n, unsigned long long* seq_out, cudaStream_t stream) {
+  if (n == 0) return cudaSuccess;
+  k_ovf_resolve<<<(n + 127) / 128, 128, 0, stream>>>(*v, n, seq_out);
   return cudaGetLastError();
 }
 

@@ -348,8 +348,20 @@ def run_sharded_bench(args, rank: int, world: int, local_rank: int, wl):
         launches = st_end["kernel_launches"] - launches0
         delivered = st_end["delivered"] - st0["delivered"]
         assert st_end["ring_overflow"] == 0, f"ring overflow on rank {rank}: {st_end['ring_overflow']} records (ring_slots={ring_slots})"
+        sustained = None
+        Ks = int(getattr(args, "sustained_steps", 0) or 0)
+        if Ks > 0:                                          # the same step for a few hundred milliseconds, timed as one block
+            clocks_s = ClockSampler(local_rank); clocks_s.start()
+            dist.barrier(); torch.cuda.synchronize()
+            ev0.record(stream)
+            for i in range(Ks):
+                device_step(W + K + i)
+            ev1.record(stream)
+            torch.cuda.synchronize(); dist.barrier()
+            sustained = {"steps": Ks, "ms": ev0.elapsed_time(ev1), "clocks": clocks_s.stop()}
+            assert shard.stats()["ring_overflow"] == 0
         if pipelined:                                       # the step prefetched by the last timed one: import it, start no other
-            device_step(W + K, start_next=False)
+            device_step(W + K + Ks, start_next=False)
             torch.cuda.synchronize()
 
         # ---- e2e: host buffers in (export H2D), results out (D2H into pinned buffers)
@@ -402,7 +414,8 @@ def run_sharded_bench(args, rank: int, world: int, local_rank: int, wl):
         pmax = pstat.clone(); dist.all_reduce(pmax, op=dist.ReduceOp.MAX)
         dist.all_reduce(pstat)
 
-    t = torch.tensor([ms, float(delivered), e2e_ms, float(got), float(launches)], dtype=torch.float64, device=dev)
+    t = torch.tensor([ms, float(delivered), e2e_ms, float(got), float(launches), sustained["ms"] if sustained else 0.0],
+                     dtype=torch.float64, device=dev)
     mx = t.clone(); dist.all_reduce(mx, op=dist.ReduceOp.MAX)
     sm = t.clone(); dist.all_reduce(sm, op=dist.ReduceOp.SUM)
     if rank == 0:
@@ -438,6 +451,9 @@ def run_sharded_bench(args, rank: int, world: int, local_rank: int, wl):
                        "l2": "inputs larger than L2 (each shard writes and reads back ~1.2 GB of records per step)",
                        "parallelism": f"shard{world}", "ring_slots": ring_slots},
             "clocks": clk,
+            "sustained": ({"steps": Ks, "ms_per_step": float(mx[5]) / Ks, "unit": "messages/s",
+                           "value": Ks * per_rank_msgs * world / (float(mx[5]) * 1e-3), "clocks": sustained["clocks"]}
+                          if sustained else None),
             "e2e": {"value": total_got / (e2e_max * 1e-3), "unit": "messages/s",
                     "h2d_bytes_per_step": (wl.S * wl.L + wl.S * 64) * world,
                     "d2h_bytes_per_step": int(total_got / Ke * (32 + wl.L)) + wl.A * 4, "steps": Ke,

@@ -51,6 +51,7 @@ class OracleShard:
     def advance_seq(self, next_seq): self.o.next_seq = max(self.o.next_seq, next_seq)
 
     def stats(self): return {"next_seq": self.o.next_seq, "ring_overflow": 0, "n_agents": self.max_agents}
+    def overflow_log(self, cap=4096): return np.zeros(0, np.uint32), np.zeros(0, np.uint64), 0
 
     def set_agent_shards(self, shard_of):
         s = np.asarray(shard_of, np.uint8)

@@ -102,3 +102,77 @@ def test_sharded_close_is_not_a_flush(tmp_path):
     db.close()
     db.close()                                                            # idempotent
     assert calls == ["close"]
+
+
+class _OverflowingShard(OracleShard):
+    """Stand-in that 'drops' chosen records of the next batch: reports them through ring_overflow + overflow_log the
+    way the device does (the oracle has no ring limit, so the drop itself is only reported, not performed)."""
+    def __init__(self, *a):
+        super().__init__(*a)
+        self.drop, self.ovf, self.truncate = [], 0, False
+
+    def stats(self):
+        st = super().stats(); st["ring_overflow"] = self.ovf
+        return st
+
+    def send_mixed_batch(self, *a, **k):
+        base = super().send_mixed_batch(*a, **k)
+        self._log = [(ag, base + off) for ag, off in self.drop]
+        self.ovf += len(self._log); self.drop = []
+        return base
+
+    def overflow_log(self, cap=4096):
+        log, self._log = self._log, []
+        if self.truncate:                                  # more drops than the log holds
+            return np.zeros(0, np.uint32), np.zeros(0, np.uint64), len(log)
+        return (np.array([x[0] for x in log], np.uint32), np.array([x[1] for x in log], np.uint64), len(log))
+
+
+def test_ring_overflow_fails_only_the_messages_that_were_lost(tmp_path):
+    """ADVICE core.py:302 (first half) - a flush that overflowed rings used to mark EVERY message of the batch FAILED,
+    so resend_failed_messages() resent messages that had been delivered.  The device now names the dropped records."""
+    shard = _OverflowingShard(64, 16, 0, 1)
+    sdb, db = _db(tmp_path, n=64, shard=shard)
+    db.register_agents(["s", "r1", "r2", "r3"])
+    ids = [db.send_message("s", f"m{k}", "r1") for k in range(5)]                 # seq offsets 0..4
+    bid = db.broadcast_message("s", "to all")                                      # offset 5, one message, three copies
+    shard.drop = [(db.agent_index("r1"), 1), (db.agent_index("r1"), 3), (db.agent_index("r2"), 5)]
+    with pytest.raises(sdb.RingOverflow) as ei:
+        db.flush()
+    assert ei.value.exact and "3 message(s)" in str(ei.value)
+    st = [db.get_message(i).status for i in ids]
+    assert [x == sdb.MessageStatus.FAILED for x in st] == [False, True, False, True, False]
+    assert "ring is full" in db.get_message(ids[1]).metadata["error"]
+    b = db.get_message(bid)
+    assert b.status == sdb.MessageStatus.DELIVERED and b.metadata["undelivered_to"] == ["r2"]
+    resent = db.resend_failed_messages()
+    assert len(resent) == 2 and [db.get_message(i).content for i in resent] == ["m1", "m3"]
+    # a log that could not name every drop: the whole batch is failed, as before
+    more = [db.send_message("s", f"n{k}", "r3") for k in range(3)]
+    db.flush()
+    more = [db.send_message("s", f"p{k}", "r3") for k in range(3)]
+    shard.drop = [(db.agent_index("r3"), 0)]; shard.truncate = True
+    with pytest.raises(sdb.RingOverflow) as ei:
+        db.flush()
+    assert not ei.value.exact and all(db.get_message(i).status == sdb.MessageStatus.FAILED for i in more)
+    db.close()
+
+
+def test_pending_snapshot_packs_its_peek_calls_by_pending_counts(tmp_path):
+    """ADVICE core.py:593 - the snapshot used to peek fixed chunks of agents with a per-agent window far above the
+    call's record capacity; agents beyond the capacity were silently left out.  Chunks now follow the pending counts."""
+    sdb, db = _db(tmp_path, n=512, max_recv_records=256, max_payload_bytes=1024)
+    names = [f"p{i:03d}" for i in range(300)]
+    db.register_agents(names)
+    for k in range(3):
+        for i in range(0, 300, 3):                                         # every third agent has 3 pending
+            db.send_message("p000", f"x{k}", names[i])
+    calls = []
+    real = db.shard.receive_batch
+    db.shard.receive_batch = lambda agents, mx, flags=0, **kw: (calls.append((len(agents), mx)), real(agents, mx, flags, **kw))[1]
+    snap = db.pending_snapshot()
+    assert sorted(snap) == sorted(names[i] for i in range(0, 300, 3))
+    assert all([m.content for m in v] == ["x0", "x1", "x2"] for v in snap.values())
+    assert all(n_ag * 3 <= 256 and mx <= 256 for n_ag, mx in calls) and len(calls) == 2          # 85 + 15 agents
+    assert len(db.receive_messages(names[3])) == 3                          # nothing was consumed
+    db.close()

@@ -151,3 +151,25 @@ def test_plain_c_caller(tmp_path):
     from tests.test_abi_cpu import _build_c_demo
     p = subprocess.run([str(_build_c_demo(tmp_path))], capture_output=True, text=True)
     assert p.returncode == 0 and 'agent 2 got 1 message(s)' in p.stdout and '"hello"' in p.stdout, p.stdout + p.stderr
+
+
+@pytest.mark.gpu
+def test_python_surface_fails_only_the_messages_a_full_ring_dropped(tmp_path):
+    """core.flush + sdb_overflow_log on the real device: 10 messages into a 4-slot ring - the first four are delivered
+    and stay DELIVERED, the other six are FAILED and are the only ones resend_failed_messages() sends again."""
+    import swarmdb_b200 as sdb
+    cfg = sdb.GpuConfig(max_agents=64, max_groups=4, ring_slots=4, deterministic_ids=True, flush_threshold=1000)
+    db = sdb.SwarmsDB(save_dir=str(tmp_path), auto_save=False, gpu_config=cfg)
+    ids = [db.send_message("s", f"m{k}", "r") for k in range(10)]
+    with pytest.raises(sdb.RingOverflow) as ei:
+        db.flush()
+    assert ei.value.exact
+    failed = [db.get_message(i).status == sdb.MessageStatus.FAILED for i in ids]
+    assert failed == [False] * 4 + [True] * 6
+    assert [m.content for m in db.receive_messages("r")] == ["m0", "m1", "m2", "m3"]
+    resent = db.resend_failed_messages()
+    assert len(resent) == 6
+    with pytest.raises(sdb.RingOverflow):
+        db.flush()                                         # six into four slots again: two more are lost, by name
+    assert [m.content for m in db.receive_messages("r")] == ["m4", "m5", "m6", "m7"]
+    db.close()

@@ -178,6 +178,9 @@ def test_ring_overflow_is_reported_not_silent():
     cnt, hdr, pay = g.receive_batch([1], 100)
     assert cnt[0] == 4
     assert hdr["seq"].tolist() == [base0 + k for k in range(4)]     # ranked enqueue: the FIRST sends of the batch are the ones kept
+    ag, sq, dropped = g.overflow_log()                      # which records were lost, not only how many
+    assert dropped == 6 and ag.tolist() == [1] * 6 and sorted(sq.tolist()) == [base0 + k for k in range(4, 10)]
+    assert g.overflow_log()[2] == 0                         # reading clears the log
     # ring usable again afterwards
     g.send_batch(np.zeros(3), np.ones(3), None, None, lens[:3], off[:3], buf)
     assert g.receive_batch([1], 100)[0][0] == 3
@@ -190,6 +193,26 @@ def test_ring_overflow_is_reported_not_silent():
     cnt, hdr, _ = g.receive_batch([1, 2], 100)
     assert cnt.tolist() == [4, 2]
     assert hdr["seq"][3] == base and hdr["seq"][4:].tolist() == [base + 1, base + 4]
+    ag, sq, dropped = g.overflow_log()
+    assert dropped == 4 and sorted(sq.tolist()) == [base + 2, base + 3, base + 5, base + 6]
+    # group fan-out through the owner-computes index build (batch above the pull threshold) and a broadcast list
+    g2, _ = _pair(20000, max_groups=2, ring_slots=4, max_batch_sends=64)
+    members = np.arange(17000, dtype=np.uint32)
+    g2.create_group(0, members)
+    lens2, off2, buf2 = _mk_payloads(rng, 6, 16)
+    b2 = g2.stats()["next_seq"]
+    g2.send_group_batch(np.full(6, 19999), np.zeros(6), None, None, lens2, off2, buf2)       # 6 sends x 17000 members, 4 slots each
+    ag, sq, dropped = g2.overflow_log()
+    assert dropped == 2 * 17000 and len(sq) == 4096
+    rel = sq - b2                                             # seq = base + send * 17000 + member position
+    assert set((rel // 17000).tolist()) <= {4, 5} and np.array_equal(rel % 17000, ag)
+    assert g2.receive_batch(members, 100)[0].tolist() == [4] * 17000
+    lo = np.array([0, 17000, 34000, 51000, 68000, 85000, 102000], np.uint64)
+    g2.send_list_batch(np.full(6, 19999), lo, np.tile(members, 6), None, None, lens2, off2, buf2)
+    ag, sq, dropped = g2.overflow_log()
+    b3 = g2.stats()["next_seq"] - 6
+    assert dropped == 2 * 17000 and set((sq - b3).tolist()) <= {4, 5}                         # a broadcast is ONE sequence number
+    g2.close()
 
 
 def test_ranked_p2p_enqueue_many_per_receiver_and_staged_resubmit():
