@@ -504,16 +504,20 @@ __device__ __forceinline__ void fill_offsets_warp(uint4* plan, uint32_t RO, uint
 }
 
 __global__ void __launch_bounds__(SDB_PLAN_TILE)
-k_recv_plan(sdb_dev_view v, sdb_recv_args r, uint32_t tiles) {
+k_recv_plan(sdb_dev_view v, sdb_recv_args r, uint32_t tiles, uint32_t ticketed) {
   __shared__ uint32_t s_tile;
   __shared__ unsigned long long s_wr[SDB_PLAN_WARPS], s_wg[SDB_PLAN_WARPS];
   __shared__ unsigned long long s_br, s_bg;
   __shared__ uint4 s_stage[SDB_PLAN_WARPS][SDB_PLAN_STAGE];                // per warp: plan entries on their way out (32 KB)
   const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const size_t ticket_at = static_cast<size_t>(tiles) + 3 * ((tiles + 31) / 32), totals_at = ticket_at + 1;
-  if (tid == 0) s_tile = atomicAdd(reinterpret_cast<unsigned int*>(r.lb + ticket_at), 1u);
-  __syncthreads();
-  const uint32_t tile = s_tile;
+  // tile id: a ticket (dispatch order by construction) or, SDB_PLAN_TICKET=0, the block index (the hardware dispatches
+  // the blocks of a 1-D grid in index order, so earlier tiles are resident or finished: saves one L2 round trip)
+  if (ticketed) {
+    if (tid == 0) s_tile = atomicAdd(reinterpret_cast<unsigned int*>(r.lb + ticket_at), 1u);
+    __syncthreads();
+  }
+  const uint32_t tile = ticketed ? s_tile : blockIdx.x;
   const uint32_t q = tile * SDB_PLAN_TILE + tid;
   const bool valid = q < r.n;
   const bool retire = !(r.flags & SDB_RECV_PEEK);
@@ -1072,7 +1076,8 @@ extern "C" cudaError_t sdb_launch_receive(const sdb_dev_view* v, const sdb_recv_
     r->plan_tops = nullptr;
     pi = sdb_prof_begin(prof, SDB_PK_RECV_SELECT, stream);
     cudaMemsetAsync(r->lb, 0, sdb_lb_words(tiles) * sizeof(unsigned long long), stream);
-    k_recv_plan<<<tiles, SDB_PLAN_TILE, 0, stream>>>(*v, *r, tiles);
+    static const uint32_t ticketed = (getenv("SDB_PLAN_TICKET") && atoi(getenv("SDB_PLAN_TICKET")) == 0) ? 0u : 1u;
+    k_recv_plan<<<tiles, SDB_PLAN_TILE, 0, stream>>>(*v, *r, tiles, ticketed);
     sdb_prof_end(prof, pi, stream);
     if (n_launches) *n_launches += 1;
     return launch_gather(v, r, r->lb + sdb_lb_words(tiles) - 1, bound, max_rec_bytes, sm_count, stream, prof, n_launches);
