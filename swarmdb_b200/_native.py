@@ -38,6 +38,12 @@ STATUS_NAMES = {0: "SDB_OK", -1: "SDB_EINVAL", -2: "SDB_ECUDA", -3: "SDB_ENOMEM"
                 -5: "SDB_EARENA_FULL", -6: "SDB_ECAPACITY", -7: "SDB_ENOTFOUND", -8: "SDB_EOUTPUT"}
 
 
+def shared_payload_enabled() -> bool:
+    """Mirror of the library's SDB_SHARED_PAYLOAD switch (csrc/sdb_api.cu, sdb_create): group sends above the pull
+    threshold keep ONE payload per send in the arena log instead of one per recipient."""
+    return os.environ.get("SDB_SHARED_PAYLOAD", "1") != "0"
+
+
 class SdbError(RuntimeError):
     def __init__(self, code: int, msg: str) -> None:
         super().__init__(f"{STATUS_NAMES.get(code, code)}: {msg}")

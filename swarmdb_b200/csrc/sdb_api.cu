@@ -23,12 +23,14 @@ cudaError_t sdb_launch_list_index(const sdb_dev_view*, const sdb_send_desc*, con
 cudaError_t sdb_launch_commit_ranked(const sdb_dev_view*, const sdb_send_desc*, uint32_t, uint32_t, cudaStream_t, sdb_profiler*);
 cudaError_t sdb_send_prepare_device();
 cudaError_t sdb_launch_fanout(const sdb_dev_view*, const sdb_send_desc*, uint32_t, const uint8_t*, const uint32_t*,
-                              uint64_t, uint64_t, uint32_t, int, int, cudaStream_t, sdb_profiler*, const sdb_batch_base*);
+                              uint64_t, uint64_t, uint32_t, int, int, cudaStream_t, sdb_profiler*, const sdb_batch_base*, uint32_t);
+cudaError_t sdb_launch_fanout_shared(const sdb_dev_view*, const sdb_send_desc*, uint32_t, const uint8_t*, uint64_t, uint64_t, uint32_t, int,
+                                     cudaStream_t, sdb_profiler*, const sdb_batch_base*);
 cudaError_t sdb_launch_commit(const sdb_dev_view*, uint32_t, uint32_t, uint32_t*, uint32_t*, int, cudaStream_t, sdb_profiler*,
                               const sdb_batch_base*);
 cudaError_t sdb_launch_pull(const sdb_dev_view*, const sdb_pull_view*, const sdb_send_desc*, uint32_t, uint32_t, const uint8_t*,
                             uint32_t, uint32_t, const uint32_t*, const uint32_t*, uint64_t, int, cudaStream_t, sdb_profiler*, int*,
-                            const sdb_batch_base*);
+                            const sdb_batch_base*, uint32_t);
 cudaError_t sdb_launch_receive(const sdb_dev_view*, const sdb_recv_args*, cudaStream_t, int*, sdb_profiler*, int, uint32_t);
 cudaError_t sdb_recv_prepare_device();
 cudaError_t sdb_launch_receive_small(const sdb_dev_view*, const uint32_t*, uint32_t, uint32_t, uint32_t, uint32_t, uint4*,
@@ -70,6 +72,7 @@ struct sdb_staged {
   bool has_pull = false;      // group sends indexed by k_pull_index
   bool has_atomic = false;    // some sends claim ring slots with atomics -> k_commit must sort
   bool ranked = false;        // pure point-to-point batch ranked per receiver at staging time: no atomics, no sort
+  bool shared = false;        // group sends laid out as headers + ONE payload per send (sdb_common.cuh "shared payloads")
   bool list_pull = false;     // pure broadcast batch over pairwise disjoint lists: ring entries built by k_list_index
   uint32_t lp_nd = 0, lp_max_count = 0, lp_words = 0;
   bool owns = false;          // device buffers owned by this object (else the handle's staging)
@@ -102,6 +105,8 @@ struct sdb_ctx {
   uint8_t* gexcl_dev = nullptr;          // [max_groups] 1: every member of the group belongs to that group only
   uint32_t n_excl_groups = 0, n_shared_agents = 0;
   std::vector<uint32_t> rank_cnt;              // per-receiver counters of the point-to-point ranking (all zero between batches)
+  bool shared_cfg = false;                     // SDB_SHARED_PAYLOAD: group sends above the pull threshold share one payload per send
+  uint32_t max_lcount = 0;                     // largest local member count of a group (shared payloads need <= 65535)
   std::vector<uint32_t> lp_first;              // broadcast batches: first chunk descriptor of every send
   std::vector<uint64_t> lp_begin, lp_end;      // broadcast batches: where each send's / list's recipients sit in the pool
   uint32_t* lp_host = nullptr; uint32_t* lp_dev = nullptr; uint64_t lp_cap = 0;   // list-parallel index tables (pinned / device)
@@ -136,6 +141,7 @@ struct sdb_ctx {
     sdb_send_desc* descs = nullptr; uint32_t* gs_off_src = nullptr; uint32_t* gs_idx_src = nullptr; uint32_t* first = nullptr;
     unsigned long long* lb = nullptr; sdb_wire_header* hdrs = nullptr; uint32_t* tmp_list = nullptr;
     sdb_import_totals* totals = nullptr; cudaEvent_t ready = nullptr; uint32_t step = 0; bool pending = false;
+    bool shared = false;            // layout the set's descriptors were localized for
   } xset[2];
   cudaStream_t pf_stream = nullptr; cudaEvent_t ev_pf_fork = nullptr;
   uint8_t* wire_host = nullptr;                // pinned: header + descriptors of an export
@@ -307,6 +313,8 @@ struct SendArrays {
 // sequence number, consecutive arena regions) so that one warp never owns a million-record fan-out; `out` therefore
 // holds s->n >= n descriptors, bounded by `out_cap`.
 static const uint32_t SDB_LIST_CHUNK = 1024;
+int rebuild_inverse(sdb_ctx* h);
+
 int build_descs(sdb_ctx* h, uint32_t batch_kind, uint32_t n, SendArrays& a, const uint64_t* list_off,
                 uint64_t payload_bytes, sdb_send_desc* out, uint64_t out_cap, sdb_staged* s, uint32_t* gs_out = nullptr,
                 uint32_t* n_gs_out = nullptr) {
@@ -318,6 +326,19 @@ int build_descs(sdb_ctx* h, uint32_t batch_kind, uint32_t n, SendArrays& a, cons
   uint32_t n_group_sends = 0, n_other = 0;
   const uint32_t A = h->cfg.max_agents;
   if (h->sharded) return fail(h, SDB_EINVAL, "sharded handle: sends go through sdb_export_*_batch + sdb_import_wire_*");
+  // shared payloads (pure group batches above the pull threshold, exclusive groups, payloads <= 512 bytes, groups of at
+  // most 65535 members): a send's region is mcount headers + ONE payload; decided before any arena offset is handed out
+  bool shared = false;
+  if (h->shared_cfg && batch_kind == 1 && gs_out && h->cfg.fanout_variant >= 2) {
+    if (h->memb_dirty) { int rc0 = rebuild_inverse(h); if (rc0 != SDB_OK) return rc0; }
+    uint64_t recs = 0; bool ok = h->n_shared_agents == 0 && h->n_excl_groups != 0;
+    for (uint32_t i = 0; i < n && ok; ++i) {
+      const uint32_t g = a.second[i];
+      if (g >= h->cfg.max_groups || !h->gdefined[g] || h->gcount[g] > 65535u || a.len[i] > 512u) ok = false;
+      else recs += h->gcount[g];
+    }
+    shared = ok && recs >= SDB_PULL_THRESHOLD;
+  }
   for (uint32_t i = 0; i < n; ++i) {
     sdb_send_desc d;
     std::memset(&d, 0, sizeof(d));
@@ -371,7 +392,8 @@ int build_descs(sdb_ctx* h, uint32_t batch_kind, uint32_t n, SendArrays& a, cons
       if (h->sharded) return fail(h, SDB_EINVAL, "sharded handle: use sdb_export_group_batch + sdb_import_wire_batches");
       d.mstart = static_cast<uint32_t>(h->gstart[g]); d.mcount = h->gcount[g]; d.group = g;
       d.flags = SDB_DESC_SKIP_SENDER;
-      rec += d.mcount; gran += static_cast<uint64_t>(d.mcount) * d.rgran;
+      rec += d.mcount;
+      gran += shared ? (d.mcount ? static_cast<uint64_t>(d.mcount) + d.rgran - 1u : 0ull) : static_cast<uint64_t>(d.mcount) * d.rgran;
       group_recs += d.mcount; ++n_group_sends;
     } else {
       const uint32_t li = batch_kind == 3 ? a.second[i] : i;
@@ -400,7 +422,7 @@ int build_descs(sdb_ctx* h, uint32_t batch_kind, uint32_t n, SendArrays& a, cons
   }
   const uint32_t n_out = static_cast<uint32_t>(o);
   s->kind = batch_kind; s->n = n_out; s->total_recs = rec; s->total_grans = gran; s->max_padlen = max_padlen;
-  s->has_pull = false; s->has_atomic = true; s->ranked = false; s->list_pull = false;
+  s->has_pull = false; s->has_atomic = true; s->ranked = false; s->list_pull = false; s->shared = shared;
   if (n_list_sends == n && n && list_copies >= SDB_PULL_THRESHOLD && a.lp_out && a.lbegin && a.list_pool) {
     // pure broadcast batch: if the lists it names are pairwise disjoint (and free of repeats), every member of a list
     // receives exactly the sends naming it, in send order -> owner-computes index build (k_list_index), no atomics.
@@ -509,7 +531,11 @@ int ensure_ltab(sdb_ctx* h) {
   if (!h->ltab_dirty) return SDB_OK;
   CUDA_TRY(h, cudaStreamSynchronize(h->stream));
   std::vector<uint32_t> st(h->cfg.max_groups), ct(h->cfg.max_groups);
-  for (uint32_t g = 0; g < h->cfg.max_groups; ++g) { st[g] = static_cast<uint32_t>(h->gstart[g]); ct[g] = h->gdefined[g] ? h->gcount[g] : 0; }
+  h->max_lcount = 0;
+  for (uint32_t g = 0; g < h->cfg.max_groups; ++g) {
+    st[g] = static_cast<uint32_t>(h->gstart[g]); ct[g] = h->gdefined[g] ? h->gcount[g] : 0;
+    h->max_lcount = std::max(h->max_lcount, ct[g]);
+  }
   CUDA_TRY(h, cudaMemcpy(h->lstart_dev, st.data(), st.size() * sizeof(uint32_t), cudaMemcpyHostToDevice));
   CUDA_TRY(h, cudaMemcpy(h->lcount_dev, ct.data(), ct.size() * sizeof(uint32_t), cudaMemcpyHostToDevice));
   h->ltab_dirty = false;
@@ -521,6 +547,8 @@ int submit(sdb_ctx* h, const sdb_staged* s, uint64_t* seq_base_out) {
   if (seq_base_out) *seq_base_out = h->next_seq;
   if (s->n == 0) return SDB_OK;
   if (s->has_pull && h->memb_dirty) { int rc0 = rebuild_inverse(h); if (rc0 != SDB_OK) return rc0; }
+  if (s->shared && (h->n_shared_agents != 0 || h->n_excl_groups == 0))
+    return fail(h, SDB_EINVAL, "batch staged before a membership change (its groups are no longer exclusive): stage it again");
   if (s->has_pull) { int rc1 = ensure_ltab(h); if (rc1 != SDB_OK) return rc1; }
   uint64_t base = 0;
   int rc = arena_reserve(h, s->total_grans, &base);
@@ -538,7 +566,7 @@ int submit(sdb_ctx* h, const sdb_staged* s, uint64_t* seq_base_out) {
     sdb_pull_view pv{h->memb_off_dev, h->memb_grp_dev, h->memb_pos_dev, s->gs_off_dev, s->gs_idx_dev, 1u, 0u, 0u, nullptr};
     int nlp = 0;
     e = sdb_launch_pull(&h->view, &pv, s->descs_dev, h->n_agents, h->cfg.max_groups, h->gexcl_dev, h->n_excl_groups,
-                        h->n_shared_agents, h->lstart_dev, h->lcount_dev, base, 1, h->side, &h->prof, &nlp, nullptr);
+                        h->n_shared_agents, h->lstart_dev, h->lcount_dev, base, 1, h->side, &h->prof, &nlp, nullptr, s->shared ? 1u : 0u);
     if (e != cudaSuccess) return fail(h, SDB_ECUDA, std::string("index launch: ") + cudaGetErrorString(e));
     CUDA_TRY(h, cudaEventRecord(h->ev_join, h->side));
     h->launches += nlp;
@@ -549,9 +577,11 @@ int submit(sdb_ctx* h, const sdb_staged* s, uint64_t* seq_base_out) {
       e = sdb_launch_commit_ranked(&h->view, s->descs_dev, s->n, h->n_agents, h->stream, &h->prof);
       h->launches += 1;
     }
+  } else if (s->shared) {
+    e = sdb_launch_fanout_shared(&h->view, s->descs_dev, s->n, s->payload_dev, h->next_seq, base, 0u, h->sm_count, h->stream, &h->prof, nullptr);
   } else {
     e = sdb_launch_fanout(&h->view, s->descs_dev, s->n, s->payload_dev, s->list_dev, h->next_seq, base,
-                          s->max_padlen, static_cast<int>(h->cfg.fanout_variant), h->sm_count, h->stream, &h->prof, nullptr);
+                          s->max_padlen, static_cast<int>(h->cfg.fanout_variant), h->sm_count, h->stream, &h->prof, nullptr, 0u);
   }
   h->launches += 1;
   if (e == cudaSuccess && overlap) {
@@ -560,7 +590,8 @@ int submit(sdb_ctx* h, const sdb_staged* s, uint64_t* seq_base_out) {
     sdb_pull_view pv{h->memb_off_dev, h->memb_grp_dev, h->memb_pos_dev, s->gs_off_dev, s->gs_idx_dev, 1u, 0u, 0u, nullptr};
     int nlp = 0;
     e = sdb_launch_pull(&h->view, &pv, s->descs_dev, h->n_agents, h->cfg.max_groups, h->gexcl_dev, h->n_excl_groups,
-                        h->n_shared_agents, h->lstart_dev, h->lcount_dev, base, s->has_atomic ? 0 : 1, h->stream, &h->prof, &nlp, nullptr);
+                        h->n_shared_agents, h->lstart_dev, h->lcount_dev, base, s->has_atomic ? 0 : 1, h->stream, &h->prof, &nlp, nullptr,
+                        s->shared ? 1u : 0u);
     h->launches += nlp;
   }
   if (e == cudaSuccess && s->list_pull) {
@@ -694,6 +725,12 @@ int sdb_create(const sdb_config* cfg, sdb_handle* out) {
     const char* fg = getenv("SDB_L2_FETCH");
     const int gran = fg ? atoi(fg) : 64;
     if (gran > 0) cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, static_cast<size_t>(gran));
+  }
+  {
+    // shared payloads for group sends above the pull threshold (sdb_common.cuh): SDB_SHARED_PAYLOAD=0 keeps one
+    // payload copy per recipient in the arena log
+    const char* sp = getenv("SDB_SHARED_PAYLOAD");
+    h->shared_cfg = sp ? atoi(sp) != 0 : true;
   }
   CUDA_TRY(h, sdb_send_prepare_device());
   CUDA_TRY(h, sdb_recv_prepare_device());
@@ -1256,18 +1293,18 @@ int sdb_import_wire_ptrs(sdb_handle h, uint32_t n_src, const void* const* wire_p
     CUDA_TRY(h, cudaStreamWaitEvent(h->side, h->ev_fork, 0));
     sdb_pull_view pv{h->memb_off_dev, h->memb_grp_dev, h->memb_pos_dev, h->xs_gs_off, h->xs_gs_idx, 1u, 0u, 0u, nullptr};
     e = sdb_launch_pull(&h->view, &pv, h->xs_descs, h->n_agents, h->cfg.max_groups, h->gexcl_dev, h->n_excl_groups,
-                        h->n_shared_agents, h->lstart_dev, h->lcount_dev, base, 1, h->side, &h->prof, &nl, nullptr);
+                        h->n_shared_agents, h->lstart_dev, h->lcount_dev, base, 1, h->side, &h->prof, &nl, nullptr, 0u);
     if (e == cudaSuccess) CUDA_TRY(h, cudaEventRecord(h->ev_join, h->side));
   }
   if (e == cudaSuccess)
     e = sdb_launch_fanout(&h->view, h->xs_descs, n_cap, nullptr, h->scratch.list_dev, h->next_seq, base, max_padlen,
-                          h->cfg.fanout_variant >= 2 ? 3 : static_cast<int>(h->cfg.fanout_variant), h->sm_count, h->stream, &h->prof, nullptr);
+                          h->cfg.fanout_variant >= 2 ? 3 : static_cast<int>(h->cfg.fanout_variant), h->sm_count, h->stream, &h->prof, nullptr, 0u);
   if (e == cudaSuccess && overlap) {
     CUDA_TRY(h, cudaStreamWaitEvent(h->stream, h->ev_join, 0));
   } else if (e == cudaSuccess) {
     sdb_pull_view pv{h->memb_off_dev, h->memb_grp_dev, h->memb_pos_dev, h->xs_gs_off, h->xs_gs_idx, 1u, 0u, 0u, nullptr};
     e = sdb_launch_pull(&h->view, &pv, h->xs_descs, h->n_agents, h->cfg.max_groups, h->gexcl_dev, h->n_excl_groups,
-                        h->n_shared_agents, h->lstart_dev, h->lcount_dev, base, n_other ? 0 : 1, h->stream, &h->prof, &nl, nullptr);
+                        h->n_shared_agents, h->lstart_dev, h->lcount_dev, base, n_other ? 0 : 1, h->stream, &h->prof, &nl, nullptr, 0u);
   }
   if (e == cudaSuccess && n_other) {     // p2p / broadcast copies claimed their slots with atomics: sort them into place
     e = sdb_launch_commit(&h->view, h->n_agents, static_cast<uint32_t>(base), h->rx_big_list, h->rx_big_count + 1, h->sm_count, h->stream, &h->prof, nullptr);
@@ -1326,6 +1363,10 @@ static int xs_localize(sdb_ctx* h, sdb_ctx::XsSet& S, uint32_t n_src, const void
   a.tmp_list = S.tmp_list; a.list_cap = static_cast<uint32_t>(std::min<uint64_t>(h->cfg.list_pool_entries, 0x7FFFFFF0ull));
   a.lb = S.lb; a.cur = h->cursor_dev; a.bb = h->bb_dev; a.arena_grans = h->arena_grans;
   a.hdrs = S.hdrs; a.commit_count = h->rx_big_count + 1; a.totals = defer ? S.totals : nullptr;
+  // shared payloads: a send's local region is lc headers + one payload (the fast shape already guarantees payloads
+  // <= 512 bytes and exclusive groups; local groups must fit the 16-bit header-to-payload distance)
+  S.shared = h->shared_cfg && h->max_lcount <= 65535u;
+  a.shared = S.shared ? 1u : 0u;
   int nl = 1;
   cudaError_t e = sdb_launch_import_fused(&a, st, &h->prof, &nl);
   h->launches += nl;
@@ -1407,13 +1448,20 @@ int sdb_import_wire_ptrs_async(sdb_handle h, uint32_t n_src, const void* const* 
   }
   int nl = 0;
   const uint32_t n_cap = n_src * h->cfg.max_batch_sends;
-  cudaError_t e = sdb_launch_fanout(&h->view, S.descs, n_cap, nullptr, S.tmp_list, 0, 0, pad32(h->cfg.max_payload_bytes), 3,
-                                    h->sm_count, h->stream, &h->prof, h->bb_dev);
+  cudaError_t e = cudaSuccess;
+  if (S.shared) {            // group sends: headers + one payload per send; the span kernel only serves p2p / broadcast descriptors
+    e = sdb_launch_fanout_shared(&h->view, S.descs, n_cap, nullptr, 0, 0, h->cfg.num_shards >= 4 ? 1u : 0u, h->sm_count, h->stream,
+                                 &h->prof, h->bb_dev);
+    ++nl;
+  }
+  if (e == cudaSuccess)
+    e = sdb_launch_fanout(&h->view, S.descs, n_cap, nullptr, S.tmp_list, 0, 0, pad32(h->cfg.max_payload_bytes), 3,
+                          h->sm_count, h->stream, &h->prof, h->bb_dev, S.shared ? 1u : 0u);
   if (e == cudaSuccess) {
     sdb_pull_view pv{h->memb_off_dev, h->memb_grp_dev, h->memb_pos_dev, S.gs_off_src, S.gs_idx_src, n_src,
                      h->cfg.max_groups + 1, h->cfg.max_batch_sends, S.first};
     e = sdb_launch_pull(&h->view, &pv, S.descs, h->n_agents, h->cfg.max_groups, h->gexcl_dev, h->n_excl_groups, 0,
-                        h->lstart_dev, h->lcount_dev, 0, 0, h->stream, &h->prof, &nl, h->bb_dev);
+                        h->lstart_dev, h->lcount_dev, 0, 0, h->stream, &h->prof, &nl, h->bb_dev, S.shared ? 1u : 0u);
   }
   // point-to-point / broadcast copies claimed their slots with atomics: sort them into place (the kernels return at
   // once when the import carried none); the group-parallel build leaves ctail to the commit

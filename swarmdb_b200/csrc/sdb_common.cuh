@@ -264,6 +264,7 @@ struct sdb_import2_args {
   uint32_t* commit_count;             // reset here for the commit sort that follows the fan-out
   sdb_import_totals* totals;          // prefetch mode (non-null): the grand totals go here and k_import_place places the
                                       // import later, on the shard's stream (the cursor is not touched by this kernel)
+  uint32_t shared;                    // group sends take the shared-payload layout: lc headers + one payload per send
 };
 
 // ---- optional per-kernel timing with CUDA events on the launching stream (bench / roofline) ----
@@ -312,6 +313,17 @@ __device__ __forceinline__ uint2* sdb_ring_of(const sdb_dev_view& v, uint32_t a)
   return v.ring + (static_cast<size_t>(a) << v.ring_shift);
 }
 __device__ __forceinline__ uint32_t sdb_meta(const uint2& e) { return e.y & 0xFFFFu; }
+// Shared payloads.  A record is a 32-byte header at `handle` and its payload at handle + 1 + dm1 granules.  dm1 = 0 is
+// the classic image (payload right behind its header); group sends above the pull threshold write the members' headers
+// back to back and ONE payload behind them (header j of m: dm1 = m - 1 - j), which every member's ring entry points at.
+// dm1 travels in the upper half of a ring entry's .y (the lower half is the meta word) and of a plan entry's .z (the
+// lower half is the payload size in granules).  The payload sits ABOVE all its headers, so the arena floor - the
+// smallest pending handle - never passes a payload that is still referenced.
+__device__ __forceinline__ uint32_t sdb_entry_dm1(uint32_t y) { return y >> 16; }
+__device__ __forceinline__ uint32_t sdb_plan_z(uint32_t y) { return ((y & SDB_META_GLEN_MASK) - 1u) | (y & 0xFFFF0000u); }   // ring .y -> plan .z
+__device__ __forceinline__ const uint8_t* sdb_payload_of(const sdb_dev_view& v, uint32_t handle, uint32_t dm1) {
+  return v.arena + (((static_cast<uint64_t>(handle) + 1u + dm1) & v.gmask) << 5);
+}
 
 __device__ __forceinline__ uint4 sdb_header_lo(uint64_t seq, double ts) {
   uint4 r;

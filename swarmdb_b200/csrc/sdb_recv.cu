@@ -172,7 +172,7 @@ __device__ __forceinline__ void select_agent_warp(const sdb_dev_view& v, uint4* 
     // long contiguous run [H, H+C)
     for (uint32_t j = lane; j < C; j += 32) {
       const uint2 e = rs[(H + j) & mask];
-      plan[RO + j] = make_uint4(e.x, 0u, (sdb_meta(e) & SDB_META_GLEN_MASK) - 1u, slot);
+      plan[RO + j] = make_uint4(e.x, 0u, sdb_plan_z(e.y), slot);
     }
     if (lane == 0 && retire) v.ring_hdr[A].head = H + C;
     return;
@@ -247,7 +247,7 @@ __device__ __forceinline__ void select_agent_warp(const sdb_dev_view& v, uint4* 
       taken[lev] += __popc(b);
     }
     if (sel) {
-      plan[RO + rank] = make_uint4(e.x, 0u, (m & SDB_META_GLEN_MASK) - 1u, slot);
+      plan[RO + rank] = make_uint4(e.x, 0u, sdb_plan_z(e.y), slot);
       if (retire) rs[p & mask].y = SDB_META_TOMB;
     }
     const uint32_t bs = __ballot_sync(0xFFFFFFFFu, sel);
@@ -303,7 +303,7 @@ k_recv_select(sdb_dev_view v, sdb_recv_args r) {
 #pragma unroll
       for (uint32_t j = 0; j < CH; ++j)
         if (b + j < cnt)
-          r.plan[roff + b + j] = make_uint4(static_cast<uint32_t>(ev[j]), 0u, (static_cast<uint32_t>(ev[j] >> 32) & SDB_META_GLEN_MASK) - 1u, q);
+          r.plan[roff + b + j] = make_uint4(static_cast<uint32_t>(ev[j]), 0u, sdb_plan_z(static_cast<uint32_t>(ev[j] >> 32)), q);
     }
     if (!(r.flags & SDB_RECV_PEEK)) v.ring_hdr[a].head = head + cnt;
   }
@@ -372,7 +372,7 @@ __device__ __forceinline__ void select_agent_warp_bounded(const sdb_dev_view& v,
     for (uint32_t k = lane; k < take; k += 32) {
       const uint32_t p = cand[lev][k];
       const uint2 e = rs[p & mask];
-      plan[RO + acc + k] = make_uint4(e.x, 0u, (sdb_meta(e) & SDB_META_GLEN_MASK) - 1u, slot);
+      plan[RO + acc + k] = make_uint4(e.x, 0u, sdb_plan_z(e.y), slot);
       if (retire) rs[p & mask].y = SDB_META_TOMB;
     }
     acc += take; need -= take; got += take;
@@ -429,7 +429,7 @@ k_scan_plan(uint4* __restrict__ plan, uint32_t* __restrict__ tops, const unsigne
   if (blockIdx.x * SDB_SCAN_TILE >= n) { if (tid == 0) tops[blockIdx.x] = 0; return; }
   uint32_t x[4];
 #pragma unroll
-  for (int k = 0; k < 4; ++k) x[k] = (base + k < n) ? plan[base + k].z : 0u;
+  for (int k = 0; k < 4; ++k) x[k] = (base + k < n) ? (plan[base + k].z & 0xFFFFu) : 0u;
   const uint32_t tsum = x[0] + x[1] + x[2] + x[3];
   uint32_t incl = tsum;
 #pragma unroll
@@ -494,7 +494,7 @@ __device__ __forceinline__ void fill_offsets_warp(uint4* plan, uint32_t RO, uint
   uint32_t run = g0;
   for (uint32_t j0 = 0; j0 < C; j0 += 32) {
     const uint32_t j = j0 + lane;
-    const uint32_t g = j < C ? plan[RO + j].z : 0u;
+    const uint32_t g = j < C ? (plan[RO + j].z & 0xFFFFu) : 0u;
     uint32_t incl = g;
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) { const uint32_t y = __shfl_up_sync(0xFFFFFFFFu, incl, o); if (lane >= o) incl += y; }
@@ -626,7 +626,7 @@ k_recv_plan(sdb_dev_view v, sdb_recv_args r, uint32_t tiles, uint32_t ticketed) 
           const uint32_t g = (static_cast<uint32_t>(e >> 32) & SDB_META_GLEN_MASK) - 1u;
           const uint32_t li = lbase + j;
           if (li >= c0 && li < c0 + SDB_PLAN_STAGE) {
-            s_stage[warp][li - c0] = make_uint4(static_cast<uint32_t>(e), g0, g, q);
+            s_stage[warp][li - c0] = make_uint4(static_cast<uint32_t>(e), g0, g | (static_cast<uint32_t>(e >> 32) & 0xFFFF0000u), q);
             s_dst[warp][li - c0] = roff + j;
           }
           g0 += g;
@@ -664,17 +664,18 @@ k_recv_plan(sdb_dev_view v, sdb_recv_args r, uint32_t tiles, uint32_t ticketed) 
 // ------------------------------------------------------------------------------------------
 __device__ __forceinline__ void gather_record(const sdb_dev_view& v, const sdb_recv_args& r, uint32_t rec, uint32_t l8, uint64_t pol) {
   const uint4 pe = __ldg(r.plan + rec);                        // handle, payload offset, payload granules, slot
-  const uint32_t g = pe.z;
+  const uint32_t g = pe.z & 0xFFFFu;
   const uint64_t po = static_cast<uint64_t>(pe.y) + (r.plan_tops ? r.plan_tops[rec / SDB_SCAN_TILE] : 0u);
   const uint8_t* src = v.arena + ((static_cast<uint64_t>(pe.x) & v.gmask) << 5);
+  const uint8_t* psrc = sdb_payload_of(v, pe.x, sdb_entry_dm1(pe.z)) - 32;   // payload chunk c >= 2 comes from psrc + 16 c
   uint8_t* hdst = reinterpret_cast<uint8_t*>(r.hdr_out + rec);
   uint8_t* pdst = r.payload_out + (po << 5) - 32;          // chunk c >= 2 lands at pdst + 16 c
   const uint32_t nchunk = 2u + (g << 1);
   for (uint32_t c = l8; c < nchunk; c += 24) {
     const uint32_t c1 = c + 8, c2 = c + 16;
-    uint4 x0 = sdb_ld_stream_pol(src + (c << 4), pol), x1, x2;
-    if (c1 < nchunk) x1 = sdb_ld_stream_pol(src + (c1 << 4), pol);
-    if (c2 < nchunk) x2 = sdb_ld_stream_pol(src + (c2 << 4), pol);
+    uint4 x0 = sdb_ld_stream_pol((c < 2 ? src : psrc) + (c << 4), pol), x1, x2;
+    if (c1 < nchunk) x1 = sdb_ld_stream_pol(psrc + (c1 << 4), pol);
+    if (c2 < nchunk) x2 = sdb_ld_stream_pol(psrc + (c2 << 4), pol);
     sdb_st_stream_pol((c < 2 ? hdst : pdst) + (c << 4), x0, pol);
     if (c1 < nchunk) sdb_st_stream_pol(pdst + (c1 << 4), x1, pol);
     if (c2 < nchunk) sdb_st_stream_pol(pdst + (c2 << 4), x2, pol);
@@ -718,25 +719,36 @@ k_recv_gather_tma(sdb_dev_view v, sdb_recv_args r, const unsigned long long* __r
   __syncwarp();
   const uint32_t gw = blockIdx.x * WARPS + warp, nw = gridDim.x * WARPS;
   uint32_t phase = 0;                                        // bit s = parity of stage s
-  // per-lane state of the two stages
+  // per-lane state of the two stages.  The 32-byte header travels through registers (two 16-byte loads now, two stores
+  // one step later: the lanes' headers are consecutive in hdr_out, so a warp stores 1 KB contiguous); the payload - right
+  // behind the header, or shared by all recipients of a group send (sdb_common.cuh) - takes ONE bulk load and ONE
+  // bulk store.  Two bulk operations per record instead of three: the copy engine, not DRAM, was the limit once the
+  // payloads came out of the L2.
   uint32_t g0 = 0, g1 = 0, rc0 = 0, rc1 = 0; uint64_t po0 = 0, po1 = 0; bool hv0 = false, hv1 = false;
+  uint4 ha0 = make_uint4(0, 0, 0, 0), hb0 = ha0, ha1 = ha0, hb1 = ha0;
+  uint4 pe_ahead = make_uint4(0, 0, 0, 0);                   // plan entry of the step after the one being requested
   auto issue = [&](uint32_t st, uint32_t r0) {               // all lanes: request step r0 into stage st
     const uint32_t rec = r0 + lane;
     const bool have = rec < total;
     uint32_t bytes = 0; uint4 pe = make_uint4(0, 0, 0, 0);
-    if (have) { pe = __ldg(r.plan + rec); bytes = 32u + (pe.z << 5); }
+    if (have) { pe = pe_ahead; bytes = (pe.z & 0xFFFFu) << 5; }
+    { const uint32_t ra = rec + nw * 32u; if (ra < total) pe_ahead = __ldg(r.plan + ra); }   // consumed one step later
     uint32_t sum = bytes;
     for (int o = 16; o; o >>= 1) sum += __shfl_xor_sync(0xFFFFFFFFu, sum, o);
     if (lane == 0) sdb_mbar_expect_tx(&s_bar[warp][st], sum);
     __syncwarp();
+    uint4 ha = make_uint4(0, 0, 0, 0), hb = ha;
     if (have) {
       const uint8_t* src = v.arena + ((static_cast<uint64_t>(pe.x) & v.gmask) << 5);
-      sdb_tma_load(wbase + (static_cast<size_t>(st) * 32u + lane) * slot_bytes, src, bytes, &s_bar[warp][st]);
+      ha = sdb_ld_stream(src); hb = sdb_ld_stream(src + 16);
+      if (bytes) sdb_tma_load(wbase + (static_cast<size_t>(st) * 32u + lane) * slot_bytes, sdb_payload_of(v, pe.x, sdb_entry_dm1(pe.z)), bytes, &s_bar[warp][st]);
     }
     const uint64_t po = static_cast<uint64_t>(pe.y) + ((have && r.plan_tops) ? r.plan_tops[rec / SDB_SCAN_TILE] : 0u);
-    if (st) { g1 = pe.z; rc1 = rec; hv1 = have; po1 = po; } else { g0 = pe.z; rc0 = rec; hv0 = have; po0 = po; }
+    if (st) { g1 = pe.z & 0xFFFFu; rc1 = rec; hv1 = have; po1 = po; ha1 = ha; hb1 = hb; }
+    else { g0 = pe.z & 0xFFFFu; rc0 = rec; hv0 = have; po0 = po; ha0 = ha; hb0 = hb; }
   };
   uint32_t r0 = gw * 32u;
+  if (r0 + lane < total) pe_ahead = __ldg(r.plan + r0 + lane);
   if (r0 < total) issue(0, r0);
   uint32_t st = 0;
   for (; r0 < total; r0 += nw * 32u, st ^= 1u) {
@@ -745,13 +757,22 @@ k_recv_gather_tma(sdb_dev_view v, sdb_recv_args r, const unsigned long long* __r
     sdb_tma_wait_read<0>();
     __syncwarp();
     if (rn < total) issue(st ^ 1u, rn);
+    if (st ? hv1 : hv0) {
+      uint4* hdst = reinterpret_cast<uint4*>(r.hdr_out + (st ? rc1 : rc0));
+      sdb_st_stream(hdst, st ? ha1 : ha0); sdb_st_stream(hdst + 1, st ? hb1 : hb0);
+    }
     sdb_mbar_wait_bounded(&s_bar[warp][st], (phase >> st) & 1u);
     phase ^= 1u << st;
-    if (st ? hv1 : hv0) {
-      const uint8_t* slot = wbase + (static_cast<size_t>(st) * 32u + lane) * slot_bytes;
+    {
+      const bool hv = st ? hv1 : hv0;
       const uint32_t g = st ? g1 : g0;
-      sdb_tma_store(r.hdr_out + (st ? rc1 : rc0), slot, 32u);
-      if (g) sdb_tma_store(r.payload_out + ((st ? po1 : po0) << 5), slot + 32, g << 5);
+      // payload offsets are cumulative in record order: when all 32 payloads fill their slots exactly, the warp's output
+      // is ONE contiguous run and the slots are contiguous too - one bulk store instead of 32
+      if (__all_sync(0xFFFFFFFFu, hv && (g << 5) == slot_bytes)) {
+        if (lane == 0) sdb_tma_store(r.payload_out + ((st ? po1 : po0) << 5), wbase + static_cast<size_t>(st) * 32u * slot_bytes, 32u * slot_bytes);
+      } else if (hv && g) {
+        sdb_tma_store(r.payload_out + ((st ? po1 : po0) << 5), wbase + (static_cast<size_t>(st) * 32u + lane) * slot_bytes, g << 5);
+      }
     }
     sdb_tma_commit();
   }
@@ -862,7 +883,7 @@ k_recv_small(sdb_dev_view v, sdb_small_agents ag, uint32_t n, uint32_t max_messa
     uint32_t run = 0;
     for (uint32_t r0 = 0; r0 < total; r0 += 32) {
       const uint32_t r = r0 + lane;
-      const uint32_t g = r < total ? plan[r].z + 1u : 0u;
+      const uint32_t g = r < total ? (plan[r].z & 0xFFFFu) + 1u : 0u;
       uint32_t incl = g;
 #pragma unroll
       for (int o = 1; o < 32; o <<= 1) { const uint32_t y = __shfl_up_sync(0xFFFFFFFFu, incl, o); if (lane >= o) incl += y; }
@@ -880,11 +901,12 @@ k_recv_small(sdb_dev_view v, sdb_small_agents ag, uint32_t n, uint32_t max_messa
   const uint32_t l8 = tid & 7;
   for (uint32_t r = tid >> 3; r < total; r += 32) {
     const uint4 pe = plan[r];
-    const uint32_t g = pe.z;
+    const uint32_t g = pe.z & 0xFFFFu;
     const uint8_t* src = v.arena + ((static_cast<uint64_t>(pe.x) & v.gmask) << 5);
+    const uint8_t* psrc = sdb_payload_of(v, pe.x, sdb_entry_dm1(pe.z)) - 32;
     uint8_t* dst = out + 64 + (static_cast<size_t>(s_goff[r]) << 5);
     const uint32_t nchunk = 2u + (g << 1);
-    for (uint32_t c = l8; c < nchunk; c += 8) sdb_st_stream(dst + (c << 4), sdb_ld_stream(src + (c << 4)));
+    for (uint32_t c = l8; c < nchunk; c += 8) sdb_st_stream(dst + (c << 4), sdb_ld_stream((c < 2 ? src : psrc) + (c << 4)));
   }
 }
 
@@ -941,7 +963,7 @@ k_latency_server(sdb_dev_view v, sdb_ls_mailbox* mb, uint8_t* out, uint32_t out_
         uint32_t incl = g;
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) { const uint32_t y = __shfl_up_sync(0xFFFFFFFFu, incl, o); if (lane >= o) incl += y; }
-        if (lane < c) { s_goff[lane] = incl - g; s_fast[lane] = make_uint2(e.x, g - 1u); }
+        if (lane < c) { s_goff[lane] = incl - g; s_fast[lane] = make_uint2(e.x, (g - 1u) | (e.y & 0xFFFF0000u)); }
         if (lane == c - 1) s_goff[c] = incl;
         if (lane == 0) {
           s_total = c; s_cnt = 0xFFFFFFFFu;                                          // marker: plan lives in shared memory
@@ -964,7 +986,7 @@ k_latency_server(sdb_dev_view v, sdb_ls_mailbox* mb, uint8_t* out, uint32_t out_
       uint32_t run = 0;
       for (uint32_t r0 = 0; r0 < cnt; r0 += 32) {
         const uint32_t r = r0 + lane;
-        const uint32_t g = r < cnt ? plan[r].z + 1u : 0u;
+        const uint32_t g = r < cnt ? (plan[r].z & 0xFFFFu) + 1u : 0u;
         uint32_t incl = g;
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) { const uint32_t y = __shfl_up_sync(0xFFFFFFFFu, incl, o); if (lane >= o) incl += y; }
@@ -978,12 +1000,14 @@ k_latency_server(sdb_dev_view v, sdb_ls_mailbox* mb, uint8_t* out, uint32_t out_
     const uint32_t total = s_total;
     const uint32_t l8 = tid & 7;
     for (uint32_t r = tid >> 3; r < total; r += 32) {
-      uint32_t handle, g;
-      if (fastpath) { handle = s_fast[r].x; g = s_fast[r].y; } else { const uint4 pe = plan[r]; handle = pe.x; g = pe.z; }
+      uint32_t handle, gz;
+      if (fastpath) { handle = s_fast[r].x; gz = s_fast[r].y; } else { const uint4 pe = plan[r]; handle = pe.x; gz = pe.z; }
+      const uint32_t g = gz & 0xFFFFu;
       const uint8_t* src = v.arena + ((static_cast<uint64_t>(handle) & v.gmask) << 5);
+      const uint8_t* psrc = sdb_payload_of(v, handle, sdb_entry_dm1(gz)) - 32;
       uint8_t* dst = out + 64 + (static_cast<size_t>(s_goff[r]) << 5);
       const uint32_t nchunk = 2u + (g << 1);
-      for (uint32_t c = l8; c < nchunk; c += 8) *reinterpret_cast<uint4*>(dst + (c << 4)) = sdb_ld_stream(src + (c << 4));
+      for (uint32_t c = l8; c < nchunk; c += 8) *reinterpret_cast<uint4*>(dst + (c << 4)) = sdb_ld_stream((c < 2 ? src : psrc) + (c << 4));
     }
     if (tid == 0) {
       // totals | granules | count: one 32-byte store group at the head of the answer block
@@ -1033,7 +1057,8 @@ static cudaError_t launch_gather(const sdb_dev_view* v, const sdb_recv_args* r, 
   const int pi = sdb_prof_begin(prof, SDB_PK_RECV_GATHER, stream);
   if (use_tma && max_rec_bytes <= 544 && bound >= 4096) {
     constexpr int WARPS = 4;
-    const size_t smem = static_cast<size_t>(WARPS) * 2u * 32u * max_rec_bytes;
+    const uint32_t slot = max_rec_bytes > 64u ? max_rec_bytes - 32u : 32u;          // a slot stages the payload only
+    const size_t smem = static_cast<size_t>(WARPS) * 2u * 32u * slot;
     uint32_t per_sm = static_cast<uint32_t>((226u * 1024u) / (smem + 1024 + 128));
     if (per_sm < 1) per_sm = 1;
     if (per_sm > 8) per_sm = 8;
@@ -1042,7 +1067,7 @@ static cudaError_t launch_gather(const sdb_dev_view* v, const sdb_recv_args* r, 
     uint64_t grid = static_cast<uint64_t>(sm_count) * per_sm * waves;              // a few waves: the tail evens out
     const uint64_t need = (bound + WARPS * 32 - 1) / (WARPS * 32);
     if (grid > need) grid = need;
-    k_recv_gather_tma<WARPS><<<static_cast<uint32_t>(grid), WARPS * 32, smem, stream>>>(*v, *r, packed_inv, max_rec_bytes);
+    k_recv_gather_tma<WARPS><<<static_cast<uint32_t>(grid), WARPS * 32, smem, stream>>>(*v, *r, packed_inv, slot);
   } else {
     uint64_t gwarps = (bound + 3) / 4;
     uint64_t gblocks = (gwarps + 7) / 8;

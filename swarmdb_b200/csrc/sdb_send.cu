@@ -410,11 +410,15 @@ template <int WARPS>
 __global__ void __launch_bounds__(WARPS * 32, 8)
 k_group_fanout_span(sdb_dev_view v, const sdb_send_desc* __restrict__ descs, uint32_t n,
                     const uint8_t* __restrict__ payload, const uint32_t* __restrict__ tmp_list,
-                    uint64_t seq_base, uint64_t arena_base, uint32_t stage_bytes, const sdb_batch_base* __restrict__ bb) {
+                    uint64_t seq_base, uint64_t arena_base, uint32_t stage_bytes, const sdb_batch_base* __restrict__ bb,
+                    uint32_t skip_pull) {
+  // skip_pull: the group sends of this batch (SDB_DESC_PULL) are written by k_group_fanout_shared; only point-to-point
+  // and broadcast descriptors are served here - usually none (the import's totals say so: return at once)
   if (bb) {                                                  // asynchronous import: placement computed on the device
-    if (bb->skip) return;
+    if (bb->skip || (skip_pull && bb->n_other == 0)) return;
     n = bb->n_total; seq_base = bb->seq_base; arena_base = bb->arena_base;
   }
+  auto mcnt = [&](const sdb_send_desc& x) -> uint32_t { return (skip_pull && (x.flags & SDB_DESC_PULL)) ? 0u : x.mcount; };
   constexpr uint32_t PAY = SDB_SPAN_PAY, DESC = SDB_SPAN_DESC, GROUP = SDB_SPAN_GROUP, NONE = 0xFFFFFFFFu;
   static_assert(DESC == 4 * GROUP && PAY == 2 * GROUP, "refill schedule below assumes these distances");
   extern __shared__ __align__(128) uint8_t s_dyn[];          // per warp: descriptors | header table | record table | payload stages
@@ -447,7 +451,7 @@ k_group_fanout_span(sdb_dev_view v, const sdb_send_desc* __restrict__ descs, uin
   auto want_payload = [&](uint32_t t) {                      // one lane: descriptor t is in shared memory
     const sdb_send_desc& x = s_desc[t & (DESC - 1)];
     const uint32_t pl = (x.rgran - 1u) * SDB_GRANULE;
-    if (x.mcount && pl) {
+    if (mcnt(x) && pl) {
       uint64_t* bar = &s_pbar[warp][t & (PAY - 1)];
       sdb_mbar_expect_tx(bar, pl);
       sdb_tma_load(s_pay + (t & (PAY - 1)) * static_cast<size_t>(stage_bytes), payload + x.payload_off, pl, bar);
@@ -463,13 +467,13 @@ k_group_fanout_span(sdb_dev_view v, const sdb_send_desc* __restrict__ descs, uin
     if ((t & (GROUP - 1)) == 0 && joff == 0)                  // first tile of a refill group: its descriptors were requested >= 8 sends ago
       for (uint32_t u = t; u < gend; ++u) wait_desc(u);
     uint32_t tt = t;
-    const uint32_t rem = s_desc[tt & (DESC - 1)].mcount - joff;
+    const uint32_t rem = mcnt(s_desc[tt & (DESC - 1)]) - joff;
     if (rem > 32u) { ts = tt; j = joff + lane; nrec = 32u; t_next = tt; joff_next = joff + 32u; }
     else {
       if (lane < rem) { ts = tt; j = joff + lane; }
       nrec = rem; ++tt;
       while (tt < gend) {                                    // whole following sends of the group while they fit
-        const uint32_t m = s_desc[tt & (DESC - 1)].mcount;
+        const uint32_t m = mcnt(s_desc[tt & (DESC - 1)]);
         if (nrec + m > 32u) break;
         if (lane >= nrec && lane < nrec + m) { ts = tt; j = lane - nrec; }
         nrec += m; ++tt;
@@ -501,7 +505,7 @@ k_group_fanout_span(sdb_dev_view v, const sdb_send_desc* __restrict__ descs, uin
     for (uint32_t u = t_first + (joff_first ? 1u : 0u); u <= t_last && u < mine; ++u) {
       const sdb_send_desc& x = s_desc[u & (DESC - 1)];
       const uint32_t padlen = (x.rgran - 1u) * SDB_GRANULE;
-      if (x.mcount && padlen) {
+      if (mcnt(x) && padlen) {
         sdb_mbar_wait_bounded(&s_pbar[warp][u & (PAY - 1)], (pay_phase >> (u & (PAY - 1))) & 1u);
         pay_phase ^= 1u << (u & (PAY - 1));
         const uint32_t b = x.len + lane;
@@ -596,6 +600,125 @@ k_group_fanout_span(sdb_dev_view v, const sdb_send_desc* __restrict__ descs, uin
     if (n_ovf) atomicAdd(&v.ctr->ring_overflow, n_ovf);
     if (n_skip) atomicAdd(&v.ctr->skipped_sender, n_skip);
   }
+}
+
+// ------------------------------------------------------------------------------------------
+// K2, shared-payload form (group sends above the pull threshold, payloads up to 512 bytes).
+// The reference gives every recipient of a group message its own copy (M:1267-1277); the copies differ in 12 header
+// bytes.  Here a send writes its members' 32-byte headers back to back and the padded payload ONCE behind them
+// (sdb_common.cuh "shared payloads"); the index build points every member's ring entry at its header and records the
+// distance to the payload, and the receive gather reads header + payload from the two places.  For the c2 shape
+// (64 recipients, 256-byte payloads) a send writes 2.3 KB instead of 18.4 KB.
+// LPS lanes per send (32: wide sends; 8: a shard's narrow share of a group at N = 8).  No shared memory; three
+// sends of a sub-warp are in flight: descriptor loads two ahead, member ids + payload chunks one ahead, stores now.
+// ------------------------------------------------------------------------------------------
+template <int LPS>
+__global__ void __launch_bounds__(256)
+k_group_fanout_shared(sdb_dev_view v, const sdb_send_desc* __restrict__ descs, uint32_t n,
+                      const uint8_t* __restrict__ payload, uint64_t seq_base, uint64_t arena_base,
+                      const sdb_batch_base* __restrict__ bb) {
+  if (bb) {
+    if (bb->skip) return;
+    n = bb->n_total; seq_base = bb->seq_base; arena_base = bb->arena_base;
+  }
+  constexpr int NCH = 32 / LPS;                                  // 16-byte payload chunks per lane (512 bytes at most)
+  const uint32_t lane = threadIdx.x & 31, sl = lane & (LPS - 1);
+  const uint32_t gsw = (blockIdx.x * blockDim.x + threadIdx.x) / LPS, nsw = (gridDim.x * blockDim.x) / LPS;
+  const uint64_t pol = sdb_policy_evict_first();
+  uint32_t n_skip = 0;
+  struct Desc { uint4 q0, q1, q2, q3; };
+  struct Work { uint32_t a0, a1, p0, p1; uint4 pc[NCH]; };
+  auto load_desc = [&](uint32_t i) {
+    Desc d; d.q0 = d.q1 = d.q2 = d.q3 = make_uint4(0, 0, 0, 0);
+    if (i < n) {
+      const uint4* dq = reinterpret_cast<const uint4*>(descs + i);
+      d.q0 = __ldg(dq); d.q1 = __ldg(dq + 1); d.q2 = __ldg(dq + 2); d.q3 = __ldg(dq + 3);
+    }
+    return d;
+  };
+  auto fetch = [&](const Desc& d, uint32_t i) {                  // member ids of the first two tiles + this lane's payload chunks
+    Work w; w.a0 = w.a1 = 0xFFFFFFFFu; w.p0 = sl; w.p1 = sl + LPS;
+#pragma unroll
+    for (int c = 0; c < NCH; ++c) w.pc[c] = make_uint4(0, 0, 0, 0);
+    if (i >= n) return w;
+    const uint32_t mstart = d.q2.y, mcount = d.q2.z, flags = d.q3.x;
+    if (!(flags & SDB_DESC_PULL) || mcount == 0) return w;
+    if (sl < mcount) w.a0 = __ldg(v.members + mstart + sl);
+    if (sl + LPS < mcount) w.a1 = __ldg(v.members + mstart + sl + LPS);
+    if (flags & SDB_DESC_POS) {
+      if (sl < mcount) w.p0 = __ldg(v.member_pos + mstart + sl);
+      if (sl + LPS < mcount) w.p1 = __ldg(v.member_pos + mstart + sl + LPS);
+    }
+    const uint32_t padlen = (d.q1.z - 1u) * SDB_GRANULE, len = d.q1.w & 0xFFFFu;
+    const uint8_t* src = payload + ((static_cast<uint64_t>(d.q0.y) << 32) | d.q0.x);
+#pragma unroll
+    for (int c = 0; c < NCH; ++c) {
+      const uint32_t b0 = (static_cast<uint32_t>(c) * LPS + sl) << 4;
+      if (b0 < padlen) {
+        uint4 x = sdb_ld_stream(src + b0);                       // (may be a peer GPU's export buffer: NVLink)
+        if (b0 + 16u > len) {                                    // deterministic pad bytes
+          uint8_t* xb = reinterpret_cast<uint8_t*>(&x);
+#pragma unroll
+          for (int k = 0; k < 16; ++k) if (b0 + k >= len) xb[k] = 0;
+        }
+        w.pc[c] = x;
+      }
+    }
+    return w;
+  };
+  uint32_t i = gsw;
+  Desc d = load_desc(i);
+  Work w = fetch(d, i);
+  Desc dn = load_desc(i + nsw);
+  for (; i < n; i += nsw) {
+    const Work wn = fetch(dn, i + nsw);                          // next send's loads are in flight while this one is written
+    const Desc dnn = load_desc(i + 2u * nsw);
+    const uint32_t mstart = d.q2.y, mcount = d.q2.z, flags = d.q3.x;
+    if ((flags & SDB_DESC_PULL) && mcount) {
+      const uint32_t sender = d.q1.y, rgran = d.q1.z, lpt = d.q1.w;
+      const bool shared_seq = (flags & SDB_DESC_SHARED_SEQ) != 0, skip_sender = (flags & SDB_DESC_SKIP_SENDER) != 0;
+      const uint64_t seq0 = (flags & SDB_DESC_ABS_SEQ) ? ((static_cast<uint64_t>(d.q3.w) << 32) | d.q3.z) : seq_base + d.q2.x;
+      const double ts = __longlong_as_double((static_cast<long long>(d.q0.w) << 32) | d.q0.z);
+      uint8_t* const base = sdb_arena_ptr(v, arena_base + d.q1.x);                // the batch region never wraps
+      const uint4 hdr_hi = make_uint4(sender, SDB_NO_RECEIVER, d.q2.w, lpt);
+      for (uint32_t tile = 0; tile < mcount; tile += 2u * LPS) {
+        uint32_t a0, a1, p0, p1;
+        const uint32_t j0 = tile + sl, j1 = j0 + LPS;
+        if (tile == 0) { a0 = w.a0; a1 = w.a1; p0 = w.p0; p1 = w.p1; }
+        else {
+          a0 = j0 < mcount ? __ldg(v.members + mstart + j0) : 0xFFFFFFFFu;
+          a1 = j1 < mcount ? __ldg(v.members + mstart + j1) : 0xFFFFFFFFu;
+          p0 = (flags & SDB_DESC_POS) ? (j0 < mcount ? __ldg(v.member_pos + mstart + j0) : 0u) : j0;
+          p1 = (flags & SDB_DESC_POS) ? (j1 < mcount ? __ldg(v.member_pos + mstart + j1) : 0u) : j1;
+        }
+        const bool s0 = j0 < mcount && skip_sender && a0 == sender, s1 = j1 < mcount && skip_sender && a1 == sender;
+        n_skip += s0 + s1;
+        if (j0 < mcount && !s0 && a0 < v.max_agents) {
+          uint4 hi = hdr_hi; if (!shared_seq) hi.y = a0;
+          uint4* dst = reinterpret_cast<uint4*>(base + (static_cast<size_t>(j0) << 5));
+          sdb_st_stream_pol(dst, sdb_header_lo(seq0 + (shared_seq ? 0u : p0), ts), pol);
+          sdb_st_stream_pol(dst + 1, hi, pol);
+        }
+        if (j1 < mcount && !s1 && a1 < v.max_agents) {
+          uint4 hi = hdr_hi; if (!shared_seq) hi.y = a1;
+          uint4* dst = reinterpret_cast<uint4*>(base + (static_cast<size_t>(j1) << 5));
+          sdb_st_stream_pol(dst, sdb_header_lo(seq0 + (shared_seq ? 0u : p1), ts), pol);
+          sdb_st_stream_pol(dst + 1, hi, pol);
+        }
+      }
+      // the one payload of the send, behind its mcount headers
+      uint8_t* const pdst = base + (static_cast<size_t>(mcount) << 5);
+      const uint32_t padlen = (rgran - 1u) * SDB_GRANULE;
+#pragma unroll
+      for (int c = 0; c < NCH; ++c) {
+        const uint32_t b0 = (static_cast<uint32_t>(c) * LPS + sl) << 4;
+        if (b0 < padlen) sdb_st_stream_pol(reinterpret_cast<uint4*>(pdst + b0), w.pc[c], pol);
+      }
+    }
+    d = dn; dn = dnn; w = wn;
+  }
+  for (int o = 16; o; o >>= 1) n_skip += __shfl_xor_sync(0xFFFFFFFFu, n_skip, o);
+  if (lane == 0 && n_skip) atomicAdd(&v.ctr->skipped_sender, n_skip);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -814,7 +937,7 @@ k_commit_ranked(sdb_dev_view v, const sdb_send_desc* __restrict__ descs, uint32_
 __global__ void __launch_bounds__(128)
 k_pull_index_group(sdb_dev_view v, sdb_pull_view pv, const sdb_send_desc* __restrict__ descs, uint32_t n_groups,
                    const uint8_t* __restrict__ gexcl, const uint32_t* __restrict__ lstart, const uint32_t* __restrict__ lcount,
-                   uint64_t arena_base, uint32_t set_ctail, const sdb_batch_base* __restrict__ bb) {
+                   uint64_t arena_base, uint32_t set_ctail, const sdb_batch_base* __restrict__ bb, uint32_t shared) {
   // Dependent-load depth 3: {bucket bounds of every source, member table} -> {send indices, member ids} ->
   // {descriptors, ring headers} (the kernel is latency-bound: every level is issued for the whole warp - 2 members
   // per lane - at once).  The group's bucket is the concatenation of the sources' buckets in source order.
@@ -895,12 +1018,14 @@ k_pull_index_group(sdb_dev_view v, sdb_pull_view pv, const sdb_send_desc* __rest
               const uint32_t qbits = (bal >> qb) & 0xFu;
               const uint32_t pos = tm + __popc(qbits & ((1u << sub) - 1u));
               if (keep) {
-                if (pos - hm >= R) { ++n_ovf; sdb_note_overflow(v, am, static_cast<uint32_t>(arena_base + gran0 + static_cast<uint64_t>(m0 + mi) * rgran)); }
+                // record slot jm of the send's region: a whole record, or (shared payloads) its header, the one payload
+                // sitting behind the region's mcount headers
+                const uint32_t jm = m0 + mi;
+                const uint32_t handle = static_cast<uint32_t>(arena_base + gran0 + (shared ? static_cast<uint64_t>(jm) : static_cast<uint64_t>(jm) * rgran));
+                if (pos - hm >= R) { ++n_ovf; sdb_note_overflow(v, am, handle); }
                 else {
-                  const uint32_t jm = m0 + mi;
-                  const uint64_t meta_hi = static_cast<uint64_t>((((lpt >> 16) & 0xFFu) << 14) | rgran) << 32;
-                  sdb_st_u64_pol(reinterpret_cast<uint64_t*>(sdb_ring_of(v, am) + (pos & mask)),
-                                 meta_hi | static_cast<uint32_t>(arena_base + gran0 + static_cast<uint64_t>(jm) * rgran), pol);
+                  const uint64_t meta_hi = static_cast<uint64_t>((((lpt >> 16) & 0xFFu) << 14) | rgran | (shared ? (mcount - 1u - jm) << 16 : 0u)) << 32;
+                  sdb_st_u64_pol(reinterpret_cast<uint64_t*>(sdb_ring_of(v, am) + (pos & mask)), meta_hi | handle, pol);
                   ++n_enq;
                 }
               }
@@ -1181,7 +1306,7 @@ k_commit_big(sdb_dev_view v, uint32_t batch_base32, const uint32_t* __restrict__
              const uint32_t* __restrict__ big_count, const sdb_batch_base* __restrict__ bb) {
   if (bb) batch_base32 = static_cast<uint32_t>(bb->arena_base);
   __shared__ uint32_t s_key[SDB_COMMIT_SMEM];
-  __shared__ uint16_t s_meta[SDB_COMMIT_SMEM];
+  __shared__ uint32_t s_meta[SDB_COMMIT_SMEM];                 // whole .y: meta word and the distance to a shared payload
   const uint32_t n_big = *big_count;
   const uint32_t R = v.ring_slots, mask = R - 1;
   for (uint32_t w = blockIdx.x; w < n_big; w += gridDim.x) {
@@ -1195,7 +1320,7 @@ k_commit_big(sdb_dev_view v, uint32_t batch_base32, const uint32_t* __restrict__
       for (uint32_t i = threadIdx.x; i < N; i += blockDim.x) {
         const uint2 e = i < cnt ? rs[(ct + i) & mask] : make_uint2(0u, 0u);
         s_key[i] = i < cnt ? e.x - batch_base32 : 0xFFFFFFFFu;
-        s_meta[i] = static_cast<uint16_t>(e.y);
+        s_meta[i] = e.y;
       }
       __syncthreads();
       for (uint32_t k = 2; k <= N; k <<= 1)
@@ -1205,7 +1330,7 @@ k_commit_big(sdb_dev_view v, uint32_t batch_base32, const uint32_t* __restrict__
             if (l > i) {
               const bool up = (i & k) == 0;
               const uint32_t ki = s_key[i], kl = s_key[l];
-              if ((ki > kl) == up) { s_key[i] = kl; s_key[l] = ki; const uint16_t t = s_meta[i]; s_meta[i] = s_meta[l]; s_meta[l] = t; }
+              if ((ki > kl) == up) { s_key[i] = kl; s_key[l] = ki; const uint32_t t = s_meta[i]; s_meta[i] = s_meta[l]; s_meta[l] = t; }
             }
           }
           __syncthreads();
@@ -1297,8 +1422,8 @@ extern "C" cudaError_t sdb_launch_fanout(const sdb_dev_view* v, const sdb_send_d
                                          const uint8_t* payload, const uint32_t* tmp_list,
                                          uint64_t seq_base, uint64_t arena_base, uint32_t max_padlen,
                                          int variant, int sm_count, cudaStream_t stream, sdb_profiler* prof,
-                                         const sdb_batch_base* bb) {
-  if (bb && !(variant == 3 && max_padlen <= 512)) return cudaErrorInvalidValue;
+                                         const sdb_batch_base* bb, uint32_t skip_pull) {
+  if ((bb || skip_pull) && !(variant == 3 && max_padlen <= 512)) return cudaErrorInvalidValue;
   if (n == 0) return cudaSuccess;
   const int pi = sdb_prof_begin(prof, SDB_PK_FANOUT, stream);
   if (variant == 3 && max_padlen <= 512) {
@@ -1312,7 +1437,7 @@ extern "C" cudaError_t sdb_launch_fanout(const sdb_dev_view* v, const sdb_send_d
     uint32_t grid = static_cast<uint32_t>(sm_count) * per_sm * static_cast<uint32_t>(mult);
     const uint32_t need = (n + WARPS - 1) / WARPS;
     if (grid > need) grid = need;
-    k_group_fanout_span<WARPS><<<grid, WARPS * 32, smem, stream>>>(*v, descs, n, payload, tmp_list, seq_base, arena_base, stage, bb);
+    k_group_fanout_span<WARPS><<<grid, WARPS * 32, smem, stream>>>(*v, descs, n, payload, tmp_list, seq_base, arena_base, stage, bb, skip_pull);
   } else if ((variant == 2 || variant == 3) && max_padlen <= 4096) {
     constexpr int WARPS = 4;
     const uint32_t stage = ((max_padlen ? max_padlen : 16) + 127u) & ~127u;
@@ -1343,19 +1468,35 @@ extern "C" cudaError_t sdb_launch_fanout(const sdb_dev_view* v, const sdb_send_d
   return cudaGetLastError();
 }
 
+// shared-payload fan-out (see k_group_fanout_shared): every descriptor of the batch that carries SDB_DESC_PULL
+extern "C" cudaError_t sdb_launch_fanout_shared(const sdb_dev_view* v, const sdb_send_desc* descs, uint32_t n, const uint8_t* payload,
+                                                uint64_t seq_base, uint64_t arena_base, uint32_t narrow, int sm_count,
+                                                cudaStream_t stream, sdb_profiler* prof, const sdb_batch_base* bb) {
+  if (n == 0) return cudaSuccess;
+  const int pi = sdb_prof_begin(prof, SDB_PK_FANOUT, stream);
+  const uint32_t lps = narrow ? 8u : 32u;
+  uint64_t grid = (static_cast<uint64_t>(n) * lps + 255) / 256;
+  const uint64_t cap = static_cast<uint64_t>(sm_count) * 8u * 4u;
+  if (grid > cap) grid = cap;
+  if (narrow) k_group_fanout_shared<8><<<static_cast<uint32_t>(grid), 256, 0, stream>>>(*v, descs, n, payload, seq_base, arena_base, bb);
+  else k_group_fanout_shared<32><<<static_cast<uint32_t>(grid), 256, 0, stream>>>(*v, descs, n, payload, seq_base, arena_base, bb);
+  sdb_prof_end(prof, pi, stream);
+  return cudaGetLastError();
+}
+
 // gexcl: per-group "exclusive" flags; n_groups: groups covered by the bucket table; n_shared: how many agents sit in
 // non-exclusive groups or in several groups (0: the agent-parallel kernel is not needed at all)
 extern "C" cudaError_t sdb_launch_pull(const sdb_dev_view* v, const sdb_pull_view* pv, const sdb_send_desc* descs,
                                        uint32_t n_agents, uint32_t n_groups, const uint8_t* gexcl, uint32_t n_excl_groups,
                                        uint32_t n_shared, const uint32_t* lstart, const uint32_t* lcount,
                                        uint64_t arena_base, int set_ctail, cudaStream_t stream,
-                                       sdb_profiler* prof, int* n_launches, const sdb_batch_base* bb) {
-  if (bb && (n_shared || !n_excl_groups)) return cudaErrorInvalidValue;      // device-side placement: group-parallel build only
+                                       sdb_profiler* prof, int* n_launches, const sdb_batch_base* bb, uint32_t shared_payload) {
+  if ((bb || shared_payload) && (n_shared || !n_excl_groups)) return cudaErrorInvalidValue;      // group-parallel build only
   if (n_agents == 0) return cudaSuccess;
   const int pi = sdb_prof_begin(prof, SDB_PK_INDEX, stream);
   if (n_excl_groups && n_groups) {
     const uint64_t threads = static_cast<uint64_t>(n_groups) * 32;
-    k_pull_index_group<<<static_cast<uint32_t>((threads + 127) / 128), 128, 0, stream>>>(*v, *pv, descs, n_groups, gexcl, lstart, lcount, arena_base, set_ctail ? 1u : 0u, bb);
+    k_pull_index_group<<<static_cast<uint32_t>((threads + 127) / 128), 128, 0, stream>>>(*v, *pv, descs, n_groups, gexcl, lstart, lcount, arena_base, set_ctail ? 1u : 0u, bb, shared_payload);
     if (n_launches) *n_launches += 1;
   }
   if (n_shared || !n_excl_groups) {

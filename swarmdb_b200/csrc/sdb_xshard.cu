@@ -400,7 +400,11 @@ k_import_fused(sdb_import2_args a, uint32_t tiles_cap) {
       lc = d.group < a.max_groups ? a.lcount[d.group] : 0u;
     }
   }
-  const unsigned long long wa = have ? static_cast<unsigned long long>(lc) * d.rgran : 0ull;     // arena granules written here
+  // arena granules written here: lc whole records, or (shared payloads, group sends) lc headers + one payload
+  const bool group_send = have && !(d.flags & (SDB_DESC_P2P | SDB_DESC_LIST_TEMP));
+  const unsigned long long wa = !have ? 0ull
+      : (a.shared && group_send) ? (lc ? static_cast<unsigned long long>(lc) + d.rgran - 1u : 0ull)
+      : static_cast<unsigned long long>(lc) * d.rgran;
   const unsigned long long wb = own;                                                            // temporary-list entries
 
   // ---- tile scan + decoupled look-back of the pair

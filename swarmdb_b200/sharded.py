@@ -428,10 +428,13 @@ def run_sharded_bench(args, rank: int, world: int, local_rank: int, wl):
             parity["match"] = False
             parity["note"] = "a shard delivered to agents it does not own, or sequence bases diverged across ranks"
         peak, peak_src = hbm_peak()
-        fan_ms, fan_n = prof["fanout"]
-        fan_avg = fan_ms / max(fan_n, 1)
+        from bench import ALG_BYTES_GATHER, ALG_OWN_GATHER
+        from ._native import shared_payload_enabled
+        gat_ms, gat_n = prof.get("recv_gather", (0.0, 0))
+        gat_avg = gat_ms / max(gat_n, 1)
         local_msgs = delivered / K
-        achieved = ALG_BYTES_FANOUT * local_msgs / (fan_avg * 1e-3) / 1e9 if fan_n else 0.0
+        achieved = ALG_BYTES_GATHER * local_msgs / (gat_avg * 1e-3) / 1e9 if gat_n else 0.0
+        step_alg = (ALG_BYTES_FANOUT + 1 + ALG_BYTES_GATHER) * local_msgs
         line = {
             "metric": "messages/sec routed (send->receive) at 1M agents, 64-way fanout",
             "value": total_delivered / (ms_max * 1e-3), "unit": "messages/s", "n_gpus": world, "steps": K, "warmup": W,
@@ -459,10 +462,15 @@ def run_sharded_bench(args, rank: int, world: int, local_rank: int, wl):
                     "d2h_bytes_per_step": int(total_got / Ke * (32 + wl.L)) + wl.A * 4, "steps": Ke,
                     "ms_per_step": e2e_max / Ke},
             "gpu_launches": int(float(sm[4])),
-            "roofline": {"kernel": "k_group_fanout", "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                         "frac": achieved / peak, "traffic": traffic_note("k_group_fanout_bytes_per_launch"), "peak_source": peak_src,
-                         "algorithmic_bytes_per_msg": ALG_BYTES_FANOUT, "msgs_per_launch": local_msgs,
-                         "ms_per_launch": fan_avg, "note": "rank 0's shard; per-send local fan-out is world-times narrower"},
+            "roofline": {"kernel": "k_recv_gather_tma (dominant: %.0f %% of rank 0's step)" % (100 * gat_avg / (ms_max / K)),
+                         "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                         "frac": achieved / peak, "traffic": traffic_note("k_recv_gather_bytes_per_launch"), "peak_source": peak_src,
+                         "algorithmic_bytes_per_msg": ALG_BYTES_GATHER, "msgs_per_launch": local_msgs,
+                         "ms_per_launch": gat_avg, "step_frac": step_alg / ((ms_max / K) * 1e-3) / 1e9 / peak,
+                         "note": "rank 0's shard (the traffic figure is the N=1 capture); SURVEY 8(d) bytes per message, see the N=1 "
+                                 "line's roofline.own_layout for the shared-payload accounting",
+                         "own_layout_gather_frac": (ALG_OWN_GATHER * local_msgs / (gat_avg * 1e-3) / 1e9 / peak
+                                                    if (gat_n and shared_payload_enabled()) else None)},
             "kernels": {k: {"ms_per_launch": v[0] / v[1], "launches": v[1]} for k, v in prof.items() if v[1]},
             "phases_ms_rank0": phases,
             "parity": parity,

@@ -569,7 +569,9 @@ def test_async_import_that_does_not_fit_is_dropped_whole_and_reported():
     A, G, F, S = 1024, 16, 64, 200
     perm = rng.permutation(A)
     groups = [perm[g * F:(g + 1) * F] for g in range(G)]
-    smap, shards, wb, bufs = _async_cluster(1, A, G, S, groups, arena_bytes=1 << 22)      # 4 MiB arena: ~1.1 imports of this size
+    from swarmdb_b200._native import shared_payload_enabled
+    # ~1.1 imports of this size: 200 sends x 64 recipients x 288 B = 3.7 MB, or x (64 headers + one payload) = 0.46 MB
+    smap, shards, wb, bufs = _async_cluster(1, A, G, S, groups, arena_bytes=1 << (19 if shared_payload_enabled() else 22))
     s = shards[0]
 
     def export(step):
