@@ -779,6 +779,81 @@ k_recv_gather_tma(sdb_dev_view v, sdb_recv_args r, const unsigned long long* __r
   sdb_tma_wait_all<0>();
 }
 
+// The same gather with the payloads brought in by the whole warp with 16-byte asynchronous copies (cp.async, LDGSTS)
+// instead of one bulk load per lane.  A per-lane bulk copy costs the warp ~12 issue slots (the copy engine takes its
+// operands from uniform registers, so the 32 lanes issue one after the other); with the payloads coming out of the L2
+// that issue loop - not memory - looked like the limit (ncu: 17 % issue active, long_scoreboard 11).  MEASURED: it is not -
+// this form runs the c2 gather in 0.382 ms against 0.357 ms for the bulk-load form (SDB_GATHER_LDGSTS=1 selects it; both
+// pass the whole parity suite); the gather moves 1.6 GB of physical DRAM traffic at 4.5 TB/s either way.  Here one warp instruction
+// moves 512 bytes: lane l copies chunk (flat % cpr) of record (flat / cpr), flat = 32 f + l, the records' source
+// addresses travelling by shuffle.  Completion by cp.async groups (one per step, also when the step is empty), then a
+// proxy fence, then ONE bulk store of the warp's 32 slots when they are all full (else one per lane).
+template <int WARPS>
+__global__ void __launch_bounds__(WARPS * 32)
+k_recv_gather_cpa(sdb_dev_view v, sdb_recv_args r, const unsigned long long* __restrict__ packed_inv, uint32_t slot_bytes) {
+  extern __shared__ __align__(128) uint8_t s_dyn[];          // [WARPS][2][32][slot_bytes]
+  const uint32_t total = gather_total(r, packed_inv);
+  const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  uint8_t* const wbase = s_dyn + static_cast<size_t>(warp) * 2u * 32u * slot_bytes;
+  const uint32_t wbase_sa = sdb_smem_u32(wbase);
+  const uint32_t gw = blockIdx.x * WARPS + warp, nw = gridDim.x * WARPS;
+  const uint32_t cpr = slot_bytes >> 4;                      // 16-byte chunks per slot
+  uint32_t g0 = 0, g1 = 0, rc0 = 0, rc1 = 0; uint64_t po0 = 0, po1 = 0; bool hv0 = false, hv1 = false;
+  uint4 ha0 = make_uint4(0, 0, 0, 0), hb0 = ha0, ha1 = ha0, hb1 = ha0;
+  auto issue = [&](uint32_t st, uint32_t r0) {               // all lanes: request step r0 into stage st
+    const uint32_t rec = r0 + lane;
+    const bool have = rec < total;
+    uint32_t bytes = 0; uint4 pe = make_uint4(0, 0, 0, 0);
+    if (have) { pe = __ldg(r.plan + rec); bytes = (pe.z & 0xFFFFu) << 5; }
+    uint4 ha = make_uint4(0, 0, 0, 0), hb = ha;
+    unsigned long long psrc = 0;
+    if (have) {
+      const uint8_t* src = v.arena + ((static_cast<uint64_t>(pe.x) & v.gmask) << 5);
+      ha = sdb_ld_stream(src); hb = sdb_ld_stream(src + 16);
+      psrc = reinterpret_cast<unsigned long long>(sdb_payload_of(v, pe.x, sdb_entry_dm1(pe.z)));
+    }
+    const uint32_t stage_sa = wbase_sa + st * 32u * slot_bytes;
+    for (uint32_t f = 0; f < cpr; ++f) {
+      const uint32_t flat = (f << 5) + lane;
+      const uint32_t k = flat / cpr, c = flat - k * cpr;     // record of the step, chunk of its payload
+      const unsigned long long sk = __shfl_sync(0xFFFFFFFFu, psrc, k);
+      const uint32_t bk = __shfl_sync(0xFFFFFFFFu, bytes, k);
+      if ((c << 4) < bk)
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" :: "r"(stage_sa + k * slot_bytes + (c << 4)), "l"(sk + (c << 4)) : "memory");
+    }
+    const uint64_t po = static_cast<uint64_t>(pe.y) + ((have && r.plan_tops) ? r.plan_tops[rec / SDB_SCAN_TILE] : 0u);
+    if (st) { g1 = pe.z & 0xFFFFu; rc1 = rec; hv1 = have; po1 = po; ha1 = ha; hb1 = hb; }
+    else { g0 = pe.z & 0xFFFFu; rc0 = rec; hv0 = have; po0 = po; ha0 = ha; hb0 = hb; }
+  };
+  uint32_t r0 = gw * 32u;
+  if (r0 < total) issue(0, r0);
+  asm volatile("cp.async.commit_group;" ::: "memory");
+  uint32_t st = 0;
+  for (; r0 < total; r0 += nw * 32u, st ^= 1u) {
+    const uint32_t rn = r0 + nw * 32u;
+    sdb_tma_wait_read<0>();                                  // the other stage's bulk stores have finished reading it
+    __syncwarp();
+    if (rn < total) issue(st ^ 1u, rn);
+    asm volatile("cp.async.commit_group;" ::: "memory");     // one group per step, empty or not: the wait below counts groups
+    const bool hv = st ? hv1 : hv0;
+    if (hv) {
+      uint4* hdst = reinterpret_cast<uint4*>(r.hdr_out + (st ? rc1 : rc0));
+      sdb_st_stream(hdst, st ? ha1 : ha0); sdb_st_stream(hdst + 1, st ? hb1 : hb0);
+    }
+    asm volatile("cp.async.wait_group 1;" ::: "memory");     // everything but the newest group: this stage has landed
+    __syncwarp();
+    sdb_fence_proxy_async();                                 // copies written through the generic proxy -> visible to the bulk store
+    const uint32_t g = st ? g1 : g0;
+    if (__all_sync(0xFFFFFFFFu, hv && (g << 5) == slot_bytes)) {
+      if (lane == 0) sdb_tma_store(r.payload_out + ((st ? po1 : po0) << 5), wbase + static_cast<size_t>(st) * 32u * slot_bytes, 32u * slot_bytes);
+    } else if (hv && g) {
+      sdb_tma_store(r.payload_out + ((st ? po1 : po0) << 5), wbase + (static_cast<size_t>(st) * 32u + lane) * slot_bytes, g << 5);
+    }
+    sdb_tma_commit();
+  }
+  sdb_tma_wait_all<0>();
+}
+
 // ------------------------------------------------------------------------------------------
 // stream digests (definition in include/swarmdb_b200.h): one warp per request slot folds the records the last
 // receive delivered to that agent, in delivery order, into digest[agent].  Lanes hash the 64-bit words of a
@@ -1067,7 +1142,10 @@ static cudaError_t launch_gather(const sdb_dev_view* v, const sdb_recv_args* r, 
     uint64_t grid = static_cast<uint64_t>(sm_count) * per_sm * waves;              // a few waves: the tail evens out
     const uint64_t need = (bound + WARPS * 32 - 1) / (WARPS * 32);
     if (grid > need) grid = need;
-    k_recv_gather_tma<WARPS><<<static_cast<uint32_t>(grid), WARPS * 32, smem, stream>>>(*v, *r, packed_inv, slot);
+    static int use_cpa = -1;
+    if (use_cpa < 0) { const char* e = getenv("SDB_GATHER_LDGSTS"); use_cpa = e ? atoi(e) : 0; }   // measured slower: off
+    if (use_cpa) k_recv_gather_cpa<WARPS><<<static_cast<uint32_t>(grid), WARPS * 32, smem, stream>>>(*v, *r, packed_inv, slot);
+    else k_recv_gather_tma<WARPS><<<static_cast<uint32_t>(grid), WARPS * 32, smem, stream>>>(*v, *r, packed_inv, slot);
   } else {
     uint64_t gwarps = (bound + 3) / 4;
     uint64_t gblocks = (gwarps + 7) / 8;
@@ -1082,6 +1160,8 @@ static cudaError_t launch_gather(const sdb_dev_view* v, const sdb_recv_args* r, 
 }
 
 extern "C" cudaError_t sdb_recv_prepare_device() {
+  cudaError_t e = cudaFuncSetAttribute(k_recv_gather_cpa<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 4 * 2 * 32 * 544);
+  if (e != cudaSuccess) return e;
   return cudaFuncSetAttribute(k_recv_gather_tma<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 4 * 2 * 32 * 544);
 }
 
