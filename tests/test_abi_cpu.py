@@ -96,3 +96,26 @@ def test_header_is_plain_c_and_a_c_caller_fails_loudly_without_a_device(tmp_path
         pytest.skip("a device is present: covered by tests/test_gpu_api.py::test_plain_c_caller")
     p = subprocess.run([str(exe)], capture_output=True, text=True)
     assert p.returncode == 3 and "sizeof(sdb_config)=96" in p.stdout and "no CPU fallback" in p.stdout, p.stdout
+
+
+def test_every_environment_switch_of_the_library_is_documented():
+    """INTEGRATION.md section 5 lists the A/B switches the library reads with getenv; a new one must be written down."""
+    import re
+    from pathlib import Path
+    root = Path(__file__).resolve().parents[1]
+    names = set()
+    for f in (root / "swarmdb_b200" / "csrc").glob("*.cu"):
+        names |= set(re.findall(r'getenv\("([A-Z0-9_]+)"\)', f.read_text()))
+    doc = (root / "INTEGRATION.md").read_text()
+    missing = sorted(n for n in names if f"`{n}`" not in doc)
+    assert names and not missing, missing
+    from swarmdb_b200._native import shared_payload_enabled
+    import os
+    old = os.environ.get("SDB_SHARED_PAYLOAD")
+    try:
+        os.environ["SDB_SHARED_PAYLOAD"] = "0"; assert not shared_payload_enabled()
+        os.environ["SDB_SHARED_PAYLOAD"] = "1"; assert shared_payload_enabled()
+        os.environ.pop("SDB_SHARED_PAYLOAD"); assert shared_payload_enabled()          # the library's default
+    finally:
+        if old is not None:
+            os.environ["SDB_SHARED_PAYLOAD"] = old
