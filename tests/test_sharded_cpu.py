@@ -158,3 +158,49 @@ def test_two_rank_exchange_matches_single_shard_oracle():
         assert p.exitcode == 0
     status, seq_sharded, seq_single = q.get(timeout=5)
     assert status == "ok" and seq_sharded == seq_single
+
+
+def test_peer_exchange_step_protocol_on_a_recording_shard():
+    """Host side of the flag-synchronised transport (sharded.PeerExchange): which buffer / step number every call
+    names, the done-wait before a buffer is reused, prefetch bookkeeping and the misuse errors.  No GPU: the shard is a
+    recorder (world = 1, so nothing is exchanged)."""
+    import pytest
+    from swarmdb_b200.sharded import PeerExchange
+
+    class Rec:
+        def __init__(self): self.calls, self.n = [], 0
+        def set_stream(self, s): self.calls.append(("set_stream", s))
+        def wire_bytes(self, a, b): return 4096
+        def wire_alloc(self, nbytes): self.n += 1; return (1000 * self.n, b"h%d" % self.n)
+        def wire_wait_done(self, ptrs, nbytes, step): self.calls.append(("wait_done", tuple(ptrs), step))
+        def export_group_batch(self, *a): self.calls.append(("export", a[7]))            # a[7] = destination buffer
+        def wire_publish(self, ptr, nbytes, step): self.calls.append(("publish", ptr, step))
+        def import_prefetch(self, ptrs, nbytes, step): self.calls.append(("prefetch", tuple(ptrs), step))
+        def import_wire_ptrs_async(self, ptrs, nbytes, step): self.calls.append(("import", tuple(ptrs), step))
+        def wire_close(self, p, opened): self.calls.append(("close", p, opened))
+
+    class Stream:
+        cuda_stream = 77
+        def synchronize(self): pass
+
+    sh = Rec()
+    ex = PeerExchange(sh, 0, 1, 16, 1024, device=None, stream=Stream())
+    assert sh.calls[0] == ("set_stream", 77) and ex.mine[0][0] == 1000 and ex.mine[1][0] == 2000
+    batch = (None,) * 7
+    with pytest.raises(RuntimeError):
+        ex.prefetch()                                   # nothing exported yet
+    ex.export(*batch)                                   # step 1 uses buffer 1 (step & 1)
+    with pytest.raises(RuntimeError):
+        ex.export(*batch)                               # step 1 is already out
+    ex.prefetch(); ex.prefetch()                        # idempotent
+    ex.import_all()
+    ex.step(*batch)                                     # step 2: buffer 0
+    ex.export(*batch)                                   # step 3: buffer 1 again -> waits for done >= 1 first
+    ex.republish()                                      # no-op: already published
+    ex.import_all()
+    got = [c for c in sh.calls[1:]]
+    assert got == [("export", 2000), ("publish", 2000, 1), ("prefetch", (2000,), 1), ("import", (2000,), 1),
+                   ("export", 1000), ("publish", 1000, 2), ("import", (1000,), 2),
+                   ("wait_done", (2000,), 1), ("export", 2000), ("publish", 2000, 3), ("import", (2000,), 3)]
+    ex.close()
+    assert ("close", 1000, False) in sh.calls and ("close", 2000, False) in sh.calls
